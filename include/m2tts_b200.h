@@ -1,0 +1,211 @@
+/*
+ * m2tts_b200.h — C ABI of the B200-native (sm_100a) synthesis hot path of m2-tts.
+ *
+ * The reference (Ryannasr11/m2-tts) is pure Python/PyTorch and has NO native
+ * interface; the hot path is the eval-mode forward of src/models/tts_model.py
+ * and src/models/components.py.  Every entry point below replaces one module
+ * forward of the reference (cited as file:line relative to the reference repo)
+ * and is what a ctypes / cffi / pybind stub in that module would bind.
+ *
+ * Conventions
+ *   - plain C, no torch types: raw DEVICE pointers + sizes + a CUDA stream
+ *     handle (cudaStream_t passed as void*; NULL = legacy default stream);
+ *   - the caller owns every buffer (inputs, outputs, workspace); the library
+ *     allocates nothing and keeps no pointer after a call returns;
+ *   - all work is enqueued on the caller's stream, no implicit synchronisation
+ *     (the only host read on the path is the caller's own read-back of `t_max`
+ *     after m2tts_length_regulate_count when max_length is not given);
+ *   - return value: 0 = ok, negative = error (M2TTS_E_*); the message is
+ *     available per thread from m2tts_last_error_string(); nothing throws;
+ *   - floating point tensors are contiguous fp32 unless strides are passed;
+ *     `lengths`/`ids` are int64 as on the reference's Python API;
+ *   - re-entrant: no mutable global state except the opt-in stage timers and
+ *     the launch counter (both atomics / guarded).
+ */
+#ifndef M2TTS_B200_H_
+#define M2TTS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* m2tts_stream_t; /* cudaStream_t */
+
+enum {
+  M2TTS_OK = 0,
+  M2TTS_E_BADSHAPE = -1,    /* non-positive / inconsistent sizes            */
+  M2TTS_E_UNSUPPORTED = -2, /* dimension outside what the kernels cover     */
+  M2TTS_E_WORKSPACE = -3,   /* workspace too small / misaligned             */
+  M2TTS_E_CUDA = -4,        /* a CUDA runtime call or launch failed         */
+  M2TTS_E_NULLPTR = -5      /* a required pointer is NULL                   */
+};
+
+/* stage ids for the opt-in per-kernel timers (m2tts_stage_timing_*) */
+enum {
+  M2TTS_STAGE_EMBED = 0,
+  M2TTS_STAGE_PACK = 1,
+  M2TTS_STAGE_LN_QKV = 2,
+  M2TTS_STAGE_ATTENTION = 3,
+  M2TTS_STAGE_OUTPROJ = 4,
+  M2TTS_STAGE_FFN1 = 5,
+  M2TTS_STAGE_FFN2 = 6,
+  M2TTS_STAGE_LN_PROJ = 7,
+  M2TTS_STAGE_LAYERNORM = 8,
+  M2TTS_STAGE_DURPRED = 9,
+  M2TTS_STAGE_LR_COUNT = 10,
+  M2TTS_STAGE_LR_GATHER = 11,
+  M2TTS_STAGE_VOC_IN = 12,
+  M2TTS_STAGE_VOC_UP = 13,
+  M2TTS_STAGE_VOC_RES1 = 14,
+  M2TTS_STAGE_VOC_RES2 = 15,
+  M2TTS_STAGE_VOC_OUT = 16,
+  M2TTS_STAGE_PROBE = 17,
+  M2TTS_NUM_STAGES = 18
+};
+
+/* ---- weights: raw views of the reference's state_dict tensors ------------- */
+
+/* One TransformerEncoderLayer (components.py:106-140). Shapes as in the
+ * state_dict: qkv_w [3H,H] (row order [3, heads, head_dim], components.py:70),
+ * out_w [H,H], ffn1_w [F,H], ffn2_w [H,F]. */
+typedef struct {
+  const float* norm1_w; const float* norm1_b;
+  const float* qkv_w;
+  const float* out_w;   const float* out_b;
+  const float* norm2_w; const float* norm2_b;
+  const float* ffn1_w;  const float* ffn1_b;
+  const float* ffn2_w;  const float* ffn2_b;
+} m2tts_layer_weights;
+
+/* VariancePredictor inside DurationPredictor (components.py:203-223,
+ * tts_model.py:92-117): two ConvBlocks (Conv1d k=3 + eval BatchNorm1d + ReLU)
+ * and a 1x1 projection. conv*_w [H,H,3], bn vectors [H], proj_w [1,H,1]. */
+typedef struct {
+  const float* conv_w[2]; const float* conv_b[2];
+  const float* bn_w[2];   const float* bn_b[2];
+  const float* bn_mean[2]; const float* bn_var[2];
+  const float* proj_w;    const float* proj_b;
+  float bn_eps;
+} m2tts_durpred_weights;
+
+/* SimpleVocoder (tts_model.py:231-297). in_w [C,M,3]; up_w[j] [c_j, c_j/2, 2r_j]
+ * (ConvTranspose1d layout), r = {4,4,2,2}; res*_w[j] [c_j/2, c_j/2, 3];
+ * out_w [1, C/16, 3]. */
+typedef struct {
+  const float* in_w;  const float* in_b;
+  const float* up_w[4];   const float* up_b[4];
+  const float* res1_w[4]; const float* res1_b[4];
+  const float* res2_w[4]; const float* res2_b[4];
+  const float* out_w; const float* out_b;
+  int res_dilation[4]; /* LightweightResBlock conv1 dilation (default 1) */
+} m2tts_vocoder_weights;
+
+/* ---- library services ------------------------------------------------------ */
+
+int m2tts_version(void);
+const char* m2tts_last_error_string(void);
+/* number of kernel launches this library has issued since load */
+uint64_t m2tts_launch_count(void);
+/* opt-in CUDA-event timers around every kernel launch, keyed by stage id.
+ * enable(1) resets and starts collecting, enable(0) stops. read() synchronises
+ * the recorded events and returns summed milliseconds + launch counts. */
+int m2tts_stage_timing_enable(int on);
+int m2tts_stage_timing_read(float* ms_sum, int* launches, int n_stages);
+/* fp32 FFMA peak probe: `iters` dependent-chain FFMAs per thread on a full grid;
+ * writes nothing but a checksum; returns flop count through *flops. */
+int m2tts_ffma_probe(float* sink, int iters, double* flops, m2tts_stream_t stream);
+
+/* ---- text encoder pieces (tts_model.py:57-89) ------------------------------ */
+
+/* x[b,s,:] = emb[ids[b,s],:]*sqrt(H) + pe[s,:]  (tts_model.py:78-80,
+ * components.py:39); mask[b,s] = s < lengths[b] (components.py:226-241) when
+ * both `lengths` and `mask` are non-NULL. */
+int m2tts_embed_posenc(const int64_t* ids, const float* emb, const float* pe,
+                       const int64_t* lengths, float* x, uint8_t* mask,
+                       int B, int S, int H, int vocab, m2tts_stream_t stream);
+
+/* bytes of scratch one transformer layer needs for [B,L,H] with ffn dim F */
+size_t m2tts_transformer_workspace_bytes(int B, int L, int H, int F);
+
+/* One pre-LN transformer layer, eval mode (components.py:131-140):
+ *   x1 = x + out_proj(softmax(mask(q k^T / sqrt(hd))) v),  q,k,v = split(qkv(LN1(x)))
+ *   y  = x1 + W2 relu(W1 LN2(x1) + b1) + b2
+ * `lengths` (int64 [B]) masks KEYS only with the reference's finite -1e9 fill
+ * (components.py:77-81); NULL = no mask (decoder). x_in may equal x_out. */
+int m2tts_transformer_layer(const m2tts_layer_weights* w, const float* x_in,
+                            float* x_out, const int64_t* lengths, int B, int L,
+                            int H, int num_heads, int F, float ln_eps,
+                            void* workspace, size_t workspace_bytes,
+                            m2tts_stream_t stream);
+
+/* y = LayerNorm(x) over the last dim (tts_model.py:87) */
+int m2tts_layernorm(const float* x, const float* w, const float* b, float* y,
+                    int rows, int H, float eps, m2tts_stream_t stream);
+
+/* y[rows,N] = LayerNorm(x) @ W^T + bias (tts_model.py:223-226: decoder.norm then
+ * mel_projection, W [N,H]). workspace: m2tts_ln_proj_workspace_bytes(H,N). */
+size_t m2tts_ln_proj_workspace_bytes(int H, int N);
+int m2tts_layernorm_proj(const float* x, const float* ln_w, const float* ln_b,
+                         const float* W, const float* bias, float* y, int rows,
+                         int H, int N, float eps, void* workspace,
+                         size_t workspace_bytes, m2tts_stream_t stream);
+
+/* ---- duration predictor (tts_model.py:99-117) ------------------------------ */
+/* enc [B,S,H] -> dur [B,S] = softplus(proj(ConvBlock(ConvBlock(enc^T)))) */
+int m2tts_duration_predictor(const m2tts_durpred_weights* w, const float* enc,
+                             float* dur, int B, int S, int H,
+                             m2tts_stream_t stream);
+
+/* ---- length regulator (tts_model.py:126-178) ------------------------------- */
+/* Pass 1: n[b,s] = trunc(dur[b,s]) if > 0 else 0 (python int(), tts_model.py:150-151);
+ * cum[b,s] = inclusive prefix sum (int32, saturating); frames[b] = sum_s n[b,s];
+ * *t_max = max_b max(1, frames[b]) (tts_model.py:158-166); *status bit0 = a NaN
+ * duration was seen (python raises ValueError), bit1 = +-inf (OverflowError),
+ * bit2 = a frame count overflowed int32. All outputs are device memory. */
+int m2tts_length_regulate_count(const float* dur, int B, int S, int32_t* cum,
+                                int32_t* frames, int32_t* t_max, int32_t* status,
+                                m2tts_stream_t stream);
+/* Pass 2: out[b,j,:] = enc[b,s(j),:] with s(j) = first s: cum[b,s] > j, zero rows
+ * for j >= frames[b]; truncated at T (tts_model.py:168-178). index[b,j] = s(j)
+ * or -1 (optional, may be NULL). */
+int m2tts_length_regulate_gather(const float* enc, const int32_t* cum,
+                                 const int32_t* frames, float* out,
+                                 int32_t* index, int B, int S, int H, int T,
+                                 m2tts_stream_t stream);
+
+/* ---- vocoder (tts_model.py:279-297) ---------------------------------------- */
+size_t m2tts_vocoder_workspace_bytes(int B, int T, int M, int C);
+/* mel element (b,m,t) is read at mel[b*stride_b + m*stride_m + t*stride_t]
+ * (so both a contiguous [B,M,T] tensor and the transposed view of the decoder's
+ * [B,T,M] output, tts_model.py:390, are accepted without a copy).
+ * audio [B,1,64*T] contiguous. */
+int m2tts_vocoder_forward(const m2tts_vocoder_weights* w, const float* mel,
+                          int64_t stride_b, int64_t stride_m, int64_t stride_t,
+                          float* audio, int B, int T, int M, int C,
+                          void* workspace, size_t workspace_bytes,
+                          m2tts_stream_t stream);
+
+/* Per-stage entry points (unit tests / profiling). Channel-first fp32.
+ * conv1d k=3, "same" zero padding = dilation (components.py:181-190,
+ * tts_model.py:246,272). act: 0 none, 1 leaky_relu(0.1), 2 tanh.
+ * residual (may be NULL) is added AFTER the conv (components.py:200).
+ * x element (b,ci,t) at x[b*xs_b + ci*xs_c + t*xs_t]; y contiguous [B,CO,L].
+ * workspace: m2tts_conv_workspace_bytes(CI,CO,3). */
+size_t m2tts_conv_workspace_bytes(int CI, int CO, int taps);
+int m2tts_conv1d_k3(const float* x, int64_t xs_b, int64_t xs_c, int64_t xs_t,
+                    const float* w, const float* bias, const float* residual,
+                    float* y, int B, int CI, int CO, int L, int dilation, int act,
+                    void* workspace, size_t workspace_bytes, m2tts_stream_t stream);
+/* ConvTranspose1d(CI, CO, k=2r, stride=r, padding=r/2) + leaky_relu(0.1)
+ * (tts_model.py:255-263,291), r in {2,4}; x [B,CI,L] -> y [B,CO,r*L]. */
+int m2tts_conv_transpose1d_lrelu(const float* x, const float* w, const float* bias,
+                                 float* y, int B, int CI, int CO, int L, int r,
+                                 m2tts_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* M2TTS_B200_H_ */

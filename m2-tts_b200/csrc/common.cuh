@@ -1,0 +1,130 @@
+// common.cuh — shared host/device helpers for the m2tts_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include "../../include/m2tts_b200.h"
+
+#ifndef __CUDA_ARCH__
+#define M2_HOST_ONLY 1
+#endif
+
+namespace m2 {
+
+// ---- error reporting (thread local message, never throws) -------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define M2_CUDA_OK(call)                                                      \
+  do {                                                                        \
+    cudaError_t _e = (call);                                                  \
+    if (_e != cudaSuccess) return m2::cuda_fail(_e, #call, __FILE__, __LINE__); \
+  } while (0)
+
+#define M2_REQUIRE(cond, code, ...)   \
+  do {                                \
+    if (!(cond)) {                    \
+      m2::set_error(__VA_ARGS__);     \
+      return (code);                  \
+    }                                 \
+  } while (0)
+
+// ---- launch accounting + optional per-stage CUDA-event timers ---------------
+void note_launch(int stage, cudaStream_t s, bool begin);
+
+struct StageScope {
+  int stage; cudaStream_t s;
+  StageScope(int st, cudaStream_t stream) : stage(st), s(stream) { note_launch(stage, s, true); }
+  ~StageScope() { note_launch(stage, s, false); }
+};
+
+// Launch `kernel` and return M2TTS_E_CUDA from the enclosing function on a
+// launch-configuration error.
+#define M2_LAUNCH(stage, kernel, grid, block, smem, stream, ...)              \
+  do {                                                                        \
+    {                                                                         \
+      m2::StageScope _scope((stage), (stream));                               \
+      kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);             \
+    }                                                                         \
+    cudaError_t _le = cudaGetLastError();                                     \
+    if (_le != cudaSuccess) return m2::cuda_fail(_le, #kernel, __FILE__, __LINE__); \
+  } while (0)
+
+// opt a kernel into > 48 KB of dynamic shared memory (once per instantiation)
+template <typename K>
+inline cudaError_t allow_smem(K kernel, size_t bytes) {
+  if (bytes <= 48 * 1024) return cudaSuccess;
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// bump allocator over the caller's workspace
+struct Carver {
+  char* base; size_t size; size_t off;
+  Carver(void* p, size_t n) : base((char*)p), size(n), off(0) {}
+  template <typename T> T* take(size_t count) {
+    off = align_up(off, 256);
+    T* r = (T*)(base + off);
+    off += count * sizeof(T);
+    return r;
+  }
+  bool ok() const { return off <= size && (((uintptr_t)base) % 256 == 0); }
+};
+
+constexpr int kNumSMs = 148;  // B200
+
+// ---- device helpers ---------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+  unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+#endif
+
+}  // namespace m2
+
+// ---- internal launchers (one per .cu file), all return M2TTS_* codes --------
+namespace m2 {
+
+struct RowGemmArgs {
+  const float* x; int ldx;            // [R,K]
+  const float* ln_w; const float* ln_b; float eps;  // LN prologue if ln_w != null
+  const float* wt;                    // packed W^T [K,N]
+  const float* bias;                  // [N] or null
+  const float* residual; int ldr;     // [R,N] or null
+  int relu;
+  float* y; int ldy;                  // ROWMAJOR output
+  // QKV-split output (if qkv_mode): q,k as [B,nh,hd,Lp], v as [B,nh,L,hd]
+  int qkv_mode; float* q; float* k; float* v; int L; int Lp; int nh; int hd;
+  int R; int K; int N;
+  int stage;
+};
+int launch_rowgemm(const RowGemmArgs& a, cudaStream_t s);
+// transposes W [N,K] -> wt [K,N] for up to 4 matrices in one launch
+struct PackJob { const float* src; float* dst; int N; int K; };
+int launch_pack_transpose(const PackJob* jobs, int n_jobs, cudaStream_t s);
+
+int launch_attention(const float* q, const float* k, const float* v, float* ctx,
+                     const int64_t* lengths, int B, int L, int Lp, int nh, int hd,
+                     cudaStream_t s);
+}  // namespace m2

@@ -1,0 +1,124 @@
+// transformer.cu — C-ABI entry points for one pre-LN transformer layer and the decoder's
+// final LayerNorm + mel projection. Composition (all on the caller's stream):
+//   pack weights -> [LN1 + QKV] -> flash attention -> [out_proj + residual]
+//                -> [LN2 + FFN1 + ReLU] -> [FFN2 + residual]
+// Reference: components.py:131-140 (TransformerEncoderLayer._forward), :59-90, :103.
+#include "common.cuh"
+
+using namespace m2;
+
+namespace {
+struct LayerWs {
+  float *wqkv_t, *wo_t, *w1_t, *w2_t;  // packed W^T
+  float *q, *k, *v, *ctx, *x1, *hid;
+  int Lp;
+};
+
+bool carve_layer(void* ws, size_t bytes, int B, int L, int H, int F, LayerWs* o) {
+  Carver cv(ws, bytes);
+  const int Lp = (L + 3) & ~3;
+  o->Lp = Lp;
+  o->wqkv_t = cv.take<float>((size_t)H * 3 * H);
+  o->wo_t = cv.take<float>((size_t)H * H);
+  o->w1_t = cv.take<float>((size_t)H * F);
+  o->w2_t = cv.take<float>((size_t)F * H);
+  o->q = cv.take<float>((size_t)B * H * Lp);
+  o->k = cv.take<float>((size_t)B * H * Lp);
+  o->v = cv.take<float>((size_t)B * L * H);
+  o->ctx = cv.take<float>((size_t)B * L * H);
+  o->x1 = cv.take<float>((size_t)B * L * H);
+  o->hid = cv.take<float>((size_t)B * L * F);
+  return cv.ok();
+}
+}  // namespace
+
+extern "C" size_t m2tts_transformer_workspace_bytes(int B, int L, int H, int F) {
+  if (B <= 0 || L <= 0 || H <= 0 || F <= 0) return 0;
+  const size_t Lp = (size_t)((L + 3) & ~3);
+  size_t fl = (size_t)H * 3 * H + (size_t)H * H + 2 * (size_t)H * F + 2 * (size_t)B * H * Lp +
+              3 * (size_t)B * L * H + (size_t)B * L * F;
+  return fl * sizeof(float) + 16 * 256;
+}
+
+extern "C" int m2tts_transformer_layer(const m2tts_layer_weights* w, const float* x_in, float* x_out,
+                                       const int64_t* lengths, int B, int L, int H, int num_heads, int F,
+                                       float ln_eps, void* workspace, size_t workspace_bytes,
+                                       m2tts_stream_t stream) {
+  M2_REQUIRE(w && x_in && x_out && workspace, M2TTS_E_NULLPTR, "transformer_layer: null pointer");
+  M2_REQUIRE(w->norm1_w && w->norm1_b && w->qkv_w && w->out_w && w->out_b && w->norm2_w && w->norm2_b &&
+                 w->ffn1_w && w->ffn1_b && w->ffn2_w && w->ffn2_b,
+             M2TTS_E_NULLPTR, "transformer_layer: null weight pointer");
+  M2_REQUIRE(B > 0 && L > 0 && H > 0 && F > 0 && num_heads > 0, M2TTS_E_BADSHAPE,
+             "transformer_layer: B=%d L=%d H=%d heads=%d F=%d", B, L, H, num_heads, F);
+  M2_REQUIRE(H % num_heads == 0, M2TTS_E_BADSHAPE, "transformer_layer: hidden_dim %d not divisible by %d heads",
+             H, num_heads);
+  const int hd = H / num_heads;
+  M2_REQUIRE(hd % 8 == 0 && hd <= 64, M2TTS_E_UNSUPPORTED,
+             "transformer_layer: head_dim %d unsupported (multiples of 8 up to 64)", hd);
+  M2_REQUIRE(H <= 256 && F <= 256, M2TTS_E_UNSUPPORTED, "transformer_layer: H=%d F=%d exceed 256", H, F);
+  M2_REQUIRE((long long)B * L < (1ll << 31), M2TTS_E_UNSUPPORTED, "transformer_layer: B*L too large");
+  LayerWs ws;
+  M2_REQUIRE(carve_layer(workspace, workspace_bytes, B, L, H, F, &ws), M2TTS_E_WORKSPACE,
+             "transformer_layer: workspace too small (%zu B, need %zu) or not 256-B aligned", workspace_bytes,
+             m2tts_transformer_workspace_bytes(B, L, H, F));
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc;
+
+  PackJob jobs[4] = {{w->qkv_w, ws.wqkv_t, 3 * H, H}, {w->out_w, ws.wo_t, H, H},
+                     {w->ffn1_w, ws.w1_t, F, H}, {w->ffn2_w, ws.w2_t, H, F}};
+  if ((rc = launch_pack_transpose(jobs, 4, s))) return rc;
+
+  const int R = B * L;
+  {  // q,k,v = split(LN1(x) Wqkv^T)
+    RowGemmArgs a{};
+    a.x = x_in; a.ldx = H; a.ln_w = w->norm1_w; a.ln_b = w->norm1_b; a.eps = ln_eps;
+    a.wt = ws.wqkv_t; a.qkv_mode = 1; a.q = ws.q; a.k = ws.k; a.v = ws.v;
+    a.L = L; a.Lp = ws.Lp; a.nh = num_heads; a.hd = hd; a.R = R; a.K = H; a.N = 3 * H;
+    a.stage = M2TTS_STAGE_LN_QKV;
+    if ((rc = launch_rowgemm(a, s))) return rc;
+  }
+  if ((rc = launch_attention(ws.q, ws.k, ws.v, ws.ctx, lengths, B, L, ws.Lp, num_heads, hd, s))) return rc;
+  {  // x1 = x + ctx Wo^T + bo
+    RowGemmArgs a{};
+    a.x = ws.ctx; a.ldx = H; a.wt = ws.wo_t; a.bias = w->out_b; a.residual = x_in; a.ldr = H;
+    a.y = ws.x1; a.ldy = H; a.R = R; a.K = H; a.N = H; a.stage = M2TTS_STAGE_OUTPROJ;
+    if ((rc = launch_rowgemm(a, s))) return rc;
+  }
+  {  // hid = relu(LN2(x1) W1^T + b1)
+    RowGemmArgs a{};
+    a.x = ws.x1; a.ldx = H; a.ln_w = w->norm2_w; a.ln_b = w->norm2_b; a.eps = ln_eps;
+    a.wt = ws.w1_t; a.bias = w->ffn1_b; a.relu = 1; a.y = ws.hid; a.ldy = F;
+    a.R = R; a.K = H; a.N = F; a.stage = M2TTS_STAGE_FFN1;
+    if ((rc = launch_rowgemm(a, s))) return rc;
+  }
+  {  // y = x1 + hid W2^T + b2
+    RowGemmArgs a{};
+    a.x = ws.hid; a.ldx = F; a.wt = ws.w2_t; a.bias = w->ffn2_b; a.residual = ws.x1; a.ldr = H;
+    a.y = x_out; a.ldy = H; a.R = R; a.K = F; a.N = H; a.stage = M2TTS_STAGE_FFN2;
+    if ((rc = launch_rowgemm(a, s))) return rc;
+  }
+  return M2TTS_OK;
+}
+
+extern "C" size_t m2tts_ln_proj_workspace_bytes(int H, int N) {
+  if (H <= 0 || N <= 0) return 0;
+  return align_up((size_t)H * N * sizeof(float), 256) + 256;
+}
+
+extern "C" int m2tts_layernorm_proj(const float* x, const float* ln_w, const float* ln_b, const float* W,
+                                    const float* bias, float* y, int rows, int H, int N, float eps,
+                                    void* workspace, size_t workspace_bytes, m2tts_stream_t stream) {
+  M2_REQUIRE(x && ln_w && ln_b && W && y && workspace, M2TTS_E_NULLPTR, "layernorm_proj: null pointer");
+  M2_REQUIRE(rows > 0 && H > 0 && N > 0, M2TTS_E_BADSHAPE, "layernorm_proj: rows=%d H=%d N=%d", rows, H, N);
+  Carver cv(workspace, workspace_bytes);
+  float* wt = cv.take<float>((size_t)H * N);
+  M2_REQUIRE(cv.ok(), M2TTS_E_WORKSPACE, "layernorm_proj: workspace too small or not 256-B aligned");
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc;
+  PackJob job{W, wt, N, H};
+  if ((rc = launch_pack_transpose(&job, 1, s))) return rc;
+  RowGemmArgs a{};
+  a.x = x; a.ldx = H; a.ln_w = ln_w; a.ln_b = ln_b; a.eps = eps; a.wt = wt; a.bias = bias;
+  a.y = y; a.ldy = N; a.R = rows; a.K = H; a.N = N; a.stage = M2TTS_STAGE_LN_PROJ;
+  return launch_rowgemm(a, s);
+}

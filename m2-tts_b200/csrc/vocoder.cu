@@ -1,0 +1,522 @@
+// vocoder.cu — fp32 kernels for SimpleVocoder (tts_model.py:231-297), channel-first [B,C,L]:
+//   conv3      : Conv1d(k=3, dilation d, zero "same" padding) + bias (+LeakyReLU(0.1) | tanh)
+//                (+ residual added after the conv)             components.py:181-200, tts_model.py:246,272
+//   convT      : ConvTranspose1d(k=2r, stride r, padding r/2) + bias + LeakyReLU(0.1), r in {2,4}
+//                written as a polyphase filter: output sample r*q+p has exactly two taps,
+//                x[q]*w[p+r/2] and x[q-1]*w[p+3r/2] (p<r/2) or x[q+1]*w[p-r/2] (p>=r/2)
+//                                                             tts_model.py:255-263,291
+//   conv3_co1  : the 1-channel output conv + tanh              tts_model.py:272,295
+// CTA = 128 threads arranged TX (time) x TY (out-channel groups). A thread owns 8 time steps
+// (two runs of 4, so each quarter-warp's LDS.128 is contiguous) x 8 output values per step and
+// streams input channels through shared memory in chunks of CK: 192 FFMA per 12 smem loads.
+#include "common.cuh"
+#include <math.h>
+
+namespace m2 {
+
+constexpr int VC_THREADS = 128;
+
+struct ConvArgs {
+  const float* x; long long xs_b, xs_c, xs_t;  // element strides of the input
+  const float* wp;        // conv3: packed [CI][3][CO]; convT: native [CI][CO][2r]
+  const float* bias;
+  const float* residual;  // [B,CO,L] or null
+  float* y;               // [B,CO,L_out]
+  int CI, CO, L, dil, act;
+};
+
+__device__ __forceinline__ float vc_act(float v, int act) {
+  if (act == 1) return v > 0.f ? v : 0.1f * v;
+  if (act == 2) return tanhf(v);
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+template <int TY, bool DIL1>
+__global__ void __launch_bounds__(VC_THREADS) conv3_kernel(ConvArgs a) {
+  constexpr int TX = VC_THREADS / TY;
+  constexpr int TT = 8 * TX;       // time steps per CTA
+  constexpr int COB = 8 * TY;      // output channels per CTA
+  constexpr int CK = (TY >= 4) ? 16 : 8;
+  extern __shared__ __align__(16) float smem[];
+  const int dil = DIL1 ? 1 : a.dil;
+  const int XW = TT + 2 * dil;            // staged columns: t = t0 - dil + c
+  const int XST = (XW + 3) & ~3;          // row stride (floats), keeps 16-B alignment
+  float* xs = smem;                       // [CK][XST]
+  float* ws = smem + CK * XST;            // [CK][3][COB]
+
+  const int tid = threadIdx.x;
+  const int tx = tid % TX, ty = tid / TX;
+  const int t0 = blockIdx.x * TT, co0 = blockIdx.y * COB, b = blockIdx.z;
+  const int L = a.L, CI = a.CI, CO = a.CO;
+  const float* xb = a.x + (long long)b * a.xs_b;
+
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[i][c] = 0.f;
+
+  const bool wvec = ((CO & 3) == 0) && ((((uintptr_t)a.wp) & 15) == 0);
+
+  for (int ci0 = 0; ci0 < CI; ci0 += CK) {
+    __syncthreads();
+    // ---- stage inputs (zero outside [0,L) and beyond CI) ----
+    if (a.xs_t == 1) {
+      for (int idx = tid; idx < CK * XW; idx += VC_THREADS) {
+        const int ci = idx / XW, c = idx - ci * XW;
+        const int t = t0 - dil + c;
+        float v = 0.f;
+        if (ci0 + ci < CI && t >= 0 && t < L) v = xb[(long long)(ci0 + ci) * a.xs_c + t];
+        xs[ci * XST + c] = v;
+      }
+    } else {  // channel-contiguous input (the decoder's [B,T,M] mel): walk channels fastest
+      for (int idx = tid; idx < CK * XW; idx += VC_THREADS) {
+        const int c = idx / CK, ci = idx - c * CK;
+        const int t = t0 - dil + c;
+        float v = 0.f;
+        if (ci0 + ci < CI && t >= 0 && t < L) v = xb[(long long)(ci0 + ci) * a.xs_c + (long long)t * a.xs_t];
+        xs[ci * XST + c] = v;
+      }
+    }
+    // ---- stage weights: ws[ci][j][co] <- wp[(ci0+ci)*3 + j][co0 + co] ----
+    if (wvec) {
+      constexpr int C4 = COB / 4;
+      for (int idx = tid; idx < CK * 3 * C4; idx += VC_THREADS) {
+        const int row = idx / C4, c = (idx - row * C4) * 4;
+        const int ci = row / 3;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ci0 + ci < CI && co0 + c < CO)
+          v = *reinterpret_cast<const float4*>(a.wp + ((long long)ci0 * 3 + row) * CO + co0 + c);
+        *reinterpret_cast<float4*>(ws + row * COB + c) = v;
+      }
+    } else {
+      for (int idx = tid; idx < CK * 3 * COB; idx += VC_THREADS) {
+        const int row = idx / COB, c = idx - row * COB;
+        const int ci = row / 3;
+        ws[idx] = (ci0 + ci < CI && co0 + c < CO) ? a.wp[((long long)ci0 * 3 + row) * CO + co0 + c] : 0.f;
+      }
+    }
+    __syncthreads();
+
+#pragma unroll 2
+    for (int ci = 0; ci < CK; ++ci) {
+      const float* xr = xs + ci * XST;
+      const float* wr = ws + ci * 3 * COB + ty * 8;
+      if constexpr (DIL1) {
+        // columns 4tx..4tx+5 cover t-1..t+4 of the left run; +TT/2 for the right run
+        const float4 l4 = *reinterpret_cast<const float4*>(xr + 4 * tx);
+        const float2 l2 = *reinterpret_cast<const float2*>(xr + 4 * tx + 4);
+        const float4 r4 = *reinterpret_cast<const float4*>(xr + TT / 2 + 4 * tx);
+        const float2 r2 = *reinterpret_cast<const float2*>(xr + TT / 2 + 4 * tx + 4);
+        const float xl[6] = {l4.x, l4.y, l4.z, l4.w, l2.x, l2.y};
+        const float xq[6] = {r4.x, r4.y, r4.z, r4.w, r2.x, r2.y};
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const float4 w0 = *reinterpret_cast<const float4*>(wr + j * COB);
+          const float4 w1 = *reinterpret_cast<const float4*>(wr + j * COB + 4);
+          const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              acc[i][c] = fmaf(xl[i + j], wv[c], acc[i][c]);
+              acc[4 + i][c] = fmaf(xq[i + j], wv[c], acc[4 + i][c]);
+            }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const float4 w0 = *reinterpret_cast<const float4*>(wr + j * COB);
+          const float4 w1 = *reinterpret_cast<const float4*>(wr + j * COB + 4);
+          const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int tl = 4 * tx + (i & 3) + (i >> 2) * (TT / 2);
+            const float xv = xr[tl + j * dil];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[i][c] = fmaf(xv, wv[c], acc[i][c]);
+          }
+        }
+      }
+    }
+  }
+
+  // ---- epilogue: bias, activation, residual, store (float4 along time when aligned) ----
+  const bool svec = ((L & 3) == 0) && ((((uintptr_t)a.y) & 15) == 0) &&
+                    (a.residual == nullptr || (((uintptr_t)a.residual) & 15) == 0);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const int co = co0 + ty * 8 + c;
+    if (co >= CO) continue;
+    const float bv = a.bias ? __ldg(a.bias + co) : 0.f;
+    const long long rowoff = ((long long)b * CO + co) * L;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int t = t0 + 4 * tx + h * (TT / 2);
+      if (t >= L) continue;
+      float v[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = vc_act(acc[h * 4 + i][c] + bv, a.act);
+      if (svec && t + 3 < L) {
+        if (a.residual) {
+          const float4 r = *reinterpret_cast<const float4*>(a.residual + rowoff + t);
+          v[0] += r.x; v[1] += r.y; v[2] += r.z; v[3] += r.w;
+        }
+        *reinterpret_cast<float4*>(a.y + rowoff + t) = make_float4(v[0], v[1], v[2], v[3]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (t + i < L) a.y[rowoff + t + i] = v[i] + (a.residual ? a.residual[rowoff + t + i] : 0.f);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+template <int R, int TY>
+__global__ void __launch_bounds__(VC_THREADS) convT_kernel(ConvArgs a) {
+  constexpr int TX = VC_THREADS / TY;
+  constexpr int TQ = 8 * TX;        // input positions per CTA
+  constexpr int COT = 8 / R;        // output channels per thread
+  constexpr int COB = COT * TY;     // output channels per CTA
+  constexpr int K2 = 2 * R;         // kernel taps
+  constexpr int CK = (TY >= 4) ? 16 : 8;
+  constexpr int XST = TQ + 8;       // columns: q = q0 - 1 + c, c in [0, TQ+2)
+  extern __shared__ __align__(16) float smem[];
+  float* xs = smem;                 // [CK][XST]
+  float* ws = smem + CK * XST;      // [CK][COB][K2]
+
+  const int tid = threadIdx.x;
+  const int tx = tid % TX, ty = tid / TX;
+  const int q0 = blockIdx.x * TQ, co0 = blockIdx.y * COB, b = blockIdx.z;
+  const int L = a.L, CI = a.CI, CO = a.CO;
+  const float* xb = a.x + (long long)b * CI * L;
+
+  float acc[2][4][COT][R];
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int c = 0; c < COT; ++c)
+#pragma unroll
+        for (int p = 0; p < R; ++p) acc[h][i][c][p] = 0.f;
+
+  for (int ci0 = 0; ci0 < CI; ci0 += CK) {
+    __syncthreads();
+    for (int idx = tid; idx < CK * (TQ + 2); idx += VC_THREADS) {
+      const int ci = idx / (TQ + 2), c = idx - ci * (TQ + 2);
+      const int q = q0 - 1 + c;
+      float v = 0.f;
+      if (ci0 + ci < CI && q >= 0 && q < L) v = xb[(long long)(ci0 + ci) * L + q];
+      xs[ci * XST + c] = v;
+    }
+    for (int idx = tid; idx < CK * COB * K2; idx += VC_THREADS) {
+      const int ci = idx / (COB * K2), rem = idx - ci * (COB * K2);
+      const int col = rem / K2, kk = rem - col * K2;
+      float v = 0.f;
+      if (ci0 + ci < CI && co0 + col < CO) v = a.wp[((long long)(ci0 + ci) * CO + co0 + col) * K2 + kk];
+      ws[idx] = v;
+    }
+    __syncthreads();
+
+#pragma unroll 2
+    for (int ci = 0; ci < CK; ++ci) {
+      const float* xr = xs + ci * XST;
+      float xv[2][6];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float4 v4 = *reinterpret_cast<const float4*>(xr + h * (TQ / 2) + 4 * tx);
+        const float2 v2 = *reinterpret_cast<const float2*>(xr + h * (TQ / 2) + 4 * tx + 4);
+        xv[h][0] = v4.x; xv[h][1] = v4.y; xv[h][2] = v4.z; xv[h][3] = v4.w; xv[h][4] = v2.x; xv[h][5] = v2.y;
+      }
+      const float* wr = ws + (ci * COB + ty * COT) * K2;
+#pragma unroll
+      for (int c = 0; c < COT; ++c) {
+        float wv[K2];
+#pragma unroll
+        for (int kk = 0; kk < K2; kk += 4) {
+          const float4 t4 = *reinterpret_cast<const float4*>(wr + c * K2 + kk);
+          wv[kk] = t4.x; wv[kk + 1] = t4.y; wv[kk + 2] = t4.z; wv[kk + 3] = t4.w;
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int p = 0; p < R; ++p) {
+              // xv[h][i+1] = x[q], xv[h][i] = x[q-1], xv[h][i+2] = x[q+1]
+              float s = fmaf(xv[h][i + 1], wv[p + R / 2], acc[h][i][c][p]);
+              if (p < R / 2) s = fmaf(xv[h][i], wv[p + R / 2 + R], s);
+              else s = fmaf(xv[h][i + 2], wv[p - R / 2], s);
+              acc[h][i][c][p] = s;
+            }
+      }
+    }
+  }
+
+  const long long Lo = (long long)R * L;
+  const bool svec = ((Lo & 3) == 0) && ((((uintptr_t)a.y) & 15) == 0);
+#pragma unroll
+  for (int c = 0; c < COT; ++c) {
+    const int co = co0 + ty * COT + c;
+    if (co >= CO) continue;
+    const float bv = a.bias ? __ldg(a.bias + co) : 0.f;
+    float* yr = a.y + ((long long)b * CO + co) * Lo;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int q = q0 + h * (TQ / 2) + 4 * tx;
+      if (q >= L) continue;
+      float v[4 * R];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int p = 0; p < R; ++p) {
+          const float t = acc[h][i][c][p] + bv;
+          v[i * R + p] = t > 0.f ? t : 0.1f * t;
+        }
+      if (svec && q + 3 < L) {
+#pragma unroll
+        for (int e = 0; e < 4 * R; e += 4)
+          *reinterpret_cast<float4*>(yr + (long long)R * q + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4 * R; ++e)
+          if (q + e / R < L) yr[(long long)R * q + e] = v[e];
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// y[b,0,t] = tanh(bias + sum_{ci,j} w[0,ci,j] * x[b,ci,t+j-1]); 4 outputs per thread, x read
+// straight from global (contiguous [B,CI,L]); purely bandwidth-bound.
+__global__ void __launch_bounds__(256) conv3_co1_tanh_kernel(const float* __restrict__ x,
+                                                             const float* __restrict__ w,
+                                                             const float* __restrict__ bias,
+                                                             float* __restrict__ y, int CI, int L) {
+  extern __shared__ float wsm[];  // [CI][3]
+  for (int i = threadIdx.x; i < CI * 3; i += blockDim.x) wsm[i] = w[i];
+  __syncthreads();
+  const int b = blockIdx.y;
+  const long long t = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (t >= L) return;
+  const float* xb = x + (long long)b * CI * L;
+  const bool vec = ((L & 3) == 0) && ((((uintptr_t)x) & 15) == 0) && ((((uintptr_t)y) & 15) == 0) && (t + 3 < L);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int ci = 0; ci < CI; ++ci) {
+    const float* xr = xb + (long long)ci * L;
+    float xv[6];
+    if (vec) {
+      const float4 c4 = *reinterpret_cast<const float4*>(xr + t);
+      xv[1] = c4.x; xv[2] = c4.y; xv[3] = c4.z; xv[4] = c4.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) xv[1 + i] = (t + i < L) ? xr[t + i] : 0.f;
+    }
+    xv[0] = (t > 0) ? xr[t - 1] : 0.f;
+    xv[5] = (t + 4 < L) ? xr[t + 4] : 0.f;
+    const float w0 = wsm[ci * 3], w1 = wsm[ci * 3 + 1], w2 = wsm[ci * 3 + 2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[i] = fmaf(xv[i], w0, fmaf(xv[i + 1], w1, fmaf(xv[i + 2], w2, acc[i])));
+  }
+  const float bv = bias ? bias[0] : 0.f;
+  float* yb = y + (long long)b * L;
+  if (vec) {
+    *reinterpret_cast<float4*>(yb + t) = make_float4(tanhf(acc[0] + bv), tanhf(acc[1] + bv), tanhf(acc[2] + bv), tanhf(acc[3] + bv));
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (t + i < L) yb[t + i] = tanhf(acc[i] + bv);
+  }
+}
+
+// w[CO][CI][3] -> wp[CI][3][CO], several convolutions per launch (blockIdx.y = job)
+struct ConvPackJob { const float* src; float* dst; int CO, CI; };
+struct ConvPackJobs { ConvPackJob j[12]; };
+__global__ void conv_pack_kernel(ConvPackJobs jobs) {
+  const ConvPackJob jb = jobs.j[blockIdx.y];
+  const int total = jb.CO * jb.CI * 3;
+  for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < total; o += gridDim.x * blockDim.x) {
+    const int co = o % jb.CO, row = o / jb.CO;  // row = ci*3 + j
+    jb.dst[o] = jb.src[(long long)co * jb.CI * 3 + row];
+  }
+}
+
+static int launch_conv_pack(const ConvPackJob* jobs, int n, cudaStream_t s) {
+  ConvPackJobs pj;
+  int mx = 1;
+  for (int i = 0; i < n; ++i) { pj.j[i] = jobs[i]; const int t = jobs[i].CO * jobs[i].CI * 3; if (t > mx) mx = t; }
+  dim3 grid(ceil_div(mx, 256) < 128 ? ceil_div(mx, 256) : 128, n);
+  M2_LAUNCH(M2TTS_STAGE_PACK, conv_pack_kernel, grid, 256, 0, s, pj);
+  return M2TTS_OK;
+}
+
+// ---- launchers ------------------------------------------------------------------------------
+template <int TY, bool DIL1>
+static int launch_conv3_t(const ConvArgs& a, int B, int stage, cudaStream_t s) {
+  constexpr int TX = VC_THREADS / TY, TT = 8 * TX, COB = 8 * TY, CK = (TY >= 4) ? 16 : 8;
+  const int dil = DIL1 ? 1 : a.dil;
+  const int XST = (TT + 2 * dil + 3) & ~3;
+  const size_t smem = (size_t)(CK * XST + CK * 3 * COB) * sizeof(float);
+  M2_REQUIRE(smem <= 227 * 1024, M2TTS_E_UNSUPPORTED, "conv1d_k3: dilation %d too large", dil);
+  M2_CUDA_OK(allow_smem(conv3_kernel<TY, DIL1>, smem));
+  dim3 grid(ceil_div(a.L, TT), ceil_div(a.CO, COB), B);
+  M2_LAUNCH(stage, (conv3_kernel<TY, DIL1>), grid, VC_THREADS, smem, s, a);
+  return M2TTS_OK;
+}
+
+static int launch_conv3(const ConvArgs& a, int B, int stage, cudaStream_t s) {
+  M2_REQUIRE(B > 0 && B <= 65535 && a.CI > 0 && a.CO > 0 && a.L > 0 && a.dil >= 1, M2TTS_E_BADSHAPE,
+             "conv1d_k3: B=%d CI=%d CO=%d L=%d dil=%d", B, a.CI, a.CO, a.L, a.dil);
+  const int ty = a.CO > 32 ? 8 : (a.CO > 16 ? 4 : (a.CO > 8 ? 2 : 1));
+  if (a.dil == 1) {
+    switch (ty) {
+      case 8: return launch_conv3_t<8, true>(a, B, stage, s);
+      case 4: return launch_conv3_t<4, true>(a, B, stage, s);
+      case 2: return launch_conv3_t<2, true>(a, B, stage, s);
+      default: return launch_conv3_t<1, true>(a, B, stage, s);
+    }
+  }
+  switch (ty) {
+    case 8: return launch_conv3_t<8, false>(a, B, stage, s);
+    case 4: return launch_conv3_t<4, false>(a, B, stage, s);
+    case 2: return launch_conv3_t<2, false>(a, B, stage, s);
+    default: return launch_conv3_t<1, false>(a, B, stage, s);
+  }
+}
+
+template <int R, int TY>
+static int launch_convT_t(const ConvArgs& a, int B, cudaStream_t s) {
+  constexpr int TX = VC_THREADS / TY, TQ = 8 * TX, COB = (8 / R) * TY, CK = (TY >= 4) ? 16 : 8;
+  const size_t smem = (size_t)(CK * (TQ + 8) + CK * COB * 2 * R) * sizeof(float);
+  M2_CUDA_OK(allow_smem(convT_kernel<R, TY>, smem));
+  dim3 grid(ceil_div(a.L, TQ), ceil_div(a.CO, COB), B);
+  M2_LAUNCH(M2TTS_STAGE_VOC_UP, (convT_kernel<R, TY>), grid, VC_THREADS, smem, s, a);
+  return M2TTS_OK;
+}
+
+static int launch_convT(const ConvArgs& a, int B, int r, cudaStream_t s) {
+  M2_REQUIRE(B > 0 && B <= 65535 && a.CI > 0 && a.CO > 0 && a.L > 0, M2TTS_E_BADSHAPE,
+             "conv_transpose1d: B=%d CI=%d CO=%d L=%d", B, a.CI, a.CO, a.L);
+  M2_REQUIRE(r == 2 || r == 4, M2TTS_E_UNSUPPORTED, "conv_transpose1d: stride %d unsupported (2 or 4)", r);
+  if (r == 4) {  // 2 channels per thread
+    if (a.CO > 8) return launch_convT_t<4, 8>(a, B, s);
+    if (a.CO > 4) return launch_convT_t<4, 4>(a, B, s);
+    return launch_convT_t<4, 2>(a, B, s);
+  }
+  if (a.CO > 16) return launch_convT_t<2, 8>(a, B, s);  // 4 channels per thread
+  if (a.CO > 8) return launch_convT_t<2, 4>(a, B, s);
+  return launch_convT_t<2, 2>(a, B, s);
+}
+
+}  // namespace m2
+
+using namespace m2;
+
+extern "C" size_t m2tts_conv_workspace_bytes(int CI, int CO, int taps) {
+  if (CI <= 0 || CO <= 0 || taps <= 0) return 0;
+  return align_up((size_t)CI * CO * taps * sizeof(float), 256) + 256;
+}
+
+extern "C" int m2tts_conv1d_k3(const float* x, int64_t xs_b, int64_t xs_c, int64_t xs_t, const float* w,
+                               const float* bias, const float* residual, float* y, int B, int CI, int CO,
+                               int L, int dilation, int act, void* workspace, size_t workspace_bytes,
+                               m2tts_stream_t stream) {
+  M2_REQUIRE(x && w && y && workspace, M2TTS_E_NULLPTR, "conv1d_k3: null pointer");
+  M2_REQUIRE(act >= 0 && act <= 2, M2TTS_E_BADSHAPE, "conv1d_k3: act=%d", act);
+  M2_REQUIRE(B > 0 && CI > 0 && CO > 0 && L > 0 && dilation >= 1, M2TTS_E_BADSHAPE,
+             "conv1d_k3: B=%d CI=%d CO=%d L=%d dil=%d", B, CI, CO, L, dilation);
+  Carver cv(workspace, workspace_bytes);
+  float* wp = cv.take<float>((size_t)CI * CO * 3);
+  M2_REQUIRE(cv.ok(), M2TTS_E_WORKSPACE, "conv1d_k3: workspace too small or not 256-B aligned");
+  cudaStream_t s = (cudaStream_t)stream;
+  ConvPackJob job{w, wp, CO, CI};
+  int rc = launch_conv_pack(&job, 1, s);
+  if (rc) return rc;
+  ConvArgs a{x, xs_b, xs_c, xs_t, wp, bias, residual, y, CI, CO, L, dilation, act};
+  return launch_conv3(a, B, M2TTS_STAGE_VOC_RES1, s);
+}
+
+extern "C" int m2tts_conv_transpose1d_lrelu(const float* x, const float* w, const float* bias, float* y,
+                                            int B, int CI, int CO, int L, int r, m2tts_stream_t stream) {
+  M2_REQUIRE(x && w && y, M2TTS_E_NULLPTR, "conv_transpose1d: null pointer");
+  ConvArgs a{x, (long long)CI * L, L, 1, w, bias, nullptr, y, CI, CO, L, 1, 1};
+  return launch_convT(a, B, r, (cudaStream_t)stream);
+}
+
+extern "C" size_t m2tts_vocoder_workspace_bytes(int B, int T, int M, int C) {
+  if (B <= 0 || T <= 0 || M <= 0 || C < 16) return 0;
+  const size_t act = align_up((size_t)B * C * T * 4 * sizeof(float), 256);  // widest activation: 4*C*T per utterance
+  size_t wts = (size_t)C * M * 3;
+  for (int j = 0, c = C / 2; j < 4; ++j, c /= 2) wts += 2 * (size_t)c * c * 3;
+  return 3 * act + align_up(wts * sizeof(float), 256) + 16 * 256;
+}
+
+extern "C" int m2tts_vocoder_forward(const m2tts_vocoder_weights* w, const float* mel, int64_t stride_b,
+                                     int64_t stride_m, int64_t stride_t, float* audio, int B, int T, int M,
+                                     int C, void* workspace, size_t workspace_bytes, m2tts_stream_t stream) {
+  M2_REQUIRE(w && mel && audio && workspace, M2TTS_E_NULLPTR, "vocoder_forward: null pointer");
+  M2_REQUIRE(B > 0 && T > 0 && M > 0, M2TTS_E_BADSHAPE, "vocoder_forward: B=%d T=%d M=%d", B, T, M);
+  M2_REQUIRE(C >= 16 && C % 16 == 0, M2TTS_E_UNSUPPORTED,
+             "vocoder_forward: hidden_channels=%d must be a positive multiple of 16", C);
+  M2_REQUIRE(w->in_w && w->in_b && w->out_w && w->out_b, M2TTS_E_NULLPTR, "vocoder_forward: null weights");
+  for (int j = 0; j < 4; ++j)
+    M2_REQUIRE(w->up_w[j] && w->up_b[j] && w->res1_w[j] && w->res1_b[j] && w->res2_w[j] && w->res2_b[j],
+               M2TTS_E_NULLPTR, "vocoder_forward: null weights in stage %d", j);
+  cudaStream_t s = (cudaStream_t)stream;
+  Carver cv(workspace, workspace_bytes);
+  const size_t act = (size_t)B * C * T * 4;
+  float* bufA = cv.take<float>(act);
+  float* bufB = cv.take<float>(act);
+  float* bufC = cv.take<float>(act);
+  // packed weights
+  ConvPackJob jobs[9];
+  float* in_wp = cv.take<float>((size_t)C * M * 3);
+  jobs[0] = ConvPackJob{w->in_w, in_wp, C, M};
+  float* r1p[4]; float* r2p[4];
+  for (int j = 0, c = C / 2; j < 4; ++j, c /= 2) {
+    r1p[j] = cv.take<float>((size_t)c * c * 3);
+    r2p[j] = cv.take<float>((size_t)c * c * 3);
+    jobs[1 + 2 * j] = ConvPackJob{w->res1_w[j], r1p[j], c, c};
+    jobs[2 + 2 * j] = ConvPackJob{w->res2_w[j], r2p[j], c, c};
+  }
+  M2_REQUIRE(cv.ok(), M2TTS_E_WORKSPACE, "vocoder_forward: workspace too small (%zu B) or not 256-B aligned",
+             workspace_bytes);
+  int rc = launch_conv_pack(jobs, 9, s);
+  if (rc) return rc;
+
+  // input conv: mel (strided) -> bufA [B,C,T]
+  {
+    ConvArgs a{mel, stride_b, stride_m, stride_t, in_wp, w->in_b, nullptr, bufA, M, C, T, 1, 0};
+    if ((rc = launch_conv3(a, B, M2TTS_STAGE_VOC_IN, s))) return rc;
+  }
+  static const int rates[4] = {4, 4, 2, 2};
+  int L = T, c_in = C;
+  for (int j = 0; j < 4; ++j) {
+    const int r = rates[j], c = c_in / 2, Lo = L * r;
+    {  // bufB = lrelu(convT(bufA))
+      ConvArgs a{bufA, (long long)c_in * L, L, 1, w->up_w[j], w->up_b[j], nullptr, bufB, c_in, c, L, 1, 1};
+      if ((rc = launch_convT(a, B, r, s))) return rc;
+    }
+    const int dil = w->res_dilation[j] > 0 ? w->res_dilation[j] : 1;
+    {  // bufC = lrelu(conv1(bufB))
+      ConvArgs a{bufB, (long long)c * Lo, Lo, 1, r1p[j], w->res1_b[j], nullptr, bufC, c, c, Lo, dil, 1};
+      if ((rc = launch_conv3(a, B, M2TTS_STAGE_VOC_RES1, s))) return rc;
+    }
+    {  // bufA = conv2(bufC) + bufB
+      ConvArgs a{bufC, (long long)c * Lo, Lo, 1, r2p[j], w->res2_b[j], bufB, bufA, c, c, Lo, 1, 0};
+      if ((rc = launch_conv3(a, B, M2TTS_STAGE_VOC_RES2, s))) return rc;
+    }
+    L = Lo; c_in = c;
+  }
+  // output conv + tanh: bufA [B,C/16,64T] -> audio [B,1,64T]
+  {
+    const int threads = 256;
+    dim3 grid(ceil_div(ceil_div(L, 4), threads), B);
+    M2_LAUNCH(M2TTS_STAGE_VOC_OUT, conv3_co1_tanh_kernel, grid, threads, (size_t)c_in * 3 * sizeof(float), s, bufA,
+              w->out_w, w->out_b, audio, c_in, L);
+  }
+  return M2TTS_OK;
+}
