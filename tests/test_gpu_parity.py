@@ -1,0 +1,274 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI
+(ctypes -> libm2tts_b200.so), against the CPU oracle on the same seeded inputs and against the
+committed golden fixtures.
+
+Tolerances (BASELINE.json north_star): length-regulator indices / frame counts / regulated rows
+bit-exact; fp32 mels and waveforms within max-abs 1e-4.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+from helpers import oracle
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-4
+DEV = "cuda:0"
+
+
+def cuda_model(stage, perturb=None, **override):
+    return H.product_model(stage, perturb=perturb, **override).to(DEV).eval()
+
+
+def cpu_sd(model):
+    return {k: v.detach().cpu() for k, v in model.state_dict().items()}
+
+
+def load(name):
+    return {k: v for k, v in np.load(H.GOLDEN / name).items()}
+
+
+def test_native_library_is_what_runs():
+    from models import _native as nat
+    assert nat.library_path().exists()
+    before = nat.launch_count()
+    m = cuda_model("tiny")
+    ids, lengths, dur = H.small_inputs(2, 10, 256, seed=11)
+    m(ids.to(DEV), lengths.to(DEV), dur.to(DEV), 50)
+    torch.cuda.synchronize()
+    assert nat.launch_count() - before >= 20  # every stage is one of our kernels
+
+
+# --------------------------------------------------------------------------- full forward
+@pytest.mark.parametrize("name,stage,pert,ml", [("tiny_fwd.npz", "tiny", None, 50),
+                                               ("tiny_biased_fwd.npz", "tiny", 7, 50),
+                                               ("stage2_biased_fwd.npz", "stage2", 7, 60)])
+def test_forward_matches_golden_and_oracle(name, stage, pert, ml):
+    g = load(name)
+    m = cuda_model(stage, pert)
+    ids, lengths, dur = (torch.from_numpy(g[k]) for k in ("ids", "lengths", "dur"))
+    out = m(ids.to(DEV), lengths.to(DEV), dur.to(DEV), ml)
+    ref = oracle.forward(cpu_sd(m), ids, lengths, dur, ml)
+    assert torch.equal(out["padding_mask"].cpu(), torch.from_numpy(g["padding_mask"]))
+    for k in ("encoder_output", "duration_pred", "mel_output", "audio_output"):
+        assert out[k].shape == g[k].shape, k
+        assert H.max_abs(out[k].cpu(), g[k]) <= FP32_TOL, f"{k} vs golden"
+        assert H.max_abs(out[k].cpu(), ref[k]) <= FP32_TOL, f"{k} vs oracle"
+    # regulated rows are copies of the (GPU) encoder rows: bit-exact gather of the GPU encoder output
+    want = oracle.length_regulator(out["encoder_output"].cpu(), dur, ml)
+    assert torch.equal(out["regulated_output"].cpu(), want)
+
+
+def test_c1_hello_world_inference():
+    g = load("c1_hello_world.npz")
+    m = cuda_model("stage1")
+    ids, lengths = torch.from_numpy(g["ids"]).to(DEV), torch.from_numpy(g["lengths"]).to(DEV)
+    mel, audio = m.inference(ids, lengths, 1.0)
+    assert mel.shape == (1, 1, 64) and audio.shape == (1, 1, 64)  # all durations truncate to 0
+    assert H.max_abs(mel.cpu(), g["mel_scale1"]) <= FP32_TOL
+    assert H.max_abs(audio.cpu(), g["audio_scale1"]) <= FP32_TOL
+    fwd = m(ids, lengths)
+    assert H.max_abs(fwd["duration_pred"].cpu(), g["duration_pred"]) <= FP32_TOL
+    # non-degenerate case: feed the golden durations x4 to the regulator on both sides
+    dur4 = torch.from_numpy(g["duration_pred"]).to(DEV) * 4.0
+    reg = m.length_regulator(fwd["encoder_output"], dur4)
+    mel4 = m.decoder(reg)
+    audio4 = m.vocoder(mel4.transpose(1, 2))
+    assert mel4.shape == g["mel_scale4"].shape and audio4.shape == g["audio_scale4"].shape
+    assert H.max_abs(mel4.cpu(), g["mel_scale4"]) <= FP32_TOL
+    assert H.max_abs(audio4.cpu(), g["audio_scale4"]) <= FP32_TOL
+
+
+def test_c2_stage1_batch16():
+    g = load("c2_stage1.npz")
+    m = cuda_model("stage1")
+    ids, lengths, dur = H.c2_inputs()
+    out = m(ids.to(DEV), lengths.to(DEV), target_durations=dur.to(DEV))
+    T = int(g["T"])
+    assert out["mel_output"].shape == (16, T, 64) and out["audio_output"].shape == (16, 1, 64 * T)
+    assert np.array_equal(m.length_regulator.last_frames.cpu().numpy(), g["frames"])
+    index, frames, _ = oracle.length_regulator_indices(dur.numpy())
+    assert np.array_equal(m.length_regulator.last_index.cpu().numpy(), index)
+    keep = g["keep"].tolist()
+    assert H.max_abs(out["encoder_output"].cpu(), g["encoder_output"]) <= FP32_TOL
+    assert H.max_abs(out["mel_output"][keep].cpu(), g["mel_keep"]) <= FP32_TOL
+    assert H.max_abs(out["audio_output"][keep].cpu(), g["audio_keep"]) <= FP32_TOL
+    assert np.allclose(out["audio_output"].double().abs().sum((1, 2)).cpu().numpy(), g["audio_abs"], rtol=1e-5)
+    ref = oracle.forward(cpu_sd(m), ids, lengths, dur)
+    assert H.max_abs(out["mel_output"].cpu(), ref["mel_output"]) <= FP32_TOL
+    assert H.max_abs(out["audio_output"].cpu(), ref["audio_output"]) <= FP32_TOL
+
+
+# --------------------------------------------------------------------------- length regulator
+def test_length_regulator_edges_bit_exact():
+    from models.tts_model import LengthRegulator
+    g = load("length_regulator_edges.npz")
+    d = torch.from_numpy(g["dur"])
+    B, S = d.shape
+    enc = torch.randn(B, S, 12, generator=torch.Generator().manual_seed(3))
+    lr = LengthRegulator().eval()
+    for name, ml in (("none", None), ("trunc20", 20), ("pad90", 90)):
+        out = lr(enc.to(DEV), d.to(DEV), ml)
+        assert np.array_equal(lr.last_index.cpu().numpy(), g[f"index_{name}"]), name
+        assert torch.equal(out.cpu(), oracle.length_regulator(enc, d, ml)), name
+    index, frames, _ = oracle.length_regulator_indices(d.numpy())
+    assert np.array_equal(lr.last_frames.cpu().numpy(), frames)
+
+
+def test_length_regulator_large_and_ragged():
+    from models.tts_model import LengthRegulator
+    g = torch.Generator().manual_seed(21)
+    B, S, Hd = 64, 256, 96
+    d = torch.randint(0, 28, (B, S), generator=g).float() + torch.rand((B, S), generator=g) * 0.999
+    d[5] = 0.3                                  # empty utterance inside a big batch
+    enc = torch.randn(B, S, Hd, generator=g)
+    lr = LengthRegulator().eval()
+    out = lr(enc.to(DEV), d.to(DEV))
+    index, frames, T = oracle.length_regulator_indices(d.numpy())
+    assert out.shape == (B, T, Hd)
+    assert np.array_equal(lr.last_frames.cpu().numpy(), frames)
+    assert np.array_equal(lr.last_index.cpu().numpy(), index)
+    assert torch.equal(out.cpu(), oracle.length_regulator(enc, d))
+    # H not a multiple of 4 (scalar copy path), S == 1
+    enc2 = torch.randn(3, 1, 7, generator=g)
+    d2 = torch.tensor([[3.9], [0.0], [1.0]])
+    assert torch.equal(lr(enc2.to(DEV), d2.to(DEV)).cpu(), oracle.length_regulator(enc2, d2))
+
+
+def test_length_regulator_nan_inf_raise_like_python_int():
+    from models.tts_model import LengthRegulator
+    lr = LengthRegulator().eval()
+    enc = torch.zeros(1, 4, 8, device=DEV)
+    d = torch.ones(1, 4, device=DEV)
+    d[0, 2] = float("nan")
+    with pytest.raises(ValueError):
+        lr(enc, d)
+    d[0, 2] = float("-inf")
+    with pytest.raises(OverflowError):
+        lr(enc, d)
+
+
+# --------------------------------------------------------------------------- encoder / attention
+@pytest.mark.parametrize("stage", ["stage1", "stage2"])
+def test_text_encoder_masks_and_edge_lengths(stage):
+    m = cuda_model(stage, perturb=5)
+    sd = cpu_sd(m)
+    g = torch.Generator().manual_seed(9)
+    ids = torch.randint(0, 256, (5, 150), generator=g)        # > one 128-query tile, ragged key tiles
+    for lengths in (torch.tensor([150, 1, 0, 64, 129]), None):
+        got, mask = m.text_encoder(ids.to(DEV), None if lengths is None else lengths.to(DEV))
+        want, wmask = oracle.text_encoder(sd, ids, lengths, 2)
+        assert H.max_abs(got.cpu(), want) <= FP32_TOL
+        if lengths is not None:
+            assert torch.equal(mask.cpu(), wmask)
+
+
+@pytest.mark.parametrize("heads,hidden", [(2, 32), (4, 64), (2, 128), (8, 64)])
+def test_decoder_head_dims(heads, hidden):
+    m = cuda_model("stage1", perturb=2, hidden_dim=hidden, num_heads=heads, mel_channels=20,
+                   text_encoder_layers=1, decoder_layers=2)
+    x = torch.randn(2, 203, hidden, generator=torch.Generator().manual_seed(1))
+    got = m.decoder(x.to(DEV))
+    want = oracle.mel_decoder(cpu_sd(m), x, heads)
+    assert H.max_abs(got.cpu(), want) <= FP32_TOL
+
+
+def test_decoder_long_sequence_stage2():
+    m = cuda_model("stage2", perturb=4)
+    x = torch.randn(1, 1500, 96, generator=torch.Generator().manual_seed(2))
+    got = m.decoder(x.to(DEV))
+    want = oracle.mel_decoder(cpu_sd(m), x, 2)
+    assert H.max_abs(got.cpu(), want) <= FP32_TOL
+
+
+def test_duration_predictor_nonzero_bias_padding():
+    m = cuda_model("stage2", perturb=8)
+    enc = torch.randn(3, 77, 96, generator=torch.Generator().manual_seed(4))
+    got = m.duration_predictor(enc.to(DEV))
+    want = oracle.duration_predictor(cpu_sd(m), enc)
+    assert H.max_abs(got.cpu(), want) <= FP32_TOL
+
+
+# --------------------------------------------------------------------------- vocoder
+@pytest.mark.parametrize("stage,B,T", [("stage1", 3, 37), ("stage2", 2, 130), ("tiny", 1, 1), ("stage2", 1, 515)])
+def test_vocoder_matches_oracle(stage, B, T):
+    m = cuda_model(stage, perturb=6)
+    M = H.STAGE_KWARGS[stage]["mel_channels"]
+    mel = torch.randn(B, M, T, generator=torch.Generator().manual_seed(T))
+    want = oracle.vocoder(cpu_sd(m), mel)
+    got = m.vocoder(mel.to(DEV))                                   # contiguous [B,M,T]
+    assert got.shape == (B, 1, 64 * T)
+    assert H.max_abs(got.cpu(), want) <= FP32_TOL
+    got_t = m.vocoder(mel.transpose(1, 2).contiguous().to(DEV).transpose(1, 2))  # strided view of [B,T,M]
+    assert H.max_abs(got_t.cpu(), want) <= FP32_TOL
+
+
+def test_vocoder_linearity_of_input_conv_stage():
+    """Size-independent property at a larger size: the vocoder is deterministic and
+    batch-independent — utterance b of a batch equals the same utterance run alone."""
+    m = cuda_model("stage2")
+    mel = torch.randn(4, 80, 700, generator=torch.Generator().manual_seed(5)).to(DEV)
+    full = m.vocoder(mel)
+    for b in (0, 3):
+        assert torch.equal(full[b:b + 1], m.vocoder(mel[b:b + 1]))
+
+
+def test_conv_entry_points_dilation_and_activation():
+    """Per-stage C-ABI entry points, incl. the generic-dilation path no config exercises."""
+    from models import _native as nat
+    lib = nat.lib()
+    g = torch.Generator().manual_seed(12)
+    for (CI, CO, L, dil, act) in [(24, 40, 301, 1, 1), (16, 16, 257, 3, 0), (8, 4, 64, 2, 2), (5, 70, 33, 1, 0)]:
+        x = torch.randn(2, CI, L, generator=g)
+        w = torch.randn(CO, CI, 3, generator=g) * 0.2
+        b = torch.randn(CO, generator=g)
+        r = torch.randn(2, CO, L, generator=g)
+        want = torch.nn.functional.conv1d(x, w, b, padding=dil, dilation=dil)
+        want = {0: want, 1: torch.nn.functional.leaky_relu(want, 0.1), 2: torch.tanh(want)}[act] + r
+        xd, wd, bd, rd = (t.to(DEV) for t in (x, w, b, r))
+        y = torch.empty(2, CO, L, device=DEV)
+        ws = torch.empty(lib.m2tts_conv_workspace_bytes(CI, CO, 3), dtype=torch.uint8, device=DEV)
+        rc = lib.m2tts_conv1d_k3(xd.data_ptr(), CI * L, L, 1, wd.data_ptr(), bd.data_ptr(), rd.data_ptr(),
+                                 y.data_ptr(), 2, CI, CO, L, dil, act, ws.data_ptr(), ws.numel(), None)
+        nat.check(rc, "conv1d_k3")
+        assert H.max_abs(y.cpu(), want) <= FP32_TOL, (CI, CO, L, dil, act)
+    for (CI, CO, L, r_) in [(32, 16, 45, 4), (12, 6, 130, 2), (256, 128, 9, 4), (6, 3, 7, 2)]:
+        x = torch.randn(2, CI, L, generator=g)
+        w = torch.randn(CI, CO, 2 * r_, generator=g) * 0.2
+        b = torch.randn(CO, generator=g)
+        want = torch.nn.functional.leaky_relu(
+            torch.nn.functional.conv_transpose1d(x, w, b, stride=r_, padding=r_ // 2), 0.1)
+        y = torch.empty(2, CO, r_ * L, device=DEV)
+        rc = lib.m2tts_conv_transpose1d_lrelu(x.to(DEV).data_ptr(), w.to(DEV).data_ptr(), b.to(DEV).data_ptr(),
+                                              y.data_ptr(), 2, CI, CO, L, r_, None)
+        nat.check(rc, "conv_transpose1d")
+        assert H.max_abs(y.cpu(), want) <= FP32_TOL, (CI, CO, L, r_)
+
+
+# --------------------------------------------------------------------------- errors / boundary behaviour
+def test_error_paths():
+    from models import _native as nat
+    m = H.product_model("tiny")  # on CPU
+    with pytest.raises(nat.NativeLibraryError):
+        m(torch.zeros(1, 4, dtype=torch.long))   # no CPU fallback in eval mode
+    lib = nat.lib()
+    assert lib.m2tts_vocoder_forward(None, None, 0, 0, 0, None, 1, 1, 1, 16, None, 0, None) == -5
+    assert b"null" in lib.m2tts_last_error_string()
+    with pytest.raises(ValueError):   # head_dim 12 is not supported by the attention kernel
+        bad = H.product_model("tiny", hidden_dim=24, num_heads=2).to(DEV).eval()
+        bad.decoder(torch.zeros(1, 8, 24, device=DEV))
+
+
+def test_batch_sharding_is_exact():
+    """with a shared max_target_length a shard's results equal the full batch's."""
+    m = cuda_model("stage1", perturb=1)
+    ids, lengths, dur = H.c2_inputs()
+    ids, lengths, dur = ids.to(DEV), lengths.to(DEV), dur.to(DEV)
+    full = m(ids, lengths, dur, 330)
+    half = m(ids[8:], lengths[8:], dur[8:], 330)
+    for k in ("regulated_output", "mel_output", "audio_output"):
+        assert torch.equal(full[k][8:], half[k]), k
