@@ -298,7 +298,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                 "roofline": roof,
                 "stage_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in sorted(stage_ms.items(), key=lambda kv: -kv[1][0])},
                 "x_realtime_per_gpu": value / world}
-        if world == 1:
+        if world == 1 and not args.skip_cpu_baseline:
             n_s = 8
             vals, threads = time_cpu_port(n_s, reps=2, warm=0)
             vals = [max(vals)]
@@ -326,6 +326,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--skip-cpu-baseline", action="store_true", help="profiling runs: omit the CPU leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

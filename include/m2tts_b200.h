@@ -114,6 +114,10 @@ uint64_t m2tts_launch_count(void);
  * the recorded events and returns summed milliseconds + launch counts. */
 int m2tts_stage_timing_enable(int on);
 int m2tts_stage_timing_read(float* ms_sum, int* launches, int n_stages);
+/* Attention kernel selection for m2tts_transformer_layer: 0 (default) = tcgen05/TMEM tensor-core
+ * kernel with 3xTF32 splitting when head_dim is one of {16,32,48,64}, else the fp32 FFMA kernel;
+ * 1 = always the fp32 FFMA kernel. Process-wide; also settable with M2TTS_ATTENTION=ffma. */
+int m2tts_set_attention_mode(int mode);
 /* fp32 FFMA peak probe: `iters` dependent-chain FFMAs per thread on a full grid;
  * writes nothing but a checksum; returns flop count through *flops. */
 int m2tts_ffma_probe(float* sink, int iters, double* flops, m2tts_stream_t stream);

@@ -1,0 +1,376 @@
+// attention_tc.cu — flash attention on the 5th-generation tensor cores (tcgen05 + TMEM + TMA),
+// fp32-faithful through 3xTF32 splitting: every operand x is carried as x = hi + lo with both
+// halves exactly representable in TF32 (10-bit mantissa), and each product is evaluated as
+//   a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi        (dropped term a_lo*b_lo ~ 2^-22 |a b|)
+// with fp32 accumulation in TMEM. This keeps the reference's fp32 results (components.py:75-87)
+// within ~1e-6 while the O(L^2) work runs on the tensor pipe instead of FFMA.
+//
+// Operands (written by the QKV row-GEMM epilogue, qkv_mode 2): one fp32 array
+//   qkv6[6][B][nh][hd][Lp]  = {Q_hi, Q_lo, K_hi, K_lo, V_hi, V_lo}, positions contiguous,
+// Q already multiplied by scale*log2(e). One TMA tensor map over it (rows = 6*B*nh*hd,
+// cols = L, row pitch Lp) with a {32 positions x hd rows} box and 128-byte swizzle, so a box is
+// hd rows of 128 B: for Q and K this is the canonical MN-major SW128 UMMA layout (K dim = d),
+// for V^T it is the canonical K-major SW128 layout (N dim = d, K dim = keys).
+//
+// CTA = 128 threads = one (utterance, head, 128-query tile); thread i owns query row i (TMEM
+// lane i). Per 64-key tile:  S = Q K^T (18 UMMAs, M128 N64 K8) -> tcgen05.ld -> online softmax
+// in registers -> P_hi/P_lo back to TMEM -> O_tile = P V (24 UMMAs, M128 N=hd K8, A from TMEM)
+// -> tcgen05.ld -> o = o*alpha + O_tile in registers. K and V tiles are single-buffered but
+// refilled by TMA as soon as the UMMAs that read them have committed; two CTAs per SM overlap
+// each other's tensor and ALU phases. TMEM: 256 columns per CTA (S 64 | P_hi 64 | P_lo 64 | O 64).
+#include "common.cuh"
+#include <cuda.h>
+#include <math.h>
+
+namespace m2 {
+
+constexpr int TC_BQ = 128;      // queries per CTA
+constexpr int TC_BK = 64;       // keys per tile
+constexpr int TC_BOX = 32;      // positions per TMA box (128 B of fp32)
+constexpr int TC_THREADS = 128;
+constexpr uint32_t TC_TMEM_COLS = 256;
+constexpr uint32_t TC_COL_S = 0, TC_COL_PHI = 64, TC_COL_PLO = 128, TC_COL_O = 192;
+
+// ---- PTX wrappers -----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  for (uint32_t it = 0; it < (1u << 24); ++it) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) return;
+  }
+  __trap();  // a lost arrival would otherwise hang the GPU; fail loudly instead
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], TF32 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem desc]
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, 128-byte swizzle (layout_type 2), descriptor version 1 (sm_100).
+// Byte offsets are encoded >> 4. For MN-major operands LBO = stride between 32-element (128 B)
+// groups along M/N and SBO = stride between 8-row groups along K; for K-major operands SBO =
+// stride between 8-row groups along M/N and LBO is unused (encoded 1).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (2ull << 61);
+}
+// UMMA instruction descriptor: fp32 accumulate (bits 4-5 = 1), A/B format TF32 (2) at bits 7-9 /
+// 10-12, A/B major at bits 15/16 (1 = MN-major), N>>3 at bits 17-22, M>>4 at bits 24-28.
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t tf32_hi(float v) { return __float_as_uint(v) & 0xFFFFE000u; }
+
+template <int HD>
+struct TcSmem {
+  static constexpr uint32_t box_bytes = HD * 128;                   // hd rows x 32 positions x 4 B
+  static constexpr uint32_t q_bytes = 2 * (TC_BQ / TC_BOX) * box_bytes;   // hi + lo
+  static constexpr uint32_t kv_bytes = 2 * (TC_BK / TC_BOX) * box_bytes;  // hi + lo, per operand
+  static constexpr uint32_t total = q_bytes + 2 * kv_bytes + 1024 /*align slack*/ + 64 /*barriers*/;
+};
+
+template <int HD>
+__global__ void __launch_bounds__(TC_THREADS, 2)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__ ctx,
+                    const int64_t* __restrict__ lengths, int B, int L, int nh) {
+  static_assert(HD % 16 == 0 && HD >= 16 && HD <= 64, "tensor-core path: head_dim in {16,32,48,64}");
+  constexpr uint32_t BOX = TcSmem<HD>::box_bytes;
+  constexpr int QBOX = TC_BQ / TC_BOX, KBOX = TC_BK / TC_BOX;  // 4, 2
+  constexpr int KSTEPS_D = HD / 8;                             // k-steps of the QK^T product
+  constexpr uint32_t IDESC_QK = umma_idesc_tf32(TC_BQ, TC_BK, 1, 1);
+  constexpr uint32_t IDESC_PV = umma_idesc_tf32(TC_BQ, HD, 0, 0);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SW128 atoms need 1024-B alignment
+  const uint32_t sQ = sbase;                                  // [hi|lo][QBOX][HD rows][128 B]
+  const uint32_t sK = sQ + TcSmem<HD>::q_bytes;               // [hi|lo][KBOX][HD][128 B]
+  const uint32_t sV = sK + TcSmem<HD>::kv_bytes;
+  const uint32_t sBar = sV + TcSmem<HD>::kv_bytes;            // 5 mbarriers + tmem slot
+  const uint32_t bar_q = sBar, bar_k = sBar + 8, bar_v = sBar + 16, bar_s = sBar + 24, bar_o = sBar + 32;
+  const uint32_t tmem_slot = sBar + 40;
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int q0 = blockIdx.x * TC_BQ, head = blockIdx.y, b = blockIdx.z;
+
+  int Leff = L;
+  bool all_masked = false;
+  if (lengths != nullptr) {
+    const long long len = lengths[b];
+    if (len <= 0) all_masked = true;
+    else if (len < L) Leff = (int)len;
+  }
+  const int nkt = (Leff + TC_BK - 1) / TC_BK;
+
+  // rows of the six operand planes in the tensor map
+  const int plane = B * nh * HD;
+  const int row_q = (b * nh + head) * HD;   // + which * plane
+
+  if (tid == 0) {
+    mbar_init(bar_q, 1); mbar_init(bar_k, 1); mbar_init(bar_v, 1); mbar_init(bar_s, 1); mbar_init(bar_o, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TC_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);  // this warp's 32 TMEM lanes
+
+  auto load_kv = [&](uint32_t sdst, uint32_t bar, int which_hi, int k0) {
+    mbar_expect_tx(bar, TcSmem<HD>::kv_bytes);
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int x = 0; x < KBOX; ++x)
+        tma_load_2d(sdst + (h * KBOX + x) * BOX, &tmap, k0 + x * TC_BOX, (which_hi + h) * plane + row_q, bar);
+  };
+  auto issue_qk = [&]() {
+    // S[128 q, 64 keys] = sum over d: Q^T and K^T boxes are MN-major (positions contiguous)
+#pragma unroll
+    for (int term = 0; term < 3; ++term) {          // hi*hi, hi*lo, lo*hi
+      const uint32_t qa = sQ + ((term == 2) ? QBOX * BOX : 0u);
+      const uint32_t kb = sK + ((term == 1) ? KBOX * BOX : 0u);
+#pragma unroll
+      for (int ks = 0; ks < KSTEPS_D; ++ks) {
+        const uint64_t ad = umma_desc_sw128(qa + ks * 1024u, BOX, 1024u);
+        const uint64_t bd = umma_desc_sw128(kb + ks * 1024u, BOX, 1024u);
+        umma_tf32_ss(tmem_base + TC_COL_S, ad, bd, IDESC_QK, (term | ks) ? 1u : 0u);
+      }
+    }
+  };
+  auto issue_pv = [&]() {
+    // O_tile[128 q, HD] = P[128, 64 keys] (TMEM) * V[64 keys, HD]; V^T boxes are K-major (keys contiguous)
+#pragma unroll
+    for (int term = 0; term < 3; ++term) {          // hi*hi, hi*lo, lo*hi
+      const uint32_t pa = tmem_base + ((term == 2) ? TC_COL_PLO : TC_COL_PHI);
+      const uint32_t vb = sV + ((term == 1) ? KBOX * BOX : 0u);
+#pragma unroll
+      for (int ks = 0; ks < TC_BK / 8; ++ks) {
+        const uint64_t bd = umma_desc_sw128(vb + (ks >> 2) * BOX + (ks & 3) * 32u, 16u, 1024u);
+        umma_tf32_ts(tmem_base + TC_COL_O, pa + ks * 8, bd, IDESC_PV, (term | ks) ? 1u : 0u);
+      }
+    }
+  };
+
+  if (tid == 0) {
+    mbar_expect_tx(bar_q, TcSmem<HD>::q_bytes);
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int x = 0; x < QBOX; ++x)
+        tma_load_2d(sQ + (h * QBOX + x) * BOX, &tmap, q0 + x * TC_BOX, h * plane + row_q, bar_q);
+    load_kv(sK, bar_k, 2, 0);
+    load_kv(sV, bar_v, 4, 0);
+    mbar_wait(bar_q, 0);
+    mbar_wait(bar_k, 0);
+    tc_fence_after();
+    issue_qk();
+    tc_commit(bar_s);
+  }
+  __syncwarp();
+
+  float o[HD];
+#pragma unroll
+  for (int c = 0; c < HD; ++c) o[c] = 0.f;
+  float m_run = -INFINITY, l_run = 0.f;
+
+  for (int t = 0; t < nkt; ++t) {
+    const uint32_t par = (uint32_t)(t & 1);
+    mbar_wait(bar_s, par);
+    tc_fence_after();
+    if (tid == 0 && t + 1 < nkt) load_kv(sK, bar_k, 2, (t + 1) * TC_BK);  // K buffer is free: QK(t) committed
+    __syncwarp();
+
+    // ---- S row -> registers ----
+    uint32_t sr[TC_BK];
+#pragma unroll
+    for (int c = 0; c < TC_BK; c += 16) tmem_ld16(t_lane + TC_COL_S + c, sr + c);
+    tmem_wait_ld();
+    float s[TC_BK];
+    const int kbase = t * TC_BK;
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < TC_BK; ++j) {
+      float v = __uint_as_float(sr[j]);
+      if (all_masked) v = (kbase + j < L) ? 0.f : -INFINITY;
+      else if (kbase + j >= Leff) v = -INFINITY;
+      s[j] = v;
+      mx = fmaxf(mx, v);
+    }
+    const float m_new = fmaxf(m_run, mx);
+    const float alpha = exp2f(m_run - m_new);
+    m_run = m_new;
+    float rs = 0.f;
+#pragma unroll
+    for (int c = 0; c < TC_BK; c += 16) {
+      uint32_t ph[16], pl[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float p = exp2f(s[c + j] - m_new);
+        rs += p;
+        ph[j] = tf32_hi(p);
+        pl[j] = tf32_hi(p - __uint_as_float(ph[j]));
+      }
+      tmem_st16(t_lane + TC_COL_PHI + c, ph);
+      tmem_st16(t_lane + TC_COL_PLO + c, pl);
+    }
+    l_run = l_run * alpha + rs;
+    tmem_wait_st();
+    tc_fence_before();
+    __syncthreads();   // every row's P is in TMEM and every S load has retired
+
+    if (tid == 0) {
+      tc_fence_after();
+      mbar_wait(bar_v, par);
+      tc_fence_after();
+      issue_pv();
+      tc_commit(bar_o);
+      if (t + 1 < nkt) {   // S columns are free again: queue the next tile's scores behind PV(t)
+        mbar_wait(bar_k, par ^ 1u);
+        tc_fence_after();
+        issue_qk();
+        tc_commit(bar_s);
+      }
+    }
+    __syncwarp();
+
+    mbar_wait(bar_o, par);
+    tc_fence_after();
+    if (tid == 0 && t + 1 < nkt) load_kv(sV, bar_v, 4, (t + 1) * TC_BK);  // V buffer is free: PV(t) committed
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < HD; c += 16) {
+      uint32_t orr[16];
+      tmem_ld16(t_lane + TC_COL_O + c, orr);
+      tmem_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) o[c + j] = fmaf(o[c + j], alpha, __uint_as_float(orr[j]));
+    }
+  }
+
+  // ---- epilogue: normalise and store this thread's query row ----
+  const int qi = q0 + tid;
+  if (qi < L) {
+    const float inv = 1.0f / l_run;
+    float* dst = ctx + ((long long)b * L + qi) * (nh * HD) + head * HD;
+#pragma unroll
+    for (int c = 0; c < HD; c += 4)
+      *reinterpret_cast<float4*>(dst + c) = make_float4(o[c] * inv, o[c + 1] * inv, o[c + 2] * inv, o[c + 3] * inv);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
+  }
+}
+
+// ---- host side --------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+template <int HD>
+static int launch_tc_hd(const CUtensorMap& tmap, float* ctx, const int64_t* lengths, int B, int L, int nh,
+                        cudaStream_t s) {
+  const size_t smem = TcSmem<HD>::total;
+  M2_CUDA_OK(allow_smem(attention_tc_kernel<HD>, smem));
+  dim3 grid(ceil_div(L, TC_BQ), nh, B);
+  M2_LAUNCH(M2TTS_STAGE_ATTENTION, attention_tc_kernel<HD>, grid, TC_THREADS, smem, s, tmap, ctx, lengths, B, L, nh);
+  return M2TTS_OK;
+}
+
+bool attention_tc_supported(int hd) { return hd == 16 || hd == 32 || hd == 48 || hd == 64; }
+
+// qkv6: [6][B][nh][hd][Lp] fp32 (Q_hi,Q_lo,K_hi,K_lo,V_hi,V_lo), Q pre-scaled by scale*log2e.
+int launch_attention_tc(const float* qkv6, float* ctx, const int64_t* lengths, int B, int L, int Lp, int nh,
+                        int hd, cudaStream_t s) {
+  M2_REQUIRE(qkv6 && ctx, M2TTS_E_NULLPTR, "attention_tc: null pointer");
+  M2_REQUIRE(attention_tc_supported(hd), M2TTS_E_UNSUPPORTED, "attention_tc: head_dim %d unsupported", hd);
+  M2_REQUIRE(B > 0 && L > 0 && nh > 0 && B <= 65535 && nh <= 65535 && (Lp & 3) == 0 && Lp >= L, M2TTS_E_BADSHAPE,
+             "attention_tc: B=%d L=%d Lp=%d nh=%d", B, L, Lp, nh);
+  M2_REQUIRE((((uintptr_t)qkv6) & 15) == 0 && ((nh * hd) & 3) == 0, M2TTS_E_BADSHAPE, "attention_tc: misaligned operands");
+  EncodeTiledFn enc = get_encode_fn();
+  M2_REQUIRE(enc != nullptr, M2TTS_E_CUDA, "attention_tc: cuTensorMapEncodeTiled unavailable");
+  CUtensorMap tmap;
+  const cuuint64_t dims[2] = {(cuuint64_t)L, (cuuint64_t)6 * B * nh * hd};
+  const cuuint64_t strides[1] = {(cuuint64_t)Lp * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)TC_BOX, (cuuint32_t)hd};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)qkv6, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  M2_REQUIRE(r == CUDA_SUCCESS, M2TTS_E_CUDA, "attention_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  switch (hd) {
+    case 16: return launch_tc_hd<16>(tmap, ctx, lengths, B, L, nh, s);
+    case 32: return launch_tc_hd<32>(tmap, ctx, lengths, B, L, nh, s);
+    case 48: return launch_tc_hd<48>(tmap, ctx, lengths, B, L, nh, s);
+    default: return launch_tc_hd<64>(tmap, ctx, lengths, B, L, nh, s);
+  }
+}
+
+}  // namespace m2

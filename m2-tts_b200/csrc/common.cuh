@@ -116,6 +116,8 @@ struct RowGemmArgs {
   float* y; int ldy;                  // ROWMAJOR output
   // QKV-split output (if qkv_mode): q,k as [B,nh,hd,Lp], v as [B,nh,L,hd]
   int qkv_mode; float* q; float* k; float* v; int L; int Lp; int nh; int hd;
+  // qkv_mode 2: q points at six hi/lo planes [6][B,nh,hd,Lp] (plane_stride floats apart), Q scaled by qscale
+  float qscale; long long plane_stride;
   int R; int K; int N;
   int stage;
 };
@@ -127,4 +129,8 @@ int launch_pack_transpose(const PackJob* jobs, int n_jobs, cudaStream_t s);
 int launch_attention(const float* q, const float* k, const float* v, float* ctx,
                      const int64_t* lengths, int B, int L, int Lp, int nh, int hd,
                      cudaStream_t s);
+bool attention_tc_supported(int hd);
+int launch_attention_tc(const float* qkv6, float* ctx, const int64_t* lengths, int B, int L, int Lp,
+                        int nh, int hd, cudaStream_t s);
+int attention_mode();  // 0 = tensor cores when supported, 1 = force the FFMA kernel
 }  // namespace m2

@@ -127,6 +127,35 @@ __global__ void __launch_bounds__(RG_THREADS) rowgemm_kernel(RowGemmArgs a) {
       }
     } else {
       const int H = a.nh * a.hd;
+      if (a.qkv_mode == 2) {
+        // tensor-core attention operands: six planes [Q_hi,Q_lo,K_hi,K_lo,V_hi,V_lo][B,nh,hd,Lp],
+        // each value split as hi + lo with both halves exact in TF32; Q carries scale*log2(e).
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+          const int n = nbase + j;
+          if (n >= N) continue;
+          const int which = n / H, rem = n - which * H;
+          const int head = rem / a.hd, d = rem - head * a.hd;
+          const float sc = (which == 0) ? a.qscale : 1.0f;
+          float* hi_p = a.q + (long long)(2 * which) * a.plane_stride +
+                        (((long long)bidx * a.nh + head) * a.hd + d) * a.Lp + l0 + tx * 4;
+          float* lo_p = hi_p + a.plane_stride;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (l0 + tx * 4 + h * 64 >= a.Lp) continue;
+            float hi[4], lo[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float v = acc[h * 4 + i][j] * sc;
+              hi[i] = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+              lo[i] = __uint_as_float(__float_as_uint(v - hi[i]) & 0xFFFFE000u);
+            }
+            *reinterpret_cast<float4*>(hi_p + h * 64) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<float4*>(lo_p + h * 64) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+          }
+        }
+        continue;
+      }
 #pragma unroll
       for (int j = 0; j < TN; j += 2) {
         const int n = nbase + j;
@@ -176,7 +205,7 @@ int launch_rowgemm(const RowGemmArgs& in, cudaStream_t s) {
   M2_REQUIRE(a.K <= 256, M2TTS_E_UNSUPPORTED, "rowgemm: inner dim %d > 256 not supported", a.K);
   int nb = 1;
   if (a.qkv_mode) {
-    M2_REQUIRE(a.q && a.k && a.v, M2TTS_E_NULLPTR, "rowgemm: null q/k/v");
+    M2_REQUIRE(a.q && (a.qkv_mode == 2 || (a.k && a.v)), M2TTS_E_NULLPTR, "rowgemm: null q/k/v");
     M2_REQUIRE(a.L > 0 && a.R % a.L == 0 && (a.Lp & 3) == 0 && a.Lp >= a.L && (a.hd & 1) == 0 &&
                    a.N == 3 * a.nh * a.hd,
                M2TTS_E_BADSHAPE, "rowgemm qkv: L=%d Lp=%d nh=%d hd=%d N=%d", a.L, a.Lp, a.nh, a.hd, a.N);

@@ -4,6 +4,7 @@
 #include <mutex>
 #include <vector>
 #include <string.h>
+#include <stdlib.h>
 
 namespace m2 {
 
@@ -61,7 +62,26 @@ void note_launch(int stage, cudaStream_t s, bool begin) {
 
 using namespace m2;
 
-extern "C" int m2tts_version(void) { return 100; }
+static std::atomic<int> g_attn_mode{-1};
+namespace m2 {
+int attention_mode() {
+  int m = g_attn_mode.load(std::memory_order_relaxed);
+  if (m < 0) {
+    const char* e = getenv("M2TTS_ATTENTION");
+    m = (e && strcmp(e, "ffma") == 0) ? 1 : 0;
+    g_attn_mode.store(m);
+  }
+  return m;
+}
+}  // namespace m2
+
+extern "C" int m2tts_set_attention_mode(int mode) {
+  M2_REQUIRE(mode == 0 || mode == 1, M2TTS_E_BADSHAPE, "set_attention_mode: mode must be 0 (tensor) or 1 (ffma)");
+  g_attn_mode.store(mode);
+  return M2TTS_OK;
+}
+
+extern "C" int m2tts_version(void) { return 101; }
 
 extern "C" const char* m2tts_last_error_string(void) { return g_err; }
 

@@ -4,6 +4,7 @@
 //                -> [LN2 + FFN1 + ReLU] -> [FFN2 + residual]
 // Reference: components.py:131-140 (TransformerEncoderLayer._forward), :59-90, :103.
 #include "common.cuh"
+#include <math.h>
 
 using namespace m2;
 
@@ -22,9 +23,10 @@ bool carve_layer(void* ws, size_t bytes, int B, int L, int H, int F, LayerWs* o)
   o->wo_t = cv.take<float>((size_t)H * H);
   o->w1_t = cv.take<float>((size_t)H * F);
   o->w2_t = cv.take<float>((size_t)F * H);
-  o->q = cv.take<float>((size_t)B * H * Lp);
-  o->k = cv.take<float>((size_t)B * H * Lp);
-  o->v = cv.take<float>((size_t)B * L * H);
+  // six planes: the tensor-core attention wants {Q,K,V} x {hi,lo}; the FFMA kernel uses the first three
+  o->q = cv.take<float>((size_t)6 * B * H * Lp);
+  o->k = o->q + (size_t)B * H * Lp;
+  o->v = o->k + (size_t)B * H * Lp;
   o->ctx = cv.take<float>((size_t)B * L * H);
   o->x1 = cv.take<float>((size_t)B * L * H);
   o->hid = cv.take<float>((size_t)B * L * F);
@@ -35,8 +37,8 @@ bool carve_layer(void* ws, size_t bytes, int B, int L, int H, int F, LayerWs* o)
 extern "C" size_t m2tts_transformer_workspace_bytes(int B, int L, int H, int F) {
   if (B <= 0 || L <= 0 || H <= 0 || F <= 0) return 0;
   const size_t Lp = (size_t)((L + 3) & ~3);
-  size_t fl = (size_t)H * 3 * H + (size_t)H * H + 2 * (size_t)H * F + 2 * (size_t)B * H * Lp +
-              3 * (size_t)B * L * H + (size_t)B * L * F;
+  size_t fl = (size_t)H * 3 * H + (size_t)H * H + 2 * (size_t)H * F + 6 * (size_t)B * H * Lp +
+              2 * (size_t)B * L * H + (size_t)B * L * F;
   return fl * sizeof(float) + 16 * 256;
 }
 
@@ -69,15 +71,22 @@ extern "C" int m2tts_transformer_layer(const m2tts_layer_weights* w, const float
   if ((rc = launch_pack_transpose(jobs, 4, s))) return rc;
 
   const int R = B * L;
+  const bool use_tc = attention_mode() == 0 && attention_tc_supported(hd);
   {  // q,k,v = split(LN1(x) Wqkv^T)
     RowGemmArgs a{};
     a.x = x_in; a.ldx = H; a.ln_w = w->norm1_w; a.ln_b = w->norm1_b; a.eps = ln_eps;
-    a.wt = ws.wqkv_t; a.qkv_mode = 1; a.q = ws.q; a.k = ws.k; a.v = ws.v;
+    a.wt = ws.wqkv_t; a.qkv_mode = use_tc ? 2 : 1; a.q = ws.q; a.k = ws.k; a.v = ws.v;
+    a.qscale = (float)((1.0 / sqrt((double)hd)) * 1.4426950408889634);
+    a.plane_stride = (long long)B * H * ws.Lp;
     a.L = L; a.Lp = ws.Lp; a.nh = num_heads; a.hd = hd; a.R = R; a.K = H; a.N = 3 * H;
     a.stage = M2TTS_STAGE_LN_QKV;
     if ((rc = launch_rowgemm(a, s))) return rc;
   }
-  if ((rc = launch_attention(ws.q, ws.k, ws.v, ws.ctx, lengths, B, L, ws.Lp, num_heads, hd, s))) return rc;
+  if (use_tc) {
+    if ((rc = launch_attention_tc(ws.q, ws.ctx, lengths, B, L, ws.Lp, num_heads, hd, s))) return rc;
+  } else {
+    if ((rc = launch_attention(ws.q, ws.k, ws.v, ws.ctx, lengths, B, L, ws.Lp, num_heads, hd, s))) return rc;
+  }
   {  // x1 = x + ctx Wo^T + bo
     RowGemmArgs a{};
     a.x = ws.ctx; a.ldx = H; a.wt = ws.wo_t; a.bias = w->out_b; a.residual = x_in; a.ldr = H;

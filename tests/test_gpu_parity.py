@@ -207,7 +207,7 @@ def test_vocoder_matches_oracle(stage, B, T):
     assert H.max_abs(got_t.cpu(), want) <= FP32_TOL
 
 
-def test_vocoder_linearity_of_input_conv_stage():
+def test_vocoder_batch_independence():
     """Size-independent property at a larger size: the vocoder is deterministic and
     batch-independent — utterance b of a batch equals the same utterance run alone."""
     m = cuda_model("stage2")
@@ -243,7 +243,8 @@ def test_conv_entry_points_dilation_and_activation():
         want = torch.nn.functional.leaky_relu(
             torch.nn.functional.conv_transpose1d(x, w, b, stride=r_, padding=r_ // 2), 0.1)
         y = torch.empty(2, CO, r_ * L, device=DEV)
-        rc = lib.m2tts_conv_transpose1d_lrelu(x.to(DEV).data_ptr(), w.to(DEV).data_ptr(), b.to(DEV).data_ptr(),
+        xd, wd, bd = (t.to(DEV) for t in (x, w, b))   # keep the device copies alive across the call
+        rc = lib.m2tts_conv_transpose1d_lrelu(xd.data_ptr(), wd.data_ptr(), bd.data_ptr(),
                                               y.data_ptr(), 2, CI, CO, L, r_, None)
         nat.check(rc, "conv_transpose1d")
         assert H.max_abs(y.cpu(), want) <= FP32_TOL, (CI, CO, L, r_)
@@ -272,3 +273,25 @@ def test_batch_sharding_is_exact():
     half = m(ids[8:], lengths[8:], dur[8:], 330)
     for k in ("regulated_output", "mel_output", "audio_output"):
         assert torch.equal(full[k][8:], half[k]), k
+
+
+# --------------------------------------------------------------------------- tensor-core attention
+@pytest.mark.parametrize("mode", [0, 1])  # 0 = tcgen05 3xTF32 kernel, 1 = fp32 FFMA kernel
+def test_attention_kernels_both_meet_fp32_tolerance(mode):
+    from models import _native as nat
+    lib = nat.lib()
+    try:
+        nat.check(lib.m2tts_set_attention_mode(mode), "set_attention_mode")
+        for stage, heads in (("stage2", 2), ("stage1", 2)):
+            m = cuda_model(stage, perturb=4)
+            sd = cpu_sd(m)
+            Hd = H.STAGE_KWARGS[stage]["hidden_dim"]
+            x = torch.randn(2, 333, Hd, generator=torch.Generator().manual_seed(8))
+            got = m.decoder(x.to(DEV))
+            assert H.max_abs(got.cpu(), oracle.mel_decoder(sd, x, heads)) <= FP32_TOL, (stage, "decoder")
+            ids = torch.randint(0, 256, (4, 200), generator=torch.Generator().manual_seed(9))
+            lengths = torch.tensor([200, 77, 0, 129])
+            enc, _ = m.text_encoder(ids.to(DEV), lengths.to(DEV))
+            assert H.max_abs(enc.cpu(), oracle.text_encoder(sd, ids, lengths, heads)[0]) <= FP32_TOL, (stage, "encoder")
+    finally:
+        lib.m2tts_set_attention_mode(0)
