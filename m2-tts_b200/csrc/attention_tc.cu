@@ -96,9 +96,13 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 // Byte offsets are encoded >> 4. For MN-major operands LBO = stride between 32-element (128 B)
 // groups along M/N and SBO = stride between 8-row groups along K; for K-major operands SBO =
 // stride between 8-row groups along M/N and LBO is unused (encoded 1).
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// layout_type: 2 = SWIZZLE_128B (16-B atomicity; K-major operands), 1 = SWIZZLE_128B_BASE32B (32-B
+// atomicity, 4-row K atoms): the ONLY layout tcgen05 accepts for MN-major 32-bit (TF32) operands —
+// with layout type 2 and the MN-major bit set the MMA silently produces zeros (measured with
+// umma_probe.cu, see tests/umma_probe_run.py).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
   return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
-         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (2ull << 61);
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | ((uint64_t)layout_type << 61);
 }
 // UMMA instruction descriptor: fp32 accumulate (bits 4-5 = 1), A/B format TF32 (2) at bits 7-9 /
 // 10-12, A/B major at bits 15/16 (1 = MN-major), N>>3 at bits 17-22, M>>4 at bits 24-28.
@@ -119,8 +123,10 @@ struct TcSmem {
 
 template <int HD>
 __global__ void __launch_bounds__(TC_THREADS, 2)
-attention_tc_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__ ctx,
-                    const int64_t* __restrict__ lengths, int B, int L, int nh) {
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_constant__ CUtensorMap tmap_v,
+                    float* __restrict__ ctx,
+                    const int64_t* __restrict__ lengths, int B, int L, int nh,
+                    float* __restrict__ dbg_s, float* __restrict__ dbg_o) {
   static_assert(HD % 16 == 0 && HD >= 16 && HD <= 64, "tensor-core path: head_dim in {16,32,48,64}");
   constexpr uint32_t BOX = TcSmem<HD>::box_bytes;
   constexpr int QBOX = TC_BQ / TC_BOX, KBOX = TC_BK / TC_BOX;  // 4, 2
@@ -156,7 +162,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict_
   if (tid == 0) {
     mbar_init(bar_q, 1); mbar_init(bar_k, 1); mbar_init(bar_v, 1); mbar_init(bar_s, 1); mbar_init(bar_o, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_qk) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_v) : "memory");
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TC_TMEM_COLS) : "memory");
@@ -170,12 +177,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict_
   const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);  // this warp's 32 TMEM lanes
 
   auto load_kv = [&](uint32_t sdst, uint32_t bar, int which_hi, int k0) {
+    const CUtensorMap* map = (which_hi == 4) ? &tmap_v : &tmap_qk;
     mbar_expect_tx(bar, TcSmem<HD>::kv_bytes);
 #pragma unroll
     for (int h = 0; h < 2; ++h)
 #pragma unroll
       for (int x = 0; x < KBOX; ++x)
-        tma_load_2d(sdst + (h * KBOX + x) * BOX, &tmap, k0 + x * TC_BOX, (which_hi + h) * plane + row_q, bar);
+        tma_load_2d(sdst + (h * KBOX + x) * BOX, map, k0 + x * TC_BOX, (which_hi + h) * plane + row_q, bar);
   };
   auto issue_qk = [&]() {
     // S[128 q, 64 keys] = sum over d: Q^T and K^T boxes are MN-major (positions contiguous)
@@ -185,8 +193,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict_
       const uint32_t kb = sK + ((term == 1) ? KBOX * BOX : 0u);
 #pragma unroll
       for (int ks = 0; ks < KSTEPS_D; ++ks) {
-        const uint64_t ad = umma_desc_sw128(qa + ks * 1024u, BOX, 1024u);
-        const uint64_t bd = umma_desc_sw128(kb + ks * 1024u, BOX, 1024u);
+        // MN-major, 128B swizzle / 32B atoms: LBO = next 32 positions (next box), SBO = next 4 d-rows
+        const uint64_t ad = umma_desc(qa + ks * 1024u, BOX, 512u, 1u);
+        const uint64_t bd = umma_desc(kb + ks * 1024u, BOX, 512u, 1u);
         umma_tf32_ss(tmem_base + TC_COL_S, ad, bd, IDESC_QK, (term | ks) ? 1u : 0u);
       }
     }
@@ -199,7 +208,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict_
       const uint32_t vb = sV + ((term == 1) ? KBOX * BOX : 0u);
 #pragma unroll
       for (int ks = 0; ks < TC_BK / 8; ++ks) {
-        const uint64_t bd = umma_desc_sw128(vb + (ks >> 2) * BOX + (ks & 3) * 32u, 16u, 1024u);
+        const uint64_t bd = umma_desc(vb + (ks >> 2) * BOX + (ks & 3) * 32u, 16u, 1024u, 2u);
         umma_tf32_ts(tmem_base + TC_COL_O, pa + ks * 8, bd, IDESC_PV, (term | ks) ? 1u : 0u);
       }
     }
@@ -211,7 +220,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict_
     for (int h = 0; h < 2; ++h)
 #pragma unroll
       for (int x = 0; x < QBOX; ++x)
-        tma_load_2d(sQ + (h * QBOX + x) * BOX, &tmap, q0 + x * TC_BOX, h * plane + row_q, bar_q);
+        tma_load_2d(sQ + (h * QBOX + x) * BOX, &tmap_qk, q0 + x * TC_BOX, h * plane + row_q, bar_q);
     load_kv(sK, bar_k, 2, 0);
     load_kv(sV, bar_v, 4, 0);
     mbar_wait(bar_q, 0);
@@ -239,6 +248,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict_
 #pragma unroll
     for (int c = 0; c < TC_BK; c += 16) tmem_ld16(t_lane + TC_COL_S + c, sr + c);
     tmem_wait_ld();
+    if (dbg_s != nullptr && t == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+#pragma unroll
+      for (int j = 0; j < TC_BK; ++j) dbg_s[tid * TC_BK + j] = __uint_as_float(sr[j]);
+    }
     float s[TC_BK];
     const int kbase = t * TC_BK;
     float mx = -INFINITY;
@@ -296,6 +309,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict_
       uint32_t orr[16];
       tmem_ld16(t_lane + TC_COL_O + c, orr);
       tmem_wait_ld();
+      if (dbg_o != nullptr && t == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) dbg_o[tid * HD + c + j] = __uint_as_float(orr[j]);
+      }
 #pragma unroll
       for (int j = 0; j < 16; ++j) o[c + j] = fmaf(o[c + j], alpha, __uint_as_float(orr[j]));
     }
@@ -335,12 +352,12 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 template <int HD>
-static int launch_tc_hd(const CUtensorMap& tmap, float* ctx, const int64_t* lengths, int B, int L, int nh,
-                        cudaStream_t s) {
+static int launch_tc_hd(const CUtensorMap& tmap_qk, const CUtensorMap& tmap_v, float* ctx, const int64_t* lengths, int B, int L, int nh,
+                        cudaStream_t s, float* dbg_s, float* dbg_o) {
   const size_t smem = TcSmem<HD>::total;
   M2_CUDA_OK(allow_smem(attention_tc_kernel<HD>, smem));
   dim3 grid(ceil_div(L, TC_BQ), nh, B);
-  M2_LAUNCH(M2TTS_STAGE_ATTENTION, attention_tc_kernel<HD>, grid, TC_THREADS, smem, s, tmap, ctx, lengths, B, L, nh);
+  M2_LAUNCH(M2TTS_STAGE_ATTENTION, attention_tc_kernel<HD>, grid, TC_THREADS, smem, s, tmap_qk, tmap_v, ctx, lengths, B, L, nh, dbg_s, dbg_o);
   return M2TTS_OK;
 }
 
@@ -348,7 +365,7 @@ bool attention_tc_supported(int hd) { return hd == 16 || hd == 32 || hd == 48 ||
 
 // qkv6: [6][B][nh][hd][Lp] fp32 (Q_hi,Q_lo,K_hi,K_lo,V_hi,V_lo), Q pre-scaled by scale*log2e.
 int launch_attention_tc(const float* qkv6, float* ctx, const int64_t* lengths, int B, int L, int Lp, int nh,
-                        int hd, cudaStream_t s) {
+                        int hd, cudaStream_t s, float* dbg_s, float* dbg_o) {
   M2_REQUIRE(qkv6 && ctx, M2TTS_E_NULLPTR, "attention_tc: null pointer");
   M2_REQUIRE(attention_tc_supported(hd), M2TTS_E_UNSUPPORTED, "attention_tc: head_dim %d unsupported", hd);
   M2_REQUIRE(B > 0 && L > 0 && nh > 0 && B <= 65535 && nh <= 65535 && (Lp & 3) == 0 && Lp >= L, M2TTS_E_BADSHAPE,
@@ -356,21 +373,34 @@ int launch_attention_tc(const float* qkv6, float* ctx, const int64_t* lengths, i
   M2_REQUIRE((((uintptr_t)qkv6) & 15) == 0 && ((nh * hd) & 3) == 0, M2TTS_E_BADSHAPE, "attention_tc: misaligned operands");
   EncodeTiledFn enc = get_encode_fn();
   M2_REQUIRE(enc != nullptr, M2TTS_E_CUDA, "attention_tc: cuTensorMapEncodeTiled unavailable");
-  CUtensorMap tmap;
+  CUtensorMap tmap_qk, tmap_v;
   const cuuint64_t dims[2] = {(cuuint64_t)L, (cuuint64_t)6 * B * nh * hd};
   const cuuint64_t strides[1] = {(cuuint64_t)Lp * sizeof(float)};
   const cuuint32_t box[2] = {(cuuint32_t)TC_BOX, (cuuint32_t)hd};
   const cuuint32_t estr[2] = {1, 1};
-  const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)qkv6, dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  M2_REQUIRE(r == CUDA_SUCCESS, M2TTS_E_CUDA, "attention_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  // Q/K boxes feed MN-major TF32 operands -> 128-B swizzle with 32-B atoms; V^T boxes are K-major -> plain 128-B swizzle
+  CUresult r = enc(&tmap_qk, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)qkv6, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  M2_REQUIRE(r == CUDA_SUCCESS, M2TTS_E_CUDA, "attention_tc: cuTensorMapEncodeTiled (q/k) failed (%d)", (int)r);
+  r = enc(&tmap_v, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)qkv6, dims, strides, box, estr,
+          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  M2_REQUIRE(r == CUDA_SUCCESS, M2TTS_E_CUDA, "attention_tc: cuTensorMapEncodeTiled (v) failed (%d)", (int)r);
   switch (hd) {
-    case 16: return launch_tc_hd<16>(tmap, ctx, lengths, B, L, nh, s);
-    case 32: return launch_tc_hd<32>(tmap, ctx, lengths, B, L, nh, s);
-    case 48: return launch_tc_hd<48>(tmap, ctx, lengths, B, L, nh, s);
-    default: return launch_tc_hd<64>(tmap, ctx, lengths, B, L, nh, s);
+    case 16: return launch_tc_hd<16>(tmap_qk, tmap_v, ctx, lengths, B, L, nh, s, dbg_s, dbg_o);
+    case 32: return launch_tc_hd<32>(tmap_qk, tmap_v, ctx, lengths, B, L, nh, s, dbg_s, dbg_o);
+    case 48: return launch_tc_hd<48>(tmap_qk, tmap_v, ctx, lengths, B, L, nh, s, dbg_s, dbg_o);
+    default: return launch_tc_hd<64>(tmap_qk, tmap_v, ctx, lengths, B, L, nh, s, dbg_s, dbg_o);
   }
 }
 
 }  // namespace m2
+
+// Test / bring-up entry: run the tensor-core attention on caller-prepared hi/lo planes and
+// optionally dump the first score tile (128x64, pre-mask, log2 domain) and the first P*V tile.
+extern "C" int m2tts_attention_tc_planes(const float* qkv6, float* ctx, const int64_t* lengths, int B, int L,
+                                         int Lp, int nh, int hd, float* dbg_s, float* dbg_o,
+                                         m2tts_stream_t stream) {
+  return m2::launch_attention_tc(qkv6, ctx, lengths, B, L, Lp, nh, hd, (cudaStream_t)stream, dbg_s, dbg_o);
+}

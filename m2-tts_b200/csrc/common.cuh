@@ -131,6 +131,6 @@ int launch_attention(const float* q, const float* k, const float* v, float* ctx,
                      cudaStream_t s);
 bool attention_tc_supported(int hd);
 int launch_attention_tc(const float* qkv6, float* ctx, const int64_t* lengths, int B, int L, int Lp,
-                        int nh, int hd, cudaStream_t s);
+                        int nh, int hd, cudaStream_t s, float* dbg_s = nullptr, float* dbg_o = nullptr);
 int attention_mode();  // 0 = tensor cores when supported, 1 = force the FFMA kernel
 }  // namespace m2
