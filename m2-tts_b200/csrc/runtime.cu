@@ -75,6 +75,25 @@ int attention_mode() {
 }
 }  // namespace m2
 
+static std::atomic<int> g_voc_mode{-1};
+namespace m2 {
+int vocoder_mode() {
+  int m = g_voc_mode.load(std::memory_order_relaxed);
+  if (m < 0) {
+    const char* e = getenv("M2TTS_VOCODER");
+    m = (e && strcmp(e, "ffma") == 0) ? 1 : 0;
+    g_voc_mode.store(m);
+  }
+  return m;
+}
+}  // namespace m2
+
+extern "C" int m2tts_set_vocoder_mode(int mode) {
+  M2_REQUIRE(mode == 0 || mode == 1, M2TTS_E_BADSHAPE, "set_vocoder_mode: mode must be 0 (tensor) or 1 (ffma)");
+  g_voc_mode.store(mode);
+  return M2TTS_OK;
+}
+
 extern "C" int m2tts_set_attention_mode(int mode) {
   M2_REQUIRE(mode == 0 || mode == 1, M2TTS_E_BADSHAPE, "set_attention_mode: mode must be 0 (tensor) or 1 (ffma)");
   g_attn_mode.store(mode);

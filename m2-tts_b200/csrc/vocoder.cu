@@ -23,6 +23,8 @@ struct ConvArgs {
   const float* residual;  // [B,CO,L] or null
   float* y;               // [B,CO,L_out]
   int CI, CO, L, dil, act;
+  float* y_lo;            // non-null: write the output as TF32 hi/lo planes (y = hi plane) for the tensor-core convs
+  int y_pitch;            // output row pitch in floats (0 = L)
 };
 
 __device__ __forceinline__ float vc_act(float v, int act) {
@@ -143,14 +145,16 @@ __global__ void __launch_bounds__(VC_THREADS) conv3_kernel(ConvArgs a) {
   }
 
   // ---- epilogue: bias, activation, residual, store (float4 along time when aligned) ----
-  const bool svec = ((L & 3) == 0) && ((((uintptr_t)a.y) & 15) == 0) &&
-                    (a.residual == nullptr || (((uintptr_t)a.residual) & 15) == 0);
+  const int P = a.y_pitch ? a.y_pitch : L;
+  const bool svec = ((P & 3) == 0) && ((L & 3) == 0) && ((((uintptr_t)a.y) & 15) == 0) &&
+                    (a.residual == nullptr || (((uintptr_t)a.residual) & 15) == 0) && a.y_lo == nullptr;
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
     const int co = co0 + ty * 8 + c;
     if (co >= CO) continue;
     const float bv = a.bias ? __ldg(a.bias + co) : 0.f;
-    const long long rowoff = ((long long)b * CO + co) * L;
+    const long long rowoff = ((long long)b * CO + co) * P;
+    const long long resoff = ((long long)b * CO + co) * L;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int t = t0 + 4 * tx + h * (TT / 2);
@@ -160,14 +164,23 @@ __global__ void __launch_bounds__(VC_THREADS) conv3_kernel(ConvArgs a) {
       for (int i = 0; i < 4; ++i) v[i] = vc_act(acc[h * 4 + i][c] + bv, a.act);
       if (svec && t + 3 < L) {
         if (a.residual) {
-          const float4 r = *reinterpret_cast<const float4*>(a.residual + rowoff + t);
+          const float4 r = *reinterpret_cast<const float4*>(a.residual + resoff + t);
           v[0] += r.x; v[1] += r.y; v[2] += r.z; v[3] += r.w;
         }
         *reinterpret_cast<float4*>(a.y + rowoff + t) = make_float4(v[0], v[1], v[2], v[3]);
       } else {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-          if (t + i < L) a.y[rowoff + t + i] = v[i] + (a.residual ? a.residual[rowoff + t + i] : 0.f);
+          if (t + i < L) {
+            const float o = v[i] + (a.residual ? a.residual[resoff + t + i] : 0.f);
+            if (a.y_lo != nullptr) {
+              const float hi = __uint_as_float(__float_as_uint(o) & 0xFFFFE000u);
+              a.y[rowoff + t + i] = hi;
+              a.y_lo[rowoff + t + i] = __uint_as_float(__float_as_uint(o - hi) & 0xFFFFE000u);
+            } else {
+              a.y[rowoff + t + i] = o;
+            }
+          }
       }
     }
   }
@@ -448,10 +461,13 @@ extern "C" int m2tts_conv_transpose1d_lrelu(const float* x, const float* w, cons
 
 extern "C" size_t m2tts_vocoder_workspace_bytes(int B, int T, int M, int C) {
   if (B <= 0 || T <= 0 || M <= 0 || C < 16) return 0;
-  const size_t act = align_up((size_t)B * C * T * 4 * sizeof(float), 256);  // widest activation: 4*C*T per utterance
+  // widest activation: 4*C*T floats per utterance; every buffer can hold a hi/lo plane pair
+  const size_t act = align_up((size_t)2 * B * C * ((size_t)T + 4) * 4 * sizeof(float), 256);
   size_t wts = (size_t)C * M * 3;
-  for (int j = 0, c = C / 2; j < 4; ++j, c /= 2) wts += 2 * (size_t)c * c * 3;
-  return 3 * act + align_up(wts * sizeof(float), 256) + 16 * 256;
+  static const int rates[4] = {4, 4, 2, 2};
+  for (int j = 0, c = C / 2; j < 4; ++j, c /= 2)
+    wts += 2 * (size_t)c * c * 3 + 2 * conv3_tc_wblob_floats(c, c) + convT_tc_wblob_floats(2 * c, c, rates[j]);
+  return 3 * act + align_up(wts * sizeof(float), 256) + 32 * 256;
 }
 
 extern "C" int m2tts_vocoder_forward(const m2tts_vocoder_weights* w, const float* mel, int64_t stride_b,
@@ -466,19 +482,23 @@ extern "C" int m2tts_vocoder_forward(const m2tts_vocoder_weights* w, const float
     M2_REQUIRE(w->up_w[j] && w->up_b[j] && w->res1_w[j] && w->res1_b[j] && w->res2_w[j] && w->res2_b[j],
                M2TTS_E_NULLPTR, "vocoder_forward: null weights in stage %d", j);
   cudaStream_t s = (cudaStream_t)stream;
+  static const int rates[4] = {4, 4, 2, 2};
   Carver cv(workspace, workspace_bytes);
-  const size_t act = (size_t)B * C * T * 4;
+  const size_t act = (size_t)2 * B * C * ((size_t)T + 4) * 4;   // floats; room for a hi/lo plane pair
   float* bufA = cv.take<float>(act);
   float* bufB = cv.take<float>(act);
   float* bufC = cv.take<float>(act);
-  // packed weights
+  // packed weights (FFMA layout [CI][3][CO]) and tensor-core weight images
   ConvPackJob jobs[9];
   float* in_wp = cv.take<float>((size_t)C * M * 3);
   jobs[0] = ConvPackJob{w->in_w, in_wp, C, M};
-  float* r1p[4]; float* r2p[4];
+  float *r1p[4], *r2p[4], *r1b[4], *r2b[4], *upb[4];
   for (int j = 0, c = C / 2; j < 4; ++j, c /= 2) {
     r1p[j] = cv.take<float>((size_t)c * c * 3);
     r2p[j] = cv.take<float>((size_t)c * c * 3);
+    r1b[j] = cv.take<float>(conv3_tc_wblob_floats(c, c));
+    r2b[j] = cv.take<float>(conv3_tc_wblob_floats(c, c));
+    upb[j] = cv.take<float>(convT_tc_wblob_floats(2 * c, c, rates[j]));
     jobs[1 + 2 * j] = ConvPackJob{w->res1_w[j], r1p[j], c, c};
     jobs[2 + 2 * j] = ConvPackJob{w->res2_w[j], r2p[j], c, c};
   }
@@ -487,27 +507,54 @@ extern "C" int m2tts_vocoder_forward(const m2tts_vocoder_weights* w, const float
   int rc = launch_conv_pack(jobs, 9, s);
   if (rc) return rc;
 
-  // input conv: mel (strided) -> bufA [B,C,T]
+  // Which stages run on the tensor cores: all three convolutions of the stage must qualify
+  // (wide early stages, >= 64 output channels); they always form a prefix of the stage list.
+  bool tc[5] = {false, false, false, false, false};
+  if (vocoder_mode() == 0) {
+    int c_in = C;
+    for (int j = 0; j < 4; ++j, c_in /= 2) {
+      const int c = c_in / 2;
+      const int dil = w->res_dilation[j] > 0 ? w->res_dilation[j] : 1;
+      tc[j] = (j == 0 || tc[j - 1]) && convT_tc_eligible(c_in, c, rates[j]) && conv3_tc_eligible(c, c) && dil >= 1;
+    }
+  }
+
+  // input conv: mel (strided) -> bufA, as hi/lo planes when stage 0 is a tensor-core stage
+  int L = T, c_in = C;
+  int Lp = (L + 3) & ~3;
   {
     ConvArgs a{mel, stride_b, stride_m, stride_t, in_wp, w->in_b, nullptr, bufA, M, C, T, 1, 0};
+    if (tc[0]) { a.y_lo = bufA + (size_t)B * C * Lp; a.y_pitch = Lp; }
     if ((rc = launch_conv3(a, B, M2TTS_STAGE_VOC_IN, s))) return rc;
   }
-  static const int rates[4] = {4, 4, 2, 2};
-  int L = T, c_in = C;
   for (int j = 0; j < 4; ++j) {
     const int r = rates[j], c = c_in / 2, Lo = L * r;
-    {  // bufB = lrelu(convT(bufA))
-      ConvArgs a{bufA, (long long)c_in * L, L, 1, w->up_w[j], w->up_b[j], nullptr, bufB, c_in, c, L, 1, 1};
-      if ((rc = launch_convT(a, B, r, s))) return rc;
-    }
     const int dil = w->res_dilation[j] > 0 ? w->res_dilation[j] : 1;
-    {  // bufC = lrelu(conv1(bufB))
-      ConvArgs a{bufB, (long long)c * Lo, Lo, 1, r1p[j], w->res1_b[j], nullptr, bufC, c, c, Lo, dil, 1};
-      if ((rc = launch_conv3(a, B, M2TTS_STAGE_VOC_RES1, s))) return rc;
-    }
-    {  // bufA = conv2(bufC) + bufB
-      ConvArgs a{bufC, (long long)c * Lo, Lo, 1, r2p[j], w->res2_b[j], bufB, bufA, c, c, Lo, 1, 0};
-      if ((rc = launch_conv3(a, B, M2TTS_STAGE_VOC_RES2, s))) return rc;
+    if (tc[j]) {
+      // planes in bufA (pitch Lp) -> up -> planes bufB -> conv1 -> planes bufC -> conv2 (+ residual bufB) -> bufA
+      const int Lpo = (Lo + 3) & ~3;
+      const size_t po = (size_t)B * c * Lpo;   // plane stride of this stage's tensors
+      if ((rc = launch_convT_tc(bufA, Lp, w->up_w[j], upb[j], w->up_b[j], bufB, bufB + po, Lpo, B, c_in, c, L, r, s))) return rc;
+      if ((rc = launch_conv3_tc(bufB, Lpo, w->res1_w[j], r1b[j], w->res1_b[j], nullptr, nullptr, 0, bufC, bufC + po, Lpo,
+                                B, c, c, Lo, dil, 1, M2TTS_STAGE_VOC_RES1, s))) return rc;
+      float* out_lo = tc[j + 1] ? bufA + po : nullptr;   // next stage on tensor cores -> planes, else plain fp32
+      const int out_pitch = tc[j + 1] ? Lpo : Lo;
+      if ((rc = launch_conv3_tc(bufC, Lpo, w->res2_w[j], r2b[j], w->res2_b[j], bufB, bufB + po, Lpo, bufA, out_lo, out_pitch,
+                                B, c, c, Lo, 1, 0, M2TTS_STAGE_VOC_RES2, s))) return rc;
+      Lp = Lpo;
+    } else {
+      {  // bufB = lrelu(convT(bufA))
+        ConvArgs a{bufA, (long long)c_in * L, L, 1, w->up_w[j], w->up_b[j], nullptr, bufB, c_in, c, L, 1, 1};
+        if ((rc = launch_convT(a, B, r, s))) return rc;
+      }
+      {  // bufC = lrelu(conv1(bufB))
+        ConvArgs a{bufB, (long long)c * Lo, Lo, 1, r1p[j], w->res1_b[j], nullptr, bufC, c, c, Lo, dil, 1};
+        if ((rc = launch_conv3(a, B, M2TTS_STAGE_VOC_RES1, s))) return rc;
+      }
+      {  // bufA = conv2(bufC) + bufB
+        ConvArgs a{bufC, (long long)c * Lo, Lo, 1, r2p[j], w->res2_b[j], bufB, bufA, c, c, Lo, 1, 0};
+        if ((rc = launch_conv3(a, B, M2TTS_STAGE_VOC_RES2, s))) return rc;
+      }
     }
     L = Lo; c_in = c;
   }

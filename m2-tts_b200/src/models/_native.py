@@ -55,6 +55,7 @@ _SIGNATURES = {
     "m2tts_stage_timing_enable": (C.c_int, [C.c_int]),
     "m2tts_stage_timing_read": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int), C.c_int]),
     "m2tts_set_attention_mode": (C.c_int, [C.c_int]),
+    "m2tts_set_vocoder_mode": (C.c_int, [C.c_int]),
     "m2tts_ffma_probe": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.c_void_p]),
     "m2tts_embed_posenc": (C.c_int, [C.c_void_p] * 6 + [C.c_int] * 4 + [C.c_void_p]),
     "m2tts_transformer_workspace_bytes": (C.c_size_t, [C.c_int] * 4),
@@ -78,6 +79,10 @@ _SIGNATURES = {
                                   C.c_void_p, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p, C.c_size_t,
                                                                               C.c_void_p]),
     "m2tts_conv_transpose1d_lrelu": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 5 + [C.c_void_p]),
+    "m2tts_conv_tc_workspace_bytes": (C.c_size_t, [C.c_int] * 5),
+    "m2tts_conv1d_k3_tc": (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 6 + [C.c_void_p, C.c_size_t, C.c_void_p]),
+    "m2tts_conv_transpose1d_lrelu_tc": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 5 + [C.c_void_p, C.c_size_t,
+                                                                                      C.c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -295,3 +295,57 @@ def test_attention_kernels_both_meet_fp32_tolerance(mode):
             assert H.max_abs(enc.cpu(), oracle.text_encoder(sd, ids, lengths, heads)[0]) <= FP32_TOL, (stage, "encoder")
     finally:
         lib.m2tts_set_attention_mode(0)
+
+
+# --------------------------------------------------------------------------- tensor-core vocoder convolutions
+def test_tensor_core_conv_entry_points():
+    from models import _native as nat
+    lib = nat.lib()
+    g = torch.Generator().manual_seed(31)
+    for (CI, CO, L, dil, act, with_res) in [(128, 128, 300, 1, 1, False), (64, 64, 517, 1, 0, True),
+                                            (16, 64, 130, 2, 0, False), (256, 128, 64, 1, 1, True)]:
+        x = torch.randn(2, CI, L, generator=g)
+        w = torch.randn(CO, CI, 3, generator=g) * (1.0 / (3 * CI) ** 0.5)
+        b = torch.randn(CO, generator=g)
+        r = torch.randn(2, CO, L, generator=g) if with_res else None
+        want = torch.nn.functional.conv1d(x, w, b, padding=dil, dilation=dil)
+        if act == 1:
+            want = torch.nn.functional.leaky_relu(want, 0.1)
+        if r is not None:
+            want = want + r
+        xd, wd, bd = x.to(DEV), w.to(DEV), b.to(DEV)
+        rd = r.to(DEV) if r is not None else None
+        y = torch.empty(2, CO, L, device=DEV)
+        ws = torch.empty(lib.m2tts_conv_tc_workspace_bytes(2, CI, CO, L, 1), dtype=torch.uint8, device=DEV)
+        rc = lib.m2tts_conv1d_k3_tc(xd.data_ptr(), wd.data_ptr(), bd.data_ptr(), nat.ptr(rd), y.data_ptr(),
+                                    2, CI, CO, L, dil, act, ws.data_ptr(), ws.numel(), None)
+        nat.check(rc, "conv1d_k3_tc")
+        assert H.max_abs(y.cpu(), want) <= FP32_TOL, ("conv3_tc", CI, CO, L, dil, act)
+    for (CI, CO, L) in [(256, 128, 77), (128, 64, 300), (32, 32, 129)]:
+        x = torch.randn(2, CI, L, generator=g)
+        w = torch.randn(CI, CO, 8, generator=g) * (1.0 / (2 * CI) ** 0.5)
+        b = torch.randn(CO, generator=g)
+        want = torch.nn.functional.leaky_relu(torch.nn.functional.conv_transpose1d(x, w, b, stride=4, padding=2), 0.1)
+        xd, wd, bd = x.to(DEV), w.to(DEV), b.to(DEV)
+        y = torch.empty(2, CO, 4 * L, device=DEV)
+        ws = torch.empty(lib.m2tts_conv_tc_workspace_bytes(2, CI, CO, L, 4), dtype=torch.uint8, device=DEV)
+        rc = lib.m2tts_conv_transpose1d_lrelu_tc(xd.data_ptr(), wd.data_ptr(), bd.data_ptr(), y.data_ptr(), 2, CI, CO, L, 4,
+                                                 ws.data_ptr(), ws.numel(), None)
+        nat.check(rc, "conv_transpose1d_lrelu_tc")
+        assert H.max_abs(y.cpu(), want) <= FP32_TOL, ("convT_tc", CI, CO, L)
+
+
+@pytest.mark.parametrize("mode", [0, 1])  # 0 = tcgen05 convs for the wide stages, 1 = FFMA everywhere
+def test_vocoder_modes_both_meet_fp32_tolerance(mode):
+    from models import _native as nat
+    lib = nat.lib()
+    try:
+        nat.check(lib.m2tts_set_vocoder_mode(mode), "set_vocoder_mode")
+        for stage, B, T in (("stage2", 2, 203), ("stage1", 3, 130)):
+            m = cuda_model(stage, perturb=6)
+            M = H.STAGE_KWARGS[stage]["mel_channels"]
+            mel = torch.randn(B, M, T, generator=torch.Generator().manual_seed(T))
+            got = m.vocoder(mel.to(DEV))
+            assert H.max_abs(got.cpu(), oracle.vocoder(cpu_sd(m), mel)) <= FP32_TOL, stage
+    finally:
+        lib.m2tts_set_vocoder_mode(0)
