@@ -114,6 +114,9 @@ uint64_t m2tts_launch_count(void);
  * the recorded events and returns summed milliseconds + launch counts. */
 int m2tts_stage_timing_enable(int on);
 int m2tts_stage_timing_read(float* ms_sum, int* launches, int n_stages);
+/* Diagnostics: the tensor-core kernels bound every mbarrier wait; on a timeout they store
+ * {code, chunk, blockIdx.x, blockIdx.y, blockIdx.z} in pinned host memory and trap. */
+int m2tts_debug_words(int* out, int n);
 /* Attention kernel selection for m2tts_transformer_layer: 0 (default) = tcgen05/TMEM tensor-core
  * kernel with 3xTF32 splitting when head_dim is one of {16,32,48,64}, else the fp32 FFMA kernel;
  * 1 = always the fp32 FFMA kernel. Process-wide; also settable with M2TTS_ATTENTION=ffma. */

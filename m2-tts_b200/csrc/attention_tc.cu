@@ -166,6 +166,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_co
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_v) : "memory");
   }
   if (warp == 0) {
+    __syncwarp();   // lane 0 just left the barrier-init branch; .sync.aligned needs the whole warp converged
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TC_TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -301,6 +302,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_co
     __syncwarp();
 
     mbar_wait(bar_o, par);
+    __syncwarp();
     tc_fence_after();
     if (tid == 0 && t + 1 < nkt) load_kv(sV, bar_v, 4, (t + 1) * TC_BK);  // V buffer is free: PV(t) committed
     __syncwarp();

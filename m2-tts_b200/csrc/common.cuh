@@ -132,6 +132,7 @@ int launch_attention(const float* q, const float* k, const float* v, float* ctx,
 bool attention_tc_supported(int hd);
 int launch_attention_tc(const float* qkv6, float* ctx, const int64_t* lengths, int B, int L, int Lp,
                         int nh, int hd, cudaStream_t s, float* dbg_s = nullptr, float* dbg_o = nullptr);
+int* debug_words_device();  // pinned mapped scratch for hang diagnostics (may be null)
 int attention_mode();  // 0 = tensor cores when supported, 1 = force the FFMA kernel
 int vocoder_mode();    // 0 = tensor-core convolutions for the wide stages, 1 = FFMA everywhere
 

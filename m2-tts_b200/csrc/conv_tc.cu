@@ -21,15 +21,18 @@
 #include "common.cuh"
 #include <cuda.h>
 #include <math.h>
+#include <stdlib.h>
 
 namespace m2 {
 
-constexpr int CT_BM = 128;            // output positions (GEMM rows) per CTA
+constexpr int CT_BM = 128;            // GEMM rows (input positions) per CTA, including the halo
+constexpr int CT_HALO = 4;            // rows on each side that are computed but not stored (|tap shift| <= 4)
+constexpr int CT_STEP = CT_BM - 2 * CT_HALO;   // 120 output positions per CTA; tile starts stay 16-B aligned for TMA
 constexpr int CT_CK = 16;             // input channels per pipeline chunk
-constexpr int CT_STAGES = 2;
+constexpr int CT_STAGES = 3;
 constexpr int CT_THREADS = 128;
 constexpr uint32_t CT_ABOX = CT_CK * 128;                        // one TMA box: 16 rows x 128 B
-constexpr uint32_t CT_A_STAGE = 2u * 3u * 4u * CT_ABOX;          // planes x taps x boxes = 48 KB
+constexpr uint32_t CT_A_STAGE = 2u * 4u * CT_ABOX;               // planes x boxes = 16 KB
 
 struct TapGemmArgs {
   int CI, L_in, B, n_chunks;
@@ -54,15 +57,21 @@ __device__ __forceinline__ void ct_mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void ct_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void ct_wait(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ void ct_wait(uint32_t bar, uint32_t parity, int* dbg, int code, int chunk) {
   for (uint32_t it = 0; it < (1u << 24); ++it) {
     uint32_t ok;
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     if (ok) return;
   }
+  if (dbg != nullptr) {
+    dbg[0] = code; dbg[1] = chunk; dbg[2] = blockIdx.x; dbg[3] = blockIdx.y; dbg[4] = blockIdx.z; dbg[5] = threadIdx.x;
+    __threadfence_system();
+  }
   __trap();
 }
+// NOTE: with 4-byte elements the innermost TMA coordinate must be a multiple of 4 (16-byte aligned box rows);
+// an unaligned coordinate raises "illegal instruction" — which is why the taps shift OUTPUT rows, not input boxes.
 __device__ __forceinline__ void ct_tma_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
@@ -89,10 +98,13 @@ __device__ __forceinline__ void ct_ld8(uint32_t taddr, uint32_t* r) {
 }
 __device__ __forceinline__ float ct_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
 
+// D_tap[m, n] = sum_ci X[ci, start + m] * W_tap[n, ci] for the three taps (separate TMEM column ranges);
+// the epilogue forms out[t] = sum_tap D_tap[t - start + shift_tap] through a shared-memory staging tile.
 __global__ void __launch_bounds__(CT_THREADS, 1)
-tapgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const TapGemmArgs a) {
+tapgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const TapGemmArgs a, int* dbg) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (ct_smem_u32(smem_raw) + 1023u) & ~1023u;
+  float* stage_f = reinterpret_cast<float*>(smem_raw + (sbase - ct_smem_u32(smem_raw)));   // epilogue staging (reuses the ring)
   const uint32_t w_plane_bytes = (uint32_t)a.rows_total * 64u;
   const uint32_t w_stage = 2u * w_plane_bytes;
   const uint32_t stage_bytes = CT_A_STAGE + ((w_stage + 1023u) & ~1023u);
@@ -101,7 +113,8 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const TapGemmArgs a) 
   const uint32_t tmem_slot = bar_acc + 8;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int m0 = blockIdx.x * CT_BM, ntile = blockIdx.y, b = blockIdx.z;
+  const int start = blockIdx.x * CT_STEP - CT_HALO;   // first input position of this tile (multiple of 4)
+  const int ntile = blockIdx.y, b = blockIdx.z;
 
   if (tid == 0) {
     for (int s = 0; s < CT_STAGES; ++s) { ct_mbar_init(bar_full + 8 * s, 1); ct_mbar_init(bar_empty + 8 * s, 1); }
@@ -110,6 +123,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const TapGemmArgs a) 
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
   }
   if (warp == 0) {
+    __syncwarp();   // lane 0 just left the barrier-init branch; .sync.aligned needs the whole warp converged
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)a.tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -120,21 +134,19 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const TapGemmArgs a) 
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   if (warp == 0 && lane == 0) {
-    // ===== producer: TMA boxes of the three shifted activation tiles + one bulk copy of the weight image =====
+    // ===== producer: 8 TMA boxes (hi/lo x 4 x 32 positions) + one bulk copy of the weight image per chunk =====
     const float* wsrc = a.wblob + (size_t)ntile * a.n_chunks * (size_t)(2 * a.rows_total * 16);
     for (int c = 0; c < a.n_chunks; ++c) {
       const int s = c % CT_STAGES;
-      if (c >= CT_STAGES) ct_wait(bar_empty + 8 * s, (uint32_t)((c / CT_STAGES - 1) & 1));
+      if (c >= CT_STAGES) ct_wait(bar_empty + 8 * s, (uint32_t)((c / CT_STAGES - 1) & 1), dbg, 1, c);
       const uint32_t sA = sbase + s * stage_bytes, sW = sA + CT_A_STAGE, full = bar_full + 8 * s;
       ct_expect_tx(full, CT_A_STAGE + w_stage);
 #pragma unroll
       for (int plane = 0; plane < 2; ++plane) {
         const int row = (plane * a.B + b) * a.CI + c * CT_CK;
 #pragma unroll
-        for (int tap = 0; tap < 3; ++tap)
-#pragma unroll
-          for (int x = 0; x < 4; ++x)
-            ct_tma_2d(sA + (uint32_t)((plane * 3 + tap) * 4 + x) * CT_ABOX, &tmap_a, m0 + a.tap_shift[tap] + 32 * x, row, full);
+        for (int x = 0; x < 4; ++x)
+          ct_tma_2d(sA + (uint32_t)(plane * 4 + x) * CT_ABOX, &tmap_a, start + 32 * x, row, full);
       }
       ct_bulk(sW, wsrc + (size_t)c * (2 * a.rows_total * 16), w_stage, full);
     }
@@ -142,7 +154,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const TapGemmArgs a) 
     // ===== UMMA issuer =====
     for (int c = 0; c < a.n_chunks; ++c) {
       const int s = c % CT_STAGES;
-      ct_wait(bar_full + 8 * s, (uint32_t)((c / CT_STAGES) & 1));
+      ct_wait(bar_full + 8 * s, (uint32_t)((c / CT_STAGES) & 1), dbg, 2, c);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t sA = sbase + s * stage_bytes, sW = sA + CT_A_STAGE;
 #pragma unroll
@@ -155,10 +167,9 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const TapGemmArgs a) 
           const uint32_t ap = (term == 2) ? 1u : 0u, wp = (term == 1) ? 1u : 0u;
 #pragma unroll
           for (int ks = 0; ks < CT_CK / 8; ++ks) {
-            const uint64_t ad = ct_desc(sA + ((ap * 3 + tap) * 4) * CT_ABOX + ks * 1024u, CT_ABOX, 512u, 1u);
+            const uint64_t ad = ct_desc(sA + (ap * 4) * CT_ABOX + ks * 1024u, CT_ABOX, 512u, 1u);
             const uint64_t bd = ct_desc(sW + wp * w_plane_bytes + wrow_off + ks * 256u, 128u, 512u, 0u);
-            const uint32_t acc = (c | tap | term | ks) ? 1u : 0u;   // tap 0 spans every accumulator column
-            ct_mma(tmem_base + (uint32_t)a.tap_dcol[tap], ad, bd, idesc, acc);
+            ct_mma(tmem_base + (uint32_t)a.tap_dcol[tap], ad, bd, idesc, (c | term | ks) ? 1u : 0u);
           }
         }
       }
@@ -168,24 +179,36 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const TapGemmArgs a) 
   }
   __syncwarp();
 
-  // ===== epilogue: thread = GEMM row = input position q =====
-  ct_wait(bar_acc, 0);
+  // ===== epilogue: thread = GEMM row m = input position start + m =====
+  ct_wait(bar_acc, 0, dbg, 3, 0);
+  __syncwarp();     // threads leave the polling loop one by one; tcgen05.ld is .sync.aligned
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const int q = m0 + tid;
-  const bool valid = q < a.L_in;
+  const int m = tid;
+  const int q = start + m;
+  const bool own = (m >= CT_HALO) && (m < CT_BM - CT_HALO) && (q < a.L_in);
   const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
   const int co0 = ntile * a.co_tile;
 
   if (a.r == 1) {
-    for (int c0 = 0; c0 < a.n_cols; c0 += 8) {
-      uint32_t v[8];
-      ct_ld8(t_lane + c0, v);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (valid) {
+    // staging tile S[tap][32 cols][128 rows]
+    const int s0 = a.tap_shift[0], s1 = a.tap_shift[1], s2 = a.tap_shift[2];
+    for (int c0 = 0; c0 < a.co_tile; c0 += 32) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int co = co0 + c0 + j;
-          float x = __uint_as_float(v[j]) + __ldg(a.bias + co);
+      for (int tap = 0; tap < 3; ++tap)
+#pragma unroll
+        for (int cc = 0; cc < 32; cc += 8) {
+          uint32_t v[8];
+          ct_ld8(t_lane + (uint32_t)(a.tap_dcol[tap] + c0 + cc), v);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 8; ++j) stage_f[((tap * 32 + cc + j) << 7) + m] = __uint_as_float(v[j]);
+        }
+      __syncthreads();
+      if (own) {
+        for (int c = 0; c < 32; ++c) {
+          const int co = co0 + c0 + c;
+          float x = stage_f[((c) << 7) + m + s0] + stage_f[((32 + c) << 7) + m + s1] + stage_f[((64 + c) << 7) + m + s2] +
+                    __ldg(a.bias + co);
           if (a.act == 1) x = x > 0.f ? x : 0.1f * x;
           if (a.res_hi != nullptr) {
             const size_t ro = ((size_t)b * a.CO + co) * a.Lp_res + q;
@@ -196,15 +219,25 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const TapGemmArgs a) 
           else a.out_hi[oo] = x;
         }
       }
+      __syncthreads();
     }
   } else {
-    // transposed conv: columns are (phase p, channel c); gather the r phases of a channel and store r samples
-    for (int c0 = 0; c0 < a.co_tile; c0 += 8) {
-      uint32_t v[4][8];   // r == 4 (convT_tc_eligible)
+    // transposed conv (r == 4): accumulator columns D0 [0,4ct) = (phase, channel), D1 [4ct,6ct) phases 0-1 (needs row q-1),
+    // D2 [6ct,8ct) phases 2-3 (needs row q+1). Staging tile S[64][128]: 0-31 D0 (p*8+j), 32-47 D1, 48-63 D2.
+    const int ct = a.co_tile;
+    for (int c0 = 0; c0 < ct; c0 += 8) {
 #pragma unroll
-      for (int p = 0; p < 4; ++p) ct_ld8(t_lane + p * a.co_tile + c0, v[p]);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (valid) {
+      for (int g = 0; g < 8; ++g) {
+        // g 0..3: D0 phase g; 4..5: D1 phase g-4; 6..7: D2 phase g-6 (+2)
+        const int col = (g < 4) ? g * ct : (g < 6 ? 4 * ct + (g - 4) * ct : 6 * ct + (g - 6) * ct);
+        uint32_t v[8];
+        ct_ld8(t_lane + (uint32_t)(col + c0), v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 8; ++j) stage_f[((g * 8 + j) << 7) + m] = __uint_as_float(v[j]);
+      }
+      __syncthreads();
+      if (own) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int co = co0 + c0 + j;
@@ -212,23 +245,23 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const TapGemmArgs a) 
           float x[4];
 #pragma unroll
           for (int p = 0; p < 4; ++p) {
-            const float t = __uint_as_float(v[p][j]) + bv;
+            float t = stage_f[((p * 8 + j) << 7) + m] + bv;
+            t += (p < 2) ? stage_f[(((4 + p) * 8 + j) << 7) + m - 1] : stage_f[(((6 + p - 2) * 8 + j) << 7) + m + 1];
             x[p] = t > 0.f ? t : 0.1f * t;
           }
           const size_t oo = ((size_t)b * a.CO + co) * a.Lp_out + (size_t)4 * q;
-          {
-            if (a.out_lo != nullptr) {
-              float h[4], l[4];
+          if (a.out_lo != nullptr) {
+            float h[4], l[4];
 #pragma unroll
-              for (int p = 0; p < 4; ++p) { h[p] = ct_hi(x[p]); l[p] = ct_hi(x[p] - h[p]); }
-              *reinterpret_cast<float4*>(a.out_hi + oo) = make_float4(h[0], h[1], h[2], h[3]);
-              *reinterpret_cast<float4*>(a.out_lo + oo) = make_float4(l[0], l[1], l[2], l[3]);
-            } else {
-              *reinterpret_cast<float4*>(a.out_hi + oo) = make_float4(x[0], x[1], x[2], x[3]);
-            }
+            for (int p = 0; p < 4; ++p) { h[p] = ct_hi(x[p]); l[p] = ct_hi(x[p] - h[p]); }
+            *reinterpret_cast<float4*>(a.out_hi + oo) = make_float4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<float4*>(a.out_lo + oo) = make_float4(l[0], l[1], l[2], l[3]);
+          } else {
+            *reinterpret_cast<float4*>(a.out_hi + oo) = make_float4(x[0], x[1], x[2], x[3]);
           }
         }
       }
+      __syncthreads();
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -303,7 +336,7 @@ static EncodeTiledFn2 ct_encode_fn() {
 
 static int next_pow2_cols(int n) { int c = 32; while (c < n) c <<= 1; return c; }
 
-bool conv3_tc_eligible(int CI, int CO) { return CI % CT_CK == 0 && CO % 64 == 0 && CO >= 64; }
+bool conv3_tc_eligible(int CI, int CO) { return CI % CT_CK == 0 && CO % 64 == 0 && CO >= 64; }  // and dilation <= 4 (checked at launch)
 bool convT_tc_eligible(int CI, int CO, int r) { return r == 4 && CI % CT_CK == 0 && CO % 32 == 0 && CO >= 32; }
 size_t conv3_tc_wblob_floats(int CI, int CO) { return (size_t)2 * 3 * CO * CI; }
 size_t convT_tc_wblob_floats(int CI, int CO, int r) { return (size_t)2 * 2 * r * CO * CI; }
@@ -326,8 +359,10 @@ static int launch_tapgemm(const float* x_planes, int Lp_in, TapGemmArgs& a, int 
   const size_t smem = (size_t)CT_STAGES * (CT_A_STAGE + ((w_stage + 1023u) & ~1023u)) + 1024 + 128;
   M2_REQUIRE(smem <= 227 * 1024, M2TTS_E_UNSUPPORTED, "conv_tc: tile needs %zu B of shared memory", smem);
   M2_CUDA_OK(allow_smem(tapgemm_kernel, smem));
-  dim3 grid(ceil_div(a.L_in, CT_BM), n_tiles, a.B);
-  M2_LAUNCH(stage, tapgemm_kernel, grid, CT_THREADS, smem, s, tmap, a);
+  for (int j = 0; j < 3; ++j)
+    M2_REQUIRE(a.tap_shift[j] >= -CT_HALO && a.tap_shift[j] <= CT_HALO, M2TTS_E_UNSUPPORTED, "conv_tc: tap shift %d exceeds the halo", a.tap_shift[j]);
+  dim3 grid(ceil_div(a.L_in, CT_STEP), n_tiles, a.B);
+  M2_LAUNCH(stage, tapgemm_kernel, grid, CT_THREADS, smem, s, tmap, a, debug_words_device());
   return M2TTS_OK;
 }
 
@@ -350,8 +385,8 @@ int launch_conv3_tc(const float* x_planes, int Lp_in, const float* w, float* wbl
   if (rc) return rc;
   TapGemmArgs a{};
   a.CI = CI; a.L_in = L; a.B = B; a.n_chunks = CI / CT_CK;
-  for (int j = 0; j < 3; ++j) { a.tap_shift[j] = (j - 1) * dil; a.tap_rows[j] = ct; a.tap_wrow[j] = j * ct; a.tap_dcol[j] = 0; }
-  a.rows_total = 3 * ct; a.n_cols = ct; a.wblob = wblob; a.r = 1; a.co_tile = ct; a.CO = CO; a.L_out = L; a.Lp_out = Lp_out;
+  for (int j = 0; j < 3; ++j) { a.tap_shift[j] = (j - 1) * dil; a.tap_rows[j] = ct; a.tap_wrow[j] = j * ct; a.tap_dcol[j] = j * ct; }
+  a.rows_total = 3 * ct; a.n_cols = 3 * ct; a.wblob = wblob; a.r = 1; a.co_tile = ct; a.CO = CO; a.L_out = L; a.Lp_out = Lp_out;
   a.bias = bias; a.act = act; a.res_hi = res_hi; a.res_lo = res_lo; a.Lp_res = Lp_res; a.out_hi = out_hi; a.out_lo = out_lo;
   return launch_tapgemm(x_planes, Lp_in, a, n_tiles, stage, s);
 }
@@ -367,9 +402,9 @@ int launch_convT_tc(const float* x_planes, int Lp_in, const float* w, float* wbl
   TapGemmArgs a{};
   a.CI = CI; a.L_in = L; a.B = B; a.n_chunks = CI / CT_CK;
   a.tap_shift[0] = 0;  a.tap_rows[0] = r * ct;       a.tap_wrow[0] = 0;                        a.tap_dcol[0] = 0;
-  a.tap_shift[1] = -1; a.tap_rows[1] = (r / 2) * ct; a.tap_wrow[1] = r * ct;                   a.tap_dcol[1] = 0;
-  a.tap_shift[2] = 1;  a.tap_rows[2] = (r / 2) * ct; a.tap_wrow[2] = r * ct + (r / 2) * ct;    a.tap_dcol[2] = (r / 2) * ct;
-  a.rows_total = 2 * r * ct; a.n_cols = r * ct; a.wblob = wblob; a.r = r; a.co_tile = ct; a.CO = CO;
+  a.tap_shift[1] = -1; a.tap_rows[1] = (r / 2) * ct; a.tap_wrow[1] = r * ct;                   a.tap_dcol[1] = r * ct;
+  a.tap_shift[2] = 1;  a.tap_rows[2] = (r / 2) * ct; a.tap_wrow[2] = r * ct + (r / 2) * ct;    a.tap_dcol[2] = r * ct + (r / 2) * ct;
+  a.rows_total = 2 * r * ct; a.n_cols = 2 * r * ct; a.wblob = wblob; a.r = r; a.co_tile = ct; a.CO = CO;
   a.L_out = r * L; a.Lp_out = Lp_out; a.bias = bias; a.act = 1; a.out_hi = out_hi; a.out_lo = out_lo;
   return launch_tapgemm(x_planes, Lp_in, a, n_tiles, M2TTS_STAGE_VOC_UP, s);
 }

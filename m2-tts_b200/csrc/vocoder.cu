@@ -515,7 +515,7 @@ extern "C" int m2tts_vocoder_forward(const m2tts_vocoder_weights* w, const float
     for (int j = 0; j < 4; ++j, c_in /= 2) {
       const int c = c_in / 2;
       const int dil = w->res_dilation[j] > 0 ? w->res_dilation[j] : 1;
-      tc[j] = (j == 0 || tc[j - 1]) && convT_tc_eligible(c_in, c, rates[j]) && conv3_tc_eligible(c, c) && dil >= 1;
+      tc[j] = (j == 0 || tc[j - 1]) && convT_tc_eligible(c_in, c, rates[j]) && conv3_tc_eligible(c, c) && dil <= 4;
     }
   }
 

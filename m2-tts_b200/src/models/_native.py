@@ -54,6 +54,7 @@ _SIGNATURES = {
     "m2tts_launch_count": (C.c_uint64, []),
     "m2tts_stage_timing_enable": (C.c_int, [C.c_int]),
     "m2tts_stage_timing_read": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int), C.c_int]),
+    "m2tts_debug_words": (C.c_int, [C.POINTER(C.c_int), C.c_int]),
     "m2tts_set_attention_mode": (C.c_int, [C.c_int]),
     "m2tts_set_vocoder_mode": (C.c_int, [C.c_int]),
     "m2tts_ffma_probe": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.c_void_p]),
