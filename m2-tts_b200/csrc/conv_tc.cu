@@ -205,15 +205,24 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const TapGemmArgs a, 
         }
       __syncthreads();
       if (own) {
+        // residual loads first (read-only path, independent of the stores below) so their latency overlaps
+        float rsd[32];
+        if (a.res_hi != nullptr) {
+          const float* __restrict__ rh = a.res_hi + ((size_t)b * a.CO + co0 + c0) * a.Lp_res + q;
+          const float* __restrict__ rl = a.res_lo + ((size_t)b * a.CO + co0 + c0) * a.Lp_res + q;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) rsd[c] = __ldg(rh + (size_t)c * a.Lp_res) + __ldg(rl + (size_t)c * a.Lp_res);
+        } else {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) rsd[c] = 0.f;
+        }
+#pragma unroll
         for (int c = 0; c < 32; ++c) {
           const int co = co0 + c0 + c;
           float x = stage_f[((c) << 7) + m + s0] + stage_f[((32 + c) << 7) + m + s1] + stage_f[((64 + c) << 7) + m + s2] +
                     __ldg(a.bias + co);
           if (a.act == 1) x = x > 0.f ? x : 0.1f * x;
-          if (a.res_hi != nullptr) {
-            const size_t ro = ((size_t)b * a.CO + co) * a.Lp_res + q;
-            x += a.res_hi[ro] + a.res_lo[ro];
-          }
+          x += rsd[c];
           const size_t oo = ((size_t)b * a.CO + co) * a.Lp_out + q;
           if (a.out_lo != nullptr) { const float h = ct_hi(x); a.out_hi[oo] = h; a.out_lo[oo] = ct_hi(x - h); }
           else a.out_hi[oo] = x;
