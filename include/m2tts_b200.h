@@ -159,6 +159,8 @@ int m2tts_layernorm(const float* x, const float* w, const float* b, float* y,
 /* y[rows,N] = LayerNorm(x) @ W^T + bias (tts_model.py:223-226: decoder.norm then
  * mel_projection, W [N,H]). workspace: m2tts_ln_proj_workspace_bytes(H,N). */
 size_t m2tts_ln_proj_workspace_bytes(int H, int N);
+/* workspace that additionally lets the call run on the tensor cores (normalised rows as hi/lo planes) */
+size_t m2tts_ln_proj_rows_workspace_bytes(int rows, int H, int N);
 int m2tts_layernorm_proj(const float* x, const float* ln_w, const float* ln_b,
                          const float* W, const float* bias, float* y, int rows,
                          int H, int N, float eps, void* workspace,

@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_constant__ CUtensorMap tmap_v,
                     float* __restrict__ ctx,
                     const int64_t* __restrict__ lengths, int B, int L, int nh,
-                    float* __restrict__ dbg_s, float* __restrict__ dbg_o) {
+                    float* __restrict__ dbg_s, float* __restrict__ dbg_o, float* __restrict__ ctx_lo) {
   static_assert(HD % 16 == 0 && HD >= 16 && HD <= 64, "tensor-core path: head_dim in {16,32,48,64}");
   constexpr uint32_t BOX = TcSmem<HD>::box_bytes;
   constexpr int QBOX = TC_BQ / TC_BOX, KBOX = TC_BK / TC_BOX;  // 4, 2
@@ -325,9 +325,21 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_co
   if (qi < L) {
     const float inv = 1.0f / l_run;
     float* dst = ctx + ((long long)b * L + qi) * (nh * HD) + head * HD;
+    if (ctx_lo == nullptr) {
 #pragma unroll
-    for (int c = 0; c < HD; c += 4)
-      *reinterpret_cast<float4*>(dst + c) = make_float4(o[c] * inv, o[c + 1] * inv, o[c + 2] * inv, o[c + 3] * inv);
+      for (int c = 0; c < HD; c += 4)
+        *reinterpret_cast<float4*>(dst + c) = make_float4(o[c] * inv, o[c + 1] * inv, o[c + 2] * inv, o[c + 3] * inv);
+    } else {   // hi/lo planes for the tensor-core out_proj
+      float* dlo = ctx_lo + ((long long)b * L + qi) * (nh * HD) + head * HD;
+#pragma unroll
+      for (int c = 0; c < HD; c += 4) {
+        float h[4], l[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { const float v = o[c + e] * inv; h[e] = __uint_as_float(tf32_hi(v)); l[e] = __uint_as_float(tf32_hi(v - h[e])); }
+        *reinterpret_cast<float4*>(dst + c) = make_float4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<float4*>(dlo + c) = make_float4(l[0], l[1], l[2], l[3]);
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -355,11 +367,11 @@ static EncodeTiledFn get_encode_fn() {
 
 template <int HD>
 static int launch_tc_hd(const CUtensorMap& tmap_qk, const CUtensorMap& tmap_v, float* ctx, const int64_t* lengths, int B, int L, int nh,
-                        cudaStream_t s, float* dbg_s, float* dbg_o) {
+                        cudaStream_t s, float* dbg_s, float* dbg_o, float* ctx_lo) {
   const size_t smem = TcSmem<HD>::total;
   M2_CUDA_OK(allow_smem(attention_tc_kernel<HD>, smem));
   dim3 grid(ceil_div(L, TC_BQ), nh, B);
-  M2_LAUNCH(M2TTS_STAGE_ATTENTION, attention_tc_kernel<HD>, grid, TC_THREADS, smem, s, tmap_qk, tmap_v, ctx, lengths, B, L, nh, dbg_s, dbg_o);
+  M2_LAUNCH(M2TTS_STAGE_ATTENTION, attention_tc_kernel<HD>, grid, TC_THREADS, smem, s, tmap_qk, tmap_v, ctx, lengths, B, L, nh, dbg_s, dbg_o, ctx_lo);
   return M2TTS_OK;
 }
 
@@ -367,7 +379,7 @@ bool attention_tc_supported(int hd) { return hd == 16 || hd == 32 || hd == 48 ||
 
 // qkv6: [6][B][nh][hd][Lp] fp32 (Q_hi,Q_lo,K_hi,K_lo,V_hi,V_lo), Q pre-scaled by scale*log2e.
 int launch_attention_tc(const float* qkv6, float* ctx, const int64_t* lengths, int B, int L, int Lp, int nh,
-                        int hd, cudaStream_t s, float* dbg_s, float* dbg_o) {
+                        int hd, cudaStream_t s, float* dbg_s, float* dbg_o, float* ctx_lo) {
   M2_REQUIRE(qkv6 && ctx, M2TTS_E_NULLPTR, "attention_tc: null pointer");
   M2_REQUIRE(attention_tc_supported(hd), M2TTS_E_UNSUPPORTED, "attention_tc: head_dim %d unsupported", hd);
   M2_REQUIRE(B > 0 && L > 0 && nh > 0 && B <= 65535 && nh <= 65535 && (Lp & 3) == 0 && Lp >= L, M2TTS_E_BADSHAPE,
@@ -390,10 +402,10 @@ int launch_attention_tc(const float* qkv6, float* ctx, const int64_t* lengths, i
           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   M2_REQUIRE(r == CUDA_SUCCESS, M2TTS_E_CUDA, "attention_tc: cuTensorMapEncodeTiled (v) failed (%d)", (int)r);
   switch (hd) {
-    case 16: return launch_tc_hd<16>(tmap_qk, tmap_v, ctx, lengths, B, L, nh, s, dbg_s, dbg_o);
-    case 32: return launch_tc_hd<32>(tmap_qk, tmap_v, ctx, lengths, B, L, nh, s, dbg_s, dbg_o);
-    case 48: return launch_tc_hd<48>(tmap_qk, tmap_v, ctx, lengths, B, L, nh, s, dbg_s, dbg_o);
-    default: return launch_tc_hd<64>(tmap_qk, tmap_v, ctx, lengths, B, L, nh, s, dbg_s, dbg_o);
+    case 16: return launch_tc_hd<16>(tmap_qk, tmap_v, ctx, lengths, B, L, nh, s, dbg_s, dbg_o, ctx_lo);
+    case 32: return launch_tc_hd<32>(tmap_qk, tmap_v, ctx, lengths, B, L, nh, s, dbg_s, dbg_o, ctx_lo);
+    case 48: return launch_tc_hd<48>(tmap_qk, tmap_v, ctx, lengths, B, L, nh, s, dbg_s, dbg_o, ctx_lo);
+    default: return launch_tc_hd<64>(tmap_qk, tmap_v, ctx, lengths, B, L, nh, s, dbg_s, dbg_o, ctx_lo);
   }
 }
 

@@ -131,7 +131,26 @@ int launch_attention(const float* q, const float* k, const float* v, float* ctx,
                      cudaStream_t s);
 bool attention_tc_supported(int hd);
 int launch_attention_tc(const float* qkv6, float* ctx, const int64_t* lengths, int B, int L, int Lp,
-                        int nh, int hd, cudaStream_t s, float* dbg_s = nullptr, float* dbg_o = nullptr);
+                        int nh, int hd, cudaStream_t s, float* dbg_s = nullptr, float* dbg_o = nullptr,
+                        float* ctx_lo = nullptr);  // ctx_lo != null: write ctx as TF32 hi/lo planes (ctx = hi plane)
+// ---- tensor-core linear layers (rowgemm_tc.cu) ----
+struct LinTcArgs {
+  int R, L, K, N, n_tile;          // rows total, rows per utterance, inner dim, outputs, outputs per CTA
+  int kboxes;                      // 32-column boxes resident per pass (set by the launcher)
+  const float* bias;               // [N] or null
+  int relu;
+  const float* residual; int ldr;  // plain fp32 [R, ldr] or null
+  float* y; int ldy;               // plain output [R, ldy] (mode 0)
+  float* y_planes;                 // mode 1: hi/lo planes [2][R][N]
+  // mode 2: attention operand planes [6][B][nh][hd][Lp]
+  float* qkv6; long long plane_stride; int nh, hd, Lp; float qscale;
+  int mode;
+};
+
+bool linear_tc_eligible(int K, int N);
+int launch_ln_split(const float* x, const float* w, const float* b, float* planes, long long R, int K, float eps, cudaStream_t s);
+int launch_w_split(const float* const* src, float* const* dst, const long long* n, int jobs, cudaStream_t s);
+int launch_linear_tc(const float* a_planes, const float* w_planes, LinTcArgs a, int B, int stage, cudaStream_t s);
 int* debug_words_device();  // pinned mapped scratch for hang diagnostics (may be null)
 int attention_mode();  // 0 = tensor cores when supported, 1 = force the FFMA kernel
 int vocoder_mode();    // 0 = tensor-core convolutions for the wide stages, 1 = FFMA everywhere

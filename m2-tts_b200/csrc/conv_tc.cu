@@ -29,7 +29,7 @@ constexpr int CT_BM = 128;            // GEMM rows (input positions) per CTA, in
 constexpr int CT_HALO = 4;            // rows on each side that are computed but not stored (|tap shift| <= 4)
 constexpr int CT_STEP = CT_BM - 2 * CT_HALO;   // 120 output positions per CTA; tile starts stay 16-B aligned for TMA
 constexpr int CT_CK = 16;             // input channels per pipeline chunk
-constexpr int CT_STAGES = 3;
+constexpr int CT_STAGES = 2;             // 2 x (16 KB activations + <= 32 KB weights): two CTAs per SM overlap each other's epilogue
 constexpr int CT_THREADS = 128;
 constexpr uint32_t CT_ABOX = CT_CK * 128;                        // one TMA box: 16 rows x 128 B
 constexpr uint32_t CT_A_STAGE = 2u * 4u * CT_ABOX;               // planes x boxes = 16 KB
@@ -100,7 +100,7 @@ __device__ __forceinline__ float ct_hi(float v) { return __uint_as_float(__float
 
 // D_tap[m, n] = sum_ci X[ci, start + m] * W_tap[n, ci] for the three taps (separate TMEM column ranges);
 // the epilogue forms out[t] = sum_tap D_tap[t - start + shift_tap] through a shared-memory staging tile.
-__global__ void __launch_bounds__(CT_THREADS, 1)
+__global__ void __launch_bounds__(CT_THREADS, 2)
 tapgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const TapGemmArgs a, int* dbg) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (ct_smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -388,7 +388,7 @@ int launch_conv3_tc(const float* x_planes, int Lp_in, const float* w, float* wbl
                     const float* res_hi, const float* res_lo, int Lp_res, float* out_hi, float* out_lo, int Lp_out,
                     int B, int CI, int CO, int L, int dil, int act, int stage, cudaStream_t s) {
   M2_REQUIRE(conv3_tc_eligible(CI, CO), M2TTS_E_UNSUPPORTED, "conv3_tc: CI=%d CO=%d not eligible", CI, CO);
-  const int ct = (CO % 128 == 0) ? 128 : 64, n_tiles = CO / ct;
+  const int ct = 64, n_tiles = CO / ct;   // 192 accumulator columns -> 256 TMEM columns per CTA, two CTAs per SM
   WPackArgs p{w, wblob, 0, CI, CO, 1, ct, 3 * ct, CI / CT_CK, n_tiles};
   int rc = launch_wpack(p, s);
   if (rc) return rc;

@@ -12,6 +12,8 @@ namespace {
 struct LayerWs {
   float *wqkv_t, *wo_t, *w1_t, *w2_t;  // packed W^T
   float *q, *k, *v, *ctx, *x1, *hid;
+  float *w_planes[4];   // tensor-core path: hi/lo planes of qkv / out_proj / ffn1 / ffn2 weights
+  float *xn;            // tensor-core path: LayerNorm output as hi/lo planes [2][R][H]
   int Lp;
 };
 
@@ -27,9 +29,14 @@ bool carve_layer(void* ws, size_t bytes, int B, int L, int H, int F, LayerWs* o)
   o->q = cv.take<float>((size_t)6 * B * H * Lp);
   o->k = o->q + (size_t)B * H * Lp;
   o->v = o->k + (size_t)B * H * Lp;
-  o->ctx = cv.take<float>((size_t)B * L * H);
+  o->ctx = cv.take<float>((size_t)2 * B * L * H);   // plain [R,H] or hi/lo planes
   o->x1 = cv.take<float>((size_t)B * L * H);
-  o->hid = cv.take<float>((size_t)B * L * F);
+  o->hid = cv.take<float>((size_t)2 * B * L * F);   // plain [R,F] or hi/lo planes
+  o->xn = cv.take<float>((size_t)2 * B * L * H);
+  o->w_planes[0] = cv.take<float>((size_t)2 * 3 * H * H);
+  o->w_planes[1] = cv.take<float>((size_t)2 * H * H);
+  o->w_planes[2] = cv.take<float>((size_t)2 * F * H);
+  o->w_planes[3] = cv.take<float>((size_t)2 * H * F);
   return cv.ok();
 }
 }  // namespace
@@ -37,9 +44,9 @@ bool carve_layer(void* ws, size_t bytes, int B, int L, int H, int F, LayerWs* o)
 extern "C" size_t m2tts_transformer_workspace_bytes(int B, int L, int H, int F) {
   if (B <= 0 || L <= 0 || H <= 0 || F <= 0) return 0;
   const size_t Lp = (size_t)((L + 3) & ~3);
-  size_t fl = (size_t)H * 3 * H + (size_t)H * H + 2 * (size_t)H * F + 6 * (size_t)B * H * Lp +
-              2 * (size_t)B * L * H + (size_t)B * L * F;
-  return fl * sizeof(float) + 16 * 256;
+  size_t fl = 3 * ((size_t)H * 3 * H + (size_t)H * H + 2 * (size_t)H * F) + 6 * (size_t)B * H * Lp +
+              5 * (size_t)B * L * H + 2 * (size_t)B * L * F;
+  return fl * sizeof(float) + 32 * 256;
 }
 
 extern "C" int m2tts_transformer_layer(const m2tts_layer_weights* w, const float* x_in, float* x_out,
@@ -66,11 +73,45 @@ extern "C" int m2tts_transformer_layer(const m2tts_layer_weights* w, const float
   cudaStream_t s = (cudaStream_t)stream;
   int rc;
 
+  const int R = B * L;
+  // ---- tensor-core path: every GEMM of the layer on tcgen05 (3xTF32), operands as hi/lo planes ----
+  if (attention_mode() == 0 && attention_tc_supported(hd) && linear_tc_eligible(H, 3 * H) && linear_tc_eligible(H, H) &&
+      linear_tc_eligible(H, F) && linear_tc_eligible(F, H) && (H % 16 == 0)) {
+    const float* srcs[4] = {w->qkv_w, w->out_w, w->ffn1_w, w->ffn2_w};
+    const long long ns[4] = {(long long)3 * H * H, (long long)H * H, (long long)F * H, (long long)H * F};
+    if ((rc = launch_w_split(srcs, ws.w_planes, ns, 4, s))) return rc;
+    if ((rc = launch_ln_split(x_in, w->norm1_w, w->norm1_b, ws.xn, R, H, ln_eps, s))) return rc;
+    {  // attention operand planes = split(LN1(x) Wqkv^T)
+      LinTcArgs a{};
+      a.R = R; a.L = L; a.K = H; a.N = 3 * H; a.mode = 2; a.qkv6 = ws.q; a.plane_stride = (long long)B * H * ws.Lp;
+      a.nh = num_heads; a.hd = hd; a.Lp = ws.Lp; a.qscale = (float)((1.0 / sqrt((double)hd)) * 1.4426950408889634);
+      if ((rc = launch_linear_tc(ws.xn, ws.w_planes[0], a, B, M2TTS_STAGE_LN_QKV, s))) return rc;
+    }
+    if ((rc = launch_attention_tc(ws.q, ws.ctx, lengths, B, L, ws.Lp, num_heads, hd, s, nullptr, nullptr,
+                                  ws.ctx + (size_t)R * H))) return rc;
+    {  // x1 = x + ctx Wo^T + bo
+      LinTcArgs a{};
+      a.R = R; a.L = L; a.K = H; a.N = H; a.mode = 0; a.bias = w->out_b; a.residual = x_in; a.ldr = H; a.y = ws.x1; a.ldy = H;
+      if ((rc = launch_linear_tc(ws.ctx, ws.w_planes[1], a, B, M2TTS_STAGE_OUTPROJ, s))) return rc;
+    }
+    if ((rc = launch_ln_split(ws.x1, w->norm2_w, w->norm2_b, ws.xn, R, H, ln_eps, s))) return rc;
+    {  // hid = relu(LN2(x1) W1^T + b1) as planes
+      LinTcArgs a{};
+      a.R = R; a.L = L; a.K = H; a.N = F; a.mode = 1; a.bias = w->ffn1_b; a.relu = 1; a.y_planes = ws.hid;
+      if ((rc = launch_linear_tc(ws.xn, ws.w_planes[2], a, B, M2TTS_STAGE_FFN1, s))) return rc;
+    }
+    {  // y = x1 + hid W2^T + b2
+      LinTcArgs a{};
+      a.R = R; a.L = L; a.K = F; a.N = H; a.mode = 0; a.bias = w->ffn2_b; a.residual = ws.x1; a.ldr = H; a.y = x_out; a.ldy = H;
+      if ((rc = launch_linear_tc(ws.hid, ws.w_planes[3], a, B, M2TTS_STAGE_FFN2, s))) return rc;
+    }
+    return M2TTS_OK;
+  }
+
   PackJob jobs[4] = {{w->qkv_w, ws.wqkv_t, 3 * H, H}, {w->out_w, ws.wo_t, H, H},
                      {w->ffn1_w, ws.w1_t, F, H}, {w->ffn2_w, ws.w2_t, H, F}};
   if ((rc = launch_pack_transpose(jobs, 4, s))) return rc;
 
-  const int R = B * L;
   const bool use_tc = attention_mode() == 0 && attention_tc_supported(hd);
   {  // q,k,v = split(LN1(x) Wqkv^T)
     RowGemmArgs a{};
@@ -111,7 +152,12 @@ extern "C" int m2tts_transformer_layer(const m2tts_layer_weights* w, const float
 
 extern "C" size_t m2tts_ln_proj_workspace_bytes(int H, int N) {
   if (H <= 0 || N <= 0) return 0;
-  return align_up((size_t)H * N * sizeof(float), 256) + 256;
+  return align_up((size_t)3 * H * N * sizeof(float), 256) + 1024;   // W^T (FFMA) or W hi/lo planes (tensor cores)
+}
+
+extern "C" size_t m2tts_ln_proj_rows_workspace_bytes(int rows, int H, int N) {
+  if (rows <= 0 || H <= 0 || N <= 0) return 0;
+  return m2tts_ln_proj_workspace_bytes(H, N) + align_up((size_t)2 * rows * H * sizeof(float), 256) + 256;
 }
 
 extern "C" int m2tts_layernorm_proj(const float* x, const float* ln_w, const float* ln_b, const float* W,
@@ -120,10 +166,23 @@ extern "C" int m2tts_layernorm_proj(const float* x, const float* ln_w, const flo
   M2_REQUIRE(x && ln_w && ln_b && W && y && workspace, M2TTS_E_NULLPTR, "layernorm_proj: null pointer");
   M2_REQUIRE(rows > 0 && H > 0 && N > 0, M2TTS_E_BADSHAPE, "layernorm_proj: rows=%d H=%d N=%d", rows, H, N);
   Carver cv(workspace, workspace_bytes);
-  float* wt = cv.take<float>((size_t)H * N);
+  float* wt = cv.take<float>((size_t)3 * H * N);
   M2_REQUIRE(cv.ok(), M2TTS_E_WORKSPACE, "layernorm_proj: workspace too small or not 256-B aligned");
   cudaStream_t s = (cudaStream_t)stream;
   int rc;
+  {  // tensor-core path when the caller's workspace also has room for the normalised rows as hi/lo planes
+    float* xn = cv.take<float>((size_t)2 * rows * H);
+    if (attention_mode() == 0 && cv.ok() && linear_tc_eligible(H, N) && (N % 16 == 0) && (H % 4 == 0)) {
+      const float* srcs[1] = {W};
+      float* dsts[1] = {wt};
+      const long long ns[1] = {(long long)N * H};
+      if ((rc = launch_w_split(srcs, dsts, ns, 1, s))) return rc;
+      if ((rc = launch_ln_split(x, ln_w, ln_b, xn, rows, H, eps, s))) return rc;
+      LinTcArgs a{};
+      a.R = rows; a.L = rows; a.K = H; a.N = N; a.mode = 0; a.bias = bias; a.y = y; a.ldy = N;
+      return launch_linear_tc(xn, wt, a, 1, M2TTS_STAGE_LN_PROJ, s);
+    }
+  }
   PackJob job{W, wt, N, H};
   if ((rc = launch_pack_transpose(&job, 1, s))) return rc;
   RowGemmArgs a{};

@@ -65,6 +65,7 @@ _SIGNATURES = {
                                           C.c_void_p, C.c_size_t, C.c_void_p]),
     "m2tts_layernorm": (C.c_int, [C.c_void_p] * 4 + [C.c_int, C.c_int, C.c_float, C.c_void_p]),
     "m2tts_ln_proj_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "m2tts_ln_proj_rows_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "m2tts_layernorm_proj": (C.c_int, [C.c_void_p] * 6 + [C.c_int, C.c_int, C.c_int, C.c_float,
                                                            C.c_void_p, C.c_size_t, C.c_void_p]),
     "m2tts_duration_predictor": (C.c_int, [C.POINTER(DurPredWeights), C.c_void_p, C.c_void_p,

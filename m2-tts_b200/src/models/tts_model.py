@@ -276,7 +276,7 @@ class MelDecoder(nn.Module):
         M = self.mel_projection.out_features
         lib = nat.lib()
         mel = torch.empty((B, T, M), dtype=torch.float32, device=dev)
-        ws = nat.workspace(dev, lib.m2tts_ln_proj_workspace_bytes(H, M), tag="ln_proj")
+        ws = nat.workspace(dev, lib.m2tts_ln_proj_rows_workspace_bytes(B * T, H, M), tag="ln_proj")
         rc = lib.m2tts_layernorm_proj(h.data_ptr(), nat.weight(self.norm.weight, "norm.weight"),
                                       nat.weight(self.norm.bias, "norm.bias"),
                                       nat.weight(self.mel_projection.weight, "mel_projection.weight"),
