@@ -121,9 +121,9 @@ int m2tts_debug_words(int* out, int n);
  * kernel with 3xTF32 splitting when head_dim is one of {16,32,48,64}, else the fp32 FFMA kernel;
  * 1 = always the fp32 FFMA kernel. Process-wide; also settable with M2TTS_ATTENTION=ffma. */
 int m2tts_set_attention_mode(int mode);
-/* Vocoder kernel selection: 0 (default) = stages whose three convolutions all have >= 64 output
- * channels (and CI % 16 == 0) run as tcgen05 implicit GEMMs with 3xTF32 splitting, the narrow late
- * stages stay fp32 FFMA; 1 = FFMA everywhere. Process-wide; also M2TTS_VOCODER=ffma. */
+/* Vocoder kernel selection: 0 (default) = every leading stage whose three convolutions have channel
+ * counts that are multiples of 16 runs as persistent tcgen05 implicit GEMMs with 3xTF32 splitting
+ * (stage2_quality: all four stages), the rest fp32 FFMA; 1 = FFMA everywhere. Process-wide; also M2TTS_VOCODER=ffma. */
 int m2tts_set_vocoder_mode(int mode);
 /* fp32 FFMA peak probe: `iters` dependent-chain FFMAs per thread on a full grid;
  * writes nothing but a checksum; returns flop count through *flops. */
@@ -220,8 +220,8 @@ int m2tts_conv_transpose1d_lrelu(const float* x, const float* w, const float* bi
 
 /* Tensor-core (tcgen05, 3xTF32) variants of the two per-stage entry points, plain fp32 tensors in
  * and out, same semantics (act: 0 none, 1 leaky_relu(0.1); residual added after the conv).
- * Eligibility: conv CI % 16 == 0 and CO % 64 == 0; transposed conv r == 4, CI % 16 == 0, CO % 32 == 0
- * (else M2TTS_E_UNSUPPORTED). workspace: m2tts_conv_tc_workspace_bytes(B, CI, CO, L, r). */
+ * Eligibility: conv CI % 16 == 0, CO a multiple of 16 that is < 64 or a multiple of 64, dilation <= 4;
+ * transposed conv CI % 16 == 0 and (r == 4, CO % 32 == 0) or (r == 2, CO % 16 == 0); else M2TTS_E_UNSUPPORTED. workspace: m2tts_conv_tc_workspace_bytes(B, CI, CO, L, r). */
 size_t m2tts_conv_tc_workspace_bytes(int B, int CI, int CO, int L, int r);
 int m2tts_conv1d_k3_tc(const float* x, const float* w, const float* bias, const float* residual, float* y,
                        int B, int CI, int CO, int L, int dilation, int act, void* workspace,

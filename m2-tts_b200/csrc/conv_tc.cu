@@ -19,84 +19,15 @@
 // warp 1 issues UMMAs (M128, N = rows of the tap, K8; 3 split terms), all four warps run the
 // epilogue (TMEM -> bias/activation/residual -> global, hi/lo planes or plain fp32).
 #include "common.cuh"
+#include "conv_tc.cuh"
 #include <cuda.h>
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 
 namespace m2 {
 
-constexpr int CT_BM = 128;            // GEMM rows (input positions) per CTA, including the halo
-constexpr int CT_HALO = 4;            // rows on each side that are computed but not stored (|tap shift| <= 4)
-constexpr int CT_STEP = CT_BM - 2 * CT_HALO;   // 120 output positions per CTA; tile starts stay 16-B aligned for TMA
-constexpr int CT_CK = 16;             // input channels per pipeline chunk
-constexpr int CT_STAGES = 2;             // 2 x (16 KB activations + <= 32 KB weights): two CTAs per SM overlap each other's epilogue
-constexpr int CT_THREADS = 128;
-constexpr uint32_t CT_ABOX = CT_CK * 128;                        // one TMA box: 16 rows x 128 B
-constexpr uint32_t CT_A_STAGE = 2u * 4u * CT_ABOX;               // planes x boxes = 16 KB
-
-struct TapGemmArgs {
-  int CI, L_in, B, n_chunks;
-  int tap_shift[3], tap_rows[3], tap_wrow[3], tap_dcol[3];
-  int rows_total;            // weight rows per (chunk, plane) image
-  int n_cols;                // accumulator columns per CTA
-  int tmem_cols;             // power of two >= 32
-  const float* wblob;        // [n_tile][chunk][plane][rows_total][16] (image order)
-  int r, co_tile, CO;
-  int L_out, Lp_out;
-  const float* bias;
-  int act;                   // 0 none, 1 leaky_relu(0.1)
-  const float* res_hi; const float* res_lo; int Lp_res;
-  float* out_hi; float* out_lo;   // out_lo == nullptr -> plain fp32 into out_hi
-};
-
-// ---- PTX helpers (same conventions as attention_tc.cu) ------------------------------------------
-__device__ __forceinline__ uint32_t ct_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void ct_mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void ct_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void ct_wait(uint32_t bar, uint32_t parity, int* dbg, int code, int chunk) {
-  for (uint32_t it = 0; it < (1u << 24); ++it) {
-    uint32_t ok;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    if (ok) return;
-  }
-  if (dbg != nullptr) {
-    dbg[0] = code; dbg[1] = chunk; dbg[2] = blockIdx.x; dbg[3] = blockIdx.y; dbg[4] = blockIdx.z; dbg[5] = threadIdx.x;
-    __threadfence_system();
-  }
-  __trap();
-}
-// NOTE: with 4-byte elements the innermost TMA coordinate must be a multiple of 4 (16-byte aligned box rows);
-// an unaligned coordinate raises "illegal instruction" — which is why the taps shift OUTPUT rows, not input boxes.
-__device__ __forceinline__ void ct_tma_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-               ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void ct_bulk(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void ct_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void ct_mma(uint32_t d, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t acc) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-               ::"r"(d), "l"(ad), "l"(bd), "r"(idesc), "r"(acc) : "memory");
-}
-__device__ __forceinline__ uint64_t ct_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t layout_type) {
-  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
-         ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46) | ((uint64_t)layout_type << 61);
-}
-__device__ __forceinline__ void ct_ld8(uint32_t taddr, uint32_t* r) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "r"(taddr));
-}
-__device__ __forceinline__ float ct_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
+// (constants, TapGemmArgs and the PTX helpers live in conv_tc.cuh)
 
 // D_tap[m, n] = sum_ci X[ci, start + m] * W_tap[n, ci] for the three taps (separate TMEM column ranges);
 // the epilogue forms out[t] = sum_tap D_tap[t - start + shift_tap] through a shared-memory staging tile.
@@ -345,8 +276,20 @@ static EncodeTiledFn2 ct_encode_fn() {
 
 static int next_pow2_cols(int n) { int c = 32; while (c < n) c <<= 1; return c; }
 
-bool conv3_tc_eligible(int CI, int CO) { return CI % CT_CK == 0 && CO % 64 == 0 && CO >= 64; }  // and dilation <= 4 (checked at launch)
-bool convT_tc_eligible(int CI, int CO, int r) { return r == 4 && CI % CT_CK == 0 && CO % 32 == 0 && CO >= 32; }
+static bool tapgemm_v1() { static int v = -1; if (v < 0) { const char* e = getenv("M2TTS_TAPGEMM"); v = (e && strcmp(e, "v1") == 0) ? 1 : 0; } return v == 1; }
+// dilation <= 4 is checked at launch. The persistent kernel takes any CO that is a multiple of 16 (<= 64 or a
+// multiple of 64); the first-generation kernel (M2TTS_TAPGEMM=v1) needs CO % 64 == 0.
+bool conv3_tc_eligible(int CI, int CO) {
+  if (CI % CT_CK != 0 || CO % 16 != 0 || CO < 16) return false;
+  if (tapgemm_v1()) return CO % 64 == 0;
+  return CO % 64 == 0 || CO < 64;
+}
+bool convT_tc_eligible(int CI, int CO, int r) {
+  if (CI % CT_CK != 0) return false;
+  if (r == 4) return CO % 32 == 0 && CO >= 32;
+  if (r == 2 && !tapgemm_v1()) return CO % 16 == 0 && CO >= 16;
+  return false;
+}
 size_t conv3_tc_wblob_floats(int CI, int CO) { return (size_t)2 * 3 * CO * CI; }
 size_t convT_tc_wblob_floats(int CI, int CO, int r) { return (size_t)2 * 2 * r * CO * CI; }
 
@@ -363,6 +306,8 @@ static int launch_tapgemm(const float* x_planes, int Lp_in, TapGemmArgs& a, int 
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   M2_REQUIRE(r == CUDA_SUCCESS, M2TTS_E_CUDA, "conv_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  a.n_tiles = n_tiles;
+  if (!tapgemm_v1()) return launch_tapgemm_persistent(tmap, a, stage, s);
   a.tmem_cols = next_pow2_cols(a.n_cols);
   const uint32_t w_stage = 2u * (uint32_t)a.rows_total * 64u;
   const size_t smem = (size_t)CT_STAGES * (CT_A_STAGE + ((w_stage + 1023u) & ~1023u)) + 1024 + 128;
@@ -388,7 +333,7 @@ int launch_conv3_tc(const float* x_planes, int Lp_in, const float* w, float* wbl
                     const float* res_hi, const float* res_lo, int Lp_res, float* out_hi, float* out_lo, int Lp_out,
                     int B, int CI, int CO, int L, int dil, int act, int stage, cudaStream_t s) {
   M2_REQUIRE(conv3_tc_eligible(CI, CO), M2TTS_E_UNSUPPORTED, "conv3_tc: CI=%d CO=%d not eligible", CI, CO);
-  const int ct = 64, n_tiles = CO / ct;   // 192 accumulator columns -> 256 TMEM columns per CTA, two CTAs per SM
+  const int ct = (CO % 64 == 0) ? 64 : CO, n_tiles = CO / ct;   // <= 192 accumulator columns, double-buffered in TMEM
   WPackArgs p{w, wblob, 0, CI, CO, 1, ct, 3 * ct, CI / CT_CK, n_tiles};
   int rc = launch_wpack(p, s);
   if (rc) return rc;
@@ -404,7 +349,7 @@ int launch_conv3_tc(const float* x_planes, int Lp_in, const float* w, float* wbl
 int launch_convT_tc(const float* x_planes, int Lp_in, const float* w, float* wblob, const float* bias, float* out_hi,
                     float* out_lo, int Lp_out, int B, int CI, int CO, int L, int r, cudaStream_t s) {
   M2_REQUIRE(convT_tc_eligible(CI, CO, r), M2TTS_E_UNSUPPORTED, "convT_tc: CI=%d CO=%d r=%d not eligible", CI, CO, r);
-  const int ct = 32, n_tiles = CO / ct;
+  const int ct = (CO % 32 == 0) ? 32 : 16, n_tiles = CO / ct;
   WPackArgs p{w, wblob, 1, CI, CO, r, ct, 2 * r * ct, CI / CT_CK, n_tiles};
   int rc = launch_wpack(p, s);
   if (rc) return rc;
@@ -443,7 +388,7 @@ extern "C" int m2tts_conv1d_k3_tc(const float* x, const float* w, const float* b
                                   size_t workspace_bytes, m2tts_stream_t stream) {
   M2_REQUIRE(x && w && bias && y && workspace, M2TTS_E_NULLPTR, "conv1d_k3_tc: null pointer");
   M2_REQUIRE(B > 0 && L > 0 && dilation >= 1 && (act == 0 || act == 1), M2TTS_E_BADSHAPE, "conv1d_k3_tc: bad arguments");
-  M2_REQUIRE(conv3_tc_eligible(CI, CO), M2TTS_E_UNSUPPORTED, "conv1d_k3_tc: needs CI %% 16 == 0 and CO %% 64 == 0 (CI=%d CO=%d)", CI, CO);
+  M2_REQUIRE(conv3_tc_eligible(CI, CO), M2TTS_E_UNSUPPORTED, "conv1d_k3_tc: needs CI %% 16 == 0 and CO a multiple of 16 that is < 64 or a multiple of 64 (CI=%d CO=%d)", CI, CO);
   const int Lp = (L + 3) & ~3;
   Carver cv(workspace, workspace_bytes);
   float* planes = cv.take<float>(2 * (size_t)B * CI * Lp);
@@ -468,7 +413,7 @@ extern "C" int m2tts_conv_transpose1d_lrelu_tc(const float* x, const float* w, c
   M2_REQUIRE(x && w && bias && y && workspace, M2TTS_E_NULLPTR, "conv_transpose1d_tc: null pointer");
   M2_REQUIRE(B > 0 && L > 0, M2TTS_E_BADSHAPE, "conv_transpose1d_tc: bad arguments");
   M2_REQUIRE(convT_tc_eligible(CI, CO, r), M2TTS_E_UNSUPPORTED,
-             "conv_transpose1d_tc: needs r == 4, CI %% 16 == 0, CO %% 32 == 0 (CI=%d CO=%d r=%d)", CI, CO, r);
+             "conv_transpose1d_tc: needs r == 4 (CO %% 32 == 0) or r == 2 (CO %% 16 == 0), CI %% 16 == 0 (CI=%d CO=%d r=%d)", CI, CO, r);
   const int Lp = (L + 3) & ~3;
   Carver cv(workspace, workspace_bytes);
   float* planes = cv.take<float>(2 * (size_t)B * CI * Lp);

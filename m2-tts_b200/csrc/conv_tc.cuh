@@ -1,0 +1,86 @@
+// conv_tc.cuh — shared definitions of the tensor-core tap-GEMM convolutions (conv_tc.cu, conv_tc2.cu).
+#pragma once
+#include "common.cuh"
+#include <cuda.h>
+
+namespace m2 {
+
+constexpr int CT_BM = 128;            // GEMM rows (input positions) per CTA, including the halo
+constexpr int CT_HALO = 4;            // rows on each side that are computed but not stored (|tap shift| <= 4)
+constexpr int CT_STEP = CT_BM - 2 * CT_HALO;   // 120 output positions per CTA; tile starts stay 16-B aligned for TMA
+constexpr int CT_CK = 16;             // input channels per pipeline chunk
+constexpr int CT_STAGES = 2;             // 2 x (16 KB activations + <= 32 KB weights): two CTAs per SM overlap each other's epilogue
+constexpr int CT_THREADS = 128;
+constexpr uint32_t CT_ABOX = CT_CK * 128;                        // one TMA box: 16 rows x 128 B
+constexpr uint32_t CT_A_STAGE = 2u * 4u * CT_ABOX;               // planes x boxes = 16 KB
+
+struct TapGemmArgs {
+  int CI, L_in, B, n_chunks;
+  int tap_shift[3], tap_rows[3], tap_wrow[3], tap_dcol[3];
+  int rows_total;            // weight rows per (chunk, plane) image
+  int n_cols;                // accumulator columns per CTA
+  int tmem_cols;             // power of two >= 32
+  const float* wblob;        // [n_tile][chunk][plane][rows_total][16] (image order)
+  int r, co_tile, CO;
+  int L_out, Lp_out;
+  const float* bias;
+  int act;                   // 0 none, 1 leaky_relu(0.1)
+  const float* res_hi; const float* res_lo; int Lp_res;
+  float* out_hi; float* out_lo;   // out_lo == nullptr -> plain fp32 into out_hi
+  // persistent kernel (conv_tc2.cu)
+  int n_tiles, m_tiles, w_resident, ring_stages;
+};
+
+// ---- PTX helpers (same conventions as attention_tc.cu) ------------------------------------------
+__device__ __forceinline__ uint32_t ct_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ct_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void ct_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ct_wait(uint32_t bar, uint32_t parity, int* dbg, int code, int chunk) {
+  for (uint32_t it = 0; it < (1u << 24); ++it) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) return;
+  }
+  if (dbg != nullptr) {
+    dbg[0] = code; dbg[1] = chunk; dbg[2] = blockIdx.x; dbg[3] = blockIdx.y; dbg[4] = blockIdx.z; dbg[5] = threadIdx.x;
+    __threadfence_system();
+  }
+  __trap();
+}
+// NOTE: with 4-byte elements the innermost TMA coordinate must be a multiple of 4 (16-byte aligned box rows);
+// an unaligned coordinate raises "illegal instruction" — which is why the taps shift OUTPUT rows, not input boxes.
+__device__ __forceinline__ void ct_tma_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void ct_bulk(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void ct_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void ct_mma(uint32_t d, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(d), "l"(ad), "l"(bd), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ uint64_t ct_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t layout_type) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46) | ((uint64_t)layout_type << 61);
+}
+__device__ __forceinline__ void ct_ld8(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
+__device__ __forceinline__ float ct_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
+
+
+int launch_tapgemm_persistent(const CUtensorMap& tmap, TapGemmArgs& a, int stage, cudaStream_t s);
+
+}  // namespace m2

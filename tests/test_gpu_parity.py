@@ -303,7 +303,9 @@ def test_tensor_core_conv_entry_points():
     lib = nat.lib()
     g = torch.Generator().manual_seed(31)
     for (CI, CO, L, dil, act, with_res) in [(128, 128, 300, 1, 1, False), (64, 64, 517, 1, 0, True),
-                                            (16, 64, 130, 2, 0, False), (256, 128, 64, 1, 1, True)]:
+                                            (16, 64, 130, 2, 0, False), (256, 128, 64, 1, 1, True),
+                                            (32, 32, 1000, 1, 1, True), (16, 16, 300, 1, 0, True),
+                                            (32, 16, 200, 3, 0, False), (48, 48, 121, 4, 1, False)]:
         x = torch.randn(2, CI, L, generator=g)
         w = torch.randn(CO, CI, 3, generator=g) * (1.0 / (3 * CI) ** 0.5)
         b = torch.randn(CO, generator=g)
@@ -321,18 +323,20 @@ def test_tensor_core_conv_entry_points():
                                     2, CI, CO, L, dil, act, ws.data_ptr(), ws.numel(), None)
         nat.check(rc, "conv1d_k3_tc")
         assert H.max_abs(y.cpu(), want) <= FP32_TOL, ("conv3_tc", CI, CO, L, dil, act)
-    for (CI, CO, L) in [(256, 128, 77), (128, 64, 300), (32, 32, 129)]:
+    for (CI, CO, L, r_) in [(256, 128, 77, 4), (128, 64, 300, 4), (32, 32, 129, 4), (64, 32, 300, 2), (32, 16, 129, 2),
+                            (16, 16, 50, 2)]:
         x = torch.randn(2, CI, L, generator=g)
-        w = torch.randn(CI, CO, 8, generator=g) * (1.0 / (2 * CI) ** 0.5)
+        w = torch.randn(CI, CO, 2 * r_, generator=g) * (1.0 / (2 * CI) ** 0.5)
         b = torch.randn(CO, generator=g)
-        want = torch.nn.functional.leaky_relu(torch.nn.functional.conv_transpose1d(x, w, b, stride=4, padding=2), 0.1)
+        want = torch.nn.functional.leaky_relu(
+            torch.nn.functional.conv_transpose1d(x, w, b, stride=r_, padding=r_ // 2), 0.1)
         xd, wd, bd = x.to(DEV), w.to(DEV), b.to(DEV)
-        y = torch.empty(2, CO, 4 * L, device=DEV)
-        ws = torch.empty(lib.m2tts_conv_tc_workspace_bytes(2, CI, CO, L, 4), dtype=torch.uint8, device=DEV)
-        rc = lib.m2tts_conv_transpose1d_lrelu_tc(xd.data_ptr(), wd.data_ptr(), bd.data_ptr(), y.data_ptr(), 2, CI, CO, L, 4,
+        y = torch.empty(2, CO, r_ * L, device=DEV)
+        ws = torch.empty(lib.m2tts_conv_tc_workspace_bytes(2, CI, CO, L, r_), dtype=torch.uint8, device=DEV)
+        rc = lib.m2tts_conv_transpose1d_lrelu_tc(xd.data_ptr(), wd.data_ptr(), bd.data_ptr(), y.data_ptr(), 2, CI, CO, L, r_,
                                                  ws.data_ptr(), ws.numel(), None)
         nat.check(rc, "conv_transpose1d_lrelu_tc")
-        assert H.max_abs(y.cpu(), want) <= FP32_TOL, ("convT_tc", CI, CO, L)
+        assert H.max_abs(y.cpu(), want) <= FP32_TOL, ("convT_tc", CI, CO, L, r_)
 
 
 @pytest.mark.parametrize("mode", [0, 1])  # 0 = tcgen05 convs for the wide stages, 1 = FFMA everywhere
