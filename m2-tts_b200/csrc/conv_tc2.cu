@@ -3,8 +3,8 @@
 //   * one CTA per SM loops over (utterance, 120-position) tiles of ONE output-channel tile, so the packed
 //     weight images stay RESIDENT in shared memory whenever they fit (every layer but the widest ones);
 //   * warp 0 = TMA producer (activation boxes, and weight chunks when streaming), warp 1 = UMMA issuer,
-//     warps 2-5 = epilogue; the accumulators are double-buffered in TMEM so tile i's epilogue overlaps
-//     tile i+1's UMMAs; ring of activation stages between producer and issuer;
+//     warps 2-5 / 6-9 = two epilogue groups that take alternate tiles (= alternate TMEM accumulator buffers),
+//     so two epilogues and the next tile's UMMAs are in flight at once; ring of activation stages between producer and issuer;
 //   * epilogue: TMEM -> staging tile in shared memory -> out[t] = sum_tap D_tap[t + shift_tap] (+bias,
 //     LeakyReLU, +residual) -> global (hi/lo planes for the next tensor-core layer, or plain fp32).
 #include "conv_tc.cuh"
@@ -12,13 +12,20 @@
 
 namespace m2 {
 
-constexpr int P_THREADS = 192;
-constexpr int P_EPI_THREADS = 128;
+constexpr int P_THREADS = 320;            // producer warp, UMMA warp, 2 x 4 epilogue warps
+constexpr int P_STAGING = 64 * 128 * 4;   // per epilogue group: 3 taps x 16 columns (or 2r x 8 channel rows) x 128 rows
 
 __device__ __forceinline__ void p_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void p_epi_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void p_epi_sync(int group) { asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory"); }
+__device__ __forceinline__ void p_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
 
 struct PersistSmem {   // byte offsets from the 1024-aligned base, computed on the host
   uint32_t a_ring, w_region, staging, bars;
@@ -133,88 +140,88 @@ tapgemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const TapG
       }
     }
   } else {
-    // ===== epilogue warps (2..5): TMEM lane quarter = warp % 4 =====
-    const int qtr = warp & 3;
+    // ===== epilogue: group g = (warp-2)/4 takes tiles t with t % 2 == g, i.e. always accumulator buffer g =====
+    const int grp = (warp - 2) >> 2;
+    const int qtr = warp & 3;                            // TMEM lane quarter this warp may access
     const int m = qtr * 32 + lane;                       // GEMM row = input position start + m
-    const uint32_t t_lane_off = ((uint32_t)(qtr * 32) << 16);
+    const int buf = grp;
+    float* stg = stage_f + grp * (P_STAGING / 4);
+    const uint32_t t_lane = tmem_base + ((uint32_t)(qtr * 32) << 16) + (uint32_t)(buf * a.n_cols);
     const int co0 = ntile * a.co_tile;
     int t = 0;
     for (int j = first; j < total_mt; j += cpg, ++t) {
-      const int buf = t & 1;
+      if ((t & 1) != grp) continue;
       const int b = j / a.m_tiles, start = (j % a.m_tiles) * CT_STEP - CT_HALO;
       const int q = start + m;
       const bool own = (m >= CT_HALO) && (m < CT_BM - CT_HALO) && (q < a.L_in);
       ct_wait(bar_accf + 8 * buf, (uint32_t)((t / 2) & 1), dbg, 3, t);
       __syncwarp();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t t_lane = tmem_base + t_lane_off + (uint32_t)(buf * a.n_cols);
 
       if (a.r == 1) {
         const int s0 = a.tap_shift[0], s1 = a.tap_shift[1], s2 = a.tap_shift[2];
-        const int CC = a.co_tile < 32 ? a.co_tile : 32;       // columns per staging pass
-        for (int c0 = 0; c0 < a.co_tile; c0 += CC) {
+        for (int c0 = 0; c0 < a.co_tile; c0 += 16) {
+          // residual loads first: 32 independent read-only loads in flight while the tile is staged
+          float rsd[16];
 #pragma unroll
-          for (int tap = 0; tap < 3; ++tap)
-            for (int cc = 0; cc < CC; cc += 8) {
-              uint32_t v[8];
-              ct_ld8(t_lane + (uint32_t)(a.tap_dcol[tap] + c0 + cc), v);
-              asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          for (int c = 0; c < 16; ++c) rsd[c] = 0.f;
+          if (own && a.res_hi != nullptr) {
+            const float* __restrict__ rh = a.res_hi + ((size_t)b * a.CO + co0 + c0) * a.Lp_res + q;
+            const float* __restrict__ rl = a.res_lo + ((size_t)b * a.CO + co0 + c0) * a.Lp_res + q;
 #pragma unroll
-              for (int jj = 0; jj < 8; ++jj) stage_f[((tap * 32 + cc + jj) << 7) + m] = __uint_as_float(v[jj]);
-            }
-          if (c0 + CC >= a.co_tile) {   // last TMEM read of this tile: hand the accumulator buffer back
+            for (int c = 0; c < 16; ++c) rsd[c] = __ldg(rh + (size_t)c * a.Lp_res) + __ldg(rl + (size_t)c * a.Lp_res);
+          }
+          uint32_t v[3][16];
+#pragma unroll
+          for (int tap = 0; tap < 3; ++tap) p_ld16(t_lane + (uint32_t)(a.tap_dcol[tap] + c0), v[tap]);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (c0 + 16 >= a.co_tile) {   // last TMEM read of this tile: hand the accumulator buffer back
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) p_arrive(bar_acce + 8 * buf);
           }
-          p_epi_sync();
+#pragma unroll
+          for (int tap = 0; tap < 3; ++tap)
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) stg[((tap * 16 + jj) << 7) + m] = __uint_as_float(v[tap][jj]);
+          p_epi_sync(grp);
           if (own) {
-            for (int cb = 0; cb < CC; cb += 8) {
-              float rsd[8];
-              if (a.res_hi != nullptr) {
-                const float* __restrict__ rh = a.res_hi + ((size_t)b * a.CO + co0 + c0 + cb) * a.Lp_res + q;
-                const float* __restrict__ rl = a.res_lo + ((size_t)b * a.CO + co0 + c0 + cb) * a.Lp_res + q;
 #pragma unroll
-                for (int c = 0; c < 8; ++c) rsd[c] = __ldg(rh + (size_t)c * a.Lp_res) + __ldg(rl + (size_t)c * a.Lp_res);
-              } else {
-#pragma unroll
-                for (int c = 0; c < 8; ++c) rsd[c] = 0.f;
-              }
-#pragma unroll
-              for (int c = 0; c < 8; ++c) {
-                const int cl = cb + c, co = co0 + c0 + cl;
-                float x = stage_f[((cl) << 7) + m + s0] + stage_f[((32 + cl) << 7) + m + s1] + stage_f[((64 + cl) << 7) + m + s2] +
-                          __ldg(a.bias + co);
-                if (a.act == 1) x = x > 0.f ? x : 0.1f * x;
-                x += rsd[c];
-                const size_t oo = ((size_t)b * a.CO + co) * a.Lp_out + q;
-                if (a.out_lo != nullptr) { const float h = ct_hi(x); a.out_hi[oo] = h; a.out_lo[oo] = ct_hi(x - h); }
-                else a.out_hi[oo] = x;
-              }
+            for (int c = 0; c < 16; ++c) {
+              const int co = co0 + c0 + c;
+              float x = stg[((c) << 7) + m + s0] + stg[((16 + c) << 7) + m + s1] + stg[((32 + c) << 7) + m + s2] + __ldg(a.bias + co);
+              if (a.act == 1) x = x > 0.f ? x : 0.1f * x;
+              x += rsd[c];
+              const size_t oo = ((size_t)b * a.CO + co) * a.Lp_out + q;
+              if (a.out_lo != nullptr) { const float h = ct_hi(x); a.out_hi[oo] = h; a.out_lo[oo] = ct_hi(x - h); }
+              else a.out_hi[oo] = x;
             }
           }
-          p_epi_sync();
+          p_epi_sync(grp);
         }
       } else {
         // transposed conv, r in {2,4}: D0 [0, r*ct) phase-major; D1 [r*ct, +r/2*ct) phases < r/2 (row q-1);
-        // D2 next r/2*ct columns, phases >= r/2 (row q+1). Staging rows: group g (8 channels each):
-        // g < r: D0 phase g; r <= g < r + r/2: D1 phase g-r; else D2 phase (g - r - r/2) + r/2.
+        // D2 next r/2*ct columns, phases >= r/2 (row q+1). Staging rows: group g of 8 channels:
+        // g < r: D0 phase g; g >= r: D1/D2 phase g - r.
         const int ct = a.co_tile, r = a.r, hr = a.r / 2, groups = 2 * a.r;
         for (int c0 = 0; c0 < ct; c0 += 8) {
-          for (int g = 0; g < groups; ++g) {
-            const int col = (g < r) ? g * ct : (g < r + hr ? r * ct + (g - r) * ct : r * ct + hr * ct + (g - r - hr) * ct);
-            uint32_t v[8];
-            ct_ld8(t_lane + (uint32_t)(col + c0), v);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          uint32_t v[8][8];
 #pragma unroll
-            for (int jj = 0; jj < 8; ++jj) stage_f[((g * 8 + jj) << 7) + m] = __uint_as_float(v[jj]);
-          }
+          for (int g = 0; g < 8; ++g)
+            if (g < groups) ct_ld8(t_lane + (uint32_t)(g * ct + c0), v[g]);   // D0|D1|D2 are contiguous: column = g*ct + c
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           if (c0 + 8 >= ct) {
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) p_arrive(bar_acce + 8 * buf);
           }
-          p_epi_sync();
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            if (g < groups) {
+#pragma unroll
+              for (int jj = 0; jj < 8; ++jj) stg[((g * 8 + jj) << 7) + m] = __uint_as_float(v[g][jj]);
+            }
+          p_epi_sync(grp);
           if (own) {
 #pragma unroll
             for (int jj = 0; jj < 8; ++jj) {
@@ -224,8 +231,8 @@ tapgemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const TapG
 #pragma unroll
               for (int p = 0; p < 4; ++p) {
                 if (p < r) {
-                  float tv = stage_f[((p * 8 + jj) << 7) + m] + bv;
-                  tv += (p < hr) ? stage_f[(((r + p) * 8 + jj) << 7) + m - 1] : stage_f[(((r + hr + p - hr) * 8 + jj) << 7) + m + 1];
+                  float tv = stg[((p * 8 + jj) << 7) + m] + bv;
+                  tv += stg[(((r + p) * 8 + jj) << 7) + m + (p < hr ? -1 : 1)];
                   x[p] = tv > 0.f ? tv : 0.1f * tv;
                 } else {
                   x[p] = 0.f;
@@ -253,7 +260,7 @@ tapgemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const TapG
               }
             }
           }
-          p_epi_sync();
+          p_epi_sync(grp);
         }
       }
     }
@@ -276,7 +283,7 @@ int launch_tapgemm_persistent(const CUtensorMap& tmap, TapGemmArgs& a, int stage
   while (a.tmem_cols < 2 * a.n_cols) a.tmem_cols <<= 1;
   PersistSmem L{};
   L.w_stage = 2u * (uint32_t)a.rows_total * 64u;
-  const uint32_t staging = 96u * 128u * 4u;   // 3 taps x 32 columns (or up to 8 groups x 8 channels) x 128 rows
+  const uint32_t staging = 2u * (uint32_t)P_STAGING;   // one staging tile per epilogue group
   const uint32_t budget = 226u * 1024u - 1024u /*alignment*/ - 256u /*barriers*/ - staging;
   const uint32_t w_all = (uint32_t)a.n_chunks * L.w_stage;
   if (w_all + 2u * CT_A_STAGE <= budget) {
