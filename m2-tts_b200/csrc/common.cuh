@@ -155,15 +155,14 @@ int* debug_words_device();  // pinned mapped scratch for hang diagnostics (may b
 int attention_mode();  // 0 = tensor cores when supported, 1 = force the FFMA kernel
 int vocoder_mode();    // 0 = tensor-core convolutions for the wide stages, 1 = FFMA everywhere
 
-// tensor-core ("tap-GEMM") convolutions on hi/lo planes [2][B][C][Lp] (conv_tc.cu)
+// tensor-core ("tap-GEMM") convolutions on plain fp32 [B][C][Lp] (conv_tc.cu / conv_tc2.cu)
 bool conv3_tc_eligible(int CI, int CO);
 bool convT_tc_eligible(int CI, int CO, int r);
 size_t conv3_tc_wblob_floats(int CI, int CO);
 size_t convT_tc_wblob_floats(int CI, int CO, int r);
-int launch_conv3_tc(const float* x_planes, int Lp_in, const float* w, float* wblob, const float* bias,
-                    const float* res_hi, const float* res_lo, int Lp_res, float* out_hi, float* out_lo, int Lp_out,
-                    int B, int CI, int CO, int L, int dil, int act, int stage, cudaStream_t s);
-int launch_convT_tc(const float* x_planes, int Lp_in, const float* w, float* wblob, const float* bias, float* out_hi,
-                    float* out_lo, int Lp_out, int B, int CI, int CO, int L, int r, cudaStream_t s);
-int launch_split_planes(const float* x, float* planes, long long rows, int L, int Lp, cudaStream_t s);
+int launch_conv3_tc(const float* x, int Lp_in, const float* w, float* wblob, const float* bias, const float* residual,
+                    int Lp_res, float* out, int Lp_out, int B, int CI, int CO, int L, int dil, int act, int stage,
+                    cudaStream_t s);
+int launch_convT_tc(const float* x, int Lp_in, const float* w, float* wblob, const float* bias, float* out, int Lp_out,
+                    int B, int CI, int CO, int L, int r, cudaStream_t s);
 }  // namespace m2

@@ -1,43 +1,47 @@
-// conv_tc.cuh — shared definitions of the tensor-core tap-GEMM convolutions (conv_tc.cu, conv_tc2.cu).
+// conv_tc.cuh — shared definitions of the tensor-core tap-GEMM convolutions (conv_tc.cu = host side and
+// weight packing, conv_tc2.cu = the persistent kernel).
 #pragma once
 #include "common.cuh"
 #include <cuda.h>
 
 namespace m2 {
 
-constexpr int CT_BM = 128;            // GEMM rows (input positions) per CTA, including the halo
+constexpr int CT_BM = 128;            // GEMM rows (input positions) per tile, including the halo
 constexpr int CT_HALO = 4;            // rows on each side that are computed but not stored (|tap shift| <= 4)
-constexpr int CT_STEP = CT_BM - 2 * CT_HALO;   // 120 output positions per CTA; tile starts stay 16-B aligned for TMA
+constexpr int CT_STEP = CT_BM - 2 * CT_HALO;   // 120 output positions per tile; tile starts stay 16-B aligned for TMA
 constexpr int CT_CK = 16;             // input channels per pipeline chunk
-constexpr int CT_STAGES = 2;             // 2 x (16 KB activations + <= 32 KB weights): two CTAs per SM overlap each other's epilogue
-constexpr int CT_THREADS = 128;
-constexpr uint32_t CT_ABOX = CT_CK * 128;                        // one TMA box: 16 rows x 128 B
-constexpr uint32_t CT_A_STAGE = 2u * 4u * CT_ABOX;               // planes x boxes = 16 KB
+constexpr uint32_t CT_ABOX = CT_CK * 128;      // one TMA box: 16 channel rows x 32 positions x 4 B
+constexpr uint32_t CT_RAW_STAGE = 4u * CT_ABOX;    // 128 positions of fp32 as delivered by TMA = 8 KB
+constexpr uint32_t CT_A_STAGE = 2u * CT_RAW_STAGE; // the same tile split into TF32 hi and lo = 16 KB
 
 struct TapGemmArgs {
   int CI, L_in, B, n_chunks;
   int tap_shift[3], tap_rows[3], tap_wrow[3], tap_dcol[3];
   int rows_total;            // weight rows per (chunk, plane) image
-  int n_cols;                // accumulator columns per CTA
-  int tmem_cols;             // power of two >= 32
+  int n_cols;                // accumulator columns per tile
+  int tmem_cols;             // allocation (power of two), n_bufs * n_cols <= tmem_cols
+  int n_bufs;                // accumulator buffers in TMEM (2..4)
   const float* wblob;        // [n_tile][chunk][plane][rows_total][16] (image order)
   int r, co_tile, CO;
   int L_out, Lp_out;
   const float* bias;
   int act;                   // 0 none, 1 leaky_relu(0.1)
-  const float* res_hi; const float* res_lo; int Lp_res;
-  float* out_hi; float* out_lo;   // out_lo == nullptr -> plain fp32 into out_hi
-  // persistent kernel (conv_tc2.cu)
-  int n_tiles, m_tiles, w_resident, ring_stages;
+  const float* residual; int Lp_res;   // plain fp32 [B][CO][Lp_res] or null
+  float* out;                // plain fp32 [B][CO][Lp_out]
+  int n_tiles, m_tiles, w_resident;
+  int raw_stages, split_stages;
 };
 
-// ---- PTX helpers (same conventions as attention_tc.cu) ------------------------------------------
+// ---- PTX helpers -------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t ct_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void ct_mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
 __device__ __forceinline__ void ct_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ct_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void ct_wait(uint32_t bar, uint32_t parity, int* dbg, int code, int chunk) {
   for (uint32_t it = 0; it < (1u << 24); ++it) {
@@ -78,8 +82,14 @@ __device__ __forceinline__ void ct_ld8(uint32_t taddr, uint32_t* r) {
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                : "r"(taddr));
 }
+__device__ __forceinline__ void ct_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
 __device__ __forceinline__ float ct_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
-
 
 int launch_tapgemm_persistent(const CUtensorMap& tmap, TapGemmArgs& a, int stage, cudaStream_t s);
 

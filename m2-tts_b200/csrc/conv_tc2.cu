@@ -1,36 +1,30 @@
-// conv_tc2.cu — persistent, warp-specialised tap-GEMM for the vocoder convolutions (tcgen05 + TMEM + TMA).
-// Same math and operand layouts as conv_tc.cu (see there), organised for throughput:
+// conv_tc2.cu — persistent, warp-specialised tap-GEMM kernel for the vocoder convolutions
+// (tcgen05 + TMEM + TMA). Math and operand layouts: see conv_tc.cu. Organisation:
 //   * one CTA per SM loops over (utterance, 120-position) tiles of ONE output-channel tile, so the packed
 //     weight images stay RESIDENT in shared memory whenever they fit (every layer but the widest ones);
-//   * warp 0 = TMA producer (activation boxes, and weight chunks when streaming), warp 1 = UMMA issuer,
-//     warps 2-5 / 6-9 = two epilogue groups that take alternate tiles (= alternate TMEM accumulator buffers),
-//     so two epilogues and the next tile's UMMAs are in flight at once; ring of activation stages between producer and issuer;
-//   * epilogue: TMEM -> staging tile in shared memory -> out[t] = sum_tap D_tap[t + shift_tap] (+bias,
-//     LeakyReLU, +residual) -> global (hi/lo planes for the next tensor-core layer, or plain fp32).
+//   * activations stay PLAIN fp32 in HBM. warp 0 streams them with TMA (box = 32 positions x 16 channels,
+//     128B swizzle / 32B atoms) into a raw ring; warps 2-3 split every raw tile into TF32 hi and lo tiles
+//     (same swizzled addresses, so the split is a flat element-wise pass) and hand them to the tensor pipe
+//     through fence.proxy.async + mbarrier; warp 1 issues the UMMAs (3 taps x {hi*hi, hi*lo, lo*hi} x 2 k-steps
+//     per 16-channel chunk) into one of up to four TMEM accumulator buffers;
+//   * warps 4-7 / 8-11 are two epilogue groups taking alternate tiles: TMEM -> staging tile in shared memory
+//     -> out[t] = sum_tap D_tap[t + shift_tap] + bias (LeakyReLU, + residual) -> plain fp32 in HBM.
+// HBM traffic is therefore the algorithmic minimum per layer (input once, residual once, output once).
 #include "conv_tc.cuh"
 #include <math.h>
 
 namespace m2 {
 
-constexpr int P_THREADS = 320;            // producer warp, UMMA warp, 2 x 4 epilogue warps
-constexpr int P_STAGING = 64 * 128 * 4;   // per epilogue group: 3 taps x 16 columns (or 2r x 8 channel rows) x 128 rows
+constexpr int P_THREADS = 384;            // producer, UMMA issuer, 2 splitter warps, 2 x 4 epilogue warps
+constexpr int P_SPLIT_WARPS = 2;
 
-__device__ __forceinline__ void p_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
 __device__ __forceinline__ void p_epi_sync(int group) { asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory"); }
-__device__ __forceinline__ void p_ld16(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-}
 
 struct PersistSmem {   // byte offsets from the 1024-aligned base, computed on the host
-  uint32_t a_ring, w_region, staging, bars;
-  uint32_t stage_bytes;      // bytes per ring stage (activations, + weights when streaming)
-  uint32_t w_stage;          // bytes of one chunk's weight image (hi + lo)
+  uint32_t raw_ring, split_ring, w_region, staging, bars;
+  uint32_t split_stage_bytes;   // hi+lo tile (+ weight chunk when streaming)
+  uint32_t w_stage;             // bytes of one chunk's weight image (hi + lo)
+  uint32_t staging_group;       // bytes of one epilogue group's staging tile
   uint32_t total;
 };
 
@@ -38,14 +32,16 @@ __global__ void __launch_bounds__(P_THREADS, 1)
 tapgemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const TapGemmArgs a, const PersistSmem L, int* dbg) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (ct_smem_u32(smem_raw) + 1023u) & ~1023u;
-  float* stage_f = reinterpret_cast<float*>(smem_raw + (sbase - ct_smem_u32(smem_raw)) + L.staging);
-  const int S = a.ring_stages;
-  const uint32_t bar_full = sbase + L.bars;            // [S]
-  const uint32_t bar_empty = bar_full + 8 * S;         // [S]
-  const uint32_t bar_wfull = bar_empty + 8 * S;        // resident weights landed
-  const uint32_t bar_accf = bar_wfull + 8;             // [2] accumulator buffer full
-  const uint32_t bar_acce = bar_accf + 16;             // [2] accumulator buffer drained by the epilogue
-  const uint32_t tmem_slot = bar_acce + 16;
+  uint8_t* gbase = smem_raw + (sbase - ct_smem_u32(smem_raw));     // generic pointer to the aligned base
+  const int R = a.raw_stages, S = a.split_stages, NB = a.n_bufs;
+  const uint32_t bar_rawf = sbase + L.bars;              // [R] raw tile landed (TMA tx)
+  const uint32_t bar_rawe = bar_rawf + 8 * R;            // [R] raw tile consumed by both splitter warps
+  const uint32_t bar_splf = bar_rawe + 8 * R;            // [S] hi/lo tile written by both splitter warps
+  const uint32_t bar_sple = bar_splf + 8 * S;            // [S] hi/lo tile (and streamed weights) consumed by the UMMAs
+  const uint32_t bar_wf = bar_sple + 8 * S;              // [S] streamed weight chunk landed / [0] resident weights landed
+  const uint32_t bar_accf = bar_wf + 8 * S;              // [NB] accumulator buffer complete
+  const uint32_t bar_acce = bar_accf + 8 * NB;           // [NB] accumulator buffer drained by the epilogue
+  const uint32_t tmem_slot = bar_acce + 8 * NB;
   const uint32_t w_plane_bytes = (uint32_t)a.rows_total * 64u;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -56,10 +52,11 @@ tapgemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const TapG
   const int total_mt = a.B * a.m_tiles;
 
   if (tid == 0) {
-    for (int s = 0; s < S; ++s) { ct_mbar_init(bar_full + 8 * s, 1); ct_mbar_init(bar_empty + 8 * s, 1); }
-    ct_mbar_init(bar_wfull, 1);
-    ct_mbar_init(bar_accf, 1); ct_mbar_init(bar_accf + 8, 1);
-    ct_mbar_init(bar_acce, 4); ct_mbar_init(bar_acce + 8, 4);     // one arrival per epilogue warp
+    for (int s = 0; s < R; ++s) { ct_mbar_init(bar_rawf + 8 * s, 1); ct_mbar_init(bar_rawe + 8 * s, P_SPLIT_WARPS); }
+    for (int s = 0; s < S; ++s) {
+      ct_mbar_init(bar_splf + 8 * s, P_SPLIT_WARPS); ct_mbar_init(bar_sple + 8 * s, 1); ct_mbar_init(bar_wf + 8 * s, 1);
+    }
+    for (int s = 0; s < NB; ++s) { ct_mbar_init(bar_accf + 8 * s, 1); ct_mbar_init(bar_acce + 8 * s, 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
   }
@@ -77,46 +74,49 @@ tapgemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const TapG
 
   if (warp == 0) {
     if (lane == 0) {
-      // ===== producer =====
+      // ===== producer: plain fp32 activation boxes (+ weight chunks when they are not resident) =====
       if (a.w_resident) {
-        ct_expect_tx(bar_wfull, (uint32_t)a.n_chunks * L.w_stage);
+        ct_expect_tx(bar_wf, (uint32_t)a.n_chunks * L.w_stage);
         for (int c = 0; c < a.n_chunks; ++c)
-          ct_bulk(sbase + L.w_region + (uint32_t)c * L.w_stage, wsrc + (size_t)c * (2 * a.rows_total * 16), L.w_stage, bar_wfull);
+          ct_bulk(sbase + L.w_region + (uint32_t)c * L.w_stage, wsrc + (size_t)c * (2 * a.rows_total * 16), L.w_stage, bar_wf);
       }
       int it = 0;
       for (int j = first; j < total_mt; j += cpg) {
         const int b = j / a.m_tiles, start = (j % a.m_tiles) * CT_STEP - CT_HALO;
         for (int c = 0; c < a.n_chunks; ++c, ++it) {
-          const int s = it % S;
-          if (it >= S) ct_wait(bar_empty + 8 * s, (uint32_t)((it / S - 1) & 1), dbg, 1, c);
-          const uint32_t sA = sbase + L.a_ring + (uint32_t)s * L.stage_bytes, full = bar_full + 8 * s;
-          ct_expect_tx(full, CT_A_STAGE + (a.w_resident ? 0u : L.w_stage));
+          const int rs = it % R;
+          if (it >= R) ct_wait(bar_rawe + 8 * rs, (uint32_t)((it / R - 1) & 1), dbg, 1, c);
+          const uint32_t dst = sbase + L.raw_ring + (uint32_t)rs * CT_RAW_STAGE, full = bar_rawf + 8 * rs;
+          ct_expect_tx(full, CT_RAW_STAGE);
+          const int row = b * a.CI + c * CT_CK;
 #pragma unroll
-          for (int plane = 0; plane < 2; ++plane) {
-            const int row = (plane * a.B + b) * a.CI + c * CT_CK;
-#pragma unroll
-            for (int x = 0; x < 4; ++x)
-              ct_tma_2d(sA + (uint32_t)(plane * 4 + x) * CT_ABOX, &tmap_a, start + 32 * x, row, full);
+          for (int x = 0; x < 4; ++x) ct_tma_2d(dst + (uint32_t)x * CT_ABOX, &tmap_a, start + 32 * x, row, full);
+          if (!a.w_resident) {
+            const int ss = it % S;
+            if (it >= S) ct_wait(bar_sple + 8 * ss, (uint32_t)((it / S - 1) & 1), dbg, 6, c);
+            ct_expect_tx(bar_wf + 8 * ss, L.w_stage);
+            ct_bulk(sbase + L.split_ring + (uint32_t)ss * L.split_stage_bytes + CT_A_STAGE,
+                    wsrc + (size_t)c * (2 * a.rows_total * 16), L.w_stage, bar_wf + 8 * ss);
           }
-          if (!a.w_resident) ct_bulk(sA + CT_A_STAGE, wsrc + (size_t)c * (2 * a.rows_total * 16), L.w_stage, full);
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // ===== UMMA issuer =====
-      if (a.w_resident) { ct_wait(bar_wfull, 0, dbg, 4, 0); }
+      if (a.w_resident) ct_wait(bar_wf, 0, dbg, 4, 0);
       int it = 0, t = 0;
       for (int j = first; j < total_mt; j += cpg, ++t) {
-        const int buf = t & 1;
-        if (t >= 2) ct_wait(bar_acce + 8 * buf, (uint32_t)((t / 2 - 1) & 1), dbg, 5, t);
+        const int buf = t % NB;
+        if (t >= NB) ct_wait(bar_acce + 8 * buf, (uint32_t)((t / NB - 1) & 1), dbg, 5, t);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t dbase = tmem_base + (uint32_t)(buf * a.n_cols);
         for (int c = 0; c < a.n_chunks; ++c, ++it) {
-          const int s = it % S;
-          ct_wait(bar_full + 8 * s, (uint32_t)((it / S) & 1), dbg, 2, c);
+          const int ss = it % S;
+          ct_wait(bar_splf + 8 * ss, (uint32_t)((it / S) & 1), dbg, 2, c);
+          if (!a.w_resident) ct_wait(bar_wf + 8 * ss, (uint32_t)((it / S) & 1), dbg, 7, c);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t sA = sbase + L.a_ring + (uint32_t)s * L.stage_bytes;
+          const uint32_t sA = sbase + L.split_ring + (uint32_t)ss * L.split_stage_bytes;
           const uint32_t sW = a.w_resident ? (sbase + L.w_region + (uint32_t)c * L.w_stage) : (sA + CT_A_STAGE);
 #pragma unroll
           for (int tap = 0; tap < 3; ++tap) {
@@ -128,57 +128,86 @@ tapgemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const TapG
               const uint32_t ap = (term == 2) ? 1u : 0u, wp = (term == 1) ? 1u : 0u;
 #pragma unroll
               for (int ks = 0; ks < CT_CK / 8; ++ks) {
-                const uint64_t ad = ct_desc(sA + (ap * 4) * CT_ABOX + ks * 1024u, CT_ABOX, 512u, 1u);
+                // activations: MN-major, 128B swizzle / 32B atoms: LBO = next 32 positions (next box), SBO = next 4 channels
+                const uint64_t ad = ct_desc(sA + ap * CT_RAW_STAGE + ks * 1024u, CT_ABOX, 512u, 1u);
+                // weights: K-major, no swizzle (8 x 16 B core matrices): LBO = next 4 channels, SBO = next 8 rows
                 const uint64_t bd = ct_desc(sW + wp * w_plane_bytes + wrow_off + ks * 256u, 128u, 512u, 0u);
                 ct_mma(dbase + (uint32_t)a.tap_dcol[tap], ad, bd, idesc, (c | term | ks) ? 1u : 0u);
               }
             }
           }
-          ct_commit(bar_empty + 8 * s);
+          ct_commit(bar_sple + 8 * ss);
         }
         ct_commit(bar_accf + 8 * buf);
       }
     }
+  } else if (warp < 2 + P_SPLIT_WARPS) {
+    // ===== splitters: raw fp32 tile -> TF32 hi tile + lo tile (flat, the swizzle is address-preserving) =====
+    const int sw = warp - 2;
+    int it = 0;
+    for (int j = first; j < total_mt; j += cpg) {
+      for (int c = 0; c < a.n_chunks; ++c, ++it) {
+        const int rs = it % R, ss = it % S;
+        ct_wait(bar_rawf + 8 * rs, (uint32_t)((it / R) & 1), dbg, 8, c);
+        if (it >= S) ct_wait(bar_sple + 8 * ss, (uint32_t)((it / S - 1) & 1), dbg, 9, c);
+        __syncwarp();
+        const float4* src = reinterpret_cast<const float4*>(gbase + L.raw_ring + (uint32_t)rs * CT_RAW_STAGE);
+        float4* dhi = reinterpret_cast<float4*>(gbase + L.split_ring + (uint32_t)ss * L.split_stage_bytes);
+        float4* dlo = dhi + CT_RAW_STAGE / 16;
+        // 512 float4 per tile, 256 per warp, 8 per lane
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int i = sw * 256 + k * 32 + lane;
+          const float4 v = src[i];
+          float4 h, l;
+          h.x = ct_hi(v.x); h.y = ct_hi(v.y); h.z = ct_hi(v.z); h.w = ct_hi(v.w);
+          l.x = ct_hi(v.x - h.x); l.y = ct_hi(v.y - h.y); l.z = ct_hi(v.z - h.z); l.w = ct_hi(v.w - h.w);
+          dhi[i] = h; dlo[i] = l;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor pipe
+        __syncwarp();
+        if (lane == 0) { ct_arrive(bar_splf + 8 * ss); ct_arrive(bar_rawe + 8 * rs); }
+      }
+    }
   } else {
-    // ===== epilogue: group g = (warp-2)/4 takes tiles t with t % 2 == g, i.e. always accumulator buffer g =====
-    const int grp = (warp - 2) >> 2;
+    // ===== epilogue: group g = (warp-4)/4 takes tiles t with t % 2 == g; accumulator buffer = t % NB =====
+    const int grp = (warp - 4) >> 2;
     const int qtr = warp & 3;                            // TMEM lane quarter this warp may access
     const int m = qtr * 32 + lane;                       // GEMM row = input position start + m
-    const int buf = grp;
-    float* stg = stage_f + grp * (P_STAGING / 4);
-    const uint32_t t_lane = tmem_base + ((uint32_t)(qtr * 32) << 16) + (uint32_t)(buf * a.n_cols);
+    float* stg = reinterpret_cast<float*>(gbase + L.staging + (uint32_t)grp * L.staging_group);
     const int co0 = ntile * a.co_tile;
     int t = 0;
     for (int j = first; j < total_mt; j += cpg, ++t) {
       if ((t & 1) != grp) continue;
+      const int buf = t % NB;
+      const uint32_t t_lane = tmem_base + ((uint32_t)(qtr * 32) << 16) + (uint32_t)(buf * a.n_cols);
       const int b = j / a.m_tiles, start = (j % a.m_tiles) * CT_STEP - CT_HALO;
       const int q = start + m;
       const bool own = (m >= CT_HALO) && (m < CT_BM - CT_HALO) && (q < a.L_in);
-      ct_wait(bar_accf + 8 * buf, (uint32_t)((t / 2) & 1), dbg, 3, t);
+      ct_wait(bar_accf + 8 * buf, (uint32_t)((t / NB) & 1), dbg, 3, t);
       __syncwarp();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
       if (a.r == 1) {
         const int s0 = a.tap_shift[0], s1 = a.tap_shift[1], s2 = a.tap_shift[2];
         for (int c0 = 0; c0 < a.co_tile; c0 += 16) {
-          // residual loads first: 32 independent read-only loads in flight while the tile is staged
+          // residual loads first: 16 independent read-only loads in flight while the tile is staged
           float rsd[16];
 #pragma unroll
           for (int c = 0; c < 16; ++c) rsd[c] = 0.f;
-          if (own && a.res_hi != nullptr) {
-            const float* __restrict__ rh = a.res_hi + ((size_t)b * a.CO + co0 + c0) * a.Lp_res + q;
-            const float* __restrict__ rl = a.res_lo + ((size_t)b * a.CO + co0 + c0) * a.Lp_res + q;
+          if (own && a.residual != nullptr) {
+            const float* __restrict__ rp = a.residual + ((size_t)b * a.CO + co0 + c0) * a.Lp_res + q;
 #pragma unroll
-            for (int c = 0; c < 16; ++c) rsd[c] = __ldg(rh + (size_t)c * a.Lp_res) + __ldg(rl + (size_t)c * a.Lp_res);
+            for (int c = 0; c < 16; ++c) rsd[c] = __ldg(rp + (size_t)c * a.Lp_res);
           }
           uint32_t v[3][16];
 #pragma unroll
-          for (int tap = 0; tap < 3; ++tap) p_ld16(t_lane + (uint32_t)(a.tap_dcol[tap] + c0), v[tap]);
+          for (int tap = 0; tap < 3; ++tap) ct_ld16(t_lane + (uint32_t)(a.tap_dcol[tap] + c0), v[tap]);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           if (c0 + 16 >= a.co_tile) {   // last TMEM read of this tile: hand the accumulator buffer back
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
-            if (lane == 0) p_arrive(bar_acce + 8 * buf);
+            if (lane == 0) ct_arrive(bar_acce + 8 * buf);
           }
 #pragma unroll
           for (int tap = 0; tap < 3; ++tap)
@@ -191,29 +220,26 @@ tapgemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const TapG
               const int co = co0 + c0 + c;
               float x = stg[((c) << 7) + m + s0] + stg[((16 + c) << 7) + m + s1] + stg[((32 + c) << 7) + m + s2] + __ldg(a.bias + co);
               if (a.act == 1) x = x > 0.f ? x : 0.1f * x;
-              x += rsd[c];
-              const size_t oo = ((size_t)b * a.CO + co) * a.Lp_out + q;
-              if (a.out_lo != nullptr) { const float h = ct_hi(x); a.out_hi[oo] = h; a.out_lo[oo] = ct_hi(x - h); }
-              else a.out_hi[oo] = x;
+              a.out[((size_t)b * a.CO + co) * a.Lp_out + q] = x + rsd[c];
             }
           }
           p_epi_sync(grp);
         }
       } else {
-        // transposed conv, r in {2,4}: D0 [0, r*ct) phase-major; D1 [r*ct, +r/2*ct) phases < r/2 (row q-1);
-        // D2 next r/2*ct columns, phases >= r/2 (row q+1). Staging rows: group g of 8 channels:
-        // g < r: D0 phase g; g >= r: D1/D2 phase g - r.
+        // transposed conv, r in {2,4}: accumulator columns D0 [0, r*ct) phase-major, D1 [r*ct, +r/2*ct) phases < r/2
+        // (needs row q-1), D2 next r/2*ct columns, phases >= r/2 (needs row q+1); column = g*ct + channel with
+        // g < r: D0 phase g, g >= r: D1/D2 phase g - r. Staging rows: g*8 + channel.
         const int ct = a.co_tile, r = a.r, hr = a.r / 2, groups = 2 * a.r;
         for (int c0 = 0; c0 < ct; c0 += 8) {
           uint32_t v[8][8];
 #pragma unroll
           for (int g = 0; g < 8; ++g)
-            if (g < groups) ct_ld8(t_lane + (uint32_t)(g * ct + c0), v[g]);   // D0|D1|D2 are contiguous: column = g*ct + c
+            if (g < groups) ct_ld8(t_lane + (uint32_t)(g * ct + c0), v[g]);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           if (c0 + 8 >= ct) {
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
-            if (lane == 0) p_arrive(bar_acce + 8 * buf);
+            if (lane == 0) ct_arrive(bar_acce + 8 * buf);
           }
 #pragma unroll
           for (int g = 0; g < 8; ++g)
@@ -238,26 +264,9 @@ tapgemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const TapG
                   x[p] = 0.f;
                 }
               }
-              const size_t oo = ((size_t)b * a.CO + co) * a.Lp_out + (size_t)r * q;
-              if (r == 4) {
-                if (a.out_lo != nullptr) {
-                  float h[4], l[4];
-#pragma unroll
-                  for (int p = 0; p < 4; ++p) { h[p] = ct_hi(x[p]); l[p] = ct_hi(x[p] - h[p]); }
-                  *reinterpret_cast<float4*>(a.out_hi + oo) = make_float4(h[0], h[1], h[2], h[3]);
-                  *reinterpret_cast<float4*>(a.out_lo + oo) = make_float4(l[0], l[1], l[2], l[3]);
-                } else {
-                  *reinterpret_cast<float4*>(a.out_hi + oo) = make_float4(x[0], x[1], x[2], x[3]);
-                }
-              } else {
-                if (a.out_lo != nullptr) {
-                  const float h0 = ct_hi(x[0]), h1 = ct_hi(x[1]);
-                  *reinterpret_cast<float2*>(a.out_hi + oo) = make_float2(h0, h1);
-                  *reinterpret_cast<float2*>(a.out_lo + oo) = make_float2(ct_hi(x[0] - h0), ct_hi(x[1] - h1));
-                } else {
-                  *reinterpret_cast<float2*>(a.out_hi + oo) = make_float2(x[0], x[1]);
-                }
-              }
+              float* op = a.out + ((size_t)b * a.CO + co) * a.Lp_out + (size_t)r * q;
+              if (r == 4) *reinterpret_cast<float4*>(op) = make_float4(x[0], x[1], x[2], x[3]);
+              else *reinterpret_cast<float2*>(op) = make_float2(x[0], x[1]);
             }
           }
           p_epi_sync(grp);
@@ -279,31 +288,36 @@ int launch_tapgemm_persistent(const CUtensorMap& tmap, TapGemmArgs& a, int stage
                "conv_tc: tap shift %d exceeds the halo", a.tap_shift[j]);
   M2_REQUIRE(2 * a.n_cols <= 512, M2TTS_E_UNSUPPORTED, "conv_tc: %d accumulator columns do not double-buffer", a.n_cols);
   a.m_tiles = ceil_div(a.L_in, CT_STEP);
+  a.n_bufs = 512 / a.n_cols;
+  if (a.n_bufs > 4) a.n_bufs = 4;
   a.tmem_cols = 32;
-  while (a.tmem_cols < 2 * a.n_cols) a.tmem_cols <<= 1;
+  while (a.tmem_cols < a.n_bufs * a.n_cols) a.tmem_cols <<= 1;
   PersistSmem L{};
   L.w_stage = 2u * (uint32_t)a.rows_total * 64u;
-  const uint32_t staging = 2u * (uint32_t)P_STAGING;   // one staging tile per epilogue group
-  const uint32_t budget = 226u * 1024u - 1024u /*alignment*/ - 256u /*barriers*/ - staging;
+  L.staging_group = (a.r == 1 ? 48u : (uint32_t)(2 * a.r * 8)) * 128u * 4u;   // conv: 3 taps x 16 columns; convT: 2r x 8 channels
+  const uint32_t staging = 2u * L.staging_group;
+  a.raw_stages = 3;
+  const uint32_t fixed = 1024u /*alignment*/ + 512u /*barriers*/ + staging + (uint32_t)a.raw_stages * CT_RAW_STAGE;
+  const uint32_t budget = 227u * 1024u - fixed;
   const uint32_t w_all = (uint32_t)a.n_chunks * L.w_stage;
   if (w_all + 2u * CT_A_STAGE <= budget) {
     a.w_resident = 1;
-    L.stage_bytes = CT_A_STAGE;
+    L.split_stage_bytes = CT_A_STAGE;
     int st = (int)((budget - w_all) / CT_A_STAGE);
-    a.ring_stages = st > 6 ? 6 : st;
-    L.a_ring = 0; L.w_region = (uint32_t)a.ring_stages * CT_A_STAGE;
-    L.staging = L.w_region + ((w_all + 1023u) & ~1023u);
+    a.split_stages = st > 4 ? 4 : st;
   } else {
     a.w_resident = 0;
-    L.stage_bytes = CT_A_STAGE + ((L.w_stage + 1023u) & ~1023u);
-    int st = (int)(budget / L.stage_bytes);
+    L.split_stage_bytes = CT_A_STAGE + ((L.w_stage + 1023u) & ~1023u);
+    int st = (int)(budget / L.split_stage_bytes);
     M2_REQUIRE(st >= 2, M2TTS_E_UNSUPPORTED, "conv_tc: weight chunk of %u B does not fit a 2-stage ring", L.w_stage);
-    a.ring_stages = st > 4 ? 4 : st;
-    L.a_ring = 0; L.w_region = 0;
-    L.staging = (uint32_t)a.ring_stages * L.stage_bytes;
+    a.split_stages = st > 4 ? 4 : st;
   }
+  L.raw_ring = 0;
+  L.split_ring = (uint32_t)a.raw_stages * CT_RAW_STAGE;
+  L.w_region = L.split_ring + (uint32_t)a.split_stages * L.split_stage_bytes;
+  L.staging = L.w_region + (a.w_resident ? ((w_all + 1023u) & ~1023u) : 0u);
   L.bars = L.staging + staging;
-  L.total = L.bars + 256u + 1024u;
+  L.total = L.bars + 512u + 1024u;
   M2_REQUIRE(L.total <= 227u * 1024u, M2TTS_E_UNSUPPORTED, "conv_tc: %u B of shared memory", L.total);
   M2_CUDA_OK(allow_smem(tapgemm_persistent_kernel, L.total));
   const int total_mt = a.B * a.m_tiles;

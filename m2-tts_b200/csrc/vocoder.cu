@@ -23,7 +23,6 @@ struct ConvArgs {
   const float* residual;  // [B,CO,L] or null
   float* y;               // [B,CO,L_out]
   int CI, CO, L, dil, act;
-  float* y_lo;            // non-null: write the output as TF32 hi/lo planes (y = hi plane) for the tensor-core convs
   int y_pitch;            // output row pitch in floats (0 = L)
 };
 
@@ -147,7 +146,7 @@ __global__ void __launch_bounds__(VC_THREADS) conv3_kernel(ConvArgs a) {
   // ---- epilogue: bias, activation, residual, store (float4 along time when aligned) ----
   const int P = a.y_pitch ? a.y_pitch : L;
   const bool svec = ((P & 3) == 0) && ((L & 3) == 0) && ((((uintptr_t)a.y) & 15) == 0) &&
-                    (a.residual == nullptr || (((uintptr_t)a.residual) & 15) == 0) && a.y_lo == nullptr;
+                    (a.residual == nullptr || (((uintptr_t)a.residual) & 15) == 0);
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
     const int co = co0 + ty * 8 + c;
@@ -172,14 +171,7 @@ __global__ void __launch_bounds__(VC_THREADS) conv3_kernel(ConvArgs a) {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
           if (t + i < L) {
-            const float o = v[i] + (a.residual ? a.residual[resoff + t + i] : 0.f);
-            if (a.y_lo != nullptr) {
-              const float hi = __uint_as_float(__float_as_uint(o) & 0xFFFFE000u);
-              a.y[rowoff + t + i] = hi;
-              a.y_lo[rowoff + t + i] = __uint_as_float(__float_as_uint(o - hi) & 0xFFFFE000u);
-            } else {
-              a.y[rowoff + t + i] = o;
-            }
+            a.y[rowoff + t + i] = v[i] + (a.residual ? a.residual[resoff + t + i] : 0.f);
           }
       }
     }
@@ -461,8 +453,8 @@ extern "C" int m2tts_conv_transpose1d_lrelu(const float* x, const float* w, cons
 
 extern "C" size_t m2tts_vocoder_workspace_bytes(int B, int T, int M, int C) {
   if (B <= 0 || T <= 0 || M <= 0 || C < 16) return 0;
-  // widest activation: 4*C*T floats per utterance; every buffer can hold a hi/lo plane pair
-  const size_t act = align_up((size_t)2 * B * C * ((size_t)T + 4) * 4 * sizeof(float), 256);
+  // widest activation: 4*C*T floats per utterance (+ row-pitch padding of the first tensor)
+  const size_t act = align_up((size_t)B * C * ((size_t)T + 4) * 4 * sizeof(float), 256);
   size_t wts = (size_t)C * M * 3;
   static const int rates[4] = {4, 4, 2, 2};
   for (int j = 0, c = C / 2; j < 4; ++j, c /= 2)
@@ -484,7 +476,7 @@ extern "C" int m2tts_vocoder_forward(const m2tts_vocoder_weights* w, const float
   cudaStream_t s = (cudaStream_t)stream;
   static const int rates[4] = {4, 4, 2, 2};
   Carver cv(workspace, workspace_bytes);
-  const size_t act = (size_t)2 * B * C * ((size_t)T + 4) * 4;   // floats; room for a hi/lo plane pair
+  const size_t act = (size_t)B * C * ((size_t)T + 4) * 4;   // floats
   float* bufA = cv.take<float>(act);
   float* bufB = cv.take<float>(act);
   float* bufC = cv.take<float>(act);
@@ -519,29 +511,25 @@ extern "C" int m2tts_vocoder_forward(const m2tts_vocoder_weights* w, const float
     }
   }
 
-  // input conv: mel (strided) -> bufA, as hi/lo planes when stage 0 is a tensor-core stage
+  // input conv: mel (strided) -> bufA [B,C,Lp] (row pitch padded to a multiple of 4 floats for the TMA tensor maps)
   int L = T, c_in = C;
-  int Lp = (L + 3) & ~3;
+  int Lp = tc[0] ? ((L + 3) & ~3) : L;
   {
     ConvArgs a{mel, stride_b, stride_m, stride_t, in_wp, w->in_b, nullptr, bufA, M, C, T, 1, 0};
-    if (tc[0]) { a.y_lo = bufA + (size_t)B * C * Lp; a.y_pitch = Lp; }
+    a.y_pitch = Lp;
     if ((rc = launch_conv3(a, B, M2TTS_STAGE_VOC_IN, s))) return rc;
   }
   for (int j = 0; j < 4; ++j) {
     const int r = rates[j], c = c_in / 2, Lo = L * r;
     const int dil = w->res_dilation[j] > 0 ? w->res_dilation[j] : 1;
     if (tc[j]) {
-      // planes in bufA (pitch Lp) -> up -> planes bufB -> conv1 -> planes bufC -> conv2 (+ residual bufB) -> bufA
-      const int Lpo = (Lo + 3) & ~3;
-      const size_t po = (size_t)B * c * Lpo;   // plane stride of this stage's tensors
-      if ((rc = launch_convT_tc(bufA, Lp, w->up_w[j], upb[j], w->up_b[j], bufB, bufB + po, Lpo, B, c_in, c, L, r, s))) return rc;
-      if ((rc = launch_conv3_tc(bufB, Lpo, w->res1_w[j], r1b[j], w->res1_b[j], nullptr, nullptr, 0, bufC, bufC + po, Lpo,
-                                B, c, c, Lo, dil, 1, M2TTS_STAGE_VOC_RES1, s))) return rc;
-      float* out_lo = tc[j + 1] ? bufA + po : nullptr;   // next stage on tensor cores -> planes, else plain fp32
-      const int out_pitch = tc[j + 1] ? Lpo : Lo;
-      if ((rc = launch_conv3_tc(bufC, Lpo, w->res2_w[j], r2b[j], w->res2_b[j], bufB, bufB + po, Lpo, bufA, out_lo, out_pitch,
-                                B, c, c, Lo, 1, 0, M2TTS_STAGE_VOC_RES2, s))) return rc;
-      Lp = Lpo;
+      // bufA (pitch Lp) -> up -> bufB -> conv1 -> bufC -> conv2 (+ residual bufB) -> bufA; Lo = r*L is a multiple of 4
+      if ((rc = launch_convT_tc(bufA, Lp, w->up_w[j], upb[j], w->up_b[j], bufB, Lo, B, c_in, c, L, r, s))) return rc;
+      if ((rc = launch_conv3_tc(bufB, Lo, w->res1_w[j], r1b[j], w->res1_b[j], nullptr, 0, bufC, Lo, B, c, c, Lo, dil, 1,
+                                M2TTS_STAGE_VOC_RES1, s))) return rc;
+      if ((rc = launch_conv3_tc(bufC, Lo, w->res2_w[j], r2b[j], w->res2_b[j], bufB, Lo, bufA, Lo, B, c, c, Lo, 1, 0,
+                                M2TTS_STAGE_VOC_RES2, s))) return rc;
+      Lp = Lo;
     } else {
       {  // bufB = lrelu(convT(bufA))
         ConvArgs a{bufA, (long long)c_in * L, L, 1, w->up_w[j], w->up_b[j], nullptr, bufB, c_in, c, L, 1, 1};
@@ -555,6 +543,7 @@ extern "C" int m2tts_vocoder_forward(const m2tts_vocoder_weights* w, const float
         ConvArgs a{bufC, (long long)c * Lo, Lo, 1, r2p[j], w->res2_b[j], bufB, bufA, c, c, Lo, 1, 0};
         if ((rc = launch_conv3(a, B, M2TTS_STAGE_VOC_RES2, s))) return rc;
       }
+      Lp = Lo;
     }
     L = Lo; c_in = c;
   }
