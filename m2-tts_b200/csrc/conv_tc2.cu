@@ -80,79 +80,92 @@ tapgemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const TapG
         for (int c = 0; c < a.n_chunks; ++c)
           ct_bulk(sbase + L.w_region + (uint32_t)c * L.w_stage, wsrc + (size_t)c * (2 * a.rows_total * 16), L.w_stage, bar_wf);
       }
-      int it = 0;
+      uint32_t rs = 0, rs_round = 0, ss = 0, ss_round = 0;
+      const bool resident = a.w_resident != 0;
       for (int j = first; j < total_mt; j += cpg) {
         const int b = j / a.m_tiles, start = (j % a.m_tiles) * CT_STEP - CT_HALO;
-        for (int c = 0; c < a.n_chunks; ++c, ++it) {
-          const int rs = it % R;
-          if (it >= R) ct_wait(bar_rawe + 8 * rs, (uint32_t)((it / R - 1) & 1), dbg, 1, c);
-          const uint32_t dst = sbase + L.raw_ring + (uint32_t)rs * CT_RAW_STAGE, full = bar_rawf + 8 * rs;
+        for (int c = 0; c < a.n_chunks; ++c) {
+          if (rs_round > 0) ct_wait(bar_rawe + 8 * rs, (rs_round - 1) & 1u, dbg, 1, c);
+          const uint32_t dst = sbase + L.raw_ring + rs * CT_RAW_STAGE, full = bar_rawf + 8 * rs;
           ct_expect_tx(full, CT_RAW_STAGE);
           const int row = b * a.CI + c * CT_CK;
 #pragma unroll
           for (int x = 0; x < 4; ++x) ct_tma_2d(dst + (uint32_t)x * CT_ABOX, &tmap_a, start + 32 * x, row, full);
-          if (!a.w_resident) {
-            const int ss = it % S;
-            if (it >= S) ct_wait(bar_sple + 8 * ss, (uint32_t)((it / S - 1) & 1), dbg, 6, c);
+          if (!resident) {
+            if (ss_round > 0) ct_wait(bar_sple + 8 * ss, (ss_round - 1) & 1u, dbg, 6, c);
             ct_expect_tx(bar_wf + 8 * ss, L.w_stage);
-            ct_bulk(sbase + L.split_ring + (uint32_t)ss * L.split_stage_bytes + CT_A_STAGE,
+            ct_bulk(sbase + L.split_ring + ss * L.split_stage_bytes + CT_A_STAGE,
                     wsrc + (size_t)c * (2 * a.rows_total * 16), L.w_stage, bar_wf + 8 * ss);
           }
+          if (++rs == (uint32_t)R) { rs = 0; ++rs_round; }
+          if (++ss == (uint32_t)S) { ss = 0; ++ss_round; }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      // ===== UMMA issuer =====
+      // ===== UMMA issuer: one thread; everything loop-invariant is hoisted so a chunk is 18 x (add, UMMA) =====
       if (a.w_resident) ct_wait(bar_wf, 0, dbg, 4, 0);
-      int it = 0, t = 0;
-      for (int j = first; j < total_mt; j += cpg, ++t) {
-        const int buf = t % NB;
-        if (t >= NB) ct_wait(bar_acce + 8 * buf, (uint32_t)((t / NB - 1) & 1), dbg, 5, t);
+      uint32_t idesc[3], dcol[3], wrow16[3];
+#pragma unroll
+      for (int tap = 0; tap < 3; ++tap) {
+        idesc[tap] = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | ((uint32_t)(a.tap_rows[tap] >> 3) << 17) |
+                     ((uint32_t)(CT_BM >> 4) << 24);
+        dcol[tap] = (uint32_t)a.tap_dcol[tap];
+        wrow16[tap] = ((uint32_t)(a.tap_wrow[tap] >> 3) * 512u) >> 4;      // descriptor address units (16 B)
+      }
+      // activations: MN-major, 128B swizzle / 32B atoms: LBO = next 32 positions (next box), SBO = next 4 channels
+      const uint64_t a_tmpl = ct_desc(0u, CT_ABOX, 512u, 1u);
+      // weights: K-major, no swizzle (8 x 16 B core matrices): LBO = next 4 channels, SBO = next 8 rows
+      const uint64_t w_tmpl = ct_desc(0u, 128u, 512u, 0u);
+      const uint32_t wplane16 = w_plane_bytes >> 4;
+      const uint32_t n_chunks = (uint32_t)a.n_chunks;
+      const bool resident = a.w_resident != 0;
+      uint32_t ss = 0, ss_par = 0;            // split-ring stage and its phase parity
+      uint32_t buf = 0, buf_round = 0;        // accumulator buffer and how many times the ring of buffers wrapped
+      for (int j = first; j < total_mt; j += cpg) {
+        if (buf_round > 0) ct_wait(bar_acce + 8 * buf, (buf_round - 1) & 1u, dbg, 5, j);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t dbase = tmem_base + (uint32_t)(buf * a.n_cols);
-        for (int c = 0; c < a.n_chunks; ++c, ++it) {
-          const int ss = it % S;
-          ct_wait(bar_splf + 8 * ss, (uint32_t)((it / S) & 1), dbg, 2, c);
-          if (!a.w_resident) ct_wait(bar_wf + 8 * ss, (uint32_t)((it / S) & 1), dbg, 7, c);
+        const uint32_t dbase = tmem_base + buf * (uint32_t)a.n_cols;
+        for (uint32_t c = 0; c < n_chunks; ++c) {
+          ct_wait(bar_splf + 8 * ss, ss_par, dbg, 2, (int)c);
+          if (!resident) ct_wait(bar_wf + 8 * ss, ss_par, dbg, 7, (int)c);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t sA = sbase + L.split_ring + (uint32_t)ss * L.split_stage_bytes;
-          const uint32_t sW = a.w_resident ? (sbase + L.w_region + (uint32_t)c * L.w_stage) : (sA + CT_A_STAGE);
+          const uint32_t sA = sbase + L.split_ring + ss * L.split_stage_bytes;
+          const uint32_t sW = resident ? (sbase + L.w_region + c * L.w_stage) : (sA + CT_A_STAGE);
+          const uint64_t ad0 = a_tmpl | (uint64_t)((sA >> 4) & 0x3FFFu);
+          const uint64_t bd0 = w_tmpl | (uint64_t)((sW >> 4) & 0x3FFFu);
 #pragma unroll
           for (int tap = 0; tap < 3; ++tap) {
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | ((uint32_t)(a.tap_rows[tap] >> 3) << 17) |
-                                   ((uint32_t)(CT_BM >> 4) << 24);
-            const uint32_t wrow_off = (uint32_t)(a.tap_wrow[tap] >> 3) * 512u;
 #pragma unroll
             for (int term = 0; term < 3; ++term) {           // hi*hi, hi*lo, lo*hi
               const uint32_t ap = (term == 2) ? 1u : 0u, wp = (term == 1) ? 1u : 0u;
 #pragma unroll
               for (int ks = 0; ks < CT_CK / 8; ++ks) {
-                // activations: MN-major, 128B swizzle / 32B atoms: LBO = next 32 positions (next box), SBO = next 4 channels
-                const uint64_t ad = ct_desc(sA + ap * CT_RAW_STAGE + ks * 1024u, CT_ABOX, 512u, 1u);
-                // weights: K-major, no swizzle (8 x 16 B core matrices): LBO = next 4 channels, SBO = next 8 rows
-                const uint64_t bd = ct_desc(sW + wp * w_plane_bytes + wrow_off + ks * 256u, 128u, 512u, 0u);
-                ct_mma(dbase + (uint32_t)a.tap_dcol[tap], ad, bd, idesc, (c | term | ks) ? 1u : 0u);
+                const uint64_t ad = ad0 + (uint64_t)((ap * CT_RAW_STAGE + ks * 1024u) >> 4);
+                const uint64_t bd = bd0 + (uint64_t)(wp * wplane16 + wrow16[tap] + ks * 16u);
+                ct_mma(dbase + dcol[tap], ad, bd, idesc[tap], (c | (uint32_t)term | (uint32_t)ks) ? 1u : 0u);
               }
             }
           }
           ct_commit(bar_sple + 8 * ss);
+          if (++ss == (uint32_t)S) { ss = 0; ss_par ^= 1u; }
         }
         ct_commit(bar_accf + 8 * buf);
+        if (++buf == (uint32_t)NB) { buf = 0; ++buf_round; }
       }
     }
   } else if (warp < 2 + P_SPLIT_WARPS) {
     // ===== splitters: raw fp32 tile -> TF32 hi tile + lo tile (flat, the swizzle is address-preserving) =====
     const int sw = warp - 2;
-    int it = 0;
+    uint32_t rs = 0, rs_par = 0, ss = 0, ss_round = 0;
     for (int j = first; j < total_mt; j += cpg) {
-      for (int c = 0; c < a.n_chunks; ++c, ++it) {
-        const int rs = it % R, ss = it % S;
-        ct_wait(bar_rawf + 8 * rs, (uint32_t)((it / R) & 1), dbg, 8, c);
-        if (it >= S) ct_wait(bar_sple + 8 * ss, (uint32_t)((it / S - 1) & 1), dbg, 9, c);
+      for (int c = 0; c < a.n_chunks; ++c) {
+        ct_wait(bar_rawf + 8 * rs, rs_par, dbg, 8, c);
+        if (ss_round > 0) ct_wait(bar_sple + 8 * ss, (ss_round - 1) & 1u, dbg, 9, c);
         __syncwarp();
-        const float4* src = reinterpret_cast<const float4*>(gbase + L.raw_ring + (uint32_t)rs * CT_RAW_STAGE);
-        float4* dhi = reinterpret_cast<float4*>(gbase + L.split_ring + (uint32_t)ss * L.split_stage_bytes);
+        const float4* src = reinterpret_cast<const float4*>(gbase + L.raw_ring + rs * CT_RAW_STAGE);
+        float4* dhi = reinterpret_cast<float4*>(gbase + L.split_ring + ss * L.split_stage_bytes);
         float4* dlo = dhi + CT_RAW_STAGE / 16;
         // 512 float4 per tile, 256 per warp, 8 per lane
 #pragma unroll
@@ -167,6 +180,8 @@ tapgemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const TapG
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor pipe
         __syncwarp();
         if (lane == 0) { ct_arrive(bar_splf + 8 * ss); ct_arrive(bar_rawe + 8 * rs); }
+        if (++rs == (uint32_t)R) { rs = 0; rs_par ^= 1u; }
+        if (++ss == (uint32_t)S) { ss = 0; ++ss_round; }
       }
     }
   } else {
