@@ -230,6 +230,25 @@ int m2tts_conv_transpose1d_lrelu_tc(const float* x, const float* w, const float*
                                     int CI, int CO, int L, int r, void* workspace, size_t workspace_bytes,
                                     m2tts_stream_t stream);
 
+/* One whole narrow vocoder stage fused into a single tcgen05 kernel, CHANNEL-LAST activations
+ * (tts_model.py:289-292 for one (upsample, resblock) pair, plus :295 for the last stage):
+ *   x [B][L][2C]  ->  u = leaky_relu(ConvTranspose1d(2C, C, k=4, s=2, p=1)(x), 0.1)
+ *                 ->  y = u + conv2(leaky_relu(conv1(u), 0.1))            (components.py:196-200)
+ *   out_w == NULL: y written channel-last [B][2L][C];
+ *   out_w != NULL: audio [B][2L] = tanh(Conv1d(C, 1, k=3, p=1)(y))  (out_w [1][C][3], out_b [1]).
+ * C in {16, 32}; weights in the reference's state_dict layouts (up_w [2C][C][4], res*_w [C][C][3]).
+ * workspace: m2tts_vocoder_stage_fused_workspace_bytes(C). */
+size_t m2tts_vocoder_stage_fused_workspace_bytes(int C);
+int m2tts_vocoder_stage_fused(const float* x, const float* up_w, const float* up_b, const float* res1_w,
+                              const float* res1_b, const float* res2_w, const float* res2_b,
+                              const float* out_w, const float* out_b, float* y, int B, int C, int L,
+                              void* workspace, size_t workspace_bytes, m2tts_stream_t stream);
+
+/* Bring-up probe (tests/rowshift_probe_run.py): K-major swizzled UMMA A operand whose descriptor start
+ * address is moved by whole rows inside the swizzle pattern. */
+int m2tts_rowshift_probe(const float* A, const float* Bm, float* D, int rows_total, int N, int K, int rowbytes,
+                         int shift, int base_offset, m2tts_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

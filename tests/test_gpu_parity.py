@@ -339,6 +339,38 @@ def test_tensor_core_conv_entry_points():
         assert H.max_abs(y.cpu(), want) <= FP32_TOL, ("convT_tc", CI, CO, L, r_)
 
 
+@pytest.mark.parametrize("C,L,B,final", [(16, 300, 2, False), (16, 300, 2, True), (32, 257, 2, False), (32, 130, 3, True),
+                                         (16, 1, 1, True), (16, 2000, 1, True), (32, 1111, 2, False), (16, 61, 5, False)])
+def test_fused_vocoder_stage(C, L, B, final):
+    """One (upsample x2, ResBlock[, output conv + tanh]) stage as a single channel-last tcgen05 kernel."""
+    from models import _native as nat
+    import torch.nn.functional as F
+    lib = nat.lib()
+    g = torch.Generator().manual_seed(100 * C + L)
+    x = torch.randn(B, 2 * C, L, generator=g)
+    up_w = torch.randn(2 * C, C, 4, generator=g) * (1.0 / (4 * C) ** 0.5)
+    w1 = torch.randn(C, C, 3, generator=g) * (1.0 / (3 * C) ** 0.5)
+    w2 = torch.randn(C, C, 3, generator=g) * (1.0 / (3 * C) ** 0.5)
+    up_b, b1, b2 = (torch.randn(C, generator=g) * 0.3 for _ in range(3))
+    ow = torch.randn(1, C, 3, generator=g) * 0.2
+    ob = torch.randn(1, generator=g)
+    u = F.leaky_relu(F.conv_transpose1d(x, up_w, up_b, stride=2, padding=1), 0.1)
+    want = u + F.conv1d(F.leaky_relu(F.conv1d(u, w1, b1, padding=1), 0.1), w2, b2, padding=1)
+    if final:
+        want = torch.tanh(F.conv1d(want, ow, ob, padding=1))[:, 0]          # [B, 2L]
+    else:
+        want = want.transpose(1, 2).contiguous()                            # channel-last [B, 2L, C]
+    d = [t.to(DEV) for t in (x.transpose(1, 2).contiguous(), up_w, up_b, w1, b1, w2, b2, ow, ob)]
+    y = torch.full(want.shape, float("nan"), device=DEV)
+    ws = torch.empty(lib.m2tts_vocoder_stage_fused_workspace_bytes(C), dtype=torch.uint8, device=DEV)
+    rc = lib.m2tts_vocoder_stage_fused(*(t.data_ptr() for t in d[:7]), d[7].data_ptr() if final else None,
+                                       d[8].data_ptr() if final else None, y.data_ptr(), B, C, L, ws.data_ptr(), ws.numel(), None)
+    nat.check(rc, "vocoder_stage_fused")
+    torch.cuda.synchronize()
+    assert not torch.isnan(y).any(), "unwritten output rows"
+    assert H.max_abs(y.cpu(), want) <= FP32_TOL, (C, L, B, final)
+
+
 @pytest.mark.parametrize("mode", [0, 1])  # 0 = tcgen05 convs for the wide stages, 1 = FFMA everywhere
 def test_vocoder_modes_both_meet_fp32_tolerance(mode):
     from models import _native as nat
