@@ -278,9 +278,10 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         dom = max(stage_ms.items(), key=lambda kv: kv[1][0]) if stage_ms else ("none", (0.0, 1))
         dom_ms_per_step = dom[1][0] / args.steps
         tensor_stages = {"attention": "tcgen05 kind::tf32, 3 split terms (3xTF32): issued MMA FLOPs = 3x algorithmic",
-                         "voc_up": "stages 0-1 tcgen05 3xTF32 tap-GEMM, stages 2-3 fp32 FFMA",
-                         "voc_res1": "stages 0-1 tcgen05 3xTF32 tap-GEMM, stages 2-3 fp32 FFMA",
-                         "voc_res2": "stages 0-1 tcgen05 3xTF32 tap-GEMM, stages 2-3 fp32 FFMA"}
+                         "voc_up": "stages 0-1 tcgen05 3xTF32 tap-GEMM",
+                         "voc_res1": "stages 0-1 tcgen05 3xTF32 tap-GEMM",
+                         "voc_res2": "stages 0-1 tcgen05 3xTF32 tap-GEMM",
+                         "voc_fused": "stages 2-3: upsample + ResBlock (+ output conv) fused, channel-last tcgen05 3xTF32"}
         roof = {"kernel": dom[0], "bound": "tensor", "unit": "TFLOP/s", "stage_ms_per_step": dom_ms_per_step,
                 "launches_per_step": dom[1][1] // args.steps, "launch_ms": dom[1][0] / max(dom[1][1], 1),
                 "peak": peaks["bf16_tflops_sustained"],
@@ -327,13 +328,18 @@ def stage_flops_per_step():
           "ffn1": L * 2 * H * F * rows, "ffn2": L * 2 * H * F * rows, "ln_proj": 2 * H * M * rows,
           "voc_in": 2 * 3 * M * C * rows, "voc_up": 0, "voc_res1": 0, "voc_res2": 0}
     c_in, Lc = C, T
-    for r in (4, 4, 2, 2):
+    fl["voc_fused"] = 0
+    for j, r in enumerate((4, 4, 2, 2)):
         c, Lc = c_in // 2, Lc * r
-        fl["voc_up"] += 2 * 2 * c_in * c * Lc * B          # two taps per output sample
-        fl["voc_res1"] += 2 * 3 * c * c * Lc * B
-        fl["voc_res2"] += 2 * 3 * c * c * Lc * B
+        up, res = 2 * 2 * c_in * c * Lc * B, 2 * 3 * c * c * Lc * B       # two taps per output sample; one k=3 conv
+        if j < 2:      # wide stages: three tap-GEMM launches each
+            fl["voc_up"] += up
+            fl["voc_res1"] += res
+            fl["voc_res2"] += res
+        else:          # narrow stages: one fused kernel each (the last one includes the output conv)
+            fl["voc_fused"] += up + 2 * res
         c_in = c
-    fl["voc_out"] = 2 * 3 * c_in * Lc * B
+    fl["voc_fused"] += 2 * 3 * c_in * Lc * B
     return fl
 
 

@@ -63,7 +63,8 @@ enum {
   M2TTS_STAGE_VOC_RES2 = 15,
   M2TTS_STAGE_VOC_OUT = 16,
   M2TTS_STAGE_PROBE = 17,
-  M2TTS_NUM_STAGES = 18
+  M2TTS_STAGE_VOC_FUSED = 18,
+  M2TTS_NUM_STAGES = 19
 };
 
 /* ---- weights: raw views of the reference's state_dict tensors ------------- */

@@ -162,7 +162,13 @@ size_t conv3_tc_wblob_floats(int CI, int CO);
 size_t convT_tc_wblob_floats(int CI, int CO, int r);
 int launch_conv3_tc(const float* x, int Lp_in, const float* w, float* wblob, const float* bias, const float* residual,
                     int Lp_res, float* out, int Lp_out, int B, int CI, int CO, int L, int dil, int act, int stage,
-                    cudaStream_t s);
+                    cudaStream_t s, int out_cl = 0);   // out_cl: write channel-last [B][L][CO] instead of [B][CO][Lp_out]
 int launch_convT_tc(const float* x, int Lp_in, const float* w, float* wblob, const float* bias, float* out, int Lp_out,
                     int B, int CI, int CO, int L, int r, cudaStream_t s);
+// fused narrow stage on channel-last activations (voc_fused.cu): upsample x2 + ResBlock (+ output conv + tanh)
+bool voc_fused_eligible(int C, int r, int dil);
+size_t voc_fused_wblob_floats(int C);
+int launch_voc_stage_fused(const float* x, const float* up_w, const float* up_b, const float* w1, const float* b1,
+                           const float* w2, const float* b2, const float* out_w, const float* out_b, float* wblob,
+                           float* out, int B, int C, int L_in, int stage, cudaStream_t s);
 }  // namespace m2

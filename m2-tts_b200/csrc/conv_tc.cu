@@ -118,7 +118,7 @@ static int launch_wpack(const WPackArgs& p, cudaStream_t s) {
 // Conv1d k=3 on plain fp32. wblob: conv3_tc_wblob_floats(CI,CO) floats of scratch. residual (plain, pitch Lp_res) may be null.
 int launch_conv3_tc(const float* x, int Lp_in, const float* w, float* wblob, const float* bias, const float* residual,
                     int Lp_res, float* out, int Lp_out, int B, int CI, int CO, int L, int dil, int act, int stage,
-                    cudaStream_t s) {
+                    cudaStream_t s, int out_cl) {
   M2_REQUIRE(conv3_tc_eligible(CI, CO), M2TTS_E_UNSUPPORTED, "conv3_tc: CI=%d CO=%d not eligible", CI, CO);
   const int ct = (CO % 64 == 0) ? 64 : CO, n_tiles = CO / ct;   // <= 192 accumulator columns per tile
   WPackArgs p{w, wblob, 0, CI, CO, 1, ct, 3 * ct, CI / CT_CK, n_tiles};
@@ -128,7 +128,7 @@ int launch_conv3_tc(const float* x, int Lp_in, const float* w, float* wblob, con
   a.CI = CI; a.L_in = L; a.B = B; a.n_chunks = CI / CT_CK;
   for (int j = 0; j < 3; ++j) { a.tap_shift[j] = (j - 1) * dil; a.tap_rows[j] = ct; a.tap_wrow[j] = j * ct; a.tap_dcol[j] = j * ct; }
   a.rows_total = 3 * ct; a.n_cols = 3 * ct; a.wblob = wblob; a.r = 1; a.co_tile = ct; a.CO = CO; a.L_out = L; a.Lp_out = Lp_out;
-  a.bias = bias; a.act = act; a.residual = residual; a.Lp_res = Lp_res; a.out = out;
+  a.bias = bias; a.act = act; a.residual = residual; a.Lp_res = Lp_res; a.out = out; a.out_cl = out_cl;
   return launch_tapgemm(x, Lp_in, a, n_tiles, stage, s);
 }
 

@@ -27,7 +27,8 @@ struct TapGemmArgs {
   const float* bias;
   int act;                   // 0 none, 1 leaky_relu(0.1)
   const float* residual; int Lp_res;   // plain fp32 [B][CO][Lp_res] or null
-  float* out;                // plain fp32 [B][CO][Lp_out]
+  float* out;                // plain fp32 [B][CO][Lp_out]  (out_cl: channel-last [B][L_out][CO], conv only)
+  int out_cl;
   int n_tiles, m_tiles, w_resident;
   int raw_stages, split_stages;
 };

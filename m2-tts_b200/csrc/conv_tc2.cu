@@ -230,12 +230,21 @@ tapgemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const TapG
             for (int jj = 0; jj < 16; ++jj) stg[((tap * 16 + jj) << 7) + m] = __uint_as_float(v[tap][jj]);
           p_epi_sync(grp);
           if (own) {
+            float xo[16];
 #pragma unroll
             for (int c = 0; c < 16; ++c) {
               const int co = co0 + c0 + c;
               float x = stg[((c) << 7) + m + s0] + stg[((16 + c) << 7) + m + s1] + stg[((32 + c) << 7) + m + s2] + __ldg(a.bias + co);
               if (a.act == 1) x = x > 0.f ? x : 0.1f * x;
-              a.out[((size_t)b * a.CO + co) * a.Lp_out + q] = x + rsd[c];
+              xo[c] = x + rsd[c];
+            }
+            if (a.out_cl) {       // channel-last rows for the fused narrow stages: 64 contiguous bytes per thread
+              float4* op = reinterpret_cast<float4*>(a.out + ((size_t)b * a.L_out + q) * a.CO + co0 + c0);
+#pragma unroll
+              for (int c4 = 0; c4 < 4; ++c4) op[c4] = make_float4(xo[4 * c4], xo[4 * c4 + 1], xo[4 * c4 + 2], xo[4 * c4 + 3]);
+            } else {
+#pragma unroll
+              for (int c = 0; c < 16; ++c) a.out[((size_t)b * a.CO + co0 + c0 + c) * a.Lp_out + q] = xo[c];
             }
           }
           p_epi_sync(grp);

@@ -27,6 +27,7 @@ struct FusedStageArgs {
   const float* bias_up; const float* bias1; const float* bias2;
   const float* out_w; const float* out_b;   // FINAL: Conv1d(C,1,3) weight [1][C][3] and bias
   float* out;                            // [B][L_out][C] channel-last, or FINAL: audio [B][L_out]
+  long long* prof;                       // optional: per-tile phase timestamps of CTA 0 / context 0 (bring-up)
 };
 
 template <int C, int NQ, int NCTX, bool FINAL>
@@ -276,6 +277,8 @@ voc_stage_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedSt
 
       // ---- EPI1: transposed-conv accumulator -> U = lrelu(. + bias), zero outside the utterance, hi/lo rows ----
       ct_wait(bar(c, ACC_UP), par, dbg, 8, it);
+      const bool pr = a.prof != nullptr && blockIdx.x == 0 && c == 0 && m == 0 && it < 64;
+      if (pr) a.prof[it * 8 + 0] = clock64();
       __syncwarp();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (m < NQ) {                                        // warp-uniform (NQ is a multiple of 32)
@@ -309,11 +312,13 @@ voc_stage_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedSt
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) ct_arrive(bar(c, U_READY));
+      if (pr) a.prof[it * 8 + 1] = clock64();
 
       // ---- EPI2: conv1 accumulator -> V = lrelu(. + bias), zero outside the utterance, hi/lo rows ----
 #pragma unroll
       for (int h = 0; h < HALVES; ++h) {
         ct_wait(bar(c, ACC_C1 + h), par, dbg, 9, it);
+        if (pr && h == 0) a.prof[it * 8 + 2] = clock64();
         __syncwarp();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int i = 128 * h + m;
@@ -343,12 +348,14 @@ voc_stage_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedSt
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) ct_arrive(bar(c, V_READY));
+      if (pr) a.prof[it * 8 + 3] = clock64();
 
       // ---- EPI3: conv2 accumulator + bias + U -> stage output (or the 1-channel output conv + tanh) ----
       float p1[HALVES];
 #pragma unroll
       for (int h = 0; h < HALVES; ++h) {
         ct_wait(bar(c, ACC_C2 + h), par, dbg, 10, it);
+        if (pr && h == 0) a.prof[it * 8 + 4] = clock64();
         __syncwarp();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int i = 128 * h + m;
@@ -406,6 +413,7 @@ voc_stage_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedSt
         }
         fs_group_sync(c);                     // exch reads done before the next tile rewrites it
       }
+      if (pr) a.prof[it * 8 + 5] = clock64();
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -479,6 +487,7 @@ static int launch_fs(const float* x, FusedStageArgs a, int stage, cudaStream_t s
   return M2TTS_OK;
 }
 
+static long long* g_fs_prof = nullptr;
 bool voc_fused_eligible(int C, int r, int dil) { return (C == 16 || C == 32) && r == 2 && dil == 1; }
 size_t voc_fused_wblob_floats(int C) { return (size_t)2 * 14 * C * C; }
 
@@ -496,7 +505,7 @@ int launch_voc_stage_fused(const float* x, const float* up_w, const float* up_b,
   }
   FusedStageArgs a{};
   a.B = B; a.L_in = L_in; a.L_out = 2 * L_in; a.wblob = wblob; a.bias_up = up_b; a.bias1 = b1; a.bias2 = b2;
-  a.out_w = out_w; a.out_b = out_b; a.out = out;
+  a.out_w = out_w; a.out_b = out_b; a.out = out; a.prof = g_fs_prof;
   const bool fin = out_w != nullptr;
   if (C == 16) return fin ? launch_fs<16, 128, 2, true>(x, a, stage, s) : launch_fs<16, 128, 2, false>(x, a, stage, s);
   return fin ? launch_fs<32, 64, 1, true>(x, a, stage, s) : launch_fs<32, 64, 1, false>(x, a, stage, s);
@@ -505,6 +514,9 @@ int launch_voc_stage_fused(const float* x, const float* up_w, const float* up_b,
 }  // namespace m2
 
 using namespace m2;
+
+// bring-up: device buffer of 64 x 8 int64 that receives phase timestamps (NULL = off)
+extern "C" int m2tts_vocoder_stage_fused_set_prof(long long* dev_buf) { m2::g_fs_prof = dev_buf; return M2TTS_OK; }
 
 extern "C" size_t m2tts_vocoder_stage_fused_workspace_bytes(int C) {
   if (C != 16 && C != 32) return 0;

@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(VC_THREADS) convT_kernel(ConvArgs a) {
   const int tx = tid % TX, ty = tid / TX;
   const int q0 = blockIdx.x * TQ, co0 = blockIdx.y * COB, b = blockIdx.z;
   const int L = a.L, CI = a.CI, CO = a.CO;
-  const float* xb = a.x + (long long)b * CI * L;
+  const float* xb = a.x + (long long)b * a.xs_b;
 
   float acc[2][4][COT][R];
 #pragma unroll
@@ -210,12 +210,22 @@ __global__ void __launch_bounds__(VC_THREADS) convT_kernel(ConvArgs a) {
 
   for (int ci0 = 0; ci0 < CI; ci0 += CK) {
     __syncthreads();
-    for (int idx = tid; idx < CK * (TQ + 2); idx += VC_THREADS) {
-      const int ci = idx / (TQ + 2), c = idx - ci * (TQ + 2);
-      const int q = q0 - 1 + c;
-      float v = 0.f;
-      if (ci0 + ci < CI && q >= 0 && q < L) v = xb[(long long)(ci0 + ci) * L + q];
-      xs[ci * XST + c] = v;
+    if (a.xs_t == 1) {
+      for (int idx = tid; idx < CK * (TQ + 2); idx += VC_THREADS) {
+        const int ci = idx / (TQ + 2), c = idx - ci * (TQ + 2);
+        const int q = q0 - 1 + c;
+        float v = 0.f;
+        if (ci0 + ci < CI && q >= 0 && q < L) v = xb[(long long)(ci0 + ci) * a.xs_c + q];
+        xs[ci * XST + c] = v;
+      }
+    } else {  // channel-last input (the output of a fused stage): walk channels fastest
+      for (int idx = tid; idx < CK * (TQ + 2); idx += VC_THREADS) {
+        const int c = idx / CK, ci = idx - c * CK;
+        const int q = q0 - 1 + c;
+        float v = 0.f;
+        if (ci0 + ci < CI && q >= 0 && q < L) v = xb[(long long)(ci0 + ci) * a.xs_c + (long long)q * a.xs_t];
+        xs[ci * XST + c] = v;
+      }
     }
     for (int idx = tid; idx < CK * COB * K2; idx += VC_THREADS) {
       const int ci = idx / (COB * K2), rem = idx - ci * (COB * K2);
@@ -458,8 +468,9 @@ extern "C" size_t m2tts_vocoder_workspace_bytes(int B, int T, int M, int C) {
   size_t wts = (size_t)C * M * 3;
   static const int rates[4] = {4, 4, 2, 2};
   for (int j = 0, c = C / 2; j < 4; ++j, c /= 2)
-    wts += 2 * (size_t)c * c * 3 + 2 * conv3_tc_wblob_floats(c, c) + convT_tc_wblob_floats(2 * c, c, rates[j]);
-  return 3 * act + align_up(wts * sizeof(float), 256) + 32 * 256;
+    wts += 2 * (size_t)c * c * 3 + 2 * conv3_tc_wblob_floats(c, c) + convT_tc_wblob_floats(2 * c, c, rates[j]) +
+           voc_fused_wblob_floats(c == 16 || c == 32 ? c : 0);
+  return 3 * act + align_up(wts * sizeof(float), 256) + 40 * 256;
 }
 
 extern "C" int m2tts_vocoder_forward(const m2tts_vocoder_weights* w, const float* mel, int64_t stride_b,
@@ -484,13 +495,14 @@ extern "C" int m2tts_vocoder_forward(const m2tts_vocoder_weights* w, const float
   ConvPackJob jobs[9];
   float* in_wp = cv.take<float>((size_t)C * M * 3);
   jobs[0] = ConvPackJob{w->in_w, in_wp, C, M};
-  float *r1p[4], *r2p[4], *r1b[4], *r2b[4], *upb[4];
+  float *r1p[4], *r2p[4], *r1b[4], *r2b[4], *upb[4], *fsb[4];
   for (int j = 0, c = C / 2; j < 4; ++j, c /= 2) {
     r1p[j] = cv.take<float>((size_t)c * c * 3);
     r2p[j] = cv.take<float>((size_t)c * c * 3);
     r1b[j] = cv.take<float>(conv3_tc_wblob_floats(c, c));
     r2b[j] = cv.take<float>(conv3_tc_wblob_floats(c, c));
     upb[j] = cv.take<float>(convT_tc_wblob_floats(2 * c, c, rates[j]));
+    fsb[j] = cv.take<float>(voc_fused_wblob_floats(c == 16 || c == 32 ? c : 0));
     jobs[1 + 2 * j] = ConvPackJob{w->res1_w[j], r1p[j], c, c};
     jobs[2 + 2 * j] = ConvPackJob{w->res2_w[j], r2p[j], c, c};
   }
@@ -499,40 +511,61 @@ extern "C" int m2tts_vocoder_forward(const m2tts_vocoder_weights* w, const float
   int rc = launch_conv_pack(jobs, 9, s);
   if (rc) return rc;
 
-  // Which stages run on the tensor cores: all three convolutions of the stage must qualify
-  // (wide early stages, >= 64 output channels); they always form a prefix of the stage list.
-  bool tc[5] = {false, false, false, false, false};
+  // Per-stage kernel choice.
+  //   TC    : the three convolutions as persistent tcgen05 tap-GEMMs on channel-first tensors (wide stages; they
+  //           form a prefix of the stage list because they need a channel-first input with a 16-B row pitch);
+  //   FUSED : the whole stage (upsample x2 + ResBlock, and for the last stage the output conv + tanh) as ONE
+  //           tcgen05 kernel on channel-last tensors (C in {16,32}); its producer must be a TC or FUSED stage,
+  //           which then writes its output channel-last;
+  //   FFMA  : fp32 FFMA kernels (any shape, any input strides).
+  enum { P_FFMA = 0, P_TC = 1, P_FUSED = 2 };
+  int path[4] = {P_FFMA, P_FFMA, P_FFMA, P_FFMA};
   if (vocoder_mode() == 0) {
-    int c_in = C;
-    for (int j = 0; j < 4; ++j, c_in /= 2) {
-      const int c = c_in / 2;
+    int ci = C;
+    for (int j = 0; j < 4; ++j, ci /= 2) {
+      const int c = ci / 2;
       const int dil = w->res_dilation[j] > 0 ? w->res_dilation[j] : 1;
-      tc[j] = (j == 0 || tc[j - 1]) && convT_tc_eligible(c_in, c, rates[j]) && conv3_tc_eligible(c, c) && dil <= 4;
+      const bool tc_ok = (j == 0 || path[j - 1] == P_TC) && convT_tc_eligible(ci, c, rates[j]) && conv3_tc_eligible(c, c) && dil <= 4;
+      const bool fused_ok = j >= 1 && path[j - 1] != P_FFMA && voc_fused_eligible(c, rates[j], dil);
+      path[j] = fused_ok ? P_FUSED : (tc_ok ? P_TC : P_FFMA);
     }
   }
 
   // input conv: mel (strided) -> bufA [B,C,Lp] (row pitch padded to a multiple of 4 floats for the TMA tensor maps)
   int L = T, c_in = C;
-  int Lp = tc[0] ? ((L + 3) & ~3) : L;
+  int Lp = path[0] == P_TC ? ((L + 3) & ~3) : L;
+  bool cl = false;                       // layout of the current activation (bufA): channel-last?
   {
     ConvArgs a{mel, stride_b, stride_m, stride_t, in_wp, w->in_b, nullptr, bufA, M, C, T, 1, 0};
     a.y_pitch = Lp;
     if ((rc = launch_conv3(a, B, M2TTS_STAGE_VOC_IN, s))) return rc;
   }
+  bool audio_done = false;
   for (int j = 0; j < 4; ++j) {
     const int r = rates[j], c = c_in / 2, Lo = L * r;
     const int dil = w->res_dilation[j] > 0 ? w->res_dilation[j] : 1;
-    if (tc[j]) {
+    const bool next_cl = j + 1 < 4 && path[j + 1] == P_FUSED;
+    if (path[j] == P_FUSED) {
+      // bufA channel-last [B][L][c_in] -> bufB channel-last [B][Lo][c] (or straight to the waveform)
+      const bool last = j == 3;
+      if ((rc = launch_voc_stage_fused(bufA, w->up_w[j], w->up_b[j], w->res1_w[j], w->res1_b[j], w->res2_w[j], w->res2_b[j],
+                                       last ? w->out_w : nullptr, last ? w->out_b : nullptr, fsb[j], last ? audio : bufB, B, c, L,
+                                       M2TTS_STAGE_VOC_FUSED, s))) return rc;
+      if (last) audio_done = true;
+      else { float* t = bufA; bufA = bufB; bufB = t; }
+      cl = true;
+    } else if (path[j] == P_TC) {
       // bufA (pitch Lp) -> up -> bufB -> conv1 -> bufC -> conv2 (+ residual bufB) -> bufA; Lo = r*L is a multiple of 4
       if ((rc = launch_convT_tc(bufA, Lp, w->up_w[j], upb[j], w->up_b[j], bufB, Lo, B, c_in, c, L, r, s))) return rc;
       if ((rc = launch_conv3_tc(bufB, Lo, w->res1_w[j], r1b[j], w->res1_b[j], nullptr, 0, bufC, Lo, B, c, c, Lo, dil, 1,
                                 M2TTS_STAGE_VOC_RES1, s))) return rc;
       if ((rc = launch_conv3_tc(bufC, Lo, w->res2_w[j], r2b[j], w->res2_b[j], bufB, Lo, bufA, Lo, B, c, c, Lo, 1, 0,
-                                M2TTS_STAGE_VOC_RES2, s))) return rc;
+                                M2TTS_STAGE_VOC_RES2, s, next_cl ? 1 : 0))) return rc;
       Lp = Lo;
+      cl = next_cl;
     } else {
-      {  // bufB = lrelu(convT(bufA))
-        ConvArgs a{bufA, (long long)c_in * L, L, 1, w->up_w[j], w->up_b[j], nullptr, bufB, c_in, c, L, 1, 1};
+      {  // bufB = lrelu(convT(bufA)); bufA is channel-first, or channel-last after a fused stage
+        ConvArgs a{bufA, (long long)c_in * L, cl ? 1 : L, cl ? c_in : 1, w->up_w[j], w->up_b[j], nullptr, bufB, c_in, c, L, 1, 1};
         if ((rc = launch_convT(a, B, r, s))) return rc;
       }
       {  // bufC = lrelu(conv1(bufB))
@@ -544,11 +577,12 @@ extern "C" int m2tts_vocoder_forward(const m2tts_vocoder_weights* w, const float
         if ((rc = launch_conv3(a, B, M2TTS_STAGE_VOC_RES2, s))) return rc;
       }
       Lp = Lo;
+      cl = false;
     }
     L = Lo; c_in = c;
   }
-  // output conv + tanh: bufA [B,C/16,64T] -> audio [B,1,64T]
-  {
+  // output conv + tanh: bufA [B,C/16,64T] -> audio [B,1,64T] (fused into the last stage when that stage is FUSED)
+  if (!audio_done) {
     const int threads = 256;
     dim3 grid(ceil_div(ceil_div(L, 4), threads), B);
     M2_LAUNCH(M2TTS_STAGE_VOC_OUT, conv3_co1_tanh_kernel, grid, threads, (size_t)c_in * 3 * sizeof(float), s, bufA,

@@ -16,10 +16,10 @@ import torch
 _PKG_ROOT = Path(__file__).resolve().parents[2]          # .../m2-tts_b200
 _LIB_PATH = Path(os.environ.get("M2TTS_B200_LIB", _PKG_ROOT / "lib" / "libm2tts_b200.so"))
 
-NUM_STAGES = 18
+NUM_STAGES = 19
 STAGE_NAMES = ["embed", "pack", "ln_qkv", "attention", "out_proj", "ffn1", "ffn2", "ln_proj",
                "layernorm", "durpred", "lr_count", "lr_gather", "voc_in", "voc_up", "voc_res1",
-               "voc_res2", "voc_out", "probe"]
+               "voc_res2", "voc_out", "probe", "voc_fused"]
 
 
 class NativeLibraryError(RuntimeError):
