@@ -76,6 +76,24 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, u
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
       ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
 }
+// Warp-collective variants: the WHOLE warp executes the call with warp-uniform operands and one elected lane
+// issues. ptxas then keeps descriptors in uniform registers and emits a predicated UTCHMMA; issuing from an
+// `if (lane == 0)` region instead makes it wrap every UMMA in an ELECT/BRA.U.ANY loop fed by R2UR moves, which
+// costs more than the MMA itself at these tile sizes (measured with mma_bench.cu).
+__device__ __forceinline__ void tc_commit_w(uint32_t bar) {
+  asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+               "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_ss_w(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p, q;\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_ts_w(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p, q;\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+               ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -348,6 +366,282 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_co
   }
 }
 
+
+// =================================================================================================
+// Warp-specialised variant (default): one CTA per SM-slot works on TWO 128-query tiles of the same
+// (utterance, head) that share every K/V tile. Roles: warp 0 = TMA loader, warp 1 = UMMA issuer,
+// warps 4-7 / 8-11 = softmax warpgroups of query tile A / B (thread = query row = TMEM lane).
+// The issuer alternates  PV(A,t) QK(A,t+1) | PV(B,t) QK(B,t+1)  so the tensor pipe runs one tile's
+// GEMMs while the other tile's warpgroup does its softmax; K and V tiles are double-buffered rings.
+// TMEM per query tile (192 columns): S (64, overwritten in place by P_hi) | P_lo (64) | O tile (64).
+// =================================================================================================
+constexpr int WS_THREADS = 384;
+constexpr uint32_t WS_TMEM_COLS = 512;
+constexpr uint32_t WS_COL_TILE = 192, WS_COL_S = 0, WS_COL_PLO = 64, WS_COL_O = 128;
+constexpr int WS_KV_STAGES = 2;
+
+template <int HD>
+struct WsSmem {
+  static constexpr uint32_t box_bytes = HD * 128;
+  static constexpr uint32_t q_bytes = 2 * (TC_BQ / TC_BOX) * box_bytes;    // one query tile, hi + lo
+  static constexpr uint32_t kv_bytes = 2 * (TC_BK / TC_BOX) * box_bytes;   // one K (or V) tile, hi + lo
+  static constexpr uint32_t off_k = 2 * q_bytes;
+  static constexpr uint32_t off_v = off_k + WS_KV_STAGES * kv_bytes;
+  static constexpr uint32_t off_bar = off_v + WS_KV_STAGES * kv_bytes;
+  static constexpr uint32_t total = off_bar + 256 + 1024 /*align slack*/;
+};
+
+__device__ __forceinline__ float ws_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int HD>
+__global__ void __launch_bounds__(WS_THREADS, 1)
+attention_ws_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_constant__ CUtensorMap tmap_v,
+                    float* __restrict__ ctx, const int64_t* __restrict__ lengths, int B, int L, int nh,
+                    float* __restrict__ ctx_lo, long long* __restrict__ prof) {
+  static_assert(HD % 16 == 0 && HD >= 16 && HD <= 64, "tensor-core path: head_dim in {16,32,48,64}");
+  constexpr uint32_t BOX = WsSmem<HD>::box_bytes;
+  constexpr int QBOX = TC_BQ / TC_BOX, KBOX = TC_BK / TC_BOX;
+  constexpr int KSTEPS_D = HD / 8;
+  constexpr uint32_t IDESC_QK = umma_idesc_tf32(TC_BQ, TC_BK, 1, 1);
+  constexpr uint32_t IDESC_PV = umma_idesc_tf32(TC_BQ, HD, 0, 0);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ = sbase;                                   // [tile][hi|lo][QBOX][HD rows][128 B]
+  const uint32_t sK = sbase + WsSmem<HD>::off_k;               // [stage][hi|lo][KBOX][HD][128 B]
+  const uint32_t sV = sbase + WsSmem<HD>::off_v;
+  const uint32_t sBar = sbase + WsSmem<HD>::off_bar;
+  // barriers: q_full[2] k_full[2] k_empty[2] v_full[2] v_empty[2] s_full[2] p_ready[2] o_ready[2] o_free[2]
+  const uint32_t bar_qf = sBar, bar_kf = sBar + 16, bar_ke = sBar + 32, bar_vf = sBar + 48, bar_ve = sBar + 64;
+  const uint32_t bar_sf = sBar + 80, bar_pr = sBar + 96, bar_or = sBar + 112, bar_of = sBar + 128;
+  const uint32_t tmem_slot = sBar + 144;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q0 = blockIdx.x * (2 * TC_BQ), head = blockIdx.y, b = blockIdx.z;
+
+  int Leff = L;
+  bool all_masked = false;
+  if (lengths != nullptr) {
+    const long long len = lengths[b];
+    if (len <= 0) all_masked = true;
+    else if (len < L) Leff = (int)len;
+  }
+  const int nkt = (Leff + TC_BK - 1) / TC_BK;
+  const int plane = B * nh * HD;
+  const int row_q = (b * nh + head) * HD;
+
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_qf + 8 * i, 1); mbar_init(bar_kf + 8 * i, 1); mbar_init(bar_ke + 8 * i, 1);
+      mbar_init(bar_vf + 8 * i, 1); mbar_init(bar_ve + 8 * i, 1); mbar_init(bar_sf + 8 * i, 1);
+      mbar_init(bar_pr + 8 * i, 4); mbar_init(bar_or + 8 * i, 1); mbar_init(bar_of + 8 * i, 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_qk) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_v) : "memory");
+  }
+  if (warp == 0) {
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(WS_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== loader: both query tiles once, then the K / V rings =====
+      for (int x = 0; x < 2; ++x) {
+        mbar_expect_tx(bar_qf + 8 * x, WsSmem<HD>::q_bytes);
+        for (int h = 0; h < 2; ++h)
+          for (int j = 0; j < QBOX; ++j)
+            tma_load_2d(sQ + (uint32_t)x * WsSmem<HD>::q_bytes + (h * QBOX + j) * BOX, &tmap_qk, q0 + x * TC_BQ + j * TC_BOX,
+                        h * plane + row_q, bar_qf + 8 * x);
+      }
+      for (int t = 0; t < nkt; ++t) {
+        const int st = t & 1;
+        const uint32_t par_prev = (uint32_t)(((t >> 1) - 1) & 1);
+        if (t >= WS_KV_STAGES) mbar_wait(bar_ke + 8 * st, par_prev);
+        mbar_expect_tx(bar_kf + 8 * st, WsSmem<HD>::kv_bytes);
+        for (int h = 0; h < 2; ++h)
+          for (int j = 0; j < KBOX; ++j)
+            tma_load_2d(sK + (uint32_t)st * WsSmem<HD>::kv_bytes + (h * KBOX + j) * BOX, &tmap_qk, t * TC_BK + j * TC_BOX,
+                        (2 + h) * plane + row_q, bar_kf + 8 * st);
+        if (t >= WS_KV_STAGES) mbar_wait(bar_ve + 8 * st, par_prev);
+        mbar_expect_tx(bar_vf + 8 * st, WsSmem<HD>::kv_bytes);
+        for (int h = 0; h < 2; ++h)
+          for (int j = 0; j < KBOX; ++j)
+            tma_load_2d(sV + (uint32_t)st * WsSmem<HD>::kv_bytes + (h * KBOX + j) * BOX, &tmap_v, t * TC_BK + j * TC_BOX,
+                        (4 + h) * plane + row_q, bar_vf + 8 * st);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== UMMA issuer: the whole warp runs the loop (uniform operands), one elected lane issues =====
+    auto issue_qk = [&](int x, int st) {
+      const uint32_t q = sQ + (uint32_t)x * WsSmem<HD>::q_bytes, k = sK + (uint32_t)st * WsSmem<HD>::kv_bytes;
+      const uint32_t d = tmem_base + (uint32_t)x * WS_COL_TILE + WS_COL_S;
+#pragma unroll
+      for (int term = 0; term < 3; ++term) {
+        const uint32_t qa = q + ((term == 2) ? QBOX * BOX : 0u);
+        const uint32_t kb = k + ((term == 1) ? KBOX * BOX : 0u);
+#pragma unroll
+        for (int ks = 0; ks < KSTEPS_D; ++ks)
+          umma_tf32_ss_w(d, umma_desc(qa + ks * 1024u, BOX, 512u, 1u), umma_desc(kb + ks * 1024u, BOX, 512u, 1u), IDESC_QK,
+                         (term | ks) ? 1u : 0u);
+      }
+    };
+    auto issue_pv = [&](int x, int st) {
+      const uint32_t v = sV + (uint32_t)st * WsSmem<HD>::kv_bytes;
+      const uint32_t tb = tmem_base + (uint32_t)x * WS_COL_TILE;
+#pragma unroll
+      for (int term = 0; term < 3; ++term) {
+        const uint32_t pa = tb + ((term == 2) ? WS_COL_PLO : WS_COL_S);
+        const uint32_t vb = v + ((term == 1) ? KBOX * BOX : 0u);
+#pragma unroll
+        for (int ks = 0; ks < TC_BK / 8; ++ks)
+          umma_tf32_ts_w(tb + WS_COL_O, pa + ks * 8, umma_desc(vb + (ks >> 2) * BOX + (ks & 3) * 32u, 16u, 1024u, 2u), IDESC_PV,
+                         (term | ks) ? 1u : 0u);
+      }
+    };
+    mbar_wait(bar_kf, 0);
+    for (int x = 0; x < 2; ++x) {
+      mbar_wait(bar_qf + 8 * x, 0);
+      tc_fence_after();
+      issue_qk(x, 0);
+      tc_commit_w(bar_sf + 8 * x);
+    }
+    tc_commit_w(bar_ke);
+    for (int t = 0; t < nkt; ++t) {
+      const int st = t & 1, sn = (t + 1) & 1;
+      const uint32_t par = (uint32_t)(t & 1);
+#pragma unroll
+      for (int x = 0; x < 2; ++x) {
+        mbar_wait(bar_pr + 8 * x, par);                         // P(x,t) is in TMEM
+        if (t > 0) mbar_wait(bar_of + 8 * x, (uint32_t)((t - 1) & 1));   // O tile (x,t-1) has been read
+        if (x == 0) mbar_wait(bar_vf + 8 * st, (uint32_t)((t >> 1) & 1));
+        tc_fence_after();
+        issue_pv(x, st);
+        tc_commit_w(bar_or + 8 * x);
+        if (x == 1) tc_commit_w(bar_ve + 8 * st);
+        if (t + 1 < nkt) {
+          if (x == 0) { mbar_wait(bar_kf + 8 * sn, (uint32_t)(((t + 1) >> 1) & 1)); tc_fence_after(); }
+          issue_qk(x, sn);                                      // S columns are free: PV(x,t) is queued ahead of it
+          tc_commit_w(bar_sf + 8 * x);
+          if (x == 1) tc_commit_w(bar_ke + 8 * sn);
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== softmax warpgroup of query tile x: thread = query row =====
+    const int x = (warp - 4) >> 2;
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)x * WS_COL_TILE;
+    float o[HD];
+#pragma unroll
+    for (int c = 0; c < HD; ++c) o[c] = 0.f;
+    float m_run = -INFINITY, l_run = 0.f;
+    for (int t = 0; t < nkt; ++t) {
+      const uint32_t par = (uint32_t)(t & 1);
+      mbar_wait(bar_sf + 8 * x, par);
+      const bool pr = prof != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && x == 0 && row == 0 && t < 48;
+      if (pr) prof[t * 8 + 0] = clock64();
+      __syncwarp();
+      tc_fence_after();
+      uint32_t sr[TC_BK];
+#pragma unroll
+      for (int c = 0; c < TC_BK; c += 16) tmem_ld16(t_lane + WS_COL_S + c, sr + c);
+      tmem_wait_ld();
+      if (pr) prof[t * 8 + 1] = clock64();
+      const int kbase = t * TC_BK;
+      if (all_masked || kbase + TC_BK > Leff) {      // only the last key tile (or a fully masked utterance) needs masking
+#pragma unroll
+        for (int j = 0; j < TC_BK; ++j) {
+          float v = __uint_as_float(sr[j]);
+          if (all_masked) v = (kbase + j < L) ? 0.f : -INFINITY;
+          else if (kbase + j >= Leff) v = -INFINITY;
+          sr[j] = __float_as_uint(v);
+        }
+      }
+      float mx = __uint_as_float(sr[0]);
+#pragma unroll
+      for (int j = 1; j < TC_BK; ++j) mx = fmaxf(mx, __uint_as_float(sr[j]));
+      const float m_new = fmaxf(m_run, mx);
+      const float alpha = ws_ex2(m_run - m_new);
+      m_run = m_new;
+      float rs = 0.f;
+#pragma unroll
+      for (int c = 0; c < TC_BK; c += 16) {
+        uint32_t ph[16], pl[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float p = ws_ex2(__uint_as_float(sr[c + j]) - m_new);
+          rs += p;
+          ph[j] = tf32_hi(p);
+          pl[j] = __float_as_uint(p - __uint_as_float(ph[j]));
+        }
+        tmem_st16(t_lane + WS_COL_S + c, ph);       // P_hi overwrites the scores in place
+        tmem_st16(t_lane + WS_COL_PLO + c, pl);
+      }
+      l_run = l_run * alpha + rs;
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_pr + 8 * x) : "memory");
+      if (pr) prof[t * 8 + 2] = clock64();
+
+      mbar_wait(bar_or + 8 * x, par);
+      if (pr) prof[t * 8 + 3] = clock64();
+      __syncwarp();
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < HD; c += 16) {
+        uint32_t orr[16];
+        tmem_ld16(t_lane + WS_COL_O + c, orr);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) o[c + j] = fmaf(o[c + j], alpha, __uint_as_float(orr[j]));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_of + 8 * x) : "memory");
+      if (pr) prof[t * 8 + 4] = clock64();
+    }
+    const int qi = q0 + x * TC_BQ + row;
+    if (qi < L) {
+      const float inv = 1.0f / l_run;
+      float* dst = ctx + ((long long)b * L + qi) * (nh * HD) + head * HD;
+      if (ctx_lo == nullptr) {
+#pragma unroll
+        for (int c = 0; c < HD; c += 4)
+          *reinterpret_cast<float4*>(dst + c) = make_float4(o[c] * inv, o[c + 1] * inv, o[c + 2] * inv, o[c + 3] * inv);
+      } else {
+        float* dlo = ctx_lo + ((long long)b * L + qi) * (nh * HD) + head * HD;
+#pragma unroll
+        for (int c = 0; c < HD; c += 4) {
+          float h[4], l[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { const float v = o[c + e] * inv; h[e] = __uint_as_float(tf32_hi(v)); l[e] = __uint_as_float(tf32_hi(v - h[e])); }
+          *reinterpret_cast<float4*>(dst + c) = make_float4(h[0], h[1], h[2], h[3]);
+          *reinterpret_cast<float4*>(dlo + c) = make_float4(l[0], l[1], l[2], l[3]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(WS_TMEM_COLS) : "memory");
+  }
+}
+
 // ---- host side --------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -372,6 +666,17 @@ static int launch_tc_hd(const CUtensorMap& tmap_qk, const CUtensorMap& tmap_v, f
   M2_CUDA_OK(allow_smem(attention_tc_kernel<HD>, smem));
   dim3 grid(ceil_div(L, TC_BQ), nh, B);
   M2_LAUNCH(M2TTS_STAGE_ATTENTION, attention_tc_kernel<HD>, grid, TC_THREADS, smem, s, tmap_qk, tmap_v, ctx, lengths, B, L, nh, dbg_s, dbg_o, ctx_lo);
+  return M2TTS_OK;
+}
+
+static long long* g_ws_prof = nullptr;
+template <int HD>
+static int launch_ws_hd(const CUtensorMap& tmap_qk, const CUtensorMap& tmap_v, float* ctx, const int64_t* lengths, int B, int L, int nh,
+                        cudaStream_t s, float* ctx_lo) {
+  const size_t smem = WsSmem<HD>::total;
+  M2_CUDA_OK(allow_smem(attention_ws_kernel<HD>, smem));
+  dim3 grid(ceil_div(L, 2 * TC_BQ), nh, B);
+  M2_LAUNCH(M2TTS_STAGE_ATTENTION, attention_ws_kernel<HD>, grid, WS_THREADS, smem, s, tmap_qk, tmap_v, ctx, lengths, B, L, nh, ctx_lo, g_ws_prof);
   return M2TTS_OK;
 }
 
@@ -401,6 +706,13 @@ int launch_attention_tc(const float* qkv6, float* ctx, const int64_t* lengths, i
           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   M2_REQUIRE(r == CUDA_SUCCESS, M2TTS_E_CUDA, "attention_tc: cuTensorMapEncodeTiled (v) failed (%d)", (int)r);
+  if (attention_mode() != 2 && dbg_s == nullptr && dbg_o == nullptr && hd <= 48) {   // default: warp-specialised two-tile pipeline (head_dim 64 does not fit two query tiles)
+    switch (hd) {
+      case 16: return launch_ws_hd<16>(tmap_qk, tmap_v, ctx, lengths, B, L, nh, s, ctx_lo);
+      case 32: return launch_ws_hd<32>(tmap_qk, tmap_v, ctx, lengths, B, L, nh, s, ctx_lo);
+      default: return launch_ws_hd<48>(tmap_qk, tmap_v, ctx, lengths, B, L, nh, s, ctx_lo);
+    }
+  }
   switch (hd) {
     case 16: return launch_tc_hd<16>(tmap_qk, tmap_v, ctx, lengths, B, L, nh, s, dbg_s, dbg_o, ctx_lo);
     case 32: return launch_tc_hd<32>(tmap_qk, tmap_v, ctx, lengths, B, L, nh, s, dbg_s, dbg_o, ctx_lo);
@@ -410,6 +722,9 @@ int launch_attention_tc(const float* qkv6, float* ctx, const int64_t* lengths, i
 }
 
 }  // namespace m2
+
+// bring-up: device buffer of 48 x 8 int64 receiving phase timestamps of CTA 0 / query tile A (NULL = off)
+extern "C" int m2tts_attention_set_prof(long long* dev_buf) { m2::g_ws_prof = dev_buf; return M2TTS_OK; }
 
 // Test / bring-up entry: run the tensor-core attention on caller-prepared hi/lo planes and
 // optionally dump the first score tile (128x64, pre-mask, log2 domain) and the first P*V tile.

@@ -152,7 +152,7 @@ int launch_ln_split(const float* x, const float* w, const float* b, float* plane
 int launch_w_split(const float* const* src, float* const* dst, const long long* n, int jobs, cudaStream_t s);
 int launch_linear_tc(const float* a_planes, const float* w_planes, LinTcArgs a, int B, int stage, cudaStream_t s);
 int* debug_words_device();  // pinned mapped scratch for hang diagnostics (may be null)
-int attention_mode();  // 0 = tensor cores when supported, 1 = force the FFMA kernel
+int attention_mode();  // 0 = tensor cores (warp-specialised kernel), 1 = force the FFMA kernel, 2 = tensor cores, single-warpgroup kernel
 int vocoder_mode();    // 0 = tensor-core convolutions for the wide stages, 1 = FFMA everywhere
 
 // tensor-core ("tap-GEMM") convolutions on plain fp32 [B][C][Lp] (conv_tc.cu / conv_tc2.cu)

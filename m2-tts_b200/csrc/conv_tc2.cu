@@ -103,17 +103,14 @@ tapgemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const TapG
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== UMMA issuer: one thread; everything loop-invariant is hoisted so a chunk is 18 x (add, UMMA) =====
+    {
+      // ===== UMMA issuer: the whole warp runs the loop with warp-uniform operands and one elected lane issues
+      // (ct_mma_w). All taps read the SAME activation rows (their shifts are applied to accumulator rows in the
+      // epilogue) and their weight rows / accumulator columns are contiguous, so one UMMA with N = rows_total covers
+      // them: a chunk is 3 terms x 2 k-steps = 6 UMMAs of N up to 256 instead of 18 narrow ones. =====
       if (a.w_resident) ct_wait(bar_wf, 0, dbg, 4, 0);
-      uint32_t idesc[3], dcol[3], wrow16[3];
-#pragma unroll
-      for (int tap = 0; tap < 3; ++tap) {
-        idesc[tap] = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | ((uint32_t)(a.tap_rows[tap] >> 3) << 17) |
-                     ((uint32_t)(CT_BM >> 4) << 24);
-        dcol[tap] = (uint32_t)a.tap_dcol[tap];
-        wrow16[tap] = ((uint32_t)(a.tap_wrow[tap] >> 3) * 512u) >> 4;      // descriptor address units (16 B)
-      }
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | ((uint32_t)(a.rows_total >> 3) << 17) |
+                             ((uint32_t)(CT_BM >> 4) << 24);
       // activations: MN-major, 128B swizzle / 32B atoms: LBO = next 32 positions (next box), SBO = next 4 channels
       const uint64_t a_tmpl = ct_desc(0u, CT_ABOX, 512u, 1u);
       // weights: K-major, no swizzle (8 x 16 B core matrices): LBO = next 4 channels, SBO = next 8 rows
@@ -136,22 +133,19 @@ tapgemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const TapG
           const uint64_t ad0 = a_tmpl | (uint64_t)((sA >> 4) & 0x3FFFu);
           const uint64_t bd0 = w_tmpl | (uint64_t)((sW >> 4) & 0x3FFFu);
 #pragma unroll
-          for (int tap = 0; tap < 3; ++tap) {
+          for (int term = 0; term < 3; ++term) {           // hi*hi, hi*lo, lo*hi
+            const uint32_t ap = (term == 2) ? 1u : 0u, wp = (term == 1) ? 1u : 0u;
 #pragma unroll
-            for (int term = 0; term < 3; ++term) {           // hi*hi, hi*lo, lo*hi
-              const uint32_t ap = (term == 2) ? 1u : 0u, wp = (term == 1) ? 1u : 0u;
-#pragma unroll
-              for (int ks = 0; ks < CT_CK / 8; ++ks) {
-                const uint64_t ad = ad0 + (uint64_t)((ap * CT_RAW_STAGE + ks * 1024u) >> 4);
-                const uint64_t bd = bd0 + (uint64_t)(wp * wplane16 + wrow16[tap] + ks * 16u);
-                ct_mma(dbase + dcol[tap], ad, bd, idesc[tap], (c | (uint32_t)term | (uint32_t)ks) ? 1u : 0u);
-              }
+            for (int ks = 0; ks < CT_CK / 8; ++ks) {
+              const uint64_t ad = ad0 + (uint64_t)((ap * CT_RAW_STAGE + ks * 1024u) >> 4);
+              const uint64_t bd = bd0 + (uint64_t)(wp * wplane16 + ks * 16u);
+              ct_mma_w(dbase, ad, bd, idesc, (c | (uint32_t)term | (uint32_t)ks) ? 1u : 0u);
             }
           }
-          ct_commit(bar_sple + 8 * ss);
+          ct_commit_w(bar_sple + 8 * ss);
           if (++ss == (uint32_t)S) { ss = 0; ss_par ^= 1u; }
         }
-        ct_commit(bar_accf + 8 * buf);
+        ct_commit_w(bar_accf + 8 * buf);
         if (++buf == (uint32_t)NB) { buf = 0; ++buf_round; }
       }
     }

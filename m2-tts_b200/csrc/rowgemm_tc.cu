@@ -78,8 +78,9 @@ lingemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  if (tid == 0) {
-    // K is consumed in passes of up to LG_KB boxes (96 columns) through the same buffers
+  if (warp == 0) {
+    // K is consumed in passes of up to LG_KB boxes (96 columns) through the same buffers. The whole warp runs the
+    // loop (warp-uniform operands) and one elected lane issues each UMMA; lane 0 alone drives the TMA.
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.n_tile >> 3) << 17) | ((uint32_t)(LG_BM >> 4) << 24);
     const int total_boxes = (a.K + 31) / 32;
     const int passes = (total_boxes + a.kboxes - 1) / a.kboxes;
@@ -87,13 +88,16 @@ lingemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const int kb0 = p * a.kboxes;
       const int nb = min(a.kboxes, total_boxes - kb0);
       if (p > 0) lg_wait(bar_empty, (uint32_t)((p - 1) & 1), dbg, 13);   // previous pass's UMMAs have read the buffers
-      const uint32_t bytes = 2u * nb * (a_box + w_box);
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_full), "r"(bytes) : "memory");
-      for (int plane = 0; plane < 2; ++plane)
-        for (int kb = 0; kb < nb; ++kb) {
-          lg_tma_2d(sA + (uint32_t)(plane * a.kboxes + kb) * a_box, &tmap_a, (kb0 + kb) * 32, plane * a.R + row0, bar_full);
-          lg_tma_2d(sW + (uint32_t)(plane * a.kboxes + kb) * w_box, &tmap_w, (kb0 + kb) * 32, plane * a.N + n0, bar_full);
-        }
+      if (tid == 0) {
+        const uint32_t bytes = 2u * nb * (a_box + w_box);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_full), "r"(bytes) : "memory");
+        for (int plane = 0; plane < 2; ++plane)
+          for (int kb = 0; kb < nb; ++kb) {
+            lg_tma_2d(sA + (uint32_t)(plane * a.kboxes + kb) * a_box, &tmap_a, (kb0 + kb) * 32, plane * a.R + row0, bar_full);
+            lg_tma_2d(sW + (uint32_t)(plane * a.kboxes + kb) * w_box, &tmap_w, (kb0 + kb) * 32, plane * a.N + n0, bar_full);
+          }
+      }
+      __syncwarp();
       lg_wait(bar_full, (uint32_t)(p & 1), dbg, 11);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int ksteps = (min(a.K - kb0 * 32, nb * 32) + 7) / 8;
@@ -103,13 +107,16 @@ lingemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           const uint64_t ad = lg_desc_k_sw128(sA + (ap * a.kboxes + (ks >> 2)) * a_box + (ks & 3) * 32u);
           const uint64_t bd = lg_desc_k_sw128(sW + (wp * a.kboxes + (ks >> 2)) * w_box + (ks & 3) * 32u);
           const uint32_t acc = (p | term | ks) ? 1u : 0u;
-          asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+          asm volatile("{\n\t.reg .pred p, q;\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                       "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
                        ::"r"(tmem_base), "l"(ad), "l"(bd), "r"(idesc), "r"(acc) : "memory");
         }
       }
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_empty) : "memory");
+      asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+                   "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar_empty) : "memory");
     }
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_acc) : "memory");
+    asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+                 "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar_acc) : "memory");
   }
   __syncwarp();
   lg_wait(bar_acc, 0, dbg, 12);

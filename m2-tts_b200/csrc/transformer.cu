@@ -75,7 +75,7 @@ extern "C" int m2tts_transformer_layer(const m2tts_layer_weights* w, const float
 
   const int R = B * L;
   // ---- tensor-core path: every GEMM of the layer on tcgen05 (3xTF32), operands as hi/lo planes ----
-  if (attention_mode() == 0 && attention_tc_supported(hd) && linear_tc_eligible(H, 3 * H) && linear_tc_eligible(H, H) &&
+  if (attention_mode() != 1 && attention_tc_supported(hd) && linear_tc_eligible(H, 3 * H) && linear_tc_eligible(H, H) &&
       linear_tc_eligible(H, F) && linear_tc_eligible(F, H) && (H % 16 == 0)) {
     const float* srcs[4] = {w->qkv_w, w->out_w, w->ffn1_w, w->ffn2_w};
     const long long ns[4] = {(long long)3 * H * H, (long long)H * H, (long long)F * H, (long long)H * F};
@@ -112,7 +112,7 @@ extern "C" int m2tts_transformer_layer(const m2tts_layer_weights* w, const float
                      {w->ffn1_w, ws.w1_t, F, H}, {w->ffn2_w, ws.w2_t, H, F}};
   if ((rc = launch_pack_transpose(jobs, 4, s))) return rc;
 
-  const bool use_tc = attention_mode() == 0 && attention_tc_supported(hd);
+  const bool use_tc = attention_mode() != 1 && attention_tc_supported(hd);
   {  // q,k,v = split(LN1(x) Wqkv^T)
     RowGemmArgs a{};
     a.x = x_in; a.ldx = H; a.ln_w = w->norm1_w; a.ln_b = w->norm1_b; a.eps = ln_eps;
@@ -172,7 +172,7 @@ extern "C" int m2tts_layernorm_proj(const float* x, const float* ln_w, const flo
   int rc;
   {  // tensor-core path when the caller's workspace also has room for the normalised rows as hi/lo planes
     float* xn = cv.take<float>((size_t)2 * rows * H);
-    if (attention_mode() == 0 && cv.ok() && linear_tc_eligible(H, N) && (N % 16 == 0) && (H % 4 == 0)) {
+    if (attention_mode() != 1 && cv.ok() && linear_tc_eligible(H, N) && (N % 16 == 0) && (H % 4 == 0)) {
       const float* srcs[1] = {W};
       float* dsts[1] = {wt};
       const long long ns[1] = {(long long)N * H};

@@ -160,8 +160,8 @@ voc_stage_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedSt
         }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== UMMA issuer =====
+    {
+      // ===== UMMA issuer: the whole warp runs the loop with uniform operands, one elected lane issues =====
       ct_wait(bar_w, 0, dbg, 2, 0);
       const uint32_t sW = sbase + K::OFF_W;
       const uint64_t w_tmpl = ct_desc(0u, 128u, 512u, 0u);
@@ -194,12 +194,12 @@ voc_stage_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedSt
 #pragma unroll
               for (int ks = 0; ks < CI / 8; ++ks) {
                 const uint32_t aaddr = sX + (uint32_t)ap * K::XRAW + (uint32_t)(ks >> 2) * (XR * 128) + (uint32_t)(1 + shift) * 128u + (uint32_t)(ks & 3) * 32u;
-                ct_mma(dcol, x_tmpl | (uint64_t)((aaddr >> 4) & 0x3FFFu), wdesc(part, N, wp, ks), tap == 0 ? id_2c : id_c,
+                ct_mma_w(dcol, x_tmpl | (uint64_t)((aaddr >> 4) & 0x3FFFu), wdesc(part, N, wp, ks), tap == 0 ? id_2c : id_c,
                        (tap | term | ks) ? 1u : 0u);
               }
             }
           }
-          ct_commit(bar(c, ACC_UP));
+          ct_commit_w(bar(c, ACC_UP));
         }
         // ---- conv1 and conv2 of the ResBlock: D[i, co] = sum_tap A[i + tap - 1, :] W_tap ----
 #pragma unroll
@@ -221,13 +221,13 @@ voc_stage_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedSt
 #pragma unroll
                   for (int ks = 0; ks < C / 8; ++ks) {
                     const uint32_t aaddr = sA + (uint32_t)ap * K::UPL + (uint32_t)(128 * h + tap) * ROWB + (uint32_t)ks * 32u;
-                    ct_mma(d, u_tmpl | (uint64_t)((aaddr >> 4) & 0x3FFFu), wdesc(wpart + tap * C * C, C, wp, ks), id_c,
+                    ct_mma_w(d, u_tmpl | (uint64_t)((aaddr >> 4) & 0x3FFFu), wdesc(wpart + tap * C * C, C, wp, ks), id_c,
                            (tap | term | ks) ? 1u : 0u);
                   }
                 }
-              ct_commit(bar(c, (conv == 0 ? ACC_C1 : ACC_C2) + h));
+              ct_commit_w(bar(c, (conv == 0 ? ACC_C1 : ACC_C2) + h));
             }
-            if (conv == 1) ct_commit(bar(c, XS_FREE));     // V (= the X split region) is dead once conv2 has run
+            if (conv == 1) ct_commit_w(bar(c, XS_FREE));     // V (= the X split region) is dead once conv2 has run
           }
         }
       }

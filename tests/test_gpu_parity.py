@@ -276,7 +276,7 @@ def test_batch_sharding_is_exact():
 
 
 # --------------------------------------------------------------------------- tensor-core attention
-@pytest.mark.parametrize("mode", [0, 1])  # 0 = tcgen05 3xTF32 kernel, 1 = fp32 FFMA kernel
+@pytest.mark.parametrize("mode", [0, 1, 2])  # 0 = warp-specialised tcgen05 3xTF32 kernel, 1 = fp32 FFMA kernel, 2 = single-warpgroup tcgen05 kernel
 def test_attention_kernels_both_meet_fp32_tolerance(mode):
     from models import _native as nat
     lib = nat.lib()
