@@ -373,11 +373,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_co
 // warps 4-7 / 8-11 = softmax warpgroups of query tile A / B (thread = query row = TMEM lane).
 // The issuer alternates  PV(A,t) QK(A,t+1) | PV(B,t) QK(B,t+1)  so the tensor pipe runs one tile's
 // GEMMs while the other tile's warpgroup does its softmax; K and V tiles are double-buffered rings.
-// TMEM per query tile (192 columns): S (64, overwritten in place by P_hi) | P_lo (64) | O tile (64).
+// The hi/lo split is folded into the N dimension so that every UMMA is wide (a tf32 UMMA with M = 128, K = 8 costs
+// ~max(N/2, 32 + N/4) cycles, measured with mma_bench.cu, so narrow ones waste the pipe):
+//   S[:, 0:64]   = Q_hi [K_hi | K_lo]^T (one N = 128 UMMA per k-step; columns 64:128 hold the Q_hi K_lo^T part)
+//   S[:, 0:64]  += Q_lo K_hi^T          (N = 64)
+//   O[:, 0:2HD]  = P_hi [V_hi | V_lo]   (N = 2 HD);   O[:, 0:HD] += P_lo V_hi   (N = HD)
+// and the softmax warpgroup adds the two column halves when it reads S and O.
+// TMEM per query tile (224 columns): S (128; P_hi overwrites columns 0:64 and P_lo columns 64:128) | O (2 HD <= 96).
 // =================================================================================================
 constexpr int WS_THREADS = 384;
 constexpr uint32_t WS_TMEM_COLS = 512;
-constexpr uint32_t WS_COL_TILE = 192, WS_COL_S = 0, WS_COL_PLO = 64, WS_COL_O = 128;
+constexpr uint32_t WS_COL_TILE = 224, WS_COL_S = 0, WS_COL_PLO = 64, WS_COL_O = 128;
 constexpr int WS_KV_STAGES = 2;
 
 template <int HD>
@@ -406,13 +412,15 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_co
   constexpr uint32_t BOX = WsSmem<HD>::box_bytes;
   constexpr int QBOX = TC_BQ / TC_BOX, KBOX = TC_BK / TC_BOX;
   constexpr int KSTEPS_D = HD / 8;
-  constexpr uint32_t IDESC_QK = umma_idesc_tf32(TC_BQ, TC_BK, 1, 1);
-  constexpr uint32_t IDESC_PV = umma_idesc_tf32(TC_BQ, HD, 0, 0);
+  constexpr uint32_t IDESC_QK2 = umma_idesc_tf32(TC_BQ, 2 * TC_BK, 1, 1);   // Q_hi x [K_hi | K_lo]
+  constexpr uint32_t IDESC_QK1 = umma_idesc_tf32(TC_BQ, TC_BK, 1, 1);       // Q_lo x K_hi
+  constexpr uint32_t IDESC_PV2 = umma_idesc_tf32(TC_BQ, 2 * HD, 0, 0);      // P_hi x [V_hi | V_lo]
+  constexpr uint32_t IDESC_PV1 = umma_idesc_tf32(TC_BQ, HD, 0, 0);          // P_lo x V_hi
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = sbase;                                   // [tile][hi|lo][QBOX][HD rows][128 B]
-  const uint32_t sK = sbase + WsSmem<HD>::off_k;               // [stage][hi|lo][KBOX][HD][128 B]
+  const uint32_t sK = sbase + WsSmem<HD>::off_k;               // [stage][hi|lo][KBOX][HD][128 B]; V: [stage][KBOX][hi|lo][HD][128 B]
   const uint32_t sV = sbase + WsSmem<HD>::off_v;
   const uint32_t sBar = sbase + WsSmem<HD>::off_bar;
   // barriers: q_full[2] k_full[2] k_empty[2] v_full[2] v_empty[2] s_full[2] p_ready[2] o_ready[2] o_free[2]
@@ -478,7 +486,7 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_co
         mbar_expect_tx(bar_vf + 8 * st, WsSmem<HD>::kv_bytes);
         for (int h = 0; h < 2; ++h)
           for (int j = 0; j < KBOX; ++j)
-            tma_load_2d(sV + (uint32_t)st * WsSmem<HD>::kv_bytes + (h * KBOX + j) * BOX, &tmap_v, t * TC_BK + j * TC_BOX,
+            tma_load_2d(sV + (uint32_t)st * WsSmem<HD>::kv_bytes + (j * 2 + h) * BOX, &tmap_v, t * TC_BK + j * TC_BOX,
                         (4 + h) * plane + row_q, bar_vf + 8 * st);
       }
     }
@@ -487,28 +495,29 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_co
     auto issue_qk = [&](int x, int st) {
       const uint32_t q = sQ + (uint32_t)x * WsSmem<HD>::q_bytes, k = sK + (uint32_t)st * WsSmem<HD>::kv_bytes;
       const uint32_t d = tmem_base + (uint32_t)x * WS_COL_TILE + WS_COL_S;
+      // MN-major, 128B swizzle / 32B atoms: LBO = next 32 positions (next box; the K_lo boxes follow the K_hi boxes,
+      // so N = 128 simply runs on into them), SBO = next 4 d-rows
 #pragma unroll
-      for (int term = 0; term < 3; ++term) {
-        const uint32_t qa = q + ((term == 2) ? QBOX * BOX : 0u);
-        const uint32_t kb = k + ((term == 1) ? KBOX * BOX : 0u);
+      for (int ks = 0; ks < KSTEPS_D; ++ks)
+        umma_tf32_ss_w(d, umma_desc(q + ks * 1024u, BOX, 512u, 1u), umma_desc(k + ks * 1024u, BOX, 512u, 1u), IDESC_QK2, ks ? 1u : 0u);
 #pragma unroll
-        for (int ks = 0; ks < KSTEPS_D; ++ks)
-          umma_tf32_ss_w(d, umma_desc(qa + ks * 1024u, BOX, 512u, 1u), umma_desc(kb + ks * 1024u, BOX, 512u, 1u), IDESC_QK,
-                         (term | ks) ? 1u : 0u);
-      }
+      for (int ks = 0; ks < KSTEPS_D; ++ks)
+        umma_tf32_ss_w(d, umma_desc(q + QBOX * BOX + ks * 1024u, BOX, 512u, 1u), umma_desc(k + ks * 1024u, BOX, 512u, 1u), IDESC_QK1, 1u);
     };
-    auto issue_pv = [&](int x, int st) {
+    auto issue_pv = [&](int x, int st, uint32_t accumulate) {
       const uint32_t v = sV + (uint32_t)st * WsSmem<HD>::kv_bytes;
       const uint32_t tb = tmem_base + (uint32_t)x * WS_COL_TILE;
+      // V^T boxes are K-major (keys contiguous): rows = d; per 32-key box the V_hi rows are followed by the V_lo rows.
+      // O accumulates in TMEM over ALL key tiles (the softmax warpgroup rescales it in place when the row maximum
+      // grows by more than 2^8, see below), so only the very first UMMA of a query tile overwrites.
 #pragma unroll
-      for (int term = 0; term < 3; ++term) {
-        const uint32_t pa = tb + ((term == 2) ? WS_COL_PLO : WS_COL_S);
-        const uint32_t vb = v + ((term == 1) ? KBOX * BOX : 0u);
+      for (int ks = 0; ks < TC_BK / 8; ++ks)
+        umma_tf32_ts_w(tb + WS_COL_O, tb + WS_COL_S + ks * 8, umma_desc(v + (ks >> 2) * (2 * BOX) + (ks & 3) * 32u, 16u, 1024u, 2u),
+                       IDESC_PV2, ks ? 1u : accumulate);
 #pragma unroll
-        for (int ks = 0; ks < TC_BK / 8; ++ks)
-          umma_tf32_ts_w(tb + WS_COL_O, pa + ks * 8, umma_desc(vb + (ks >> 2) * BOX + (ks & 3) * 32u, 16u, 1024u, 2u), IDESC_PV,
-                         (term | ks) ? 1u : 0u);
-      }
+      for (int ks = 0; ks < TC_BK / 8; ++ks)
+        umma_tf32_ts_w(tb + WS_COL_O, tb + WS_COL_PLO + ks * 8, umma_desc(v + (ks >> 2) * (2 * BOX) + (ks & 3) * 32u, 16u, 1024u, 2u),
+                       IDESC_PV1, 1u);
     };
     mbar_wait(bar_kf, 0);
     for (int x = 0; x < 2; ++x) {
@@ -523,12 +532,11 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_co
       const uint32_t par = (uint32_t)(t & 1);
 #pragma unroll
       for (int x = 0; x < 2; ++x) {
-        mbar_wait(bar_pr + 8 * x, par);                         // P(x,t) is in TMEM
-        if (t > 0) mbar_wait(bar_of + 8 * x, (uint32_t)((t - 1) & 1));   // O tile (x,t-1) has been read
+        mbar_wait(bar_pr + 8 * x, par);                         // P(x,t) is in TMEM (and O has been rescaled if needed)
         if (x == 0) mbar_wait(bar_vf + 8 * st, (uint32_t)((t >> 1) & 1));
         tc_fence_after();
-        issue_pv(x, st);
-        tc_commit_w(bar_or + 8 * x);
+        issue_pv(x, st, t > 0 ? 1u : 0u);
+        if (t + 1 == nkt) tc_commit_w(bar_or + 8 * x);          // the query tile's O is complete
         if (x == 1) tc_commit_w(bar_ve + 8 * st);
         if (t + 1 < nkt) {
           if (x == 0) { mbar_wait(bar_kf + 8 * sn, (uint32_t)(((t + 1) >> 1) & 1)); tc_fence_after(); }
@@ -543,10 +551,10 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_co
     const int x = (warp - 4) >> 2;
     const int row = (warp & 3) * 32 + lane;
     const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)x * WS_COL_TILE;
-    float o[HD];
-#pragma unroll
-    for (int c = 0; c < HD; ++c) o[c] = 0.f;
-    float m_run = -INFINITY, l_run = 0.f;
+    // Online softmax with LAZY rescaling: p = 2^(s - m_ref) where m_ref is a per-row reference that is only raised
+    // when the running maximum exceeds it by more than 2^8 (p stays <= 256, harmless in fp32 / TF32 hi+lo), so O can
+    // accumulate in TMEM across key tiles and the warpgroup touches it only on those rare occasions and at the end.
+    float m_ref = -INFINITY, l_run = 0.f;
     for (int t = 0; t < nkt; ++t) {
       const uint32_t par = (uint32_t)(t & 1);
       mbar_wait(bar_sf + 8 * x, par);
@@ -557,7 +565,14 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_co
       uint32_t sr[TC_BK];
 #pragma unroll
       for (int c = 0; c < TC_BK; c += 16) tmem_ld16(t_lane + WS_COL_S + c, sr + c);
-      tmem_wait_ld();
+#pragma unroll
+      for (int c = 0; c < TC_BK; c += 16) {       // + the Q_hi K_lo^T part
+        uint32_t s2[16];
+        tmem_ld16(t_lane + WS_COL_S + TC_BK + c, s2);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) sr[c + j] = __float_as_uint(__uint_as_float(sr[c + j]) + __uint_as_float(s2[j]));
+      }
       if (pr) prof[t * 8 + 1] = clock64();
       const int kbase = t * TC_BK;
       if (all_masked || kbase + TC_BK > Leff) {      // only the last key tile (or a fully masked utterance) needs masking
@@ -572,16 +587,32 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_co
       float mx = __uint_as_float(sr[0]);
 #pragma unroll
       for (int j = 1; j < TC_BK; ++j) mx = fmaxf(mx, __uint_as_float(sr[j]));
-      const float m_new = fmaxf(m_run, mx);
-      const float alpha = ws_ex2(m_run - m_new);
-      m_run = m_new;
+      if (t == 0) {
+        m_ref = mx;                                  // key 0 is never masked, so mx is finite; PV(0) overwrites O
+      } else if (__any_sync(0xffffffffu, mx > m_ref + 8.0f)) {
+        // S(t) complete implies PV(t-1) complete (issued ahead of it), and PV(t) waits for our arrival below:
+        // O is quiescent, rescale this warp's rows in place.
+        const float m_new = fmaxf(m_ref, mx);
+        const float alpha = ws_ex2(m_ref - m_new);
+        m_ref = m_new;
+        l_run *= alpha;
+#pragma unroll
+        for (int c = 0; c < 2 * HD; c += 16) {
+          uint32_t orr[16];
+          tmem_ld16(t_lane + WS_COL_O + c, orr);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) orr[j] = __float_as_uint(__uint_as_float(orr[j]) * alpha);
+          tmem_st16(t_lane + WS_COL_O + c, orr);
+        }
+      }
       float rs = 0.f;
 #pragma unroll
       for (int c = 0; c < TC_BK; c += 16) {
         uint32_t ph[16], pl[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const float p = ws_ex2(__uint_as_float(sr[c + j]) - m_new);
+          const float p = ws_ex2(__uint_as_float(sr[c + j]) - m_ref);
           rs += p;
           ph[j] = tf32_hi(p);
           pl[j] = __float_as_uint(p - __uint_as_float(ph[j]));
@@ -589,29 +620,26 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_co
         tmem_st16(t_lane + WS_COL_S + c, ph);       // P_hi overwrites the scores in place
         tmem_st16(t_lane + WS_COL_PLO + c, pl);
       }
-      l_run = l_run * alpha + rs;
+      l_run += rs;
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_pr + 8 * x) : "memory");
       if (pr) prof[t * 8 + 2] = clock64();
-
-      mbar_wait(bar_or + 8 * x, par);
-      if (pr) prof[t * 8 + 3] = clock64();
-      __syncwarp();
-      tc_fence_after();
+    }
+    // ---- the query tile's O is complete: fetch it (both column halves), normalise, store ----
+    mbar_wait(bar_or + 8 * x, 0);
+    __syncwarp();
+    tc_fence_after();
+    float o[HD];
 #pragma unroll
-      for (int c = 0; c < HD; c += 16) {
-        uint32_t orr[16];
-        tmem_ld16(t_lane + WS_COL_O + c, orr);
-        tmem_wait_ld();
+    for (int c = 0; c < HD; c += 16) {
+      uint32_t orr[16], or2[16];
+      tmem_ld16(t_lane + WS_COL_O + c, orr);
+      tmem_ld16(t_lane + WS_COL_O + HD + c, or2);    // the P_hi V_lo part
+      tmem_wait_ld();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) o[c + j] = fmaf(o[c + j], alpha, __uint_as_float(orr[j]));
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_of + 8 * x) : "memory");
-      if (pr) prof[t * 8 + 4] = clock64();
+      for (int j = 0; j < 16; ++j) o[c + j] = __uint_as_float(orr[j]) + __uint_as_float(or2[j]);
     }
     const int qi = q0 + x * TC_BQ + row;
     if (qi < L) {

@@ -56,12 +56,22 @@ __global__ void __launch_bounds__(128) mma_bench_kernel(int mode, int N, int n, 
     }
     const uint32_t d0 = tmem, d1 = tmem + (nacc > 1 ? (uint32_t)N : 0u);
     t0 = clock64();
+    if (mode == 2) {
+      for (int i = 0; i < n; i += 4) {
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          asm volatile("{\n\t.reg .pred p, q;\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                       "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+                       ::"r"((ks & 1) ? d1 : d0), "r"(tmem + 256u + (uint32_t)ks * 8u), "l"(bd[ks]), "r"(idesc), "r"((uint32_t)(i > 0)) : "memory");
+      }
+    } else {
     for (int i = 0; i < n; i += 4) {
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks)
         asm volatile("{\n\t.reg .pred p, q;\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
                      ::"r"((ks & 1) ? d1 : d0), "l"(ad[ks]), "l"(bd[ks]), "r"(idesc), "r"((uint32_t)(i > 0)) : "memory");
+    }
     }
     t1 = clock64();
     asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"

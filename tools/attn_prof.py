@@ -22,6 +22,6 @@ torch.cuda.synchronize()
 lib.m2tts_attention_set_prof(None)
 p = prof.cpu().view(48, 8)
 d = p[8:40]
-names = ["S ld", "softmax+P st", "wait PV", "O update"]
-segs = [(d[:, i + 1] - d[:, i]).float().mean().item() for i in range(4)] + [(p[9:41, 0] - p[8:40, 4]).float().mean().item()]
+names = ["S ld", "softmax+P st"]
+segs = [(d[:, i + 1] - d[:, i]).float().mean().item() for i in range(2)] + [(p[9:41, 0] - p[8:40, 2]).float().mean().item()]
 print("per-tile cycles " + ", ".join(f"{n}={v:.0f}" for n, v in zip(names + ["wait next S"], segs)) + f"  total={(p[40, 0] - p[8, 0]).item() / 32:.0f}")

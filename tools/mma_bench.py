@@ -10,9 +10,9 @@ out = torch.zeros(2, dtype=torch.int64, device="cuda")
 names = {0: "A smem K-major SW128 / B K-major noswz", 1: "A,B smem MN-major SW128-32B", 2: "A TMEM / B K-major SW128",
          3: "A smem K-major SW64 / B K-major noswz", 4: "A,B smem K-major SW128"}
 n = 512
-for mode in (0, 1, 3):
-    for N in (16, 32, 64, 128):
-        for nacc, elect in ((1, 0), (1, 2)):
+for mode in (2, 4):
+    for N in (16, 32, 48, 64, 96, 128, 192, 256):
+        for nacc, elect in ((1, 2),):
             if nacc * N > 256:
                 continue
             for _ in range(2):
