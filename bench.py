@@ -298,13 +298,31 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             roof.update(achieved=None, frac=None)
         all_stage_tflops = {k: round(fl[k] / (v[0] / args.steps * 1e-3) / 1e12, 2) for k, v in stage_ms.items()
                             if k in fl and v[0] > 0}
+        # every stage as a fraction of ITS roofline: GEMM-shaped stages against the measured bf16 tensor peak (an
+        # fp32-faithful 3xTF32 kernel tops out at 1/6 of it), streaming stages against the measured HBM copy bandwidth
+        by = stage_bytes_per_step()
+        stage_roofline = {}
+        for k, v in stage_ms.items():
+            sec = v[0] / args.steps * 1e-3
+            if sec <= 0:
+                continue
+            if k in by:
+                ach = by[k] / sec / 1e9
+                stage_roofline[k] = {"bound": "hbm", "achieved": round(ach, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                     "frac": round(ach / peaks["hbm_gbs"], 4)}
+            elif k in fl:
+                ach = fl[k] / sec / 1e12
+                stage_roofline[k] = {"bound": "tensor" if k in tensor_stages or k in TENSOR_LINEAR else "ffma",
+                                     "achieved": round(ach, 2), "unit": "TFLOP/s",
+                                     "peak": peaks["bf16_tflops_sustained"] if (k in tensor_stages or k in TENSOR_LINEAR) else round(ffma_peak_tflops, 1),
+                                     "frac": round(ach / (peaks["bf16_tflops_sustained"] if (k in tensor_stages or k in TENSOR_LINEAR) else ffma_peak_tflops), 4)}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": workload_config(world), "clocks": clocks, "gpu_launches": launches,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4,
                         "d2h_bytes_per_step": audio_host.numel() * 4, "ms_per_step": e2e_ms / args.steps},
-                "roofline": roof, "stage_tflops": all_stage_tflops,
+                "roofline": roof, "stage_roofline": stage_roofline, "stage_tflops": all_stage_tflops,
                 "stage_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in sorted(stage_ms.items(), key=lambda kv: -kv[1][0])},
                 "x_realtime_per_gpu": value / world}
         if world == 1 and not args.skip_cpu_baseline:
@@ -341,6 +359,16 @@ def stage_flops_per_step():
         c_in = c
     fl["voc_fused"] += 2 * 3 * c_in * Lc * B
     return fl
+
+
+TENSOR_LINEAR = {"ln_qkv", "out_proj", "ffn1", "ffn2", "ln_proj"}      # tcgen05 3xTF32 linear layers
+
+
+def stage_bytes_per_step():
+    """Algorithmic HBM bytes of one C3 step for the streaming (bandwidth-bound) stages: every operand once."""
+    rows = BATCH * FRAMES
+    return {"layernorm": (2 * LAYERS) * 2 * rows * HIDDEN * 4 + 2 * rows * HIDDEN * 4,   # 2 per layer + the final one: x in, LN(x) out
+            "pack": 2 * 4 * sum(x * 4 for x in (3 * HIDDEN * HIDDEN, HIDDEN * HIDDEN, 2 * HIDDEN * HIDDEN, 2 * HIDDEN * HIDDEN)) * LAYERS}
 
 
 def read_traffic(kernel: str):
