@@ -367,7 +367,12 @@ TENSOR_LINEAR = {"ln_qkv", "out_proj", "ffn1", "ffn2", "ln_proj"}      # tcgen05
 def stage_bytes_per_step():
     """Algorithmic HBM bytes of one C3 step for the streaming (bandwidth-bound) stages: every operand once."""
     rows = BATCH * FRAMES
+    F = 2 * HIDDEN
+    per = rows * 4
     return {"layernorm": (2 * LAYERS) * 2 * rows * HIDDEN * 4 + 2 * rows * HIDDEN * 4,   # 2 per layer + the final one: x in, LN(x) out
+            # K = 96 linear layers sit at the 3xTF32 ridge (36 FLOP/B): reported against HBM, every operand once in fp32
+            "ln_qkv": LAYERS * per * (HIDDEN + 3 * HIDDEN), "out_proj": LAYERS * per * 3 * HIDDEN,
+            "ffn1": LAYERS * per * (HIDDEN + F), "ffn2": LAYERS * per * (F + 2 * HIDDEN), "ln_proj": per * (HIDDEN + MEL),
             "pack": 2 * 4 * sum(x * 4 for x in (3 * HIDDEN * HIDDEN, HIDDEN * HIDDEN, 2 * HIDDEN * HIDDEN, 2 * HIDDEN * HIDDEN)) * LAYERS}
 
 
