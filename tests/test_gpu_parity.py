@@ -207,6 +207,30 @@ def test_vocoder_matches_oracle(stage, B, T):
     assert H.max_abs(got_t.cpu(), want) <= FP32_TOL
 
 
+@pytest.mark.parametrize("B,T", [(1, 128), (2, 256), (4, 128), (8, 131), (1, 2048)])
+def test_c5_vocoder_sweep_points_match_oracle(B, T):
+    """BASELINE.json configs[4] (vocoder-only sweep): points the CPU oracle finishes in seconds; the full grid is
+    timed by tools/sweep_vocoder.py and covered at large sizes by the batch-independence property below."""
+    m = cuda_model("stage2")
+    mel = torch.randn(B, 80, T, generator=torch.Generator().manual_seed(B * 10000 + T))
+    got = m.vocoder(mel.to(DEV))
+    assert got.shape == (B, 1, 64 * T)
+    assert H.max_abs(got.cpu(), oracle.vocoder(cpu_sd(m), mel)) <= FP32_TOL
+
+
+def test_vocoder_large_batch_rows_are_independent_and_deterministic():
+    """C5 at sizes the oracle cannot reach: utterance b of a 64 x 1024 batch equals the same mel run alone (bit-exact),
+    twice in a row, and a batch of one utterance repeated gives identical rows."""
+    m = cuda_model("stage2")
+    mel = torch.randn(64, 80, 1024, generator=torch.Generator().manual_seed(77)).to(DEV)
+    full = m.vocoder(mel)
+    assert torch.equal(full, m.vocoder(mel))
+    for b in (0, 31, 63):
+        assert torch.equal(full[b:b + 1], m.vocoder(mel[b:b + 1]))
+    rep = m.vocoder(mel[5:6].expand(16, -1, -1).contiguous())
+    assert all(torch.equal(rep[0], rep[i]) for i in range(1, 16))
+
+
 def test_vocoder_batch_independence():
     """Size-independent property at a larger size: the vocoder is deterministic and
     batch-independent — utterance b of a batch equals the same utterance run alone."""
