@@ -250,6 +250,10 @@ int m2tts_vocoder_stage_fused(const float* x, const float* up_w, const float* up
 int m2tts_rowshift_probe(const float* A, const float* Bm, float* D, int rows_total, int N, int K, int rowbytes,
                          int shift, int base_offset, m2tts_stream_t stream);
 
+/* ---- after the path: waveform -> PCM16 on the device (scripts/synthesize.py:147-155 saves through
+ * src/utils/audio.py:154-180; clip to [-1,1], x32767, round half to even). audio/pcm: n samples, device memory. */
+int m2tts_pcm16(const float* audio, int16_t* pcm, long long n, m2tts_stream_t stream);
+
 /* Bring-up / measurement tools (tools/mma_bench.py, tools/fused_prof.py, tools/attn_prof.py): tcgen05.mma cost per
  * operand configuration, and optional clock64 phase timestamps of the fused vocoder stage / attention kernels. */
 int m2tts_mma_bench(int mode, int N, int n, int nacc, int elect, long long* out_dev, m2tts_stream_t stream);

@@ -77,9 +77,39 @@ int launch_pack_transpose(const PackJob* jobs, int n_jobs, cudaStream_t s) {
   return M2TTS_OK;
 }
 
+// float waveform -> PCM16 (clip to [-1, 1], scale by 32767, round half to even like numpy.round): the wav writer's
+// conversion done where the samples already are, so only 2 bytes per sample cross PCIe (utils/audio.py).
+__global__ void pcm16_kernel(const float* __restrict__ x, int16_t* __restrict__ y, long long n) {
+  const long long n4 = n >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    short4 o;
+    o.x = (short)__float2int_rn(fminf(fmaxf(v.x, -1.f), 1.f) * 32767.f);
+    o.y = (short)__float2int_rn(fminf(fmaxf(v.y, -1.f), 1.f) * 32767.f);
+    o.z = (short)__float2int_rn(fminf(fmaxf(v.z, -1.f), 1.f) * 32767.f);
+    o.w = (short)__float2int_rn(fminf(fmaxf(v.w, -1.f), 1.f) * 32767.f);
+    reinterpret_cast<short4*>(y)[i] = o;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const long long i = (n4 << 2) + threadIdx.x;
+    y[i] = (int16_t)__float2int_rn(fminf(fmaxf(x[i], -1.f), 1.f) * 32767.f);
+  }
+}
+
 }  // namespace m2
 
 using namespace m2;
+
+extern "C" int m2tts_pcm16(const float* audio, int16_t* pcm, long long n, m2tts_stream_t stream) {
+  M2_REQUIRE(audio && pcm, M2TTS_E_NULLPTR, "pcm16: null pointer");
+  M2_REQUIRE(n > 0, M2TTS_E_BADSHAPE, "pcm16: n=%lld", n);
+  M2_REQUIRE((((uintptr_t)audio) & 15) == 0 && (((uintptr_t)pcm) & 7) == 0, M2TTS_E_BADSHAPE, "pcm16: misaligned pointers");
+  long long blocks = ((n >> 2) + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  M2_LAUNCH(M2TTS_STAGE_EMBED, pcm16_kernel, (int)blocks, 256, 0, (cudaStream_t)stream, audio, pcm, n);
+  return M2TTS_OK;
+}
 
 extern "C" int m2tts_embed_posenc(const int64_t* ids, const float* emb, const float* pe,
                                   const int64_t* lengths, float* x, uint8_t* mask, int B, int S,
