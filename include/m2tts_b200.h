@@ -118,9 +118,10 @@ int m2tts_stage_timing_read(float* ms_sum, int* launches, int n_stages);
 /* Diagnostics: the tensor-core kernels bound every mbarrier wait; on a timeout they store
  * {code, chunk, blockIdx.x, blockIdx.y, blockIdx.z} in pinned host memory and trap. */
 int m2tts_debug_words(int* out, int n);
-/* Attention kernel selection for m2tts_transformer_layer: 0 (default) = tcgen05/TMEM tensor-core
- * kernel with 3xTF32 splitting when head_dim is one of {16,32,48,64}, else the fp32 FFMA kernel;
- * 1 = always the fp32 FFMA kernel. Process-wide; also settable with M2TTS_ATTENTION=ffma. */
+/* Attention kernel selection for m2tts_transformer_layer (head_dim in {16,32,48,64}; other head dims always take the
+ * fp32 FFMA kernel): 0 (default) = tcgen05 warp-specialised kernel with the 16-bit split (fp16 hi/lo operands, fp32
+ * accumulation; operands saturate at +-65000); 1 = fp32 FFMA kernel; 2 = TF32 split, single-warpgroup kernel;
+ * 3 = TF32 split, warp-specialised kernel (no range limit). Process-wide; also M2TTS_ATTENTION=ffma|tc1|tf32. */
 int m2tts_set_attention_mode(int mode);
 /* Vocoder kernel selection: 0 (default) = every leading stage whose three convolutions have channel
  * counts that are multiples of 16 runs as persistent tcgen05 implicit GEMMs with 3xTF32 splitting
@@ -257,6 +258,8 @@ int m2tts_pcm16(const float* audio, int16_t* pcm, long long n, m2tts_stream_t st
 /* Bring-up / measurement tools (tools/mma_bench.py, tools/fused_prof.py, tools/attn_prof.py): tcgen05.mma cost per
  * operand configuration, and optional clock64 phase timestamps of the fused vocoder stage / attention kernels. */
 int m2tts_mma_bench(int mode, int N, int n, int nacc, int elect, long long* out_dev, m2tts_stream_t stream);
+/* kind::f16 operand-layout probe (tests/umma_probe_f16_run.py): mode 0 MN-major smem x MN-major smem, 1 TMEM x K-major, 2 K-major x K-major */
+int m2tts_umma_probe_f16(const float* A, const float* Bm, float* D, int N, int K, int mode, m2tts_stream_t stream);
 int m2tts_vocoder_stage_fused_set_prof(long long* dev_buf);
 int m2tts_attention_set_prof(long long* dev_buf);
 

@@ -18,118 +18,14 @@
 // -> tcgen05.ld -> o = o*alpha + O_tile in registers. K and V tiles are single-buffered but
 // refilled by TMA as soon as the UMMAs that read them have committed; two CTAs per SM overlap
 // each other's tensor and ALU phases. TMEM: 256 columns per CTA (S 64 | P_hi 64 | P_lo 64 | O 64).
-#include "common.cuh"
-#include <cuda.h>
-#include <math.h>
+#include "attention_tc.cuh"
 
 namespace m2 {
 
-constexpr int TC_BQ = 128;      // queries per CTA
-constexpr int TC_BK = 64;       // keys per tile
 constexpr int TC_BOX = 32;      // positions per TMA box (128 B of fp32)
 constexpr int TC_THREADS = 128;
 constexpr uint32_t TC_TMEM_COLS = 256;
 constexpr uint32_t TC_COL_S = 0, TC_COL_PHI = 64, TC_COL_PLO = 128, TC_COL_O = 192;
-
-// ---- PTX wrappers -----------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  for (uint32_t it = 0; it < (1u << 24); ++it) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    if (ok) return;
-  }
-  __trap();  // a lost arrival would otherwise hang the GPU; fail loudly instead
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// D[tmem] (+)= A[smem desc] * B[smem desc], TF32 inputs, fp32 accumulate
-__device__ __forceinline__ void umma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
-}
-// D[tmem] (+)= A[tmem] * B[smem desc]
-__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
-}
-// Warp-collective variants: the WHOLE warp executes the call with warp-uniform operands and one elected lane
-// issues. ptxas then keeps descriptors in uniform registers and emits a predicated UTCHMMA; issuing from an
-// `if (lane == 0)` region instead makes it wrap every UMMA in an ELECT/BRA.U.ANY loop fed by R2UR moves, which
-// costs more than the MMA itself at these tile sizes (measured with mma_bench.cu).
-__device__ __forceinline__ void tc_commit_w(uint32_t bar) {
-  asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
-               "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void umma_tf32_ss_w(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
-  asm volatile("{\n\t.reg .pred p, q;\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-               "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-               ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
-}
-__device__ __forceinline__ void umma_tf32_ts_w(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
-  asm volatile("{\n\t.reg .pred p, q;\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-               "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
-               ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
-      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
-        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
-}
-__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
-// UMMA shared-memory descriptor, 128-byte swizzle (layout_type 2), descriptor version 1 (sm_100).
-// Byte offsets are encoded >> 4. For MN-major operands LBO = stride between 32-element (128 B)
-// groups along M/N and SBO = stride between 8-row groups along K; for K-major operands SBO =
-// stride between 8-row groups along M/N and LBO is unused (encoded 1).
-// layout_type: 2 = SWIZZLE_128B (16-B atomicity; K-major operands), 1 = SWIZZLE_128B_BASE32B (32-B
-// atomicity, 4-row K atoms): the ONLY layout tcgen05 accepts for MN-major 32-bit (TF32) operands —
-// with layout type 2 and the MN-major bit set the MMA silently produces zeros (measured with
-// umma_probe.cu, see tests/umma_probe_run.py).
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
-  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
-         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | ((uint64_t)layout_type << 61);
-}
-// UMMA instruction descriptor: fp32 accumulate (bits 4-5 = 1), A/B format TF32 (2) at bits 7-9 /
-// 10-12, A/B major at bits 15/16 (1 = MN-major), N>>3 at bits 17-22, M>>4 at bits 24-28.
-__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N, int a_mn_major, int b_mn_major) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
-         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-__device__ __forceinline__ uint32_t tf32_hi(float v) { return __float_as_uint(v) & 0xFFFFE000u; }
 
 template <int HD>
 struct TcSmem {
@@ -397,11 +293,6 @@ struct WsSmem {
   static constexpr uint32_t total = off_bar + 256 + 1024 /*align slack*/;
 };
 
-__device__ __forceinline__ float ws_ex2(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
 
 template <int HD>
 __global__ void __launch_bounds__(WS_THREADS, 1)
@@ -734,7 +625,7 @@ int launch_attention_tc(const float* qkv6, float* ctx, const int64_t* lengths, i
           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   M2_REQUIRE(r == CUDA_SUCCESS, M2TTS_E_CUDA, "attention_tc: cuTensorMapEncodeTiled (v) failed (%d)", (int)r);
-  if (attention_mode() != 2 && dbg_s == nullptr && dbg_o == nullptr && hd <= 48) {   // default: warp-specialised two-tile pipeline (head_dim 64 does not fit two query tiles)
+  if (attention_mode() != 2 && dbg_s == nullptr && dbg_o == nullptr && hd <= 48) {   // mode 3 (or 0 via the plane entry point)   // default: warp-specialised two-tile pipeline (head_dim 64 does not fit two query tiles)
     switch (hd) {
       case 16: return launch_ws_hd<16>(tmap_qk, tmap_v, ctx, lengths, B, L, nh, s, ctx_lo);
       case 32: return launch_ws_hd<32>(tmap_qk, tmap_v, ctx, lengths, B, L, nh, s, ctx_lo);

@@ -133,6 +133,9 @@ bool attention_tc_supported(int hd);
 int launch_attention_tc(const float* qkv6, float* ctx, const int64_t* lengths, int B, int L, int Lp,
                         int nh, int hd, cudaStream_t s, float* dbg_s = nullptr, float* dbg_o = nullptr,
                         float* ctx_lo = nullptr);  // ctx_lo != null: write ctx as TF32 hi/lo planes (ctx = hi plane)
+// 16-bit split attention (attention_h.cu): qkvh = six fp16 planes [6][B][nh][hd][Lp], Lp % 8 == 0
+int launch_attention_h(const void* qkvh, float* ctx, const int64_t* lengths, int B, int L, int Lp, int nh, int hd,
+                       cudaStream_t s, float* ctx_lo = nullptr);
 // ---- tensor-core linear layers (rowgemm_tc.cu) ----
 struct LinTcArgs {
   int R, L, K, N, n_tile;          // rows total, rows per utterance, inner dim, outputs, outputs per CTA
@@ -142,7 +145,7 @@ struct LinTcArgs {
   const float* residual; int ldr;  // plain fp32 [R, ldr] or null
   float* y; int ldy;               // plain output [R, ldy] (mode 0)
   float* y_planes;                 // mode 1: hi/lo planes [2][R][N]
-  // mode 2: attention operand planes [6][B][nh][hd][Lp]
+  // mode 2: attention operand planes [6][B][nh][hd][Lp] (fp32 holding TF32 hi/lo); mode 3: the same as fp16 hi/lo
   float* qkv6; long long plane_stride; int nh, hd, Lp; float qscale;
   int mode;
 };
@@ -152,7 +155,7 @@ int launch_ln_split(const float* x, const float* w, const float* b, float* plane
 int launch_w_split(const float* const* src, float* const* dst, const long long* n, int jobs, cudaStream_t s);
 int launch_linear_tc(const float* a_planes, const float* w_planes, LinTcArgs a, int B, int stage, cudaStream_t s);
 int* debug_words_device();  // pinned mapped scratch for hang diagnostics (may be null)
-int attention_mode();  // 0 = tensor cores (warp-specialised kernel), 1 = force the FFMA kernel, 2 = tensor cores, single-warpgroup kernel
+int attention_mode();  // 0 = tensor cores, 16-bit split (attention_h.cu); 1 = fp32 FFMA kernel; 2 = TF32 split, single-warpgroup kernel; 3 = TF32 split, warp-specialised kernel
 int vocoder_mode();    // 0 = tensor-core convolutions for the wide stages, 1 = FFMA everywhere
 
 // tensor-core ("tap-GEMM") convolutions on plain fp32 [B][C][Lp] (conv_tc.cu / conv_tc2.cu)

@@ -8,6 +8,7 @@
 // Reference ops: components.py:55,70-72 (qkv), :90 (out_proj), :103 (ffn), tts_model.py:223-226.
 #include "common.cuh"
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <math.h>
 
 namespace m2 {
@@ -162,6 +163,21 @@ lingemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         for (int e = 0; e < 4; ++e) { h[e] = lg_hi(x[4 * j + e]); lo[e] = lg_hi(x[4 * j + e] - h[e]); }
         hp[j] = make_float4(h[0], h[1], h[2], h[3]);
         lp[j] = make_float4(lo[0], lo[1], lo[2], lo[3]);
+      }
+    } else if (a.mode == 3) {      // attention operand planes as fp16 hi/lo (attention_h.cu), saturated to the fp16 range
+      const int H = a.nh * a.hd;
+      __half* base = reinterpret_cast<__half*>(a.qkv6);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int n = n0 + c0 + j;
+        const int which = n / H, rem = n - which * H;
+        const int head = rem / a.hd, d = rem - head * a.hd;
+        float t = (which == 0) ? x[j] * a.qscale : x[j];
+        t = fminf(fmaxf(t, -65000.f), 65000.f);
+        const __half h = __float2half_rn(t);
+        __half* hp = base + (long long)(2 * which) * a.plane_stride + (((long long)b * a.nh + head) * a.hd + d) * a.Lp + l;
+        hp[0] = h;
+        hp[a.plane_stride] = __float2half_rn(t - __half2float(h));
       }
     } else {
       const int H = a.nh * a.hd;

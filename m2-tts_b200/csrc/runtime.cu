@@ -68,7 +68,7 @@ int attention_mode() {
   int m = g_attn_mode.load(std::memory_order_relaxed);
   if (m < 0) {
     const char* e = getenv("M2TTS_ATTENTION");
-    m = (e && strcmp(e, "ffma") == 0) ? 1 : ((e && strcmp(e, "tc1") == 0) ? 2 : 0);
+    m = (e && strcmp(e, "ffma") == 0) ? 1 : ((e && strcmp(e, "tc1") == 0) ? 2 : ((e && strcmp(e, "tf32") == 0) ? 3 : 0));
     g_attn_mode.store(m);
   }
   return m;
@@ -95,7 +95,8 @@ extern "C" int m2tts_set_vocoder_mode(int mode) {
 }
 
 extern "C" int m2tts_set_attention_mode(int mode) {
-  M2_REQUIRE(mode >= 0 && mode <= 2, M2TTS_E_BADSHAPE, "set_attention_mode: mode must be 0 (tensor), 1 (ffma) or 2 (tensor, single-warpgroup kernel)");
+  M2_REQUIRE(mode >= 0 && mode <= 3, M2TTS_E_BADSHAPE,
+             "set_attention_mode: 0 = tensor cores 16-bit split, 1 = ffma, 2 = TF32 single-warpgroup kernel, 3 = TF32 warp-specialised kernel");
   g_attn_mode.store(mode);
   return M2TTS_OK;
 }

@@ -81,14 +81,20 @@ extern "C" int m2tts_transformer_layer(const m2tts_layer_weights* w, const float
     const long long ns[4] = {(long long)3 * H * H, (long long)H * H, (long long)F * H, (long long)H * F};
     if ((rc = launch_w_split(srcs, ws.w_planes, ns, 4, s))) return rc;
     if ((rc = launch_ln_split(x_in, w->norm1_w, w->norm1_b, ws.xn, R, H, ln_eps, s))) return rc;
+    const bool half_planes = attention_mode() == 0;      // 16-bit split attention (default): fp16 hi/lo planes
+    const int Lp = half_planes ? ((L + 7) & ~7) : ws.Lp;
     {  // attention operand planes = split(LN1(x) Wqkv^T)
       LinTcArgs a{};
-      a.R = R; a.L = L; a.K = H; a.N = 3 * H; a.mode = 2; a.qkv6 = ws.q; a.plane_stride = (long long)B * H * ws.Lp;
-      a.nh = num_heads; a.hd = hd; a.Lp = ws.Lp; a.qscale = (float)((1.0 / sqrt((double)hd)) * 1.4426950408889634);
+      a.R = R; a.L = L; a.K = H; a.N = 3 * H; a.mode = half_planes ? 3 : 2; a.qkv6 = ws.q; a.plane_stride = (long long)B * H * Lp;
+      a.nh = num_heads; a.hd = hd; a.Lp = Lp; a.qscale = (float)((1.0 / sqrt((double)hd)) * 1.4426950408889634);
       if ((rc = launch_linear_tc(ws.xn, ws.w_planes[0], a, B, M2TTS_STAGE_LN_QKV, s))) return rc;
     }
-    if ((rc = launch_attention_tc(ws.q, ws.ctx, lengths, B, L, ws.Lp, num_heads, hd, s, nullptr, nullptr,
-                                  ws.ctx + (size_t)R * H))) return rc;
+    if (half_planes) {
+      if ((rc = launch_attention_h(ws.q, ws.ctx, lengths, B, L, Lp, num_heads, hd, s, ws.ctx + (size_t)R * H))) return rc;
+    } else {
+      if ((rc = launch_attention_tc(ws.q, ws.ctx, lengths, B, L, ws.Lp, num_heads, hd, s, nullptr, nullptr,
+                                    ws.ctx + (size_t)R * H))) return rc;
+    }
     {  // x1 = x + ctx Wo^T + bo
       LinTcArgs a{};
       a.R = R; a.L = L; a.K = H; a.N = H; a.mode = 0; a.bias = w->out_b; a.residual = x_in; a.ldr = H; a.y = ws.x1; a.ldy = H;

@@ -89,6 +89,7 @@ _SIGNATURES = {
     "m2tts_vocoder_stage_fused": (C.c_int, [C.c_void_p] * 10 + [C.c_int] * 3 + [C.c_void_p, C.c_size_t, C.c_void_p]),
     "m2tts_rowshift_probe": (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 6 + [C.c_void_p]),
     "m2tts_mma_bench": (C.c_int, [C.c_int] * 5 + [C.c_void_p, C.c_void_p]),
+    "m2tts_umma_probe_f16": (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 3 + [C.c_void_p]),
     "m2tts_pcm16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
     "m2tts_vocoder_stage_fused_set_prof": (C.c_int, [C.c_void_p]),
     "m2tts_attention_set_prof": (C.c_int, [C.c_void_p]),

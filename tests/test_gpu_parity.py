@@ -300,7 +300,7 @@ def test_batch_sharding_is_exact():
 
 
 # --------------------------------------------------------------------------- tensor-core attention
-@pytest.mark.parametrize("mode", [0, 1, 2])  # 0 = warp-specialised tcgen05 3xTF32 kernel, 1 = fp32 FFMA kernel, 2 = single-warpgroup tcgen05 kernel
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])  # 0 = 16-bit split tcgen05 kernel, 1 = fp32 FFMA, 2 = TF32 single-warpgroup, 3 = TF32 warp-specialised
 def test_attention_kernels_both_meet_fp32_tolerance(mode):
     from models import _native as nat
     lib = nat.lib()
