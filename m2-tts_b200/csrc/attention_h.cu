@@ -58,7 +58,7 @@ __device__ __forceinline__ void umma_f16_ts_w(uint32_t d_tmem, uint32_t a_tmem, 
 template <int HD>
 __global__ void __launch_bounds__(AH_THREADS, 1)
 attention_h_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__ ctx, const int64_t* __restrict__ lengths,
-                   int B, int L, int nh, float* __restrict__ ctx_lo) {
+                   int B, int L, int nh, float* __restrict__ ctx_lo, __half* __restrict__ ctx_h) {
   static_assert(HD % 16 == 0 && HD >= 16 && HD <= 64, "16-bit split attention: head_dim in {16,32,48,64}");
   constexpr uint32_t BOX = AhSmem<HD>::box;
   constexpr int KSTEPS_D = HD / 16;
@@ -290,7 +290,25 @@ attention_h_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__
     if (qi < L) {
       const float inv = 1.0f / l_run;
       float* dst = ctx + ((long long)b * L + qi) * (nh * HD) + head * HD;
-      if (ctx_lo == nullptr) {
+      if (ctx_h != nullptr) {   // fp16 hi/lo planes [2][B*L][nh*HD] for the 16-bit split out_proj (lin_h.cu)
+        __half* dh = ctx_h + ((long long)b * L + qi) * (nh * HD) + head * HD;
+        __half* dl = dh + (long long)B * L * (nh * HD);
+#pragma unroll
+        for (int c = 0; c < HD; c += 8) {
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float v0 = fminf(fmaxf(o[c + 2 * e] * inv, -65000.f), 65000.f), v1 = fminf(fmaxf(o[c + 2 * e + 1] * inv, -65000.f), 65000.f);
+            const __half2 h = __floats2half2_rn(v0, v1);
+            const float2 hf = __half22float2(h);
+            const __half2 lw = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+            hi[e] = *reinterpret_cast<const uint32_t*>(&h);
+            lo[e] = *reinterpret_cast<const uint32_t*>(&lw);
+          }
+          *reinterpret_cast<uint4*>(dh + c) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(dl + c) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+      } else if (ctx_lo == nullptr) {
 #pragma unroll
         for (int c = 0; c < HD; c += 4)
           *reinterpret_cast<float4*>(dst + c) = make_float4(o[c] * inv, o[c + 1] * inv, o[c + 2] * inv, o[c + 3] * inv);
@@ -331,18 +349,20 @@ static EncodeTiledFnH ah_encode_fn() {
 }
 
 template <int HD>
-static int launch_ah_hd(const CUtensorMap& tmap, float* ctx, const int64_t* lengths, int B, int L, int nh, cudaStream_t s, float* ctx_lo) {
+static int launch_ah_hd(const CUtensorMap& tmap, float* ctx, const int64_t* lengths, int B, int L, int nh, cudaStream_t s, float* ctx_lo,
+                        __half* ctx_h) {
   const size_t smem = AhSmem<HD>::total;
   M2_CUDA_OK(allow_smem(attention_h_kernel<HD>, smem));
   dim3 grid(ceil_div(L, 2 * TC_BQ), nh, B);
-  M2_LAUNCH(M2TTS_STAGE_ATTENTION, attention_h_kernel<HD>, grid, AH_THREADS, smem, s, tmap, ctx, lengths, B, L, nh, ctx_lo);
+  M2_LAUNCH(M2TTS_STAGE_ATTENTION, attention_h_kernel<HD>, grid, AH_THREADS, smem, s, tmap, ctx, lengths, B, L, nh, ctx_lo, ctx_h);
   return M2TTS_OK;
 }
 
 // qkvh: [6][B][nh][hd][Lp] fp16 (Q_hi,Q_lo,K_hi,K_lo,V_hi,V_lo), Lp % 8 == 0, Q pre-scaled by scale*log2e.
 int launch_attention_h(const void* qkvh, float* ctx, const int64_t* lengths, int B, int L, int Lp, int nh, int hd,
-                       cudaStream_t s, float* ctx_lo) {
-  M2_REQUIRE(qkvh && ctx, M2TTS_E_NULLPTR, "attention_h: null pointer");
+                       cudaStream_t s, float* ctx_lo, void* ctx_half_planes) {
+  __half* ctx_h = reinterpret_cast<__half*>(ctx_half_planes);
+  M2_REQUIRE(qkvh && (ctx || ctx_half_planes), M2TTS_E_NULLPTR, "attention_h: null pointer");
   M2_REQUIRE(attention_tc_supported(hd), M2TTS_E_UNSUPPORTED, "attention_h: head_dim %d unsupported", hd);
   M2_REQUIRE(B > 0 && L > 0 && nh > 0 && B <= 65535 && nh <= 65535 && (Lp & 7) == 0 && Lp >= L, M2TTS_E_BADSHAPE,
              "attention_h: B=%d L=%d Lp=%d nh=%d", B, L, Lp, nh);
@@ -359,10 +379,10 @@ int launch_attention_h(const void* qkvh, float* ctx, const int64_t* lengths, int
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   M2_REQUIRE(r == CUDA_SUCCESS, M2TTS_E_CUDA, "attention_h: cuTensorMapEncodeTiled failed (%d)", (int)r);
   switch (hd) {
-    case 16: return launch_ah_hd<16>(tmap, ctx, lengths, B, L, nh, s, ctx_lo);
-    case 32: return launch_ah_hd<32>(tmap, ctx, lengths, B, L, nh, s, ctx_lo);
-    case 48: return launch_ah_hd<48>(tmap, ctx, lengths, B, L, nh, s, ctx_lo);
-    default: return launch_ah_hd<64>(tmap, ctx, lengths, B, L, nh, s, ctx_lo);
+    case 16: return launch_ah_hd<16>(tmap, ctx, lengths, B, L, nh, s, ctx_lo, ctx_h);
+    case 32: return launch_ah_hd<32>(tmap, ctx, lengths, B, L, nh, s, ctx_lo, ctx_h);
+    case 48: return launch_ah_hd<48>(tmap, ctx, lengths, B, L, nh, s, ctx_lo, ctx_h);
+    default: return launch_ah_hd<64>(tmap, ctx, lengths, B, L, nh, s, ctx_lo, ctx_h);
   }
 }
 

@@ -135,7 +135,21 @@ int launch_attention_tc(const float* qkv6, float* ctx, const int64_t* lengths, i
                         float* ctx_lo = nullptr);  // ctx_lo != null: write ctx as TF32 hi/lo planes (ctx = hi plane)
 // 16-bit split attention (attention_h.cu): qkvh = six fp16 planes [6][B][nh][hd][Lp], Lp % 8 == 0
 int launch_attention_h(const void* qkvh, float* ctx, const int64_t* lengths, int B, int L, int Lp, int nh, int hd,
-                       cudaStream_t s, float* ctx_lo = nullptr);
+                       cudaStream_t s, float* ctx_lo = nullptr, void* ctx_half_planes = nullptr);   // ctx_half_planes: fp16 [2][B*L][nh*hd]
+// ---- persistent 16-bit split linear layers (lin_h.cu): operands as fp16 hi/lo planes ----
+struct LinHParams {
+  int R, K, N;
+  const float* bias; int relu;
+  const float* residual; int ldr;  // fp32 [R][ldr] or null (mode 0)
+  float* y; int ldy;               // mode 0: fp32 [R][ldy]
+  void* y_planes;                  // mode 1: fp16 hi/lo planes [2][R][N]
+  void* qkvh; long long plane_stride; int L, nh, hd, Lp; float qscale;   // mode 3: attention operand planes
+  int mode;
+};
+bool linear_h_eligible(int K, int N);
+int launch_ln_split_h(const float* x, const float* w, const float* b, void* planes, long long R, int K, float eps, cudaStream_t s);
+int launch_w_split_h(const float* const* src, void* const* dst, const long long* n, int jobs, cudaStream_t s);
+int launch_linear_h(const void* a_planes, const void* w_planes, const LinHParams& q, int stage, cudaStream_t s);
 // ---- tensor-core linear layers (rowgemm_tc.cu) ----
 struct LinTcArgs {
   int R, L, K, N, n_tile;          // rows total, rows per utterance, inner dim, outputs, outputs per CTA

@@ -1,0 +1,365 @@
+// lin_h.cu — the transformer's linear layers as ONE persistent, warp-specialised tcgen05 kernel with the 16-bit split
+// (fp16 hi/lo operands, fp32 accumulation; see attention_h.cu for the error model):
+//   C[rows, N] = A[rows, K] @ W[N, K]^T  (+bias, ReLU, +residual)      components.py:55,70-72,90,103; tts_model.py:223-226
+// A arrives as fp16 hi/lo planes [2][R][K] (LayerNorm/split kernel below, the attention epilogue, or the FFN1 epilogue),
+// W as fp16 hi/lo planes [2][N][K]. Unlike lingemm_tc_kernel (rowgemm_tc.cu), which re-loaded the whole weight matrix
+// for every 128-row tile and ran load -> UMMA -> epilogue serially, here
+//   * every weight row is RESIDENT in shared memory for the life of the CTA (<= 110 KB),
+//   * warp 0 streams 128-row A tiles through a ring with TMA, warp 1 issues the UMMAs (warp-collective), warps 2-5
+//     run the epilogue out of one of two TMEM accumulator buffers while the next unit's UMMAs execute,
+//   * N is processed in passes of np <= 128 columns and the hi/lo split is folded into N: per k-step
+//     A_hi x [W_hi ; W_lo] (N = 2 np) and A_lo x W_hi (N = np); the epilogue adds the two column halves.
+// Epilogue modes: 0 = fp32 row-major (+bias, +residual), 1 = fp16 hi/lo planes [2][R][N] (+bias, ReLU) for the next
+// GEMM, 3 = the attention operand planes [6][B][nh][hd][Lp] (Q rows scaled by scale*log2 e), saturated to fp16 range.
+#include "common.cuh"
+#include "attention_tc.cuh"
+#include <cuda_fp16.h>
+
+namespace m2 {
+
+constexpr int LH_BM = 128;
+constexpr int LH_THREADS = 192;            // producer, issuer, 4 epilogue warps
+
+struct LinHArgs {
+  int R, K, N;                     // rows, inner dim, outputs
+  int np, n_passes, kboxes;        // columns per pass, passes, 32-column boxes of K
+  int a_stages;
+  const float* bias;               // [N] or null
+  int relu;
+  const float* residual; int ldr;  // fp32 [R][ldr] or null (mode 0)
+  float* y; int ldy;               // mode 0
+  __half* y_planes;                // mode 1: [2][R][N]
+  __half* qkvh; long long plane_stride; int L, nh, hd, Lp; float qscale;   // mode 3
+  int mode;
+};
+
+// Operand rows are 32 halves = 64 bytes (64-B swizzle): K = 96 is then exactly three boxes (with 128-byte rows a
+// quarter of every weight/activation tile would be zero padding, and the QKV weights would not leave room for a ring).
+__device__ __forceinline__ uint64_t lh_desc(uint32_t saddr) {   // K-major, 64-B swizzle: SBO = 8 rows = 512 B
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(512u >> 4) << 32) | (1ull << 46) | (4ull << 61);
+}
+__device__ __forceinline__ void lh_mma_w(uint32_t d, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p, q;\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(d), "l"(ad), "l"(bd), "r"(idesc), "r"(acc) : "memory");
+}
+
+__global__ void __launch_bounds__(LH_THREADS, 1)
+lin_h_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, const LinHArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (sbase - smem_u32(smem_raw));
+  const uint32_t a_box = LH_BM * 64u;                                   // 128 rows x 32 halves
+  const uint32_t a_stage = 2u * a.kboxes * a_box;                       // hi + lo
+  const uint32_t w_box = (uint32_t)a.np * 64u;
+  const uint32_t w_bytes = (uint32_t)a.kboxes * a.n_passes * 2u * w_box;
+  const uint32_t sA = sbase;                                            // [stage][plane][kbox][128 x 64 B]
+  const uint32_t sW = sA + (uint32_t)a.a_stages * a_stage;              // [kbox][pass][plane][np x 64 B]
+  const uint32_t sBias = sW + w_bytes;                                  // N floats
+  const uint32_t sBar = (sBias + (uint32_t)a.N * 4u + 15u) & ~15u;
+  // barriers: a_full[4] a_empty[4] acc_full[2] acc_empty[2] w_full
+  const uint32_t bar_af = sBar, bar_ae = sBar + 32, bar_cf = sBar + 64, bar_ce = sBar + 80, bar_w = sBar + 96, tmem_slot = sBar + 104;
+  float* bias_s = reinterpret_cast<float*>(gbase + (sBias - sbase));
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m_tiles = (a.R + LH_BM - 1) / LH_BM;
+  const int S = a.a_stages;
+
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) { mbar_init(bar_af + 8 * i, 1); mbar_init(bar_ae + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_cf + 8 * i, 1); mbar_init(bar_ce + 8 * i, 4); }
+    mbar_init(bar_w, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
+  }
+  for (int i = tid; i < a.N; i += LH_THREADS) bias_s[i] = a.bias != nullptr ? a.bias[i] : 0.f;
+  if (warp == 0) {
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== producer: all weight rows once, then the A tiles =====
+      mbar_expect_tx(bar_w, w_bytes);
+      for (int kb = 0; kb < a.kboxes; ++kb)
+        for (int p = 0; p < a.n_passes; ++p)
+          for (int pl = 0; pl < 2; ++pl)
+            tma_load_2d(sW + (uint32_t)((kb * a.n_passes + p) * 2 + pl) * w_box, &tmap_w, kb * 32, pl * a.N + p * a.np, bar_w);
+      int it = 0;
+      for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x, ++it) {
+        const int st = it % S;
+        if (it >= S) mbar_wait(bar_ae + 8 * st, (uint32_t)(((it / S) - 1) & 1));
+        mbar_expect_tx(bar_af + 8 * st, a_stage);
+        for (int pl = 0; pl < 2; ++pl)
+          for (int kb = 0; kb < a.kboxes; ++kb)
+            tma_load_2d(sA + (uint32_t)st * a_stage + (uint32_t)(pl * a.kboxes + kb) * a_box, &tmap_a, kb * 32, pl * a.R + mt * LH_BM,
+                        bar_af + 8 * st);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== UMMA issuer (whole warp, one elected lane issues) =====
+    mbar_wait(bar_w, 0);
+    const uint32_t idesc2 = (1u << 4) | ((uint32_t)((2 * a.np) >> 3) << 17) | ((uint32_t)(LH_BM >> 4) << 24);   // fp16 x fp16 -> fp32, K-major
+    const uint32_t idesc1 = (1u << 4) | ((uint32_t)(a.np >> 3) << 17) | ((uint32_t)(LH_BM >> 4) << 24);
+    const int ksteps = a.K / 16;
+    int it = 0, unit = 0;
+    for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x, ++it) {
+      const int st = it % S;
+      mbar_wait(bar_af + 8 * st, (uint32_t)((it / S) & 1));
+      tc_fence_after();
+      const uint32_t aHi = sA + (uint32_t)st * a_stage, aLo = aHi + (uint32_t)a.kboxes * a_box;
+      for (int p = 0; p < a.n_passes; ++p, ++unit) {
+        const int buf = unit & 1;
+        if (unit >= 2) mbar_wait(bar_ce + 8 * buf, (uint32_t)(((unit >> 1) - 1) & 1));
+        tc_fence_after();
+        const uint32_t d = tmem_base + (uint32_t)buf * 256u;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint32_t koff = (uint32_t)(ks >> 1) * a_box + (uint32_t)(ks & 1) * 32u;
+          const uint64_t bd = lh_desc(sW + (uint32_t)(((ks >> 1) * a.n_passes + p) * 2) * w_box + (uint32_t)(ks & 1) * 32u);
+          lh_mma_w(d, lh_desc(aHi + koff), bd, idesc2, ks ? 1u : 0u);     // A_hi x [W_hi ; W_lo]
+          lh_mma_w(d, lh_desc(aLo + koff), bd, idesc1, 1u);               // A_lo x W_hi
+        }
+        tc_commit_w(bar_cf + 8 * buf);
+      }
+      tc_commit_w(bar_ae + 8 * st);        // the A tile is free once every pass has read it
+    }
+  } else {
+    // ===== epilogue: thread = row of the tile =====
+    const int qtr = warp & 3;
+    const int row = qtr * 32 + lane;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(qtr * 32) << 16);
+    const int H = a.nh * a.hd;
+    int unit = 0;
+    for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x) {
+      const long long r = (long long)mt * LH_BM + row;
+      const bool valid = r < a.R;
+      int b = 0, l = 0;
+      if (a.mode == 3 && valid) { b = (int)(r / a.L); l = (int)(r - (long long)b * a.L); }
+      for (int p = 0; p < a.n_passes; ++p, ++unit) {
+        const int buf = unit & 1;
+        const int n0 = p * a.np;
+        mbar_wait(bar_cf + 8 * buf, (uint32_t)((unit >> 1) & 1));
+        __syncwarp();
+        tc_fence_after();
+        const uint32_t tb = t_lane + (uint32_t)buf * 256u;
+        for (int c0 = 0; c0 < a.np; c0 += 16) {
+          uint32_t v[16], w[16];
+          float4 rs[4];
+          if (a.mode == 0 && a.residual != nullptr && valid) {          // issue the residual loads ahead of the TMEM reads
+            const float4* rp = reinterpret_cast<const float4*>(a.residual + r * a.ldr + n0 + c0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) rs[j] = __ldg(rp + j);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) rs[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          tmem_ld16(tb + c0, v);
+          tmem_ld16(tb + a.np + c0, w);
+          tmem_wait_ld();
+          if (c0 + 16 >= a.np) {            // last TMEM read of this unit: hand the accumulator buffer back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_ce + 8 * buf) : "memory");
+          }
+          if (!valid) continue;
+          float x[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float t = __uint_as_float(v[j]) + __uint_as_float(w[j]) + bias_s[n0 + c0 + j];
+            if (a.relu) t = fmaxf(t, 0.f);
+            x[j] = t;
+          }
+          if (a.mode == 0) {
+            float4* yp = reinterpret_cast<float4*>(a.y + r * a.ldy + n0 + c0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              yp[j] = make_float4(x[4 * j] + rs[j].x, x[4 * j + 1] + rs[j].y, x[4 * j + 2] + rs[j].z, x[4 * j + 3] + rs[j].w);
+          } else if (a.mode == 1) {
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float t0 = fminf(x[2 * j], 65000.f), t1 = fminf(x[2 * j + 1], 65000.f);    // ReLU output: only the upper bound matters
+              const __half2 h = __floats2half2_rn(fmaxf(t0, -65000.f), fmaxf(t1, -65000.f));
+              const float2 hf = __half22float2(h);
+              const __half2 lw = __floats2half2_rn(t0 - hf.x, t1 - hf.y);
+              hi[j] = *reinterpret_cast<const uint32_t*>(&h);
+              lo[j] = *reinterpret_cast<const uint32_t*>(&lw);
+            }
+            uint4* hp = reinterpret_cast<uint4*>(a.y_planes + r * a.N + n0 + c0);
+            uint4* lp = reinterpret_cast<uint4*>(a.y_planes + ((long long)a.R + r) * a.N + n0 + c0);
+            hp[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]); hp[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+            lp[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]); lp[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int n = n0 + c0 + j;
+              const int which = n / H, rem = n - which * H;
+              const int head = rem / a.hd, dd = rem - head * a.hd;
+              float t = (which == 0) ? x[j] * a.qscale : x[j];
+              t = fminf(fmaxf(t, -65000.f), 65000.f);
+              const __half h = __float2half_rn(t);
+              __half* hp = a.qkvh + (long long)(2 * which) * a.plane_stride + (((long long)b * a.nh + head) * a.hd + dd) * a.Lp + l;
+              hp[0] = h;
+              hp[a.plane_stride] = __float2half_rn(t - __half2float(h));
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// LayerNorm over the last dim (optional) + fp16 hi/lo split: x [R,K] fp32 -> planes [2][R][K] fp16. One warp per row.
+__global__ void ln_split_h_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bvec,
+                                  __half* __restrict__ planes, long long R, int K, float eps) {
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= R) return;
+  const float* xr = x + row * K;
+  // K <= 256: up to 8 values per lane, read once (float2 pairs so the fp16 pairs below are 4-byte stores)
+  float2 v[4];
+  int cnt = 0;
+  float s = 0.f;
+  for (int k = 2 * lane; k < K; k += 64, ++cnt) { v[cnt] = *reinterpret_cast<const float2*>(xr + k); s += v[cnt].x + v[cnt].y; }
+  float mean = 0.f, rstd = 1.f;
+  if (w != nullptr) {
+    mean = warp_sum(s) / (float)K;
+    float q = 0.f;
+    for (int i = 0; i < cnt; ++i) { const float d0 = v[i].x - mean, d1 = v[i].y - mean; q += d0 * d0 + d1 * d1; }
+    rstd = 1.0f / sqrtf(warp_sum(q) / (float)K + eps);
+  }
+  __half* hp = planes + row * K;
+  __half* lp = planes + (R + row) * K;
+  int i = 0;
+  for (int k = 2 * lane; k < K; k += 64, ++i) {
+    float a0 = v[i].x, a1 = v[i].y;
+    if (w != nullptr) {
+      a0 = (a0 - mean) * rstd * __ldg(w + k) + __ldg(bvec + k);
+      a1 = (a1 - mean) * rstd * __ldg(w + k + 1) + __ldg(bvec + k + 1);
+    }
+    a0 = fminf(fmaxf(a0, -65000.f), 65000.f); a1 = fminf(fmaxf(a1, -65000.f), 65000.f);
+    const __half2 h = __floats2half2_rn(a0, a1);
+    const float2 hf = __half22float2(h);
+    *reinterpret_cast<__half2*>(hp + k) = h;
+    *reinterpret_cast<__half2*>(lp + k) = __floats2half2_rn(a0 - hf.x, a1 - hf.y);
+  }
+}
+
+// W [N,K] fp32 -> fp16 planes [2][N][K]; several matrices per launch (blockIdx.y = job)
+struct WSplitHJobs { const float* src[4]; __half* dst[4]; long long n[4]; };
+__global__ void w_split_h_kernel(WSplitHJobs jobs) {
+  const float* s = jobs.src[blockIdx.y];
+  __half* d = jobs.dst[blockIdx.y];
+  const long long n = jobs.n[blockIdx.y];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = fminf(fmaxf(s[i], -65000.f), 65000.f);
+    const __half h = __float2half_rn(v);
+    d[i] = h;
+    d[n + i] = __float2half_rn(v - __half2float(h));
+  }
+}
+
+// ---- host ----------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn5)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn5 lh_encode_fn() {
+  static EncodeTiledFn5 fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn5)p;
+  }
+  return fn;
+}
+
+static int lh_passes(int N) { return (N + 127) / 128; }
+bool linear_h_eligible(int K, int N) {
+  if (K % 32 != 0 || K > 256 || N % 16 != 0 || N > 512) return false;
+  const int p = lh_passes(N);
+  if (N % p != 0 || (N / p) % 16 != 0) return false;
+  const int kboxes = K / 32;
+  const size_t w = (size_t)kboxes * 2 * N * 64, a1 = (size_t)2 * kboxes * LH_BM * 64;
+  return w + a1 + (size_t)N * 4 + 2048 <= 225 * 1024;
+}
+
+int launch_ln_split_h(const float* x, const float* w, const float* b, void* planes, long long R, int K, float eps, cudaStream_t s) {
+  M2_REQUIRE(K % 2 == 0 && K <= 256 && (((uintptr_t)x) & 7) == 0, M2TTS_E_UNSUPPORTED, "ln_split_h: K=%d", K);
+  const int wpb = 8;
+  M2_LAUNCH(M2TTS_STAGE_LAYERNORM, ln_split_h_kernel, (unsigned)((R + wpb - 1) / wpb), wpb * 32, 0, s, x, w, b, (__half*)planes, R, K, eps);
+  return M2TTS_OK;
+}
+
+int launch_w_split_h(const float* const* src, void* const* dst, const long long* n, int jobs, cudaStream_t s) {
+  M2_REQUIRE(jobs >= 1 && jobs <= 4, M2TTS_E_BADSHAPE, "w_split_h: 1..4 jobs");
+  WSplitHJobs j{};
+  long long mx = 1;
+  for (int i = 0; i < jobs; ++i) { j.src[i] = src[i]; j.dst[i] = (__half*)dst[i]; j.n[i] = n[i]; if (n[i] > mx) mx = n[i]; }
+  dim3 grid((unsigned)((mx + 255) / 256 > 256 ? 256 : (mx + 255) / 256), jobs);
+  M2_LAUNCH(M2TTS_STAGE_PACK, w_split_h_kernel, grid, 256, 0, s, j);
+  return M2TTS_OK;
+}
+
+// a_planes: fp16 [2][R][K]; w_planes: fp16 [2][N][K]
+int launch_linear_h(const void* a_planes, const void* w_planes, const LinHParams& q, int stage, cudaStream_t s) {
+  M2_REQUIRE(linear_h_eligible(q.K, q.N), M2TTS_E_UNSUPPORTED, "linear_h: K=%d N=%d not eligible", q.K, q.N);
+  M2_REQUIRE((((uintptr_t)a_planes) & 15) == 0 && (((uintptr_t)w_planes) & 15) == 0 && (q.K & 7) == 0, M2TTS_E_BADSHAPE,
+             "linear_h: misaligned operands");
+  EncodeTiledFn5 enc = lh_encode_fn();
+  M2_REQUIRE(enc != nullptr, M2TTS_E_CUDA, "linear_h: cuTensorMapEncodeTiled unavailable");
+  LinHArgs a{};
+  a.R = q.R; a.K = q.K; a.N = q.N;
+  a.n_passes = lh_passes(q.N); a.np = q.N / a.n_passes; a.kboxes = q.K / 32;
+  a.bias = q.bias; a.relu = q.relu; a.residual = q.residual; a.ldr = q.ldr; a.y = q.y; a.ldy = q.ldy;
+  a.y_planes = (__half*)q.y_planes; a.qkvh = (__half*)q.qkvh; a.plane_stride = q.plane_stride;
+  a.L = q.L; a.nh = q.nh; a.hd = q.hd; a.Lp = q.Lp; a.qscale = q.qscale; a.mode = q.mode;
+  const size_t a_stage = (size_t)2 * a.kboxes * LH_BM * 64, w_bytes = (size_t)a.kboxes * 2 * a.N * 64;
+  const size_t fixed = w_bytes + (size_t)a.N * 4 + 16 + 256 + 1024;
+  int st = (int)((225 * 1024 - fixed) / a_stage);
+  a.a_stages = st > 4 ? 4 : st;
+  M2_REQUIRE(a.a_stages >= 1, M2TTS_E_UNSUPPORTED, "linear_h: operands do not fit shared memory");
+  const size_t smem = fixed + (size_t)a.a_stages * a_stage;
+  CUtensorMap ta, tw;
+  const cuuint32_t estr[2] = {1, 1};
+  {
+    const cuuint64_t dims[2] = {(cuuint64_t)a.K, (cuuint64_t)2 * a.R};
+    const cuuint64_t strides[1] = {(cuuint64_t)a.K * 2};
+    const cuuint32_t box[2] = {32u, (cuuint32_t)LH_BM};
+    const CUresult r = enc(&ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(a_planes), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    M2_REQUIRE(r == CUDA_SUCCESS, M2TTS_E_CUDA, "linear_h: tensor map (A) failed (%d)", (int)r);
+  }
+  {
+    const cuuint64_t dims[2] = {(cuuint64_t)a.K, (cuuint64_t)2 * a.N};
+    const cuuint64_t strides[1] = {(cuuint64_t)a.K * 2};
+    const cuuint32_t box[2] = {32u, (cuuint32_t)a.np};
+    const CUresult r = enc(&tw, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(w_planes), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    M2_REQUIRE(r == CUDA_SUCCESS, M2TTS_E_CUDA, "linear_h: tensor map (W) failed (%d)", (int)r);
+  }
+  M2_CUDA_OK(allow_smem(lin_h_kernel, smem));
+  const int m_tiles = ceil_div(a.R, LH_BM);
+  const int grid = m_tiles < kNumSMs ? m_tiles : kNumSMs;
+  M2_LAUNCH(stage, lin_h_kernel, grid, LH_THREADS, smem, s, ta, tw, a);
+  return M2TTS_OK;
+}
+
+}  // namespace m2

@@ -129,6 +129,41 @@ lingemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const bool valid = l < a.L;
   const long long row = (long long)row0 + tid;
   const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+  if (a.mode == 3) {
+    // Attention operand planes as fp16 hi/lo (attention_h.cu), positions contiguous: the accumulator tile is
+    // transposed through shared memory (the operand buffers are dead once the accumulator is complete) so that
+    // every global store is 16 bytes of 8 consecutive positions instead of 2-byte scalars.
+    __half* stg = reinterpret_cast<__half*>(smem_raw + (sbase - lg_smem_u32(smem_raw)));     // [plane][n_tile][128]
+    const int H = a.nh * a.hd, nt = a.n_tile;
+    for (int c0 = 0; c0 < nt; c0 += 16) {
+      uint32_t v[16];
+      lg_ld16(t_lane + c0, v);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int n = n0 + c0 + j;
+        float t = __uint_as_float(v[j]);
+        if (a.bias != nullptr) t += __ldg(a.bias + n);
+        if (n < H) t *= a.qscale;                                  // Q rows carry scale * log2(e)
+        t = valid ? fminf(fmaxf(t, -65000.f), 65000.f) : 0.f;      // saturate to the fp16 range
+        const __half h = __float2half_rn(t);
+        stg[(c0 + j) * LG_BM + tid] = h;
+        stg[(nt + c0 + j) * LG_BM + tid] = __float2half_rn(t - __half2float(h));
+      }
+    }
+    __syncthreads();
+    __half* base = reinterpret_cast<__half*>(a.qkv6);
+    for (int idx = tid; idx < 2 * nt * 16; idx += LG_THREADS) {
+      const int chunk = idx & 15, nl = (idx >> 4) % nt, pl = idx / (16 * nt);
+      const int lpos = l0 + chunk * 8;
+      if (lpos >= a.Lp) continue;
+      const int n = n0 + nl;
+      const int which = n / H, rem = n - which * H;
+      const int head = rem / a.hd, d = rem - head * a.hd;
+      const uint4 val = *reinterpret_cast<const uint4*>(stg + (pl * nt + nl) * LG_BM + chunk * 8);
+      *reinterpret_cast<uint4*>(base + (long long)(2 * which + pl) * a.plane_stride + (((long long)b * a.nh + head) * a.hd + d) * a.Lp + lpos) = val;
+    }
+  } else
   for (int c0 = 0; c0 < a.n_tile; c0 += 16) {
     uint32_t v[16];
     __syncwarp();   // rows past the end skip the stores below; reconverge before the .sync.aligned load
@@ -163,21 +198,6 @@ lingemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         for (int e = 0; e < 4; ++e) { h[e] = lg_hi(x[4 * j + e]); lo[e] = lg_hi(x[4 * j + e] - h[e]); }
         hp[j] = make_float4(h[0], h[1], h[2], h[3]);
         lp[j] = make_float4(lo[0], lo[1], lo[2], lo[3]);
-      }
-    } else if (a.mode == 3) {      // attention operand planes as fp16 hi/lo (attention_h.cu), saturated to the fp16 range
-      const int H = a.nh * a.hd;
-      __half* base = reinterpret_cast<__half*>(a.qkv6);
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int n = n0 + c0 + j;
-        const int which = n / H, rem = n - which * H;
-        const int head = rem / a.hd, d = rem - head * a.hd;
-        float t = (which == 0) ? x[j] * a.qscale : x[j];
-        t = fminf(fmaxf(t, -65000.f), 65000.f);
-        const __half h = __float2half_rn(t);
-        __half* hp = base + (long long)(2 * which) * a.plane_stride + (((long long)b * a.nh + head) * a.hd + d) * a.Lp + l;
-        hp[0] = h;
-        hp[a.plane_stride] = __float2half_rn(t - __half2float(h));
       }
     } else {
       const int H = a.nh * a.hd;

@@ -74,6 +74,41 @@ extern "C" int m2tts_transformer_layer(const m2tts_layer_weights* w, const float
   int rc;
 
   const int R = B * L;
+  // ---- 16-bit split path (default): every GEMM of the layer on tcgen05 with fp16 hi/lo operand planes, persistent
+  //      weight-resident linear kernels (lin_h.cu) and the warp-specialised attention (attention_h.cu) ----
+  if (attention_mode() == 0 && attention_tc_supported(hd) && linear_h_eligible(H, 3 * H) && linear_h_eligible(H, H) &&
+      linear_h_eligible(H, F) && linear_h_eligible(F, H) && (hd % 8 == 0)) {
+    const float* srcs[4] = {w->qkv_w, w->out_w, w->ffn1_w, w->ffn2_w};
+    void* wpl[4] = {ws.w_planes[0], ws.w_planes[1], ws.w_planes[2], ws.w_planes[3]};
+    const long long ns[4] = {(long long)3 * H * H, (long long)H * H, (long long)F * H, (long long)H * F};
+    if ((rc = launch_w_split_h(srcs, wpl, ns, 4, s))) return rc;
+    if ((rc = launch_ln_split_h(x_in, w->norm1_w, w->norm1_b, ws.xn, R, H, ln_eps, s))) return rc;
+    const int Lp = (L + 7) & ~7;
+    {  // attention operand planes = split(LN1(x) Wqkv^T)
+      LinHParams q{};
+      q.R = R; q.K = H; q.N = 3 * H; q.mode = 3; q.qkvh = ws.q; q.plane_stride = (long long)B * H * Lp;
+      q.L = L; q.nh = num_heads; q.hd = hd; q.Lp = Lp; q.qscale = (float)((1.0 / sqrt((double)hd)) * 1.4426950408889634);
+      if ((rc = launch_linear_h(ws.xn, wpl[0], q, M2TTS_STAGE_LN_QKV, s))) return rc;
+    }
+    if ((rc = launch_attention_h(ws.q, nullptr, lengths, B, L, Lp, num_heads, hd, s, nullptr, ws.ctx))) return rc;
+    {  // x1 = x + ctx Wo^T + bo
+      LinHParams q{};
+      q.R = R; q.K = H; q.N = H; q.mode = 0; q.bias = w->out_b; q.residual = x_in; q.ldr = H; q.y = ws.x1; q.ldy = H;
+      if ((rc = launch_linear_h(ws.ctx, wpl[1], q, M2TTS_STAGE_OUTPROJ, s))) return rc;
+    }
+    if ((rc = launch_ln_split_h(ws.x1, w->norm2_w, w->norm2_b, ws.xn, R, H, ln_eps, s))) return rc;
+    {  // hid = relu(LN2(x1) W1^T + b1) as planes
+      LinHParams q{};
+      q.R = R; q.K = H; q.N = F; q.mode = 1; q.bias = w->ffn1_b; q.relu = 1; q.y_planes = ws.hid;
+      if ((rc = launch_linear_h(ws.xn, wpl[2], q, M2TTS_STAGE_FFN1, s))) return rc;
+    }
+    {  // y = x1 + hid W2^T + b2
+      LinHParams q{};
+      q.R = R; q.K = F; q.N = H; q.mode = 0; q.bias = w->ffn2_b; q.residual = ws.x1; q.ldr = H; q.y = x_out; q.ldy = H;
+      if ((rc = launch_linear_h(ws.hid, wpl[3], q, M2TTS_STAGE_FFN2, s))) return rc;
+    }
+    return M2TTS_OK;
+  }
   // ---- tensor-core path: every GEMM of the layer on tcgen05 (3xTF32), operands as hi/lo planes ----
   if (attention_mode() != 1 && attention_tc_supported(hd) && linear_tc_eligible(H, 3 * H) && linear_tc_eligible(H, H) &&
       linear_tc_eligible(H, F) && linear_tc_eligible(F, H) && (H % 16 == 0)) {
@@ -178,6 +213,16 @@ extern "C" int m2tts_layernorm_proj(const float* x, const float* ln_w, const flo
   int rc;
   {  // tensor-core path when the caller's workspace also has room for the normalised rows as hi/lo planes
     float* xn = cv.take<float>((size_t)2 * rows * H);
+    if (attention_mode() == 0 && cv.ok() && linear_h_eligible(H, N)) {   // 16-bit split (default)
+      const float* srcs[1] = {W};
+      void* dsts[1] = {wt};
+      const long long ns[1] = {(long long)N * H};
+      if ((rc = launch_w_split_h(srcs, dsts, ns, 1, s))) return rc;
+      if ((rc = launch_ln_split_h(x, ln_w, ln_b, xn, rows, H, eps, s))) return rc;
+      LinHParams q{};
+      q.R = rows; q.K = H; q.N = N; q.mode = 0; q.bias = bias; q.y = y; q.ldy = N;
+      return launch_linear_h(xn, wt, q, M2TTS_STAGE_LN_PROJ, s);
+    }
     if (attention_mode() != 1 && cv.ok() && linear_tc_eligible(H, N) && (N % 16 == 0) && (H % 4 == 0)) {
       const float* srcs[1] = {W};
       float* dsts[1] = {wt};
