@@ -198,17 +198,19 @@ lin_h_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
             hp[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]); hp[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
             lp[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]); lp[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
           } else {
+            // head_dim is a multiple of 16, so the 16 columns of a chunk belong to ONE (q|k|v, head): the index
+            // arithmetic (two integer divisions) is done once per chunk, not per column
+            const int n = n0 + c0;
+            const int which = n / H, rem = n - which * H;
+            const int head = rem / a.hd, d0 = rem - head * a.hd;
+            const float sc = (which == 0) ? a.qscale : 1.0f;
+            __half* hp = a.qkvh + (long long)(2 * which) * a.plane_stride + (((long long)b * a.nh + head) * a.hd + d0) * a.Lp + l;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              const int n = n0 + c0 + j;
-              const int which = n / H, rem = n - which * H;
-              const int head = rem / a.hd, dd = rem - head * a.hd;
-              float t = (which == 0) ? x[j] * a.qscale : x[j];
-              t = fminf(fmaxf(t, -65000.f), 65000.f);
+              const float t = fminf(fmaxf(x[j] * sc, -65000.f), 65000.f);
               const __half h = __float2half_rn(t);
-              __half* hp = a.qkvh + (long long)(2 * which) * a.plane_stride + (((long long)b * a.nh + head) * a.hd + dd) * a.Lp + l;
-              hp[0] = h;
-              hp[a.plane_stride] = __float2half_rn(t - __half2float(h));
+              hp[(long long)j * a.Lp] = h;
+              hp[(long long)j * a.Lp + a.plane_stride] = __float2half_rn(t - __half2float(h));
             }
           }
         }
@@ -223,39 +225,61 @@ lin_h_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
   }
 }
 
-// LayerNorm over the last dim (optional) + fp16 hi/lo split: x [R,K] fp32 -> planes [2][R][K] fp16. One warp per row.
-__global__ void ln_split_h_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bvec,
-                                  __half* __restrict__ planes, long long R, int K, float eps) {
-  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (row >= R) return;
-  const float* xr = x + row * K;
-  // K <= 256: up to 8 values per lane, read once (float2 pairs so the fp16 pairs below are 4-byte stores)
-  float2 v[4];
-  int cnt = 0;
-  float s = 0.f;
-  for (int k = 2 * lane; k < K; k += 64, ++cnt) { v[cnt] = *reinterpret_cast<const float2*>(xr + k); s += v[cnt].x + v[cnt].y; }
-  float mean = 0.f, rstd = 1.f;
-  if (w != nullptr) {
-    mean = warp_sum(s) / (float)K;
-    float q = 0.f;
-    for (int i = 0; i < cnt; ++i) { const float d0 = v[i].x - mean, d1 = v[i].y - mean; q += d0 * d0 + d1 * d1; }
-    rstd = 1.0f / sqrtf(warp_sum(q) / (float)K + eps);
-  }
-  __half* hp = planes + row * K;
-  __half* lp = planes + (R + row) * K;
-  int i = 0;
-  for (int k = 2 * lane; k < K; k += 64, ++i) {
-    float a0 = v[i].x, a1 = v[i].y;
+// LayerNorm over the last dim (optional) + fp16 hi/lo split: x [R,K] fp32 -> planes [2][R][K] fp16.
+// 8 lanes per row (float4 each, up to 8 per lane: K <= 256), 4 rows per warp pass, grid-stride over row groups.
+__global__ void __launch_bounds__(256) ln_split_h_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                         const float* __restrict__ bvec, __half* __restrict__ planes,
+                                                         long long R, int K, float eps) {
+  const int lane = threadIdx.x & 31, sub = lane & 7;
+  const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int n4 = K >> 5;                       // float4 per lane (K % 32 == 0)
+  for (long long row = warp_id * 4 + (lane >> 3); row < ((R + 3) & ~3LL); row += warps * 4) {
+    const bool valid = row < R;
+    const float* xr = x + (valid ? row : 0) * K;
+    float4 v[8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i < n4) { v[i] = __ldg(reinterpret_cast<const float4*>(xr + 32 * i + 4 * sub)); s += (v[i].x + v[i].y) + (v[i].z + v[i].w); }
+    float mean = 0.f, rstd = 1.f;
     if (w != nullptr) {
-      a0 = (a0 - mean) * rstd * __ldg(w + k) + __ldg(bvec + k);
-      a1 = (a1 - mean) * rstd * __ldg(w + k + 1) + __ldg(bvec + k + 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 1); s += __shfl_xor_sync(0xffffffffu, s, 2); s += __shfl_xor_sync(0xffffffffu, s, 4);
+      mean = s / (float)K;
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (i < n4) {
+          const float d0 = v[i].x - mean, d1 = v[i].y - mean, d2 = v[i].z - mean, d3 = v[i].w - mean;
+          q += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+        }
+      q += __shfl_xor_sync(0xffffffffu, q, 1); q += __shfl_xor_sync(0xffffffffu, q, 2); q += __shfl_xor_sync(0xffffffffu, q, 4);
+      rstd = 1.0f / sqrtf(q / (float)K + eps);
     }
-    a0 = fminf(fmaxf(a0, -65000.f), 65000.f); a1 = fminf(fmaxf(a1, -65000.f), 65000.f);
-    const __half2 h = __floats2half2_rn(a0, a1);
-    const float2 hf = __half22float2(h);
-    *reinterpret_cast<__half2*>(hp + k) = h;
-    *reinterpret_cast<__half2*>(lp + k) = __floats2half2_rn(a0 - hf.x, a1 - hf.y);
+    if (!valid) continue;
+    __half* hp = planes + row * K;
+    __half* lp = planes + (R + row) * K;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i < n4) {
+        const int k = 32 * i + 4 * sub;
+        float a[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+        if (w != nullptr) {
+          const float4 ww = __ldg(reinterpret_cast<const float4*>(w + k)), bb = __ldg(reinterpret_cast<const float4*>(bvec + k));
+          a[0] = (a[0] - mean) * rstd * ww.x + bb.x; a[1] = (a[1] - mean) * rstd * ww.y + bb.y;
+          a[2] = (a[2] - mean) * rstd * ww.z + bb.z; a[3] = (a[3] - mean) * rstd * ww.w + bb.w;
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) a[e] = fminf(fmaxf(a[e], -65000.f), 65000.f);
+        const __half2 h0 = __floats2half2_rn(a[0], a[1]), h1 = __floats2half2_rn(a[2], a[3]);
+        const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+        const __half2 l0 = __floats2half2_rn(a[0] - f0.x, a[1] - f0.y), l1 = __floats2half2_rn(a[2] - f1.x, a[3] - f1.y);
+        uint2 hv, lv;
+        hv.x = *reinterpret_cast<const uint32_t*>(&h0); hv.y = *reinterpret_cast<const uint32_t*>(&h1);
+        lv.x = *reinterpret_cast<const uint32_t*>(&l0); lv.y = *reinterpret_cast<const uint32_t*>(&l1);
+        *reinterpret_cast<uint2*>(hp + k) = hv;
+        *reinterpret_cast<uint2*>(lp + k) = lv;
+      }
   }
 }
 
@@ -300,9 +324,10 @@ bool linear_h_eligible(int K, int N) {
 }
 
 int launch_ln_split_h(const float* x, const float* w, const float* b, void* planes, long long R, int K, float eps, cudaStream_t s) {
-  M2_REQUIRE(K % 2 == 0 && K <= 256 && (((uintptr_t)x) & 7) == 0, M2TTS_E_UNSUPPORTED, "ln_split_h: K=%d", K);
-  const int wpb = 8;
-  M2_LAUNCH(M2TTS_STAGE_LAYERNORM, ln_split_h_kernel, (unsigned)((R + wpb - 1) / wpb), wpb * 32, 0, s, x, w, b, (__half*)planes, R, K, eps);
+  M2_REQUIRE(K % 32 == 0 && K <= 256 && (((uintptr_t)x) & 15) == 0, M2TTS_E_UNSUPPORTED, "ln_split_h: K=%d", K);
+  long long blocks = (R + 31) / 32;            // 8 warps x 4 rows per block pass
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  M2_LAUNCH(M2TTS_STAGE_LAYERNORM, ln_split_h_kernel, (unsigned)blocks, 256, 0, s, x, w, b, (__half*)planes, R, K, eps);
   return M2TTS_OK;
 }
 

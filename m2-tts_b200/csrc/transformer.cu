@@ -77,7 +77,7 @@ extern "C" int m2tts_transformer_layer(const m2tts_layer_weights* w, const float
   // ---- 16-bit split path (default): every GEMM of the layer on tcgen05 with fp16 hi/lo operand planes, persistent
   //      weight-resident linear kernels (lin_h.cu) and the warp-specialised attention (attention_h.cu) ----
   if (attention_mode() == 0 && attention_tc_supported(hd) && linear_h_eligible(H, 3 * H) && linear_h_eligible(H, H) &&
-      linear_h_eligible(H, F) && linear_h_eligible(F, H) && (hd % 8 == 0)) {
+      linear_h_eligible(H, F) && linear_h_eligible(F, H) && (hd % 16 == 0)) {
     const float* srcs[4] = {w->qkv_w, w->out_w, w->ffn1_w, w->ffn2_w};
     void* wpl[4] = {ws.w_planes[0], ws.w_planes[1], ws.w_planes[2], ws.w_planes[3]};
     const long long ns[4] = {(long long)3 * H * H, (long long)H * H, (long long)F * H, (long long)H * F};
