@@ -12,7 +12,7 @@ constexpr int CT_STEP = CT_BM - 2 * CT_HALO;   // 120 output positions per tile;
 constexpr int CT_CK = 16;             // input channels per pipeline chunk
 constexpr uint32_t CT_ABOX = CT_CK * 128;      // one TMA box: 16 channel rows x 32 positions x 4 B
 constexpr uint32_t CT_RAW_STAGE = 4u * CT_ABOX;    // 128 positions of fp32 as delivered by TMA = 8 KB
-constexpr uint32_t CT_A_STAGE = 2u * CT_RAW_STAGE; // the same tile split into TF32 hi and lo = 16 KB
+constexpr uint32_t CT_A_STAGE = CT_RAW_STAGE;      // the lo tile (x - trunc_tf32(x)); the raw tile itself is the hi operand
 
 struct TapGemmArgs {
   int CI, L_in, B, n_chunks;
@@ -31,6 +31,7 @@ struct TapGemmArgs {
   int out_cl;
   int n_tiles, m_tiles, w_resident;
   int raw_stages, split_stages;
+  long long* prof;           // optional bring-up timestamps (CTA 0, epilogue group 0)
 };
 
 // ---- PTX helpers -------------------------------------------------------------------------------------

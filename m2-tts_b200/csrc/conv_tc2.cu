@@ -3,9 +3,10 @@
 //   * one CTA per SM loops over (utterance, 120-position) tiles of ONE output-channel tile, so the packed
 //     weight images stay RESIDENT in shared memory whenever they fit (every layer but the widest ones);
 //   * activations stay PLAIN fp32 in HBM. warp 0 streams them with TMA (box = 32 positions x 16 channels,
-//     128B swizzle / 32B atoms) into a raw ring; warps 2-3 split every raw tile into TF32 hi and lo tiles
-//     (same swizzled addresses, so the split is a flat element-wise pass) and hand them to the tensor pipe
-//     through fence.proxy.async + mbarrier; warp 1 issues the UMMAs (3 taps x {hi*hi, hi*lo, lo*hi} x 2 k-steps
+//     128B swizzle / 32B atoms) into a raw ring. kind::tf32 UMMAs TRUNCATE fp32 operands (they ignore the low 13
+//     mantissa bits; measured: tools/tf32_trunc_probe.py), so the raw tile IS the hi operand; warps 2-3 only
+//     compute the lo tile x - trunc(x) (same swizzled addresses: a flat element-wise pass) and hand it to the
+//     tensor pipe through fence.proxy.async + mbarrier; a raw stage is released by the UMMAs that read it; warp 1 issues the UMMAs (3 taps x {hi*hi, hi*lo, lo*hi} x 2 k-steps
 //     per 16-channel chunk) into one of up to four TMEM accumulator buffers;
 //   * warps 4-7 / 8-11 are two epilogue groups taking alternate tiles: TMEM -> staging tile in shared memory
 //     -> out[t] = sum_tap D_tap[t + shift_tap] + bias (LeakyReLU, + residual) -> plain fp32 in HBM.
@@ -52,7 +53,7 @@ tapgemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const TapG
   const int total_mt = a.B * a.m_tiles;
 
   if (tid == 0) {
-    for (int s = 0; s < R; ++s) { ct_mbar_init(bar_rawf + 8 * s, 1); ct_mbar_init(bar_rawe + 8 * s, P_SPLIT_WARPS); }
+    for (int s = 0; s < R; ++s) { ct_mbar_init(bar_rawf + 8 * s, 1); ct_mbar_init(bar_rawe + 8 * s, 1); }
     for (int s = 0; s < S; ++s) {
       ct_mbar_init(bar_splf + 8 * s, P_SPLIT_WARPS); ct_mbar_init(bar_sple + 8 * s, 1); ct_mbar_init(bar_wf + 8 * s, 1);
     }
@@ -118,7 +119,8 @@ tapgemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const TapG
       const uint32_t wplane16 = w_plane_bytes >> 4;
       const uint32_t n_chunks = (uint32_t)a.n_chunks;
       const bool resident = a.w_resident != 0;
-      uint32_t ss = 0, ss_par = 0;            // split-ring stage and its phase parity
+      uint32_t ss = 0, ss_par = 0;            // lo-ring stage and its phase parity
+      uint32_t rs = 0;                        // raw-ring stage (the hi operand)
       uint32_t buf = 0, buf_round = 0;        // accumulator buffer and how many times the ring of buffers wrapped
       for (int j = first; j < total_mt; j += cpg) {
         if (buf_round > 0) ct_wait(bar_acce + 8 * buf, (buf_round - 1) & 1u, dbg, 5, j);
@@ -128,22 +130,26 @@ tapgemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const TapG
           ct_wait(bar_splf + 8 * ss, ss_par, dbg, 2, (int)c);
           if (!resident) ct_wait(bar_wf + 8 * ss, ss_par, dbg, 7, (int)c);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t sA = sbase + L.split_ring + ss * L.split_stage_bytes;
-          const uint32_t sW = resident ? (sbase + L.w_region + c * L.w_stage) : (sA + CT_A_STAGE);
-          const uint64_t ad0 = a_tmpl | (uint64_t)((sA >> 4) & 0x3FFFu);
+          const uint32_t sLo = sbase + L.split_ring + ss * L.split_stage_bytes;
+          const uint32_t sHi = sbase + L.raw_ring + rs * CT_RAW_STAGE;
+          const uint32_t sW = resident ? (sbase + L.w_region + c * L.w_stage) : (sLo + CT_A_STAGE);
+          const uint64_t ahi0 = a_tmpl | (uint64_t)((sHi >> 4) & 0x3FFFu);
+          const uint64_t alo0 = a_tmpl | (uint64_t)((sLo >> 4) & 0x3FFFu);
           const uint64_t bd0 = w_tmpl | (uint64_t)((sW >> 4) & 0x3FFFu);
 #pragma unroll
           for (int term = 0; term < 3; ++term) {           // hi*hi, hi*lo, lo*hi
             const uint32_t ap = (term == 2) ? 1u : 0u, wp = (term == 1) ? 1u : 0u;
 #pragma unroll
             for (int ks = 0; ks < CT_CK / 8; ++ks) {
-              const uint64_t ad = ad0 + (uint64_t)((ap * CT_RAW_STAGE + ks * 1024u) >> 4);
+              const uint64_t ad = (ap ? alo0 : ahi0) + (uint64_t)((ks * 1024u) >> 4);
               const uint64_t bd = bd0 + (uint64_t)(wp * wplane16 + ks * 16u);
               ct_mma_w(dbase, ad, bd, idesc, (c | (uint32_t)term | (uint32_t)ks) ? 1u : 0u);
             }
           }
           ct_commit_w(bar_sple + 8 * ss);
+          ct_commit_w(bar_rawe + 8 * rs);           // the raw (= hi) stage is free once these UMMAs have read it
           if (++ss == (uint32_t)S) { ss = 0; ss_par ^= 1u; }
+          if (++rs == (uint32_t)R) rs = 0;
         }
         ct_commit_w(bar_accf + 8 * buf);
         if (++buf == (uint32_t)NB) { buf = 0; ++buf_round; }
@@ -155,25 +161,30 @@ tapgemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const TapG
     uint32_t rs = 0, rs_par = 0, ss = 0, ss_round = 0;
     for (int j = first; j < total_mt; j += cpg) {
       for (int c = 0; c < a.n_chunks; ++c) {
+        const bool prs = a.prof != nullptr && blockIdx.x == 0 && sw == 0 && lane == 0 && j == first + 8 * cpg && c < 8;
+        if (prs) a.prof[512 + c * 4 + 0] = clock64();
         ct_wait(bar_rawf + 8 * rs, rs_par, dbg, 8, c);
+        if (prs) a.prof[512 + c * 4 + 1] = clock64();
         if (ss_round > 0) ct_wait(bar_sple + 8 * ss, (ss_round - 1) & 1u, dbg, 9, c);
+        if (prs) a.prof[512 + c * 4 + 2] = clock64();
         __syncwarp();
         const float4* src = reinterpret_cast<const float4*>(gbase + L.raw_ring + rs * CT_RAW_STAGE);
-        float4* dhi = reinterpret_cast<float4*>(gbase + L.split_ring + ss * L.split_stage_bytes);
-        float4* dlo = dhi + CT_RAW_STAGE / 16;
-        // 512 float4 per tile, 256 per warp, 8 per lane
+        float4* dlo = reinterpret_cast<float4*>(gbase + L.split_ring + ss * L.split_stage_bytes);
+        // 512 float4 per tile, 256 per warp, 8 per lane: all eight loads first (the compiler cannot hoist them over the
+        // stores, both being shared memory), then the arithmetic and the stores
+        float4 v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = src[sw * 256 + k * 32 + lane];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          const int i = sw * 256 + k * 32 + lane;
-          const float4 v = src[i];
-          float4 h, l;
-          h.x = ct_hi(v.x); h.y = ct_hi(v.y); h.z = ct_hi(v.z); h.w = ct_hi(v.w);
-          l.x = ct_hi(v.x - h.x); l.y = ct_hi(v.y - h.y); l.z = ct_hi(v.z - h.z); l.w = ct_hi(v.w - h.w);
-          dhi[i] = h; dlo[i] = l;
+          float4 l;
+          l.x = v[k].x - ct_hi(v[k].x); l.y = v[k].y - ct_hi(v[k].y); l.z = v[k].z - ct_hi(v[k].z); l.w = v[k].w - ct_hi(v[k].w);
+          dlo[sw * 256 + k * 32 + lane] = l;
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor pipe
         __syncwarp();
-        if (lane == 0) { ct_arrive(bar_splf + 8 * ss); ct_arrive(bar_rawe + 8 * rs); }
+        if (lane == 0) ct_arrive(bar_splf + 8 * ss);
+        if (prs) a.prof[512 + c * 4 + 3] = clock64();
         if (++rs == (uint32_t)R) { rs = 0; rs_par ^= 1u; }
         if (++ss == (uint32_t)S) { ss = 0; ++ss_round; }
       }
@@ -193,7 +204,10 @@ tapgemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const TapG
       const int b = j / a.m_tiles, start = (j % a.m_tiles) * CT_STEP - CT_HALO;
       const int q = start + m;
       const bool own = (m >= CT_HALO) && (m < CT_BM - CT_HALO) && (q < a.L_in);
+      const bool pr = a.prof != nullptr && blockIdx.x == 0 && grp == 0 && m == 0 && t < 128;
+      if (pr) a.prof[t * 4 + 0] = clock64();
       ct_wait(bar_accf + 8 * buf, (uint32_t)((t / NB) & 1), dbg, 3, t);
+      if (pr) a.prof[t * 4 + 1] = clock64();
       __syncwarp();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
@@ -290,6 +304,7 @@ tapgemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const TapG
           p_epi_sync(grp);
         }
       }
+      if (pr) a.prof[t * 4 + 2] = clock64();
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -300,7 +315,9 @@ tapgemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const TapG
   }
 }
 
+static long long* g_tg_prof = nullptr;
 int launch_tapgemm_persistent(const CUtensorMap& tmap, TapGemmArgs& a, int stage, cudaStream_t s) {
+  a.prof = g_tg_prof;
   for (int j = 0; j < 3; ++j)
     M2_REQUIRE(a.tap_shift[j] >= -CT_HALO && a.tap_shift[j] <= CT_HALO, M2TTS_E_UNSUPPORTED,
                "conv_tc: tap shift %d exceeds the halo", a.tap_shift[j]);
@@ -314,21 +331,31 @@ int launch_tapgemm_persistent(const CUtensorMap& tmap, TapGemmArgs& a, int stage
   L.w_stage = 2u * (uint32_t)a.rows_total * 64u;
   L.staging_group = (a.r == 1 ? 48u : (uint32_t)(2 * a.r * 8)) * 128u * 4u;   // conv: 3 taps x 16 columns; convT: 2r x 8 channels
   const uint32_t staging = 2u * L.staging_group;
-  a.raw_stages = 3;
-  const uint32_t fixed = 1024u /*alignment*/ + 512u /*barriers*/ + staging + (uint32_t)a.raw_stages * CT_RAW_STAGE;
-  const uint32_t budget = 227u * 1024u - fixed;
+  // Ring depths. The raw ring is what is in flight from HBM (8 KB per stage): it takes every stage the budget allows
+  // (up to 8); the lo ring (consumed within a chunk's UMMAs) stays at two stages.
+  const uint32_t fixed0 = 1024u /*alignment*/ + 512u /*barriers*/ + staging;
+  const uint32_t budget0 = 227u * 1024u - fixed0;
   const uint32_t w_all = (uint32_t)a.n_chunks * L.w_stage;
-  if (w_all + 2u * CT_A_STAGE <= budget) {
+  const uint32_t w_al = (w_all + 1023u) & ~1023u;
+  if (w_al + 2u * CT_A_STAGE + 3u * CT_RAW_STAGE <= budget0) {
     a.w_resident = 1;
     L.split_stage_bytes = CT_A_STAGE;
-    int st = (int)((budget - w_all) / CT_A_STAGE);
-    a.split_stages = st > 4 ? 4 : st;
+    a.split_stages = 2;
+    int rs = (int)((budget0 - w_al - 2u * CT_A_STAGE) / CT_RAW_STAGE);
+    a.raw_stages = rs > 8 ? 8 : rs;
   } else {
     a.w_resident = 0;
     L.split_stage_bytes = CT_A_STAGE + ((L.w_stage + 1023u) & ~1023u);
-    int st = (int)(budget / L.split_stage_bytes);
-    M2_REQUIRE(st >= 2, M2TTS_E_UNSUPPORTED, "conv_tc: weight chunk of %u B does not fit a 2-stage ring", L.w_stage);
-    a.split_stages = st > 4 ? 4 : st;
+    M2_REQUIRE(2u * L.split_stage_bytes + 3u * CT_RAW_STAGE <= budget0, M2TTS_E_UNSUPPORTED,
+               "conv_tc: weight chunk of %u B does not fit a 2-stage ring", L.w_stage);
+    a.split_stages = 2;
+    int rs = (int)((budget0 - 2u * L.split_stage_bytes) / CT_RAW_STAGE);
+    a.raw_stages = rs > 8 ? 8 : rs;
+    // a third lo stage (the streamed weights travel with it) helps more than raw stages beyond 4
+    if (a.raw_stages >= 4 + (int)((L.split_stage_bytes + CT_RAW_STAGE - 1) / CT_RAW_STAGE)) {
+      a.split_stages = 3;
+      a.raw_stages -= (int)((L.split_stage_bytes + CT_RAW_STAGE - 1) / CT_RAW_STAGE);
+    }
   }
   L.raw_ring = 0;
   L.split_ring = (uint32_t)a.raw_stages * CT_RAW_STAGE;
@@ -348,3 +375,6 @@ int launch_tapgemm_persistent(const CUtensorMap& tmap, TapGemmArgs& a, int stage
 }
 
 }  // namespace m2
+
+// bring-up: device buffer of >= 576 int64 receiving epilogue / splitter timestamps of CTA 0 (NULL = off)
+extern "C" int m2tts_tapgemm_set_prof(long long* dev_buf) { m2::g_tg_prof = dev_buf; return M2TTS_OK; }
