@@ -212,7 +212,12 @@ tapgemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const TapG
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
       if (a.r == 1) {
-        const int s0 = a.tap_shift[0], s1 = a.tap_shift[1], s2 = a.tap_shift[2];
+        // Conv1d: out[m] = D0[m - d] + D1[m] + D2[m + d]. D1 stays in registers; D0 and D2 go through a row-major
+        // staging tile (one padded row of 32 floats per thread) with 128-bit shared-memory accesses: 16 vector
+        // instructions per 16 channels instead of 96 scalar ones (the epilogue was bound by shared-memory
+        // instruction issue, measured with tools/tapgemm_prof.py).
+        constexpr int SP = 36;                                  // staging row pitch in floats (conflict-free for 128-bit)
+        const int r0 = min(max(m + a.tap_shift[0], 0), CT_BM - 1), r2 = min(max(m + a.tap_shift[2], 0), CT_BM - 1);
         for (int c0 = 0; c0 < a.co_tile; c0 += 16) {
           // residual loads first: 16 independent read-only loads in flight while the tile is staged
           float rsd[16];
@@ -232,17 +237,29 @@ tapgemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const TapG
             __syncwarp();
             if (lane == 0) ct_arrive(bar_acce + 8 * buf);
           }
+          uint4* myrow = reinterpret_cast<uint4*>(stg + m * SP);
 #pragma unroll
-          for (int tap = 0; tap < 3; ++tap)
-#pragma unroll
-            for (int jj = 0; jj < 16; ++jj) stg[((tap * 16 + jj) << 7) + m] = __uint_as_float(v[tap][jj]);
+          for (int j4 = 0; j4 < 4; ++j4) {
+            myrow[j4] = make_uint4(v[0][4 * j4], v[0][4 * j4 + 1], v[0][4 * j4 + 2], v[0][4 * j4 + 3]);
+            myrow[4 + j4] = make_uint4(v[2][4 * j4], v[2][4 * j4 + 1], v[2][4 * j4 + 2], v[2][4 * j4 + 3]);
+          }
           p_epi_sync(grp);
           if (own) {
+            const float4* d0p = reinterpret_cast<const float4*>(stg + r0 * SP);
+            const float4* d2p = reinterpret_cast<const float4*>(stg + r2 * SP + 16);
+            const float4* bp = reinterpret_cast<const float4*>(a.bias + co0 + c0);
             float xo[16];
 #pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const float4 d0 = d0p[j4], d2 = d2p[j4], bb = __ldg(bp + j4);
+              xo[4 * j4 + 0] = d0.x + __uint_as_float(v[1][4 * j4 + 0]) + d2.x + bb.x;
+              xo[4 * j4 + 1] = d0.y + __uint_as_float(v[1][4 * j4 + 1]) + d2.y + bb.y;
+              xo[4 * j4 + 2] = d0.z + __uint_as_float(v[1][4 * j4 + 2]) + d2.z + bb.z;
+              xo[4 * j4 + 3] = d0.w + __uint_as_float(v[1][4 * j4 + 3]) + d2.w + bb.w;
+            }
+#pragma unroll
             for (int c = 0; c < 16; ++c) {
-              const int co = co0 + c0 + c;
-              float x = stg[((c) << 7) + m + s0] + stg[((16 + c) << 7) + m + s1] + stg[((32 + c) << 7) + m + s2] + __ldg(a.bias + co);
+              float x = xo[c];
               if (a.act == 1) x = x > 0.f ? x : 0.1f * x;
               xo[c] = x + rsd[c];
             }
