@@ -206,6 +206,15 @@ tapgemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const TapG
       const bool own = (m >= CT_HALO) && (m < CT_BM - CT_HALO) && (q < a.L_in);
       const bool pr = a.prof != nullptr && blockIdx.x == 0 && grp == 0 && m == 0 && t < 128;
       if (pr) a.prof[t * 4 + 0] = clock64();
+      if (a.residual != nullptr) {
+        // pull this warp's residual lines (one 128-B line per output channel) into L2 while the tile's UMMAs are
+        // still running: the loads below then cost an L2 hit instead of a DRAM round trip per 16-channel round
+        const int qw = start + qtr * 32;
+        if (qw < a.L_in) {
+          const float* rp = a.residual + ((size_t)b * a.CO + co0) * a.Lp_res + (qw < 0 ? 0 : qw);
+          for (int c = lane; c < a.co_tile; c += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + (size_t)c * a.Lp_res));
+        }
+      }
       ct_wait(bar_accf + 8 * buf, (uint32_t)((t / NB) & 1), dbg, 3, t);
       if (pr) a.prof[t * 4 + 1] = clock64();
       __syncwarp();
