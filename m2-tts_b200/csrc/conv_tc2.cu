@@ -55,7 +55,7 @@ tapgemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const TapG
   if (tid == 0) {
     for (int s = 0; s < R; ++s) { ct_mbar_init(bar_rawf + 8 * s, 1); ct_mbar_init(bar_rawe + 8 * s, 1); }
     for (int s = 0; s < S; ++s) {
-      ct_mbar_init(bar_splf + 8 * s, P_SPLIT_WARPS); ct_mbar_init(bar_sple + 8 * s, 1); ct_mbar_init(bar_wf + 8 * s, 1);
+      ct_mbar_init(bar_splf + 8 * s, 1); ct_mbar_init(bar_sple + 8 * s, 1); ct_mbar_init(bar_wf + 8 * s, 1);
     }
     for (int s = 0; s < NB; ++s) { ct_mbar_init(bar_accf + 8 * s, 1); ct_mbar_init(bar_acce + 8 * s, 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -157,34 +157,41 @@ tapgemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const TapG
     }
   } else if (warp < 2 + P_SPLIT_WARPS) {
     // ===== splitters: raw fp32 tile -> TF32 hi tile + lo tile (flat, the swizzle is address-preserving) =====
+    // The two splitter warps take ALTERNATE chunks (a whole 8 KB tile each), so the fixed cost of a hand-off (two
+    // barrier waits, the proxy fence, the arrive) of one warp overlaps the other warp's arithmetic.
     const int sw = warp - 2;
-    uint32_t rs = 0, rs_par = 0, ss = 0, ss_round = 0;
+    uint32_t rs = 0, rs_par = 0, ss = 0, ss_round = 0, g = 0;
     for (int j = first; j < total_mt; j += cpg) {
-      for (int c = 0; c < a.n_chunks; ++c) {
-        const bool prs = a.prof != nullptr && blockIdx.x == 0 && sw == 0 && lane == 0 && j == first + 8 * cpg && c < 8;
-        if (prs) a.prof[512 + c * 4 + 0] = clock64();
-        ct_wait(bar_rawf + 8 * rs, rs_par, dbg, 8, c);
-        if (prs) a.prof[512 + c * 4 + 1] = clock64();
-        if (ss_round > 0) ct_wait(bar_sple + 8 * ss, (ss_round - 1) & 1u, dbg, 9, c);
-        if (prs) a.prof[512 + c * 4 + 2] = clock64();
-        __syncwarp();
-        const float4* src = reinterpret_cast<const float4*>(gbase + L.raw_ring + rs * CT_RAW_STAGE);
-        float4* dlo = reinterpret_cast<float4*>(gbase + L.split_ring + ss * L.split_stage_bytes);
-        // 512 float4 per tile, 256 per warp, 8 per lane: all eight loads first (the compiler cannot hoist them over the
-        // stores, both being shared memory), then the arithmetic and the stores
-        float4 v[8];
+      for (int c = 0; c < a.n_chunks; ++c, ++g) {
+        if ((g & 1u) == (uint32_t)sw) {
+          const bool prs = a.prof != nullptr && blockIdx.x == 0 && sw == 0 && lane == 0 && j == first + 8 * cpg && c < 8;
+          if (prs) a.prof[512 + c * 4 + 0] = clock64();
+          ct_wait(bar_rawf + 8 * rs, rs_par, dbg, 8, c);
+          if (prs) a.prof[512 + c * 4 + 1] = clock64();
+          if (ss_round > 0) ct_wait(bar_sple + 8 * ss, (ss_round - 1) & 1u, dbg, 9, c);
+          if (prs) a.prof[512 + c * 4 + 2] = clock64();
+          __syncwarp();
+          const float4* src = reinterpret_cast<const float4*>(gbase + L.raw_ring + rs * CT_RAW_STAGE);
+          float4* dlo = reinterpret_cast<float4*>(gbase + L.split_ring + ss * L.split_stage_bytes);
+          // 512 float4 per tile, 16 per lane, in two batches of 8 loads (the compiler cannot hoist shared-memory loads
+          // over shared-memory stores)
 #pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = src[sw * 256 + k * 32 + lane];
+          for (int h = 0; h < 2; ++h) {
+            float4 v[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          float4 l;
-          l.x = v[k].x - ct_hi(v[k].x); l.y = v[k].y - ct_hi(v[k].y); l.z = v[k].z - ct_hi(v[k].z); l.w = v[k].w - ct_hi(v[k].w);
-          dlo[sw * 256 + k * 32 + lane] = l;
+            for (int k = 0; k < 8; ++k) v[k] = src[h * 256 + k * 32 + lane];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              float4 l;
+              l.x = v[k].x - ct_hi(v[k].x); l.y = v[k].y - ct_hi(v[k].y); l.z = v[k].z - ct_hi(v[k].z); l.w = v[k].w - ct_hi(v[k].w);
+              dlo[h * 256 + k * 32 + lane] = l;
+            }
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor pipe
+          __syncwarp();
+          if (lane == 0) ct_arrive(bar_splf + 8 * ss);
+          if (prs) a.prof[512 + c * 4 + 3] = clock64();
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor pipe
-        __syncwarp();
-        if (lane == 0) ct_arrive(bar_splf + 8 * ss);
-        if (prs) a.prof[512 + c * 4 + 3] = clock64();
         if (++rs == (uint32_t)R) { rs = 0; rs_par ^= 1u; }
         if (++ss == (uint32_t)S) { ss = 0; ++ss_round; }
       }
