@@ -29,6 +29,60 @@ struct PersistSmem {   // byte offsets from the 1024-aligned base, computed on t
   uint32_t total;
 };
 
+// Transposed-conv epilogue of one tile (R = upsampling rate, compile time so the accumulator arrays stay in registers).
+// Only the D1/D2 groups cross rows; the D0 groups stay in registers. Row-major staging (one padded row of 8 R floats per
+// thread) with 128-bit accesses, as in the Conv1d branch.
+template <int R>
+__device__ __forceinline__ void convT_epilogue(const TapGemmArgs& a, float* stg, uint32_t t_lane, uint32_t bar_release, int grp,
+                                               int m, int lane, bool own, int b, int q, int co0) {
+  constexpr int HR = R / 2, SP = 36;
+  const int ct = a.co_tile;
+  const int rm = max(m - 1, 0), rp = min(m + 1, CT_BM - 1);
+  for (int c0 = 0; c0 < ct; c0 += 8) {
+    uint32_t v[2 * R][8];
+#pragma unroll
+    for (int g = 0; g < 2 * R; ++g) ct_ld8(t_lane + (uint32_t)(g * ct + c0), v[g]);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    if (c0 + 8 >= ct) {      // last TMEM read of this tile: hand the accumulator buffer back
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) ct_arrive(bar_release);
+    }
+    uint4* myrow = reinterpret_cast<uint4*>(stg + m * SP);
+#pragma unroll
+    for (int p = 0; p < R; ++p) {
+      myrow[2 * p] = make_uint4(v[R + p][0], v[R + p][1], v[R + p][2], v[R + p][3]);
+      myrow[2 * p + 1] = make_uint4(v[R + p][4], v[R + p][5], v[R + p][6], v[R + p][7]);
+    }
+    p_epi_sync(grp);
+    if (own) {
+      float nb[R][8];            // neighbour-row contribution per phase: row q-1 for p < R/2, row q+1 otherwise
+#pragma unroll
+      for (int p = 0; p < R; ++p) {
+        const float4* np4 = reinterpret_cast<const float4*>(stg + (p < HR ? rm : rp) * SP + 8 * p);
+        const float4 n0 = np4[0], n1 = np4[1];
+        nb[p][0] = n0.x; nb[p][1] = n0.y; nb[p][2] = n0.z; nb[p][3] = n0.w;
+        nb[p][4] = n1.x; nb[p][5] = n1.y; nb[p][6] = n1.z; nb[p][7] = n1.w;
+      }
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        const int co = co0 + c0 + jj;
+        const float bv = __ldg(a.bias + co);
+        float x[R];
+#pragma unroll
+        for (int p = 0; p < R; ++p) {
+          const float tv = __uint_as_float(v[p][jj]) + bv + nb[p][jj];
+          x[p] = tv > 0.f ? tv : 0.1f * tv;
+        }
+        float* op = a.out + ((size_t)b * a.CO + co) * a.Lp_out + (size_t)R * q;
+        if (R == 4) *reinterpret_cast<float4*>(op) = make_float4(x[0], x[1], x[2], x[3]);
+        else *reinterpret_cast<float2*>(op) = make_float2(x[0], x[1]);
+      }
+    }
+    p_epi_sync(grp);
+  }
+}
+
 __global__ void __launch_bounds__(P_THREADS, 1)
 tapgemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const TapGemmArgs a, const PersistSmem L, int* dbg) {
   extern __shared__ uint8_t smem_raw[];
@@ -294,48 +348,8 @@ tapgemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const TapG
         // transposed conv, r in {2,4}: accumulator columns D0 [0, r*ct) phase-major, D1 [r*ct, +r/2*ct) phases < r/2
         // (needs row q-1), D2 next r/2*ct columns, phases >= r/2 (needs row q+1); column = g*ct + channel with
         // g < r: D0 phase g, g >= r: D1/D2 phase g - r. Staging rows: g*8 + channel.
-        const int ct = a.co_tile, r = a.r, hr = a.r / 2, groups = 2 * a.r;
-        for (int c0 = 0; c0 < ct; c0 += 8) {
-          uint32_t v[8][8];
-#pragma unroll
-          for (int g = 0; g < 8; ++g)
-            if (g < groups) ct_ld8(t_lane + (uint32_t)(g * ct + c0), v[g]);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          if (c0 + 8 >= ct) {
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) ct_arrive(bar_acce + 8 * buf);
-          }
-#pragma unroll
-          for (int g = 0; g < 8; ++g)
-            if (g < groups) {
-#pragma unroll
-              for (int jj = 0; jj < 8; ++jj) stg[((g * 8 + jj) << 7) + m] = __uint_as_float(v[g][jj]);
-            }
-          p_epi_sync(grp);
-          if (own) {
-#pragma unroll
-            for (int jj = 0; jj < 8; ++jj) {
-              const int co = co0 + c0 + jj;
-              const float bv = __ldg(a.bias + co);
-              float x[4];
-#pragma unroll
-              for (int p = 0; p < 4; ++p) {
-                if (p < r) {
-                  float tv = stg[((p * 8 + jj) << 7) + m] + bv;
-                  tv += stg[(((r + p) * 8 + jj) << 7) + m + (p < hr ? -1 : 1)];
-                  x[p] = tv > 0.f ? tv : 0.1f * tv;
-                } else {
-                  x[p] = 0.f;
-                }
-              }
-              float* op = a.out + ((size_t)b * a.CO + co) * a.Lp_out + (size_t)r * q;
-              if (r == 4) *reinterpret_cast<float4*>(op) = make_float4(x[0], x[1], x[2], x[3]);
-              else *reinterpret_cast<float2*>(op) = make_float2(x[0], x[1]);
-            }
-          }
-          p_epi_sync(grp);
-        }
+        if (a.r == 4) convT_epilogue<4>(a, stg, t_lane, bar_acce + 8 * buf, grp, m, lane, own, b, q, co0);
+        else convT_epilogue<2>(a, stg, t_lane, bar_acce + 8 * buf, grp, m, lane, own, b, q, co0);
       }
       if (pr) a.prof[t * 4 + 2] = clock64();
     }
