@@ -279,7 +279,8 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         fl = stage_flops_per_step()
         dom = max(stage_ms.items(), key=lambda kv: kv[1][0]) if stage_ms else ("none", (0.0, 1))
         dom_ms_per_step = dom[1][0] / args.steps
-        tensor_stages = {"attention": "tcgen05 kind::tf32, 3 split terms (3xTF32): issued MMA FLOPs = 3x algorithmic",
+        tensor_stages = {"attention": "tcgen05 kind::f16, 16-bit split (fp16 hi/lo, 3 product terms, fp32 accumulate): issued MMA FLOPs = 3x algorithmic",
+                         "voc_in": "tcgen05 3xTF32 tap-GEMM (after a strided -> channel-first copy of the mel)",
                          "voc_up": "stages 0-1 tcgen05 3xTF32 tap-GEMM",
                          "voc_res1": "stages 0-1 tcgen05 3xTF32 tap-GEMM",
                          "voc_res2": "stages 0-1 tcgen05 3xTF32 tap-GEMM",
@@ -294,8 +295,9 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             ach = fl[dom[0]] / (dom_ms_per_step * 1e-3) / 1e12
             roof.update(achieved=ach, frac=ach / peaks["bf16_tflops_sustained"],
                         algorithmic_flops_per_step=fl[dom[0]],
-                        note="achieved = algorithmic (useful fp32-equivalent) FLOPs / device time of the stage; an "
-                             "fp32-faithful 3xTF32 kernel can reach at most 1/6 of the bf16 peak (TF32 = half rate, 3 terms)")
+                        note="achieved = algorithmic (useful fp32-equivalent) FLOPs / device time of the stage; an fp32-faithful "
+                             "split-precision kernel issues 3 products per algorithmic one: ceiling 1/3 of the bf16 peak with fp16 "
+                             "halves (attention, linear layers), 1/6 with TF32 halves (vocoder)")
         else:
             roof.update(achieved=None, frac=None)
         all_stage_tflops = {k: round(fl[k] / (v[0] / args.steps * 1e-3) / 1e12, 2) for k, v in stage_ms.items()

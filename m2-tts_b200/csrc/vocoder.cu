@@ -347,6 +347,33 @@ __global__ void __launch_bounds__(256) conv3_co1_tanh_kernel(const float* __rest
   }
 }
 
+// mel element (b,m,t) at x[b*sb + m*sm + t*st]  ->  y[b][m][t] with row pitch Lp (zero tail), through a 32x32 tile so
+// both sides are coalesced whichever of m / t is contiguous in x. Feeds the tensor-core input convolution, whose TMA
+// needs channel-first rows with a 16-byte pitch (the decoder hands the vocoder a [B,T,M] tensor, tts_model.py:390).
+__global__ void __launch_bounds__(256) mel_to_channel_first_kernel(const float* __restrict__ x, long long sb, long long sm, long long st,
+                                                                    float* __restrict__ y, int M, int T, int Lp) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, t0 = blockIdx.x * 32, m0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
+  const float* xb = x + (long long)b * sb;
+  if (st == 1) {          // t contiguous: read rows of t
+    for (int r = ty; r < 32; r += 8) {
+      const int m = m0 + r, t = t0 + tx;
+      tile[r][tx] = (m < M && t < T) ? xb[(long long)m * sm + t] : 0.f;
+    }
+  } else {                // m contiguous (or generic): read rows of m
+    for (int r = ty; r < 32; r += 8) {
+      const int t = t0 + r, m = m0 + tx;
+      tile[tx][r] = (m < M && t < T) ? xb[(long long)m * sm + (long long)t * st] : 0.f;
+    }
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int m = m0 + r, t = t0 + tx;
+    if (m < M && t < Lp) y[((long long)b * M + m) * Lp + t] = tile[r][tx];
+  }
+}
+
 // w[CO][CI][3] -> wp[CI][3][CO], several convolutions per launch (blockIdx.y = job)
 struct ConvPackJob { const float* src; float* dst; int CO, CI; };
 struct ConvPackJobs { ConvPackJob j[12]; };
@@ -465,7 +492,7 @@ extern "C" size_t m2tts_vocoder_workspace_bytes(int B, int T, int M, int C) {
   if (B <= 0 || T <= 0 || M <= 0 || C < 16) return 0;
   // widest activation: 4*C*T floats per utterance (+ row-pitch padding of the first tensor)
   const size_t act = align_up((size_t)B * C * ((size_t)T + 4) * 4 * sizeof(float), 256);
-  size_t wts = (size_t)C * M * 3;
+  size_t wts = (size_t)C * M * 3 + conv3_tc_wblob_floats(M, C);
   static const int rates[4] = {4, 4, 2, 2};
   for (int j = 0, c = C / 2; j < 4; ++j, c /= 2)
     wts += 2 * (size_t)c * c * 3 + 2 * conv3_tc_wblob_floats(c, c) + convT_tc_wblob_floats(2 * c, c, rates[j]) +
@@ -494,6 +521,7 @@ extern "C" int m2tts_vocoder_forward(const m2tts_vocoder_weights* w, const float
   // packed weights (FFMA layout [CI][3][CO]) and tensor-core weight images
   ConvPackJob jobs[9];
   float* in_wp = cv.take<float>((size_t)C * M * 3);
+  float* in_wb = cv.take<float>(conv3_tc_wblob_floats(M, C));
   jobs[0] = ConvPackJob{w->in_w, in_wp, C, M};
   float *r1p[4], *r2p[4], *r1b[4], *r2b[4], *upb[4], *fsb[4];
   for (int j = 0, c = C / 2; j < 4; ++j, c /= 2) {
@@ -535,7 +563,17 @@ extern "C" int m2tts_vocoder_forward(const m2tts_vocoder_weights* w, const float
   int L = T, c_in = C;
   int Lp = path[0] == P_TC ? ((L + 3) & ~3) : L;
   bool cl = false;                       // layout of the current activation (bufA): channel-last?
-  {
+  if (path[0] == P_TC && conv3_tc_eligible(M, C) && B <= 65535) {
+    // tensor-core input conv: channel-first copy of the mel with a 16-byte row pitch (bufC), then the tap-GEMM
+    const float* xin = mel;
+    if (!(stride_t == 1 && stride_m == Lp && stride_b == (int64_t)M * Lp && (((uintptr_t)mel) & 15) == 0)) {
+      dim3 grid(ceil_div(Lp, 32), ceil_div(M, 32), B);
+      M2_LAUNCH(M2TTS_STAGE_VOC_IN, mel_to_channel_first_kernel, grid, 256, 0, s, mel, (long long)stride_b, (long long)stride_m,
+                (long long)stride_t, bufC, M, T, Lp);
+      xin = bufC;
+    }
+    if ((rc = launch_conv3_tc(xin, Lp, w->in_w, in_wb, w->in_b, nullptr, 0, bufA, Lp, B, M, C, T, 1, 0, M2TTS_STAGE_VOC_IN, s))) return rc;
+  } else {
     ConvArgs a{mel, stride_b, stride_m, stride_t, in_wp, w->in_b, nullptr, bufA, M, C, T, 1, 0};
     a.y_pitch = Lp;
     if ((rc = launch_conv3(a, B, M2TTS_STAGE_VOC_IN, s))) return rc;
