@@ -123,9 +123,10 @@ int m2tts_debug_words(int* out, int n);
  * accumulation; operands saturate at +-65000); 1 = fp32 FFMA kernel; 2 = TF32 split, single-warpgroup kernel;
  * 3 = TF32 split, warp-specialised kernel (no range limit). Process-wide; also M2TTS_ATTENTION=ffma|tc1|tf32. */
 int m2tts_set_attention_mode(int mode);
-/* Vocoder kernel selection: 0 (default) = every leading stage whose three convolutions have channel
- * counts that are multiples of 16 runs as persistent tcgen05 implicit GEMMs with 3xTF32 splitting
- * (stage2_quality: all four stages), the rest fp32 FFMA; 1 = FFMA everywhere. Process-wide; also M2TTS_VOCODER=ffma. */
+/* Vocoder kernel selection: 0 (default) = tensor cores: the input conv and the wide stages as TF32-split tap-GEMMs, the
+ * narrow stages (C in {32,16}) as fused channel-last kernels with the 16-bit split (activations saturate at +-65000);
+ * 1 = fp32 FFMA everywhere; 2 = as 0 but the fused stages use the TF32 split (no range limit). Shapes the tensor
+ * kernels do not take fall back to FFMA per stage. Process-wide; also M2TTS_VOCODER=ffma|tf32. */
 int m2tts_set_vocoder_mode(int mode);
 /* fp32 FFMA peak probe: `iters` dependent-chain FFMAs per thread on a full grid;
  * writes nothing but a checksum; returns flop count through *flops. */
@@ -245,6 +246,14 @@ int m2tts_vocoder_stage_fused(const float* x, const float* up_w, const float* up
                               const float* res1_b, const float* res2_w, const float* res2_b,
                               const float* out_w, const float* out_b, float* y, int B, int C, int L,
                               void* workspace, size_t workspace_bytes, m2tts_stream_t stream);
+
+/* The same stage with the 16-bit split (fp16 hi/lo operands; activations saturate at +-65000): what m2tts_vocoder_forward uses
+ * for its narrow stages by default. Same arguments; workspace: m2tts_vocoder_stage_fused_h_workspace_bytes(B, C, L). */
+size_t m2tts_vocoder_stage_fused_h_workspace_bytes(int B, int C, int L);
+int m2tts_vocoder_stage_fused_h(const float* x, const float* up_w, const float* up_b, const float* res1_w,
+                                const float* res1_b, const float* res2_w, const float* res2_b,
+                                const float* out_w, const float* out_b, float* y, int B, int C, int L,
+                                void* workspace, size_t workspace_bytes, m2tts_stream_t stream);
 
 /* Bring-up probe (tests/rowshift_probe_run.py): K-major swizzled UMMA A operand whose descriptor start
  * address is moved by whole rows inside the swizzle pattern. */

@@ -170,7 +170,7 @@ int launch_w_split(const float* const* src, float* const* dst, const long long* 
 int launch_linear_tc(const float* a_planes, const float* w_planes, LinTcArgs a, int B, int stage, cudaStream_t s);
 int* debug_words_device();  // pinned mapped scratch for hang diagnostics (may be null)
 int attention_mode();  // 0 = tensor cores, 16-bit split (attention_h.cu); 1 = fp32 FFMA kernel; 2 = TF32 split, single-warpgroup kernel; 3 = TF32 split, warp-specialised kernel
-int vocoder_mode();    // 0 = tensor-core convolutions for the wide stages, 1 = FFMA everywhere
+int vocoder_mode();    // 0 = tensor cores (fused narrow stages with the 16-bit split), 1 = FFMA everywhere, 2 = tensor cores, TF32 split everywhere
 
 // tensor-core ("tap-GEMM") convolutions on plain fp32 [B][C][Lp] (conv_tc.cu / conv_tc2.cu)
 bool conv3_tc_eligible(int CI, int CO);
@@ -179,9 +179,15 @@ size_t conv3_tc_wblob_floats(int CI, int CO);
 size_t convT_tc_wblob_floats(int CI, int CO, int r);
 int launch_conv3_tc(const float* x, int Lp_in, const float* w, float* wblob, const float* bias, const float* residual,
                     int Lp_res, float* out, int Lp_out, int B, int CI, int CO, int L, int dil, int act, int stage,
-                    cudaStream_t s, int out_cl = 0);   // out_cl: write channel-last [B][L][CO] instead of [B][CO][Lp_out]
+                    cudaStream_t s, int out_cl = 0);   // out_cl 1: write channel-last fp32 [B][L][CO]; 2: channel-last fp16 hi/lo planes [2][B][L][CO]
 int launch_convT_tc(const float* x, int Lp_in, const float* w, float* wblob, const float* bias, float* out, int Lp_out,
                     int B, int CI, int CO, int L, int r, cudaStream_t s);
+// 16-bit split flavour (voc_fused_h.cu): input as fp16 hi/lo planes [2][B][L][2C]
+size_t voc_fused_h_wblob_bytes(int C);
+int launch_voc_stage_fused_h(const void* xh, long long x_plane, const float* up_w, const float* up_b, const float* w1, const float* b1,
+                             const float* w2, const float* b2, const float* out_w, const float* out_b, void* wblob,
+                             void* out_h, long long out_plane, float* out_f, int B, int C, int L_in, int stage, cudaStream_t s);
+int launch_split_planes_h(const float* x, void* planes, long long n, cudaStream_t s);
 // fused narrow stage on channel-last activations (voc_fused.cu): upsample x2 + ResBlock (+ output conv + tanh)
 bool voc_fused_eligible(int C, int r, int dil);
 size_t voc_fused_wblob_floats(int C);

@@ -12,6 +12,7 @@
 //     -> out[t] = sum_tap D_tap[t + shift_tap] + bias (LeakyReLU, + residual) -> plain fp32 in HBM.
 // HBM traffic is therefore the algorithmic minimum per layer (input once, residual once, output once).
 #include "conv_tc.cuh"
+#include <cuda_fp16.h>
 #include <math.h>
 
 namespace m2 {
@@ -333,7 +334,25 @@ tapgemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const TapG
               if (a.act == 1) x = x > 0.f ? x : 0.1f * x;
               xo[c] = x + rsd[c];
             }
-            if (a.out_cl) {       // channel-last rows for the fused narrow stages: 64 contiguous bytes per thread
+            if (a.out_cl == 2) {  // channel-last fp16 hi/lo planes for the 16-bit split fused stages (same bytes as fp32)
+              __half* oh = reinterpret_cast<__half*>(a.out) + ((size_t)b * a.L_out + q) * a.CO + co0 + c0;
+              __half* ol = oh + (size_t)a.B * a.L_out * a.CO;
+#pragma unroll
+              for (int j8 = 0; j8 < 2; ++j8) {
+                uint32_t hw[4], lw[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float a0 = fminf(fmaxf(xo[8 * j8 + 2 * e], -65000.f), 65000.f), a1 = fminf(fmaxf(xo[8 * j8 + 2 * e + 1], -65000.f), 65000.f);
+                  const __half2 hh = __floats2half2_rn(a0, a1);
+                  const float2 hf = __half22float2(hh);
+                  const __half2 ll = __floats2half2_rn(a0 - hf.x, a1 - hf.y);
+                  hw[e] = *reinterpret_cast<const uint32_t*>(&hh);
+                  lw[e] = *reinterpret_cast<const uint32_t*>(&ll);
+                }
+                *reinterpret_cast<uint4*>(oh + 8 * j8) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                *reinterpret_cast<uint4*>(ol + 8 * j8) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+              }
+            } else if (a.out_cl) {       // channel-last rows for the fused narrow stages: 64 contiguous bytes per thread
               float4* op = reinterpret_cast<float4*>(a.out + ((size_t)b * a.L_out + q) * a.CO + co0 + c0);
 #pragma unroll
               for (int c4 = 0; c4 < 4; ++c4) op[c4] = make_float4(xo[4 * c4], xo[4 * c4 + 1], xo[4 * c4 + 2], xo[4 * c4 + 3]);

@@ -81,7 +81,7 @@ int vocoder_mode() {
   int m = g_voc_mode.load(std::memory_order_relaxed);
   if (m < 0) {
     const char* e = getenv("M2TTS_VOCODER");
-    m = (e && strcmp(e, "ffma") == 0) ? 1 : 0;
+    m = (e && strcmp(e, "ffma") == 0) ? 1 : ((e && strcmp(e, "tf32") == 0) ? 2 : 0);
     g_voc_mode.store(m);
   }
   return m;
@@ -89,7 +89,8 @@ int vocoder_mode() {
 }  // namespace m2
 
 extern "C" int m2tts_set_vocoder_mode(int mode) {
-  M2_REQUIRE(mode == 0 || mode == 1, M2TTS_E_BADSHAPE, "set_vocoder_mode: mode must be 0 (tensor) or 1 (ffma)");
+  M2_REQUIRE(mode >= 0 && mode <= 2, M2TTS_E_BADSHAPE,
+             "set_vocoder_mode: 0 = tensor cores (narrow stages 16-bit split), 1 = ffma, 2 = tensor cores (narrow stages TF32 split)");
   g_voc_mode.store(mode);
   return M2TTS_OK;
 }

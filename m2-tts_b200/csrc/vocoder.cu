@@ -548,7 +548,8 @@ extern "C" int m2tts_vocoder_forward(const m2tts_vocoder_weights* w, const float
   //   FFMA  : fp32 FFMA kernels (any shape, any input strides).
   enum { P_FFMA = 0, P_TC = 1, P_FUSED = 2 };
   int path[4] = {P_FFMA, P_FFMA, P_FFMA, P_FFMA};
-  if (vocoder_mode() == 0) {
+  const bool fused_h = vocoder_mode() == 0;      // fused narrow stages: 16-bit split (default) or TF32 split (mode 2)
+  if (vocoder_mode() != 1) {
     int ci = C;
     for (int j = 0; j < 4; ++j, ci /= 2) {
       const int c = ci / 2;
@@ -583,7 +584,19 @@ extern "C" int m2tts_vocoder_forward(const m2tts_vocoder_weights* w, const float
     const int r = rates[j], c = c_in / 2, Lo = L * r;
     const int dil = w->res_dilation[j] > 0 ? w->res_dilation[j] : 1;
     const bool next_cl = j + 1 < 4 && path[j + 1] == P_FUSED;
-    if (path[j] == P_FUSED) {
+    if (path[j] == P_FUSED && fused_h) {
+      // 16-bit split: bufA = fp16 hi/lo planes, channel-last [2][B][L][c_in] -> bufB planes [2][B][Lo][c] when the next
+      // stage is fused too, plain fp32 channel-last otherwise, or straight to the waveform
+      const bool last = j == 3;
+      const bool planes_out = !last && next_cl;
+      if ((rc = launch_voc_stage_fused_h(bufA, (long long)B * L * c_in, w->up_w[j], w->up_b[j], w->res1_w[j], w->res1_b[j], w->res2_w[j],
+                                         w->res2_b[j], last ? w->out_w : nullptr, last ? w->out_b : nullptr, fsb[j],
+                                         planes_out ? (void*)bufB : nullptr, (long long)B * Lo * c,
+                                         last ? audio : (planes_out ? nullptr : bufB), B, c, L, M2TTS_STAGE_VOC_FUSED, s))) return rc;
+      if (last) audio_done = true;
+      else { float* t = bufA; bufA = bufB; bufB = t; }
+      cl = true;
+    } else if (path[j] == P_FUSED) {
       // bufA channel-last [B][L][c_in] -> bufB channel-last [B][Lo][c] (or straight to the waveform)
       const bool last = j == 3;
       if ((rc = launch_voc_stage_fused(bufA, w->up_w[j], w->up_b[j], w->res1_w[j], w->res1_b[j], w->res2_w[j], w->res2_b[j],
@@ -598,7 +611,7 @@ extern "C" int m2tts_vocoder_forward(const m2tts_vocoder_weights* w, const float
       if ((rc = launch_conv3_tc(bufB, Lo, w->res1_w[j], r1b[j], w->res1_b[j], nullptr, 0, bufC, Lo, B, c, c, Lo, dil, 1,
                                 M2TTS_STAGE_VOC_RES1, s))) return rc;
       if ((rc = launch_conv3_tc(bufC, Lo, w->res2_w[j], r2b[j], w->res2_b[j], bufB, Lo, bufA, Lo, B, c, c, Lo, 1, 0,
-                                M2TTS_STAGE_VOC_RES2, s, next_cl ? 1 : 0))) return rc;
+                                M2TTS_STAGE_VOC_RES2, s, next_cl ? (fused_h ? 2 : 1) : 0))) return rc;
       Lp = Lo;
       cl = next_cl;
     } else {

@@ -363,10 +363,12 @@ def test_tensor_core_conv_entry_points():
         assert H.max_abs(y.cpu(), want) <= FP32_TOL, ("convT_tc", CI, CO, L, r_)
 
 
+@pytest.mark.parametrize("prec", ["f16", "tf32"])
 @pytest.mark.parametrize("C,L,B,final", [(16, 300, 2, False), (16, 300, 2, True), (32, 257, 2, False), (32, 130, 3, True),
                                          (16, 1, 1, True), (16, 2000, 1, True), (32, 1111, 2, False), (16, 61, 5, False)])
-def test_fused_vocoder_stage(C, L, B, final):
-    """One (upsample x2, ResBlock[, output conv + tanh]) stage as a single channel-last tcgen05 kernel."""
+def test_fused_vocoder_stage(C, L, B, final, prec):
+    """One (upsample x2, ResBlock[, output conv + tanh]) stage as a single channel-last tcgen05 kernel, in both split
+    flavours (16-bit: fp16 hi/lo operands, the default of vocoder_forward; TF32)."""
     from models import _native as nat
     import torch.nn.functional as F
     lib = nat.lib()
@@ -386,16 +388,21 @@ def test_fused_vocoder_stage(C, L, B, final):
         want = want.transpose(1, 2).contiguous()                            # channel-last [B, 2L, C]
     d = [t.to(DEV) for t in (x.transpose(1, 2).contiguous(), up_w, up_b, w1, b1, w2, b2, ow, ob)]
     y = torch.full(want.shape, float("nan"), device=DEV)
-    ws = torch.empty(lib.m2tts_vocoder_stage_fused_workspace_bytes(C), dtype=torch.uint8, device=DEV)
-    rc = lib.m2tts_vocoder_stage_fused(*(t.data_ptr() for t in d[:7]), d[7].data_ptr() if final else None,
-                                       d[8].data_ptr() if final else None, y.data_ptr(), B, C, L, ws.data_ptr(), ws.numel(), None)
+    if prec == "f16":
+        ws = torch.empty(lib.m2tts_vocoder_stage_fused_h_workspace_bytes(B, C, L), dtype=torch.uint8, device=DEV)
+        fn = lib.m2tts_vocoder_stage_fused_h
+    else:
+        ws = torch.empty(lib.m2tts_vocoder_stage_fused_workspace_bytes(C), dtype=torch.uint8, device=DEV)
+        fn = lib.m2tts_vocoder_stage_fused
+    rc = fn(*(t.data_ptr() for t in d[:7]), d[7].data_ptr() if final else None,
+            d[8].data_ptr() if final else None, y.data_ptr(), B, C, L, ws.data_ptr(), ws.numel(), None)
     nat.check(rc, "vocoder_stage_fused")
     torch.cuda.synchronize()
     assert not torch.isnan(y).any(), "unwritten output rows"
     assert H.max_abs(y.cpu(), want) <= FP32_TOL, (C, L, B, final)
 
 
-@pytest.mark.parametrize("mode", [0, 1])  # 0 = tcgen05 convs for the wide stages, 1 = FFMA everywhere
+@pytest.mark.parametrize("mode", [0, 1, 2])  # 0 = tensor cores (16-bit split fused stages), 1 = FFMA everywhere, 2 = tensor cores, TF32 split
 def test_vocoder_modes_both_meet_fp32_tolerance(mode):
     from models import _native as nat
     lib = nat.lib()
