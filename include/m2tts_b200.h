@@ -255,6 +255,13 @@ int m2tts_vocoder_stage_fused_h(const float* x, const float* up_w, const float* 
                                 const float* out_w, const float* out_b, float* y, int B, int C, int L,
                                 void* workspace, size_t workspace_bytes, m2tts_stream_t stream);
 
+/* A whole LightweightResBlock (components.py:177-200), y = x + conv2(leaky_relu(conv1(x), 0.1)), as one tcgen05 kernel with
+ * the 16-bit split; x / y fp32 CHANNEL-LAST [B][L][C], C = 64, kernel 3, dilation 1; weights in state_dict layout [C][C][3].
+ * workspace: m2tts_resblock_fused_h_workspace_bytes(B, C, L). */
+size_t m2tts_resblock_fused_h_workspace_bytes(int B, int C, int L);
+int m2tts_resblock_fused_h(const float* x, const float* w1, const float* b1, const float* w2, const float* b2, float* y,
+                           int B, int C, int L, void* workspace, size_t workspace_bytes, m2tts_stream_t stream);
+
 /* Bring-up probe (tests/rowshift_probe_run.py): K-major swizzled UMMA A operand whose descriptor start
  * address is moved by whole rows inside the swizzle pattern. */
 int m2tts_rowshift_probe(const float* A, const float* Bm, float* D, int rows_total, int N, int K, int rowbytes,

@@ -181,7 +181,12 @@ int launch_conv3_tc(const float* x, int Lp_in, const float* w, float* wblob, con
                     int Lp_res, float* out, int Lp_out, int B, int CI, int CO, int L, int dil, int act, int stage,
                     cudaStream_t s, int out_cl = 0);   // out_cl 1: write channel-last fp32 [B][L][CO]; 2: channel-last fp16 hi/lo planes [2][B][L][CO]
 int launch_convT_tc(const float* x, int Lp_in, const float* w, float* wblob, const float* bias, float* out, int Lp_out,
-                    int B, int CI, int CO, int L, int r, cudaStream_t s);
+                    int B, int CI, int CO, int L, int r, cudaStream_t s, int out_cl = 0);   // out_cl 2: fp16 hi/lo planes, channel-last
+// whole ResBlock for C = 64 as one kernel, channel-last fp16 hi/lo planes in (voc_res_h.cu)
+bool voc_res_h_eligible(int C, int dil);
+size_t voc_res_h_wblob_bytes(int C);
+int launch_voc_res_h(const void* uh, long long u_plane, const float* w1, const float* b1, const float* w2, const float* b2, void* wblob,
+                     void* out_h, long long out_plane, float* out_f, int B, int C, int L, int stage, cudaStream_t s);
 // 16-bit split flavour (voc_fused_h.cu): input as fp16 hi/lo planes [2][B][L][2C]
 size_t voc_fused_h_wblob_bytes(int C);
 int launch_voc_stage_fused_h(const void* xh, long long x_plane, const float* up_w, const float* up_b, const float* w1, const float* b1,

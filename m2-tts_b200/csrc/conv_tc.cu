@@ -134,7 +134,7 @@ int launch_conv3_tc(const float* x, int Lp_in, const float* w, float* wblob, con
 
 // ConvTranspose1d(k=2r, stride r, pad r/2) + leaky_relu on plain fp32, r in {2,4}.
 int launch_convT_tc(const float* x, int Lp_in, const float* w, float* wblob, const float* bias, float* out, int Lp_out,
-                    int B, int CI, int CO, int L, int r, cudaStream_t s) {
+                    int B, int CI, int CO, int L, int r, cudaStream_t s, int out_cl) {
   M2_REQUIRE(convT_tc_eligible(CI, CO, r), M2TTS_E_UNSUPPORTED, "convT_tc: CI=%d CO=%d r=%d not eligible", CI, CO, r);
   M2_REQUIRE((Lp_out % r) == 0 && (Lp_out & 3) == 0, M2TTS_E_BADSHAPE, "convT_tc: output pitch %d", Lp_out);
   const int ct = (CO % 32 == 0) ? 32 : 16, n_tiles = CO / ct;
@@ -147,7 +147,7 @@ int launch_convT_tc(const float* x, int Lp_in, const float* w, float* wblob, con
   a.tap_shift[1] = -1; a.tap_rows[1] = (r / 2) * ct; a.tap_wrow[1] = r * ct;                   a.tap_dcol[1] = r * ct;
   a.tap_shift[2] = 1;  a.tap_rows[2] = (r / 2) * ct; a.tap_wrow[2] = r * ct + (r / 2) * ct;    a.tap_dcol[2] = r * ct + (r / 2) * ct;
   a.rows_total = 2 * r * ct; a.n_cols = 2 * r * ct; a.wblob = wblob; a.r = r; a.co_tile = ct; a.CO = CO;
-  a.L_out = r * L; a.Lp_out = Lp_out; a.bias = bias; a.act = 1; a.out = out;
+  a.L_out = r * L; a.Lp_out = Lp_out; a.bias = bias; a.act = 1; a.out = out; a.out_cl = out_cl;
   return launch_tapgemm(x, Lp_in, a, n_tiles, M2TTS_STAGE_VOC_UP, s);
 }
 

@@ -65,6 +65,29 @@ __device__ __forceinline__ void convT_epilogue(const TapGemmArgs& a, float* stg,
         nb[p][0] = n0.x; nb[p][1] = n0.y; nb[p][2] = n0.z; nb[p][3] = n0.w;
         nb[p][4] = n1.x; nb[p][5] = n1.y; nb[p][6] = n1.z; nb[p][7] = n1.w;
       }
+      if (a.out_cl == 2) {
+        // channel-last fp16 hi/lo planes [2][B][L_out][CO] for the 16-bit split ResBlock kernel: 8 channels = one 16-byte
+        // chunk per (output position, plane)
+#pragma unroll
+        for (int p = 0; p < R; ++p) {
+          uint32_t hw[4], lw[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float t0 = __uint_as_float(v[p][2 * e]) + __ldg(a.bias + co0 + c0 + 2 * e) + nb[p][2 * e];
+            float t1 = __uint_as_float(v[p][2 * e + 1]) + __ldg(a.bias + co0 + c0 + 2 * e + 1) + nb[p][2 * e + 1];
+            t0 = t0 > 0.f ? t0 : 0.1f * t0; t1 = t1 > 0.f ? t1 : 0.1f * t1;
+            t0 = fminf(t0, 65000.f); t1 = fminf(t1, 65000.f); t0 = fmaxf(t0, -65000.f); t1 = fmaxf(t1, -65000.f);
+            const __half2 hh = __floats2half2_rn(t0, t1);
+            const float2 hf = __half22float2(hh);
+            const __half2 ll = __floats2half2_rn(t0 - hf.x, t1 - hf.y);
+            hw[e] = *reinterpret_cast<const uint32_t*>(&hh);
+            lw[e] = *reinterpret_cast<const uint32_t*>(&ll);
+          }
+          __half* oh = reinterpret_cast<__half*>(a.out) + ((size_t)b * a.L_out + (size_t)R * q + p) * a.CO + co0 + c0;
+          *reinterpret_cast<uint4*>(oh) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+          *reinterpret_cast<uint4*>(oh + (size_t)a.B * a.L_out * a.CO) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        }
+      } else {
 #pragma unroll
       for (int jj = 0; jj < 8; ++jj) {
         const int co = co0 + c0 + jj;
@@ -78,6 +101,7 @@ __device__ __forceinline__ void convT_epilogue(const TapGemmArgs& a, float* stg,
         float* op = a.out + ((size_t)b * a.CO + co) * a.Lp_out + (size_t)R * q;
         if (R == 4) *reinterpret_cast<float4*>(op) = make_float4(x[0], x[1], x[2], x[3]);
         else *reinterpret_cast<float2*>(op) = make_float2(x[0], x[1]);
+      }
       }
     }
     p_epi_sync(grp);

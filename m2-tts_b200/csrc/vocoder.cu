@@ -605,6 +605,14 @@ extern "C" int m2tts_vocoder_forward(const m2tts_vocoder_weights* w, const float
       if (last) audio_done = true;
       else { float* t = bufA; bufA = bufB; bufB = t; }
       cl = true;
+    } else if (path[j] == P_TC && fused_h && next_cl && voc_res_h_eligible(c, dil)) {
+      // C = 64: the upsampling tap-GEMM writes fp16 hi/lo planes channel-last (bufB) and the whole ResBlock is ONE
+      // 16-bit split kernel (bufB -> bufA planes): v = lrelu(conv1(u)) and the residual never travel through HBM
+      if ((rc = launch_convT_tc(bufA, Lp, w->up_w[j], upb[j], w->up_b[j], bufB, Lo, B, c_in, c, L, r, s, 2))) return rc;
+      if ((rc = launch_voc_res_h(bufB, (long long)B * Lo * c, w->res1_w[j], w->res1_b[j], w->res2_w[j], w->res2_b[j], r1b[j],
+                                 bufA, (long long)B * Lo * c, nullptr, B, c, Lo, M2TTS_STAGE_VOC_RES1, s))) return rc;
+      Lp = Lo;
+      cl = true;
     } else if (path[j] == P_TC) {
       // bufA (pitch Lp) -> up -> bufB -> conv1 -> bufC -> conv2 (+ residual bufB) -> bufA; Lo = r*L is a multiple of 4
       if ((rc = launch_convT_tc(bufA, Lp, w->up_w[j], upb[j], w->up_b[j], bufB, Lo, B, c_in, c, L, r, s))) return rc;

@@ -402,6 +402,28 @@ def test_fused_vocoder_stage(C, L, B, final, prec):
     assert H.max_abs(y.cpu(), want) <= FP32_TOL, (C, L, B, final)
 
 
+@pytest.mark.parametrize("L,B", [(300, 2), (126, 1), (127, 3), (1, 1), (2000, 2)])
+def test_fused_resblock_c64(L, B):
+    """A whole ResBlock (C = 64) as one channel-last 16-bit-split tcgen05 kernel."""
+    from models import _native as nat
+    import torch.nn.functional as F
+    lib = nat.lib()
+    C = 64
+    g = torch.Generator().manual_seed(7 * L + B)
+    x = torch.randn(B, C, L, generator=g)
+    w1 = torch.randn(C, C, 3, generator=g) * (1.0 / (3 * C) ** 0.5)
+    w2 = torch.randn(C, C, 3, generator=g) * (1.0 / (3 * C) ** 0.5)
+    b1, b2 = (torch.randn(C, generator=g) * 0.3 for _ in range(2))
+    want = (x + F.conv1d(F.leaky_relu(F.conv1d(x, w1, b1, padding=1), 0.1), w2, b2, padding=1)).transpose(1, 2).contiguous()
+    d = [t.to(DEV) for t in (x.transpose(1, 2).contiguous(), w1, b1, w2, b2)]
+    y = torch.full(want.shape, float("nan"), device=DEV)
+    ws = torch.empty(lib.m2tts_resblock_fused_h_workspace_bytes(B, C, L), dtype=torch.uint8, device=DEV)
+    nat.check(lib.m2tts_resblock_fused_h(*(t.data_ptr() for t in d), y.data_ptr(), B, C, L, ws.data_ptr(), ws.numel(), None), "resblock_fused_h")
+    torch.cuda.synchronize()
+    assert not torch.isnan(y).any(), "unwritten output rows"
+    assert H.max_abs(y.cpu(), want) <= FP32_TOL, (L, B)
+
+
 @pytest.mark.parametrize("mode", [0, 1, 2])  # 0 = tensor cores (16-bit split fused stages), 1 = FFMA everywhere, 2 = tensor cores, TF32 split
 def test_vocoder_modes_both_meet_fp32_tolerance(mode):
     from models import _native as nat
