@@ -281,10 +281,10 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         dom_ms_per_step = dom[1][0] / args.steps
         tensor_stages = {"attention": "tcgen05 kind::f16, 16-bit split (fp16 hi/lo, 3 product terms, fp32 accumulate): issued MMA FLOPs = 3x algorithmic",
                          "voc_in": "tcgen05 3xTF32 tap-GEMM (after a strided -> channel-first copy of the mel)",
-                         "voc_up": "stages 0-1 tcgen05 3xTF32 tap-GEMM",
-                         "voc_res1": "stages 0-1 tcgen05 3xTF32 tap-GEMM",
-                         "voc_res2": "stages 0-1 tcgen05 3xTF32 tap-GEMM",
-                         "voc_fused": "stages 2-3: upsample + ResBlock (+ output conv) fused, channel-last tcgen05 3xTF32"}
+                         "voc_up": "stages 0-1 transposed convs: tcgen05 3xTF32 tap-GEMM writing fp16 hi/lo planes channel-last",
+                         "voc_res1": "stage 0 conv1 (C=128, channel-last 16-bit split conv kernel) + the whole stage-1 ResBlock (C=64, one fused 16-bit split kernel)",
+                         "voc_res2": "stage 0 conv2 + residual (C=128, channel-last 16-bit split conv kernel, writes fp32 channel-first)",
+                         "voc_fused": "stages 2-3: upsample + ResBlock (+ output conv + tanh) fused, channel-last tcgen05 kind::f16 16-bit split"}
         roof = {"kernel": dom[0], "bound": "tensor", "unit": "TFLOP/s", "stage_ms_per_step": dom_ms_per_step,
                 "launches_per_step": dom[1][1] // args.steps, "launch_ms": dom[1][0] / max(dom[1][1], 1),
                 "peak": peaks["bf16_tflops_sustained"],
@@ -297,7 +297,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                         algorithmic_flops_per_step=fl[dom[0]],
                         note="achieved = algorithmic (useful fp32-equivalent) FLOPs / device time of the stage; an fp32-faithful "
                              "split-precision kernel issues 3 products per algorithmic one: ceiling 1/3 of the bf16 peak with fp16 "
-                             "halves (attention, linear layers), 1/6 with TF32 halves (vocoder)")
+                             "halves (attention, linear layers, ResBlocks, narrow stages), 1/6 with TF32 halves (input conv, upsampling tap-GEMMs)")
         else:
             roof.update(achieved=None, frac=None)
         all_stage_tflops = {k: round(fl[k] / (v[0] / args.steps * 1e-3) / 1e12, 2) for k, v in stage_ms.items()
@@ -355,10 +355,10 @@ def stage_flops_per_step():
     for j, r in enumerate((4, 4, 2, 2)):
         c, Lc = c_in // 2, Lc * r
         up, res = 2 * 2 * c_in * c * Lc * B, 2 * 3 * c * c * Lc * B       # two taps per output sample; one k=3 conv
-        if j < 2:      # wide stages: three tap-GEMM launches each
-            fl["voc_up"] += up
-            fl["voc_res1"] += res
-            fl["voc_res2"] += res
+        if j < 2:      # wide stages: upsampling tap-GEMM, then two conv launches (C = 128) or one fused ResBlock launch (C = 64,
+            fl["voc_up"] += up          # accounted under voc_res1)
+            fl["voc_res1"] += res if j == 0 else 2 * res
+            fl["voc_res2"] += res if j == 0 else 0
         else:          # narrow stages: one fused kernel each (the last one includes the output conv)
             fl["voc_fused"] += up + 2 * res
         c_in = c
@@ -366,7 +366,7 @@ def stage_flops_per_step():
     return fl
 
 
-TENSOR_LINEAR = {"ln_qkv", "out_proj", "ffn1", "ffn2", "ln_proj"}      # tcgen05 3xTF32 linear layers
+TENSOR_LINEAR = {"ln_qkv", "out_proj", "ffn1", "ffn2", "ln_proj"}      # tcgen05 16-bit split linear layers (lin_h.cu)
 
 
 def stage_bytes_per_step():

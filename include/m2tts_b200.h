@@ -262,6 +262,14 @@ size_t m2tts_resblock_fused_h_workspace_bytes(int B, int C, int L);
 int m2tts_resblock_fused_h(const float* x, const float* w1, const float* b1, const float* w2, const float* b2, float* y,
                            int B, int C, int L, void* workspace, size_t workspace_bytes, m2tts_stream_t stream);
 
+/* One convolution of the widest LightweightResBlock (components.py:181-200): y = act(conv1d(x, w, b, padding 1)) (+ residual),
+ * C = 128, kernel 3, dilation 1, 16-bit split, channel-last operands. x / residual fp32 CHANNEL-LAST [B][L][C]; act 0 none,
+ * 1 leaky_relu(0.1); y fp32 channel-first [B][C][L] (out_cl 0) or channel-last [B][L][C] (out_cl 1).
+ * workspace: m2tts_conv1d_k3_h_workspace_bytes(B, C, L). */
+size_t m2tts_conv1d_k3_h_workspace_bytes(int B, int C, int L);
+int m2tts_conv1d_k3_h(const float* x, const float* w, const float* b, const float* residual, float* y, int B, int C, int L,
+                      int act, int out_cl, void* workspace, size_t workspace_bytes, m2tts_stream_t stream);
+
 /* Bring-up probe (tests/rowshift_probe_run.py): K-major swizzled UMMA A operand whose descriptor start
  * address is moved by whole rows inside the swizzle pattern. */
 int m2tts_rowshift_probe(const float* A, const float* Bm, float* D, int rows_total, int N, int K, int rowbytes,

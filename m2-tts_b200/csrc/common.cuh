@@ -187,6 +187,12 @@ bool voc_res_h_eligible(int C, int dil);
 size_t voc_res_h_wblob_bytes(int C);
 int launch_voc_res_h(const void* uh, long long u_plane, const float* w1, const float* b1, const float* w2, const float* b2, void* wblob,
                      void* out_h, long long out_plane, float* out_f, int B, int C, int L, int stage, cudaStream_t s);
+// one Conv1d(C, C, 3) for C = 128 on channel-last fp16 hi/lo planes (voc_conv_h.cu); output planes or fp32 channel-first
+bool voc_conv_h_eligible(int C, int dil);
+size_t voc_conv_h_wblob_bytes(int C);
+int launch_voc_conv_h(const void* xh, long long x_plane, const float* w, const float* bias, void* wblob, const void* res_h,
+                      long long res_plane, void* out_h, long long out_plane, float* out_cf, int Lp_out, int B, int C, int L, int act,
+                      int stage, cudaStream_t s);
 // 16-bit split flavour (voc_fused_h.cu): input as fp16 hi/lo planes [2][B][L][2C]
 size_t voc_fused_h_wblob_bytes(int C);
 int launch_voc_stage_fused_h(const void* xh, long long x_plane, const float* up_w, const float* up_b, const float* w1, const float* b1,

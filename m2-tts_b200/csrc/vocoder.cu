@@ -500,6 +500,12 @@ extern "C" size_t m2tts_vocoder_workspace_bytes(int B, int T, int M, int C) {
   return 3 * act + align_up(wts * sizeof(float), 256) + 40 * 256;
 }
 
+static bool conv_h_enabled() {      // M2TTS_CONV_H=0 keeps the TF32 tap-GEMM for the C = 128 ResBlock (A/B measurements)
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("M2TTS_CONV_H"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+
 extern "C" int m2tts_vocoder_forward(const m2tts_vocoder_weights* w, const float* mel, int64_t stride_b,
                                      int64_t stride_m, int64_t stride_t, float* audio, int B, int T, int M,
                                      int C, void* workspace, size_t workspace_bytes, m2tts_stream_t stream) {
@@ -613,6 +619,17 @@ extern "C" int m2tts_vocoder_forward(const m2tts_vocoder_weights* w, const float
                                  bufA, (long long)B * Lo * c, nullptr, B, c, Lo, M2TTS_STAGE_VOC_RES1, s))) return rc;
       Lp = Lo;
       cl = true;
+    } else if (path[j] == P_TC && fused_h && voc_conv_h_eligible(c, dil) && conv_h_enabled()) {
+      // C = 128: the upsampling tap-GEMM writes fp16 hi/lo planes channel-last (bufB); the two convolutions of the ResBlock run
+      // on those planes (no splitter, one accumulator for the three taps); conv2 writes what the next stage reads
+      const long long plane = (long long)B * Lo * c;
+      if ((rc = launch_convT_tc(bufA, Lp, w->up_w[j], upb[j], w->up_b[j], bufB, Lo, B, c_in, c, L, r, s, 2))) return rc;
+      if ((rc = launch_voc_conv_h(bufB, plane, w->res1_w[j], w->res1_b[j], r1b[j], nullptr, 0, bufC, plane, nullptr, 0, B, c, Lo, 1,
+                                  M2TTS_STAGE_VOC_RES1, s))) return rc;
+      if ((rc = launch_voc_conv_h(bufC, plane, w->res2_w[j], w->res2_b[j], r2b[j], bufB, plane, next_cl ? (void*)bufA : nullptr, plane,
+                                  next_cl ? nullptr : bufA, Lo, B, c, Lo, 0, M2TTS_STAGE_VOC_RES2, s))) return rc;
+      Lp = Lo;
+      cl = next_cl;
     } else if (path[j] == P_TC) {
       // bufA (pitch Lp) -> up -> bufB -> conv1 -> bufC -> conv2 (+ residual bufB) -> bufA; Lo = r*L is a multiple of 4
       if ((rc = launch_convT_tc(bufA, Lp, w->up_w[j], upb[j], w->up_b[j], bufB, Lo, B, c_in, c, L, r, s))) return rc;

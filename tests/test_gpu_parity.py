@@ -424,6 +424,38 @@ def test_fused_resblock_c64(L, B):
     assert H.max_abs(y.cpu(), want) <= FP32_TOL, (L, B)
 
 
+@pytest.mark.parametrize("L,B,act,res,out_cl", [(1, 1, 0, False, 0), (127, 2, 1, False, 1), (128, 2, 0, True, 0), (129, 3, 1, True, 1),
+                                                (1000, 5, 0, True, 0), (13784, 3, 1, False, 1), (13784, 3, 0, True, 0)])
+def test_conv1d_k3_h_c128_matches_torch(L, B, act, res, out_cl):
+    """One convolution of the widest ResBlock (C = 128) on channel-last 16-bit split operands (voc_conv_h.cu) against
+    torch's conv1d (components.py:196-200): both activations, with and without the residual, both output layouts;
+    lengths around the 128-row tile, a length that leaves CTAs idle and the C3 stage-0 length."""
+    from models import _native as nat
+    import torch.nn.functional as F
+    lib = nat.lib()
+    C = 128
+    g = torch.Generator().manual_seed(11 * L + B)
+    x = torch.randn(B, C, L, generator=g)
+    r = torch.randn(B, C, L, generator=g)
+    w = torch.randn(C, C, 3, generator=g) * (1.0 / (3 * C) ** 0.5)
+    b = torch.randn(C, generator=g) * 0.3
+    want = F.conv1d(x, w, b, padding=1)
+    if act:
+        want = F.leaky_relu(want, 0.1)
+    if res:
+        want = want + r
+    if out_cl:
+        want = want.transpose(1, 2).contiguous()
+    xd, rd, wd, bd = (t.to(DEV) for t in (x.transpose(1, 2).contiguous(), r.transpose(1, 2).contiguous(), w, b))
+    y = torch.full(want.shape, float("nan"), device=DEV)
+    ws = torch.empty(lib.m2tts_conv1d_k3_h_workspace_bytes(B, C, L), dtype=torch.uint8, device=DEV)
+    nat.check(lib.m2tts_conv1d_k3_h(xd.data_ptr(), wd.data_ptr(), bd.data_ptr(), rd.data_ptr() if res else None, y.data_ptr(), B, C, L,
+                                    act, out_cl, ws.data_ptr(), ws.numel(), None), "conv1d_k3_h")
+    torch.cuda.synchronize()
+    assert not torch.isnan(y).any(), "unwritten output rows"
+    assert H.max_abs(y.cpu(), want) <= FP32_TOL, (L, B, act, res, out_cl)
+
+
 @pytest.mark.parametrize("mode", [0, 1, 2])  # 0 = tensor cores (16-bit split fused stages), 1 = FFMA everywhere, 2 = tensor cores, TF32 split
 def test_vocoder_modes_both_meet_fp32_tolerance(mode):
     from models import _native as nat
