@@ -270,6 +270,14 @@ size_t m2tts_conv1d_k3_h_workspace_bytes(int B, int C, int L);
 int m2tts_conv1d_k3_h(const float* x, const float* w, const float* b, const float* residual, float* y, int B, int C, int L,
                       int act, int out_cl, void* workspace, size_t workspace_bytes, m2tts_stream_t stream);
 
+/* One upsampling layer of the vocoder with its activation (components.py:225-241):
+ * y = leaky_relu(conv_transpose1d(x, w, b, stride 4, padding 2), 0.1), kernel 8, CI in {128, 256}, CO = CI / 2, 16-bit split,
+ * channel-last operands: x fp32 [B][L][CI], w [CI][CO][8] (state_dict layout), y fp32 [B][4L][CO].
+ * workspace: m2tts_conv_transpose_x4_h_workspace_bytes(B, CI, L). */
+size_t m2tts_conv_transpose_x4_h_workspace_bytes(int B, int CI, int L);
+int m2tts_conv_transpose_x4_h(const float* x, const float* w, const float* b, float* y, int B, int CI, int L,
+                              void* workspace, size_t workspace_bytes, m2tts_stream_t stream);
+
 /* Bring-up probe (tests/rowshift_probe_run.py): K-major swizzled UMMA A operand whose descriptor start
  * address is moved by whole rows inside the swizzle pattern. */
 int m2tts_rowshift_probe(const float* A, const float* Bm, float* D, int rows_total, int N, int K, int rowbytes,

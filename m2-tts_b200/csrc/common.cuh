@@ -193,6 +193,11 @@ size_t voc_conv_h_wblob_bytes(int C);
 int launch_voc_conv_h(const void* xh, long long x_plane, const float* w, const float* bias, void* wblob, const void* res_h,
                       long long res_plane, void* out_h, long long out_plane, float* out_cf, int Lp_out, int B, int C, int L, int act,
                       int stage, cudaStream_t s);
+// ConvTranspose1d(CI, CI/2, 8, stride 4, padding 2) + leaky_relu on channel-last fp16 hi/lo planes (voc_up_h.cu)
+bool voc_up_h_eligible(int CI, int CO, int r);
+size_t voc_up_h_wblob_bytes(int CI);
+int launch_voc_up_h(const void* xh, long long x_plane, const float* w, const float* bias, void* wblob, void* out_h, long long out_plane,
+                    int B, int CI, int L, int stage, cudaStream_t s);
 // 16-bit split flavour (voc_fused_h.cu): input as fp16 hi/lo planes [2][B][L][2C]
 size_t voc_fused_h_wblob_bytes(int C);
 int launch_voc_stage_fused_h(const void* xh, long long x_plane, const float* up_w, const float* up_b, const float* w1, const float* b1,

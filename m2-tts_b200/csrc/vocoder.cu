@@ -566,6 +566,20 @@ extern "C" int m2tts_vocoder_forward(const m2tts_vocoder_weights* w, const float
     }
   }
 
+  // wide stages whose transposed convolution runs on channel-last fp16 hi/lo planes (voc_up_h.cu): the producer (input conv or
+  // the previous stage) writes planes and the stage's ResBlock kernels consume planes
+  bool up_h[4] = {false, false, false, false};
+  if (fused_h && conv_h_enabled()) {
+    int ci = C;
+    for (int j = 0; j < 4; ++j, ci /= 2) {
+      const int c = ci / 2;
+      const int dil = w->res_dilation[j] > 0 ? w->res_dilation[j] : 1;
+      const bool res_planes = voc_conv_h_eligible(c, dil) || (voc_res_h_eligible(c, dil) && j + 1 < 4 && path[j + 1] == P_FUSED);
+      const bool producer_ok = j == 0 ? (conv3_tc_eligible(M, C) && B <= 65535) : path[j - 1] == P_TC;
+      up_h[j] = path[j] == P_TC && voc_up_h_eligible(ci, c, rates[j]) && res_planes && producer_ok;
+    }
+  }
+
   // input conv: mel (strided) -> bufA [B,C,Lp] (row pitch padded to a multiple of 4 floats for the TMA tensor maps)
   int L = T, c_in = C;
   int Lp = path[0] == P_TC ? ((L + 3) & ~3) : L;
@@ -579,7 +593,7 @@ extern "C" int m2tts_vocoder_forward(const m2tts_vocoder_weights* w, const float
                 (long long)stride_t, bufC, M, T, Lp);
       xin = bufC;
     }
-    if ((rc = launch_conv3_tc(xin, Lp, w->in_w, in_wb, w->in_b, nullptr, 0, bufA, Lp, B, M, C, T, 1, 0, M2TTS_STAGE_VOC_IN, s))) return rc;
+    if ((rc = launch_conv3_tc(xin, Lp, w->in_w, in_wb, w->in_b, nullptr, 0, bufA, Lp, B, M, C, T, 1, 0, M2TTS_STAGE_VOC_IN, s, up_h[0] ? 2 : 0))) return rc;
   } else {
     ConvArgs a{mel, stride_b, stride_m, stride_t, in_wp, w->in_b, nullptr, bufA, M, C, T, 1, 0};
     a.y_pitch = Lp;
@@ -589,7 +603,7 @@ extern "C" int m2tts_vocoder_forward(const m2tts_vocoder_weights* w, const float
   for (int j = 0; j < 4; ++j) {
     const int r = rates[j], c = c_in / 2, Lo = L * r;
     const int dil = w->res_dilation[j] > 0 ? w->res_dilation[j] : 1;
-    const bool next_cl = j + 1 < 4 && path[j + 1] == P_FUSED;
+    const bool next_cl = j + 1 < 4 && (path[j + 1] == P_FUSED || up_h[j + 1]);      // the next stage reads channel-last (planes)
     if (path[j] == P_FUSED && fused_h) {
       // 16-bit split: bufA = fp16 hi/lo planes, channel-last [2][B][L][c_in] -> bufB planes [2][B][Lo][c] when the next
       // stage is fused too, plain fp32 channel-last otherwise, or straight to the waveform
@@ -614,7 +628,10 @@ extern "C" int m2tts_vocoder_forward(const m2tts_vocoder_weights* w, const float
     } else if (path[j] == P_TC && fused_h && next_cl && voc_res_h_eligible(c, dil)) {
       // C = 64: the upsampling tap-GEMM writes fp16 hi/lo planes channel-last (bufB) and the whole ResBlock is ONE
       // 16-bit split kernel (bufB -> bufA planes): v = lrelu(conv1(u)) and the residual never travel through HBM
-      if ((rc = launch_convT_tc(bufA, Lp, w->up_w[j], upb[j], w->up_b[j], bufB, Lo, B, c_in, c, L, r, s, 2))) return rc;
+      if (up_h[j]) rc = launch_voc_up_h(bufA, (long long)B * L * c_in, w->up_w[j], w->up_b[j], upb[j], bufB, (long long)B * Lo * c, B, c_in, L,
+                                        M2TTS_STAGE_VOC_UP, s);
+      else rc = launch_convT_tc(bufA, Lp, w->up_w[j], upb[j], w->up_b[j], bufB, Lo, B, c_in, c, L, r, s, 2);
+      if (rc) return rc;
       if ((rc = launch_voc_res_h(bufB, (long long)B * Lo * c, w->res1_w[j], w->res1_b[j], w->res2_w[j], w->res2_b[j], r1b[j],
                                  bufA, (long long)B * Lo * c, nullptr, B, c, Lo, M2TTS_STAGE_VOC_RES1, s))) return rc;
       Lp = Lo;
@@ -623,7 +640,10 @@ extern "C" int m2tts_vocoder_forward(const m2tts_vocoder_weights* w, const float
       // C = 128: the upsampling tap-GEMM writes fp16 hi/lo planes channel-last (bufB); the two convolutions of the ResBlock run
       // on those planes (no splitter, one accumulator for the three taps); conv2 writes what the next stage reads
       const long long plane = (long long)B * Lo * c;
-      if ((rc = launch_convT_tc(bufA, Lp, w->up_w[j], upb[j], w->up_b[j], bufB, Lo, B, c_in, c, L, r, s, 2))) return rc;
+      if (up_h[j]) rc = launch_voc_up_h(bufA, (long long)B * L * c_in, w->up_w[j], w->up_b[j], upb[j], bufB, plane, B, c_in, L,
+                                        M2TTS_STAGE_VOC_UP, s);
+      else rc = launch_convT_tc(bufA, Lp, w->up_w[j], upb[j], w->up_b[j], bufB, Lo, B, c_in, c, L, r, s, 2);
+      if (rc) return rc;
       if ((rc = launch_voc_conv_h(bufB, plane, w->res1_w[j], w->res1_b[j], r1b[j], nullptr, 0, bufC, plane, nullptr, 0, B, c, Lo, 1,
                                   M2TTS_STAGE_VOC_RES1, s))) return rc;
       if ((rc = launch_voc_conv_h(bufC, plane, w->res2_w[j], w->res2_b[j], r2b[j], bufB, plane, next_cl ? (void*)bufA : nullptr, plane,

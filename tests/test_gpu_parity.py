@@ -456,6 +456,31 @@ def test_conv1d_k3_h_c128_matches_torch(L, B, act, res, out_cl):
     assert H.max_abs(y.cpu(), want) <= FP32_TOL, (L, B, act, res, out_cl)
 
 
+@pytest.mark.parametrize("CI,L,B", [(256, 1, 1), (256, 127, 2), (256, 128, 1), (256, 129, 3), (256, 3446, 2), (128, 1, 2), (128, 128, 2),
+                                    (128, 1000, 3), (128, 13784, 2)])
+def test_conv_transpose_x4_h_matches_torch(CI, L, B):
+    """One upsampling layer + leaky_relu of the wide vocoder stages (voc_up_h.cu, polyphase ConvTranspose1d on channel-last
+    16-bit split operands) against torch's conv_transpose1d (components.py:225-241): both shapes, lengths around the
+    128-row tile and the C3 lengths of stages 0 and 1."""
+    from models import _native as nat
+    import torch.nn.functional as F
+    lib = nat.lib()
+    CO = CI // 2
+    g = torch.Generator().manual_seed(13 * L + B + CI)
+    x = torch.randn(B, CI, L, generator=g)
+    w = torch.randn(CI, CO, 8, generator=g) * (1.0 / (2 * CI) ** 0.5)
+    b = torch.randn(CO, generator=g) * 0.3
+    want = F.leaky_relu(F.conv_transpose1d(x, w, b, stride=4, padding=2), 0.1).transpose(1, 2).contiguous()
+    xd, wd, bd = (t.to(DEV) for t in (x.transpose(1, 2).contiguous(), w, b))
+    y = torch.full(want.shape, float("nan"), device=DEV)
+    ws = torch.empty(lib.m2tts_conv_transpose_x4_h_workspace_bytes(B, CI, L), dtype=torch.uint8, device=DEV)
+    nat.check(lib.m2tts_conv_transpose_x4_h(xd.data_ptr(), wd.data_ptr(), bd.data_ptr(), y.data_ptr(), B, CI, L, ws.data_ptr(), ws.numel(), None),
+              "conv_transpose_x4_h")
+    torch.cuda.synchronize()
+    assert not torch.isnan(y).any(), "unwritten output rows"
+    assert H.max_abs(y.cpu(), want) <= FP32_TOL, (CI, L, B)
+
+
 @pytest.mark.parametrize("mode", [0, 1, 2])  # 0 = tensor cores (16-bit split fused stages), 1 = FFMA everywhere, 2 = tensor cores, TF32 split
 def test_vocoder_modes_both_meet_fp32_tolerance(mode):
     from models import _native as nat
