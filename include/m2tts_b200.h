@@ -278,6 +278,10 @@ size_t m2tts_conv_transpose_x4_h_workspace_bytes(int B, int CI, int L);
 int m2tts_conv_transpose_x4_h(const float* x, const float* w, const float* b, float* y, int B, int CI, int L,
                               void* workspace, size_t workspace_bytes, m2tts_stream_t stream);
 
+/* Bring-up only (tools/up_h_prof.py): switch parts of the upsampling kernel off for timing experiments
+ * (1 no stores, 2 no UMMAs, 4 no TMA loads; results are invalid while non-zero). */
+int m2tts_voc_up_h_set_debug(int mode);
+
 /* Bring-up probe (tests/rowshift_probe_run.py): K-major swizzled UMMA A operand whose descriptor start
  * address is moved by whole rows inside the swizzle pattern. */
 int m2tts_rowshift_probe(const float* A, const float* Bm, float* D, int rows_total, int N, int K, int rowbytes,

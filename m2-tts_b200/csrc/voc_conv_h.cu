@@ -8,7 +8,7 @@
 // start address) and therefore a plain thread-per-row epilogue.
 // Each CTA owns 32 output channels (weights resident: 48 KB) and strides over 128-row tiles; two input slots and two TMEM
 // accumulator buffers keep TMA, UMMA and epilogue of consecutive tiles overlapped.
-// Warp roles: 0 TMA producer | 1 UMMA issuer (warp-collective) | 2-5 epilogue (thread = row).
+// Warp roles: 0 TMA producer | 1 UMMA issuer (warp-collective) | 2-9 two epilogue warpgroups (thread = row, 16 channels).
 #include "conv_tc.cuh"
 #include "attention_tc.cuh"
 #include <cuda_fp16.h>
@@ -40,7 +40,8 @@ constexpr uint32_t CH_OFF_W = 2 * CH_XSLOT;
 constexpr uint32_t CH_OFF_CONST = CH_OFF_W + CH_WBYTES;
 constexpr uint32_t CH_OFF_BAR = CH_OFF_CONST + 256;
 constexpr uint32_t CH_TOTAL = CH_OFF_BAR + 128 + 1024;
-constexpr int CH_THREADS = 64 + 128;
+constexpr int CH_G = CH_NT / 16;                     // epilogue warpgroups, 16 channels each
+constexpr int CH_THREADS = 64 + 128 * CH_G;
 
 __device__ __forceinline__ void ch_tma_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
   asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
@@ -72,7 +73,7 @@ voc_conv_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const ConvHArgs a,
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
       ct_mbar_init(bar_xf + 8 * s, 1); ct_mbar_init(bar_xe + 8 * s, 1);
-      ct_mbar_init(bar_cf + 8 * s, 1); ct_mbar_init(bar_ce + 8 * s, 4);
+      ct_mbar_init(bar_cf + 8 * s, 1); ct_mbar_init(bar_ce + 8 * s, 4 * CH_G);
     }
     ct_mbar_init(bar_w, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -134,22 +135,25 @@ voc_conv_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const ConvHArgs a,
       ct_commit_w(bar_xe + 8 * slot);
     }
   } else {
-    // ===== epilogue: thread m = output row of the tile =====
+    // ===== epilogue warpgroup eg: thread m = output row of the tile, channels [16 eg, 16 eg + 16) =====
+    // (two warpgroups: one warp per scheduler cannot hide the latency of its own dependent instructions)
+    const int eg = (warp - 2) >> 2;
     const int qtr = warp & 3;
     const int m = qtr * 32 + lane;
     const uint32_t t_lane = tmem_base + ((uint32_t)(qtr * 32) << 16);
+    const float* bs = bias_s + eg * 16;
     int it = 0;
     for (int g = first; g < a.total_tiles; g += cpg, ++it) {
       const int slot = it & 1, use = it >> 1;
       const int b = g / a.tiles_per_utt, k = g % a.tiles_per_utt;
       const int t = k * CH_NOUT + m;
       const bool valid = t < a.L;
-      const size_t o = ((size_t)b * a.L + t) * CH_C + co0;
-      // residual planes of this row (64 B + 64 B): requested before the accumulator wait
-      uint4 rh[4], rl[4];
+      const size_t o = ((size_t)b * a.L + t) * CH_C + co0 + eg * 16;
+      // residual planes of this row (32 B + 32 B): requested before the accumulator wait
+      uint4 rh[2], rl[2];
       if (a.res_h != nullptr && valid) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < 2; ++j) {
           rh[j] = __ldg(reinterpret_cast<const uint4*>(a.res_h + o) + j);
           rl[j] = __ldg(reinterpret_cast<const uint4*>(a.res_h + a.res_plane + o) + j);
         }
@@ -157,26 +161,24 @@ voc_conv_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const ConvHArgs a,
       ct_wait(bar_cf + 8 * slot, (uint32_t)(use & 1), dbg, 9, it);
       __syncwarp();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      uint32_t vm[32], vc[32];
-      ct_ld16(t_lane + (uint32_t)(slot * 64), vm);
-      ct_ld16(t_lane + (uint32_t)(slot * 64 + 16), vm + 16);
-      ct_ld16(t_lane + (uint32_t)(slot * 64 + 32), vc);
-      ct_ld16(t_lane + (uint32_t)(slot * 64 + 48), vc + 16);
+      uint32_t vm[16], vc[16];
+      ct_ld16(t_lane + (uint32_t)(slot * 64 + eg * 16), vm);
+      ct_ld16(t_lane + (uint32_t)(slot * 64 + CH_NT + eg * 16), vc);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) ct_arrive(bar_ce + 8 * slot);
       if (!valid) continue;
-      float y[32];
+      float y[16];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float x = __uint_as_float(vm[j]) + __uint_as_float(vc[j]) + bias_s[j];
+      for (int j = 0; j < 16; ++j) {
+        float x = __uint_as_float(vm[j]) + __uint_as_float(vc[j]) + bs[j];
         if (a.act == 1) x = x > 0.f ? x : 0.1f * x;
         y[j] = x;
       }
       if (a.res_h != nullptr) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < 2; ++j) {
           const uint32_t h[4] = {rh[j].x, rh[j].y, rh[j].z, rh[j].w}, l[4] = {rl[j].x, rl[j].y, rl[j].z, rl[j].w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
@@ -188,7 +190,7 @@ voc_conv_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const ConvHArgs a,
       }
       if (a.out_h != nullptr) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < 2; ++j) {
           uint32_t hw[4], lw[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
@@ -203,9 +205,9 @@ voc_conv_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const ConvHArgs a,
           *(reinterpret_cast<uint4*>(a.out_h + a.out_plane + o) + j) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
         }
       } else {
-        float* op = a.out_cf + ((size_t)b * CH_C + co0) * a.Lp_out + t;     // channel-first: coalesced across the warp's rows
+        float* op = a.out_cf + ((size_t)b * CH_C + co0 + eg * 16) * a.Lp_out + t;     // channel-first: coalesced across the warp's rows
 #pragma unroll
-        for (int j = 0; j < 32; ++j) op[(size_t)j * a.Lp_out] = y[j];
+        for (int j = 0; j < 16; ++j) op[(size_t)j * a.Lp_out] = y[j];
       }
     }
   }

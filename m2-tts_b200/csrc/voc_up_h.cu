@@ -5,9 +5,10 @@
 // so for one phase p the stage is a GEMM over the input rows with two row-shifted A operands (a shift moves the start
 // address of the K-major swizzled descriptor by whole rows) and ONE accumulator. Each CTA owns one (phase, COT output
 // channels) pair with its weights resident in shared memory (64 KB for both shapes) and strides over 128-row tiles of
-// the input; the input tile streams through a 4-stage ring of 64-channel k-blocks (hi + lo plane per stage).
+// the input; the input tile streams through a 3- or 4-stage ring of 64-channel k-blocks (hi + lo plane per stage); the output tile
+// leaves through a swizzled staging buffer and two TMA stores (one per plane).
 //   x : planes [2][B][L][CI] (the previous kernel wrote them)      y : planes [2][B][4L][CI/2]
-// Warp roles: 0 TMA producer | 1 UMMA issuer (warp-collective) | 2-5 epilogue (thread = input row q).
+// Warp roles: 0 TMA producer | 1 UMMA issuer (warp-collective) | 2.. epilogue warpgroups (thread = input row q, 16 channels).
 #include "conv_tc.cuh"
 #include "attention_tc.cuh"
 #include <cuda_fp16.h>
@@ -21,21 +22,25 @@ struct UpHArgs {
   const __half* wblob;                   // [n_tile][tap][k-block][hi rows ; lo rows][64] swizzled image
   const float* bias;
   __half* out_h; long long out_plane;
+  int dbg_mode;                          // bring-up timing experiments: 1 no stores, 2 no UMMAs, 4 no TMA loads (results invalid)
 };
 
 template <int CI, int COT>
 struct UhCfg {
-  static constexpr int CO = CI / 2, KB = CI / 64, NST = 4;
+  static constexpr int CO = CI / 2, KB = CI / 64, NST = COT == 64 ? 3 : 4;
   static constexpr int XR = 136, NQ = 128;
   static constexpr uint32_t XPL = XR * 128;                 // one plane of one k-block
   static constexpr uint32_t STAGE = 2 * XPL;
   static constexpr uint32_t WKB = 2 * COT * 128;            // [hi rows ; lo rows] of one (tap, k-block)
   static constexpr uint32_t WBYTES = 2 * KB * WKB;
   static constexpr uint32_t OFF_W = NST * STAGE;
-  static constexpr uint32_t OFF_CONST = OFF_W + WBYTES;
+  static constexpr uint32_t OPL = 128 * COT * 2;            // output staging: one plane of one tile, rows of COT halves (swizzled)
+  static constexpr uint32_t OFF_STG = OFF_W + WBYTES;
+  static constexpr uint32_t OFF_CONST = OFF_STG + 2 * OPL;
   static constexpr uint32_t OFF_BAR = OFF_CONST + 256;
   static constexpr uint32_t TOTAL = OFF_BAR + 256 + 1024;
-  static constexpr int THREADS = 64 + 128;
+  static constexpr int G = COT / 16;                        // epilogue warpgroups, 16 channels each
+  static constexpr int THREADS = 64 + 128 * G;
   static constexpr uint32_t TMEM_COLS = 4 * COT;            // two accumulator buffers of (main | corr)
   static_assert(TOTAL <= 227 * 1024, "voc_up_h: shared memory");
   static_assert(COT == 32 || COT == 64, "voc_up_h: channel tile");
@@ -56,7 +61,7 @@ __device__ __forceinline__ void uh_mma_w(uint32_t d, uint64_t ad, uint64_t bd, u
 
 template <int CI, int COT>
 __global__ void __launch_bounds__(UhCfg<CI, COT>::THREADS, 1)
-voc_up_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const UpHArgs a, int* dbg) {
+voc_up_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_y, const UpHArgs a, int* dbg) {
   using K = UhCfg<CI, COT>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (ct_smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -72,10 +77,11 @@ voc_up_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const UpHArgs a, int
 
   if (tid == 0) {
     for (int s = 0; s < K::NST; ++s) { ct_mbar_init(bar_f + 8 * s, 1); ct_mbar_init(bar_e + 8 * s, 1); }
-    for (int s = 0; s < 2; ++s) { ct_mbar_init(bar_cf + 8 * s, 1); ct_mbar_init(bar_ce + 8 * s, 4); }
+    for (int s = 0; s < 2; ++s) { ct_mbar_init(bar_cf + 8 * s, 1); ct_mbar_init(bar_ce + 8 * s, 4 * K::G); }
     ct_mbar_init(bar_w, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_x) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_y) : "memory");
   }
   if (tid < COT) bias_s[tid] = a.bias[co0 + tid];
   if (warp == 0) {
@@ -100,6 +106,7 @@ voc_up_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const UpHArgs a, int
         for (int kb = 0; kb < K::KB; ++kb, ++u) {
           const int st = u % K::NST, use = u / K::NST;
           if (use > 0) ct_wait(bar_e + 8 * st, (uint32_t)((use - 1) & 1), dbg, 1, u);
+          if (a.dbg_mode & 4) { ct_arrive(bar_f + 8 * st); continue; }
           ct_expect_tx(bar_f + 8 * st, K::STAGE);
           const uint32_t dst = sbase + (uint32_t)st * K::STAGE;
           uh_tma_4d(dst, &tmap_x, kb * 64, q0 - 1, b, 0, bar_f + 8 * st);
@@ -123,6 +130,7 @@ voc_up_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const UpHArgs a, int
         ct_wait(bar_f + 8 * st, (uint32_t)(use & 1), dbg, 3, u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t sX = sbase + (uint32_t)st * K::STAGE;
+        if (!(a.dbg_mode & 2))
 #pragma unroll
         for (int tap = 0; tap < 2; ++tap)
 #pragma unroll
@@ -137,58 +145,75 @@ voc_up_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const UpHArgs a, int
       ct_commit_w(bar_cf + 8 * ab);
     }
   } else {
-    // ===== epilogue: thread m = input row of the tile -> output row 4 (q0 + m) + phase =====
+    // ===== epilogue warpgroup eg: thread m = input row of the tile -> output row 4 (q0 + m) + phase, channels [16 eg, 16 eg + 16) =====
+    // (several warpgroups: one warp per scheduler cannot hide the latency of its own dependent instructions)
+    const int eg = (warp - 2) >> 2;
     const int qtr = warp & 3;
     const int m = qtr * 32 + lane;
     const uint32_t t_lane = tmem_base + ((uint32_t)(qtr * 32) << 16);
-    const int Lo = 4 * a.L;
+    const float* bs = bias_s + eg * 16;
+    // the tile's output goes through a swizzled staging buffer and leaves as two TMA stores (whole 2 COT-byte row pieces
+    // at a row stride of 4 CO halves: thread-per-row global stores would touch 32 lines per instruction)
+    uint8_t* stg = gbase + K::OFF_STG;
+    constexpr uint32_t ORB = COT * 2;
+    const uint32_t sw = ORB == 128 ? (uint32_t)(m & 7) : (uint32_t)((m >> 1) & 3);
+    const bool leader = warp == 2 && lane == 0;
     int it = 0;
     for (int g = first; g < a.total_tiles; g += cpg, ++it) {
       const int ab = it & 1, ause = it >> 1;
-      const int b = g / a.tiles_per_utt, q = (g % a.tiles_per_utt) * K::NQ + m;
-      const bool valid = q < a.L;
+      const int b = g / a.tiles_per_utt, q0 = (g % a.tiles_per_utt) * K::NQ;
       ct_wait(bar_cf + 8 * ab, (uint32_t)(ause & 1), dbg, 9, it);
       __syncwarp();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const size_t o = ((size_t)b * Lo + (size_t)4 * q + ph) * K::CO + co0;
+      uint32_t vm[16], vc[16];
+      const uint32_t col = (uint32_t)(ab * 2 * COT + eg * 16);
+      ct_ld16(t_lane + col, vm);
+      ct_ld16(t_lane + col + COT, vc);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) ct_arrive(bar_ce + 8 * ab);
+      uint4 hv[2], lv[2];
 #pragma unroll
-      for (int h = 0; h < COT / 32; ++h) {
-        uint32_t vm[32], vc[32];
-        const uint32_t col = (uint32_t)(ab * 2 * COT + h * 32);
-        ct_ld16(t_lane + col, vm);
-        ct_ld16(t_lane + col + 16, vm + 16);
-        ct_ld16(t_lane + col + COT, vc);
-        ct_ld16(t_lane + col + COT + 16, vc + 16);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (h == COT / 32 - 1) {
-          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          __syncwarp();
-          if (lane == 0) ct_arrive(bar_ce + 8 * ab);
+      for (int j = 0; j < 2; ++j) {
+        uint32_t hw[4], lw[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int c = 8 * j + 2 * e;
+          float y0 = __uint_as_float(vm[c]) + __uint_as_float(vc[c]) + bs[c];
+          float y1 = __uint_as_float(vm[c + 1]) + __uint_as_float(vc[c + 1]) + bs[c + 1];
+          y0 = y0 > 0.f ? y0 : 0.1f * y0;
+          y1 = y1 > 0.f ? y1 : 0.1f * y1;
+          y0 = fminf(fmaxf(y0, -65000.f), 65000.f); y1 = fminf(fmaxf(y1, -65000.f), 65000.f);
+          const __half2 hh = __floats2half2_rn(y0, y1);
+          const float2 hf = __half22float2(hh);
+          const __half2 ll = __floats2half2_rn(y0 - hf.x, y1 - hf.y);
+          hw[e] = *reinterpret_cast<const uint32_t*>(&hh);
+          lw[e] = *reinterpret_cast<const uint32_t*>(&ll);
         }
-        if (valid) {
+        hv[j] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        lv[j] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+      }
+      if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the previous tile's stores have read the staging buffer
+      asm volatile("bar.sync 1, %0;" ::"n"(128 * K::G) : "memory");
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint32_t hw[4], lw[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int c = 8 * j + 2 * e;
-              float y0 = __uint_as_float(vm[c]) + __uint_as_float(vc[c]) + bias_s[h * 32 + c];
-              float y1 = __uint_as_float(vm[c + 1]) + __uint_as_float(vc[c + 1]) + bias_s[h * 32 + c + 1];
-              y0 = y0 > 0.f ? y0 : 0.1f * y0;
-              y1 = y1 > 0.f ? y1 : 0.1f * y1;
-              y0 = fminf(fmaxf(y0, -65000.f), 65000.f); y1 = fminf(fmaxf(y1, -65000.f), 65000.f);
-              const __half2 hh = __floats2half2_rn(y0, y1);
-              const float2 hf = __half22float2(hh);
-              const __half2 ll = __floats2half2_rn(y0 - hf.x, y1 - hf.y);
-              hw[e] = *reinterpret_cast<const uint32_t*>(&hh);
-              lw[e] = *reinterpret_cast<const uint32_t*>(&ll);
-            }
-            *(reinterpret_cast<uint4*>(a.out_h + o + h * 32) + j) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-            *(reinterpret_cast<uint4*>(a.out_h + a.out_plane + o + h * 32) + j) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-          }
-        }
+      for (int j = 0; j < 2; ++j) {
+        const uint32_t off = (uint32_t)m * ORB + ((((uint32_t)(eg * 2 + j)) ^ sw) << 4);
+        *reinterpret_cast<uint4*>(stg + off) = hv[j];
+        *reinterpret_cast<uint4*>(stg + K::OPL + off) = lv[j];
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("bar.sync 2, %0;" ::"n"(128 * K::G) : "memory");
+      if (leader && !(a.dbg_mode & 1)) {
+        const uint32_t s0 = sbase + K::OFF_STG;
+        asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4, %5}], [%6];"
+                     ::"l"(&tmap_y), "r"(co0), "r"(ph), "r"(q0), "r"(b), "r"(0), "r"(s0) : "memory");
+        asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4, %5}], [%6];"
+                     ::"l"(&tmap_y), "r"(co0), "r"(ph), "r"(q0), "r"(b), "r"(1), "r"(s0 + K::OPL) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
     }
+    if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -236,18 +261,19 @@ static EncodeTiledFn9 uh_encode_fn() {
   return fn;
 }
 
+static int g_uh_dbg = 0;
 bool voc_up_h_eligible(int CI, int CO, int r) { return r == 4 && CO * 2 == CI && (CI == 256 || CI == 128); }
 size_t voc_up_h_wblob_bytes(int CI) { return (size_t)8 * CI * (CI / 2) * 2 * 2; }      // every weight once, hi + lo
 
 template <int CI, int COT>
-static int launch_up_h_t(const CUtensorMap& tmap, UpHArgs a, int stage, cudaStream_t s) {
+static int launch_up_h_t(const CUtensorMap& tmap, const CUtensorMap& tmap_y, UpHArgs a, int stage, cudaStream_t s) {
   using K = UhCfg<CI, COT>;
   a.co_tiles = K::CO / COT;
   a.n_tiles = 4 * a.co_tiles;
   int cpg = kNumSMs / a.n_tiles;
   if (cpg > a.total_tiles) cpg = a.total_tiles;
   M2_CUDA_OK(allow_smem(voc_up_h_kernel<CI, COT>, K::TOTAL));
-  M2_LAUNCH(stage, (voc_up_h_kernel<CI, COT>), cpg * a.n_tiles, K::THREADS, K::TOTAL, s, tmap, a, debug_words_device());
+  M2_LAUNCH(stage, (voc_up_h_kernel<CI, COT>), cpg * a.n_tiles, K::THREADS, K::TOTAL, s, tmap, tmap_y, a, debug_words_device());
   return M2TTS_OK;
 }
 
@@ -278,12 +304,31 @@ int launch_voc_up_h(const void* xh, long long x_plane, const float* w, const flo
   a.B = B; a.L = L; a.wblob = (const __half*)wblob; a.bias = bias; a.out_h = (__half*)out_h; a.out_plane = out_plane;
   a.tiles_per_utt = ceil_div(L, 128);
   a.total_tiles = B * a.tiles_per_utt;
-  return CI == 256 ? launch_up_h_t<256, 32>(tmap, a, stage, s) : launch_up_h_t<128, 64>(tmap, a, stage, s);
+  a.dbg_mode = g_uh_dbg;
+  // output planes [2][B][4L][CO] seen as {CO, phase, q, B, plane}: one store = one phase of 128 input rows, COT channels
+  CUtensorMap tmap_y;
+  {
+    const int CO = CI / 2;
+    const cuuint64_t ydims[5] = {(cuuint64_t)CO, 4, (cuuint64_t)L, (cuuint64_t)B, 2};
+    const cuuint64_t ystr[4] = {(cuuint64_t)CO * 2, (cuuint64_t)4 * CO * 2, (cuuint64_t)4 * L * CO * 2, (cuuint64_t)out_plane * 2};
+    const cuuint32_t ybox[5] = {(cuuint32_t)COT, 1u, 128u, 1u, 1u};
+    const cuuint32_t yes[5] = {1, 1, 1, 1, 1};
+    const CUresult ry = enc(&tmap_y, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, out_h, ydims, ystr, ybox, yes, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            COT == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    M2_REQUIRE(ry == CUDA_SUCCESS, M2TTS_E_CUDA, "voc_up_h: cuTensorMapEncodeTiled (output) failed (%d)", (int)ry);
+  }
+  return CI == 256 ? launch_up_h_t<256, 32>(tmap, tmap_y, a, stage, s) : launch_up_h_t<128, 64>(tmap, tmap_y, a, stage, s);
 }
+
+void voc_up_h_set_debug(int m) { g_uh_dbg = m; }
 
 }  // namespace m2
 
 using namespace m2;
+
+// bring-up only (tools/up_h_prof.py): timing experiments with parts of the kernel switched off; results are invalid while set
+extern "C" int m2tts_voc_up_h_set_debug(int mode) { voc_up_h_set_debug(mode); return M2TTS_OK; }
 
 namespace {
 __global__ void uh_join_planes_kernel(const __half* planes, long long n, float* y) {
@@ -313,6 +358,6 @@ extern "C" int m2tts_conv_transpose_x4_h(const float* x, const float* w, const f
   int rc = launch_split_planes_h(x, xp, n_in, s);
   if (rc) return rc;
   if ((rc = launch_voc_up_h(xp, n_in, w, b, wblob, yp, n_out, B, CI, L, M2TTS_STAGE_VOC_UP, s))) return rc;
-  M2_LAUNCH(M2TTS_STAGE_VOC_UP, uh_join_planes_kernel, 1184, 256, 0, s, yp, n_out, y);
+  M2_LAUNCH(M2TTS_STAGE_PACK, uh_join_planes_kernel, 1184, 256, 0, s, yp, n_out, y);
   return M2TTS_OK;
 }

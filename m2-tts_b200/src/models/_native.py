@@ -93,6 +93,7 @@ _SIGNATURES = {
     "m2tts_conv1d_k3_h": (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 5 + [C.c_void_p, C.c_size_t, C.c_void_p]),
     "m2tts_conv_transpose_x4_h_workspace_bytes": (C.c_size_t, [C.c_int] * 3),
     "m2tts_conv_transpose_x4_h": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 3 + [C.c_void_p, C.c_size_t, C.c_void_p]),
+    "m2tts_voc_up_h_set_debug": (C.c_int, [C.c_int]),
     "m2tts_resblock_fused_h_workspace_bytes": (C.c_size_t, [C.c_int] * 3),
     "m2tts_resblock_fused_h": (C.c_int, [C.c_void_p] * 6 + [C.c_int] * 3 + [C.c_void_p, C.c_size_t, C.c_void_p]),
     "m2tts_tapgemm_set_prof": (C.c_int, [C.c_void_p]),
