@@ -7,6 +7,8 @@
 //   mode 2: A from TMEM                         B K-major 128B-swizzle    (attention P V)
 //   mode 3: A K-major 64B-swizzle (smem)       B K-major no-swizzle      (channel-last convolutions, C = 16)
 //   mode 4: A K-major 128B-swizzle (smem)      B K-major 128B-swizzle    (linear layers)
+//   mode 5: as mode 4 with kind::f16 (K = 16)                              (16-bit split kernels)
+//   mode 6: as mode 5 with the A start address moved by one 128-byte row  (row-shifted conv taps)
 #include "common.cuh"
 
 namespace m2 {
@@ -39,7 +41,9 @@ __global__ void __launch_bounds__(128) mma_bench_kernel(int mode, int N, int n, 
   uint32_t tmem;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(slot));
   const uint32_t a_mn = mode == 1 ? 1u : 0u, b_mn = mode == 1 ? 1u : 0u;
-  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (a_mn << 15) | (b_mn << 16) | ((uint32_t)(N >> 3) << 17) | (8u << 24);
+  const bool f16 = mode >= 5;
+  const uint32_t idesc = f16 ? ((1u << 4) | ((uint32_t)(N >> 3) << 17) | (8u << 24))
+                             : ((1u << 4) | (2u << 7) | (2u << 10) | (a_mn << 15) | (b_mn << 16) | ((uint32_t)(N >> 3) << 17) | (8u << 24));
   long long t0 = 0, t1 = 0;
   bool issuer = false;
   if (warp == 0 && elect == 2) {
@@ -47,7 +51,8 @@ __global__ void __launch_bounds__(128) mma_bench_kernel(int mode, int N, int n, 
     uint64_t ad[4], bd[4];
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
-      if (mode == 0 || mode == 4) ad[ks] = mb_desc(sA + ks * 32u, 16u, 1024u, 2u);
+      if (mode == 0 || mode == 4 || mode == 5) ad[ks] = mb_desc(sA + ks * 32u, 16u, 1024u, 2u);
+      else if (mode == 6) ad[ks] = mb_desc(sA + 128u * (1u + (ks & 1)) + ks * 32u, 16u, 1024u, 2u);
       else if (mode == 1) ad[ks] = mb_desc(sA + ks * 1024u, 6144u, 512u, 1u);
       else ad[ks] = mb_desc(sA + (ks & 1) * 32u, 16u, 512u, 4u);
       if (mode == 0 || mode == 3) bd[ks] = mb_desc(sB + (ks >> 1) * (uint32_t)(N * 64) + (ks & 1) * 256u, 128u, 512u, 0u);
@@ -63,6 +68,14 @@ __global__ void __launch_bounds__(128) mma_bench_kernel(int mode, int N, int n, 
           asm volatile("{\n\t.reg .pred p, q;\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
                        ::"r"((ks & 1) ? d1 : d0), "r"(tmem + 256u + (uint32_t)ks * 8u), "l"(bd[ks]), "r"(idesc), "r"((uint32_t)(i > 0)) : "memory");
+      }
+    } else if (f16) {
+      for (int i = 0; i < n; i += 4) {
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          asm volatile("{\n\t.reg .pred p, q;\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                       "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                       ::"r"((ks & 1) ? d1 : d0), "l"(ad[ks]), "l"(bd[ks]), "r"(idesc), "r"((uint32_t)(i > 0)) : "memory");
       }
     } else {
     for (int i = 0; i < n; i += 4) {
@@ -152,7 +165,7 @@ __global__ void __launch_bounds__(128) mma_bench_kernel(int mode, int N, int n, 
 using namespace m2;
 
 extern "C" int m2tts_mma_bench(int mode, int N, int n, int nacc, int elect, long long* out_dev, m2tts_stream_t stream) {
-  M2_REQUIRE(out_dev && mode >= 0 && mode <= 4 && N >= 16 && N <= 256 && N % 16 == 0 && n > 0 && nacc >= 1 && nacc * N <= 256,
+  M2_REQUIRE(out_dev && mode >= 0 && mode <= 6 && N >= 16 && N <= 256 && N % 16 == 0 && n > 0 && nacc >= 1 && nacc * N <= 256,
              M2TTS_E_BADSHAPE, "mma_bench: bad arguments");
   const size_t smem = 128 * 1024 + 1024 + 64;
   M2_CUDA_OK(allow_smem(mma_bench_kernel, smem));

@@ -26,6 +26,7 @@ struct FusedHArgs {
   const float* out_w; const float* out_b;   // FINAL: Conv1d(C,1,3) weight [1][C][3] and bias
   __half* out_h;                         // non-final: fp16 hi/lo planes [2][B][L_out][C]
   float* out_f;                          // non-final alternative: fp32 channel-last [B][L_out][C]; FINAL: audio [B][L_out]
+  int dbg_nostore;                       // bring-up timing experiment (M2TTS_DBG_NOSTORE=1): skip the plane stores, results invalid
   long long out_plane;                   // elements between the hi and the lo plane of out_h
 };
 
@@ -399,8 +400,8 @@ voc_stage_fused_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const Fused
                 for (int j8 = 0; j8 < 2; ++j8) {
                   uint4 hi, lo;
                   fh_split8(y + 8 * j8, hi, lo);
-                  *reinterpret_cast<uint4*>(a.out_h + o + 8 * j8) = hi;
-                  *reinterpret_cast<uint4*>(a.out_h + a.out_plane + o + 8 * j8) = lo;
+                  if (!a.dbg_nostore) *reinterpret_cast<uint4*>(a.out_h + o + 8 * j8) = hi;
+                  if (!a.dbg_nostore) *reinterpret_cast<uint4*>(a.out_h + a.out_plane + o + 8 * j8) = lo;
                 }
               } else {                         // plain fp32 channel-last
                 float4* op = reinterpret_cast<float4*>(a.out_f + o);
@@ -562,6 +563,7 @@ int launch_voc_stage_fused_h(const void* xh, long long x_plane, const float* up_
   FusedHArgs a{};
   a.B = B; a.L_in = L_in; a.L_out = 2 * L_in; a.wblob = (const __half*)wblob; a.bias_up = up_b; a.bias1 = b1; a.bias2 = b2;
   a.out_w = out_w; a.out_b = out_b; a.out_h = (__half*)out_h; a.out_f = out_f; a.out_plane = out_plane;
+  { static int ns = -1; if (ns < 0) { const char* e = getenv("M2TTS_DBG_NOSTORE"); ns = (e && e[0] == '1') ? 1 : 0; } a.dbg_nostore = ns; }
   const bool fin = out_w != nullptr;
   if (fin) M2_REQUIRE(out_f != nullptr, M2TTS_E_NULLPTR, "voc_fused_h: the last stage writes fp32 audio");
   const __half* x = (const __half*)xh;

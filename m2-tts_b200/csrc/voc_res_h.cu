@@ -22,6 +22,7 @@ struct ResHArgs {
   const float* bias1; const float* bias2;
   __half* out_h; long long out_plane;    // fp16 hi/lo planes [2][B][L][C], or
   float* out_f;                          // fp32 channel-last [B][L][C]
+  int dbg_nostore;                       // bring-up timing experiment (M2TTS_DBG_NOSTORE=1): skip the plane stores, results invalid
 };
 
 template <int C>
@@ -249,8 +250,8 @@ voc_res_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const ResHArgs a, i
             for (int j8 = 0; j8 < 2; ++j8) {
               uint4 hi, lo;
               rh_split8(y + 8 * j8, hi, lo);
-              *reinterpret_cast<uint4*>(a.out_h + o + 8 * j8) = hi;
-              *reinterpret_cast<uint4*>(a.out_h + a.out_plane + o + 8 * j8) = lo;
+              if (!a.dbg_nostore) *reinterpret_cast<uint4*>(a.out_h + o + 8 * j8) = hi;
+              if (!a.dbg_nostore) *reinterpret_cast<uint4*>(a.out_h + a.out_plane + o + 8 * j8) = lo;
             }
           } else {
             float4* op = reinterpret_cast<float4*>(a.out_f + o);
@@ -332,7 +333,8 @@ int launch_voc_res_h(const void* uh, long long u_plane, const float* w1, const f
   M2_REQUIRE(r == CUDA_SUCCESS, M2TTS_E_CUDA, "voc_res_h: cuTensorMapEncodeTiled failed (%d)", (int)r);
   ResHArgs a{};
   a.B = B; a.L = L; a.wblob = (const __half*)wblob; a.bias1 = b1; a.bias2 = b2;
-  a.out_h = (__half*)out_h; a.out_plane = out_plane; a.out_f = out_f;
+  a.out_h = (__half*)out_h; a.out_plane = out_plane;
+  { static int ns = -1; if (ns < 0) { const char* e = getenv("M2TTS_DBG_NOSTORE"); ns = (e && e[0] == '1') ? 1 : 0; } a.dbg_nostore = ns; } a.out_f = out_f;
   a.tiles_per_utt = ceil_div(L, K::NOUT);
   a.total_tiles = B * a.tiles_per_utt;
   const int grid = a.total_tiles < kNumSMs ? a.total_tiles : kNumSMs;

@@ -8,9 +8,10 @@ from models import _native as nat
 lib = nat.lib()
 out = torch.zeros(2, dtype=torch.int64, device="cuda")
 names = {0: "A smem K-major SW128 / B K-major noswz", 1: "A,B smem MN-major SW128-32B", 2: "A TMEM / B K-major SW128",
-         3: "A smem K-major SW64 / B K-major noswz", 4: "A,B smem K-major SW128"}
+         3: "A smem K-major SW64 / B K-major noswz", 4: "A,B smem K-major SW128", 5: "kind::f16, A,B smem K-major SW128",
+         6: "kind::f16, A row-shifted, SW128"}
 n = 512
-for mode in (2, 4):
+for mode in ((int(sys.argv[1]),) if len(sys.argv) > 1 else (2, 4, 5, 6)):
     for N in (16, 32, 48, 64, 96, 128, 192, 256):
         for nacc, elect in ((1, 2),):
             if nacc * N > 256:
