@@ -252,7 +252,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     # ---- e2e: pinned host in -> pinned host out, copies inside the timed region. The caller-facing helper
     # (utils.host_pipeline.HostPipeline) chunks the utterance batch so the PCIe copies overlap compute. ----
     from utils.host_pipeline import HostPipeline
-    pipe = HostPipeline(dev, n_chunks=args.e2e_chunks)
+    pipe = HostPipeline(dev, n_chunks=args.e2e_chunks, edge=args.e2e_edge)
     for _ in range(2):
         pipe.run(step, x_host, audio_host)
         pipe.synchronize()
@@ -326,7 +326,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                 "config": workload_config(world), "clocks": clocks, "gpu_launches": launches,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4,
                         "d2h_bytes_per_step": audio_host.numel() * 4, "ms_per_step": e2e_ms / args.steps,
-                        "api": f"utils.host_pipeline.HostPipeline(n_chunks={args.e2e_chunks}).run(decoder+vocoder, pinned host in, pinned host out)"},
+                        "api": f"utils.host_pipeline.HostPipeline(n_chunks={args.e2e_chunks}, edge={args.e2e_edge}).run(decoder+vocoder, pinned host in, pinned host out)"},
                 "roofline": roof, "stage_roofline": stage_roofline, "stage_tflops": all_stage_tflops,
                 "stage_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in sorted(stage_ms.items(), key=lambda kv: -kv[1][0])},
                 "x_realtime_per_gpu": value / world}
@@ -399,6 +399,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--skip-cpu-baseline", action="store_true", help="profiling runs: omit the CPU leg")
     ap.add_argument("--e2e-chunks", type=int, default=3, help="utterance chunks of the host-to-host pipeline (1 = no overlap)")
+    ap.add_argument("--e2e-edge", type=float, default=1.0, help="relative size of the first and last chunk (their copies are the unhidden ones)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -78,7 +78,14 @@ attention_h_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__
   const uint32_t tmem_slot = bar_ve + 8 * AH_STAGES;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int q0 = blockIdx.x * (2 * TC_BQ), head = blockIdx.y, b = blockIdx.z;
+  // 1-D grid, longest first: all CTAs with two query tiles, then (odd tile count) the single-tile CTAs, which take about
+  // 0.6 of the time and fill the last wave
+  const int n_tiles_q = (L + TC_BQ - 1) / TC_BQ, npf = n_tiles_q >> 1, n_long = npf * nh * B;
+  int qx, bh;
+  if ((int)blockIdx.x < n_long) { bh = (int)blockIdx.x / npf; qx = (int)blockIdx.x % npf; }
+  else { bh = (int)blockIdx.x - n_long; qx = npf; }
+  const int q0 = qx * (2 * TC_BQ), head = bh % nh, b = bh / nh;
+  const int ntq = q0 + TC_BQ < L ? 2 : 1;
 
   int Leff = L;
   bool all_masked = false;
@@ -116,7 +123,7 @@ attention_h_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__
   if (warp == 0) {
     if (lane == 0) {
       // ===== loader =====
-      for (int x = 0; x < 2; ++x) {
+      for (int x = 0; x < ntq; ++x) {
         mbar_expect_tx(bar_qf + 8 * x, AhSmem<HD>::q_bytes);
         for (int h = 0; h < 2; ++h)
           for (int j = 0; j < 2; ++j)
@@ -167,7 +174,7 @@ attention_h_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__
     // prologue: the scores of key tiles 0 and 1 for both query tiles
     for (int t = 0; t < 2 && t < nkt; ++t) {
       mbar_wait(bar_kf + 8 * t, 0);
-      for (int x = 0; x < 2; ++x) {
+      for (int x = 0; x < ntq; ++x) {
         if (t == 0) mbar_wait(bar_qf + 8 * x, 0);
         tc_fence_after();
         issue_qk(x, t, t);
@@ -180,21 +187,22 @@ attention_h_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__
       const uint32_t par = (uint32_t)(t & 1);
 #pragma unroll
       for (int x = 0; x < 2; ++x) {
+        if (x >= ntq) break;
         mbar_wait(bar_pr + 8 * x, par);                         // P(x,t) is in TMEM (and O has been rescaled if needed)
         if (x == 0) mbar_wait(bar_vf + 8 * st, (uint32_t)((t / AH_STAGES) & 1));
         tc_fence_after();
         issue_pv(x, st, buf, t > 0 ? 1u : 0u);
         tc_commit_w(bar_pv + 8 * x);
-        if (x == 1) tc_commit_w(bar_ve + 8 * st);
+        if (x == ntq - 1) tc_commit_w(bar_ve + 8 * st);
         if (t + 2 < nkt) {                                      // score buffer `buf` is free again once PV(x,t) has read P
           if (x == 0) { mbar_wait(bar_kf + 8 * s2, (uint32_t)(((t + 2) / AH_STAGES) & 1)); tc_fence_after(); }
           issue_qk(x, s2, buf);
           tc_commit_w(bar_sf + 16 * x + 8 * buf);
-          if (x == 1) tc_commit_w(bar_ke + 8 * s2);
+          if (x == ntq - 1) tc_commit_w(bar_ke + 8 * s2);
         }
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && ((warp - 4) >> 2) < ntq) {
     // ===== softmax warpgroup of query tile x: thread = query row =====
     const int x = (warp - 4) >> 2;
     const int row = (warp & 3) * 32 + lane;
@@ -353,7 +361,7 @@ static int launch_ah_hd(const CUtensorMap& tmap, float* ctx, const int64_t* leng
                         __half* ctx_h) {
   const size_t smem = AhSmem<HD>::total;
   M2_CUDA_OK(allow_smem(attention_h_kernel<HD>, smem));
-  dim3 grid(ceil_div(L, 2 * TC_BQ), nh, B);
+  dim3 grid((unsigned)(ceil_div(L, 2 * TC_BQ) * nh * B), 1, 1);
   M2_LAUNCH(M2TTS_STAGE_ATTENTION, attention_h_kernel<HD>, grid, AH_THREADS, smem, s, tmap, ctx, lengths, B, L, nh, ctx_lo, ctx_h);
   return M2TTS_OK;
 }
