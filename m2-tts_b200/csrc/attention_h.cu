@@ -58,7 +58,7 @@ __device__ __forceinline__ void umma_f16_ts_w(uint32_t d_tmem, uint32_t a_tmem, 
 template <int HD>
 __global__ void __launch_bounds__(AH_THREADS, 1)
 attention_h_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__ ctx, const int64_t* __restrict__ lengths,
-                   int B, int L, int nh, float* __restrict__ ctx_lo, __half* __restrict__ ctx_h) {
+                   int B, int L, int nh, float* __restrict__ ctx_lo, __half* __restrict__ ctx_h, long long* __restrict__ prof) {
   static_assert(HD % 16 == 0 && HD >= 16 && HD <= 64, "16-bit split attention: head_dim in {16,32,48,64}");
   constexpr uint32_t BOX = AhSmem<HD>::box;
   constexpr int KSTEPS_D = HD / 16;
@@ -145,6 +145,7 @@ attention_h_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__
     }
   } else if (warp == 1) {
     // ===== UMMA issuer (whole warp, one elected lane issues) =====
+    const bool pr_on = prof != nullptr && blockIdx.x == 0;
     auto issue_qk = [&](int x, int st, int buf) {
       const uint32_t q = sQ + (uint32_t)x * AhSmem<HD>::q_bytes, k = sK + (uint32_t)st * AhSmem<HD>::kv_bytes;
       const uint32_t d = tmem_base + (uint32_t)x * AH_COL_TILE + AH_COL_S + (uint32_t)buf * 64u;
@@ -188,7 +189,9 @@ attention_h_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__
 #pragma unroll
       for (int x = 0; x < 2; ++x) {
         if (x >= ntq) break;
+        if (pr_on && lane == 0 && t >= 8 && t < 40) prof[384 + (t - 8) * 8 + 3 * x] = clock64();
         mbar_wait(bar_pr + 8 * x, par);                         // P(x,t) is in TMEM (and O has been rescaled if needed)
+        if (pr_on && lane == 0 && t >= 8 && t < 40) prof[384 + (t - 8) * 8 + 3 * x + 1] = clock64();
         if (x == 0) mbar_wait(bar_vf + 8 * st, (uint32_t)((t / AH_STAGES) & 1));
         tc_fence_after();
         issue_pv(x, st, buf, t > 0 ? 1u : 0u);
@@ -200,6 +203,7 @@ attention_h_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__
           tc_commit_w(bar_sf + 16 * x + 8 * buf);
           if (x == ntq - 1) tc_commit_w(bar_ke + 8 * s2);
         }
+        if (pr_on && lane == 0 && t >= 8 && t < 40) prof[384 + (t - 8) * 8 + 3 * x + 2] = clock64();
       }
     }
   } else if (warp >= 4 && ((warp - 4) >> 2) < ntq) {
@@ -208,15 +212,21 @@ attention_h_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__
     const int row = (warp & 3) * 32 + lane;
     const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)x * AH_COL_TILE;
     float m_ref = -INFINITY, l_run = 0.f;
+    const bool pw = prof != nullptr && blockIdx.x == 0 && x == 0 && row == 0;
     for (int t = 0; t < nkt; ++t) {
+      const bool pt = pw && t >= 8 && t < 40;
+      long long* pp = prof + (pt ? (t - 8) * 8 : 0);
       const uint32_t t_s = t_lane + AH_COL_S + (uint32_t)(t & 1) * 64u;     // this tile's score buffer (P goes over it)
+      if (pt) pp[0] = clock64();
       mbar_wait(bar_sf + 16 * x + 8 * (t & 1), (uint32_t)((t >> 1) & 1));
+      if (pt) pp[1] = clock64();
       __syncwarp();
       tc_fence_after();
       uint32_t sr[TC_BK];
 #pragma unroll
       for (int c = 0; c < TC_BK; c += 16) tmem_ld16(t_s + c, sr + c);
       tmem_wait_ld();
+      if (pt) pp[2] = clock64();
       const int kbase = t * TC_BK;
       if (all_masked || kbase + TC_BK > Leff) {
 #pragma unroll
@@ -256,6 +266,7 @@ attention_h_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__
           tmem_st16(t_lane + AH_COL_O + c, orr);
         }
       }
+      if (pt) pp[3] = clock64();
       float rs = 0.f;
 #pragma unroll
       for (int c = 0; c < TC_BK; c += 32) {        // 32 keys -> 16 packed columns of P_hi and of P_lo
@@ -275,8 +286,11 @@ attention_h_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__
         tmem_st16(t_s + AH_COL_PLO + (c >> 1), pl);
       }
       l_run += rs;
+      if (pt) pp[4] = clock64();
       tmem_wait_st();
+      if (pt) pp[5] = clock64();
       if (!pv_waited) mbar_wait(bar_pv + 8 * x, (uint32_t)((t - 1) & 1));
+      if (pt) pp[6] = clock64();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_pr + 8 * x) : "memory");
@@ -356,13 +370,15 @@ static EncodeTiledFnH ah_encode_fn() {
   return fn;
 }
 
+extern long long* g_ws_prof;      // attention_tc.cu (m2tts_attention_set_prof)
+
 template <int HD>
 static int launch_ah_hd(const CUtensorMap& tmap, float* ctx, const int64_t* lengths, int B, int L, int nh, cudaStream_t s, float* ctx_lo,
                         __half* ctx_h) {
   const size_t smem = AhSmem<HD>::total;
   M2_CUDA_OK(allow_smem(attention_h_kernel<HD>, smem));
   dim3 grid((unsigned)(ceil_div(L, 2 * TC_BQ) * nh * B), 1, 1);
-  M2_LAUNCH(M2TTS_STAGE_ATTENTION, attention_h_kernel<HD>, grid, AH_THREADS, smem, s, tmap, ctx, lengths, B, L, nh, ctx_lo, ctx_h);
+  M2_LAUNCH(M2TTS_STAGE_ATTENTION, attention_h_kernel<HD>, grid, AH_THREADS, smem, s, tmap, ctx, lengths, B, L, nh, ctx_lo, ctx_h, g_ws_prof);
   return M2TTS_OK;
 }
 

@@ -588,7 +588,7 @@ static int launch_tc_hd(const CUtensorMap& tmap_qk, const CUtensorMap& tmap_v, f
   return M2TTS_OK;
 }
 
-static long long* g_ws_prof = nullptr;
+long long* g_ws_prof = nullptr;      // shared with attention_h.cu
 template <int HD>
 static int launch_ws_hd(const CUtensorMap& tmap_qk, const CUtensorMap& tmap_v, float* ctx, const int64_t* lengths, int B, int L, int nh,
                         cudaStream_t s, float* ctx_lo) {
