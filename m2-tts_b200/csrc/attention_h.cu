@@ -104,7 +104,7 @@ attention_h_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__
       mbar_init(bar_pr + 8 * i, 4); mbar_init(bar_pv + 8 * i, 1);
     }
     for (int i = 0; i < AH_STAGES; ++i) {
-      mbar_init(bar_kf + 8 * i, 1); mbar_init(bar_ke + 8 * i, 1); mbar_init(bar_vf + 8 * i, 1); mbar_init(bar_ve + 8 * i, 1);
+      mbar_init(bar_kf + 8 * i, 1); mbar_init(bar_ke + 8 * i, (uint32_t)ntq); mbar_init(bar_vf + 8 * i, 1); mbar_init(bar_ve + 8 * i, (uint32_t)ntq);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
@@ -143,8 +143,9 @@ attention_h_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__
           tma_load_2d(sV + (uint32_t)st * AhSmem<HD>::kv_bytes + h * BOX, &tmap, t * TC_BK, (4 + h) * plane + row_q, bar_vf + 8 * st);
       }
     }
-  } else if (warp == 1) {
-    // ===== UMMA issuer (whole warp, one elected lane issues) =====
+  } else if ((warp == 1 || warp == 2) && warp - 1 < ntq) {
+    // ===== UMMA issuer of query tile x (whole warp, one elected lane issues) =====
+    const int x = warp - 1;
     const bool pr_on = prof != nullptr && blockIdx.x == 0;
     auto issue_qk = [&](int x, int st, int buf) {
       const uint32_t q = sQ + (uint32_t)x * AhSmem<HD>::q_bytes, k = sK + (uint32_t)st * AhSmem<HD>::kv_bytes;
@@ -172,39 +173,38 @@ attention_h_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__
       for (int ks = 0; ks < TC_BK / 16; ++ks)
         umma_f16_ts_w(tb + AH_COL_O, pb + AH_COL_PLO + ks * 8, umma_desc(v + ks * 32u, 16u, 1024u, 2u), IDESC_PV1, 1u);
     };
-    // prologue: the scores of key tiles 0 and 1 for both query tiles
+    // One issuer warp per query tile (warps 1 and 2 sit on different schedulers): an UMMA costs its issuer ~12 instructions
+    // (descriptor moves into uniform registers, elect), ~50 cycles next to two busy softmax warps, and a single issuer
+    // for both tiles was the critical path (tools/attn_prof.py: 1870 of 2355 cycles per key tile spent issuing).
+    // A K/V stage is free when BOTH issuers' UMMAs on it have completed (k_empty / v_empty count = tiles).
+    // prologue: the scores of key tiles 0 and 1
     for (int t = 0; t < 2 && t < nkt; ++t) {
       mbar_wait(bar_kf + 8 * t, 0);
-      for (int x = 0; x < ntq; ++x) {
-        if (t == 0) mbar_wait(bar_qf + 8 * x, 0);
-        tc_fence_after();
-        issue_qk(x, t, t);
-        tc_commit_w(bar_sf + 16 * x + 8 * t);
-      }
+      if (t == 0) mbar_wait(bar_qf + 8 * x, 0);
+      tc_fence_after();
+      issue_qk(x, t, t);
+      tc_commit_w(bar_sf + 16 * x + 8 * t);
       tc_commit_w(bar_ke + 8 * t);
     }
     for (int t = 0; t < nkt; ++t) {
       const int st = t % AH_STAGES, s2 = (t + 2) % AH_STAGES, buf = t & 1;
       const uint32_t par = (uint32_t)(t & 1);
-#pragma unroll
-      for (int x = 0; x < 2; ++x) {
-        if (x >= ntq) break;
-        if (pr_on && lane == 0 && t >= 8 && t < 40) prof[384 + (t - 8) * 8 + 3 * x] = clock64();
-        mbar_wait(bar_pr + 8 * x, par);                         // P(x,t) is in TMEM (and O has been rescaled if needed)
-        if (pr_on && lane == 0 && t >= 8 && t < 40) prof[384 + (t - 8) * 8 + 3 * x + 1] = clock64();
-        if (x == 0) mbar_wait(bar_vf + 8 * st, (uint32_t)((t / AH_STAGES) & 1));
+      if (pr_on && lane == 0 && t >= 8 && t < 40) prof[384 + (t - 8) * 8 + 3 * x] = clock64();
+      mbar_wait(bar_pr + 8 * x, par);                         // P(x,t) is in TMEM (and O has been rescaled if needed)
+      if (pr_on && lane == 0 && t >= 8 && t < 40) prof[384 + (t - 8) * 8 + 3 * x + 1] = clock64();
+      mbar_wait(bar_vf + 8 * st, (uint32_t)((t / AH_STAGES) & 1));
+      tc_fence_after();
+      issue_pv(x, st, buf, t > 0 ? 1u : 0u);
+      tc_commit_w(bar_pv + 8 * x);
+      tc_commit_w(bar_ve + 8 * st);
+      if (t + 2 < nkt) {                                      // score buffer `buf` is free again once PV(x,t) has read P
+        mbar_wait(bar_kf + 8 * s2, (uint32_t)(((t + 2) / AH_STAGES) & 1));
         tc_fence_after();
-        issue_pv(x, st, buf, t > 0 ? 1u : 0u);
-        tc_commit_w(bar_pv + 8 * x);
-        if (x == ntq - 1) tc_commit_w(bar_ve + 8 * st);
-        if (t + 2 < nkt) {                                      // score buffer `buf` is free again once PV(x,t) has read P
-          if (x == 0) { mbar_wait(bar_kf + 8 * s2, (uint32_t)(((t + 2) / AH_STAGES) & 1)); tc_fence_after(); }
-          issue_qk(x, s2, buf);
-          tc_commit_w(bar_sf + 16 * x + 8 * buf);
-          if (x == ntq - 1) tc_commit_w(bar_ke + 8 * s2);
-        }
-        if (pr_on && lane == 0 && t >= 8 && t < 40) prof[384 + (t - 8) * 8 + 3 * x + 2] = clock64();
+        issue_qk(x, s2, buf);
+        tc_commit_w(bar_sf + 16 * x + 8 * buf);
+        tc_commit_w(bar_ke + 8 * s2);
       }
+      if (pr_on && lane == 0 && t >= 8 && t < 40) prof[384 + (t - 8) * 8 + 3 * x + 2] = clock64();
     }
   } else if (warp >= 4 && ((warp - 4) >> 2) < ntq) {
     // ===== softmax warpgroup of query tile x: thread = query row =====
