@@ -6,9 +6,11 @@
 // (what the next upsampling tap-GEMM reads). Against the tap-GEMM kernel there is no splitter (the producer already
 // wrote the operand planes), K = 16 per UMMA, one accumulator for all taps (a tap is a row shift of the descriptor
 // start address) and therefore a plain thread-per-row epilogue.
-// Each CTA owns 32 output channels (weights resident: 48 KB) and strides over 128-row tiles; two input slots and two TMEM
-// accumulator buffers keep TMA, UMMA and epilogue of consecutive tiles overlapped.
-// Warp roles: 0 TMA producer | 1 UMMA issuer (warp-collective) | 2-9 two epilogue warpgroups (thread = row, 16 channels).
+// Each CTA owns 64 output channels (weights resident: 96 KB; a kind::f16 UMMA costs ~60 cycles in this kernel whatever its
+// N <= 128, so N is made as large as the weights allow) and strides over 128-row tiles; the input tile streams through a
+// 3-stage ring of 64-channel k-blocks (hi + lo plane per stage) and two TMEM accumulator buffers keep UMMA and epilogue
+// of consecutive tiles overlapped.
+// Warp roles: 0 TMA producer | 1 UMMA issuer (warp-collective) | 2-17 four epilogue warpgroups (thread = row, 16 channels).
 #include "conv_tc.cuh"
 #include "attention_tc.cuh"
 #include <cuda_fp16.h>
@@ -27,21 +29,23 @@ struct ConvHArgs {
   float* out_cf;                         // fp32 channel-first [B][C][Lp_out]
 };
 
-constexpr int CH_C = 128, CH_NT = 32;                // channels, output channels per CTA
+constexpr int CH_C = 128, CH_NT = 64;                // channels, output channels per CTA
 constexpr int CH_RB = 128;                           // bytes of one k-block row (64 halves)
 constexpr int CH_KB = CH_C / 64;                     // k-blocks per row
 constexpr int CH_XR = 136, CH_NOUT = 128;
 constexpr uint32_t CH_XKB = CH_XR * CH_RB;           // one k-block of one plane of the input tile
-constexpr uint32_t CH_XPL = CH_KB * CH_XKB;          // one plane
-constexpr uint32_t CH_XSLOT = 2 * CH_XPL;            // hi + lo
+constexpr uint32_t CH_STAGE = 2 * CH_XKB;            // ring stage: hi + lo plane of one k-block
+constexpr int CH_NST = 3;
 constexpr uint32_t CH_WKB = 2 * CH_NT * CH_RB;       // [hi rows ; lo rows] of one (tap, k-block)
-constexpr uint32_t CH_WBYTES = 3 * CH_KB * CH_WKB;   // 48 KB
-constexpr uint32_t CH_OFF_W = 2 * CH_XSLOT;
+constexpr uint32_t CH_WBYTES = 3 * CH_KB * CH_WKB;   // 96 KB
+constexpr uint32_t CH_OFF_W = CH_NST * CH_STAGE;
 constexpr uint32_t CH_OFF_CONST = CH_OFF_W + CH_WBYTES;
 constexpr uint32_t CH_OFF_BAR = CH_OFF_CONST + 256;
 constexpr uint32_t CH_TOTAL = CH_OFF_BAR + 128 + 1024;
 constexpr int CH_G = CH_NT / 16;                     // epilogue warpgroups, 16 channels each
 constexpr int CH_THREADS = 64 + 128 * CH_G;
+constexpr uint32_t CH_TMEM = 4 * CH_NT;               // two accumulator buffers of (main | corr)
+static_assert(CH_TOTAL <= 227 * 1024, "voc_conv_h: shared memory");
 
 __device__ __forceinline__ void ch_tma_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
   asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
@@ -62,8 +66,8 @@ voc_conv_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const ConvHArgs a,
   const uint32_t sbase = (ct_smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (sbase - ct_smem_u32(smem_raw));
   const uint32_t bars = sbase + CH_OFF_BAR;
-  // x_full[2] x_free[2] acc_full[2] acc_free[2] w_full
-  const uint32_t bar_xf = bars, bar_xe = bars + 16, bar_cf = bars + 32, bar_ce = bars + 48, bar_w = bars + 64, tmem_slot = bars + 72;
+  // x_full[3] x_free[3] acc_full[2] acc_free[2] w_full
+  const uint32_t bar_xf = bars, bar_xe = bars + 24, bar_cf = bars + 48, bar_ce = bars + 64, bar_w = bars + 80, tmem_slot = bars + 88;
   float* bias_s = reinterpret_cast<float*>(gbase + CH_OFF_CONST);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -71,10 +75,8 @@ voc_conv_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const ConvHArgs a,
   const int co0 = ntile * CH_NT;
 
   if (tid == 0) {
-    for (int s = 0; s < 2; ++s) {
-      ct_mbar_init(bar_xf + 8 * s, 1); ct_mbar_init(bar_xe + 8 * s, 1);
-      ct_mbar_init(bar_cf + 8 * s, 1); ct_mbar_init(bar_ce + 8 * s, 4 * CH_G);
-    }
+    for (int s = 0; s < CH_NST; ++s) { ct_mbar_init(bar_xf + 8 * s, 1); ct_mbar_init(bar_xe + 8 * s, 1); }
+    for (int s = 0; s < 2; ++s) { ct_mbar_init(bar_cf + 8 * s, 1); ct_mbar_init(bar_ce + 8 * s, 4 * CH_G); }
     ct_mbar_init(bar_w, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_x) : "memory");
@@ -82,7 +84,7 @@ voc_conv_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const ConvHArgs a,
   if (tid < CH_NT) bias_s[tid] = a.bias[co0 + tid];
   if (warp == 0) {
     __syncwarp();
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(128u) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(CH_TMEM) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -96,17 +98,18 @@ voc_conv_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const ConvHArgs a,
       ct_expect_tx(bar_w, CH_WBYTES);
       for (uint32_t off = 0; off < CH_WBYTES; off += 8192u)
         ct_bulk(sbase + CH_OFF_W + off, reinterpret_cast<const uint8_t*>(a.wblob) + (size_t)ntile * CH_WBYTES + off, 8192u, bar_w);
-      int it = 0;
-      for (int g = first; g < a.total_tiles; g += cpg, ++it) {
+      int u = 0;
+      for (int g = first; g < a.total_tiles; g += cpg) {
         const int b = g / a.tiles_per_utt, k = g % a.tiles_per_utt;
         const int Ts = k * CH_NOUT;                    // output row 0 of the tile; X row j <-> t = Ts - 1 + j
-        const int slot = it & 1, use = it >> 1;
-        if (use > 0) ct_wait(bar_xe + 8 * slot, (uint32_t)((use - 1) & 1), dbg, 1, it);
-        ct_expect_tx(bar_xf + 8 * slot, CH_XSLOT);
-        const uint32_t dst = sbase + (uint32_t)slot * CH_XSLOT;
-        for (int pl = 0; pl < 2; ++pl)
-          for (int kb = 0; kb < CH_KB; ++kb)
-            ch_tma_4d(dst + (uint32_t)pl * CH_XPL + (uint32_t)kb * CH_XKB, &tmap_x, kb * 64, Ts - 1, b, pl, bar_xf + 8 * slot);
+        for (int kb = 0; kb < CH_KB; ++kb, ++u) {
+          const int st = u % CH_NST, use = u / CH_NST;
+          if (use > 0) ct_wait(bar_xe + 8 * st, (uint32_t)((use - 1) & 1), dbg, 1, u);
+          ct_expect_tx(bar_xf + 8 * st, CH_STAGE);
+          const uint32_t dst = sbase + (uint32_t)st * CH_STAGE;
+          ch_tma_4d(dst, &tmap_x, kb * 64, Ts - 1, b, 0, bar_xf + 8 * st);
+          ch_tma_4d(dst + CH_XKB, &tmap_x, kb * 64, Ts - 1, b, 1, bar_xf + 8 * st);
+        }
       }
     }
   } else if (warp == 1) {
@@ -114,29 +117,32 @@ voc_conv_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const ConvHArgs a,
     ct_wait(bar_w, 0, dbg, 2, 0);
     const uint32_t sW = sbase + CH_OFF_W;
     const uint32_t id_2n = (1u << 4) | ((uint32_t)((2 * CH_NT) >> 3) << 17) | (8u << 24), id_n = (1u << 4) | ((uint32_t)(CH_NT >> 3) << 17) | (8u << 24);
-    int it = 0;
+    int it = 0, u = 0;
     for (int g = first; g < a.total_tiles; g += cpg, ++it) {
-      const int slot = it & 1, use = it >> 1;
-      ct_wait(bar_xf + 8 * slot, (uint32_t)(use & 1), dbg, 3, it);
-      if (use > 0) ct_wait(bar_ce + 8 * slot, (uint32_t)((use - 1) & 1), dbg, 4, it);     // accumulator buffer `slot` drained
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t sX = sbase + (uint32_t)slot * CH_XSLOT;
-      const uint32_t d = tmem_base + (uint32_t)slot * 64u;
+      const int slot = it & 1, ause = it >> 1;
+      if (ause > 0) ct_wait(bar_ce + 8 * slot, (uint32_t)((ause - 1) & 1), dbg, 4, it);     // accumulator buffer `slot` drained
+      const uint32_t d = tmem_base + (uint32_t)slot * (2 * CH_NT);
+      for (int kb = 0; kb < CH_KB; ++kb, ++u) {
+        const int st = u % CH_NST, use = u / CH_NST;
+        ct_wait(bar_xf + 8 * st, (uint32_t)(use & 1), dbg, 3, u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sX = sbase + (uint32_t)st * CH_STAGE;
 #pragma unroll
-      for (int tap = 0; tap < 3; ++tap)
+        for (int tap = 0; tap < 3; ++tap)
 #pragma unroll
-        for (int ks = 0; ks < CH_C / 16; ++ks) {
-          const uint32_t a_hi = sX + (uint32_t)(ks >> 2) * CH_XKB + (uint32_t)tap * CH_RB + (uint32_t)(ks & 3) * 32u;
-          const uint64_t bd = ch_desc(sW + (uint32_t)(tap * CH_KB + (ks >> 2)) * CH_WKB + (uint32_t)(ks & 3) * 32u);
-          ch_mma_w(d, ch_desc(a_hi), bd, id_2n, (tap | ks) ? 1u : 0u);          // A_hi x [W_hi ; W_lo]
-          ch_mma_w(d, ch_desc(a_hi + CH_XPL), bd, id_n, 1u);                    // A_lo x W_hi
-        }
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint32_t a_hi = sX + (uint32_t)tap * CH_RB + (uint32_t)ks * 32u;
+            const uint64_t bd = ch_desc(sW + (uint32_t)(tap * CH_KB + kb) * CH_WKB + (uint32_t)ks * 32u);
+            ch_mma_w(d, ch_desc(a_hi), bd, id_2n, (kb | tap | ks) ? 1u : 0u);       // A_hi x [W_hi ; W_lo]
+            ch_mma_w(d, ch_desc(a_hi + CH_XKB), bd, id_n, 1u);                      // A_lo x W_hi
+          }
+        ct_commit_w(bar_xe + 8 * st);
+      }
       ct_commit_w(bar_cf + 8 * slot);
-      ct_commit_w(bar_xe + 8 * slot);
     }
   } else {
     // ===== epilogue warpgroup eg: thread m = output row of the tile, channels [16 eg, 16 eg + 16) =====
-    // (two warpgroups: one warp per scheduler cannot hide the latency of its own dependent instructions)
+    // (several warpgroups: one warp per scheduler cannot hide the latency of its own dependent instructions)
     const int eg = (warp - 2) >> 2;
     const int qtr = warp & 3;
     const int m = qtr * 32 + lane;
@@ -149,7 +155,8 @@ voc_conv_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const ConvHArgs a,
       const int t = k * CH_NOUT + m;
       const bool valid = t < a.L;
       const size_t o = ((size_t)b * a.L + t) * CH_C + co0 + eg * 16;
-      // residual planes of this row (32 B + 32 B): requested before the accumulator wait
+      // residual planes of this row (32 B + 32 B): requested before the accumulator wait (fetching them a whole tile ahead
+      // was measured and changes nothing: with the residual the kernel moves 1.34 GB and sits at ~55 % of the HBM peak)
       uint4 rh[2], rl[2];
       if (a.res_h != nullptr && valid) {
 #pragma unroll
@@ -162,8 +169,8 @@ voc_conv_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const ConvHArgs a,
       __syncwarp();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       uint32_t vm[16], vc[16];
-      ct_ld16(t_lane + (uint32_t)(slot * 64 + eg * 16), vm);
-      ct_ld16(t_lane + (uint32_t)(slot * 64 + CH_NT + eg * 16), vc);
+      ct_ld16(t_lane + (uint32_t)(slot * 2 * CH_NT + eg * 16), vm);
+      ct_ld16(t_lane + (uint32_t)(slot * 2 * CH_NT + CH_NT + eg * 16), vc);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
@@ -215,7 +222,7 @@ voc_conv_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const ConvHArgs a,
   __syncthreads();
   if (warp == 0) {
     __syncwarp();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(CH_TMEM) : "memory");
   }
 }
 

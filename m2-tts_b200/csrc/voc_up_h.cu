@@ -27,16 +27,20 @@ struct UpHArgs {
 
 template <int CI, int COT>
 struct UhCfg {
-  static constexpr int CO = CI / 2, KB = CI / 64, NST = COT == 64 ? 3 : 4;
+  static constexpr int CO = CI / 2, KB = CI / 64;
   static constexpr int XR = 136, NQ = 128;
-  static constexpr uint32_t XPL = XR * 128;                 // one plane of one k-block
-  static constexpr uint32_t STAGE = 2 * XPL;
+  static constexpr uint32_t XPL = XR * 128;                 // one plane (hi or lo) of one 64-channel k-block
   static constexpr uint32_t WKB = 2 * COT * 128;            // [hi rows ; lo rows] of one (tap, k-block)
   static constexpr uint32_t WBYTES = 2 * KB * WKB;
+  static constexpr int STG_PLANES = WBYTES > 64 * 1024 ? 1 : 2;      // output staging: both planes at once, or one after the other
+  static constexpr int SPL = WBYTES > 64 * 1024 ? 1 : 2;             // planes per ring stage (2: hi and lo UMMAs interleave on one B descriptor)
+  static constexpr int NST = WBYTES > 64 * 1024 ? 4 : 3;
+  static constexpr uint32_t STAGE = SPL * XPL;
+  static constexpr int UNITS = KB * 2 / SPL;                // ring units per tile
   static constexpr uint32_t OFF_W = NST * STAGE;
   static constexpr uint32_t OPL = 128 * COT * 2;            // output staging: one plane of one tile, rows of COT halves (swizzled)
   static constexpr uint32_t OFF_STG = OFF_W + WBYTES;
-  static constexpr uint32_t OFF_CONST = OFF_STG + 2 * OPL;
+  static constexpr uint32_t OFF_CONST = OFF_STG + STG_PLANES * OPL;
   static constexpr uint32_t OFF_BAR = OFF_CONST + 256;
   static constexpr uint32_t TOTAL = OFF_BAR + 256 + 1024;
   static constexpr int G = COT / 16;                        // epilogue warpgroups, 16 channels each
@@ -44,6 +48,7 @@ struct UhCfg {
   static constexpr uint32_t TMEM_COLS = 4 * COT;            // two accumulator buffers of (main | corr)
   static_assert(TOTAL <= 227 * 1024, "voc_up_h: shared memory");
   static_assert(COT == 32 || COT == 64, "voc_up_h: channel tile");
+  static_assert(NST <= 6, "voc_up_h: barrier block");
 };
 
 __device__ __forceinline__ void uh_tma_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
@@ -67,8 +72,8 @@ voc_up_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   const uint32_t sbase = (ct_smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (sbase - ct_smem_u32(smem_raw));
   const uint32_t bars = sbase + K::OFF_BAR;
-  // full[4] empty[4] acc_full[2] acc_free[2] w_full
-  const uint32_t bar_f = bars, bar_e = bars + 32, bar_cf = bars + 64, bar_ce = bars + 80, bar_w = bars + 96, tmem_slot = bars + 104;
+  // full[6] empty[6] acc_full[2] acc_free[2] w_full
+  const uint32_t bar_f = bars, bar_e = bars + 48, bar_cf = bars + 96, bar_ce = bars + 112, bar_w = bars + 128, tmem_slot = bars + 136;
   float* bias_s = reinterpret_cast<float*>(gbase + K::OFF_CONST);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -103,14 +108,18 @@ voc_up_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       int u = 0;
       for (int g = first; g < a.total_tiles; g += cpg) {
         const int b = g / a.tiles_per_utt, q0 = (g % a.tiles_per_utt) * K::NQ;      // X row j <-> input row q0 - 1 + j
-        for (int kb = 0; kb < K::KB; ++kb, ++u) {
+        for (int kp = 0; kp < K::UNITS; ++kp, ++u) {       // unit = (k-block, plane) or (k-block, both planes)
           const int st = u % K::NST, use = u / K::NST;
           if (use > 0) ct_wait(bar_e + 8 * st, (uint32_t)((use - 1) & 1), dbg, 1, u);
           if (a.dbg_mode & 4) { ct_arrive(bar_f + 8 * st); continue; }
           ct_expect_tx(bar_f + 8 * st, K::STAGE);
           const uint32_t dst = sbase + (uint32_t)st * K::STAGE;
-          uh_tma_4d(dst, &tmap_x, kb * 64, q0 - 1, b, 0, bar_f + 8 * st);
-          uh_tma_4d(dst + K::XPL, &tmap_x, kb * 64, q0 - 1, b, 1, bar_f + 8 * st);
+          if (K::SPL == 1) {
+            uh_tma_4d(dst, &tmap_x, (kp >> 1) * 64, q0 - 1, b, kp & 1, bar_f + 8 * st);
+          } else {
+            uh_tma_4d(dst, &tmap_x, kp * 64, q0 - 1, b, 0, bar_f + 8 * st);
+            uh_tma_4d(dst + K::XPL, &tmap_x, kp * 64, q0 - 1, b, 1, bar_f + 8 * st);
+          }
         }
       }
     }
@@ -125,21 +134,39 @@ voc_up_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       const int ab = it & 1, ause = it >> 1;
       if (ause > 0) ct_wait(bar_ce + 8 * ab, (uint32_t)((ause - 1) & 1), dbg, 4, it);
       const uint32_t d = tmem_base + (uint32_t)ab * (2 * COT);
-      for (int kb = 0; kb < K::KB; ++kb, ++u) {
+      for (int kp = 0; kp < K::UNITS; ++kp, ++u) {
         const int st = u % K::NST, use = u / K::NST;
+        const int kb = K::SPL == 1 ? (kp >> 1) : kp;
         ct_wait(bar_f + 8 * st, (uint32_t)(use & 1), dbg, 3, u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t sX = sbase + (uint32_t)st * K::STAGE;
-        if (!(a.dbg_mode & 2))
+        if (!(a.dbg_mode & 2)) {
+          if (K::SPL == 2) {
 #pragma unroll
-        for (int tap = 0; tap < 2; ++tap)
+            for (int tap = 0; tap < 2; ++tap)
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const uint32_t a_hi = sX + (tap == 0 ? 128u : shift1) + (uint32_t)ks * 32u;
-            const uint64_t bd = uh_desc(sW + (uint32_t)(tap * K::KB + kb) * K::WKB + (uint32_t)ks * 32u);
-            uh_mma_w(d, uh_desc(a_hi), bd, id_2n, (kb | tap | ks) ? 1u : 0u);        // A_hi x [W_hi ; W_lo]
-            uh_mma_w(d, uh_desc(a_hi + K::XPL), bd, id_n, 1u);                       // A_lo x W_hi
+              for (int ks = 0; ks < 4; ++ks) {
+                const uint32_t a_hi = sX + (tap == 0 ? 128u : shift1) + (uint32_t)ks * 32u;
+                const uint64_t bd = uh_desc(sW + (uint32_t)(tap * K::KB + kb) * K::WKB + (uint32_t)ks * 32u);
+                uh_mma_w(d, uh_desc(a_hi), bd, id_2n, (kp | tap | ks) ? 1u : 0u);        // A_hi x [W_hi ; W_lo]
+                uh_mma_w(d, uh_desc(a_hi + K::XPL), bd, id_n, 1u);                       // A_lo x W_hi
+              }
+          } else if ((kp & 1) == 0) {
+#pragma unroll
+            for (int tap = 0; tap < 2; ++tap)
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)                                           // A_hi x [W_hi ; W_lo]
+                uh_mma_w(d, uh_desc(sX + (tap == 0 ? 128u : shift1) + (uint32_t)ks * 32u),
+                         uh_desc(sW + (uint32_t)(tap * K::KB + kb) * K::WKB + (uint32_t)ks * 32u), id_2n, (kp | tap | ks) ? 1u : 0u);
+          } else {
+#pragma unroll
+            for (int tap = 0; tap < 2; ++tap)
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)                                           // A_lo x W_hi
+                uh_mma_w(d, uh_desc(sX + (tap == 0 ? 128u : shift1) + (uint32_t)ks * 32u),
+                         uh_desc(sW + (uint32_t)(tap * K::KB + kb) * K::WKB + (uint32_t)ks * 32u), id_n, 1u);
           }
+        }
         ct_commit_w(bar_e + 8 * st);
       }
       ct_commit_w(bar_cf + 8 * ab);
@@ -194,23 +221,32 @@ voc_up_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         hv[j] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
         lv[j] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
       }
-      if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the previous tile's stores have read the staging buffer
-      asm volatile("bar.sync 1, %0;" ::"n"(128 * K::G) : "memory");
+      const uint32_t off0 = (uint32_t)m * ORB + ((((uint32_t)(eg * 2)) ^ sw) << 4), off1 = (uint32_t)m * ORB + ((((uint32_t)(eg * 2 + 1)) ^ sw) << 4);
+      const uint32_t s0 = sbase + K::OFF_STG;
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const uint32_t off = (uint32_t)m * ORB + ((((uint32_t)(eg * 2 + j)) ^ sw) << 4);
-        *reinterpret_cast<uint4*>(stg + off) = hv[j];
-        *reinterpret_cast<uint4*>(stg + K::OPL + off) = lv[j];
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("bar.sync 2, %0;" ::"n"(128 * K::G) : "memory");
-      if (leader && !(a.dbg_mode & 1)) {
-        const uint32_t s0 = sbase + K::OFF_STG;
-        asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4, %5}], [%6];"
-                     ::"l"(&tmap_y), "r"(co0), "r"(ph), "r"(q0), "r"(b), "r"(0), "r"(s0) : "memory");
-        asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4, %5}], [%6];"
-                     ::"l"(&tmap_y), "r"(co0), "r"(ph), "r"(q0), "r"(b), "r"(1), "r"(s0 + K::OPL) : "memory");
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      for (int pass = 0; pass < 3 - K::STG_PLANES; ++pass) {      // one pass with both planes staged, or hi then lo through one buffer
+        if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");    // earlier stores have read the staging buffer
+        asm volatile("bar.sync 1, %0;" ::"n"(128 * K::G) : "memory");
+        if (K::STG_PLANES == 2) {
+          *reinterpret_cast<uint4*>(stg + off0) = hv[0]; *reinterpret_cast<uint4*>(stg + off1) = hv[1];
+          *reinterpret_cast<uint4*>(stg + K::OPL + off0) = lv[0]; *reinterpret_cast<uint4*>(stg + K::OPL + off1) = lv[1];
+        } else {
+          *reinterpret_cast<uint4*>(stg + off0) = pass == 0 ? hv[0] : lv[0]; *reinterpret_cast<uint4*>(stg + off1) = pass == 0 ? hv[1] : lv[1];
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync 2, %0;" ::"n"(128 * K::G) : "memory");
+        if (leader && !(a.dbg_mode & 1)) {
+          if (K::STG_PLANES == 2) {
+            asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4, %5}], [%6];"
+                         ::"l"(&tmap_y), "r"(co0), "r"(ph), "r"(q0), "r"(b), "r"(0), "r"(s0) : "memory");
+            asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4, %5}], [%6];"
+                         ::"l"(&tmap_y), "r"(co0), "r"(ph), "r"(q0), "r"(b), "r"(1), "r"(s0 + K::OPL) : "memory");
+          } else {
+            asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4, %5}], [%6];"
+                         ::"l"(&tmap_y), "r"(co0), "r"(ph), "r"(q0), "r"(b), "r"(pass), "r"(s0) : "memory");
+          }
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
       }
     }
     if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -286,7 +322,7 @@ int launch_voc_up_h(const void* xh, long long x_plane, const float* w, const flo
   M2_REQUIRE(B > 0 && L > 0, M2TTS_E_BADSHAPE, "voc_up_h: B=%d L=%d", B, L);
   EncodeTiledFn9 enc = uh_encode_fn();
   M2_REQUIRE(enc != nullptr, M2TTS_E_CUDA, "voc_up_h: cuTensorMapEncodeTiled unavailable");
-  const int COT = CI == 256 ? 32 : 64;
+  const int COT = 64;
   {
     UhPackArgs p{w, (__half*)wblob, CI, COT};
     M2_LAUNCH(M2TTS_STAGE_PACK, uh_wpack_kernel, ceil_div(16 * CI * (CI / 2), 256), 256, 0, s, p);
@@ -318,7 +354,7 @@ int launch_voc_up_h(const void* xh, long long x_plane, const float* w, const flo
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     M2_REQUIRE(ry == CUDA_SUCCESS, M2TTS_E_CUDA, "voc_up_h: cuTensorMapEncodeTiled (output) failed (%d)", (int)ry);
   }
-  return CI == 256 ? launch_up_h_t<256, 32>(tmap, tmap_y, a, stage, s) : launch_up_h_t<128, 64>(tmap, tmap_y, a, stage, s);
+  return CI == 256 ? launch_up_h_t<256, 64>(tmap, tmap_y, a, stage, s) : launch_up_h_t<128, 64>(tmap, tmap_y, a, stage, s);
 }
 
 void voc_up_h_set_debug(int m) { g_uh_dbg = m; }
