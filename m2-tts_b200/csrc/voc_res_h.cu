@@ -91,7 +91,7 @@ __device__ __forceinline__ void rh_ld_sum16(uint32_t t_main, uint32_t t_corr, fl
 
 template <int C>
 __global__ void __launch_bounds__(RhCfg<C>::THREADS, 1)
-voc_res_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const ResHArgs a, int* dbg) {
+voc_res_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_y, const ResHArgs a, int* dbg) {
   using K = RhCfg<C>;
   constexpr int RB = K::RB;
   extern __shared__ uint8_t smem_raw[];
@@ -108,7 +108,7 @@ voc_res_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const ResHArgs a, i
   auto tile_of = [&](int it) { return it * (int)gridDim.x + (int)blockIdx.x; };
 
   if (tid == 0) {
-    for (int s = 0; s < 2; ++s) { ct_mbar_init(bar_xf + 8 * s, 1); ct_mbar_init(bar_xe + 8 * s, 8); }
+    for (int s = 0; s < 2; ++s) { ct_mbar_init(bar_xf + 8 * s, 1); ct_mbar_init(bar_xe + 8 * s, a.out_h != nullptr ? 1 : 8); }
     ct_mbar_init(bar_c1, 1); ct_mbar_init(bar_vr, 8); ct_mbar_init(bar_c2, 1); ct_mbar_init(bar_w, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_x) : "memory");
@@ -227,6 +227,14 @@ voc_res_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const ResHArgs a, i
       __syncwarp();
       if (lane == 0) ct_arrive(bar_vr);
 
+      // planes mode: the previous tile's output left through TMA stores that read its input slot; once they have read it the
+      // slot goes back to the producer (the leader has nothing else to do while conv2 runs)
+      const bool leader = warp == 2 && lane == 0;
+      if (a.out_h != nullptr && leader && it > 0) {
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        ct_arrive(bar_xe + 8 * ((it - 1) & 1));
+      }
+
       // ---- EPI3: conv2 accumulator + bias + u (row m + 1 of the input tile) -> output ----
       ct_wait(bar_c2, par, dbg, 10, it);
       __syncwarp();
@@ -243,27 +251,44 @@ voc_res_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const ResHArgs a, i
 #pragma unroll
           for (int e = 0; e < 8; ++e) y[8 * j8 + e] += b2[c0 + 8 * j8 + e] + u8[e];
         }
-        if (inside && m >= 1 && m < 1 + K::NOUT) {
-          const size_t o = ((size_t)b * a.L + t) * C + c0;
-          if (a.out_h != nullptr) {
+        if (a.out_h != nullptr) {
+          // planes: y overwrites this thread's own residual chunks in the input slot (same swizzled addresses); the rows
+          // leave as two TMA stores below (thread-per-row global stores touch 32 lines per instruction: 0.2 ms)
+          uint8_t* Xw = gbase + K::O_X + (uint32_t)(it & 1) * 2 * K::XPL;
 #pragma unroll
-            for (int j8 = 0; j8 < 2; ++j8) {
-              uint4 hi, lo;
-              rh_split8(y + 8 * j8, hi, lo);
-              if (!a.dbg_nostore) *reinterpret_cast<uint4*>(a.out_h + o + 8 * j8) = hi;
-              if (!a.dbg_nostore) *reinterpret_cast<uint4*>(a.out_h + a.out_plane + o + 8 * j8) = lo;
-            }
-          } else {
-            float4* op = reinterpret_cast<float4*>(a.out_f + o);
-#pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) op[j4] = make_float4(y[4 * j4], y[4 * j4 + 1], y[4 * j4 + 2], y[4 * j4 + 3]);
+          for (int j8 = 0; j8 < 2; ++j8) {
+            uint4 hi, lo;
+            rh_split8(y + 8 * j8, hi, lo);
+            const uint32_t off = rh_swz128(m + 1, (c0 >> 3) + j8);
+            *reinterpret_cast<uint4*>(Xw + off) = hi;
+            *reinterpret_cast<uint4*>(Xw + K::XPL + off) = lo;
           }
+        } else if (inside && m >= 1 && m < 1 + K::NOUT) {
+          const size_t o = ((size_t)b * a.L + t) * C + c0;
+          float4* op = reinterpret_cast<float4*>(a.out_f + o);
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) op[j4] = make_float4(y[4 * j4], y[4 * j4 + 1], y[4 * j4 + 2], y[4 * j4 + 3]);
         }
+      }
+      if (a.out_h != nullptr) {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (leader && !a.dbg_nostore) {      // output rows m = 1 .. NOUT sit in slot rows 2 .. NOUT + 1; TMA clips positions >= L
+          const uint32_t s0 = sbase + K::O_X + (uint32_t)(it & 1) * 2 * K::XPL + 2u * RB;
+          asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4}], [%5];"
+                       ::"l"(&tmap_y), "r"(0), "r"(k * K::NOUT), "r"(b), "r"(0), "r"(s0) : "memory");
+          asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4}], [%5];"
+                       ::"l"(&tmap_y), "r"(0), "r"(k * K::NOUT), "r"(b), "r"(1), "r"(s0 + K::XPL) : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        continue;
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) ct_arrive(bar_xe + 8 * (it & 1));      // this input slot (the residual) has been read
     }
+    if (a.out_h != nullptr && warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -339,7 +364,17 @@ int launch_voc_res_h(const void* uh, long long u_plane, const float* w1, const f
   a.total_tiles = B * a.tiles_per_utt;
   const int grid = a.total_tiles < kNumSMs ? a.total_tiles : kNumSMs;
   M2_CUDA_OK(allow_smem(voc_res_h_kernel<64>, K::TOTAL));
-  M2_LAUNCH(stage, voc_res_h_kernel<64>, grid, K::THREADS, K::TOTAL, s, tmap, a, debug_words_device());
+  CUtensorMap tmap_y = tmap;      // placeholder when the output is fp32
+  if (out_h != nullptr) {
+    const cuuint64_t ydims[4] = {(cuuint64_t)C, (cuuint64_t)L, (cuuint64_t)B, 2};
+    const cuuint64_t ystr[3] = {(cuuint64_t)C * 2, (cuuint64_t)L * C * 2, (cuuint64_t)out_plane * 2};
+    const cuuint32_t ybox[4] = {(cuuint32_t)C, (cuuint32_t)K::NOUT, 1u, 1u};
+    const cuuint32_t yes[4] = {1, 1, 1, 1};
+    const CUresult ry = enc(&tmap_y, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, out_h, ydims, ystr, ybox, yes, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    M2_REQUIRE(ry == CUDA_SUCCESS, M2TTS_E_CUDA, "voc_res_h: cuTensorMapEncodeTiled (output) failed (%d)", (int)ry);
+  }
+  M2_LAUNCH(stage, voc_res_h_kernel<64>, grid, K::THREADS, K::TOTAL, s, tmap, tmap_y, a, debug_words_device());
   return M2TTS_OK;
 }
 
