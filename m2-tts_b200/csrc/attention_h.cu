@@ -58,7 +58,7 @@ __device__ __forceinline__ void umma_f16_ts_w(uint32_t d_tmem, uint32_t a_tmem, 
 template <int HD>
 __global__ void __launch_bounds__(AH_THREADS, 1)
 attention_h_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__ ctx, const int64_t* __restrict__ lengths,
-                   int B, int L, int nh, float* __restrict__ ctx_lo, __half* __restrict__ ctx_h, long long* __restrict__ prof) {
+                   int B, int L, int nh, float* __restrict__ ctx_lo, __half* __restrict__ ctx_h, long long* __restrict__ prof, int dbg_skip) {
   static_assert(HD % 16 == 0 && HD >= 16 && HD <= 64, "16-bit split attention: head_dim in {16,32,48,64}");
   constexpr uint32_t BOX = AhSmem<HD>::box;
   constexpr int KSTEPS_D = HD / 16;
@@ -148,6 +148,7 @@ attention_h_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__
     const int x = warp - 1;
     const bool pr_on = prof != nullptr && blockIdx.x == 0;
     auto issue_qk = [&](int x, int st, int buf) {
+      if (dbg_skip & 1) return;      // bring-up timing experiment (M2TTS_ATT_DBG): results invalid
       const uint32_t q = sQ + (uint32_t)x * AhSmem<HD>::q_bytes, k = sK + (uint32_t)st * AhSmem<HD>::kv_bytes;
       const uint32_t d = tmem_base + (uint32_t)x * AH_COL_TILE + AH_COL_S + (uint32_t)buf * 64u;
       // MN-major, 128B swizzle, 16-bit: LBO = next 64 positions (next box), SBO = next 8 d-rows (1024 B);
@@ -162,6 +163,7 @@ attention_h_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__
       }
     };
     auto issue_pv = [&](int x, int st, int buf, uint32_t accumulate) {
+      if (dbg_skip & 2) return;
       const uint32_t v = sV + (uint32_t)st * AhSmem<HD>::kv_bytes;
       const uint32_t tb = tmem_base + (uint32_t)x * AH_COL_TILE;
       const uint32_t pb = tb + AH_COL_S + (uint32_t)buf * 64u;
@@ -376,9 +378,11 @@ template <int HD>
 static int launch_ah_hd(const CUtensorMap& tmap, float* ctx, const int64_t* lengths, int B, int L, int nh, cudaStream_t s, float* ctx_lo,
                         __half* ctx_h) {
   const size_t smem = AhSmem<HD>::total;
+  static int dbg_skip = -1;
+  if (dbg_skip < 0) { const char* e = getenv("M2TTS_ATT_DBG"); dbg_skip = e ? atoi(e) : 0; }
   M2_CUDA_OK(allow_smem(attention_h_kernel<HD>, smem));
   dim3 grid((unsigned)(ceil_div(L, 2 * TC_BQ) * nh * B), 1, 1);
-  M2_LAUNCH(M2TTS_STAGE_ATTENTION, attention_h_kernel<HD>, grid, AH_THREADS, smem, s, tmap, ctx, lengths, B, L, nh, ctx_lo, ctx_h, g_ws_prof);
+  M2_LAUNCH(M2TTS_STAGE_ATTENTION, attention_h_kernel<HD>, grid, AH_THREADS, smem, s, tmap, ctx, lengths, B, L, nh, ctx_lo, ctx_h, g_ws_prof, dbg_skip);
   return M2TTS_OK;
 }
 
