@@ -22,7 +22,7 @@
 
 namespace m2 {
 
-constexpr int AH_THREADS = 384;
+constexpr int AH_THREADS = 128 + 512;      // loader, two issuers, idle | four softmax warpgroups (two per query tile)
 constexpr uint32_t AH_TMEM_COLS = 512;
 // TMEM per query tile (tile stride 256 columns): two score buffers of 64 columns (tile t uses buffer t & 1; P(t) is
 // packed over it: P_hi in columns 0:32, P_lo in 32:64 of the buffer) and O in 2 hd columns from 128.
@@ -38,7 +38,8 @@ struct AhSmem {
   static constexpr uint32_t off_k = 2 * q_bytes;
   static constexpr uint32_t off_v = off_k + AH_STAGES * kv_bytes;
   static constexpr uint32_t off_bar = off_v + AH_STAGES * kv_bytes;
-  static constexpr uint32_t total = off_bar + 512 + 1024 /*align slack*/;
+  static constexpr uint32_t off_exch = off_bar + 512;          // float [parity 2][tile 2][half 2][128 rows]: row maxima / final row sums
+  static constexpr uint32_t total = off_exch + 4096 + 1024 /*align slack*/;
 };
 
 __host__ __device__ constexpr uint32_t ah_idesc(int M, int N, int mn_major) {   // kind::f16: fp16 x fp16 -> fp32
@@ -101,7 +102,7 @@ attention_h_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_qf + 8 * i, 1); mbar_init(bar_sf + 16 * i, 1); mbar_init(bar_sf + 16 * i + 8, 1);
-      mbar_init(bar_pr + 8 * i, 4); mbar_init(bar_pv + 8 * i, 1);
+      mbar_init(bar_pr + 8 * i, 8); mbar_init(bar_pv + 8 * i, 1);
     }
     for (int i = 0; i < AH_STAGES; ++i) {
       mbar_init(bar_kf + 8 * i, 1); mbar_init(bar_ke + 8 * i, (uint32_t)ntq); mbar_init(bar_vf + 8 * i, 1); mbar_init(bar_ve + 8 * i, (uint32_t)ntq);
@@ -208,13 +209,20 @@ attention_h_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__
       }
       if (pr_on && lane == 0 && t >= 8 && t < 40) prof[384 + (t - 8) * 8 + 3 * x + 2] = clock64();
     }
-  } else if (warp >= 4 && ((warp - 4) >> 2) < ntq) {
-    // ===== softmax warpgroup of query tile x: thread = query row =====
-    const int x = (warp - 4) >> 2;
+  } else if (warp >= 4 && (((warp - 4) >> 2) & 1) < ntq) {
+    // ===== softmax warpgroups: query tile x has TWO of them (warps 4-7 / 12-15 for tile A, 8-11 / 16-19 for tile B); thread =
+    // query row = TMEM lane, warpgroup `half` owns 32 of the 64 score columns of every key tile. Four softmax warps per
+    // scheduler instead of two: the loop is bound by MUFU (quarter rate) and by the latency of its own dependent
+    // instructions, not by issue slots (tools/attn_prof.py: 2054 cycles per key tile even with the UMMAs switched off).
+    // The two warps that share a row exchange their partial row maxima through shared memory at a 64-thread named barrier,
+    // which also orders "both have loaded their scores" before either packs P over the score columns.
+    const int x = ((warp - 4) >> 2) & 1, half = (warp - 4) >> 3;
     const int row = (warp & 3) * 32 + lane;
     const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)x * AH_COL_TILE;
+    float* exch = reinterpret_cast<float*>(smem_raw + (sbase - smem_u32(smem_raw)) + AhSmem<HD>::off_exch);
+    const int pair_bar = 1 + x * 4 + (warp & 3);          // named barrier of the two warps sharing these 32 rows
     float m_ref = -INFINITY, l_run = 0.f;
-    const bool pw = prof != nullptr && blockIdx.x == 0 && x == 0 && row == 0;
+    const bool pw = prof != nullptr && blockIdx.x == 0 && x == 0 && half == 0 && row == 0;
     for (int t = 0; t < nkt; ++t) {
       const bool pt = pw && t >= 8 && t < 40;
       long long* pp = prof + (pt ? (t - 8) * 8 : 0);
@@ -224,15 +232,15 @@ attention_h_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__
       if (pt) pp[1] = clock64();
       __syncwarp();
       tc_fence_after();
-      uint32_t sr[TC_BK];
-#pragma unroll
-      for (int c = 0; c < TC_BK; c += 16) tmem_ld16(t_s + c, sr + c);
+      uint32_t sr[32];
+      tmem_ld16(t_s + half * 32, sr);
+      tmem_ld16(t_s + half * 32 + 16, sr + 16);
       tmem_wait_ld();
       if (pt) pp[2] = clock64();
-      const int kbase = t * TC_BK;
-      if (all_masked || kbase + TC_BK > Leff) {
+      const int kbase = t * TC_BK + half * 32;
+      if (all_masked || kbase + 32 > Leff) {
 #pragma unroll
-        for (int j = 0; j < TC_BK; ++j) {
+        for (int j = 0; j < 32; ++j) {
           float v = __uint_as_float(sr[j]);
           if (all_masked) v = (kbase + j < L) ? 0.f : -INFINITY;
           else if (kbase + j >= Leff) v = -INFINITY;
@@ -241,7 +249,13 @@ attention_h_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__
       }
       float mx = __uint_as_float(sr[0]);
 #pragma unroll
-      for (int j = 1; j < TC_BK; ++j) mx = fmaxf(mx, __uint_as_float(sr[j]));
+      for (int j = 1; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(sr[j]));
+      {  // row maximum over all 64 columns
+        float* e = exch + ((t & 1) * 4 + x * 2) * 128;
+        e[half * 128 + row] = mx;
+        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+        mx = fmaxf(mx, e[(half ^ 1) * 128 + row]);
+      }
       if (t == 0) {
         m_ref = mx;
       }
@@ -250,7 +264,8 @@ attention_h_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__
       // end of the tile, when PV(t-1) has long landed and the wait costs nothing.
       bool pv_waited = t == 0;
       if (t > 0 && __any_sync(0xffffffffu, mx > m_ref + 8.0f)) {
-        // lazy rescale: PV(t-1) has landed and PV(t) waits for our arrival below, so O is quiescent
+        // lazy rescale (both warps of the pair take the same decision: they see the same maxima): PV(t-1) has landed and
+        // PV(t) waits for our arrival below, so O is quiescent; this half rescales its hd of the 2 hd accumulator columns
         mbar_wait(bar_pv + 8 * x, (uint32_t)((t - 1) & 1));
         pv_waited = true;
         tc_fence_after();
@@ -259,24 +274,23 @@ attention_h_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__
         m_ref = m_new;
         l_run *= alpha;
 #pragma unroll
-        for (int c = 0; c < 2 * HD; c += 16) {
+        for (int c = 0; c < HD; c += 16) {
           uint32_t orr[16];
-          tmem_ld16(t_lane + AH_COL_O + c, orr);
+          tmem_ld16(t_lane + AH_COL_O + half * HD + c, orr);
           tmem_wait_ld();
 #pragma unroll
           for (int j = 0; j < 16; ++j) orr[j] = __float_as_uint(__uint_as_float(orr[j]) * alpha);
-          tmem_st16(t_lane + AH_COL_O + c, orr);
+          tmem_st16(t_lane + AH_COL_O + half * HD + c, orr);
         }
       }
       if (pt) pp[3] = clock64();
       float rs = 0.f;
-#pragma unroll
-      for (int c = 0; c < TC_BK; c += 32) {        // 32 keys -> 16 packed columns of P_hi and of P_lo
+      {        // 32 keys -> 16 packed columns of P_hi and of P_lo
         uint32_t ph[16], pl[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const float p0 = ws_ex2(__uint_as_float(sr[c + 2 * j]) - m_ref);
-          const float p1 = ws_ex2(__uint_as_float(sr[c + 2 * j + 1]) - m_ref);
+          const float p0 = ws_ex2(__uint_as_float(sr[2 * j]) - m_ref);
+          const float p1 = ws_ex2(__uint_as_float(sr[2 * j + 1]) - m_ref);
           rs += p0 + p1;
           const __half2 h = __floats2half2_rn(p0, p1);
           const float2 hf = __half22float2(h);
@@ -284,8 +298,8 @@ attention_h_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__
           ph[j] = *reinterpret_cast<const uint32_t*>(&h);
           pl[j] = *reinterpret_cast<const uint32_t*>(&lo);
         }
-        tmem_st16(t_s + (c >> 1), ph);                      // P overwrites the scores in place
-        tmem_st16(t_s + AH_COL_PLO + (c >> 1), pl);
+        tmem_st16(t_s + half * 16, ph);                      // P overwrites the scores in place
+        tmem_st16(t_s + AH_COL_PLO + half * 16, pl);
       }
       l_run += rs;
       if (pt) pp[4] = clock64();
@@ -297,6 +311,14 @@ attention_h_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__
       __syncwarp();
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_pr + 8 * x) : "memory");
     }
+    // total row sum: the second warpgroup of the tile publishes its part and is done
+    {
+      float* e = exch + ((nkt & 1) * 4 + x * 2) * 128;
+      if (half == 1) e[128 + row] = l_run;
+      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+      if (half == 0) l_run += e[128 + row];
+    }
+    if (half == 0) {
     mbar_wait(bar_pv + 8 * x, (uint32_t)((nkt - 1) & 1));     // the last PV has landed: O is complete
     __syncwarp();
     tc_fence_after();
@@ -348,6 +370,7 @@ attention_h_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__
         }
       }
     }
+    }      // half == 0
   }
   tc_fence_before();
   __syncthreads();
