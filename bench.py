@@ -282,8 +282,8 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         dom = max(stage_ms.items(), key=lambda kv: kv[1][0]) if stage_ms else ("none", (0.0, 1))
         dom_ms_per_step = dom[1][0] / args.steps
         tensor_stages = {"attention": "tcgen05 kind::f16, 16-bit split (fp16 hi/lo, 3 product terms, fp32 accumulate): issued MMA FLOPs = 3x algorithmic",
-                         "voc_in": "tcgen05 3xTF32 tap-GEMM (after a strided -> channel-first copy of the mel)",
-                         "voc_up": "stages 0-1 transposed convs: tcgen05 3xTF32 tap-GEMM writing fp16 hi/lo planes channel-last",
+                         "voc_in": "tcgen05 3xTF32 tap-GEMM (after a strided -> channel-first copy of the mel), writes fp16 hi/lo planes channel-last",
+                         "voc_up": "stages 0-1 transposed convs: polyphase channel-last tcgen05 kind::f16 16-bit split kernel with TMA stores (voc_up_h.cu)",
                          "voc_res1": "stage 0 conv1 (C=128, channel-last 16-bit split conv kernel) + the whole stage-1 ResBlock (C=64, one fused 16-bit split kernel)",
                          "voc_res2": "stage 0 conv2 + residual (C=128, channel-last 16-bit split conv kernel, writes fp32 channel-first)",
                          "voc_fused": "stages 2-3: upsample + ResBlock (+ output conv + tanh) fused, channel-last tcgen05 kind::f16 16-bit split"}
@@ -299,7 +299,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                         algorithmic_flops_per_step=fl[dom[0]],
                         note="achieved = algorithmic (useful fp32-equivalent) FLOPs / device time of the stage; an fp32-faithful "
                              "split-precision kernel issues 3 products per algorithmic one: ceiling 1/3 of the bf16 peak with fp16 "
-                             "halves (attention, linear layers, ResBlocks, narrow stages), 1/6 with TF32 halves (input conv, upsampling tap-GEMMs)")
+                             "halves (attention, linear layers, ResBlocks, narrow stages), 1/6 with TF32 halves (input conv)")
         else:
             roof.update(achieved=None, frac=None)
         all_stage_tflops = {k: round(fl[k] / (v[0] / args.steps * 1e-3) / 1e12, 2) for k, v in stage_ms.items()
