@@ -189,9 +189,10 @@ int launch_voc_res_h(const void* uh, long long u_plane, const float* w1, const f
                      void* out_h, long long out_plane, float* out_f, int B, int C, int L, int stage, cudaStream_t s);
 // one Conv1d(C, C, 3) for C = 128 on channel-last fp16 hi/lo planes (voc_conv_h.cu); output planes or fp32 channel-first
 bool voc_conv_h_eligible(int C, int dil);
-size_t voc_conv_h_wblob_bytes(int C);
+bool voc_conv_h_io_eligible(int CI, int CO);      // 64 < CI <= 128 (zero-padded to 128), CO a multiple of 64: also the input conv
+size_t voc_conv_h_wblob_bytes(int CO);
 int launch_voc_conv_h(const void* xh, long long x_plane, const float* w, const float* bias, void* wblob, const void* res_h,
-                      long long res_plane, void* out_h, long long out_plane, float* out_cf, int Lp_out, int B, int C, int L, int act,
+                      long long res_plane, void* out_h, long long out_plane, float* out_cf, int Lp_out, int B, int CI, int CO, int L, int act,
                       int stage, cudaStream_t s);
 // ConvTranspose1d(CI, CI/2, 8, stride 4, padding 2) + leaky_relu on channel-last fp16 hi/lo planes (voc_up_h.cu)
 bool voc_up_h_eligible(int CI, int CO, int r);

@@ -20,6 +20,8 @@ namespace m2 {
 
 struct ConvHArgs {
   int B, L, Lp_out;
+  int CO;                                // output channels = row length of the output (and residual) planes
+  int ks1;                               // 16-channel k-steps of the second k-block (4, or fewer when CI < 128: the input conv)
   int tiles_per_utt, total_tiles, n_tiles;
   const __half* wblob;                   // [n_tile][tap][hi rows ; lo rows][C] swizzled image
   const float* bias;
@@ -127,10 +129,12 @@ voc_conv_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const ConvHArgs a,
         ct_wait(bar_xf + 8 * st, (uint32_t)(use & 1), dbg, 3, u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t sX = sbase + (uint32_t)st * CH_STAGE;
+        const int nks = kb == 0 ? 4 : a.ks1;
 #pragma unroll
         for (int tap = 0; tap < 3; ++tap)
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
+            if (ks >= nks) break;
             const uint32_t a_hi = sX + (uint32_t)tap * CH_RB + (uint32_t)ks * 32u;
             const uint64_t bd = ch_desc(sW + (uint32_t)(tap * CH_KB + kb) * CH_WKB + (uint32_t)ks * 32u);
             ch_mma_w(d, ch_desc(a_hi), bd, id_2n, (kb | tap | ks) ? 1u : 0u);       // A_hi x [W_hi ; W_lo]
@@ -154,7 +158,7 @@ voc_conv_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const ConvHArgs a,
       const int b = g / a.tiles_per_utt, k = g % a.tiles_per_utt;
       const int t = k * CH_NOUT + m;
       const bool valid = t < a.L;
-      const size_t o = ((size_t)b * a.L + t) * CH_C + co0 + eg * 16;
+      const size_t o = ((size_t)b * a.L + t) * a.CO + co0 + eg * 16;
       // residual planes of this row (32 B + 32 B): requested before the accumulator wait (fetching them a whole tile ahead
       // was measured and changes nothing: with the residual the kernel moves 1.34 GB and sits at ~55 % of the HBM peak)
       uint4 rh[2], rl[2];
@@ -212,7 +216,7 @@ voc_conv_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const ConvHArgs a,
           *(reinterpret_cast<uint4*>(a.out_h + a.out_plane + o) + j) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
         }
       } else {
-        float* op = a.out_cf + ((size_t)b * CH_C + co0 + eg * 16) * a.Lp_out + t;     // channel-first: coalesced across the warp's rows
+        float* op = a.out_cf + ((size_t)b * a.CO + co0 + eg * 16) * a.Lp_out + t;     // channel-first: coalesced across the warp's rows
 #pragma unroll
         for (int j = 0; j < 16; ++j) op[(size_t)j * a.Lp_out] = y[j];
       }
@@ -227,16 +231,16 @@ voc_conv_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const ConvHArgs a,
 }
 
 // weight image: [n_tile][tap][k-block][W_hi rows (32) ; W_lo rows (32)][64 k], K-major rows with the 128-byte swizzle
-struct ChPackArgs { const float* w; __half* blob; };
+struct ChPackArgs { const float* w; __half* blob; int CI, CO; };
 __global__ void ch_wpack_kernel(ChPackArgs p) {
-  const int total = CH_C * CH_C * 3 * 2;
+  const int total = p.CO * CH_C * 3 * 2;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
     int e = idx;
     const int k = e % CH_C; e /= CH_C;
     const int n = e % (2 * CH_NT); e /= (2 * CH_NT);
     const int tap = e % 3; const int ntile = e / 3;
     const int lo = n / CH_NT, co = ntile * CH_NT + n % CH_NT;
-    const float v = fminf(fmaxf(p.w[((size_t)co * CH_C + k) * 3 + tap], -65000.f), 65000.f);
+    const float v = k < p.CI ? fminf(fmaxf(p.w[((size_t)co * p.CI + k) * 3 + tap], -65000.f), 65000.f) : 0.f;      // k >= CI: zero padding
     const __half h = __float2half_rn(v);
     const int kb = k >> 6, kk = k & 63;
     const uint32_t off = (uint32_t)ntile * CH_WBYTES + (uint32_t)(tap * CH_KB + kb) * CH_WKB + (uint32_t)n * CH_RB +
@@ -261,21 +265,24 @@ static EncodeTiledFn8 ch_encode_fn() {
 }
 
 bool voc_conv_h_eligible(int C, int dil) { return C == CH_C && dil == 1; }
-size_t voc_conv_h_wblob_bytes(int C) { return C == CH_C ? (size_t)(CH_C / CH_NT) * CH_WBYTES : 0; }
+bool voc_conv_h_io_eligible(int CI, int CO) { return CI > 64 && CI <= CH_C && CI % 16 == 0 && CO >= CH_NT && CO % CH_NT == 0; }
+size_t voc_conv_h_wblob_bytes(int C) { return C % CH_NT == 0 ? (size_t)(C / CH_NT) * CH_WBYTES : 0; }      // C = output channels
 
-// xh: fp16 hi/lo planes channel-last [2][B][L][C] (x_plane apart); residual planes optional; output planes or fp32 channel-first.
+// xh: fp16 hi/lo planes channel-last [2][B][L][CI] (x_plane apart), 64 < CI <= 128 (channels CI..127 are zero-filled by TMA and
+// have zero weights); CO output channels (multiple of 64); residual planes [2][B][L][CO] optional; output planes or fp32 channel-first.
 int launch_voc_conv_h(const void* xh, long long x_plane, const float* w, const float* bias, void* wblob, const void* res_h,
-                      long long res_plane, void* out_h, long long out_plane, float* out_cf, int Lp_out, int B, int C, int L, int act,
+                      long long res_plane, void* out_h, long long out_plane, float* out_cf, int Lp_out, int B, int CI, int CO, int L, int act,
                       int stage, cudaStream_t s) {
-  M2_REQUIRE(C == CH_C, M2TTS_E_UNSUPPORTED, "voc_conv_h: C=%d (128)", C);
+  M2_REQUIRE(voc_conv_h_io_eligible(CI, CO), M2TTS_E_UNSUPPORTED, "voc_conv_h: CI=%d CO=%d", CI, CO);
+  const int C = CI;
   M2_REQUIRE((((uintptr_t)xh) & 15) == 0 && (((uintptr_t)wblob) & 15) == 0 && (x_plane & 7) == 0 && (out_plane & 7) == 0 && (res_plane & 7) == 0,
              M2TTS_E_BADSHAPE, "voc_conv_h: misaligned pointers");
   M2_REQUIRE(B > 0 && L > 0 && (out_h != nullptr || out_cf != nullptr), M2TTS_E_BADSHAPE, "voc_conv_h: B=%d L=%d", B, L);
   EncodeTiledFn8 enc = ch_encode_fn();
   M2_REQUIRE(enc != nullptr, M2TTS_E_CUDA, "voc_conv_h: cuTensorMapEncodeTiled unavailable");
   {
-    ChPackArgs p{w, (__half*)wblob};
-    M2_LAUNCH(M2TTS_STAGE_PACK, ch_wpack_kernel, ceil_div(CH_C * CH_C * 6, 256), 256, 0, s, p);
+    ChPackArgs p{w, (__half*)wblob, CI, CO};
+    M2_LAUNCH(M2TTS_STAGE_PACK, ch_wpack_kernel, ceil_div(CO * CH_C * 6, 256), 256, 0, s, p);
   }
   CUtensorMap tmap;
   const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)L, (cuuint64_t)B, 2};
@@ -289,7 +296,8 @@ int launch_voc_conv_h(const void* xh, long long x_plane, const float* w, const f
   ConvHArgs a{};
   a.B = B; a.L = L; a.Lp_out = Lp_out; a.wblob = (const __half*)wblob; a.bias = bias; a.act = act;
   a.res_h = (const __half*)res_h; a.res_plane = res_plane; a.out_h = (__half*)out_h; a.out_plane = out_plane; a.out_cf = out_cf;
-  a.n_tiles = CH_C / CH_NT;
+  a.CO = CO; a.ks1 = (CI - 64 + 15) / 16;
+  a.n_tiles = CO / CH_NT;
   a.tiles_per_utt = ceil_div(L, CH_NOUT);
   a.total_tiles = B * a.tiles_per_utt;
   int cpg = kNumSMs / a.n_tiles;
@@ -335,7 +343,7 @@ extern "C" int m2tts_conv1d_k3_h(const float* x, const float* w, const float* b,
   int rc = launch_split_planes_h(x, xp, n, s);
   if (rc) return rc;
   if (residual != nullptr && (rc = launch_split_planes_h(residual, rp, n, s))) return rc;
-  rc = launch_voc_conv_h(xp, n, w, b, wblob, residual ? rp : nullptr, n, out_cl ? yp : nullptr, n, out_cl ? nullptr : y, L, B, C, L, act,
+  rc = launch_voc_conv_h(xp, n, w, b, wblob, residual ? rp : nullptr, n, out_cl ? yp : nullptr, n, out_cl ? nullptr : y, L, B, C, C, L, act,
                          M2TTS_STAGE_VOC_RES1, s);
   if (rc) return rc;
   if (out_cl) M2_LAUNCH(M2TTS_STAGE_VOC_RES1, ch_join_planes_kernel, 1184, 256, 0, s, yp, n, y);

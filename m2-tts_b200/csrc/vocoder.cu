@@ -10,6 +10,7 @@
 // (two runs of 4, so each quarter-warp's LDS.128 is contiguous) x 8 output values per step and
 // streams input channels through shared memory in chunks of CK: 192 FFMA per 12 smem loads.
 #include "common.cuh"
+#include <cuda_fp16.h>
 #include <math.h>
 
 namespace m2 {
@@ -374,6 +375,39 @@ __global__ void __launch_bounds__(256) mel_to_channel_first_kernel(const float* 
   }
 }
 
+// x [B, M, T] fp32 with element strides -> fp16 hi/lo planes channel-last [2][B][T][M] (the input of the channel-last
+// 16-bit split input convolution); a 32 x 32 tile goes through shared memory so that both sides are coalesced whichever
+// of m / t is contiguous in x.
+__global__ void __launch_bounds__(256) mel_to_planes_kernel(const float* __restrict__ x, long long sb, long long sm, long long st,
+                                                             __half* __restrict__ planes, long long plane, int M, int T) {
+  __shared__ float tile[32][33];      // [t][m]
+  const int b = blockIdx.z, t0 = blockIdx.x * 32, m0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
+  const float* xb = x + (long long)b * sb;
+  if (st == 1) {          // t contiguous: read rows of t
+    for (int r = ty; r < 32; r += 8) {
+      const int m = m0 + r, t = t0 + tx;
+      tile[tx][r] = (m < M && t < T) ? xb[(long long)m * sm + t] : 0.f;
+    }
+  } else {                // m contiguous (or generic): read rows of m
+    for (int r = ty; r < 32; r += 8) {
+      const int t = t0 + r, m = m0 + tx;
+      tile[r][tx] = (m < M && t < T) ? xb[(long long)m * sm + (long long)t * st] : 0.f;
+    }
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int t = t0 + r, m = m0 + tx;
+    if (m < M && t < T) {
+      const float v = fminf(fmaxf(tile[r][tx], -65000.f), 65000.f);
+      const __half h = __float2half_rn(v);
+      const long long o = ((long long)b * T + t) * M + m;
+      planes[o] = h;
+      planes[plane + o] = __float2half_rn(v - __half2float(h));
+    }
+  }
+}
+
 // w[CO][CI][3] -> wp[CI][3][CO], several convolutions per launch (blockIdx.y = job)
 struct ConvPackJob { const float* src; float* dst; int CO, CI; };
 struct ConvPackJobs { ConvPackJob j[12]; };
@@ -584,7 +618,18 @@ extern "C" int m2tts_vocoder_forward(const m2tts_vocoder_weights* w, const float
   int L = T, c_in = C;
   int Lp = path[0] == P_TC ? ((L + 3) & ~3) : L;
   bool cl = false;                       // layout of the current activation (bufA): channel-last?
-  if (path[0] == P_TC && conv3_tc_eligible(M, C) && B <= 65535) {
+  if (up_h[0] && voc_conv_h_io_eligible(M, C) && B <= 65535 && conv_h_enabled() &&
+      (size_t)C / 64 * 98304 <= conv3_tc_wblob_floats(M, C) * sizeof(float)) {
+    // channel-last 16-bit split input conv: mel -> fp16 hi/lo planes [2][B][T][M] (bufC), then the conv kernel of the wide
+    // ResBlocks with CI = M zero-padded to 128 (the padding costs nothing: TMA zero-fills, the k-steps beyond M are skipped)
+    __half* mp = reinterpret_cast<__half*>(bufC);
+    const long long mplane = (long long)B * T * M;
+    dim3 grid(ceil_div(T, 32), ceil_div(M, 32), B);
+    M2_LAUNCH(M2TTS_STAGE_VOC_IN, mel_to_planes_kernel, grid, 256, 0, s, mel, (long long)stride_b, (long long)stride_m, (long long)stride_t,
+              mp, mplane, M, T);
+    if ((rc = launch_voc_conv_h(mp, mplane, w->in_w, w->in_b, in_wb, nullptr, 0, bufA, (long long)B * T * C, nullptr, 0, B, M, C, T, 0,
+                                M2TTS_STAGE_VOC_IN, s))) return rc;
+  } else if (path[0] == P_TC && conv3_tc_eligible(M, C) && B <= 65535) {
     // tensor-core input conv: channel-first copy of the mel with a 16-byte row pitch (bufC), then the tap-GEMM
     const float* xin = mel;
     if (!(stride_t == 1 && stride_m == Lp && stride_b == (int64_t)M * Lp && (((uintptr_t)mel) & 15) == 0)) {
@@ -644,10 +689,10 @@ extern "C" int m2tts_vocoder_forward(const m2tts_vocoder_weights* w, const float
                                         M2TTS_STAGE_VOC_UP, s);
       else rc = launch_convT_tc(bufA, Lp, w->up_w[j], upb[j], w->up_b[j], bufB, Lo, B, c_in, c, L, r, s, 2);
       if (rc) return rc;
-      if ((rc = launch_voc_conv_h(bufB, plane, w->res1_w[j], w->res1_b[j], r1b[j], nullptr, 0, bufC, plane, nullptr, 0, B, c, Lo, 1,
+      if ((rc = launch_voc_conv_h(bufB, plane, w->res1_w[j], w->res1_b[j], r1b[j], nullptr, 0, bufC, plane, nullptr, 0, B, c, c, Lo, 1,
                                   M2TTS_STAGE_VOC_RES1, s))) return rc;
       if ((rc = launch_voc_conv_h(bufC, plane, w->res2_w[j], w->res2_b[j], r2b[j], bufB, plane, next_cl ? (void*)bufA : nullptr, plane,
-                                  next_cl ? nullptr : bufA, Lo, B, c, Lo, 0, M2TTS_STAGE_VOC_RES2, s))) return rc;
+                                  next_cl ? nullptr : bufA, Lo, B, c, c, Lo, 0, M2TTS_STAGE_VOC_RES2, s))) return rc;
       Lp = Lo;
       cl = next_cl;
     } else if (path[j] == P_TC) {
