@@ -18,7 +18,9 @@
 namespace m2 {
 
 constexpr int LH_BM = 128;
-constexpr int LH_THREADS = 192;            // producer, issuer, 4 epilogue warps
+constexpr int LH_G = 3;                    // epilogue warpgroups: the 16-column chunks of a pass are dealt round-robin (one warp per
+                                           // scheduler cannot hide the latency of its own dependent instructions)
+constexpr int LH_THREADS = 64 + 128 * LH_G;      // producer, issuer, epilogue warps
 
 struct LinHArgs {
   int R, K, N;                     // rows, inner dim, outputs
@@ -31,6 +33,8 @@ struct LinHArgs {
   __half* y_planes;                // mode 1: [2][R][N]
   __half* qkvh; long long plane_stride; int L, nh, hd, Lp; float qscale;   // mode 3
   int mode;
+  int stg_bytes;                   // > 0: the epilogue stages the output tile in shared memory and writes it with TMA stores (modes 0, 1)
+  int dbg;                         // bring-up timing experiments (M2TTS_LIN_DBG): 1 no stores, 2 no UMMAs, 4 no A-tile loads; results invalid
 };
 
 // Operand rows are 32 halves = 64 bytes (64-B swizzle): K = 96 is then exactly three boxes (with 128-byte rows a
@@ -45,7 +49,8 @@ __device__ __forceinline__ void lh_mma_w(uint32_t d, uint64_t ad, uint64_t bd, u
 }
 
 __global__ void __launch_bounds__(LH_THREADS, 1)
-lin_h_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, const LinHArgs a) {
+lin_h_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_y,
+             const LinHArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (sbase - smem_u32(smem_raw));
@@ -54,7 +59,8 @@ lin_h_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
   const uint32_t w_box = (uint32_t)a.np * 64u;
   const uint32_t w_bytes = (uint32_t)a.kboxes * a.n_passes * 2u * w_box;
   const uint32_t sA = sbase;                                            // [stage][plane][kbox][128 x 64 B]
-  const uint32_t sW = sA + (uint32_t)a.a_stages * a_stage;              // [kbox][pass][plane][np x 64 B]
+  const uint32_t sStg = sA + (uint32_t)a.a_stages * a_stage;            // output staging: 8 KB boxes of 128 rows x 64 B, 64-byte swizzle
+  const uint32_t sW = sStg + (uint32_t)a.stg_bytes;                     // [kbox][pass][plane][np x 64 B]
   const uint32_t sBias = sW + w_bytes;                                  // N floats
   const uint32_t sBar = (sBias + (uint32_t)a.N * 4u + 15u) & ~15u;
   // barriers: a_full[4] a_empty[4] acc_full[2] acc_empty[2] w_full
@@ -67,11 +73,12 @@ lin_h_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
 
   if (tid == 0) {
     for (int i = 0; i < 4; ++i) { mbar_init(bar_af + 8 * i, 1); mbar_init(bar_ae + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(bar_cf + 8 * i, 1); mbar_init(bar_ce + 8 * i, 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_cf + 8 * i, 1); mbar_init(bar_ce + 8 * i, 4 * LH_G); }
     mbar_init(bar_w, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_y) : "memory");
   }
   for (int i = tid; i < a.N; i += LH_THREADS) bias_s[i] = a.bias != nullptr ? a.bias[i] : 0.f;
   if (warp == 0) {
@@ -97,6 +104,7 @@ lin_h_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
       for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x, ++it) {
         const int st = it % S;
         if (it >= S) mbar_wait(bar_ae + 8 * st, (uint32_t)(((it / S) - 1) & 1));
+        if (a.dbg & 4) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_af + 8 * st) : "memory"); continue; }
         mbar_expect_tx(bar_af + 8 * st, a_stage);
         for (int pl = 0; pl < 2; ++pl)
           for (int kb = 0; kb < a.kboxes; ++kb)
@@ -121,7 +129,7 @@ lin_h_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         if (unit >= 2) mbar_wait(bar_ce + 8 * buf, (uint32_t)(((unit >> 1) - 1) & 1));
         tc_fence_after();
         const uint32_t d = tmem_base + (uint32_t)buf * 256u;
-        for (int ks = 0; ks < ksteps; ++ks) {
+        for (int ks = 0; ks < ksteps && !(a.dbg & 2); ++ks) {
           const uint32_t koff = (uint32_t)(ks >> 1) * a_box + (uint32_t)(ks & 1) * 32u;
           const uint64_t bd = lh_desc(sW + (uint32_t)(((ks >> 1) * a.n_passes + p) * 2) * w_box + (uint32_t)(ks & 1) * 32u);
           lh_mma_w(d, lh_desc(aHi + koff), bd, idesc2, ks ? 1u : 0u);     // A_hi x [W_hi ; W_lo]
@@ -132,11 +140,19 @@ lin_h_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
       tc_commit_w(bar_ae + 8 * st);        // the A tile is free once every pass has read it
     }
   } else {
-    // ===== epilogue: thread = row of the tile =====
+    // ===== epilogue warpgroup eg: thread = row of the tile, chunks eg, eg + G, ... of every pass =====
+    const int eg = (warp - 2) >> 2;
     const int qtr = warp & 3;
     const int row = qtr * 32 + lane;
     const uint32_t t_lane = tmem_base + ((uint32_t)(qtr * 32) << 16);
     const int H = a.nh * a.hd;
+    // modes 0 / 1 with staging: the tile leaves through 64-byte-swizzled 8 KB boxes (128 rows x 16 floats, or x 32 halves per
+    // plane) and TMA stores; written thread-per-row straight to global memory every store instruction touched 32 lines and
+    // the stores were 2/3 of the kernel time (M2TTS_LIN_DBG=1)
+    const bool tma_out = a.stg_bytes != 0;
+    uint8_t* stg = gbase + (sStg - sbase);
+    const uint32_t swz = (uint32_t)((row >> 1) & 3);
+    const bool leader = warp == 2 && lane == 0;
     int unit = 0;
     for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x) {
       const long long r = (long long)mt * LH_BM + row;
@@ -149,8 +165,13 @@ lin_h_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         mbar_wait(bar_cf + 8 * buf, (uint32_t)((unit >> 1) & 1));
         __syncwarp();
         tc_fence_after();
+        if (tma_out) {                      // the previous unit's TMA stores have read the staging tile
+          if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          asm volatile("bar.sync 1, %0;" ::"n"(128 * LH_G) : "memory");
+        }
         const uint32_t tb = t_lane + (uint32_t)buf * 256u;
-        for (int c0 = 0; c0 < a.np; c0 += 16) {
+        bool released = false;
+        for (int c0 = eg * 16; c0 < a.np; c0 += 16 * LH_G) {
           uint32_t v[16], w[16];
           float4 rs[4];
           if (a.mode == 0 && a.residual != nullptr && valid) {          // issue the residual loads ahead of the TMEM reads
@@ -164,12 +185,13 @@ lin_h_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
           tmem_ld16(tb + c0, v);
           tmem_ld16(tb + a.np + c0, w);
           tmem_wait_ld();
-          if (c0 + 16 >= a.np) {            // last TMEM read of this unit: hand the accumulator buffer back
+          if (c0 + 16 * LH_G >= a.np) {     // this warpgroup's last TMEM read of the unit: hand the accumulator buffer back
             tc_fence_before();
             __syncwarp();
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_ce + 8 * buf) : "memory");
+            released = true;
           }
-          if (!valid) continue;
+          if (!valid || (a.dbg & 1)) continue;
           float x[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
@@ -177,7 +199,13 @@ lin_h_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
             if (a.relu) t = fmaxf(t, 0.f);
             x[j] = t;
           }
-          if (a.mode == 0) {
+          if (a.mode == 0 && tma_out) {
+            uint8_t* bx = stg + (uint32_t)(c0 >> 4) * 8192u + (uint32_t)row * 64u;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<float4*>(bx + (((uint32_t)j ^ swz) << 4)) =
+                  make_float4(x[4 * j] + rs[j].x, x[4 * j + 1] + rs[j].y, x[4 * j + 2] + rs[j].z, x[4 * j + 3] + rs[j].w);
+          } else if (a.mode == 0) {
             float4* yp = reinterpret_cast<float4*>(a.y + r * a.ldy + n0 + c0);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
@@ -193,10 +221,20 @@ lin_h_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
               hi[j] = *reinterpret_cast<const uint32_t*>(&h);
               lo[j] = *reinterpret_cast<const uint32_t*>(&lw);
             }
-            uint4* hp = reinterpret_cast<uint4*>(a.y_planes + r * a.N + n0 + c0);
-            uint4* lp = reinterpret_cast<uint4*>(a.y_planes + ((long long)a.R + r) * a.N + n0 + c0);
-            hp[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]); hp[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-            lp[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]); lp[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+            if (tma_out) {
+              uint8_t* bh = stg + (uint32_t)(c0 >> 5) * 8192u + (uint32_t)row * 64u;
+              uint8_t* bl = bh + (uint32_t)(a.np >> 5) * 8192u;
+              const uint32_t p0 = (c0 & 16) ? 2u : 0u;
+              *reinterpret_cast<uint4*>(bh + ((p0 ^ swz) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              *reinterpret_cast<uint4*>(bh + (((p0 + 1u) ^ swz) << 4)) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+              *reinterpret_cast<uint4*>(bl + ((p0 ^ swz) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+              *reinterpret_cast<uint4*>(bl + (((p0 + 1u) ^ swz) << 4)) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+            } else {
+              uint4* hp = reinterpret_cast<uint4*>(a.y_planes + r * a.N + n0 + c0);
+              uint4* lp = reinterpret_cast<uint4*>(a.y_planes + ((long long)a.R + r) * a.N + n0 + c0);
+              hp[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]); hp[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+              lp[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]); lp[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+            }
           } else {
             // head_dim is a multiple of 16, so the 16 columns of a chunk belong to ONE (q|k|v, head): the index
             // arithmetic (two integer divisions) is done once per chunk, not per column
@@ -214,8 +252,32 @@ lin_h_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
             }
           }
         }
+        if (!released) {                    // narrow pass: this warpgroup had no chunk, the buffer still needs its arrival
+          __syncwarp();
+          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_ce + 8 * buf) : "memory");
+        }
+        if (tma_out) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          asm volatile("bar.sync 2, %0;" ::"n"(128 * LH_G) : "memory");
+          if (leader && !(a.dbg & 1)) {
+            const int r0 = mt * LH_BM;
+            if (a.mode == 0) {
+              for (int c = 0; c < (a.np >> 4); ++c)
+                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                             ::"l"(&tmap_y), "r"(n0 + 16 * c), "r"(r0), "r"(sStg + (uint32_t)c * 8192u) : "memory");
+            } else {
+              const int nb = a.np >> 5;
+              for (int pl = 0; pl < 2; ++pl)
+                for (int c = 0; c < nb; ++c)
+                  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
+                               ::"l"(&tmap_y), "r"(n0 + 32 * c), "r"(r0), "r"(pl), "r"(sStg + (uint32_t)(pl * nb + c) * 8192u) : "memory");
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
       }
     }
+    if (tma_out && leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
@@ -354,9 +416,16 @@ int launch_linear_h(const void* a_planes, const void* w_planes, const LinHParams
   a.bias = q.bias; a.relu = q.relu; a.residual = q.residual; a.ldr = q.ldr; a.y = q.y; a.ldy = q.ldy;
   a.y_planes = (__half*)q.y_planes; a.qkvh = (__half*)q.qkvh; a.plane_stride = q.plane_stride;
   a.L = q.L; a.nh = q.nh; a.hd = q.hd; a.Lp = q.Lp; a.qscale = q.qscale; a.mode = q.mode;
+  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("M2TTS_LIN_DBG"); dbg = e ? atoi(e) : 0; } a.dbg = dbg; }
   const size_t a_stage = (size_t)2 * a.kboxes * LH_BM * 64, w_bytes = (size_t)a.kboxes * 2 * a.N * 64;
-  const size_t fixed = w_bytes + (size_t)a.N * 4 + 16 + 256 + 1024;
+  a.stg_bytes = (q.mode == 0 && (q.ldy & 3) == 0 && (((uintptr_t)q.y) & 15) == 0) || (q.mode == 1 && a.np % 32 == 0) ? a.np * 512 : 0;
+  size_t fixed = w_bytes + (size_t)a.stg_bytes + (size_t)a.N * 4 + 16 + 256 + 1024;
   int st = (int)((225 * 1024 - fixed) / a_stage);
+  if (st < 1 && a.stg_bytes != 0) {      // no room for the staging tile: the epilogue stores directly
+    fixed -= (size_t)a.stg_bytes;
+    a.stg_bytes = 0;
+    st = (int)((225 * 1024 - fixed) / a_stage);
+  }
   a.a_stages = st > 4 ? 4 : st;
   M2_REQUIRE(a.a_stages >= 1, M2TTS_E_UNSUPPORTED, "linear_h: operands do not fit shared memory");
   const size_t smem = fixed + (size_t)a.a_stages * a_stage;
@@ -380,10 +449,27 @@ int launch_linear_h(const void* a_planes, const void* w_planes, const LinHParams
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     M2_REQUIRE(r == CUDA_SUCCESS, M2TTS_E_CUDA, "linear_h: tensor map (W) failed (%d)", (int)r);
   }
+  CUtensorMap ty = ta;      // placeholder when the epilogue stores directly
+  if (a.stg_bytes != 0 && q.mode == 0) {
+    const cuuint64_t dims[2] = {(cuuint64_t)a.N, (cuuint64_t)a.R};
+    const cuuint64_t strides[1] = {(cuuint64_t)q.ldy * 4};
+    const cuuint32_t box[2] = {16u, (cuuint32_t)LH_BM};
+    const CUresult r = enc(&ty, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, q.y, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    M2_REQUIRE(r == CUDA_SUCCESS, M2TTS_E_CUDA, "linear_h: tensor map (Y) failed (%d)", (int)r);
+  } else if (a.stg_bytes != 0) {
+    const cuuint64_t dims[3] = {(cuuint64_t)a.N, (cuuint64_t)a.R, 2};
+    const cuuint64_t strides[2] = {(cuuint64_t)a.N * 2, (cuuint64_t)a.R * a.N * 2};
+    const cuuint32_t box[3] = {32u, (cuuint32_t)LH_BM, 1u};
+    const cuuint32_t es3[3] = {1, 1, 1};
+    const CUresult r = enc(&ty, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, q.y_planes, dims, strides, box, es3, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    M2_REQUIRE(r == CUDA_SUCCESS, M2TTS_E_CUDA, "linear_h: tensor map (Y planes) failed (%d)", (int)r);
+  }
   M2_CUDA_OK(allow_smem(lin_h_kernel, smem));
   const int m_tiles = ceil_div(a.R, LH_BM);
   const int grid = m_tiles < kNumSMs ? m_tiles : kNumSMs;
-  M2_LAUNCH(stage, lin_h_kernel, grid, LH_THREADS, smem, s, ta, tw, a);
+  M2_LAUNCH(stage, lin_h_kernel, grid, LH_THREADS, smem, s, ta, tw, ty, a);
   return M2TTS_OK;
 }
 
