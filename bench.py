@@ -193,8 +193,8 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     if world > 1:
         import torch.distributed as dist_mod
         dist = dist_mod
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line (NCCL prints its version banner there)
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "WARN"):
+            os.environ["NCCL_DEBUG"] = "NONE"      # keep stdout to the one JSON line (from level VERSION up NCCL prints a banner there)
         dist.init_process_group("nccl", device_id=dev)
 
     torch.manual_seed(1234)
