@@ -33,7 +33,10 @@ struct LinHArgs {
   __half* y_planes;                // mode 1: [2][R][N]
   __half* qkvh; long long plane_stride; int L, nh, hd, Lp; float qscale;   // mode 3
   int mode;
+  int res_tma;                     // mode 0 with staging: the residual tile is TMA-loaded into the staging tile and updated in place
+  int tpu;                         // mode 3 with staging: 128-row tiles per utterance (tiles do not straddle utterances); else 0
   int stg_bytes;                   // > 0: the epilogue stages the output tile in shared memory and writes it with TMA stores (modes 0, 1)
+  long long* prof;                 // bring-up: phase timestamps of CTA 0's first epilogue warp (m2tts_attention_set_prof buffer)
   int dbg;                         // bring-up timing experiments (M2TTS_LIN_DBG): 1 no stores, 2 no UMMAs, 4 no A-tile loads; results invalid
 };
 
@@ -48,9 +51,14 @@ __device__ __forceinline__ void lh_mma_w(uint32_t d, uint64_t ad, uint64_t bd, u
                ::"r"(d), "l"(ad), "l"(bd), "r"(idesc), "r"(acc) : "memory");
 }
 
+__device__ __forceinline__ void lh_tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+               ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+
 __global__ void __launch_bounds__(LH_THREADS, 1)
 lin_h_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_y,
-             const LinHArgs a) {
+             const __grid_constant__ CUtensorMap tmap_r, const LinHArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (sbase - smem_u32(smem_raw));
@@ -64,21 +72,22 @@ lin_h_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
   const uint32_t sBias = sW + w_bytes;                                  // N floats
   const uint32_t sBar = (sBias + (uint32_t)a.N * 4u + 15u) & ~15u;
   // barriers: a_full[4] a_empty[4] acc_full[2] acc_empty[2] w_full
-  const uint32_t bar_af = sBar, bar_ae = sBar + 32, bar_cf = sBar + 64, bar_ce = sBar + 80, bar_w = sBar + 96, tmem_slot = sBar + 104;
+  const uint32_t bar_af = sBar, bar_ae = sBar + 32, bar_cf = sBar + 64, bar_ce = sBar + 80, bar_w = sBar + 96, bar_rs = sBar + 104, tmem_slot = sBar + 112;
   float* bias_s = reinterpret_cast<float*>(gbase + (sBias - sbase));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int m_tiles = (a.R + LH_BM - 1) / LH_BM;
+  const int m_tiles = a.tpu > 0 ? (a.R / a.L) * a.tpu : (a.R + LH_BM - 1) / LH_BM;
   const int S = a.a_stages;
 
   if (tid == 0) {
     for (int i = 0; i < 4; ++i) { mbar_init(bar_af + 8 * i, 1); mbar_init(bar_ae + 8 * i, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(bar_cf + 8 * i, 1); mbar_init(bar_ce + 8 * i, 4 * LH_G); }
-    mbar_init(bar_w, 1);
+    mbar_init(bar_w, 1); mbar_init(bar_rs, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_y) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_r) : "memory");
   }
   for (int i = tid; i < a.N; i += LH_THREADS) bias_s[i] = a.bias != nullptr ? a.bias[i] : 0.f;
   if (warp == 0) {
@@ -106,10 +115,13 @@ lin_h_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         if (it >= S) mbar_wait(bar_ae + 8 * st, (uint32_t)(((it / S) - 1) & 1));
         if (a.dbg & 4) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_af + 8 * st) : "memory"); continue; }
         mbar_expect_tx(bar_af + 8 * st, a_stage);
+        const int nb = a.tpu > 0 ? a.R / a.L : 0, ub = a.tpu > 0 ? mt / a.tpu : 0, ul = a.tpu > 0 ? (mt % a.tpu) * LH_BM : 0;
         for (int pl = 0; pl < 2; ++pl)
-          for (int kb = 0; kb < a.kboxes; ++kb)
-            tma_load_2d(sA + (uint32_t)st * a_stage + (uint32_t)(pl * a.kboxes + kb) * a_box, &tmap_a, kb * 32, pl * a.R + mt * LH_BM,
-                        bar_af + 8 * st);
+          for (int kb = 0; kb < a.kboxes; ++kb) {
+            const uint32_t dst = sA + (uint32_t)st * a_stage + (uint32_t)(pl * a.kboxes + kb) * a_box;
+            if (a.tpu > 0) lh_tma_load_3d(dst, &tmap_a, kb * 32, ul, pl * nb + ub, bar_af + 8 * st);      // rows >= L of the utterance: zero-filled
+            else tma_load_2d(dst, &tmap_a, kb * 32, pl * a.R + mt * LH_BM, bar_af + 8 * st);
+          }
       }
     }
   } else if (warp == 1) {
@@ -156,25 +168,54 @@ lin_h_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     int unit = 0;
     for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x) {
       const long long r = (long long)mt * LH_BM + row;
-      const bool valid = r < a.R;
+      bool valid = r < a.R;
       int b = 0, l = 0;
-      if (a.mode == 3 && valid) { b = (int)(r / a.L); l = (int)(r - (long long)b * a.L); }
+      if (a.tpu > 0) { b = mt / a.tpu; l = (mt % a.tpu) * LH_BM + row; valid = l < a.L; }
+      else if (a.mode == 3 && valid) { b = (int)(r / a.L); l = (int)(r - (long long)b * a.L); }
       for (int p = 0; p < a.n_passes; ++p, ++unit) {
         const int buf = unit & 1;
         const int n0 = p * a.np;
-        mbar_wait(bar_cf + 8 * buf, (uint32_t)((unit >> 1) & 1));
-        __syncwarp();
-        tc_fence_after();
-        if (tma_out) {                      // the previous unit's TMA stores have read the staging tile
+        const bool pt = a.prof != nullptr && blockIdx.x == 0 && warp == 2 && lane == 0 && unit < 48;
+        if (pt) a.prof[unit * 8 + 0] = clock64();
+        if (a.res_tma) {                    // the previous unit's TMA stores have read the staging tile
           if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           asm volatile("bar.sync 1, %0;" ::"n"(128 * LH_G) : "memory");
         }
+        if (a.res_tma && leader) {
+          // residual tile -> staging tile (same boxes as the output; rows >= R are zero-filled). Read thread-per-row straight
+          // from global memory these loads took 3-6 k cycles per unit (tools/lin_prof.py): 32 lines per load instruction.
+          mbar_expect_tx(bar_rs, (uint32_t)a.np * 512u);
+          for (int c = 0; c < (a.np >> 4); ++c)
+            tma_load_2d(sStg + (uint32_t)c * 8192u, &tmap_r, n0 + 16 * c, mt * LH_BM, bar_rs);
+          // and the next unit's residual tile towards L2: the staging tile is single, so its load cannot start before this
+          // unit's stores have drained, but it can at least find its data in L2
+          int mt2 = mt, p2 = p + 1;
+          if (p2 == a.n_passes) { p2 = 0; mt2 = mt + (int)gridDim.x; }
+          if (mt2 < m_tiles)
+            for (int c = 0; c < (a.np >> 4); ++c)
+              asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];"
+                           ::"l"(&tmap_r), "r"(p2 * a.np + 16 * c), "r"(mt2 * LH_BM) : "memory");
+        }
+        if (pt) a.prof[unit * 8 + 1] = clock64();
+        mbar_wait(bar_cf + 8 * buf, (uint32_t)((unit >> 1) & 1));
+        __syncwarp();
+        tc_fence_after();
+        if (a.res_tma) mbar_wait(bar_rs, (uint32_t)(unit & 1));
+        else if (tma_out) {                 // no residual to fetch: the staging tile is only needed now
+          if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          asm volatile("bar.sync 1, %0;" ::"n"(128 * LH_G) : "memory");
+        }
+        if (pt) a.prof[unit * 8 + 2] = clock64();
         const uint32_t tb = t_lane + (uint32_t)buf * 256u;
         bool released = false;
         for (int c0 = eg * 16; c0 < a.np; c0 += 16 * LH_G) {
           uint32_t v[16], w[16];
           float4 rs[4];
-          if (a.mode == 0 && a.residual != nullptr && valid) {          // issue the residual loads ahead of the TMEM reads
+          if (a.res_tma) {
+            const uint8_t* bx = stg + (uint32_t)(c0 >> 4) * 8192u + (uint32_t)row * 64u;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) rs[j] = *reinterpret_cast<const float4*>(bx + (((uint32_t)j ^ swz) << 4));
+          } else if (a.mode == 0 && a.residual != nullptr && valid) {          // issue the residual loads ahead of the TMEM reads
             const float4* rp = reinterpret_cast<const float4*>(a.residual + r * a.ldr + n0 + c0);
 #pragma unroll
             for (int j = 0; j < 4; ++j) rs[j] = __ldg(rp + j);
@@ -242,16 +283,38 @@ lin_h_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
             const int which = n / H, rem = n - which * H;
             const int head = rem / a.hd, d0 = rem - head * a.hd;
             const float sc = (which == 0) ? a.qscale : 1.0f;
-            __half* hp = a.qkvh + (long long)(2 * which) * a.plane_stride + (((long long)b * a.nh + head) * a.hd + d0) * a.Lp + l;
+            if (tma_out) {      // staging [plane][np d-rows][128 positions]: a warp writes 64 contiguous bytes per row
+              __half* sp = reinterpret_cast<__half*>(stg) + (uint32_t)c0 * 128u + (uint32_t)row;
+              // packed conversions (F2FP / HADD2.F32 run at full rate; the scalar cvt goes through the quarter-rate XU pipe and
+              // made this epilogue XU-bound)
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float t = fminf(fmaxf(x[j] * sc, -65000.f), 65000.f);
-              const __half h = __float2half_rn(t);
-              hp[(long long)j * a.Lp] = h;
-              hp[(long long)j * a.Lp + a.plane_stride] = __float2half_rn(t - __half2float(h));
+              for (int j = 0; j < 16; j += 2) {
+                const float t0 = fminf(fmaxf(x[j] * sc, -65000.f), 65000.f), t1 = fminf(fmaxf(x[j + 1] * sc, -65000.f), 65000.f);
+                const __half2 h = __floats2half2_rn(t0, t1);
+                const float2 hf = __half22float2(h);
+                const __half2 lo = __floats2half2_rn(t0 - hf.x, t1 - hf.y);
+                sp[j * 128] = __low2half(h);
+                sp[(j + 1) * 128] = __high2half(h);
+                sp[j * 128 + a.np * 128] = __low2half(lo);
+                sp[(j + 1) * 128 + a.np * 128] = __high2half(lo);
+              }
+            } else {
+              __half* hp = a.qkvh + (long long)(2 * which) * a.plane_stride + (((long long)b * a.nh + head) * a.hd + d0) * a.Lp + l;
+#pragma unroll
+              for (int j = 0; j < 16; j += 2) {
+                const float t0 = fminf(fmaxf(x[j] * sc, -65000.f), 65000.f), t1 = fminf(fmaxf(x[j + 1] * sc, -65000.f), 65000.f);
+                const __half2 h = __floats2half2_rn(t0, t1);
+                const float2 hf = __half22float2(h);
+                const __half2 lo = __floats2half2_rn(t0 - hf.x, t1 - hf.y);
+                hp[(long long)j * a.Lp] = __low2half(h);
+                hp[(long long)(j + 1) * a.Lp] = __high2half(h);
+                hp[(long long)j * a.Lp + a.plane_stride] = __low2half(lo);
+                hp[(long long)(j + 1) * a.Lp + a.plane_stride] = __high2half(lo);
+              }
             }
           }
         }
+        if (pt) a.prof[unit * 8 + 3] = clock64();
         if (!released) {                    // narrow pass: this warpgroup had no chunk, the buffer still needs its arrival
           __syncwarp();
           if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_ce + 8 * buf) : "memory");
@@ -261,7 +324,14 @@ lin_h_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
           asm volatile("bar.sync 2, %0;" ::"n"(128 * LH_G) : "memory");
           if (leader && !(a.dbg & 1)) {
             const int r0 = mt * LH_BM;
-            if (a.mode == 0) {
+            if (a.mode == 3) {      // pass p = q, k or v: one box of 128 positions x hd rows per (plane, head)
+              const int nbat = a.R / a.L, l0 = (mt % a.tpu) * LH_BM;
+              for (int pl = 0; pl < 2; ++pl)
+                for (int hh = 0; hh < a.nh; ++hh)
+                  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                               ::"l"(&tmap_y), "r"(l0), "r"((((2 * p + pl) * nbat + b) * a.nh + hh) * a.hd),
+                                 "r"(sStg + (uint32_t)((pl * a.np + hh * a.hd) * 256)) : "memory");
+            } else if (a.mode == 0) {
               for (int c = 0; c < (a.np >> 4); ++c)
                 asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
                              ::"l"(&tmap_y), "r"(n0 + 16 * c), "r"(r0), "r"(sStg + (uint32_t)c * 8192u) : "memory");
@@ -275,6 +345,7 @@ lin_h_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
         }
+        if (pt) a.prof[unit * 8 + 4] = clock64();
       }
     }
     if (tma_out && leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -403,6 +474,8 @@ int launch_w_split_h(const float* const* src, void* const* dst, const long long*
   return M2TTS_OK;
 }
 
+extern long long* g_ws_prof;      // attention_tc.cu (m2tts_attention_set_prof)
+
 // a_planes: fp16 [2][R][K]; w_planes: fp16 [2][N][K]
 int launch_linear_h(const void* a_planes, const void* w_planes, const LinHParams& q, int stage, cudaStream_t s) {
   M2_REQUIRE(linear_h_eligible(q.K, q.N), M2TTS_E_UNSUPPORTED, "linear_h: K=%d N=%d not eligible", q.K, q.N);
@@ -416,9 +489,12 @@ int launch_linear_h(const void* a_planes, const void* w_planes, const LinHParams
   a.bias = q.bias; a.relu = q.relu; a.residual = q.residual; a.ldr = q.ldr; a.y = q.y; a.ldy = q.ldy;
   a.y_planes = (__half*)q.y_planes; a.qkvh = (__half*)q.qkvh; a.plane_stride = q.plane_stride;
   a.L = q.L; a.nh = q.nh; a.hd = q.hd; a.Lp = q.Lp; a.qscale = q.qscale; a.mode = q.mode;
+  { static int ps = -2; if (ps == -2) { const char* e = getenv("M2TTS_LIN_PROF_STAGE"); ps = e ? atoi(e) : -1; } a.prof = (ps < 0 || ps == stage) ? g_ws_prof : nullptr; }
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("M2TTS_LIN_DBG"); dbg = e ? atoi(e) : 0; } a.dbg = dbg; }
   const size_t a_stage = (size_t)2 * a.kboxes * LH_BM * 64, w_bytes = (size_t)a.kboxes * 2 * a.N * 64;
-  a.stg_bytes = (q.mode == 0 && (q.ldy & 3) == 0 && (((uintptr_t)q.y) & 15) == 0) || (q.mode == 1 && a.np % 32 == 0) ? a.np * 512 : 0;
+  const bool stage3 = q.mode == 3 && a.np == q.nh * q.hd && q.L > 0 && q.R % q.L == 0 && q.plane_stride == (long long)(q.R / q.L) * q.nh * q.hd * q.Lp &&
+                      (q.Lp & 7) == 0 && (((uintptr_t)q.qkvh) & 15) == 0;
+  a.stg_bytes = (q.mode == 0 && (q.ldy & 3) == 0 && (((uintptr_t)q.y) & 15) == 0) || (q.mode == 1 && a.np % 32 == 0) || stage3 ? a.np * 512 : 0;
   size_t fixed = w_bytes + (size_t)a.stg_bytes + (size_t)a.N * 4 + 16 + 256 + 1024;
   int st = (int)((225 * 1024 - fixed) / a_stage);
   if (st < 1 && a.stg_bytes != 0) {      // no room for the staging tile: the epilogue stores directly
@@ -427,11 +503,21 @@ int launch_linear_h(const void* a_planes, const void* w_planes, const LinHParams
     st = (int)((225 * 1024 - fixed) / a_stage);
   }
   a.a_stages = st > 4 ? 4 : st;
+  a.tpu = (q.mode == 3 && a.stg_bytes != 0) ? ceil_div(q.L, LH_BM) : 0;
   M2_REQUIRE(a.a_stages >= 1, M2TTS_E_UNSUPPORTED, "linear_h: operands do not fit shared memory");
   const size_t smem = fixed + (size_t)a.a_stages * a_stage;
   CUtensorMap ta, tw;
   const cuuint32_t estr[2] = {1, 1};
-  {
+  if (a.tpu > 0) {      // per-utterance tiles: {K, L, plane * B + b}
+    const cuuint64_t dims[3] = {(cuuint64_t)a.K, (cuuint64_t)q.L, (cuuint64_t)2 * (a.R / q.L)};
+    const cuuint64_t strides[2] = {(cuuint64_t)a.K * 2, (cuuint64_t)q.L * a.K * 2};
+    const cuuint32_t box[3] = {32u, (cuuint32_t)LH_BM, 1u};
+    const cuuint32_t es3[3] = {1, 1, 1};
+    const CUresult r = enc(&ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(a_planes), dims, strides, box, es3,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    M2_REQUIRE(r == CUDA_SUCCESS, M2TTS_E_CUDA, "linear_h: tensor map (A, per utterance) failed (%d)", (int)r);
+  } else {
     const cuuint64_t dims[2] = {(cuuint64_t)a.K, (cuuint64_t)2 * a.R};
     const cuuint64_t strides[1] = {(cuuint64_t)a.K * 2};
     const cuuint32_t box[2] = {32u, (cuuint32_t)LH_BM};
@@ -449,7 +535,18 @@ int launch_linear_h(const void* a_planes, const void* w_planes, const LinHParams
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     M2_REQUIRE(r == CUDA_SUCCESS, M2TTS_E_CUDA, "linear_h: tensor map (W) failed (%d)", (int)r);
   }
-  CUtensorMap ty = ta;      // placeholder when the epilogue stores directly
+  CUtensorMap ty = ta, tr = ta;      // placeholders when the epilogue stores / loads directly
+  a.res_tma = 0;
+  if (a.stg_bytes != 0 && q.mode == 0 && q.residual != nullptr && (q.ldr & 3) == 0 && (((uintptr_t)q.residual) & 15) == 0) {
+    const cuuint64_t dims[2] = {(cuuint64_t)a.N, (cuuint64_t)a.R};
+    const cuuint64_t strides[1] = {(cuuint64_t)q.ldr * 4};
+    const cuuint32_t box[2] = {16u, (cuuint32_t)LH_BM};
+    const CUresult r = enc(&tr, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(q.residual), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    M2_REQUIRE(r == CUDA_SUCCESS, M2TTS_E_CUDA, "linear_h: tensor map (residual) failed (%d)", (int)r);
+    a.res_tma = 1;
+  }
   if (a.stg_bytes != 0 && q.mode == 0) {
     const cuuint64_t dims[2] = {(cuuint64_t)a.N, (cuuint64_t)a.R};
     const cuuint64_t strides[1] = {(cuuint64_t)q.ldy * 4};
@@ -457,6 +554,13 @@ int launch_linear_h(const void* a_planes, const void* w_planes, const LinHParams
     const CUresult r = enc(&ty, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, q.y, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                            CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     M2_REQUIRE(r == CUDA_SUCCESS, M2TTS_E_CUDA, "linear_h: tensor map (Y) failed (%d)", (int)r);
+  } else if (a.stg_bytes != 0 && q.mode == 3) {      // operand planes as {positions (clipped at L), all d-rows}
+    const cuuint64_t dims[2] = {(cuuint64_t)q.L, (cuuint64_t)6 * (a.R / q.L) * q.nh * q.hd};
+    const cuuint64_t strides[1] = {(cuuint64_t)q.Lp * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)LH_BM, (cuuint32_t)q.hd};
+    const CUresult r = enc(&ty, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, q.qkvh, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    M2_REQUIRE(r == CUDA_SUCCESS, M2TTS_E_CUDA, "linear_h: tensor map (attention planes) failed (%d)", (int)r);
   } else if (a.stg_bytes != 0) {
     const cuuint64_t dims[3] = {(cuuint64_t)a.N, (cuuint64_t)a.R, 2};
     const cuuint64_t strides[2] = {(cuuint64_t)a.N * 2, (cuuint64_t)a.R * a.N * 2};
@@ -467,9 +571,9 @@ int launch_linear_h(const void* a_planes, const void* w_planes, const LinHParams
     M2_REQUIRE(r == CUDA_SUCCESS, M2TTS_E_CUDA, "linear_h: tensor map (Y planes) failed (%d)", (int)r);
   }
   M2_CUDA_OK(allow_smem(lin_h_kernel, smem));
-  const int m_tiles = ceil_div(a.R, LH_BM);
+  const int m_tiles = a.tpu > 0 ? (a.R / q.L) * a.tpu : ceil_div(a.R, LH_BM);
   const int grid = m_tiles < kNumSMs ? m_tiles : kNumSMs;
-  M2_LAUNCH(stage, lin_h_kernel, grid, LH_THREADS, smem, s, ta, tw, ty, a);
+  M2_LAUNCH(stage, lin_h_kernel, grid, LH_THREADS, smem, s, ta, tw, ty, tr, a);
   return M2TTS_OK;
 }
 
