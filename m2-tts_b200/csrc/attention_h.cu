@@ -405,7 +405,8 @@ static int launch_ah_hd(const CUtensorMap& tmap, float* ctx, const int64_t* leng
   if (dbg_skip < 0) { const char* e = getenv("M2TTS_ATT_DBG"); dbg_skip = e ? atoi(e) : 0; }
   M2_CUDA_OK(allow_smem(attention_h_kernel<HD>, smem));
   dim3 grid((unsigned)(ceil_div(L, 2 * TC_BQ) * nh * B), 1, 1);
-  M2_LAUNCH(M2TTS_STAGE_ATTENTION, attention_h_kernel<HD>, grid, AH_THREADS, smem, s, tmap, ctx, lengths, B, L, nh, ctx_lo, ctx_h, g_ws_prof, dbg_skip);
+  M2_LAUNCH(M2TTS_STAGE_ATTENTION, attention_h_kernel<HD>, grid, AH_THREADS, smem, s, tmap, ctx, lengths, B, L, nh, ctx_lo, ctx_h,
+            getenv("M2TTS_LIN_PROF_STAGE") != nullptr ? nullptr : g_ws_prof, dbg_skip);      // the buffer belongs to tools/lin_prof.py then
   return M2TTS_OK;
 }
 
