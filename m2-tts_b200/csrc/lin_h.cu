@@ -33,6 +33,7 @@ struct LinHArgs {
   __half* y_planes;                // mode 1: [2][R][N]
   __half* qkvh; long long plane_stride; int L, nh, hd, Lp; float qscale;   // mode 3
   int mode;
+  int stg2;                        // 1: two staging tiles (units alternate), when shared memory allows
   int res_tma;                     // mode 0 with staging: the residual tile is TMA-loaded into the staging tile and updated in place
   int tpu;                         // mode 3 with staging: 128-row tiles per utterance (tiles do not straddle utterances); else 0
   int stg_bytes;                   // > 0: the epilogue stages the output tile in shared memory and writes it with TMA stores (modes 0, 1)
@@ -68,7 +69,7 @@ lin_h_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
   const uint32_t w_bytes = (uint32_t)a.kboxes * a.n_passes * 2u * w_box;
   const uint32_t sA = sbase;                                            // [stage][plane][kbox][128 x 64 B]
   const uint32_t sStg = sA + (uint32_t)a.a_stages * a_stage;            // output staging: 8 KB boxes of 128 rows x 64 B, 64-byte swizzle
-  const uint32_t sW = sStg + (uint32_t)a.stg_bytes;                     // [kbox][pass][plane][np x 64 B]
+  const uint32_t sW = sStg + (uint32_t)a.stg_bytes * (uint32_t)(1 + a.stg2);       // [kbox][pass][plane][np x 64 B]
   const uint32_t sBias = sW + w_bytes;                                  // N floats
   const uint32_t sBar = (sBias + (uint32_t)a.N * 4u + 15u) & ~15u;
   // barriers: a_full[4] a_empty[4] acc_full[2] acc_empty[2] w_full
@@ -162,7 +163,7 @@ lin_h_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     // plane) and TMA stores; written thread-per-row straight to global memory every store instruction touched 32 lines and
     // the stores were 2/3 of the kernel time (M2TTS_LIN_DBG=1)
     const bool tma_out = a.stg_bytes != 0;
-    uint8_t* stg = gbase + (sStg - sbase);
+    uint8_t* stg0 = gbase + (sStg - sbase);
     const uint32_t swz = (uint32_t)((row >> 1) & 3);
     const bool leader = warp == 2 && lane == 0;
     int unit = 0;
@@ -177,8 +178,12 @@ lin_h_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         const int n0 = p * a.np;
         const bool pt = a.prof != nullptr && blockIdx.x == 0 && warp == 2 && lane == 0 && unit < 48;
         if (pt) a.prof[unit * 8 + 0] = clock64();
-        if (a.res_tma) {                    // the previous unit's TMA stores have read the staging tile
-          if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        // with two staging tiles the units alternate and only the stores of the unit before the previous one must have drained
+        const uint32_t so = a.stg2 ? (uint32_t)(unit & 1) * (uint32_t)a.stg_bytes : 0u;
+        uint8_t* stg = stg0 + so;
+        const uint32_t sStgU = sStg + so;
+        if (a.res_tma) {                    // earlier TMA stores have read this staging tile
+          if (leader) { if (a.stg2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
           asm volatile("bar.sync 1, %0;" ::"n"(128 * LH_G) : "memory");
         }
         if (a.res_tma && leader) {
@@ -186,7 +191,7 @@ lin_h_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
           // from global memory these loads took 3-6 k cycles per unit (tools/lin_prof.py): 32 lines per load instruction.
           mbar_expect_tx(bar_rs, (uint32_t)a.np * 512u);
           for (int c = 0; c < (a.np >> 4); ++c)
-            tma_load_2d(sStg + (uint32_t)c * 8192u, &tmap_r, n0 + 16 * c, mt * LH_BM, bar_rs);
+            tma_load_2d(sStgU + (uint32_t)c * 8192u, &tmap_r, n0 + 16 * c, mt * LH_BM, bar_rs);
           // and the next unit's residual tile towards L2: the staging tile is single, so its load cannot start before this
           // unit's stores have drained, but it can at least find its data in L2
           int mt2 = mt, p2 = p + 1;
@@ -202,7 +207,7 @@ lin_h_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         tc_fence_after();
         if (a.res_tma) mbar_wait(bar_rs, (uint32_t)(unit & 1));
         else if (tma_out) {                 // no residual to fetch: the staging tile is only needed now
-          if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          if (leader) { if (a.stg2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
           asm volatile("bar.sync 1, %0;" ::"n"(128 * LH_G) : "memory");
         }
         if (pt) a.prof[unit * 8 + 2] = clock64();
@@ -330,17 +335,17 @@ lin_h_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                 for (int hh = 0; hh < a.nh; ++hh)
                   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
                                ::"l"(&tmap_y), "r"(l0), "r"((((2 * p + pl) * nbat + b) * a.nh + hh) * a.hd),
-                                 "r"(sStg + (uint32_t)((pl * a.np + hh * a.hd) * 256)) : "memory");
+                                 "r"(sStgU + (uint32_t)((pl * a.np + hh * a.hd) * 256)) : "memory");
             } else if (a.mode == 0) {
               for (int c = 0; c < (a.np >> 4); ++c)
                 asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
-                             ::"l"(&tmap_y), "r"(n0 + 16 * c), "r"(r0), "r"(sStg + (uint32_t)c * 8192u) : "memory");
+                             ::"l"(&tmap_y), "r"(n0 + 16 * c), "r"(r0), "r"(sStgU + (uint32_t)c * 8192u) : "memory");
             } else {
               const int nb = a.np >> 5;
               for (int pl = 0; pl < 2; ++pl)
                 for (int c = 0; c < nb; ++c)
                   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
-                               ::"l"(&tmap_y), "r"(n0 + 32 * c), "r"(r0), "r"(pl), "r"(sStg + (uint32_t)(pl * nb + c) * 8192u) : "memory");
+                               ::"l"(&tmap_y), "r"(n0 + 32 * c), "r"(r0), "r"(pl), "r"(sStgU + (uint32_t)(pl * nb + c) * 8192u) : "memory");
             }
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
@@ -500,6 +505,12 @@ int launch_linear_h(const void* a_planes, const void* w_planes, const LinHParams
   if (st < 1 && a.stg_bytes != 0) {      // no room for the staging tile: the epilogue stores directly
     fixed -= (size_t)a.stg_bytes;
     a.stg_bytes = 0;
+    st = (int)((225 * 1024 - fixed) / a_stage);
+  }
+  a.stg2 = 0;
+  if (a.stg_bytes != 0 && 225 * 1024 >= fixed + (size_t)a.stg_bytes + a_stage) {      // room for a second staging tile (and at least one A stage)
+    a.stg2 = 1;
+    fixed += (size_t)a.stg_bytes;
     st = (int)((225 * 1024 - fixed) / a_stage);
   }
   a.a_stages = st > 4 ? 4 : st;
