@@ -239,11 +239,20 @@ lin_h_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
           }
           if (!valid || (a.dbg & 1)) continue;
           float x[16];
+          {
+            const float4* bp = reinterpret_cast<const float4*>(bias_s + n0 + c0);      // 16-byte aligned: n0 + c0 is a multiple of 16
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float t = __uint_as_float(v[j]) + __uint_as_float(w[j]) + bias_s[n0 + c0 + j];
-            if (a.relu) t = fmaxf(t, 0.f);
-            x[j] = t;
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const float4 bv = bp[j4];
+              const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int j = 4 * j4 + e;
+                float t = __uint_as_float(v[j]) + __uint_as_float(w[j]) + bb[e];
+                if (a.relu) t = fmaxf(t, 0.f);
+                x[j] = t;
+              }
+            }
           }
           if (a.mode == 0 && tma_out) {
             uint8_t* bx = stg + (uint32_t)(c0 >> 4) * 8192u + (uint32_t)row * 64u;
@@ -284,9 +293,13 @@ lin_h_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
           } else {
             // head_dim is a multiple of 16, so the 16 columns of a chunk belong to ONE (q|k|v, head): the index
             // arithmetic (two integer divisions) is done once per chunk, not per column
-            const int n = n0 + c0;
-            const int which = n / H, rem = n - which * H;
-            const int head = rem / a.hd, d0 = rem - head * a.hd;
+            int which = p, head = 0, d0 = 0;
+            if (!tma_out) {     // direct stores need (q|k|v, head, d); with staging a pass is exactly q, k or v and the box does the rest
+              const int n = n0 + c0;
+              which = n / H;
+              const int rem = n - which * H;
+              head = rem / a.hd; d0 = rem - head * a.hd;
+            }
             const float sc = (which == 0) ? a.qscale : 1.0f;
             if (tma_out) {      // staging [plane][np d-rows][128 positions]: a warp writes 64 contiguous bytes per row
               __half* sp = reinterpret_cast<__half*>(stg) + (uint32_t)c0 * 128u + (uint32_t)row;
