@@ -38,7 +38,8 @@ struct RhCfg {
   static constexpr uint32_t OFF_CONST = OFF_W + WBYTES;
   static constexpr uint32_t OFF_BAR = OFF_CONST + 1024;
   static constexpr uint32_t TOTAL = OFF_BAR + 128 + 1024;
-  static constexpr int THREADS = 64 + 256;
+  static constexpr int NG = 2;                       // epilogue warpgroups, C / NG channels each (4 were measured: no faster)
+  static constexpr int THREADS = 64 + 128 * NG;
   static constexpr int T_C1 = 0, T_C2 = 2 * C;
   static_assert(C == 64, "fused ResBlock: C = 64");
   static_assert(TOTAL <= 227 * 1024, "fused ResBlock: shared memory");
@@ -108,8 +109,8 @@ voc_res_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   auto tile_of = [&](int it) { return it * (int)gridDim.x + (int)blockIdx.x; };
 
   if (tid == 0) {
-    for (int s = 0; s < 2; ++s) { ct_mbar_init(bar_xf + 8 * s, 1); ct_mbar_init(bar_xe + 8 * s, a.out_h != nullptr ? 1 : 8); }
-    ct_mbar_init(bar_c1, 1); ct_mbar_init(bar_vr, 8); ct_mbar_init(bar_c2, 1); ct_mbar_init(bar_w, 1);
+    for (int s = 0; s < 2; ++s) { ct_mbar_init(bar_xf + 8 * s, 1); ct_mbar_init(bar_xe + 8 * s, a.out_h != nullptr ? 1 : 4 * K::NG); }
+    ct_mbar_init(bar_c1, 1); ct_mbar_init(bar_vr, 4 * K::NG); ct_mbar_init(bar_c2, 1); ct_mbar_init(bar_w, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_x) : "memory");
   }
@@ -181,14 +182,14 @@ voc_res_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       }
     }
   } else {
-    // ===== epilogue warpgroup g: thread m owns TMEM lane m and channels [32 g, 32 g + 32) =====
+    // ===== epilogue warpgroup g: thread m owns TMEM lane m and channels [CG g, CG g + CG) =====
     const int g = (warp - 2) >> 2;
     const int qtr = warp & 3;
     const int m = qtr * 32 + lane;
     const uint32_t t_lane = tmem_base + ((uint32_t)(qtr * 32) << 16);
     uint8_t* Vb = gbase + K::O_V;
     const float* b1 = consts, *b2 = consts + C;
-    constexpr int CG = C / 2;
+    constexpr int CG = C / K::NG;
     const int cg0 = g * CG;
     for (int it = 0; it < n_iter; ++it) {
       const int gt = tile_of(it);
@@ -273,7 +274,7 @@ voc_res_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       if (a.out_h != nullptr) {
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(128 * K::NG) : "memory");
         if (leader && !a.dbg_nostore) {      // output rows m = 1 .. NOUT sit in slot rows 2 .. NOUT + 1; TMA clips positions >= L
           const uint32_t s0 = sbase + K::O_X + (uint32_t)(it & 1) * 2 * K::XPL + 2u * RB;
           asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4}], [%5];"
