@@ -624,9 +624,14 @@ extern "C" int m2tts_vocoder_forward(const m2tts_vocoder_weights* w, const float
     // ResBlocks with CI = M zero-padded to 128 (the padding costs nothing: TMA zero-fills, the k-steps beyond M are skipped)
     __half* mp = reinterpret_cast<__half*>(bufC);
     const long long mplane = (long long)B * T * M;
-    dim3 grid(ceil_div(T, 32), ceil_div(M, 32), B);
-    M2_LAUNCH(M2TTS_STAGE_VOC_IN, mel_to_planes_kernel, grid, 256, 0, s, mel, (long long)stride_b, (long long)stride_m, (long long)stride_t,
-              mp, mplane, M, T);
+    if (stride_m == 1 && stride_t == M && stride_b == (int64_t)T * M && (((uintptr_t)mel) & 15) == 0 && (mplane & 7) == 0) {
+      // the decoder's own [B,T,M] output (tts_model.py:390 passes its transpose view): already channel-last, a flat split
+      if ((rc = launch_split_planes_h(mel, mp, mplane, s))) return rc;
+    } else {
+      dim3 grid(ceil_div(T, 32), ceil_div(M, 32), B);
+      M2_LAUNCH(M2TTS_STAGE_VOC_IN, mel_to_planes_kernel, grid, 256, 0, s, mel, (long long)stride_b, (long long)stride_m, (long long)stride_t,
+                mp, mplane, M, T);
+    }
     if ((rc = launch_voc_conv_h(mp, mplane, w->in_w, w->in_b, in_wb, nullptr, 0, bufA, (long long)B * T * C, nullptr, 0, B, M, C, T, 0,
                                 M2TTS_STAGE_VOC_IN, s))) return rc;
   } else if (path[0] == P_TC && conv3_tc_eligible(M, C) && B <= 65535) {
