@@ -22,6 +22,7 @@ struct ResHArgs {
   const float* bias1; const float* bias2;
   __half* out_h; long long out_plane;    // fp16 hi/lo planes [2][B][L][C], or
   float* out_f;                          // fp32 channel-last [B][L][C]
+  long long* prof;                       // bring-up: phase timestamps of CTA 0's first epilogue warp (m2tts_attention_set_prof buffer)
   int dbg_nostore;                       // bring-up timing experiment (M2TTS_DBG_NOSTORE=1): skip the plane stores, results invalid
 };
 
@@ -201,8 +202,11 @@ voc_res_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       const bool inside = t >= 0 && t < a.L;
       const uint8_t* Xb = gbase + K::O_X + (uint32_t)(it & 1) * 2 * K::XPL;
 
+      const bool pt = a.prof != nullptr && blockIdx.x == 0 && warp == 2 && lane == 0 && it < 48;
+      if (pt) a.prof[it * 8 + 0] = clock64();
       // ---- EPI2: conv1 accumulator -> V = lrelu(. + bias), zero outside the utterance, fp16 hi/lo rows ----
       ct_wait(bar_c1, par, dbg, 9, it);
+      if (pt) a.prof[it * 8 + 1] = clock64();
       __syncwarp();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       {
@@ -227,6 +231,7 @@ voc_res_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) ct_arrive(bar_vr);
+      if (pt) a.prof[it * 8 + 2] = clock64();
 
       // planes mode: the previous tile's output left through TMA stores that read its input slot; once they have read it the
       // slot goes back to the producer (the leader has nothing else to do while conv2 runs)
@@ -238,6 +243,7 @@ voc_res_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 
       // ---- EPI3: conv2 accumulator + bias + u (row m + 1 of the input tile) -> output ----
       ct_wait(bar_c2, par, dbg, 10, it);
+      if (pt) a.prof[it * 8 + 3] = clock64();
       __syncwarp();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
@@ -271,6 +277,7 @@ voc_res_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           for (int j4 = 0; j4 < 4; ++j4) op[j4] = make_float4(y[4 * j4], y[4 * j4 + 1], y[4 * j4 + 2], y[4 * j4 + 3]);
         }
       }
+      if (pt) a.prof[it * 8 + 4] = clock64();
       if (a.out_h != nullptr) {
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -283,6 +290,7 @@ voc_res_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                        ::"l"(&tmap_y), "r"(0), "r"(k * K::NOUT), "r"(b), "r"(1), "r"(s0 + K::XPL) : "memory");
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
+        if (pt) a.prof[it * 8 + 5] = clock64();
         continue;
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -331,6 +339,7 @@ static EncodeTiledFn7 rh_encode_fn() {
   return fn;
 }
 
+extern long long* g_ws_prof;      // attention_tc.cu (m2tts_attention_set_prof)
 bool voc_res_h_eligible(int C, int dil) { return C == 64 && dil == 1; }
 size_t voc_res_h_wblob_bytes(int C) { return C == 64 ? RhCfg<64>::WBYTES : 0; }
 
@@ -360,6 +369,7 @@ int launch_voc_res_h(const void* uh, long long u_plane, const float* w1, const f
   ResHArgs a{};
   a.B = B; a.L = L; a.wblob = (const __half*)wblob; a.bias1 = b1; a.bias2 = b2;
   a.out_h = (__half*)out_h; a.out_plane = out_plane;
+  a.prof = g_ws_prof;
   { static int ns = -1; if (ns < 0) { const char* e = getenv("M2TTS_DBG_NOSTORE"); ns = (e && e[0] == '1') ? 1 : 0; } a.dbg_nostore = ns; } a.out_f = out_f;
   a.tiles_per_utt = ceil_div(L, K::NOUT);
   a.total_tiles = B * a.tiles_per_utt;
