@@ -184,8 +184,8 @@ def workload_config(n_gpus: int):
 # --------------------------------------------------------------------------------------------
 def run_b200(args, rank: int, world: int, local_rank: int):
     from models import _native as nat
+    from models.stage_configs import STAGE_KWARGS
     from models.tts_model import M2TTSModel
-    from oracle import m2tts_oracle as oracle
 
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
@@ -198,7 +198,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         dist.init_process_group("nccl", device_id=dev)
 
     torch.manual_seed(1234)
-    model = M2TTSModel(**oracle.STAGE_KWARGS[STAGE]).eval().to(dev)
+    model = M2TTSModel(**STAGE_KWARGS[STAGE]).eval().to(dev)
     x_host = torch.randn(BATCH, FRAMES, HIDDEN, generator=torch.Generator().manual_seed(rank)).pin_memory()
     x_dev = x_host.to(dev)
     audio_host = torch.empty((BATCH, 1, FRAMES * SAMPLES_PER_FRAME), dtype=torch.float32).pin_memory()

@@ -9,11 +9,11 @@ for p in (str(ROOT), str(ROOT / "m2-tts_b200" / "src")):
 import torch
 from models import _native as nat
 from models.tts_model import M2TTSModel
-from oracle import m2tts_oracle as oracle
+from models.stage_configs import STAGE_KWARGS
 lib = nat.lib()
 lib.m2tts_attention_set_prof.argtypes = [C.c_void_p]
 torch.manual_seed(1234)
-m = M2TTSModel(**oracle.STAGE_KWARGS["stage2"]).eval().cuda()
+m = M2TTSModel(**STAGE_KWARGS["stage2"]).eval().cuda()
 x = torch.randn(64, 3446, 96, device="cuda")
 prof = torch.zeros(2 * 48 * 8, dtype=torch.int64, device="cuda")
 m.decoder(x)

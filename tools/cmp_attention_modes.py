@@ -5,10 +5,10 @@ sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/m2-tts_b200/src')
 import torch
 from models import _native as nat
 from models.tts_model import M2TTSModel
-from oracle import m2tts_oracle as oracle
+from models.stage_configs import STAGE_KWARGS
 lib=nat.lib()
 torch.manual_seed(1234)
-m = M2TTSModel(**oracle.STAGE_KWARGS["stage2"]).eval().cuda()
+m = M2TTSModel(**STAGE_KWARGS["stage2"]).eval().cuda()
 for L in (1, 64, 65, 128, 129, 192, 193, 256, 257, 300, 512, 700):
     x = torch.randn(2, L, 96, device="cuda")
     lib.m2tts_set_attention_mode(3); a = m.decoder(x).clone()

@@ -8,13 +8,13 @@ for p in (str(ROOT), str(ROOT / "m2-tts_b200" / "src")):
     sys.path.insert(0, p)
 import torch  # noqa: E402
 from models.tts_model import M2TTSModel  # noqa: E402
-from oracle import m2tts_oracle as oracle  # noqa: E402
+from models.stage_configs import STAGE_KWARGS  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 T = int(sys.argv[2]) if len(sys.argv) > 2 else 3446
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 torch.manual_seed(1234)
-m = M2TTSModel(**oracle.STAGE_KWARGS["stage2"]).eval().cuda()
+m = M2TTSModel(**STAGE_KWARGS["stage2"]).eval().cuda()
 x = torch.randn(B, T, 96, device="cuda")
 for _ in range(reps):
     y = m.decoder(x)

@@ -8,10 +8,10 @@ for p in (str(ROOT), str(ROOT / "m2-tts_b200" / "src")):
     sys.path.insert(0, p)
 import torch
 from models.tts_model import M2TTSModel
-from oracle import m2tts_oracle as oracle
+from models.stage_configs import STAGE_KWARGS
 torch.manual_seed(1234)
 dev = torch.device("cuda:0")
-m = M2TTSModel(**oracle.STAGE_KWARGS["stage2"]).eval().to(dev)
+m = M2TTSModel(**STAGE_KWARGS["stage2"]).eval().to(dev)
 
 
 def step(x):

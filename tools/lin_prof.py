@@ -14,9 +14,9 @@ lib.m2tts_attention_set_prof.argtypes = [C.c_void_p]
 # one QKV-shaped GEMM through the layernorm_proj entry (mode 0) is not mode 3; run a full layer and keep the QKV launch by
 # stopping after it: simplest is to run the decoder and read the buffer after the first layer's QKV only -> we use a 1-layer model
 from models.tts_model import M2TTSModel
-from oracle import m2tts_oracle as oracle
+from models.stage_configs import STAGE_KWARGS
 torch.manual_seed(1234)
-m = M2TTSModel(**oracle.STAGE_KWARGS["stage2"]).eval().cuda()
+m = M2TTSModel(**STAGE_KWARGS["stage2"]).eval().cuda()
 x = torch.randn(64, 3446, 96, device="cuda")
 prof = torch.zeros(2 * 48 * 8, dtype=torch.int64, device="cuda")
 m.decoder(x)

@@ -10,10 +10,10 @@ for p in (str(ROOT), str(ROOT / "m2-tts_b200" / "src")):
     sys.path.insert(0, p)
 import torch  # noqa: E402
 from models.tts_model import M2TTSModel  # noqa: E402
-from oracle import m2tts_oracle as oracle  # noqa: E402
+from models.stage_configs import STAGE_KWARGS  # noqa: E402
 
 torch.manual_seed(1234)
-m = M2TTSModel(**oracle.STAGE_KWARGS["stage2"]).eval().cuda()
+m = M2TTSModel(**STAGE_KWARGS["stage2"]).eval().cuda()
 rows = ["batch,frames,ms,audio_s_per_s"]
 for B in (1, 2, 4, 8, 16, 32, 64, 128, 256):
     for T in (128, 256, 512, 1024, 2048):
