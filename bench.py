@@ -1,21 +1,26 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the B200 synthesis path (contract: see DESIGN.md §Measurement).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config c3|c1|c2|c5]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (BASELINE.json configs[2], "C3"): stage2_quality VAE-less transformer mel decoder +
-HiFi-GAN-style vocoder, 64 utterances x 3446 frames (10.0 s at 22.05 kHz) PER GPU (weak scaling:
-C4 = 8 x 64 = 512 utterances at N=8), seeded random-init weights, synthetic `regulated_output`.
-One step = decoder + vocoder over the batch. Metric = audio-seconds synthesised per second.
+Headline workload (BASELINE.json configs[2], "C3"): stage2_quality transformer mel decoder + HiFi-GAN-style vocoder,
+64 utterances x 3446 frames (10.0 s at 22.05 kHz) PER GPU (weak scaling: C4 = 8 x 64 = 512 utterances at N=8), seeded
+random-init weights, synthetic `regulated_output`. One step = decoder + vocoder over the batch. Metric = audio-seconds
+synthesised per second.
 
-  value : inputs resident in HBM, CUDA events per step, max over ranks
-  e2e   : same step through the module API from PINNED HOST input to PINNED HOST waveform
-          (H2D + D2H inside the timed region)
-  roofline     : dominant kernel, timed live by the library's per-launch CUDA events
-  cpu_baseline : the oracle port (torch CPU, all host threads) on a bounded sample (rank 0, N=1)
-  --impl reference : the reference's CPU implementation of the path (the oracle port: the
-          reference is pure Python and cannot travel to the GPU box), same metric/config.
+  value        : inputs resident in HBM, CUDA events per step, max over ranks; nothing but the step inside the timed region
+                 (no stage timers, status word read once after the region)
+  e2e          : same step through the module API from PINNED HOST input to PINNED HOST waveform (H2D + D2H inside the
+                 timed region, utils.host_pipeline.HostPipeline)
+  e2e_from_ids : the whole model from host phoneme ids (S = 256, 3446 frames) to a host waveform (SURVEY §8d C3 e2e variant)
+  parity       : utterance 0 of the timed step's own output against the CPU oracle; the run fails above 1e-4
+  roofline     : dominant kernel, timed by the library's per-launch CUDA events in a SEPARATE instrumented pass
+  cpu_baseline : the reference's CPU path (oracle/_ref = the unmodified reference modules when vendored by
+                 oracle/build_ref.py, else the oracle port) on a bounded sample (rank 0, N=1)
+  gather       : at N > 1, the all-gather of the sharded waveforms after the path (utils.shard.gather_batch), timed apart
+  --impl reference : the reference's CPU implementation of the path, same metric/config, all host threads
+  --config c1|c2|c5 : secondary lines for BASELINE.json configs[0], [1], [4] (headline stays C3)
 """
 from __future__ import annotations
 
@@ -43,6 +48,7 @@ HIDDEN, MEL, LAYERS, VOC = 96, 80, 3, 256
 SAMPLES_PER_FRAME, SAMPLE_RATE = 64, 22050
 METRIC = "audio-sec/sec (synthesis RTF^-1)"
 UNIT = "audio-s/s"
+PARITY_TOL = 1e-4
 
 
 def audio_seconds(n_utt: int, frames: int = FRAMES) -> float:
@@ -116,7 +122,7 @@ class ClockSampler:
                             self.reasons.add(k)
             except Exception:
                 pass
-            self._stop.wait(0.05)
+            self._stop.wait(0.02)
 
     def start(self):
         self._thr = threading.Thread(target=self._loop, daemon=True)
@@ -131,44 +137,84 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------
-def cpu_port_step(sd, x, oracle):
-    mel = oracle.mel_decoder(sd, x, 2)
-    return oracle.vocoder(sd, mel.transpose(1, 2))
+# CPU arm: the reference's own modules (oracle/_ref, vendored by oracle/build_ref.py where /root/reference exists) or,
+# without them, the oracle port. Only this leg and the parity check touch oracle/.
+class CpuPath:
+    def __init__(self, stage: str = STAGE):
+        from oracle import build_ref
+        from oracle import m2tts_oracle as oracle
+        self.oracle = oracle
+        self.threads = os.cpu_count() or 1
+        torch.set_num_threads(self.threads)
+        kw = oracle.STAGE_KWARGS[stage]
+        self.heads = kw["num_heads"]
+        if build_ref.available():
+            ref = build_ref.load()
+            torch.manual_seed(1234)
+            self.model = ref.M2TTSModel(**kw).eval()      # unmodified reference code, its own seeded init
+            self.kind = "reference"
+            self.sd = None
+        else:
+            from models.tts_model import M2TTSModel
+            torch.manual_seed(1234)
+            self.sd = M2TTSModel(**kw).eval().state_dict()
+            self.model = None
+            self.kind = "port"
 
+    @torch.no_grad()
+    def decoder_vocoder(self, x: torch.Tensor, chunk: int = 8) -> torch.Tensor:
+        """reference tts_model.py:211-228, 279-297 on utterance chunks (utterances are independent in eval mode; chunking
+        bounds the materialised [chunk, 2, T, T] score tensors of components.py:75-87 to 0.76 GB per layer)."""
+        outs = []
+        for lo in range(0, x.shape[0], chunk):
+            xs = x[lo:lo + chunk]
+            if self.model is not None:
+                mel = self.model.decoder(xs)
+                outs.append(self.model.vocoder(mel.transpose(1, 2)))
+            else:
+                mel = self.oracle.mel_decoder(self.sd, xs, self.heads)
+                outs.append(self.oracle.vocoder(self.sd, mel.transpose(1, 2)))
+        return torch.cat(outs, 0)
 
-def time_cpu_port(n_utt: int, reps: int, warm: int, seed: int = 0):
-    """The reference's CPU path (oracle port: torch CPU fp32, scores materialised exactly like
-    components.py:75-87) on `n_utt` utterances of the C3 workload. Returns (audio-s/s list, threads)."""
-    from oracle import m2tts_oracle as oracle
-    threads = os.cpu_count() or 1
-    torch.set_num_threads(threads)
-    torch.manual_seed(1234)
-    from models.tts_model import M2TTSModel
-    sd = M2TTSModel(**oracle.STAGE_KWARGS[STAGE]).eval().state_dict()
-    x = torch.randn(n_utt, FRAMES, HIDDEN, generator=torch.Generator().manual_seed(seed))
-    vals = []
-    with torch.no_grad():
+    def time_c3(self, n_utt: int, reps: int, warm: int, seed: int = 0):
+        x = torch.randn(n_utt, FRAMES, HIDDEN, generator=torch.Generator().manual_seed(seed))
+        vals = []
         for i in range(warm + reps):
             t0 = time.perf_counter()
-            cpu_port_step(sd, x, oracle)
+            self.decoder_vocoder(x)
             dt = time.perf_counter() - t0
             if i >= warm:
                 vals.append(audio_seconds(n_utt) / dt)
-    return vals, threads
+        return vals
 
 
 def run_reference(args, rank: int):
+    """`--impl reference`: the reference's CPU implementation of the C3 step on all host threads. A step processes as many
+    of the 64 utterances as keep the whole run within ~2 minutes (a power of two >= 8; the sample is stated in the line)."""
     if rank != 0:
         return
+    cpu = CpuPath()
+    x8 = torch.randn(8, FRAMES, HIDDEN, generator=torch.Generator().manual_seed(0))
+    cpu.decoder_vocoder(x8[:2])                                   # page in
+    t0 = time.perf_counter()
+    cpu.decoder_vocoder(x8)
+    t8 = time.perf_counter() - t0
+    total_steps = max(args.steps + args.warmup, 1)
     n_utt = 8
-    vals, threads = time_cpu_port(n_utt, reps=args.steps, warm=args.warmup)
+    while n_utt < BATCH and (2 * n_utt / 8) * t8 * total_steps <= 120.0:
+        n_utt *= 2
+    vals = cpu.time_c3(n_utt, reps=args.steps, warm=args.warmup)
     value = audio_seconds(n_utt) * len(vals) / sum(audio_seconds(n_utt) / v for v in vals)
-    sample = f"{n_utt} of {BATCH} utterances x {FRAMES} frames per step (decoder+vocoder), torch CPU fp32"
+    sample = (f"{n_utt} of {BATCH} utterances x {FRAMES} frames per step (decoder+vocoder, same per-utterance work; bounded so that "
+              f"{total_steps} steps end within ~2 min), torch CPU fp32, {cpu.threads} threads")
+    cfg = workload_config(args.gpus)
+    cfg["workload"] += f" [reference arm: {n_utt} of the 64 utterances per step]"
+    cfg["utterances_per_step_reference_arm"] = n_utt
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * audio_seconds(n_utt) / value,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args.gpus), "gpu_launches": 0,
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "config": cfg, "gpu_launches": 0,
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cpu.threads, "kind": cpu.kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -182,20 +228,40 @@ def workload_config(n_gpus: int):
 
 
 # --------------------------------------------------------------------------------------------
+def setup_dist(world: int, dev):
+    if world <= 1:
+        return None
+    import torch.distributed as dist
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "WARN"):
+        os.environ["NCCL_DEBUG"] = "NONE"      # keep stdout to the one JSON line (from level VERSION up NCCL prints a banner there)
+    dist.init_process_group("nccl", device_id=dev)
+    return dist
+
+
+def ffma_peak(nat, dev) -> float:
+    """fp32 FFMA peak of this GPU right now (no such number in MEASURED_PEAKS.json)."""
+    import ctypes as C
+    sink = torch.zeros(4, device=dev)
+    flops = C.c_double(0.0)
+    nat.check(nat.lib().m2tts_ffma_probe(sink.data_ptr(), 4096, C.byref(flops), nat.stream_handle(dev)), "probe")
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    nat.check(nat.lib().m2tts_ffma_probe(sink.data_ptr(), 65536, C.byref(flops), nat.stream_handle(dev)), "probe")
+    e1.record()
+    torch.cuda.synchronize(dev)
+    return flops.value / (e0.elapsed_time(e1) * 1e-3) / 1e12
+
+
 def run_b200(args, rank: int, world: int, local_rank: int):
     from models import _native as nat
     from models.stage_configs import STAGE_KWARGS
     from models.tts_model import M2TTSModel
+    from utils.host_pipeline import HostPipeline
 
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist_mod
-        dist = dist_mod
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "WARN"):
-            os.environ["NCCL_DEBUG"] = "NONE"      # keep stdout to the one JSON line (from level VERSION up NCCL prints a banner there)
-        dist.init_process_group("nccl", device_id=dev)
+    dist = setup_dist(world, dev)
 
     torch.manual_seed(1234)
     model = M2TTSModel(**STAGE_KWARGS[STAGE]).eval().to(dev)
@@ -214,102 +280,180 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for _ in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    for _ in range(warm):                 # eager: packs the weight images, validates the status word per stage
         step(x_dev)
     torch.cuda.synchronize(dev)
+    ffma_peak_tflops = ffma_peak(nat, dev)
 
-    # fp32 FFMA peak of this GPU right now (no such number in MEASURED_PEAKS.json)
-    sink = torch.zeros(4, device=dev)
-    import ctypes as C
-    flops = C.c_double(0.0)
-    nat.check(nat.lib().m2tts_ffma_probe(sink.data_ptr(), 4096, C.byref(flops), nat.stream_handle(dev)), "probe")
-    torch.cuda.synchronize(dev)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    nat.check(nat.lib().m2tts_ffma_probe(sink.data_ptr(), 65536, C.byref(flops), nat.stream_handle(dev)), "probe")
-    e1.record()
-    torch.cuda.synchronize(dev)
-    ffma_peak_tflops = flops.value / (e0.elapsed_time(e1) * 1e-3) / 1e12
-
-    # ---- timed region: K steps, device-resident input ----
+    # ---- timed region: K steps, device-resident input, nothing else on the stream ----
     sampler = ClockSampler(local_rank)
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     barrier()
     sampler.start()
-    nat.stage_timing_enable(True)
     launches0 = nat.launch_count()
-    for i in range(args.steps):
-        flush.fill_(i & 0xFF)            # evict L2 between steps (outside the event pair)
-        starts[i].record()
-        step(x_dev)
-        ends[i].record()
+    with nat.deferred_status():
+        for i in range(args.steps):
+            flush.fill_(i & 0xFF)            # evict L2 between steps (outside the event pair)
+            starts[i].record()
+            audio_dev = step(x_dev)
+            ends[i].record()
     barrier()
     launches = nat.launch_count() - launches0
-    nat.stage_timing_enable(False)
     clocks = sampler.stop()
-    stage_ms = nat.stage_timing_read()
+    nat.check_status(dev, "timed region")     # raises if any step left the fp16 range: the number would be invalid
     total_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
+    mel_dev0 = model.decoder(x_dev[:1])       # utterance 0 again, for the parity check below (bit-identical rows)
+
+    # ---- instrumented pass (not part of any headline number): per-kernel CUDA events keyed by stage ----
+    prof_steps = 3
+    nat.stage_timing_enable(True)
+    with nat.deferred_status():
+        for i in range(prof_steps):
+            flush.fill_(i & 0xFF)
+            step(x_dev)
+    torch.cuda.synchronize(dev)
+    nat.stage_timing_enable(False)
+    stage_ms = nat.stage_timing_read()
+    nat.check_status(dev, "instrumented pass")
 
     # ---- e2e: pinned host in -> pinned host out, copies inside the timed region. The caller-facing helper
     # (utils.host_pipeline.HostPipeline) chunks the utterance batch so the PCIe copies overlap compute. ----
-    from utils.host_pipeline import HostPipeline
     pipe = HostPipeline(dev, n_chunks=args.e2e_chunks, edge=args.e2e_edge)
-    for _ in range(2):
-        pipe.run(step, x_host, audio_host)
-        pipe.synchronize()
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        pipe.run(step, x_host, audio_host)
-        pipe.synchronize()               # the caller needs the waveform on the host
-    barrier()
-    e2e_s = time.perf_counter() - t0
+    with nat.deferred_status():
+        for _ in range(2):
+            pipe.run(step, x_host, audio_host)
+            pipe.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            pipe.run(step, x_host, audio_host)
+            pipe.synchronize()               # the caller needs the waveform on the host
+        barrier()
+        e2e_s = time.perf_counter() - t0
+    nat.check_status(dev, "e2e region")
+    e2e_first = audio_host[0].clone()
 
-    t = torch.tensor([total_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    # ---- e2e from phoneme ids: the whole model (encoder, duration predictor, length regulator, decoder, vocoder) ----
+    S = 256
+    g = torch.Generator().manual_seed(100 + rank)
+    ids_host = torch.randint(0, 256, (BATCH, S), generator=g).pin_memory()
+    len_host = torch.full((BATCH,), S, dtype=torch.int64).pin_memory()
+    dur = torch.full((BATCH, S), 13.0)
+    for b in range(BATCH):
+        dur[b, torch.randperm(S, generator=g)[:FRAMES - 13 * S]] = 14.0
+    dur_host = (dur + 0.5).pin_memory()
+
+    def synth_from_ids(ids, lens, durs):
+        return model(ids, lens, target_durations=durs, max_target_length=FRAMES)["audio_output"]
+
+    def ids_step():
+        n = args.e2e_chunks
+        outs = []
+        for lo, hi in HostPipeline.bounds(BATCH, n):
+            i_d = ids_host[lo:hi].to(dev, non_blocking=True)
+            l_d = len_host[lo:hi].to(dev, non_blocking=True)
+            d_d = dur_host[lo:hi].to(dev, non_blocking=True)
+            y = synth_from_ids(i_d, l_d, d_d)
+            done = torch.cuda.Event(); done.record()
+            with torch.cuda.stream(pipe.d2h):
+                pipe.d2h.wait_event(done)
+                audio_host[lo:hi].copy_(y, non_blocking=True)
+            y.record_stream(pipe.d2h)
+            outs.append(y)
+        pipe.d2h.synchronize()
+
+    with nat.deferred_status():
+        for _ in range(2):
+            ids_step()
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            ids_step()
+        barrier()
+        ids_s = time.perf_counter() - t0
+    nat.check_status(dev, "e2e-from-ids region")
+
+    # ---- N > 1: all-gather of the sharded waveforms after the path, timed apart from the path ----
+    gather_ms = None
+    gather_ok = None
+    if dist is not None:
+        from utils.shard import gather_batch, shard_bounds
+        n_total = BATCH * world
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        full = gather_batch(audio_dev, n_total)
+        g1.record()
+        barrier()
+        lo, hi = shard_bounds(n_total, rank, world)
+        gather_ok = bool(full.shape[0] == n_total and torch.equal(full[lo:hi], audio_dev))
+        gt = torch.tensor([g0.elapsed_time(g1), 0.0 if gather_ok else 1.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(gt, op=dist.ReduceOp.MAX)
+        gather_ms, gather_ok = float(gt[0]), float(gt[1]) == 0.0
+        del full
+
+    t = torch.tensor([total_ms, e2e_s * 1e3, ids_s * 1e3], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms = float(t[0]), float(t[1])
+    total_ms, e2e_ms, ids_ms = float(t[0]), float(t[1]), float(t[2])
 
+    rc = 0
     if rank == 0:
+        # ---- parity of what was just timed: utterance 0 against the CPU oracle (decoder 0.5 s, vocoder 0.2 s of CPU) ----
+        from oracle import m2tts_oracle as oracle
+        sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+        with torch.no_grad():
+            want_mel = oracle.mel_decoder(sd, x_host[:1].clone(), 2)
+            want_audio = oracle.vocoder(sd, want_mel.transpose(1, 2))
+        got_audio = audio_dev[:1].cpu()
+        parity = {"max_abs_mel": float((mel_dev0.cpu() - want_mel).abs().max()),
+                  "max_abs_audio": float((got_audio - want_audio).abs().max()),
+                  "e2e_equals_device_path": bool(torch.equal(e2e_first, got_audio[0])),
+                  "tolerance": PARITY_TOL,
+                  "checked": "utterance 0 of rank 0's timed batch (decoder -> mel, vocoder -> waveform) vs oracle/m2tts_oracle.py on the CPU"}
+        parity["ok"] = bool(parity["max_abs_mel"] <= PARITY_TOL and parity["max_abs_audio"] <= PARITY_TOL and parity["e2e_equals_device_path"])
+        if not parity["ok"]:
+            rc = 3
+
         n_utt_total = BATCH * world
         aud = audio_seconds(n_utt_total)
         value = aud * args.steps / (total_ms * 1e-3)
         e2e_value = aud * args.steps / (e2e_ms * 1e-3)
+        ids_value = aud * args.steps / (ids_ms * 1e-3)
         peaks = measured_peaks()
         # dominant stage by summed device time; algorithmic FLOPs per step from SURVEY §8d's model
         fl = stage_flops_per_step()
         dom = max(stage_ms.items(), key=lambda kv: kv[1][0]) if stage_ms else ("none", (0.0, 1))
-        dom_ms_per_step = dom[1][0] / args.steps
+        dom_ms_per_step = dom[1][0] / prof_steps
         tensor_stages = {"attention": "tcgen05 kind::f16, 16-bit split (fp16 hi/lo, 3 product terms, fp32 accumulate): issued MMA FLOPs = 3x algorithmic",
-                         "voc_in": "tcgen05 3xTF32 tap-GEMM (after a strided -> channel-first copy of the mel), writes fp16 hi/lo planes channel-last",
+                         "voc_in": "channel-last 16-bit split conv kernel (CI = 80 zero-padded to 128 by TMA) after a flat fp32 -> fp16 hi/lo split of the mel",
                          "voc_up": "stages 0-1 transposed convs: polyphase channel-last tcgen05 kind::f16 16-bit split kernel with TMA stores (voc_up_h.cu)",
                          "voc_res1": "stage 0 conv1 (C=128, channel-last 16-bit split conv kernel) + the whole stage-1 ResBlock (C=64, one fused 16-bit split kernel)",
-                         "voc_res2": "stage 0 conv2 + residual (C=128, channel-last 16-bit split conv kernel, writes fp32 channel-first)",
+                         "voc_res2": "stage 0 conv2 + residual (C=128, channel-last 16-bit split conv kernel)",
                          "voc_fused": "stages 2-3: upsample + ResBlock (+ output conv + tanh) fused, channel-last tcgen05 kind::f16 16-bit split"}
         roof = {"kernel": dom[0], "bound": "tensor", "unit": "TFLOP/s", "stage_ms_per_step": dom_ms_per_step,
-                "launches_per_step": dom[1][1] // args.steps, "launch_ms": dom[1][0] / max(dom[1][1], 1),
+                "launches_per_step": dom[1][1] // prof_steps, "launch_ms": dom[1][0] / max(dom[1][1], 1),
                 "peak": peaks["bf16_tflops_sustained"],
                 "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']})",
                 "traffic": read_traffic(dom[0]), "fp32_ffma_peak_tflops": ffma_peak_tflops,
+                "measured_in": f"separate instrumented pass of {prof_steps} steps (per-launch CUDA events on the launching stream)",
                 "path": tensor_stages.get(dom[0], "fp32 FFMA")}
         if dom[0] in fl and dom_ms_per_step > 0:
             ach = fl[dom[0]] / (dom_ms_per_step * 1e-3) / 1e12
             roof.update(achieved=ach, frac=ach / peaks["bf16_tflops_sustained"],
                         algorithmic_flops_per_step=fl[dom[0]],
                         note="achieved = algorithmic (useful fp32-equivalent) FLOPs / device time of the stage; an fp32-faithful "
-                             "split-precision kernel issues 3 products per algorithmic one: ceiling 1/3 of the bf16 peak with fp16 "
-                             "halves (attention, linear layers, ResBlocks, narrow stages), 1/6 with TF32 halves (input conv)")
+                             "split-precision kernel issues 3 products per algorithmic one: ceiling 1/3 of the bf16 peak with fp16 halves")
         else:
             roof.update(achieved=None, frac=None)
-        all_stage_tflops = {k: round(fl[k] / (v[0] / args.steps * 1e-3) / 1e12, 2) for k, v in stage_ms.items()
+        all_stage_tflops = {k: round(fl[k] / (v[0] / prof_steps * 1e-3) / 1e12, 2) for k, v in stage_ms.items()
                             if k in fl and v[0] > 0}
-        # every stage as a fraction of ITS roofline: GEMM-shaped stages against the measured bf16 tensor peak (an
-        # fp32-faithful 3xTF32 kernel tops out at 1/6 of it), streaming stages against the measured HBM copy bandwidth
         by = stage_bytes_per_step()
         stage_roofline = {}
         for k, v in stage_ms.items():
-            sec = v[0] / args.steps * 1e-3
+            sec = v[0] / prof_steps * 1e-3
             if sec <= 0:
                 continue
             if k in by:
@@ -318,30 +462,45 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                                      "frac": round(ach / peaks["hbm_gbs"], 4)}
             elif k in fl:
                 ach = fl[k] / sec / 1e12
-                stage_roofline[k] = {"bound": "tensor" if k in tensor_stages or k in TENSOR_LINEAR else "ffma",
-                                     "achieved": round(ach, 2), "unit": "TFLOP/s",
-                                     "peak": peaks["bf16_tflops_sustained"] if (k in tensor_stages or k in TENSOR_LINEAR) else round(ffma_peak_tflops, 1),
-                                     "frac": round(ach / (peaks["bf16_tflops_sustained"] if (k in tensor_stages or k in TENSOR_LINEAR) else ffma_peak_tflops), 4)}
+                tens = k in tensor_stages or k in TENSOR_LINEAR
+                stage_roofline[k] = {"bound": "tensor" if tens else "ffma", "achieved": round(ach, 2), "unit": "TFLOP/s",
+                                     "peak": peaks["bf16_tflops_sustained"] if tens else round(ffma_peak_tflops, 1),
+                                     "frac": round(ach / (peaks["bf16_tflops_sustained"] if tens else ffma_peak_tflops), 4)}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+                "warmup": warm, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": workload_config(world), "clocks": clocks, "gpu_launches": launches,
+                "launches_per_step": launches // max(args.steps, 1),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4,
                         "d2h_bytes_per_step": audio_host.numel() * 4, "ms_per_step": e2e_ms / args.steps,
+                        "exposed_copy_ms": e2e_ms / args.steps - total_ms / args.steps,
                         "api": f"utils.host_pipeline.HostPipeline(n_chunks={args.e2e_chunks}, edge={args.e2e_edge}).run(decoder+vocoder, pinned host in, pinned host out)"},
+                "e2e_from_ids": {"value": ids_value, "unit": UNIT, "ms_per_step": ids_ms / args.steps,
+                                 "h2d_bytes_per_step": ids_host.numel() * 8 + len_host.numel() * 8 + dur_host.numel() * 4,
+                                 "d2h_bytes_per_step": audio_host.numel() * 4,
+                                 "api": f"M2TTSModel.forward(ids[{BATCH},{S}], lengths, target_durations, max_target_length={FRAMES}) in {args.e2e_chunks} utterance chunks, pinned host ids in, pinned host waveform out"},
+                "parity": parity,
                 "roofline": roof, "stage_roofline": stage_roofline, "stage_tflops": all_stage_tflops,
-                "stage_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in sorted(stage_ms.items(), key=lambda kv: -kv[1][0])},
+                "stage_ms_per_step": {k: round(v[0] / prof_steps, 4) for k, v in sorted(stage_ms.items(), key=lambda kv: -kv[1][0])},
                 "x_realtime_per_gpu": value / world}
+        if gather_ms is not None:
+            line["gather"] = {"ms": gather_ms, "bytes_per_rank": audio_dev.numel() * 4, "equals_local_shard": gather_ok,
+                              "api": "utils.shard.gather_batch (NCCL all_gather of [B/N,1,64T] fp32 waveforms), after the path, not in `value`"}
+            if not gather_ok:
+                rc = 4
         if world == 1 and not args.skip_cpu_baseline:
-            n_s = 8
-            vals, threads = time_cpu_port(n_s, reps=2, warm=0)
-            vals = [max(vals)]
-            line["cpu_baseline"] = {"value": vals[0], "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": f"{n_s} of {BATCH} utterances x {FRAMES} frames, best of 2 passes, torch CPU fp32"}
+            cpu = CpuPath()
+            n_s = 16
+            cpu.decoder_vocoder(torch.randn(2, FRAMES, HIDDEN))           # page in
+            vals = cpu.time_c3(n_s, reps=1, warm=0)
+            line["cpu_baseline"] = {"value": vals[0], "unit": UNIT, "cores": cpu.threads, "kind": cpu.kind,
+                                    "sample": f"{n_s} of {BATCH} utterances x {FRAMES} frames, one pass, torch CPU fp32 ({'oracle/_ref: the unmodified reference modules' if cpu.kind == 'reference' else 'oracle port'})"}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+    if rc:
+        raise SystemExit(rc)
 
 
 def stage_flops_per_step():
@@ -357,7 +516,7 @@ def stage_flops_per_step():
     for j, r in enumerate((4, 4, 2, 2)):
         c, Lc = c_in // 2, Lc * r
         up, res = 2 * 2 * c_in * c * Lc * B, 2 * 3 * c * c * Lc * B       # two taps per output sample; one k=3 conv
-        if j < 2:      # wide stages: upsampling tap-GEMM, then two conv launches (C = 128) or one fused ResBlock launch (C = 64,
+        if j < 2:      # wide stages: upsampling kernel, then two conv launches (C = 128) or one fused ResBlock launch (C = 64,
             fl["voc_up"] += up          # accounted under voc_res1)
             fl["voc_res1"] += res if j == 0 else 2 * res
             fl["voc_res2"] += res if j == 0 else 0
@@ -377,10 +536,9 @@ def stage_bytes_per_step():
     F = 2 * HIDDEN
     per = rows * 4
     return {"layernorm": (2 * LAYERS) * 2 * rows * HIDDEN * 4 + 2 * rows * HIDDEN * 4,   # 2 per layer + the final one: x in, LN(x) out
-            # K = 96 linear layers sit at the 3xTF32 ridge (36 FLOP/B): reported against HBM, every operand once in fp32
+            # K = 96 linear layers sit at the split-precision ridge: reported against HBM, every operand once in fp32
             "ln_qkv": LAYERS * per * (HIDDEN + 3 * HIDDEN), "out_proj": LAYERS * per * 3 * HIDDEN,
-            "ffn1": LAYERS * per * (HIDDEN + F), "ffn2": LAYERS * per * (F + 2 * HIDDEN), "ln_proj": per * (HIDDEN + MEL),
-            "pack": 2 * 4 * sum(x * 4 for x in (3 * HIDDEN * HIDDEN, HIDDEN * HIDDEN, 2 * HIDDEN * HIDDEN, 2 * HIDDEN * HIDDEN)) * LAYERS}
+            "ffn1": LAYERS * per * (HIDDEN + F), "ffn2": LAYERS * per * (F + 2 * HIDDEN), "ln_proj": per * (HIDDEN + MEL)}
 
 
 def read_traffic(kernel: str):
@@ -393,12 +551,115 @@ def read_traffic(kernel: str):
     return None
 
 
+# --------------------------------------------------------------------------------------------
+# Secondary lines: BASELINE.json configs[0] (C1), [1] (C2), [4] (C5). One GPU, same JSON shape, `config.workload` names them.
+def _time_calls(fn, steps: int, warmup: int, dev) -> float:
+    """Median milliseconds of fn() measured with CUDA events around each call (host enqueue included: these small
+    configurations are launch-bound, which is the point of measuring them)."""
+    for _ in range(max(warmup, 3)):
+        fn()
+    torch.cuda.synchronize(dev)
+    ts = []
+    for _ in range(steps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record()
+        torch.cuda.synchronize(dev)
+        ts.append(a.elapsed_time(b))
+    return statistics.median(ts)
+
+
+def run_secondary(args, local_rank: int):
+    from models import _native as nat
+    from models.stage_configs import STAGE_KWARGS
+    from models.tts_model import M2TTSModel
+    from oracle import m2tts_oracle as oracle
+    from utils.graph import GraphedStep
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    cfg = args.config
+    base = {"metric": METRIC, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "secondary": True}
+    if cfg in ("c1", "c2"):
+        torch.manual_seed(1234)
+        model = M2TTSModel(**STAGE_KWARGS["stage1"]).eval().to(dev)
+        sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    if cfg == "c1":
+        # "Hello world" through TextProcessor (SURVEY §8d C1): ids[0:11] = 39,21,6,24,11,40,35,7,24,17,39, rest 39, length 9.
+        from utils.text import TextProcessor
+        tp = TextProcessor().process_text("Hello world", max_length=256)
+        ids = torch.as_tensor(tp["phoneme_ids"], dtype=torch.int64).reshape(1, -1)
+        lens = torch.tensor([int(tp["length"])])
+        res = {}
+        for scale in (1.0, 4.0):        # scale 1: every random-init duration truncates to 0 -> one zero frame (the reference's edge case)
+            ids_h, lens_h = ids.pin_memory(), lens.pin_memory()
+
+            def call():
+                mel, audio = model.inference(ids_h.to(dev, non_blocking=True), lens_h.to(dev, non_blocking=True), scale)
+                return mel, audio.cpu()
+            mel, audio = call()
+            want_mel, want_audio = oracle.inference(sd, ids, lens, scale)
+            # truncation boundary: compare shapes, and values when the frame counts agree (SURVEY §7 "hard parts")
+            ok = mel.shape == want_mel.shape and float((audio - want_audio).abs().max()) <= PARITY_TOL
+            ms = _time_calls(call, args.steps, args.warmup, dev)
+            frames = int(mel.shape[1])
+            res[f"scale{scale:g}"] = {"ms_per_call": ms, "frames": frames, "audio_s_per_s": audio_seconds(1, frames) / (ms * 1e-3), "parity_ok": bool(ok)}
+        main = res["scale4"]
+        line = dict(base, value=main["audio_s_per_s"], ms_per_step=main["ms_per_call"],
+                    config={"workload": "C1 stage1_poc random-init single-utterance synthesis 'Hello world' through M2TTSModel.inference "
+                                        "(host ids in, host waveform out), duration_scale 4 (scale 1 gives the reference's zero-frame edge case)"},
+                    detail=res, e2e={"value": main["audio_s_per_s"], "unit": UNIT, "h2d_bytes_per_step": 256 * 8 + 8,
+                                     "d2h_bytes_per_step": main["frames"] * 64 * 4})
+    elif cfg == "c2":
+        g = torch.Generator().manual_seed(0)
+        ids = torch.randint(0, 256, (16, 64), generator=g)
+        lengths = torch.randint(32, 65, (16,), generator=g)
+        dur = torch.randint(1, 9, (16, 64), generator=g).float()
+        ids_d, len_d, dur_d = ids.to(dev), lengths.to(dev), dur.to(dev)
+        out = model(ids_d, len_d, target_durations=dur_d)
+        ref = oracle.forward(sd, ids, lengths, dur)
+        T = int(out["mel_output"].shape[1])
+        valid = float(model.length_regulator.last_frames.sum()) * SAMPLES_PER_FRAME / SAMPLE_RATE
+        parity = {"max_abs_mel": float((out["mel_output"].cpu() - ref["mel_output"]).abs().max()),
+                  "max_abs_audio": float((out["audio_output"].cpu() - ref["audio_output"]).abs().max()), "tolerance": PARITY_TOL}
+        ms = _time_calls(lambda: model(ids_d, len_d, target_durations=dur_d), args.steps, args.warmup, dev)
+        before = nat.launch_count()
+        model(ids_d, len_d, target_durations=dur_d)
+        launches = nat.launch_count() - before
+        line = dict(base, value=valid / (ms * 1e-3), ms_per_step=ms, gpu_launches=launches,
+                    config={"workload": f"C2 stage1_poc full pipeline (encoder, duration predictor, length regulator, decoder, vocoder), batch 16, "
+                                        f"64 phonemes, T = {T} frames, {valid:.2f} valid audio-s per step, inputs in HBM, one host read (frame maximum)"},
+                    padded_value=audio_seconds(16, T) / (ms * 1e-3), parity=parity)
+    else:       # c5: vocoder-only sweep
+        torch.manual_seed(1234)
+        model = M2TTSModel(**STAGE_KWARGS["stage2"]).eval().to(dev)
+        rows = []
+        for B in (1, 4, 16, 64, 256):
+            for T in (128, 512, 2048):
+                if B * T > 64 * 2048 * 2:
+                    continue
+                mel = torch.randn(B, 80, T, device=dev)
+                ms = _time_calls(lambda: model.vocoder(mel), max(args.steps // 2, 3), 3, dev)
+                rows.append({"B": B, "T": T, "ms": round(ms, 4), "audio_s_per_s": round(audio_seconds(B, T) / (ms * 1e-3), 1)})
+        mel1 = torch.randn(1, 80, 128, device=dev)
+        graphed = GraphedStep(lambda m_: model.vocoder(m_), mel1)
+        ms_graph = _time_calls(lambda: graphed(mel1, check=False), args.steps, args.warmup, dev)
+        ms_eager = next(r["ms"] for r in rows if r["B"] == 1 and r["T"] == 128)
+        best = max(rows, key=lambda r: r["audio_s_per_s"])
+        line = dict(base, value=best["audio_s_per_s"], ms_per_step=best["ms"],
+                    config={"workload": f"C5 HiFi-GAN vocoder-only mel->wave sweep, stage2 (80 mel, 256 channels); value = best point (B={best['B']}, T={best['T']})"},
+                    sweep=rows, small_batch={"B": 1, "T": 128, "eager_ms": ms_eager, "cuda_graph_ms": round(ms_graph, 4),
+                                             "launches_in_graph": graphed.launches_captured,
+                                             "audio_s_per_s_graph": round(audio_seconds(1, 128) / (ms_graph * 1e-3), 1)})
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="c3", choices=["c3", "c1", "c2", "c5"], help="c3 = headline (BASELINE configs[2]); c1/c2/c5 = secondary lines")
     ap.add_argument("--skip-cpu-baseline", action="store_true", help="profiling runs: omit the CPU leg")
     ap.add_argument("--e2e-chunks", type=int, default=3, help="utterance chunks of the host-to-host pipeline (1 = no overlap)")
     ap.add_argument("--e2e-edge", type=float, default=1.0, help="relative size of the first and last chunk (their copies are the unhidden ones)")
@@ -411,6 +672,10 @@ def main():
         return
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference for the CPU path)")
+    if args.config != "c3":
+        if rank == 0:
+            run_secondary(args, local_rank)
+        return
     run_b200(args, rank, world, local_rank)
 
 

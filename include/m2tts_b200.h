@@ -10,17 +10,38 @@
  * Conventions
  *   - plain C, no torch types: raw DEVICE pointers + sizes + a CUDA stream
  *     handle (cudaStream_t passed as void*; NULL = legacy default stream);
- *   - the caller owns every buffer (inputs, outputs, workspace); the library
- *     allocates nothing and keeps no pointer after a call returns;
- *   - all work is enqueued on the caller's stream, no implicit synchronisation
- *     (the only host read on the path is the caller's own read-back of `t_max`
- *     after m2tts_length_regulate_count when max_length is not given);
+ *   - the caller owns every buffer (inputs, outputs, workspace, packed weight
+ *     images, the status word); the library allocates nothing and keeps no
+ *     pointer after a call returns;
+ *   - all work is enqueued on the caller's stream on the CURRENT CUDA device,
+ *     no implicit synchronisation (the only host read on the path is the
+ *     caller's own read-back of `t_max` after m2tts_length_regulate_count when
+ *     max_length is not given);
  *   - return value: 0 = ok, negative = error (M2TTS_E_*); the message is
  *     available per thread from m2tts_last_error_string(); nothing throws;
  *   - floating point tensors are contiguous fp32 unless strides are passed;
  *     `lengths`/`ids` are int64 as on the reference's Python API;
  *   - re-entrant: no mutable global state except the opt-in stage timers and
- *     the launch counter (both atomics / guarded).
+ *     the launch counter (both atomics / guarded). Kernel selection is a
+ *     per-call argument (`precision`), not a process-wide switch.
+ *
+ * Status word.  Entry points that take `int32_t* status` (device memory, may be
+ * NULL = do not report) OR the M2TTS_ST_* bits below into it with an atomic on
+ * the rare path; the caller zeroes it and reads it whenever it synchronises.
+ * A set bit means the OUTPUT OF THAT CALL IS NOT VALID:
+ *   M2TTS_ST_FP16_RANGE  an operand of the 16-bit split (precision 0) left the
+ *                        fp16 range (|x| > 65504) or was not finite: run the
+ *                        call again with M2TTS_PREC_TF32 (no range limit);
+ *   M2TTS_ST_BAD_ID      m2tts_embed_posenc saw an id outside [0, vocab): the
+ *                        reference's nn.Embedding raises IndexError.
+ *
+ * Packed weights.  The tensor-core kernels read weights from re-arranged images
+ * (fp16 or TF32 hi/lo planes, swizzled shared-memory images). m2tts_*_pack
+ * writes the images of one module into a caller-owned device buffer of
+ * m2tts_*_pack_bytes; the forward entry points take that buffer as `packed`
+ * (valid for the same shapes and precision until the weights change). With
+ * packed == NULL the forward packs into its workspace on every call (stateless
+ * form, a few extra small launches).
  */
 #ifndef M2TTS_B200_H_
 #define M2TTS_B200_H_
@@ -41,6 +62,23 @@ enum {
   M2TTS_E_WORKSPACE = -3,   /* workspace too small / misaligned             */
   M2TTS_E_CUDA = -4,        /* a CUDA runtime call or launch failed         */
   M2TTS_E_NULLPTR = -5      /* a required pointer is NULL                   */
+};
+
+/* bits of the device status word */
+enum {
+  M2TTS_ST_FP16_RANGE = 1,
+  M2TTS_ST_BAD_ID = 2
+};
+
+/* `precision` argument of the GEMM-shaped entry points. Every choice is fp32-faithful (max-abs 1e-4 against the
+ * reference's fp32, tests/test_gpu_parity.py); they differ in speed and operand range. */
+enum {
+  M2TTS_PREC_DEFAULT = -1, /* SPLIT16 unless the environment overrides it for A/B measurements
+                              (M2TTS_PRECISION=split16|ffma|tf32, read once)                                   */
+  M2TTS_PREC_SPLIT16 = 0,  /* tcgen05 kind::f16, operands as fp16 hi + lo, 3 products, fp32 accumulate.
+                              |operand| <= 65504 or M2TTS_ST_FP16_RANGE is raised                              */
+  M2TTS_PREC_FFMA = 1,     /* fp32 FFMA kernels (any shape)                                                    */
+  M2TTS_PREC_TF32 = 2      /* tcgen05 kind::tf32, operands as TF32 hi + lo, 3 products; no range limit         */
 };
 
 /* stage ids for the opt-in per-kernel timers (m2tts_stage_timing_*) */
@@ -118,40 +156,36 @@ int m2tts_stage_timing_read(float* ms_sum, int* launches, int n_stages);
 /* Diagnostics: the tensor-core kernels bound every mbarrier wait; on a timeout they store
  * {code, chunk, blockIdx.x, blockIdx.y, blockIdx.z} in pinned host memory and trap. */
 int m2tts_debug_words(int* out, int n);
-/* Attention kernel selection for m2tts_transformer_layer (head_dim in {16,32,48,64}; other head dims always take the
- * fp32 FFMA kernel): 0 (default) = tcgen05 warp-specialised kernel with the 16-bit split (fp16 hi/lo operands, fp32
- * accumulation; operands saturate at +-65000); 1 = fp32 FFMA kernel; 2 = TF32 split, single-warpgroup kernel;
- * 3 = TF32 split, warp-specialised kernel (no range limit). Process-wide; also M2TTS_ATTENTION=ffma|tc1|tf32. */
-int m2tts_set_attention_mode(int mode);
-/* Vocoder kernel selection: 0 (default) = tensor cores: the input conv and the wide stages as TF32-split tap-GEMMs, the
- * narrow stages (C in {32,16}) as fused channel-last kernels with the 16-bit split (activations saturate at +-65000);
- * 1 = fp32 FFMA everywhere; 2 = as 0 but the fused stages use the TF32 split (no range limit). Shapes the tensor
- * kernels do not take fall back to FFMA per stage. Process-wide; also M2TTS_VOCODER=ffma|tf32. */
-int m2tts_set_vocoder_mode(int mode);
-/* fp32 FFMA peak probe: `iters` dependent-chain FFMAs per thread on a full grid;
- * writes nothing but a checksum; returns flop count through *flops. */
+/* fp32 FFMA peak probe (bench.py's roofline denominator for the FFMA kernels): `iters` dependent-chain FFMAs per
+ * thread on a full grid; writes nothing but a checksum; returns the flop count through *flops. */
 int m2tts_ffma_probe(float* sink, int iters, double* flops, m2tts_stream_t stream);
 
 /* ---- text encoder pieces (tts_model.py:57-89) ------------------------------ */
 
 /* x[b,s,:] = emb[ids[b,s],:]*sqrt(H) + pe[s,:]  (tts_model.py:78-80,
  * components.py:39); mask[b,s] = s < lengths[b] (components.py:226-241) when
- * both `lengths` and `mask` are non-NULL. */
+ * both `lengths` and `mask` are non-NULL. An id outside [0, vocab) raises
+ * M2TTS_ST_BAD_ID in *status (its row is computed from a clamped id and is not valid). */
 int m2tts_embed_posenc(const int64_t* ids, const float* emb, const float* pe,
                        const int64_t* lengths, float* x, uint8_t* mask,
-                       int B, int S, int H, int vocab, m2tts_stream_t stream);
+                       int B, int S, int H, int vocab, int32_t* status, m2tts_stream_t stream);
 
 /* bytes of scratch one transformer layer needs for [B,L,H] with ffn dim F */
 size_t m2tts_transformer_workspace_bytes(int B, int L, int H, int F);
+/* packed images of one layer's four weight matrices for `precision` */
+size_t m2tts_transformer_pack_bytes(int H, int F, int precision);
+int m2tts_transformer_pack(const m2tts_layer_weights* w, int H, int F, int precision, void* packed,
+                           size_t packed_bytes, int32_t* status, m2tts_stream_t stream);
 
 /* One pre-LN transformer layer, eval mode (components.py:131-140):
  *   x1 = x + out_proj(softmax(mask(q k^T / sqrt(hd))) v),  q,k,v = split(qkv(LN1(x)))
  *   y  = x1 + W2 relu(W1 LN2(x1) + b1) + b2
  * `lengths` (int64 [B]) masks KEYS only with the reference's finite -1e9 fill
- * (components.py:77-81); NULL = no mask (decoder). x_in may equal x_out. */
-int m2tts_transformer_layer(const m2tts_layer_weights* w, const float* x_in,
+ * (components.py:77-81); NULL = no mask (decoder). x_in may equal x_out.
+ * `packed`: NULL or the buffer written by m2tts_transformer_pack for the same (H, F, precision). */
+int m2tts_transformer_layer(const m2tts_layer_weights* w, const void* packed, const float* x_in,
                             float* x_out, const int64_t* lengths, int B, int L,
-                            int H, int num_heads, int F, float ln_eps,
+                            int H, int num_heads, int F, float ln_eps, int precision, int32_t* status,
                             void* workspace, size_t workspace_bytes,
                             m2tts_stream_t stream);
 
@@ -160,13 +194,17 @@ int m2tts_layernorm(const float* x, const float* w, const float* b, float* y,
                     int rows, int H, float eps, m2tts_stream_t stream);
 
 /* y[rows,N] = LayerNorm(x) @ W^T + bias (tts_model.py:223-226: decoder.norm then
- * mel_projection, W [N,H]). workspace: m2tts_ln_proj_workspace_bytes(H,N). */
+ * mel_projection, W [N,H]). workspace: m2tts_ln_proj_rows_workspace_bytes(rows,H,N) lets the call run on
+ * the tensor cores (normalised rows as hi/lo planes); m2tts_ln_proj_workspace_bytes(H,N) is the FFMA minimum.
+ * `packed`: NULL or the image written by m2tts_ln_proj_pack for the same (H, N, precision). */
 size_t m2tts_ln_proj_workspace_bytes(int H, int N);
-/* workspace that additionally lets the call run on the tensor cores (normalised rows as hi/lo planes) */
 size_t m2tts_ln_proj_rows_workspace_bytes(int rows, int H, int N);
+size_t m2tts_ln_proj_pack_bytes(int H, int N, int precision);
+int m2tts_ln_proj_pack(const float* W, int H, int N, int precision, void* packed, size_t packed_bytes,
+                       int32_t* status, m2tts_stream_t stream);
 int m2tts_layernorm_proj(const float* x, const float* ln_w, const float* ln_b,
-                         const float* W, const float* bias, float* y, int rows,
-                         int H, int N, float eps, void* workspace,
+                         const float* W, const float* bias, const void* packed, float* y, int rows,
+                         int H, int N, float eps, int precision, int32_t* status, void* workspace,
                          size_t workspace_bytes, m2tts_stream_t stream);
 
 /* ---- duration predictor (tts_model.py:99-117) ------------------------------ */
@@ -180,7 +218,8 @@ int m2tts_duration_predictor(const m2tts_durpred_weights* w, const float* enc,
  * cum[b,s] = inclusive prefix sum (int32, saturating); frames[b] = sum_s n[b,s];
  * *t_max = max_b max(1, frames[b]) (tts_model.py:158-166); *status bit0 = a NaN
  * duration was seen (python raises ValueError), bit1 = +-inf (OverflowError),
- * bit2 = a frame count overflowed int32. All outputs are device memory. */
+ * bit2 = a frame count overflowed int32 (this word is the regulator's own, not the
+ * M2TTS_ST_* word). All outputs are device memory. */
 int m2tts_length_regulate_count(const float* dur, int B, int S, int32_t* cum,
                                 int32_t* frames, int32_t* t_max, int32_t* status,
                                 m2tts_stream_t stream);
@@ -194,13 +233,18 @@ int m2tts_length_regulate_gather(const float* enc, const int32_t* cum,
 
 /* ---- vocoder (tts_model.py:279-297) ---------------------------------------- */
 size_t m2tts_vocoder_workspace_bytes(int B, int T, int M, int C);
+/* packed images of every convolution of the vocoder for `precision` */
+size_t m2tts_vocoder_pack_bytes(int M, int C, int precision);
+int m2tts_vocoder_pack(const m2tts_vocoder_weights* w, int M, int C, int precision, void* packed,
+                       size_t packed_bytes, int32_t* status, m2tts_stream_t stream);
 /* mel element (b,m,t) is read at mel[b*stride_b + m*stride_m + t*stride_t]
  * (so both a contiguous [B,M,T] tensor and the transposed view of the decoder's
  * [B,T,M] output, tts_model.py:390, are accepted without a copy).
- * audio [B,1,64*T] contiguous. */
-int m2tts_vocoder_forward(const m2tts_vocoder_weights* w, const float* mel,
+ * audio [B,1,64*T] contiguous. `packed`: NULL or the buffer written by
+ * m2tts_vocoder_pack for the same (M, C, precision) and res_dilation. */
+int m2tts_vocoder_forward(const m2tts_vocoder_weights* w, const void* packed, const float* mel,
                           int64_t stride_b, int64_t stride_m, int64_t stride_t,
-                          float* audio, int B, int T, int M, int C,
+                          float* audio, int B, int T, int M, int C, int precision, int32_t* status,
                           void* workspace, size_t workspace_bytes,
                           m2tts_stream_t stream);
 
@@ -240,27 +284,28 @@ int m2tts_conv_transpose1d_lrelu_tc(const float* x, const float* w, const float*
  *   out_w == NULL: y written channel-last [B][2L][C];
  *   out_w != NULL: audio [B][2L] = tanh(Conv1d(C, 1, k=3, p=1)(y))  (out_w [1][C][3], out_b [1]).
  * C in {16, 32}; weights in the reference's state_dict layouts (up_w [2C][C][4], res*_w [C][C][3]).
- * workspace: m2tts_vocoder_stage_fused_workspace_bytes(C). */
+ * TF32 split; workspace: m2tts_vocoder_stage_fused_workspace_bytes(C). */
 size_t m2tts_vocoder_stage_fused_workspace_bytes(int C);
 int m2tts_vocoder_stage_fused(const float* x, const float* up_w, const float* up_b, const float* res1_w,
                               const float* res1_b, const float* res2_w, const float* res2_b,
                               const float* out_w, const float* out_b, float* y, int B, int C, int L,
                               void* workspace, size_t workspace_bytes, m2tts_stream_t stream);
 
-/* The same stage with the 16-bit split (fp16 hi/lo operands; activations saturate at +-65000): what m2tts_vocoder_forward uses
- * for its narrow stages by default. Same arguments; workspace: m2tts_vocoder_stage_fused_h_workspace_bytes(B, C, L). */
+/* The same stage with the 16-bit split: what m2tts_vocoder_forward uses for its narrow stages by default.
+ * Same arguments plus the status word; workspace: m2tts_vocoder_stage_fused_h_workspace_bytes(B, C, L). */
 size_t m2tts_vocoder_stage_fused_h_workspace_bytes(int B, int C, int L);
 int m2tts_vocoder_stage_fused_h(const float* x, const float* up_w, const float* up_b, const float* res1_w,
                                 const float* res1_b, const float* res2_w, const float* res2_b,
                                 const float* out_w, const float* out_b, float* y, int B, int C, int L,
-                                void* workspace, size_t workspace_bytes, m2tts_stream_t stream);
+                                int32_t* status, void* workspace, size_t workspace_bytes, m2tts_stream_t stream);
 
 /* A whole LightweightResBlock (components.py:177-200), y = x + conv2(leaky_relu(conv1(x), 0.1)), as one tcgen05 kernel with
  * the 16-bit split; x / y fp32 CHANNEL-LAST [B][L][C], C = 64, kernel 3, dilation 1; weights in state_dict layout [C][C][3].
  * workspace: m2tts_resblock_fused_h_workspace_bytes(B, C, L). */
 size_t m2tts_resblock_fused_h_workspace_bytes(int B, int C, int L);
 int m2tts_resblock_fused_h(const float* x, const float* w1, const float* b1, const float* w2, const float* b2, float* y,
-                           int B, int C, int L, void* workspace, size_t workspace_bytes, m2tts_stream_t stream);
+                           int B, int C, int L, int32_t* status, void* workspace, size_t workspace_bytes,
+                           m2tts_stream_t stream);
 
 /* One convolution of the widest LightweightResBlock (components.py:181-200): y = act(conv1d(x, w, b, padding 1)) (+ residual),
  * C = 128, kernel 3, dilation 1, 16-bit split, channel-last operands. x / residual fp32 CHANNEL-LAST [B][L][C]; act 0 none,
@@ -268,36 +313,19 @@ int m2tts_resblock_fused_h(const float* x, const float* w1, const float* b1, con
  * workspace: m2tts_conv1d_k3_h_workspace_bytes(B, C, L). */
 size_t m2tts_conv1d_k3_h_workspace_bytes(int B, int C, int L);
 int m2tts_conv1d_k3_h(const float* x, const float* w, const float* b, const float* residual, float* y, int B, int C, int L,
-                      int act, int out_cl, void* workspace, size_t workspace_bytes, m2tts_stream_t stream);
+                      int act, int out_cl, int32_t* status, void* workspace, size_t workspace_bytes, m2tts_stream_t stream);
 
-/* One upsampling layer of the vocoder with its activation (components.py:225-241):
+/* One upsampling layer of the vocoder with its activation (tts_model.py:255-263,291):
  * y = leaky_relu(conv_transpose1d(x, w, b, stride 4, padding 2), 0.1), kernel 8, CI in {128, 256}, CO = CI / 2, 16-bit split,
  * channel-last operands: x fp32 [B][L][CI], w [CI][CO][8] (state_dict layout), y fp32 [B][4L][CO].
  * workspace: m2tts_conv_transpose_x4_h_workspace_bytes(B, CI, L). */
 size_t m2tts_conv_transpose_x4_h_workspace_bytes(int B, int CI, int L);
 int m2tts_conv_transpose_x4_h(const float* x, const float* w, const float* b, float* y, int B, int CI, int L,
-                              void* workspace, size_t workspace_bytes, m2tts_stream_t stream);
-
-/* Bring-up only (tools/up_h_prof.py): switch parts of the upsampling kernel off for timing experiments
- * (1 no stores, 2 no UMMAs, 4 no TMA loads; results are invalid while non-zero). */
-int m2tts_voc_up_h_set_debug(int mode);
-
-/* Bring-up probe (tests/rowshift_probe_run.py): K-major swizzled UMMA A operand whose descriptor start
- * address is moved by whole rows inside the swizzle pattern. */
-int m2tts_rowshift_probe(const float* A, const float* Bm, float* D, int rows_total, int N, int K, int rowbytes,
-                         int shift, int base_offset, m2tts_stream_t stream);
+                              int32_t* status, void* workspace, size_t workspace_bytes, m2tts_stream_t stream);
 
 /* ---- after the path: waveform -> PCM16 on the device (scripts/synthesize.py:147-155 saves through
  * src/utils/audio.py:154-180; clip to [-1,1], x32767, round half to even). audio/pcm: n samples, device memory. */
 int m2tts_pcm16(const float* audio, int16_t* pcm, long long n, m2tts_stream_t stream);
-
-/* Bring-up / measurement tools (tools/mma_bench.py, tools/fused_prof.py, tools/attn_prof.py): tcgen05.mma cost per
- * operand configuration, and optional clock64 phase timestamps of the fused vocoder stage / attention kernels. */
-int m2tts_mma_bench(int mode, int N, int n, int nacc, int elect, long long* out_dev, m2tts_stream_t stream);
-/* kind::f16 operand-layout probe (tests/umma_probe_f16_run.py): mode 0 MN-major smem x MN-major smem, 1 TMEM x K-major, 2 K-major x K-major */
-int m2tts_umma_probe_f16(const float* A, const float* Bm, float* D, int N, int K, int mode, m2tts_stream_t stream);
-int m2tts_vocoder_stage_fused_set_prof(long long* dev_buf);
-int m2tts_attention_set_prof(long long* dev_buf);
 
 #ifdef __cplusplus
 }

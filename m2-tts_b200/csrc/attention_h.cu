@@ -59,7 +59,8 @@ __device__ __forceinline__ void umma_f16_ts_w(uint32_t d_tmem, uint32_t a_tmem, 
 template <int HD>
 __global__ void __launch_bounds__(AH_THREADS, 1)
 attention_h_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__ ctx, const int64_t* __restrict__ lengths,
-                   int B, int L, int nh, float* __restrict__ ctx_lo, __half* __restrict__ ctx_h, long long* __restrict__ prof, int dbg_skip) {
+                   int B, int L, int nh, float* __restrict__ ctx_lo, __half* __restrict__ ctx_h, long long* __restrict__ prof, int dbg_skip,
+                   int32_t* __restrict__ status) {
   static_assert(HD % 16 == 0 && HD >= 16 && HD <= 64, "16-bit split attention: head_dim in {16,32,48,64}");
   constexpr uint32_t BOX = AhSmem<HD>::box;
   constexpr int KSTEPS_D = HD / 16;
@@ -339,21 +340,16 @@ attention_h_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__
       if (ctx_h != nullptr) {   // fp16 hi/lo planes [2][B*L][nh*HD] for the 16-bit split out_proj (lin_h.cu)
         __half* dh = ctx_h + ((long long)b * L + qi) * (nh * HD) + head * HD;
         __half* dl = dh + (long long)B * L * (nh * HD);
+        bool bad = false;
 #pragma unroll
         for (int c = 0; c < HD; c += 8) {
           uint32_t hi[4], lo[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float v0 = fminf(fmaxf(o[c + 2 * e] * inv, -65000.f), 65000.f), v1 = fminf(fmaxf(o[c + 2 * e + 1] * inv, -65000.f), 65000.f);
-            const __half2 h = __floats2half2_rn(v0, v1);
-            const float2 hf = __half22float2(h);
-            const __half2 lw = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
-            hi[e] = *reinterpret_cast<const uint32_t*>(&h);
-            lo[e] = *reinterpret_cast<const uint32_t*>(&lw);
-          }
+          for (int e = 0; e < 4; ++e) h_split2(o[c + 2 * e] * inv, o[c + 2 * e + 1] * inv, hi[e], lo[e], bad);
           *reinterpret_cast<uint4*>(dh + c) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
           *reinterpret_cast<uint4*>(dl + c) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
+        h_flag(bad, status);
       } else if (ctx_lo == nullptr) {
 #pragma unroll
         for (int c = 0; c < HD; c += 4)
@@ -399,20 +395,20 @@ extern long long* g_ws_prof;      // attention_tc.cu (m2tts_attention_set_prof)
 
 template <int HD>
 static int launch_ah_hd(const CUtensorMap& tmap, float* ctx, const int64_t* lengths, int B, int L, int nh, cudaStream_t s, float* ctx_lo,
-                        __half* ctx_h) {
+                        __half* ctx_h, int32_t* status) {
   const size_t smem = AhSmem<HD>::total;
   static int dbg_skip = -1;
-  if (dbg_skip < 0) { const char* e = getenv("M2TTS_ATT_DBG"); dbg_skip = e ? atoi(e) : 0; }
+  if (dbg_skip < 0) dbg_skip = tools_env_int("M2TTS_ATT_DBG", 0);
   M2_CUDA_OK(allow_smem(attention_h_kernel<HD>, smem));
   dim3 grid((unsigned)(ceil_div(L, 2 * TC_BQ) * nh * B), 1, 1);
   M2_LAUNCH(M2TTS_STAGE_ATTENTION, attention_h_kernel<HD>, grid, AH_THREADS, smem, s, tmap, ctx, lengths, B, L, nh, ctx_lo, ctx_h,
-            getenv("M2TTS_LIN_PROF_STAGE") != nullptr ? nullptr : g_ws_prof, dbg_skip);      // the buffer belongs to tools/lin_prof.py then
+            tools_env_int("M2TTS_LIN_PROF_STAGE", -1) >= 0 ? nullptr : g_ws_prof, dbg_skip, status);      // the buffer belongs to tools/lin_prof.py then
   return M2TTS_OK;
 }
 
 // qkvh: [6][B][nh][hd][Lp] fp16 (Q_hi,Q_lo,K_hi,K_lo,V_hi,V_lo), Lp % 8 == 0, Q pre-scaled by scale*log2e.
 int launch_attention_h(const void* qkvh, float* ctx, const int64_t* lengths, int B, int L, int Lp, int nh, int hd,
-                       cudaStream_t s, float* ctx_lo, void* ctx_half_planes) {
+                       cudaStream_t s, float* ctx_lo, void* ctx_half_planes, int32_t* status) {
   __half* ctx_h = reinterpret_cast<__half*>(ctx_half_planes);
   M2_REQUIRE(qkvh && (ctx || ctx_half_planes), M2TTS_E_NULLPTR, "attention_h: null pointer");
   M2_REQUIRE(attention_tc_supported(hd), M2TTS_E_UNSUPPORTED, "attention_h: head_dim %d unsupported", hd);
@@ -431,10 +427,10 @@ int launch_attention_h(const void* qkvh, float* ctx, const int64_t* lengths, int
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   M2_REQUIRE(r == CUDA_SUCCESS, M2TTS_E_CUDA, "attention_h: cuTensorMapEncodeTiled failed (%d)", (int)r);
   switch (hd) {
-    case 16: return launch_ah_hd<16>(tmap, ctx, lengths, B, L, nh, s, ctx_lo, ctx_h);
-    case 32: return launch_ah_hd<32>(tmap, ctx, lengths, B, L, nh, s, ctx_lo, ctx_h);
-    case 48: return launch_ah_hd<48>(tmap, ctx, lengths, B, L, nh, s, ctx_lo, ctx_h);
-    default: return launch_ah_hd<64>(tmap, ctx, lengths, B, L, nh, s, ctx_lo, ctx_h);
+    case 16: return launch_ah_hd<16>(tmap, ctx, lengths, B, L, nh, s, ctx_lo, ctx_h, status);
+    case 32: return launch_ah_hd<32>(tmap, ctx, lengths, B, L, nh, s, ctx_lo, ctx_h, status);
+    case 48: return launch_ah_hd<48>(tmap, ctx, lengths, B, L, nh, s, ctx_lo, ctx_h, status);
+    default: return launch_ah_hd<64>(tmap, ctx, lengths, B, L, nh, s, ctx_lo, ctx_h, status);
   }
 }
 

@@ -625,7 +625,7 @@ int launch_attention_tc(const float* qkv6, float* ctx, const int64_t* lengths, i
           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   M2_REQUIRE(r == CUDA_SUCCESS, M2TTS_E_CUDA, "attention_tc: cuTensorMapEncodeTiled (v) failed (%d)", (int)r);
-  if (attention_mode() != 2 && dbg_s == nullptr && dbg_o == nullptr && hd <= 48) {   // mode 3 (or 0 via the plane entry point)   // default: warp-specialised two-tile pipeline (head_dim 64 does not fit two query tiles)
+  if (dbg_s == nullptr && dbg_o == nullptr && hd <= 48) {   // warp-specialised two-tile pipeline (head_dim 64 does not fit two query tiles: single-warpgroup kernel)
     switch (hd) {
       case 16: return launch_ws_hd<16>(tmap_qk, tmap_v, ctx, lengths, B, L, nh, s, ctx_lo);
       case 32: return launch_ws_hd<32>(tmap_qk, tmap_v, ctx, lengths, B, L, nh, s, ctx_lo);
@@ -642,6 +642,7 @@ int launch_attention_tc(const float* qkv6, float* ctx, const int64_t* lengths, i
 
 }  // namespace m2
 
+#ifdef M2TTS_TOOLS
 // bring-up: device buffer of 48 x 8 int64 receiving phase timestamps of CTA 0 / query tile A (NULL = off)
 extern "C" int m2tts_attention_set_prof(long long* dev_buf) { m2::g_ws_prof = dev_buf; return M2TTS_OK; }
 
@@ -652,3 +653,4 @@ extern "C" int m2tts_attention_tc_planes(const float* qkv6, float* ctx, const in
                                          m2tts_stream_t stream) {
   return m2::launch_attention_tc(qkv6, ctx, lengths, B, L, Lp, nh, hd, (cudaStream_t)stream, dbg_s, dbg_o);
 }
+#endif  // M2TTS_TOOLS

@@ -1,6 +1,7 @@
 // common.cuh — shared host/device helpers for the m2tts_b200 kernels (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
@@ -74,10 +75,40 @@ struct Carver {
   bool ok() const { return off <= size && (((uintptr_t)base) % 256 == 0); }
 };
 
-constexpr int kNumSMs = 148;  // B200
+// SM count of the CURRENT device (148 on B200), cached per device index
+int num_sms();
+#define kNumSMs (m2::num_sms())
+
+// `precision` argument of the entry points -> M2TTS_PREC_SPLIT16 / _FFMA / _TF32 (M2TTS_PREC_DEFAULT reads M2TTS_PRECISION once)
+int resolve_precision(int precision);
+
+// Bring-up switches (environment variables, prof buffers) exist only in the tools build (-DM2TTS_TOOLS); the product
+// library never reads them.
+#ifdef M2TTS_TOOLS
+int tools_env_int(const char* name, int dflt);
+#else
+inline int tools_env_int(const char*, int dflt) { return dflt; }
+#endif
 
 // ---- device helpers ---------------------------------------------------------
 #ifdef __CUDACC__
+// fp16-range guard of the 16-bit split. A producer converts without clamping (overflow -> inf, NaN -> NaN) and records
+// the violation: one FSETP per value instead of the two FMNMX of a clamp. The flagged call's output is invalid and the
+// caller re-runs it with M2TTS_PREC_TF32 (include/m2tts_b200.h, "Status word").
+__device__ __forceinline__ void h_chk(float v, bool& bad) { bad |= !(fabsf(v) <= 65504.f); }
+__device__ __forceinline__ void h_flag(bool bad, int32_t* status) {
+  if (bad && status != nullptr) atomicOr(status, (int32_t)M2TTS_ST_FP16_RANGE);
+}
+// two floats -> packed fp16 hi pair and packed fp16 lo pair, x = hi + lo (22 significant bits)
+__device__ __forceinline__ void h_split2(float a0, float a1, uint32_t& hi, uint32_t& lo, bool& bad) {
+  h_chk(a0, bad);
+  h_chk(a1, bad);
+  const __half2 h = __floats2half2_rn(a0, a1);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a0 - hf.x, a1 - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -135,7 +166,8 @@ int launch_attention_tc(const float* qkv6, float* ctx, const int64_t* lengths, i
                         float* ctx_lo = nullptr);  // ctx_lo != null: write ctx as TF32 hi/lo planes (ctx = hi plane)
 // 16-bit split attention (attention_h.cu): qkvh = six fp16 planes [6][B][nh][hd][Lp], Lp % 8 == 0
 int launch_attention_h(const void* qkvh, float* ctx, const int64_t* lengths, int B, int L, int Lp, int nh, int hd,
-                       cudaStream_t s, float* ctx_lo = nullptr, void* ctx_half_planes = nullptr);   // ctx_half_planes: fp16 [2][B*L][nh*hd]
+                       cudaStream_t s, float* ctx_lo = nullptr, void* ctx_half_planes = nullptr,   // ctx_half_planes: fp16 [2][B*L][nh*hd]
+                       int32_t* status = nullptr);
 // ---- persistent 16-bit split linear layers (lin_h.cu): operands as fp16 hi/lo planes ----
 struct LinHParams {
   int R, K, N;
@@ -145,10 +177,11 @@ struct LinHParams {
   void* y_planes;                  // mode 1: fp16 hi/lo planes [2][R][N]
   void* qkvh; long long plane_stride; int L, nh, hd, Lp; float qscale;   // mode 3: attention operand planes
   int mode;
+  int32_t* status;                 // M2TTS_ST_FP16_RANGE when an fp16-plane output leaves the fp16 range (may be null)
 };
 bool linear_h_eligible(int K, int N);
-int launch_ln_split_h(const float* x, const float* w, const float* b, void* planes, long long R, int K, float eps, cudaStream_t s);
-int launch_w_split_h(const float* const* src, void* const* dst, const long long* n, int jobs, cudaStream_t s);
+int launch_ln_split_h(const float* x, const float* w, const float* b, void* planes, long long R, int K, float eps, int32_t* status, cudaStream_t s);
+int launch_w_split_h(const float* const* src, void* const* dst, const long long* n, int jobs, int32_t* status, cudaStream_t s);
 int launch_linear_h(const void* a_planes, const void* w_planes, const LinHParams& q, int stage, cudaStream_t s);
 // ---- tensor-core linear layers (rowgemm_tc.cu) ----
 struct LinTcArgs {
@@ -162,49 +195,50 @@ struct LinTcArgs {
   // mode 2: attention operand planes [6][B][nh][hd][Lp] (fp32 holding TF32 hi/lo); mode 3: the same as fp16 hi/lo
   float* qkv6; long long plane_stride; int nh, hd, Lp; float qscale;
   int mode;
+  int32_t* status;                 // mode 3 (fp16 planes): M2TTS_ST_FP16_RANGE
 };
 
 bool linear_tc_eligible(int K, int N);
 int launch_ln_split(const float* x, const float* w, const float* b, float* planes, long long R, int K, float eps, cudaStream_t s);
 int launch_w_split(const float* const* src, float* const* dst, const long long* n, int jobs, cudaStream_t s);
-int launch_linear_tc(const float* a_planes, const float* w_planes, LinTcArgs a, int B, int stage, cudaStream_t s);
+int launch_linear_tc(const float* a_planes, const float* w_planes, LinTcArgs a, int B, int stage, cudaStream_t s);   // a.status: see LinTcArgs
 int* debug_words_device();  // pinned mapped scratch for hang diagnostics (may be null)
-int attention_mode();  // 0 = tensor cores, 16-bit split (attention_h.cu); 1 = fp32 FFMA kernel; 2 = TF32 split, single-warpgroup kernel; 3 = TF32 split, warp-specialised kernel
-int vocoder_mode();    // 0 = tensor cores (fused narrow stages with the 16-bit split), 1 = FFMA everywhere, 2 = tensor cores, TF32 split everywhere
 
 // tensor-core ("tap-GEMM") convolutions on plain fp32 [B][C][Lp] (conv_tc.cu / conv_tc2.cu)
 bool conv3_tc_eligible(int CI, int CO);
 bool convT_tc_eligible(int CI, int CO, int r);
 size_t conv3_tc_wblob_floats(int CI, int CO);
 size_t convT_tc_wblob_floats(int CI, int CO, int r);
+// Every conv launcher below takes the module weight `w` AND its image buffer `wblob`: with w != nullptr the image is (re)written
+// by a small pack kernel first; w == nullptr means wblob already holds the image (m2tts_vocoder_pack). x == nullptr: pack only.
 int launch_conv3_tc(const float* x, int Lp_in, const float* w, float* wblob, const float* bias, const float* residual,
                     int Lp_res, float* out, int Lp_out, int B, int CI, int CO, int L, int dil, int act, int stage,
-                    cudaStream_t s, int out_cl = 0);   // out_cl 1: write channel-last fp32 [B][L][CO]; 2: channel-last fp16 hi/lo planes [2][B][L][CO]
+                    cudaStream_t s, int out_cl = 0, int32_t* status = nullptr);   // out_cl 1: write channel-last fp32 [B][L][CO]; 2: channel-last fp16 hi/lo planes [2][B][L][CO]
 int launch_convT_tc(const float* x, int Lp_in, const float* w, float* wblob, const float* bias, float* out, int Lp_out,
-                    int B, int CI, int CO, int L, int r, cudaStream_t s, int out_cl = 0);   // out_cl 2: fp16 hi/lo planes, channel-last
+                    int B, int CI, int CO, int L, int r, cudaStream_t s, int out_cl = 0, int32_t* status = nullptr);   // out_cl 2: fp16 hi/lo planes, channel-last
 // whole ResBlock for C = 64 as one kernel, channel-last fp16 hi/lo planes in (voc_res_h.cu)
 bool voc_res_h_eligible(int C, int dil);
 size_t voc_res_h_wblob_bytes(int C);
 int launch_voc_res_h(const void* uh, long long u_plane, const float* w1, const float* b1, const float* w2, const float* b2, void* wblob,
-                     void* out_h, long long out_plane, float* out_f, int B, int C, int L, int stage, cudaStream_t s);
+                     void* out_h, long long out_plane, float* out_f, int B, int C, int L, int stage, int32_t* status, cudaStream_t s);
 // one Conv1d(C, C, 3) for C = 128 on channel-last fp16 hi/lo planes (voc_conv_h.cu); output planes or fp32 channel-first
 bool voc_conv_h_eligible(int C, int dil);
 bool voc_conv_h_io_eligible(int CI, int CO);      // 64 < CI <= 128 (zero-padded to 128), CO a multiple of 64: also the input conv
 size_t voc_conv_h_wblob_bytes(int CO);
 int launch_voc_conv_h(const void* xh, long long x_plane, const float* w, const float* bias, void* wblob, const void* res_h,
                       long long res_plane, void* out_h, long long out_plane, float* out_cf, int Lp_out, int B, int CI, int CO, int L, int act,
-                      int stage, cudaStream_t s);
+                      int stage, int32_t* status, cudaStream_t s);
 // ConvTranspose1d(CI, CI/2, 8, stride 4, padding 2) + leaky_relu on channel-last fp16 hi/lo planes (voc_up_h.cu)
 bool voc_up_h_eligible(int CI, int CO, int r);
 size_t voc_up_h_wblob_bytes(int CI);
 int launch_voc_up_h(const void* xh, long long x_plane, const float* w, const float* bias, void* wblob, void* out_h, long long out_plane,
-                    int B, int CI, int L, int stage, cudaStream_t s);
+                    int B, int CI, int L, int stage, int32_t* status, cudaStream_t s);
 // 16-bit split flavour (voc_fused_h.cu): input as fp16 hi/lo planes [2][B][L][2C]
 size_t voc_fused_h_wblob_bytes(int C);
 int launch_voc_stage_fused_h(const void* xh, long long x_plane, const float* up_w, const float* up_b, const float* w1, const float* b1,
                              const float* w2, const float* b2, const float* out_w, const float* out_b, void* wblob,
-                             void* out_h, long long out_plane, float* out_f, int B, int C, int L_in, int stage, cudaStream_t s);
-int launch_split_planes_h(const float* x, void* planes, long long n, cudaStream_t s);
+                             void* out_h, long long out_plane, float* out_f, int B, int C, int L_in, int stage, int32_t* status, cudaStream_t s);
+int launch_split_planes_h(const float* x, void* planes, long long n, int32_t* status, cudaStream_t s);
 // fused narrow stage on channel-last activations (voc_fused.cu): upsample x2 + ResBlock (+ output conv + tanh)
 bool voc_fused_eligible(int C, int r, int dil);
 size_t voc_fused_wblob_floats(int C);

@@ -118,13 +118,17 @@ static int launch_wpack(const WPackArgs& p, cudaStream_t s) {
 // Conv1d k=3 on plain fp32. wblob: conv3_tc_wblob_floats(CI,CO) floats of scratch. residual (plain, pitch Lp_res) may be null.
 int launch_conv3_tc(const float* x, int Lp_in, const float* w, float* wblob, const float* bias, const float* residual,
                     int Lp_res, float* out, int Lp_out, int B, int CI, int CO, int L, int dil, int act, int stage,
-                    cudaStream_t s, int out_cl) {
+                    cudaStream_t s, int out_cl, int32_t* status) {
   M2_REQUIRE(conv3_tc_eligible(CI, CO), M2TTS_E_UNSUPPORTED, "conv3_tc: CI=%d CO=%d not eligible", CI, CO);
   const int ct = (CO % 64 == 0) ? 64 : CO, n_tiles = CO / ct;   // <= 192 accumulator columns per tile
-  WPackArgs p{w, wblob, 0, CI, CO, 1, ct, 3 * ct, CI / CT_CK, n_tiles};
-  int rc = launch_wpack(p, s);
-  if (rc) return rc;
+  if (w != nullptr) {      // (re)write the weight image; w == nullptr: wblob already holds it
+    WPackArgs p{w, wblob, 0, CI, CO, 1, ct, 3 * ct, CI / CT_CK, n_tiles};
+    int rc = launch_wpack(p, s);
+    if (rc) return rc;
+  }
+  if (x == nullptr) return M2TTS_OK;      // pack only
   TapGemmArgs a{};
+  a.status = status;
   a.CI = CI; a.L_in = L; a.B = B; a.n_chunks = CI / CT_CK;
   for (int j = 0; j < 3; ++j) { a.tap_shift[j] = (j - 1) * dil; a.tap_rows[j] = ct; a.tap_wrow[j] = j * ct; a.tap_dcol[j] = j * ct; }
   a.rows_total = 3 * ct; a.n_cols = 3 * ct; a.wblob = wblob; a.r = 1; a.co_tile = ct; a.CO = CO; a.L_out = L; a.Lp_out = Lp_out;
@@ -134,14 +138,18 @@ int launch_conv3_tc(const float* x, int Lp_in, const float* w, float* wblob, con
 
 // ConvTranspose1d(k=2r, stride r, pad r/2) + leaky_relu on plain fp32, r in {2,4}.
 int launch_convT_tc(const float* x, int Lp_in, const float* w, float* wblob, const float* bias, float* out, int Lp_out,
-                    int B, int CI, int CO, int L, int r, cudaStream_t s, int out_cl) {
+                    int B, int CI, int CO, int L, int r, cudaStream_t s, int out_cl, int32_t* status) {
   M2_REQUIRE(convT_tc_eligible(CI, CO, r), M2TTS_E_UNSUPPORTED, "convT_tc: CI=%d CO=%d r=%d not eligible", CI, CO, r);
-  M2_REQUIRE((Lp_out % r) == 0 && (Lp_out & 3) == 0, M2TTS_E_BADSHAPE, "convT_tc: output pitch %d", Lp_out);
   const int ct = (CO % 32 == 0) ? 32 : 16, n_tiles = CO / ct;
-  WPackArgs p{w, wblob, 1, CI, CO, r, ct, 2 * r * ct, CI / CT_CK, n_tiles};
-  int rc = launch_wpack(p, s);
-  if (rc) return rc;
+  if (w != nullptr) {      // (re)write the weight image; w == nullptr: wblob already holds it
+    WPackArgs p{w, wblob, 1, CI, CO, r, ct, 2 * r * ct, CI / CT_CK, n_tiles};
+    int rc = launch_wpack(p, s);
+    if (rc) return rc;
+  }
+  if (x == nullptr) return M2TTS_OK;      // pack only
+  M2_REQUIRE((Lp_out % r) == 0 && (Lp_out & 3) == 0, M2TTS_E_BADSHAPE, "convT_tc: output pitch %d", Lp_out);
   TapGemmArgs a{};
+  a.status = status;
   a.CI = CI; a.L_in = L; a.B = B; a.n_chunks = CI / CT_CK;
   a.tap_shift[0] = 0;  a.tap_rows[0] = r * ct;       a.tap_wrow[0] = 0;                        a.tap_dcol[0] = 0;
   a.tap_shift[1] = -1; a.tap_rows[1] = (r / 2) * ct; a.tap_wrow[1] = r * ct;                   a.tap_dcol[1] = r * ct;

@@ -32,6 +32,7 @@ struct TapGemmArgs {
   int n_tiles, m_tiles, w_resident;
   int raw_stages, split_stages;
   long long* prof;           // optional bring-up timestamps (CTA 0, epilogue group 0)
+  int32_t* status;           // out_cl == 2 (fp16 hi/lo planes out): M2TTS_ST_FP16_RANGE
 };
 
 // ---- PTX helpers -------------------------------------------------------------------------------------

@@ -68,6 +68,7 @@ __device__ __forceinline__ void convT_epilogue(const TapGemmArgs& a, float* stg,
       if (a.out_cl == 2) {
         // channel-last fp16 hi/lo planes [2][B][L_out][CO] for the 16-bit split ResBlock kernel: 8 channels = one 16-byte
         // chunk per (output position, plane)
+        bool bad = false;
 #pragma unroll
         for (int p = 0; p < R; ++p) {
           uint32_t hw[4], lw[4];
@@ -76,17 +77,13 @@ __device__ __forceinline__ void convT_epilogue(const TapGemmArgs& a, float* stg,
             float t0 = __uint_as_float(v[p][2 * e]) + __ldg(a.bias + co0 + c0 + 2 * e) + nb[p][2 * e];
             float t1 = __uint_as_float(v[p][2 * e + 1]) + __ldg(a.bias + co0 + c0 + 2 * e + 1) + nb[p][2 * e + 1];
             t0 = t0 > 0.f ? t0 : 0.1f * t0; t1 = t1 > 0.f ? t1 : 0.1f * t1;
-            t0 = fminf(t0, 65000.f); t1 = fminf(t1, 65000.f); t0 = fmaxf(t0, -65000.f); t1 = fmaxf(t1, -65000.f);
-            const __half2 hh = __floats2half2_rn(t0, t1);
-            const float2 hf = __half22float2(hh);
-            const __half2 ll = __floats2half2_rn(t0 - hf.x, t1 - hf.y);
-            hw[e] = *reinterpret_cast<const uint32_t*>(&hh);
-            lw[e] = *reinterpret_cast<const uint32_t*>(&ll);
+            h_split2(t0, t1, hw[e], lw[e], bad);
           }
           __half* oh = reinterpret_cast<__half*>(a.out) + ((size_t)b * a.L_out + (size_t)R * q + p) * a.CO + co0 + c0;
           *reinterpret_cast<uint4*>(oh) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
           *reinterpret_cast<uint4*>(oh + (size_t)a.B * a.L_out * a.CO) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
         }
+        h_flag(bad, a.status);
       } else {
 #pragma unroll
       for (int jj = 0; jj < 8; ++jj) {
@@ -361,21 +358,18 @@ tapgemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const TapG
             if (a.out_cl == 2) {  // channel-last fp16 hi/lo planes for the 16-bit split fused stages (same bytes as fp32)
               __half* oh = reinterpret_cast<__half*>(a.out) + ((size_t)b * a.L_out + q) * a.CO + co0 + c0;
               __half* ol = oh + (size_t)a.B * a.L_out * a.CO;
+              bool bad = false;
 #pragma unroll
               for (int j8 = 0; j8 < 2; ++j8) {
                 uint32_t hw[4], lw[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                  const float a0 = fminf(fmaxf(xo[8 * j8 + 2 * e], -65000.f), 65000.f), a1 = fminf(fmaxf(xo[8 * j8 + 2 * e + 1], -65000.f), 65000.f);
-                  const __half2 hh = __floats2half2_rn(a0, a1);
-                  const float2 hf = __half22float2(hh);
-                  const __half2 ll = __floats2half2_rn(a0 - hf.x, a1 - hf.y);
-                  hw[e] = *reinterpret_cast<const uint32_t*>(&hh);
-                  lw[e] = *reinterpret_cast<const uint32_t*>(&ll);
+                  h_split2(xo[8 * j8 + 2 * e], xo[8 * j8 + 2 * e + 1], hw[e], lw[e], bad);
                 }
                 *reinterpret_cast<uint4*>(oh + 8 * j8) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
                 *reinterpret_cast<uint4*>(ol + 8 * j8) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
               }
+              h_flag(bad, a.status);
             } else if (a.out_cl) {       // channel-last rows for the fused narrow stages: 64 contiguous bytes per thread
               float4* op = reinterpret_cast<float4*>(a.out + ((size_t)b * a.L_out + q) * a.CO + co0 + c0);
 #pragma unroll
@@ -405,7 +399,7 @@ tapgemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const TapG
   }
 }
 
-static long long* g_tg_prof = nullptr;
+static long long* g_tg_prof = nullptr;      // set only by the tools build (m2tts_tapgemm_set_prof)
 int launch_tapgemm_persistent(const CUtensorMap& tmap, TapGemmArgs& a, int stage, cudaStream_t s) {
   a.prof = g_tg_prof;
   for (int j = 0; j < 3; ++j)
@@ -467,4 +461,6 @@ int launch_tapgemm_persistent(const CUtensorMap& tmap, TapGemmArgs& a, int stage
 }  // namespace m2
 
 // bring-up: device buffer of >= 576 int64 receiving epilogue / splitter timestamps of CTA 0 (NULL = off)
+#ifdef M2TTS_TOOLS
 extern "C" int m2tts_tapgemm_set_prof(long long* dev_buf) { m2::g_tg_prof = dev_buf; return M2TTS_OK; }
+#endif

@@ -9,8 +9,9 @@ namespace m2 {
 __global__ void embed_posenc_kernel(const int64_t* __restrict__ ids, const float* __restrict__ emb,
                                     const float* __restrict__ pe, const int64_t* __restrict__ lengths,
                                     float* __restrict__ x, uint8_t* __restrict__ mask,
-                                    int B, int S, int H, int vocab, float scale) {
+                                    int B, int S, int H, int vocab, float scale, int32_t* __restrict__ status) {
   const long long total = (long long)B * S * H;
+  bool bad_id = false;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int h = (int)(i % H);
@@ -18,10 +19,14 @@ __global__ void embed_posenc_kernel(const int64_t* __restrict__ ids, const float
     const int s = (int)(row % S);
     const int b = (int)(row / S);
     long long id = ids[row];
-    id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+    if (id < 0 || id >= vocab) {      // nn.Embedding raises IndexError (tts_model.py:78): report, and stay inside the table
+      bad_id = true;
+      id = id < 0 ? 0 : vocab - 1;
+    }
     x[i] = __fadd_rn(__fmul_rn(emb[id * H + h], scale), pe[(long long)s * H + h]);  // mul then add, as torch
     if (h == 0 && mask != nullptr && lengths != nullptr) mask[row] = (uint8_t)((long long)s < lengths[b]);
   }
+  if (bad_id && status != nullptr) atomicOr(status, (int32_t)M2TTS_ST_BAD_ID);
 }
 
 // One warp per row; biased variance, eps inside the sqrt (nn.LayerNorm).
@@ -113,7 +118,7 @@ extern "C" int m2tts_pcm16(const float* audio, int16_t* pcm, long long n, m2tts_
 
 extern "C" int m2tts_embed_posenc(const int64_t* ids, const float* emb, const float* pe,
                                   const int64_t* lengths, float* x, uint8_t* mask, int B, int S,
-                                  int H, int vocab, m2tts_stream_t stream) {
+                                  int H, int vocab, int32_t* status, m2tts_stream_t stream) {
   M2_REQUIRE(ids && emb && pe && x, M2TTS_E_NULLPTR, "embed_posenc: null pointer");
   M2_REQUIRE(B > 0 && S > 0 && H > 0 && vocab > 0, M2TTS_E_BADSHAPE,
              "embed_posenc: B=%d S=%d H=%d vocab=%d must be positive", B, S, H, vocab);
@@ -121,7 +126,7 @@ extern "C" int m2tts_embed_posenc(const int64_t* ids, const float* emb, const fl
   int grid = (int)((total + 255) / 256);
   if (grid > kNumSMs * 16) grid = kNumSMs * 16;
   M2_LAUNCH(M2TTS_STAGE_EMBED, embed_posenc_kernel, grid, 256, 0, (cudaStream_t)stream, ids, emb, pe,
-            lengths, x, mask, B, S, H, vocab, (float)sqrt((double)H));
+            lengths, x, mask, B, S, H, vocab, (float)sqrt((double)H), status);
   return M2TTS_OK;
 }
 

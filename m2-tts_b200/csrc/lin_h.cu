@@ -39,6 +39,7 @@ struct LinHArgs {
   int stg_bytes;                   // > 0: the epilogue stages the output tile in shared memory and writes it with TMA stores (modes 0, 1)
   long long* prof;                 // bring-up: phase timestamps of CTA 0's first epilogue warp (m2tts_attention_set_prof buffer)
   int dbg;                         // bring-up timing experiments (M2TTS_LIN_DBG): 1 no stores, 2 no UMMAs, 4 no A-tile loads; results invalid
+  int32_t* status;                 // fp16-plane outputs (modes 1, 3): M2TTS_ST_FP16_RANGE
 };
 
 // Operand rows are 32 halves = 64 bytes (64-B swizzle): K = 96 is then exactly three boxes (with 128-byte rows a
@@ -166,6 +167,7 @@ lin_h_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     uint8_t* stg0 = gbase + (sStg - sbase);
     const uint32_t swz = (uint32_t)((row >> 1) & 3);
     const bool leader = warp == 2 && lane == 0;
+    bool bad = false;               // an fp16-plane output left the fp16 range
     int unit = 0;
     for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x) {
       const long long r = (long long)mt * LH_BM + row;
@@ -268,14 +270,7 @@ lin_h_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
           } else if (a.mode == 1) {
             uint32_t hi[8], lo[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float t0 = fminf(x[2 * j], 65000.f), t1 = fminf(x[2 * j + 1], 65000.f);    // ReLU output: only the upper bound matters
-              const __half2 h = __floats2half2_rn(fmaxf(t0, -65000.f), fmaxf(t1, -65000.f));
-              const float2 hf = __half22float2(h);
-              const __half2 lw = __floats2half2_rn(t0 - hf.x, t1 - hf.y);
-              hi[j] = *reinterpret_cast<const uint32_t*>(&h);
-              lo[j] = *reinterpret_cast<const uint32_t*>(&lw);
-            }
+            for (int j = 0; j < 8; ++j) h_split2(x[2 * j], x[2 * j + 1], hi[j], lo[j], bad);
             if (tma_out) {
               uint8_t* bh = stg + (uint32_t)(c0 >> 5) * 8192u + (uint32_t)row * 64u;
               uint8_t* bl = bh + (uint32_t)(a.np >> 5) * 8192u;
@@ -307,7 +302,8 @@ lin_h_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
               // made this epilogue XU-bound)
 #pragma unroll
               for (int j = 0; j < 16; j += 2) {
-                const float t0 = fminf(fmaxf(x[j] * sc, -65000.f), 65000.f), t1 = fminf(fmaxf(x[j + 1] * sc, -65000.f), 65000.f);
+                const float t0 = x[j] * sc, t1 = x[j + 1] * sc;
+                h_chk(t0, bad); h_chk(t1, bad);
                 const __half2 h = __floats2half2_rn(t0, t1);
                 const float2 hf = __half22float2(h);
                 const __half2 lo = __floats2half2_rn(t0 - hf.x, t1 - hf.y);
@@ -320,7 +316,8 @@ lin_h_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
               __half* hp = a.qkvh + (long long)(2 * which) * a.plane_stride + (((long long)b * a.nh + head) * a.hd + d0) * a.Lp + l;
 #pragma unroll
               for (int j = 0; j < 16; j += 2) {
-                const float t0 = fminf(fmaxf(x[j] * sc, -65000.f), 65000.f), t1 = fminf(fmaxf(x[j + 1] * sc, -65000.f), 65000.f);
+                const float t0 = x[j] * sc, t1 = x[j + 1] * sc;
+                h_chk(t0, bad); h_chk(t1, bad);
                 const __half2 h = __floats2half2_rn(t0, t1);
                 const float2 hf = __half22float2(h);
                 const __half2 lo = __floats2half2_rn(t0 - hf.x, t1 - hf.y);
@@ -367,6 +364,7 @@ lin_h_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
       }
     }
     if (tma_out && leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    h_flag(bad, a.status);
   }
   tc_fence_before();
   __syncthreads();
@@ -380,11 +378,12 @@ lin_h_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
 // 8 lanes per row (float4 each, up to 8 per lane: K <= 256), 4 rows per warp pass, grid-stride over row groups.
 __global__ void __launch_bounds__(256) ln_split_h_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                          const float* __restrict__ bvec, __half* __restrict__ planes,
-                                                         long long R, int K, float eps) {
+                                                         long long R, int K, float eps, int32_t* __restrict__ status) {
   const int lane = threadIdx.x & 31, sub = lane & 7;
   const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
   const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int n4 = K >> 5;                       // float4 per lane (K % 32 == 0)
+  bool bad = false;
   for (long long row = warp_id * 4 + (lane >> 3); row < ((R + 3) & ~3LL); row += warps * 4) {
     const bool valid = row < R;
     const float* xr = x + (valid ? row : 0) * K;
@@ -420,32 +419,31 @@ __global__ void __launch_bounds__(256) ln_split_h_kernel(const float* __restrict
           a[0] = (a[0] - mean) * rstd * ww.x + bb.x; a[1] = (a[1] - mean) * rstd * ww.y + bb.y;
           a[2] = (a[2] - mean) * rstd * ww.z + bb.z; a[3] = (a[3] - mean) * rstd * ww.w + bb.w;
         }
-#pragma unroll
-        for (int e = 0; e < 4; ++e) a[e] = fminf(fmaxf(a[e], -65000.f), 65000.f);
-        const __half2 h0 = __floats2half2_rn(a[0], a[1]), h1 = __floats2half2_rn(a[2], a[3]);
-        const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
-        const __half2 l0 = __floats2half2_rn(a[0] - f0.x, a[1] - f0.y), l1 = __floats2half2_rn(a[2] - f1.x, a[3] - f1.y);
         uint2 hv, lv;
-        hv.x = *reinterpret_cast<const uint32_t*>(&h0); hv.y = *reinterpret_cast<const uint32_t*>(&h1);
-        lv.x = *reinterpret_cast<const uint32_t*>(&l0); lv.y = *reinterpret_cast<const uint32_t*>(&l1);
+        h_split2(a[0], a[1], hv.x, lv.x, bad);
+        h_split2(a[2], a[3], hv.y, lv.y, bad);
         *reinterpret_cast<uint2*>(hp + k) = hv;
         *reinterpret_cast<uint2*>(lp + k) = lv;
       }
   }
+  h_flag(bad, status);
 }
 
 // W [N,K] fp32 -> fp16 planes [2][N][K]; several matrices per launch (blockIdx.y = job)
-struct WSplitHJobs { const float* src[4]; __half* dst[4]; long long n[4]; };
+struct WSplitHJobs { const float* src[4]; __half* dst[4]; long long n[4]; int32_t* status; };
 __global__ void w_split_h_kernel(WSplitHJobs jobs) {
   const float* s = jobs.src[blockIdx.y];
   __half* d = jobs.dst[blockIdx.y];
   const long long n = jobs.n[blockIdx.y];
+  bool bad = false;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const float v = fminf(fmaxf(s[i], -65000.f), 65000.f);
+    const float v = s[i];
+    h_chk(v, bad);
     const __half h = __float2half_rn(v);
     d[i] = h;
     d[n + i] = __float2half_rn(v - __half2float(h));
   }
+  h_flag(bad, jobs.status);
 }
 
 // ---- host ----------------------------------------------------------------------------------------
@@ -474,17 +472,18 @@ bool linear_h_eligible(int K, int N) {
   return w + a1 + (size_t)N * 4 + 2048 <= 225 * 1024;
 }
 
-int launch_ln_split_h(const float* x, const float* w, const float* b, void* planes, long long R, int K, float eps, cudaStream_t s) {
+int launch_ln_split_h(const float* x, const float* w, const float* b, void* planes, long long R, int K, float eps, int32_t* status, cudaStream_t s) {
   M2_REQUIRE(K % 32 == 0 && K <= 256 && (((uintptr_t)x) & 15) == 0, M2TTS_E_UNSUPPORTED, "ln_split_h: K=%d", K);
   long long blocks = (R + 31) / 32;            // 8 warps x 4 rows per block pass
   if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-  M2_LAUNCH(M2TTS_STAGE_LAYERNORM, ln_split_h_kernel, (unsigned)blocks, 256, 0, s, x, w, b, (__half*)planes, R, K, eps);
+  M2_LAUNCH(M2TTS_STAGE_LAYERNORM, ln_split_h_kernel, (unsigned)blocks, 256, 0, s, x, w, b, (__half*)planes, R, K, eps, status);
   return M2TTS_OK;
 }
 
-int launch_w_split_h(const float* const* src, void* const* dst, const long long* n, int jobs, cudaStream_t s) {
+int launch_w_split_h(const float* const* src, void* const* dst, const long long* n, int jobs, int32_t* status, cudaStream_t s) {
   M2_REQUIRE(jobs >= 1 && jobs <= 4, M2TTS_E_BADSHAPE, "w_split_h: 1..4 jobs");
   WSplitHJobs j{};
+  j.status = status;
   long long mx = 1;
   for (int i = 0; i < jobs; ++i) { j.src[i] = src[i]; j.dst[i] = (__half*)dst[i]; j.n[i] = n[i]; if (n[i] > mx) mx = n[i]; }
   dim3 grid((unsigned)((mx + 255) / 256 > 256 ? 256 : (mx + 255) / 256), jobs);
@@ -507,8 +506,9 @@ int launch_linear_h(const void* a_planes, const void* w_planes, const LinHParams
   a.bias = q.bias; a.relu = q.relu; a.residual = q.residual; a.ldr = q.ldr; a.y = q.y; a.ldy = q.ldy;
   a.y_planes = (__half*)q.y_planes; a.qkvh = (__half*)q.qkvh; a.plane_stride = q.plane_stride;
   a.L = q.L; a.nh = q.nh; a.hd = q.hd; a.Lp = q.Lp; a.qscale = q.qscale; a.mode = q.mode;
-  { static int ps = -2; if (ps == -2) { const char* e = getenv("M2TTS_LIN_PROF_STAGE"); ps = e ? atoi(e) : -1; } a.prof = (ps < 0 || ps == stage) ? g_ws_prof : nullptr; }
-  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("M2TTS_LIN_DBG"); dbg = e ? atoi(e) : 0; } a.dbg = dbg; }
+  { static int ps = -2; if (ps == -2) ps = tools_env_int("M2TTS_LIN_PROF_STAGE", -1); a.prof = (ps < 0 || ps == stage) ? g_ws_prof : nullptr; }
+  { static int dbg = -1; if (dbg < 0) dbg = tools_env_int("M2TTS_LIN_DBG", 0); a.dbg = dbg; }
+  a.status = q.status;
   const size_t a_stage = (size_t)2 * a.kboxes * LH_BM * 64, w_bytes = (size_t)a.kboxes * 2 * a.N * 64;
   const bool stage3 = q.mode == 3 && a.np == q.nh * q.hd && q.L > 0 && q.R % q.L == 0 && q.plane_stride == (long long)(q.R / q.L) * q.nh * q.hd * q.Lp &&
                       (q.Lp & 7) == 0 && (((uintptr_t)q.qkvh) & 15) == 0;

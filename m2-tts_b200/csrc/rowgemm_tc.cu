@@ -135,6 +135,7 @@ lingemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     // every global store is 16 bytes of 8 consecutive positions instead of 2-byte scalars.
     __half* stg = reinterpret_cast<__half*>(smem_raw + (sbase - lg_smem_u32(smem_raw)));     // [plane][n_tile][128]
     const int H = a.nh * a.hd, nt = a.n_tile;
+    bool bad = false;
     for (int c0 = 0; c0 < nt; c0 += 16) {
       uint32_t v[16];
       lg_ld16(t_lane + c0, v);
@@ -145,12 +146,14 @@ lingemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         float t = __uint_as_float(v[j]);
         if (a.bias != nullptr) t += __ldg(a.bias + n);
         if (n < H) t *= a.qscale;                                  // Q rows carry scale * log2(e)
-        t = valid ? fminf(fmaxf(t, -65000.f), 65000.f) : 0.f;      // saturate to the fp16 range
+        t = valid ? t : 0.f;
+        h_chk(t, bad);                                             // fp16 range (M2TTS_ST_FP16_RANGE)
         const __half h = __float2half_rn(t);
         stg[(c0 + j) * LG_BM + tid] = h;
         stg[(nt + c0 + j) * LG_BM + tid] = __float2half_rn(t - __half2float(h));
       }
     }
+    h_flag(bad, a.status);
     __syncthreads();
     __half* base = reinterpret_cast<__half*>(a.qkv6);
     for (int idx = tid; idx < 2 * nt * 16; idx += LG_THREADS) {

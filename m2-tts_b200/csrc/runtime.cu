@@ -62,45 +62,40 @@ void note_launch(int stage, cudaStream_t s, bool begin) {
 
 using namespace m2;
 
-static std::atomic<int> g_attn_mode{-1};
 namespace m2 {
-int attention_mode() {
-  int m = g_attn_mode.load(std::memory_order_relaxed);
+// M2TTS_PREC_DEFAULT -> the 16-bit split, unless M2TTS_PRECISION=split16|ffma|tf32 overrides it (read once; an A/B
+// measurement aid, not a mode switch: callers that care pass an explicit precision)
+int resolve_precision(int precision) {
+  if (precision >= 0) return precision;
+  static std::atomic<int> dflt{-1};
+  int m = dflt.load(std::memory_order_relaxed);
   if (m < 0) {
-    const char* e = getenv("M2TTS_ATTENTION");
-    m = (e && strcmp(e, "ffma") == 0) ? 1 : ((e && strcmp(e, "tc1") == 0) ? 2 : ((e && strcmp(e, "tf32") == 0) ? 3 : 0));
-    g_attn_mode.store(m);
+    const char* e = getenv("M2TTS_PRECISION");
+    m = (e && strcmp(e, "ffma") == 0) ? M2TTS_PREC_FFMA : ((e && strcmp(e, "tf32") == 0) ? M2TTS_PREC_TF32 : M2TTS_PREC_SPLIT16);
+    dflt.store(m);
   }
   return m;
 }
-}  // namespace m2
 
-static std::atomic<int> g_voc_mode{-1};
-namespace m2 {
-int vocoder_mode() {
-  int m = g_voc_mode.load(std::memory_order_relaxed);
-  if (m < 0) {
-    const char* e = getenv("M2TTS_VOCODER");
-    m = (e && strcmp(e, "ffma") == 0) ? 1 : ((e && strcmp(e, "tf32") == 0) ? 2 : 0);
-    g_voc_mode.store(m);
+int num_sms() {
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  int n = cache[dev].load(std::memory_order_relaxed);
+  if (n <= 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cache[dev].store(n);
   }
-  return m;
+  return n;
 }
+
+#ifdef M2TTS_TOOLS
+int tools_env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+#endif
 }  // namespace m2
-
-extern "C" int m2tts_set_vocoder_mode(int mode) {
-  M2_REQUIRE(mode >= 0 && mode <= 2, M2TTS_E_BADSHAPE,
-             "set_vocoder_mode: 0 = tensor cores (narrow stages 16-bit split), 1 = ffma, 2 = tensor cores (narrow stages TF32 split)");
-  g_voc_mode.store(mode);
-  return M2TTS_OK;
-}
-
-extern "C" int m2tts_set_attention_mode(int mode) {
-  M2_REQUIRE(mode >= 0 && mode <= 3, M2TTS_E_BADSHAPE,
-             "set_attention_mode: 0 = tensor cores 16-bit split, 1 = ffma, 2 = TF32 single-warpgroup kernel, 3 = TF32 warp-specialised kernel");
-  g_attn_mode.store(mode);
-  return M2TTS_OK;
-}
 
 // 64 ints of pinned, device-mapped host memory: kernels that give up on an mbarrier write a code here
 // before trapping, and the host can still read it after the context has been poisoned.
@@ -124,7 +119,7 @@ extern "C" int m2tts_debug_words(int* out, int n) {
   return M2TTS_OK;
 }
 
-extern "C" int m2tts_version(void) { return 101; }
+extern "C" int m2tts_version(void) { return 200; }
 
 extern "C" const char* m2tts_last_error_string(void) { return g_err; }
 

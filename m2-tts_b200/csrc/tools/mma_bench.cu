@@ -9,7 +9,7 @@
 //   mode 4: A K-major 128B-swizzle (smem)      B K-major 128B-swizzle    (linear layers)
 //   mode 5: as mode 4 with kind::f16 (K = 16)                              (16-bit split kernels)
 //   mode 6: as mode 5 with the A start address moved by one 128-byte row  (row-shifted conv taps)
-#include "common.cuh"
+#include "../common.cuh"
 
 namespace m2 {
 

@@ -4,7 +4,7 @@
 // SWIZZLE_64B, chunk index XORed with address bits [7..]); the MMA reads 128 rows starting at row `shift`:
 //   D[m, n] = sum_k A_full[shift + m, k] * B[n, k],   B in the K-major no-swizzle core-matrix layout.
 // `base_offset` is written into descriptor bits 49-51 so both conventions can be checked.
-#include "common.cuh"
+#include "../common.cuh"
 
 namespace m2 {
 

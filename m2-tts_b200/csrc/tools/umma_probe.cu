@@ -4,7 +4,7 @@
 // the canonical UMMA layouts, so descriptor semantics can be checked against a host matmul.
 //   mode 0: K-major,  128-byte swizzle   mode 1: MN-major, 128-byte swizzle
 //   mode 2: K-major,  no swizzle         mode 3: MN-major, no swizzle
-#include "common.cuh"
+#include "../common.cuh"
 
 namespace m2 {
 

@@ -3,7 +3,7 @@
 //   mode 0: A MN-major 128B-swizzle in shared memory, B MN-major 128B-swizzle   (attention Q K^T)
 //   mode 1: A from TMEM (two fp16 per 32-bit column, low half = even k), B K-major 128B-swizzle   (attention P V)
 //   mode 2: A K-major 128B-swizzle in shared memory, B K-major 128B-swizzle
-#include "common.cuh"
+#include "../common.cuh"
 #include <cuda_fp16.h>
 
 namespace m2 {

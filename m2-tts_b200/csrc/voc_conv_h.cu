@@ -29,6 +29,7 @@ struct ConvHArgs {
   const __half* res_h; long long res_plane;     // optional residual planes
   __half* out_h; long long out_plane;    // planes out, or
   float* out_cf;                         // fp32 channel-first [B][C][Lp_out]
+  int32_t* status;                       // M2TTS_ST_FP16_RANGE when the output planes leave the fp16 range
 };
 
 constexpr int CH_C = 128, CH_NT = 64;                // channels, output channels per CTA
@@ -152,6 +153,7 @@ voc_conv_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const ConvHArgs a,
     const int m = qtr * 32 + lane;
     const uint32_t t_lane = tmem_base + ((uint32_t)(qtr * 32) << 16);
     const float* bs = bias_s + eg * 16;
+    bool bad = false;
     int it = 0;
     for (int g = first; g < a.total_tiles; g += cpg, ++it) {
       const int slot = it & 1, use = it >> 1;
@@ -204,14 +206,7 @@ voc_conv_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const ConvHArgs a,
         for (int j = 0; j < 2; ++j) {
           uint32_t hw[4], lw[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float a0 = fminf(fmaxf(y[8 * j + 2 * e], -65000.f), 65000.f), a1 = fminf(fmaxf(y[8 * j + 2 * e + 1], -65000.f), 65000.f);
-            const __half2 hh = __floats2half2_rn(a0, a1);
-            const float2 hf = __half22float2(hh);
-            const __half2 ll = __floats2half2_rn(a0 - hf.x, a1 - hf.y);
-            hw[e] = *reinterpret_cast<const uint32_t*>(&hh);
-            lw[e] = *reinterpret_cast<const uint32_t*>(&ll);
-          }
+          for (int e = 0; e < 4; ++e) h_split2(y[8 * j + 2 * e], y[8 * j + 2 * e + 1], hw[e], lw[e], bad);
           *(reinterpret_cast<uint4*>(a.out_h + o) + j) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
           *(reinterpret_cast<uint4*>(a.out_h + a.out_plane + o) + j) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
         }
@@ -221,6 +216,7 @@ voc_conv_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const ConvHArgs a,
         for (int j = 0; j < 16; ++j) op[(size_t)j * a.Lp_out] = y[j];
       }
     }
+    h_flag(bad, a.status);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -231,22 +227,25 @@ voc_conv_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const ConvHArgs a,
 }
 
 // weight image: [n_tile][tap][k-block][W_hi rows (32) ; W_lo rows (32)][64 k], K-major rows with the 128-byte swizzle
-struct ChPackArgs { const float* w; __half* blob; int CI, CO; };
+struct ChPackArgs { const float* w; __half* blob; int CI, CO; int32_t* status; };
 __global__ void ch_wpack_kernel(ChPackArgs p) {
   const int total = p.CO * CH_C * 3 * 2;
+  bool bad = false;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
     int e = idx;
     const int k = e % CH_C; e /= CH_C;
     const int n = e % (2 * CH_NT); e /= (2 * CH_NT);
     const int tap = e % 3; const int ntile = e / 3;
     const int lo = n / CH_NT, co = ntile * CH_NT + n % CH_NT;
-    const float v = k < p.CI ? fminf(fmaxf(p.w[((size_t)co * p.CI + k) * 3 + tap], -65000.f), 65000.f) : 0.f;      // k >= CI: zero padding
+    const float v = k < p.CI ? p.w[((size_t)co * p.CI + k) * 3 + tap] : 0.f;      // k >= CI: zero padding
+    h_chk(v, bad);
     const __half h = __float2half_rn(v);
     const int kb = k >> 6, kk = k & 63;
     const uint32_t off = (uint32_t)ntile * CH_WBYTES + (uint32_t)(tap * CH_KB + kb) * CH_WKB + (uint32_t)n * CH_RB +
                          ((((uint32_t)kk >> 3) ^ (uint32_t)(n & 7)) << 4) + (uint32_t)(kk & 7) * 2u;
     p.blob[off >> 1] = lo ? __float2half_rn(v - __half2float(h)) : h;
   }
+  h_flag(bad, p.status);
 }
 
 typedef CUresult (*EncodeTiledFn8)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -272,18 +271,20 @@ size_t voc_conv_h_wblob_bytes(int C) { return C % CH_NT == 0 ? (size_t)(C / CH_N
 // have zero weights); CO output channels (multiple of 64); residual planes [2][B][L][CO] optional; output planes or fp32 channel-first.
 int launch_voc_conv_h(const void* xh, long long x_plane, const float* w, const float* bias, void* wblob, const void* res_h,
                       long long res_plane, void* out_h, long long out_plane, float* out_cf, int Lp_out, int B, int CI, int CO, int L, int act,
-                      int stage, cudaStream_t s) {
+                      int stage, int32_t* status, cudaStream_t s) {
   M2_REQUIRE(voc_conv_h_io_eligible(CI, CO), M2TTS_E_UNSUPPORTED, "voc_conv_h: CI=%d CO=%d", CI, CO);
+  if (w != nullptr) {      // (re)write the weight image; w == nullptr: wblob already holds it
+    M2_REQUIRE((((uintptr_t)wblob) & 15) == 0, M2TTS_E_BADSHAPE, "voc_conv_h: misaligned weight image");
+    ChPackArgs p{w, (__half*)wblob, CI, CO, status};
+    M2_LAUNCH(M2TTS_STAGE_PACK, ch_wpack_kernel, ceil_div(CO * CH_C * 6, 256), 256, 0, s, p);
+  }
+  if (xh == nullptr) return M2TTS_OK;      // pack only
   const int C = CI;
   M2_REQUIRE((((uintptr_t)xh) & 15) == 0 && (((uintptr_t)wblob) & 15) == 0 && (x_plane & 7) == 0 && (out_plane & 7) == 0 && (res_plane & 7) == 0,
              M2TTS_E_BADSHAPE, "voc_conv_h: misaligned pointers");
   M2_REQUIRE(B > 0 && L > 0 && (out_h != nullptr || out_cf != nullptr), M2TTS_E_BADSHAPE, "voc_conv_h: B=%d L=%d", B, L);
   EncodeTiledFn8 enc = ch_encode_fn();
   M2_REQUIRE(enc != nullptr, M2TTS_E_CUDA, "voc_conv_h: cuTensorMapEncodeTiled unavailable");
-  {
-    ChPackArgs p{w, (__half*)wblob, CI, CO};
-    M2_LAUNCH(M2TTS_STAGE_PACK, ch_wpack_kernel, ceil_div(CO * CH_C * 6, 256), 256, 0, s, p);
-  }
   CUtensorMap tmap;
   const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)L, (cuuint64_t)B, 2};
   const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)L * C * 2, (cuuint64_t)x_plane * 2};
@@ -296,7 +297,7 @@ int launch_voc_conv_h(const void* xh, long long x_plane, const float* w, const f
   ConvHArgs a{};
   a.B = B; a.L = L; a.Lp_out = Lp_out; a.wblob = (const __half*)wblob; a.bias = bias; a.act = act;
   a.res_h = (const __half*)res_h; a.res_plane = res_plane; a.out_h = (__half*)out_h; a.out_plane = out_plane; a.out_cf = out_cf;
-  a.CO = CO; a.ks1 = (CI - 64 + 15) / 16;
+  a.CO = CO; a.ks1 = (CI - 64 + 15) / 16; a.status = status;
   a.n_tiles = CO / CH_NT;
   a.tiles_per_utt = ceil_div(L, CH_NOUT);
   a.total_tiles = B * a.tiles_per_utt;
@@ -328,7 +329,7 @@ extern "C" size_t m2tts_conv1d_k3_h_workspace_bytes(int B, int C, int L) {
 // x / residual fp32 CHANNEL-LAST [B][L][C]; y fp32 channel-first [B][C][L] (out_cl = 0) or channel-last [B][L][C] (out_cl = 1, through
 // the fp16 hi/lo planes the kernel hands to the next 16-bit split kernel).
 extern "C" int m2tts_conv1d_k3_h(const float* x, const float* w, const float* b, const float* residual, float* y, int B, int C, int L,
-                                 int act, int out_cl, void* workspace, size_t workspace_bytes, m2tts_stream_t stream) {
+                                 int act, int out_cl, int32_t* status, void* workspace, size_t workspace_bytes, m2tts_stream_t stream) {
   M2_REQUIRE(x && w && b && y && workspace, M2TTS_E_NULLPTR, "conv1d_k3_h: null pointer");
   M2_REQUIRE(voc_conv_h_eligible(C, 1), M2TTS_E_UNSUPPORTED, "conv1d_k3_h: C=%d (128)", C);
   M2_REQUIRE(act >= 0 && act <= 1 && out_cl >= 0 && out_cl <= 1, M2TTS_E_BADSHAPE, "conv1d_k3_h: act=%d out_cl=%d", act, out_cl);
@@ -340,11 +341,11 @@ extern "C" int m2tts_conv1d_k3_h(const float* x, const float* w, const float* b,
   __half* yp = cv.take<__half>((size_t)2 * n);
   M2_REQUIRE(cv.ok(), M2TTS_E_WORKSPACE, "conv1d_k3_h: workspace too small or misaligned");
   cudaStream_t s = (cudaStream_t)stream;
-  int rc = launch_split_planes_h(x, xp, n, s);
+  int rc = launch_split_planes_h(x, xp, n, status, s);
   if (rc) return rc;
-  if (residual != nullptr && (rc = launch_split_planes_h(residual, rp, n, s))) return rc;
+  if (residual != nullptr && (rc = launch_split_planes_h(residual, rp, n, status, s))) return rc;
   rc = launch_voc_conv_h(xp, n, w, b, wblob, residual ? rp : nullptr, n, out_cl ? yp : nullptr, n, out_cl ? nullptr : y, L, B, C, C, L, act,
-                         M2TTS_STAGE_VOC_RES1, s);
+                         M2TTS_STAGE_VOC_RES1, status, s);
   if (rc) return rc;
   if (out_cl) M2_LAUNCH(M2TTS_STAGE_VOC_RES1, ch_join_planes_kernel, 1184, 256, 0, s, yp, n, y);
   return M2TTS_OK;

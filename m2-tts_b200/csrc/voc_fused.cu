@@ -575,13 +575,15 @@ int launch_voc_stage_fused(const float* x, const float* up_w, const float* up_b,
                            const float* w2, const float* b2, const float* out_w, const float* out_b, float* wblob,
                            float* out, int B, int C, int L_in, int stage, cudaStream_t s) {
   M2_REQUIRE(C == 16 || C == 32, M2TTS_E_UNSUPPORTED, "voc_fused: C=%d (16 or 32)", C);
-  M2_REQUIRE((((uintptr_t)x) & 15) == 0 && (((uintptr_t)out) & 15) == 0 && (((uintptr_t)wblob) & 15) == 0, M2TTS_E_BADSHAPE,
-             "voc_fused: misaligned pointers");
-  M2_REQUIRE(B > 0 && L_in > 0 && (long long)B * L_in * 2 < (1ll << 31), M2TTS_E_BADSHAPE, "voc_fused: B=%d L=%d", B, L_in);
-  {
+  if (up_w != nullptr) {      // (re)write the weight image; up_w == nullptr: wblob already holds it
+    M2_REQUIRE(w1 != nullptr && w2 != nullptr && (((uintptr_t)wblob) & 15) == 0, M2TTS_E_BADSHAPE, "voc_fused: pack arguments");
     FsPackArgs p{up_w, w1, w2, wblob, C};
     M2_LAUNCH(M2TTS_STAGE_PACK, fs_wpack_kernel, ceil_div(28 * C * C, 256), 256, 0, s, p);
   }
+  if (x == nullptr) return M2TTS_OK;      // pack only
+  M2_REQUIRE((((uintptr_t)x) & 15) == 0 && (((uintptr_t)out) & 15) == 0 && (((uintptr_t)wblob) & 15) == 0, M2TTS_E_BADSHAPE,
+             "voc_fused: misaligned pointers");
+  M2_REQUIRE(B > 0 && L_in > 0 && (long long)B * L_in * 2 < (1ll << 31), M2TTS_E_BADSHAPE, "voc_fused: B=%d L=%d", B, L_in);
   FusedStageArgs a{};
   a.B = B; a.L_in = L_in; a.L_out = 2 * L_in; a.wblob = wblob; a.bias_up = up_b; a.bias1 = b1; a.bias2 = b2;
   a.out_w = out_w; a.out_b = out_b; a.out = out; a.prof = g_fs_prof;
@@ -595,7 +597,9 @@ int launch_voc_stage_fused(const float* x, const float* up_w, const float* up_b,
 using namespace m2;
 
 // bring-up: device buffer of 64 x 8 int64 that receives phase timestamps (NULL = off)
+#ifdef M2TTS_TOOLS
 extern "C" int m2tts_vocoder_stage_fused_set_prof(long long* dev_buf) { m2::g_fs_prof = dev_buf; return M2TTS_OK; }
+#endif
 
 extern "C" size_t m2tts_vocoder_stage_fused_workspace_bytes(int C) {
   if (C != 16 && C != 32) return 0;

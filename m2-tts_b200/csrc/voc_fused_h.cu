@@ -10,7 +10,7 @@
 //   * K = 16 per UMMA: half the UMMA count of the TF32 kernel.
 // Same organisation otherwise: channel-last rows are the K-major A operand, a convolution tap is the descriptor start
 // address moved by whole rows, taps / phases / hi-lo folded into N, U and V written by the epilogue warps straight
-// into swizzled operand rows. fp16 needs |x| < 65504: every producer saturates at +-65000.
+// into swizzled operand rows. fp16 needs |x| <= 65504: every producer checks its values and raises M2TTS_ST_FP16_RANGE.
 #include "conv_tc.cuh"
 #include "attention_tc.cuh"
 #include <cuda_fp16.h>
@@ -28,6 +28,7 @@ struct FusedHArgs {
   float* out_f;                          // non-final alternative: fp32 channel-last [B][L_out][C]; FINAL: audio [B][L_out]
   int dbg_nostore;                       // bring-up timing experiment (M2TTS_DBG_NOSTORE=1): skip the plane stores, results invalid
   long long out_plane;                   // elements between the hi and the lo plane of out_h
+  int32_t* status;                       // M2TTS_ST_FP16_RANGE when U, V or the output planes leave the fp16 range
 };
 
 template <int C, int NCTX, bool FINAL>
@@ -97,18 +98,11 @@ __device__ __forceinline__ void fh_ld_sum16(uint32_t t_main, uint32_t t_corr, fl
 #pragma unroll
   for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(a[j]) + __uint_as_float(b[j]);
 }
-// 8 floats -> one 16-byte chunk of fp16 hi and one of fp16 lo (saturated to the fp16 range)
-__device__ __forceinline__ void fh_split8(const float* x, uint4& hi, uint4& lo) {
+// 8 floats -> one 16-byte chunk of fp16 hi and one of fp16 lo; `bad` records a value outside the fp16 range
+__device__ __forceinline__ void fh_split8(const float* x, uint4& hi, uint4& lo, bool& bad) {
   uint32_t h[4], l[4];
 #pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    const float a0 = fminf(fmaxf(x[2 * e], -65000.f), 65000.f), a1 = fminf(fmaxf(x[2 * e + 1], -65000.f), 65000.f);
-    const __half2 hh = __floats2half2_rn(a0, a1);
-    const float2 hf = __half22float2(hh);
-    const __half2 ll = __floats2half2_rn(a0 - hf.x, a1 - hf.y);
-    h[e] = *reinterpret_cast<const uint32_t*>(&hh);
-    l[e] = *reinterpret_cast<const uint32_t*>(&ll);
-  }
+  for (int e = 0; e < 4; ++e) h_split2(x[2 * e], x[2 * e + 1], h[e], l[e], bad);
   hi = make_uint4(h[0], h[1], h[2], h[3]);
   lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
@@ -299,6 +293,7 @@ voc_stage_fused_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const Fused
     const float* b_up = consts, *b1 = consts + C, *b2 = consts + 2 * C, *ow = consts + 3 * C;
     constexpr int CG = C / G;                        // channels per warpgroup in EPI2 / EPI3
     const int cg0 = g * CG;
+    bool bad = false;
     for (int it = 0; it < n_iter; ++it) {
       const int gt = tile_of(it, c);
       if (gt >= a.total_tiles) break;
@@ -327,7 +322,7 @@ voc_stage_fused_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const Fused
 #pragma unroll
             for (int j8 = 0; j8 < 2; ++j8) {
               uint4 hi, lo;
-              fh_split8(v + 8 * j8, hi, lo);
+              fh_split8(v + 8 * j8, hi, lo, bad);
               const uint32_t off = fh_swz64(row, (c0 >> 3) + j8);
               *reinterpret_cast<uint4*>(Ub + off) = hi;
               *reinterpret_cast<uint4*>(Ub + K::UPL + off) = lo;
@@ -358,7 +353,7 @@ voc_stage_fused_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const Fused
 #pragma unroll
           for (int j8 = 0; j8 < 2; ++j8) {
             uint4 hi, lo;
-            fh_split8(v + 8 * j8, hi, lo);
+            fh_split8(v + 8 * j8, hi, lo, bad);
             const uint32_t off = fh_swz64(i + 1, (c0 >> 3) + j8);
             *reinterpret_cast<uint4*>(Vb + off) = hi;
             *reinterpret_cast<uint4*>(Vb + K::UPL + off) = lo;
@@ -399,7 +394,7 @@ voc_stage_fused_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const Fused
 #pragma unroll
                 for (int j8 = 0; j8 < 2; ++j8) {
                   uint4 hi, lo;
-                  fh_split8(y + 8 * j8, hi, lo);
+                  fh_split8(y + 8 * j8, hi, lo, bad);
                   if (!a.dbg_nostore) *reinterpret_cast<uint4*>(a.out_h + o + 8 * j8) = hi;
                   if (!a.dbg_nostore) *reinterpret_cast<uint4*>(a.out_h + a.out_plane + o + 8 * j8) = lo;
                 }
@@ -447,6 +442,7 @@ voc_stage_fused_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const Fused
         fh_group_sync(c, 128 * G);            // exch reads done before the next tile rewrites it
       }
     }
+    h_flag(bad, a.status);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -457,12 +453,13 @@ voc_stage_fused_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const Fused
 }
 
 // ---- weight image: K-major rows with the swizzle of the operand they multiply; parts stack [hi rows ; lo rows] ----
-struct FhPackArgs { const float* up_w; const float* w1; const float* w2; __half* blob; int C; };
+struct FhPackArgs { const float* up_w; const float* w1; const float* w2; __half* blob; int C; int32_t* status; };
 __global__ void fh_wpack_kernel(FhPackArgs p) {
   const int C = p.C, CI = 2 * C, XRB = CI * 2;
   const int n_up0 = 4 * C * CI, n_upm = 2 * C * CI, n_conv = 2 * C * C;
   const int total = n_up0 + 2 * n_upm + 6 * n_conv;
   const uint32_t b_upm = 4 * C * XRB, b_upp = b_upm + 2 * C * XRB, b_c = b_upp + 2 * C * XRB;
+  bool bad = false;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
     int e = idx, n, k, lo, rowb;
     uint32_t base;
@@ -485,25 +482,28 @@ __global__ void fh_wpack_kernel(FhPackArgs p) {
       const float* w = part < 3 ? p.w1 : p.w2;
       v = w[((size_t)co * C + k) * 3 + (part % 3)];
     }
-    v = fminf(fmaxf(v, -65000.f), 65000.f);
+    h_chk(v, bad);
     const __half h = __float2half_rn(v);
     const uint32_t sw = rowb == 128 ? (uint32_t)(n & 7) : (uint32_t)((n >> 1) & 3);
     const uint32_t off = base + (uint32_t)n * rowb + ((((uint32_t)k >> 3) ^ sw) << 4) + (uint32_t)(k & 7) * 2u;
     p.blob[off >> 1] = lo ? __float2half_rn(v - __half2float(h)) : h;
   }
+  h_flag(bad, p.status);
 }
 
 // fp32 channel-last rows -> fp16 hi/lo planes (stand-alone entry / producers that are not ours) and back
-__global__ void fh_split_planes_kernel(const float* __restrict__ x, __half* __restrict__ planes, long long n) {
+__global__ void fh_split_planes_kernel(const float* __restrict__ x, __half* __restrict__ planes, long long n, int32_t* __restrict__ status) {
+  bool bad = false;
   for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8; i < n; i += (long long)gridDim.x * blockDim.x * 8) {
     float v[8];
     const float4 a = *reinterpret_cast<const float4*>(x + i), b = *reinterpret_cast<const float4*>(x + i + 4);
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
     uint4 hi, lo;
-    fh_split8(v, hi, lo);
+    fh_split8(v, hi, lo, bad);
     *reinterpret_cast<uint4*>(planes + i) = hi;
     *reinterpret_cast<uint4*>(planes + n + i) = lo;
   }
+  h_flag(bad, status);
 }
 
 typedef CUresult (*EncodeTiledFn6)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -550,20 +550,23 @@ size_t voc_fused_h_wblob_bytes(int C) { return C == 32 ? FhCfg<32, 1, false>::WB
 // [2][B][2L][C], out_plane apart) or out_f (fp32 channel-last [B][2L][C]); with out_w != null: audio fp32 [B][2L] in out_f.
 int launch_voc_stage_fused_h(const void* xh, long long x_plane, const float* up_w, const float* up_b, const float* w1, const float* b1,
                              const float* w2, const float* b2, const float* out_w, const float* out_b, void* wblob,
-                             void* out_h, long long out_plane, float* out_f, int B, int C, int L_in, int stage, cudaStream_t s) {
+                             void* out_h, long long out_plane, float* out_f, int B, int C, int L_in, int stage, int32_t* status, cudaStream_t s) {
   M2_REQUIRE(C == 16 || C == 32, M2TTS_E_UNSUPPORTED, "voc_fused_h: C=%d (16 or 32)", C);
+  if (up_w != nullptr) {      // (re)write the weight image; up_w == nullptr: wblob already holds it
+    M2_REQUIRE(w1 != nullptr && w2 != nullptr && (((uintptr_t)wblob) & 15) == 0, M2TTS_E_BADSHAPE, "voc_fused_h: pack arguments");
+    FhPackArgs p{up_w, w1, w2, (__half*)wblob, C, status};
+    M2_LAUNCH(M2TTS_STAGE_PACK, fh_wpack_kernel, ceil_div(28 * C * C, 256), 256, 0, s, p);
+  }
+  if (xh == nullptr) return M2TTS_OK;      // pack only
   M2_REQUIRE((((uintptr_t)xh) & 15) == 0 && (((uintptr_t)wblob) & 15) == 0 && (x_plane & 7) == 0 && (out_plane & 7) == 0, M2TTS_E_BADSHAPE,
              "voc_fused_h: misaligned pointers");
   M2_REQUIRE(B > 0 && L_in > 0 && (long long)B * L_in * 2 < (1ll << 31), M2TTS_E_BADSHAPE, "voc_fused_h: B=%d L=%d", B, L_in);
   M2_REQUIRE(out_h != nullptr || out_f != nullptr, M2TTS_E_NULLPTR, "voc_fused_h: no output");
-  {
-    FhPackArgs p{up_w, w1, w2, (__half*)wblob, C};
-    M2_LAUNCH(M2TTS_STAGE_PACK, fh_wpack_kernel, ceil_div(28 * C * C, 256), 256, 0, s, p);
-  }
   FusedHArgs a{};
   a.B = B; a.L_in = L_in; a.L_out = 2 * L_in; a.wblob = (const __half*)wblob; a.bias_up = up_b; a.bias1 = b1; a.bias2 = b2;
   a.out_w = out_w; a.out_b = out_b; a.out_h = (__half*)out_h; a.out_f = out_f; a.out_plane = out_plane;
-  { static int ns = -1; if (ns < 0) { const char* e = getenv("M2TTS_DBG_NOSTORE"); ns = (e && e[0] == '1') ? 1 : 0; } a.dbg_nostore = ns; }
+  { static int ns = -1; if (ns < 0) ns = tools_env_int("M2TTS_DBG_NOSTORE", 0) == 1 ? 1 : 0; a.dbg_nostore = ns; }
+  a.status = status;
   const bool fin = out_w != nullptr;
   if (fin) M2_REQUIRE(out_f != nullptr, M2TTS_E_NULLPTR, "voc_fused_h: the last stage writes fp32 audio");
   const __half* x = (const __half*)xh;
@@ -571,11 +574,11 @@ int launch_voc_stage_fused_h(const void* xh, long long x_plane, const float* up_
   return fin ? launch_fh<32, 1, true>(x, x_plane, a, stage, s) : launch_fh<32, 1, false>(x, x_plane, a, stage, s);
 }
 
-int launch_split_planes_h(const float* x, void* planes, long long n, cudaStream_t s) {
+int launch_split_planes_h(const float* x, void* planes, long long n, int32_t* status, cudaStream_t s) {
   M2_REQUIRE((n & 7) == 0 && (((uintptr_t)x) & 15) == 0 && (((uintptr_t)planes) & 15) == 0, M2TTS_E_BADSHAPE, "split_planes: n=%lld", n);
   long long blocks = (n / 8 + 255) / 256;
   if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
-  M2_LAUNCH(M2TTS_STAGE_PACK, fh_split_planes_kernel, (unsigned)blocks, 256, 0, s, x, (__half*)planes, n);
+  M2_LAUNCH(M2TTS_STAGE_PACK, fh_split_planes_kernel, (unsigned)blocks, 256, 0, s, x, (__half*)planes, n, status);
   return M2TTS_OK;
 }
 
@@ -592,7 +595,7 @@ extern "C" size_t m2tts_vocoder_stage_fused_h_workspace_bytes(int B, int C, int 
 extern "C" int m2tts_vocoder_stage_fused_h(const float* x, const float* up_w, const float* up_b, const float* res1_w,
                                            const float* res1_b, const float* res2_w, const float* res2_b,
                                            const float* out_w, const float* out_b, float* y, int B, int C, int L,
-                                           void* workspace, size_t workspace_bytes, m2tts_stream_t stream) {
+                                           int32_t* status, void* workspace, size_t workspace_bytes, m2tts_stream_t stream) {
   M2_REQUIRE(x && up_w && up_b && res1_w && res1_b && res2_w && res2_b && y && workspace, M2TTS_E_NULLPTR,
              "vocoder_stage_fused_h: null pointer");
   M2_REQUIRE((out_w == nullptr) == (out_b == nullptr), M2TTS_E_NULLPTR, "vocoder_stage_fused_h: out_w/out_b must both be set or both null");
@@ -603,8 +606,8 @@ extern "C" int m2tts_vocoder_stage_fused_h(const float* x, const float* up_w, co
   __half* planes = cv.take<__half>((size_t)2 * n);
   M2_REQUIRE(cv.ok(), M2TTS_E_WORKSPACE, "vocoder_stage_fused_h: workspace too small or misaligned");
   cudaStream_t s = (cudaStream_t)stream;
-  int rc = launch_split_planes_h(x, planes, n, s);
+  int rc = launch_split_planes_h(x, planes, n, status, s);
   if (rc) return rc;
   return launch_voc_stage_fused_h(planes, n, up_w, up_b, res1_w, res1_b, res2_w, res2_b, out_w, out_b, wblob, nullptr, 0, y, B, C, L,
-                                  M2TTS_STAGE_VOC_FUSED, s);
+                                  M2TTS_STAGE_VOC_FUSED, status, s);
 }

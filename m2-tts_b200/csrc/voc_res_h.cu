@@ -24,6 +24,7 @@ struct ResHArgs {
   float* out_f;                          // fp32 channel-last [B][L][C]
   long long* prof;                       // bring-up: phase timestamps of CTA 0's first epilogue warp (m2tts_attention_set_prof buffer)
   int dbg_nostore;                       // bring-up timing experiment (M2TTS_DBG_NOSTORE=1): skip the plane stores, results invalid
+  int32_t* status;                       // M2TTS_ST_FP16_RANGE when V or the output planes leave the fp16 range
 };
 
 template <int C>
@@ -59,17 +60,10 @@ __device__ __forceinline__ void rh_mma_w(uint32_t d, uint64_t ad, uint64_t bd, u
                "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                ::"r"(d), "l"(ad), "l"(bd), "r"(idesc), "r"(acc) : "memory");
 }
-__device__ __forceinline__ void rh_split8(const float* x, uint4& hi, uint4& lo) {
+__device__ __forceinline__ void rh_split8(const float* x, uint4& hi, uint4& lo, bool& bad) {
   uint32_t h[4], l[4];
 #pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    const float a0 = fminf(fmaxf(x[2 * e], -65000.f), 65000.f), a1 = fminf(fmaxf(x[2 * e + 1], -65000.f), 65000.f);
-    const __half2 hh = __floats2half2_rn(a0, a1);
-    const float2 hf = __half22float2(hh);
-    const __half2 ll = __floats2half2_rn(a0 - hf.x, a1 - hf.y);
-    h[e] = *reinterpret_cast<const uint32_t*>(&hh);
-    l[e] = *reinterpret_cast<const uint32_t*>(&ll);
-  }
+  for (int e = 0; e < 4; ++e) h_split2(x[2 * e], x[2 * e + 1], h[e], l[e], bad);
   hi = make_uint4(h[0], h[1], h[2], h[3]);
   lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
@@ -192,6 +186,7 @@ voc_res_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     const float* b1 = consts, *b2 = consts + C;
     constexpr int CG = C / K::NG;
     const int cg0 = g * CG;
+    bool bad = false;
     for (int it = 0; it < n_iter; ++it) {
       const int gt = tile_of(it);
       if (gt >= a.total_tiles) break;
@@ -220,7 +215,7 @@ voc_res_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 #pragma unroll
           for (int j8 = 0; j8 < 2; ++j8) {
             uint4 hi, lo;
-            rh_split8(v + 8 * j8, hi, lo);
+            rh_split8(v + 8 * j8, hi, lo, bad);
             const uint32_t off = rh_swz128(m + 1, (c0 >> 3) + j8);
             *reinterpret_cast<uint4*>(Vb + off) = hi;
             *reinterpret_cast<uint4*>(Vb + K::VPL + off) = lo;
@@ -265,7 +260,7 @@ voc_res_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 #pragma unroll
           for (int j8 = 0; j8 < 2; ++j8) {
             uint4 hi, lo;
-            rh_split8(y + 8 * j8, hi, lo);
+            rh_split8(y + 8 * j8, hi, lo, bad);
             const uint32_t off = rh_swz128(m + 1, (c0 >> 3) + j8);
             *reinterpret_cast<uint4*>(Xw + off) = hi;
             *reinterpret_cast<uint4*>(Xw + K::XPL + off) = lo;
@@ -298,6 +293,7 @@ voc_res_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       if (lane == 0) ct_arrive(bar_xe + 8 * (it & 1));      // this input slot (the residual) has been read
     }
     if (a.out_h != nullptr && warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    h_flag(bad, a.status);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -308,20 +304,23 @@ voc_res_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 }
 
 // weight image: per (conv, tap) a part [W_hi rows ; W_lo rows] x C, K-major rows with the 128-byte swizzle
-struct RhPackArgs { const float* w1; const float* w2; __half* blob; int C; };
+struct RhPackArgs { const float* w1; const float* w2; __half* blob; int C; int32_t* status; };
 __global__ void rh_wpack_kernel(RhPackArgs p) {
   const int C = p.C, RB = 2 * C;
   const int per = 2 * C * C, total = 6 * per;
+  bool bad = false;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
     const int part = idx / per, e = idx - part * per;
     const int n = e / C, k = e % C;
     const int co = n % C, lo = n / C;
     const float* w = part < 3 ? p.w1 : p.w2;
-    const float v = fminf(fmaxf(w[((size_t)co * C + k) * 3 + (part % 3)], -65000.f), 65000.f);
+    const float v = w[((size_t)co * C + k) * 3 + (part % 3)];
+    h_chk(v, bad);
     const __half h = __float2half_rn(v);
     const uint32_t off = (uint32_t)part * (2 * C * RB) + (uint32_t)n * RB + ((((uint32_t)k >> 3) ^ (uint32_t)(n & 7)) << 4) + (uint32_t)(k & 7) * 2u;
     p.blob[off >> 1] = lo ? __float2half_rn(v - __half2float(h)) : h;
   }
+  h_flag(bad, p.status);
 }
 
 typedef CUresult (*EncodeTiledFn7)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -345,18 +344,20 @@ size_t voc_res_h_wblob_bytes(int C) { return C == 64 ? RhCfg<64>::WBYTES : 0; }
 
 // uh: fp16 hi/lo planes channel-last [2][B][L][C] (u_plane elements apart); output planes (out_h/out_plane) or fp32 CL (out_f)
 int launch_voc_res_h(const void* uh, long long u_plane, const float* w1, const float* b1, const float* w2, const float* b2, void* wblob,
-                     void* out_h, long long out_plane, float* out_f, int B, int C, int L, int stage, cudaStream_t s) {
+                     void* out_h, long long out_plane, float* out_f, int B, int C, int L, int stage, int32_t* status, cudaStream_t s) {
   M2_REQUIRE(C == 64, M2TTS_E_UNSUPPORTED, "voc_res_h: C=%d (64)", C);
+  if (w1 != nullptr) {      // (re)write the weight image; w1 == nullptr: wblob already holds it
+    M2_REQUIRE(w2 != nullptr && (((uintptr_t)wblob) & 15) == 0, M2TTS_E_BADSHAPE, "voc_res_h: pack arguments");
+    RhPackArgs p{w1, w2, (__half*)wblob, C, status};
+    M2_LAUNCH(M2TTS_STAGE_PACK, rh_wpack_kernel, ceil_div(12 * C * C, 256), 256, 0, s, p);
+  }
+  if (uh == nullptr) return M2TTS_OK;      // pack only
   M2_REQUIRE((((uintptr_t)uh) & 15) == 0 && (((uintptr_t)wblob) & 15) == 0 && (u_plane & 7) == 0 && (out_plane & 7) == 0, M2TTS_E_BADSHAPE,
              "voc_res_h: misaligned pointers");
   M2_REQUIRE(B > 0 && L > 0 && (out_h != nullptr || out_f != nullptr), M2TTS_E_BADSHAPE, "voc_res_h: B=%d L=%d", B, L);
   using K = RhCfg<64>;
   EncodeTiledFn7 enc = rh_encode_fn();
   M2_REQUIRE(enc != nullptr, M2TTS_E_CUDA, "voc_res_h: cuTensorMapEncodeTiled unavailable");
-  {
-    RhPackArgs p{w1, w2, (__half*)wblob, C};
-    M2_LAUNCH(M2TTS_STAGE_PACK, rh_wpack_kernel, ceil_div(12 * C * C, 256), 256, 0, s, p);
-  }
   CUtensorMap tmap;
   const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)L, (cuuint64_t)B, 2};
   const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)L * C * 2, (cuuint64_t)u_plane * 2};
@@ -370,7 +371,8 @@ int launch_voc_res_h(const void* uh, long long u_plane, const float* w1, const f
   a.B = B; a.L = L; a.wblob = (const __half*)wblob; a.bias1 = b1; a.bias2 = b2;
   a.out_h = (__half*)out_h; a.out_plane = out_plane;
   a.prof = g_ws_prof;
-  { static int ns = -1; if (ns < 0) { const char* e = getenv("M2TTS_DBG_NOSTORE"); ns = (e && e[0] == '1') ? 1 : 0; } a.dbg_nostore = ns; } a.out_f = out_f;
+  { static int ns = -1; if (ns < 0) ns = tools_env_int("M2TTS_DBG_NOSTORE", 0) == 1 ? 1 : 0; a.dbg_nostore = ns; }
+  a.out_f = out_f; a.status = status;
   a.tiles_per_utt = ceil_div(L, K::NOUT);
   a.total_tiles = B * a.tiles_per_utt;
   const int grid = a.total_tiles < kNumSMs ? a.total_tiles : kNumSMs;
@@ -400,7 +402,7 @@ extern "C" size_t m2tts_resblock_fused_h_workspace_bytes(int B, int C, int L) {
 
 // y = x + conv2(leaky_relu(conv1(x), 0.1)) (components.py:196-200), x / y fp32 CHANNEL-LAST [B][L][C], C = 64, k = 3, dilation 1.
 extern "C" int m2tts_resblock_fused_h(const float* x, const float* w1, const float* b1, const float* w2, const float* b2, float* y,
-                                      int B, int C, int L, void* workspace, size_t workspace_bytes, m2tts_stream_t stream) {
+                                      int B, int C, int L, int32_t* status, void* workspace, size_t workspace_bytes, m2tts_stream_t stream) {
   M2_REQUIRE(x && w1 && b1 && w2 && b2 && y && workspace, M2TTS_E_NULLPTR, "resblock_fused_h: null pointer");
   M2_REQUIRE(C == 64, M2TTS_E_UNSUPPORTED, "resblock_fused_h: C=%d (64)", C);
   Carver cv(workspace, workspace_bytes);
@@ -409,7 +411,7 @@ extern "C" int m2tts_resblock_fused_h(const float* x, const float* w1, const flo
   __half* planes = cv.take<__half>((size_t)2 * n);
   M2_REQUIRE(cv.ok(), M2TTS_E_WORKSPACE, "resblock_fused_h: workspace too small or misaligned");
   cudaStream_t s = (cudaStream_t)stream;
-  int rc = launch_split_planes_h(x, planes, n, s);
+  int rc = launch_split_planes_h(x, planes, n, status, s);
   if (rc) return rc;
-  return launch_voc_res_h(planes, n, w1, b1, w2, b2, wblob, nullptr, 0, y, B, C, L, M2TTS_STAGE_VOC_RES1, s);
+  return launch_voc_res_h(planes, n, w1, b1, w2, b2, wblob, nullptr, 0, y, B, C, L, M2TTS_STAGE_VOC_RES1, status, s);
 }

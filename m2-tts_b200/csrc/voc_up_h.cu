@@ -23,6 +23,7 @@ struct UpHArgs {
   const float* bias;
   __half* out_h; long long out_plane;
   int dbg_mode;                          // bring-up timing experiments: 1 no stores, 2 no UMMAs, 4 no TMA loads (results invalid)
+  int32_t* status;                       // M2TTS_ST_FP16_RANGE when the output planes leave the fp16 range
 };
 
 template <int CI, int COT>
@@ -185,6 +186,7 @@ voc_up_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     constexpr uint32_t ORB = COT * 2;
     const uint32_t sw = ORB == 128 ? (uint32_t)(m & 7) : (uint32_t)((m >> 1) & 3);
     const bool leader = warp == 2 && lane == 0;
+    bool bad = false;
     int it = 0;
     for (int g = first; g < a.total_tiles; g += cpg, ++it) {
       const int ab = it & 1, ause = it >> 1;
@@ -211,12 +213,7 @@ voc_up_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
           float y1 = __uint_as_float(vm[c + 1]) + __uint_as_float(vc[c + 1]) + bs[c + 1];
           y0 = y0 > 0.f ? y0 : 0.1f * y0;
           y1 = y1 > 0.f ? y1 : 0.1f * y1;
-          y0 = fminf(fmaxf(y0, -65000.f), 65000.f); y1 = fminf(fmaxf(y1, -65000.f), 65000.f);
-          const __half2 hh = __floats2half2_rn(y0, y1);
-          const float2 hf = __half22float2(hh);
-          const __half2 ll = __floats2half2_rn(y0 - hf.x, y1 - hf.y);
-          hw[e] = *reinterpret_cast<const uint32_t*>(&hh);
-          lw[e] = *reinterpret_cast<const uint32_t*>(&ll);
+          h_split2(y0, y1, hw[e], lw[e], bad);
         }
         hv[j] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
         lv[j] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
@@ -250,6 +247,7 @@ voc_up_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       }
     }
     if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    h_flag(bad, a.status);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -261,11 +259,12 @@ voc_up_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
 
 // weight image: [n_tile = phase * co_tiles + co_tile][tap][k-block][W_hi rows (COT) ; W_lo rows (COT)][64 k], 128-byte swizzle.
 // ConvTranspose1d weight [CI][CO][8]: tap 0 <-> kernel index p + 2 (x[q]); tap 1 <-> p + 6 (x[q-1], p < 2) or p - 2 (x[q+1], p >= 2).
-struct UhPackArgs { const float* w; __half* blob; int CI, COT; };
+struct UhPackArgs { const float* w; __half* blob; int CI, COT; int32_t* status; };
 __global__ void uh_wpack_kernel(UhPackArgs p) {
   const int CO = p.CI / 2, KB = p.CI / 64, co_tiles = CO / p.COT;
   const int total = 4 * CO * 2 * p.CI * 2;       // phases x co x taps x ci x (hi, lo)
   const uint32_t wkb = 2u * p.COT * 128u, wbytes = 2u * KB * wkb;
+  bool bad = false;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
     int e = idx;
     const int k = e % p.CI; e /= p.CI;
@@ -273,13 +272,15 @@ __global__ void uh_wpack_kernel(UhPackArgs p) {
     const int tap = e % 2; const int ntile = e / 2;
     const int ph = ntile / co_tiles, co = (ntile % co_tiles) * p.COT + n % p.COT, lo = n / p.COT;
     const int kw = tap == 0 ? ph + 2 : (ph < 2 ? ph + 6 : ph - 2);
-    const float v = fminf(fmaxf(p.w[((size_t)k * CO + co) * 8 + kw], -65000.f), 65000.f);
+    const float v = p.w[((size_t)k * CO + co) * 8 + kw];
+    h_chk(v, bad);
     const __half h = __float2half_rn(v);
     const int kb = k >> 6, kk = k & 63;
     const uint32_t off = (uint32_t)ntile * wbytes + (uint32_t)(tap * KB + kb) * wkb + (uint32_t)n * 128u +
                          ((((uint32_t)kk >> 3) ^ (uint32_t)(n & 7)) << 4) + (uint32_t)(kk & 7) * 2u;
     p.blob[off >> 1] = lo ? __float2half_rn(v - __half2float(h)) : h;
   }
+  h_flag(bad, p.status);
 }
 
 typedef CUresult (*EncodeTiledFn9)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -315,18 +316,20 @@ static int launch_up_h_t(const CUtensorMap& tmap, const CUtensorMap& tmap_y, UpH
 
 // xh: fp16 hi/lo planes channel-last [2][B][L][CI] (x_plane elements apart) -> out_h planes [2][B][4L][CI/2] = lrelu(convT(x) + bias)
 int launch_voc_up_h(const void* xh, long long x_plane, const float* w, const float* bias, void* wblob, void* out_h, long long out_plane,
-                    int B, int CI, int L, int stage, cudaStream_t s) {
+                    int B, int CI, int L, int stage, int32_t* status, cudaStream_t s) {
   M2_REQUIRE(voc_up_h_eligible(CI, CI / 2, 4), M2TTS_E_UNSUPPORTED, "voc_up_h: CI=%d (256 or 128)", CI);
+  const int COT = 64;
+  if (w != nullptr) {      // (re)write the weight image; w == nullptr: wblob already holds it
+    M2_REQUIRE((((uintptr_t)wblob) & 15) == 0, M2TTS_E_BADSHAPE, "voc_up_h: misaligned weight image");
+    UhPackArgs p{w, (__half*)wblob, CI, COT, status};
+    M2_LAUNCH(M2TTS_STAGE_PACK, uh_wpack_kernel, ceil_div(16 * CI * (CI / 2), 256), 256, 0, s, p);
+  }
+  if (xh == nullptr) return M2TTS_OK;      // pack only
   M2_REQUIRE((((uintptr_t)xh) & 15) == 0 && (((uintptr_t)wblob) & 15) == 0 && (((uintptr_t)out_h) & 15) == 0 && (x_plane & 7) == 0 && (out_plane & 7) == 0,
              M2TTS_E_BADSHAPE, "voc_up_h: misaligned pointers");
   M2_REQUIRE(B > 0 && L > 0, M2TTS_E_BADSHAPE, "voc_up_h: B=%d L=%d", B, L);
   EncodeTiledFn9 enc = uh_encode_fn();
   M2_REQUIRE(enc != nullptr, M2TTS_E_CUDA, "voc_up_h: cuTensorMapEncodeTiled unavailable");
-  const int COT = 64;
-  {
-    UhPackArgs p{w, (__half*)wblob, CI, COT};
-    M2_LAUNCH(M2TTS_STAGE_PACK, uh_wpack_kernel, ceil_div(16 * CI * (CI / 2), 256), 256, 0, s, p);
-  }
   CUtensorMap tmap;
   const cuuint64_t dims[4] = {(cuuint64_t)CI, (cuuint64_t)L, (cuuint64_t)B, 2};
   const cuuint64_t strides[3] = {(cuuint64_t)CI * 2, (cuuint64_t)L * CI * 2, (cuuint64_t)x_plane * 2};
@@ -340,7 +343,7 @@ int launch_voc_up_h(const void* xh, long long x_plane, const float* w, const flo
   a.B = B; a.L = L; a.wblob = (const __half*)wblob; a.bias = bias; a.out_h = (__half*)out_h; a.out_plane = out_plane;
   a.tiles_per_utt = ceil_div(L, 128);
   a.total_tiles = B * a.tiles_per_utt;
-  a.dbg_mode = g_uh_dbg;
+  a.dbg_mode = g_uh_dbg; a.status = status;
   // output planes [2][B][4L][CO] seen as {CO, phase, q, B, plane}: one store = one phase of 128 input rows, COT channels
   CUtensorMap tmap_y;
   {
@@ -363,8 +366,10 @@ void voc_up_h_set_debug(int m) { g_uh_dbg = m; }
 
 using namespace m2;
 
+#ifdef M2TTS_TOOLS
 // bring-up only (tools/up_h_prof.py): timing experiments with parts of the kernel switched off; results are invalid while set
 extern "C" int m2tts_voc_up_h_set_debug(int mode) { voc_up_h_set_debug(mode); return M2TTS_OK; }
+#endif
 
 namespace {
 __global__ void uh_join_planes_kernel(const __half* planes, long long n, float* y) {
@@ -381,7 +386,7 @@ extern "C" size_t m2tts_conv_transpose_x4_h_workspace_bytes(int B, int CI, int L
 // y = leaky_relu(conv_transpose1d(x, w, b, stride 4, padding 2), 0.1) (components.py:225-241, one `ups` layer + its activation):
 // x fp32 CHANNEL-LAST [B][L][CI], w [CI][CI/2][8] (state_dict layout), y fp32 channel-last [B][4L][CI/2]; CI in {128, 256}.
 extern "C" int m2tts_conv_transpose_x4_h(const float* x, const float* w, const float* b, float* y, int B, int CI, int L,
-                                         void* workspace, size_t workspace_bytes, m2tts_stream_t stream) {
+                                         int32_t* status, void* workspace, size_t workspace_bytes, m2tts_stream_t stream) {
   M2_REQUIRE(x && w && b && y && workspace, M2TTS_E_NULLPTR, "conv_transpose_x4_h: null pointer");
   M2_REQUIRE(voc_up_h_eligible(CI, CI / 2, 4), M2TTS_E_UNSUPPORTED, "conv_transpose_x4_h: CI=%d (128 or 256)", CI);
   Carver cv(workspace, workspace_bytes);
@@ -391,9 +396,9 @@ extern "C" int m2tts_conv_transpose_x4_h(const float* x, const float* w, const f
   __half* yp = cv.take<__half>((size_t)2 * n_out);
   M2_REQUIRE(cv.ok(), M2TTS_E_WORKSPACE, "conv_transpose_x4_h: workspace too small or misaligned");
   cudaStream_t s = (cudaStream_t)stream;
-  int rc = launch_split_planes_h(x, xp, n_in, s);
+  int rc = launch_split_planes_h(x, xp, n_in, status, s);
   if (rc) return rc;
-  if ((rc = launch_voc_up_h(xp, n_in, w, b, wblob, yp, n_out, B, CI, L, M2TTS_STAGE_VOC_UP, s))) return rc;
+  if ((rc = launch_voc_up_h(xp, n_in, w, b, wblob, yp, n_out, B, CI, L, M2TTS_STAGE_VOC_UP, status, s))) return rc;
   M2_LAUNCH(M2TTS_STAGE_PACK, uh_join_planes_kernel, 1184, 256, 0, s, yp, n_out, y);
   return M2TTS_OK;
 }

@@ -379,8 +379,10 @@ __global__ void __launch_bounds__(256) mel_to_channel_first_kernel(const float* 
 // 16-bit split input convolution); a 32 x 32 tile goes through shared memory so that both sides are coalesced whichever
 // of m / t is contiguous in x.
 __global__ void __launch_bounds__(256) mel_to_planes_kernel(const float* __restrict__ x, long long sb, long long sm, long long st,
-                                                             __half* __restrict__ planes, long long plane, int M, int T) {
+                                                             __half* __restrict__ planes, long long plane, int M, int T,
+                                                             int32_t* __restrict__ status) {
   __shared__ float tile[32][33];      // [t][m]
+  bool bad = false;
   const int b = blockIdx.z, t0 = blockIdx.x * 32, m0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
   const float* xb = x + (long long)b * sb;
@@ -399,13 +401,15 @@ __global__ void __launch_bounds__(256) mel_to_planes_kernel(const float* __restr
   for (int r = ty; r < 32; r += 8) {
     const int t = t0 + r, m = m0 + tx;
     if (m < M && t < T) {
-      const float v = fminf(fmaxf(tile[r][tx], -65000.f), 65000.f);
+      const float v = tile[r][tx];
+      h_chk(v, bad);
       const __half h = __float2half_rn(v);
       const long long o = ((long long)b * T + t) * M + m;
       planes[o] = h;
       planes[plane + o] = __float2half_rn(v - __half2float(h));
     }
   }
+  h_flag(bad, status);
 }
 
 // w[CO][CI][3] -> wp[CI][3][CO], several convolutions per launch (blockIdx.y = job)
@@ -522,204 +526,243 @@ extern "C" int m2tts_conv_transpose1d_lrelu(const float* x, const float* w, cons
   return launch_convT(a, B, r, (cudaStream_t)stream);
 }
 
-extern "C" size_t m2tts_vocoder_workspace_bytes(int B, int T, int M, int C) {
-  if (B <= 0 || T <= 0 || M <= 0 || C < 16) return 0;
-  // widest activation: 4*C*T floats per utterance (+ row-pitch padding of the first tensor)
-  const size_t act = align_up((size_t)B * C * ((size_t)T + 4) * 4 * sizeof(float), 256);
+// ---- the vocoder as a chain of per-stage kernels ------------------------------------------------------------------------
+namespace {
+
+static const int kRates[4] = {4, 4, 2, 2};      // tts_model.py:244
+
+// Per-stage kernel choice, a function of (M, C, precision, dilations) only, so that m2tts_vocoder_pack and
+// m2tts_vocoder_forward agree on which weight images exist.
+//   IN_H / S_UPH_* / S_FUSED_H : channel-last 16-bit split kernels (fp16 hi/lo planes between stages)
+//   *_TC / S_FUSED_TF32        : TF32-split tcgen05 kernels (tap-GEMMs on channel-first fp32; fused narrow stages channel-last)
+//   *_FFMA                     : fp32 FFMA kernels (any shape, any input strides)
+enum { IN_FFMA = 0, IN_TC = 1, IN_H = 2 };
+enum { S_FFMA = 0, S_TC = 1, S_FUSED_TF32 = 2, S_FUSED_H = 3, S_UPH_RESH = 4, S_UPH_CONVH = 5, S_TC_RESH = 6, S_TC_CONVH = 7 };
+
+struct VocPlan {
+  int in_kind;
+  int kind[4];
+  bool out_planes[4];      // stage j hands fp16 hi/lo planes (channel-last) to stage j + 1
+  bool in_planes;          // the input conv hands planes to stage 0
+};
+
+bool stage_reads_planes(int k) { return k == S_FUSED_H || k == S_UPH_RESH || k == S_UPH_CONVH; }
+bool stage_is_tc_family(int k) { return k == S_TC || k == S_UPH_RESH || k == S_UPH_CONVH || k == S_TC_RESH || k == S_TC_CONVH; }
+
+VocPlan make_plan(int M, int C, int prec, const int* res_dilation) {
+  VocPlan p{};
+  p.in_kind = IN_FFMA;
+  for (int j = 0; j < 4; ++j) { p.kind[j] = S_FFMA; p.out_planes[j] = false; }
+  if (prec == M2TTS_PREC_FFMA) return p;
+  const bool h = prec == M2TTS_PREC_SPLIT16;
+  // pass 1: the TF32-era skeleton — wide stages as a prefix of tap-GEMM stages, narrow stages fused
+  int base[4];      // 0 ffma, 1 tc, 2 fused
+  int ci = C;
+  for (int j = 0; j < 4; ++j, ci /= 2) {
+    const int c = ci / 2;
+    const int dil = res_dilation[j] > 0 ? res_dilation[j] : 1;
+    const bool tc_ok = (j == 0 || base[j - 1] == 1) && convT_tc_eligible(ci, c, kRates[j]) && conv3_tc_eligible(c, c) && dil <= 4;
+    const bool fused_ok = j >= 1 && base[j - 1] != 0 && voc_fused_eligible(c, kRates[j], dil);
+    base[j] = fused_ok ? 2 : (tc_ok ? 1 : 0);
+  }
+  // pass 2: 16-bit split refinements of the tap-GEMM stages
+  ci = C;
+  for (int j = 0; j < 4; ++j, ci /= 2) {
+    const int c = ci / 2;
+    const int dil = res_dilation[j] > 0 ? res_dilation[j] : 1;
+    if (base[j] == 0) { p.kind[j] = S_FFMA; continue; }
+    if (base[j] == 2) { p.kind[j] = h ? S_FUSED_H : S_FUSED_TF32; continue; }
+    p.kind[j] = S_TC;
+    if (!h) continue;
+    const bool next_fused = j + 1 < 4 && base[j + 1] == 2;
+    const bool resh = voc_res_h_eligible(c, dil) && next_fused;      // C = 64: whole ResBlock in one kernel, output as planes
+    const bool convh = voc_conv_h_eligible(c, dil);                  // C = 128: two channel-last conv launches
+    if (!resh && !convh) continue;
+    const bool producer_tc = j == 0 ? conv3_tc_eligible(M, C) : stage_is_tc_family(p.kind[j - 1]);
+    const bool uph = voc_up_h_eligible(ci, c, kRates[j]) && producer_tc;
+    p.kind[j] = resh ? (uph ? S_UPH_RESH : S_TC_RESH) : (uph ? S_UPH_CONVH : S_TC_CONVH);
+  }
+  for (int j = 0; j < 4; ++j)
+    p.out_planes[j] = h && j + 1 < 4 && stage_reads_planes(p.kind[j + 1]) &&
+                      (p.kind[j] == S_FUSED_H || p.kind[j] == S_UPH_RESH || p.kind[j] == S_TC_RESH || p.kind[j] == S_UPH_CONVH || p.kind[j] == S_TC_CONVH);
+  p.in_planes = h && stage_reads_planes(p.kind[0]);
+  if (p.kind[0] != S_FFMA && conv3_tc_eligible(M, C)) p.in_kind = IN_TC;
+  if (p.in_planes && voc_conv_h_io_eligible(M, C) && (size_t)C / 64 * 98304 <= conv3_tc_wblob_floats(M, C) * sizeof(float)) p.in_kind = IN_H;
+  if (p.in_planes && p.in_kind == IN_FFMA) {      // no producer of planes for stage 0: fall back to the tap-GEMM upsampler there
+    p.in_planes = false;
+    if (p.kind[0] == S_UPH_RESH) p.kind[0] = S_TC_RESH;
+    if (p.kind[0] == S_UPH_CONVH) p.kind[0] = S_TC_CONVH;
+  }
+  return p;
+}
+
+// weight images of one vocoder, carved from the caller's `packed` buffer or from the workspace
+struct VocBlobs {
+  float* in_ffma; float* in_img;
+  float* r1_ffma[4]; float* r2_ffma[4];
+  float* r1_img[4]; float* r2_img[4]; float* up_img[4]; float* fs_img[4];
+};
+
+bool carve_blobs(Carver& cv, int M, int C, VocBlobs* o) {
+  o->in_ffma = cv.take<float>((size_t)C * M * 3);
+  o->in_img = cv.take<float>(conv3_tc_wblob_floats(M, C));
+  for (int j = 0, c = C / 2; j < 4; ++j, c /= 2) {
+    o->r1_ffma[j] = cv.take<float>((size_t)c * c * 3);
+    o->r2_ffma[j] = cv.take<float>((size_t)c * c * 3);
+    o->r1_img[j] = cv.take<float>(conv3_tc_wblob_floats(c, c));
+    o->r2_img[j] = cv.take<float>(conv3_tc_wblob_floats(c, c));
+    o->up_img[j] = cv.take<float>(convT_tc_wblob_floats(2 * c, c, kRates[j]));
+    o->fs_img[j] = cv.take<float>(voc_fused_wblob_floats(c == 16 || c == 32 ? c : 0));
+  }
+  return cv.ok();
+}
+
+size_t blobs_bytes(int M, int C) {
   size_t wts = (size_t)C * M * 3 + conv3_tc_wblob_floats(M, C);
-  static const int rates[4] = {4, 4, 2, 2};
   for (int j = 0, c = C / 2; j < 4; ++j, c /= 2)
-    wts += 2 * (size_t)c * c * 3 + 2 * conv3_tc_wblob_floats(c, c) + convT_tc_wblob_floats(2 * c, c, rates[j]) +
+    wts += 2 * (size_t)c * c * 3 + 2 * conv3_tc_wblob_floats(c, c) + convT_tc_wblob_floats(2 * c, c, kRates[j]) +
            voc_fused_wblob_floats(c == 16 || c == 32 ? c : 0);
-  return 3 * act + align_up(wts * sizeof(float), 256) + 40 * 256;
+  return align_up(wts * sizeof(float), 256) + 40 * 256;
 }
 
-static bool conv_h_enabled() {      // M2TTS_CONV_H=0 keeps the TF32 tap-GEMM for the C = 128 ResBlock (A/B measurements)
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("M2TTS_CONV_H"); v = (e && e[0] == '0') ? 0 : 1; }
-  return v == 1;
-}
-
-extern "C" int m2tts_vocoder_forward(const m2tts_vocoder_weights* w, const float* mel, int64_t stride_b,
-                                     int64_t stride_m, int64_t stride_t, float* audio, int B, int T, int M,
-                                     int C, void* workspace, size_t workspace_bytes, m2tts_stream_t stream) {
-  M2_REQUIRE(w && mel && audio && workspace, M2TTS_E_NULLPTR, "vocoder_forward: null pointer");
-  M2_REQUIRE(B > 0 && T > 0 && M > 0, M2TTS_E_BADSHAPE, "vocoder_forward: B=%d T=%d M=%d", B, T, M);
-  M2_REQUIRE(C >= 16 && C % 16 == 0, M2TTS_E_UNSUPPORTED,
-             "vocoder_forward: hidden_channels=%d must be a positive multiple of 16", C);
-  M2_REQUIRE(w->in_w && w->in_b && w->out_w && w->out_b, M2TTS_E_NULLPTR, "vocoder_forward: null weights");
+int check_weights(const m2tts_vocoder_weights* w, const char* who) {
+  M2_REQUIRE(w != nullptr, M2TTS_E_NULLPTR, "%s: null weights", who);
+  M2_REQUIRE(w->in_w && w->in_b && w->out_w && w->out_b, M2TTS_E_NULLPTR, "%s: null weights", who);
   for (int j = 0; j < 4; ++j)
     M2_REQUIRE(w->up_w[j] && w->up_b[j] && w->res1_w[j] && w->res1_b[j] && w->res2_w[j] && w->res2_b[j],
-               M2TTS_E_NULLPTR, "vocoder_forward: null weights in stage %d", j);
-  cudaStream_t s = (cudaStream_t)stream;
-  static const int rates[4] = {4, 4, 2, 2};
-  Carver cv(workspace, workspace_bytes);
-  const size_t act = (size_t)B * C * ((size_t)T + 4) * 4;   // floats
-  float* bufA = cv.take<float>(act);
-  float* bufB = cv.take<float>(act);
-  float* bufC = cv.take<float>(act);
-  // packed weights (FFMA layout [CI][3][CO]) and tensor-core weight images
-  ConvPackJob jobs[9];
-  float* in_wp = cv.take<float>((size_t)C * M * 3);
-  float* in_wb = cv.take<float>(conv3_tc_wblob_floats(M, C));
-  jobs[0] = ConvPackJob{w->in_w, in_wp, C, M};
-  float *r1p[4], *r2p[4], *r1b[4], *r2b[4], *upb[4], *fsb[4];
-  for (int j = 0, c = C / 2; j < 4; ++j, c /= 2) {
-    r1p[j] = cv.take<float>((size_t)c * c * 3);
-    r2p[j] = cv.take<float>((size_t)c * c * 3);
-    r1b[j] = cv.take<float>(conv3_tc_wblob_floats(c, c));
-    r2b[j] = cv.take<float>(conv3_tc_wblob_floats(c, c));
-    upb[j] = cv.take<float>(convT_tc_wblob_floats(2 * c, c, rates[j]));
-    fsb[j] = cv.take<float>(voc_fused_wblob_floats(c == 16 || c == 32 ? c : 0));
-    jobs[1 + 2 * j] = ConvPackJob{w->res1_w[j], r1p[j], c, c};
-    jobs[2 + 2 * j] = ConvPackJob{w->res2_w[j], r2p[j], c, c};
-  }
-  M2_REQUIRE(cv.ok(), M2TTS_E_WORKSPACE, "vocoder_forward: workspace too small (%zu B) or not 256-B aligned",
-             workspace_bytes);
-  int rc = launch_conv_pack(jobs, 9, s);
-  if (rc) return rc;
+               M2TTS_E_NULLPTR, "%s: null weights in stage %d", who, j);
+  return M2TTS_OK;
+}
 
-  // Per-stage kernel choice.
-  //   TC    : the three convolutions as persistent tcgen05 tap-GEMMs on channel-first tensors (wide stages; they
-  //           form a prefix of the stage list because they need a channel-first input with a 16-B row pitch);
-  //   FUSED : the whole stage (upsample x2 + ResBlock, and for the last stage the output conv + tanh) as ONE
-  //           tcgen05 kernel on channel-last tensors (C in {16,32}); its producer must be a TC or FUSED stage,
-  //           which then writes its output channel-last;
-  //   FFMA  : fp32 FFMA kernels (any shape, any input strides).
-  enum { P_FFMA = 0, P_TC = 1, P_FUSED = 2 };
-  int path[4] = {P_FFMA, P_FFMA, P_FFMA, P_FFMA};
-  const bool fused_h = vocoder_mode() == 0;      // fused narrow stages: 16-bit split (default) or TF32 split (mode 2)
-  if (vocoder_mode() != 1) {
-    int ci = C;
-    for (int j = 0; j < 4; ++j, ci /= 2) {
-      const int c = ci / 2;
-      const int dil = w->res_dilation[j] > 0 ? w->res_dilation[j] : 1;
-      const bool tc_ok = (j == 0 || path[j - 1] == P_TC) && convT_tc_eligible(ci, c, rates[j]) && conv3_tc_eligible(c, c) && dil <= 4;
-      const bool fused_ok = j >= 1 && path[j - 1] != P_FFMA && voc_fused_eligible(c, rates[j], dil);
-      path[j] = fused_ok ? P_FUSED : (tc_ok ? P_TC : P_FFMA);
-    }
+// run == false: only the weight images are written (m2tts_vocoder_pack); pack == false: the images are already in `bl`.
+int vocoder_chain(const m2tts_vocoder_weights* w, const VocPlan& plan, const VocBlobs& bl, bool pack, bool run, const float* mel,
+                  int64_t stride_b, int64_t stride_m, int64_t stride_t, float* audio, int B, int T, int M, int C, float* bufA, float* bufB,
+                  float* bufC, int32_t* status, cudaStream_t s) {
+  int rc;
+  auto W = [&](const float* p) { return pack ? p : (const float*)nullptr; };      // weight pointer handed to a launcher (null: image is ready)
+  // FFMA weight layout [CI][3][CO], only for the stages that run FFMA kernels
+  if (pack) {
+    ConvPackJob jobs[9];
+    int n = 0;
+    if (plan.in_kind == IN_FFMA) jobs[n++] = ConvPackJob{w->in_w, bl.in_ffma, C, M};
+    for (int j = 0, c = C / 2; j < 4; ++j, c /= 2)
+      if (plan.kind[j] == S_FFMA) {
+        jobs[n++] = ConvPackJob{w->res1_w[j], bl.r1_ffma[j], c, c};
+        jobs[n++] = ConvPackJob{w->res2_w[j], bl.r2_ffma[j], c, c};
+      }
+    if (n > 0 && (rc = launch_conv_pack(jobs, n, s))) return rc;
   }
-
-  // wide stages whose transposed convolution runs on channel-last fp16 hi/lo planes (voc_up_h.cu): the producer (input conv or
-  // the previous stage) writes planes and the stage's ResBlock kernels consume planes
-  bool up_h[4] = {false, false, false, false};
-  if (fused_h && conv_h_enabled()) {
-    int ci = C;
-    for (int j = 0; j < 4; ++j, ci /= 2) {
-      const int c = ci / 2;
-      const int dil = w->res_dilation[j] > 0 ? w->res_dilation[j] : 1;
-      const bool res_planes = voc_conv_h_eligible(c, dil) || (voc_res_h_eligible(c, dil) && j + 1 < 4 && path[j + 1] == P_FUSED);
-      const bool producer_ok = j == 0 ? (conv3_tc_eligible(M, C) && B <= 65535) : path[j - 1] == P_TC;
-      up_h[j] = path[j] == P_TC && voc_up_h_eligible(ci, c, rates[j]) && res_planes && producer_ok;
-    }
-  }
-
-  // input conv: mel (strided) -> bufA [B,C,Lp] (row pitch padded to a multiple of 4 floats for the TMA tensor maps)
+  const float* nx = nullptr;      // "no input": pack-only call of a launcher
+  // ---- input conv: mel (strided) -> bufA ----
   int L = T, c_in = C;
-  int Lp = path[0] == P_TC ? ((L + 3) & ~3) : L;
-  bool cl = false;                       // layout of the current activation (bufA): channel-last?
-  if (up_h[0] && voc_conv_h_io_eligible(M, C) && B <= 65535 && conv_h_enabled() &&
-      (size_t)C / 64 * 98304 <= conv3_tc_wblob_floats(M, C) * sizeof(float)) {
+  int Lp = (plan.kind[0] != S_FFMA) ? ((L + 3) & ~3) : L;      // row pitch of channel-first tensors feeding TMA: multiple of 4 floats
+  bool cl = false;                                            // layout of the current activation (bufA): channel-last?
+  if (plan.in_kind == IN_H) {
     // channel-last 16-bit split input conv: mel -> fp16 hi/lo planes [2][B][T][M] (bufC), then the conv kernel of the wide
     // ResBlocks with CI = M zero-padded to 128 (the padding costs nothing: TMA zero-fills, the k-steps beyond M are skipped)
     __half* mp = reinterpret_cast<__half*>(bufC);
     const long long mplane = (long long)B * T * M;
-    if (stride_m == 1 && stride_t == M && stride_b == (int64_t)T * M && (((uintptr_t)mel) & 15) == 0 && (mplane & 7) == 0) {
-      // the decoder's own [B,T,M] output (tts_model.py:390 passes its transpose view): already channel-last, a flat split
-      if ((rc = launch_split_planes_h(mel, mp, mplane, s))) return rc;
-    } else {
-      dim3 grid(ceil_div(T, 32), ceil_div(M, 32), B);
-      M2_LAUNCH(M2TTS_STAGE_VOC_IN, mel_to_planes_kernel, grid, 256, 0, s, mel, (long long)stride_b, (long long)stride_m, (long long)stride_t,
-                mp, mplane, M, T);
+    if (run) {
+      if (stride_m == 1 && stride_t == M && stride_b == (int64_t)T * M && (((uintptr_t)mel) & 15) == 0 && (mplane & 7) == 0) {
+        // the decoder's own [B,T,M] output (tts_model.py:390 passes its transpose view): already channel-last, a flat split
+        if ((rc = launch_split_planes_h(mel, mp, mplane, status, s))) return rc;
+      } else {
+        dim3 grid(ceil_div(T, 32), ceil_div(M, 32), B);
+        M2_LAUNCH(M2TTS_STAGE_VOC_IN, mel_to_planes_kernel, grid, 256, 0, s, mel, (long long)stride_b, (long long)stride_m, (long long)stride_t,
+                  mp, mplane, M, T, status);
+      }
     }
-    if ((rc = launch_voc_conv_h(mp, mplane, w->in_w, w->in_b, in_wb, nullptr, 0, bufA, (long long)B * T * C, nullptr, 0, B, M, C, T, 0,
-                                M2TTS_STAGE_VOC_IN, s))) return rc;
-  } else if (path[0] == P_TC && conv3_tc_eligible(M, C) && B <= 65535) {
+    if ((rc = launch_voc_conv_h(run ? mp : nullptr, mplane, W(w->in_w), w->in_b, bl.in_img, nullptr, 0, bufA, (long long)B * T * C, nullptr, 0, B, M, C,
+                                T, 0, M2TTS_STAGE_VOC_IN, status, s))) return rc;
+  } else if (plan.in_kind == IN_TC) {
     // tensor-core input conv: channel-first copy of the mel with a 16-byte row pitch (bufC), then the tap-GEMM
     const float* xin = mel;
-    if (!(stride_t == 1 && stride_m == Lp && stride_b == (int64_t)M * Lp && (((uintptr_t)mel) & 15) == 0)) {
+    if (run && !(stride_t == 1 && stride_m == Lp && stride_b == (int64_t)M * Lp && (((uintptr_t)mel) & 15) == 0)) {
       dim3 grid(ceil_div(Lp, 32), ceil_div(M, 32), B);
       M2_LAUNCH(M2TTS_STAGE_VOC_IN, mel_to_channel_first_kernel, grid, 256, 0, s, mel, (long long)stride_b, (long long)stride_m,
                 (long long)stride_t, bufC, M, T, Lp);
       xin = bufC;
     }
-    if ((rc = launch_conv3_tc(xin, Lp, w->in_w, in_wb, w->in_b, nullptr, 0, bufA, Lp, B, M, C, T, 1, 0, M2TTS_STAGE_VOC_IN, s, up_h[0] ? 2 : 0))) return rc;
-  } else {
-    ConvArgs a{mel, stride_b, stride_m, stride_t, in_wp, w->in_b, nullptr, bufA, M, C, T, 1, 0};
+    if ((rc = launch_conv3_tc(run ? xin : nx, Lp, W(w->in_w), bl.in_img, w->in_b, nullptr, 0, bufA, Lp, B, M, C, T, 1, 0, M2TTS_STAGE_VOC_IN, s,
+                              plan.in_planes ? 2 : 0, status))) return rc;
+  } else if (run) {
+    ConvArgs a{mel, stride_b, stride_m, stride_t, bl.in_ffma, w->in_b, nullptr, bufA, M, C, T, 1, 0};
     a.y_pitch = Lp;
     if ((rc = launch_conv3(a, B, M2TTS_STAGE_VOC_IN, s))) return rc;
   }
   bool audio_done = false;
   for (int j = 0; j < 4; ++j) {
-    const int r = rates[j], c = c_in / 2, Lo = L * r;
+    const int r = kRates[j], c = c_in / 2, Lo = L * r;
     const int dil = w->res_dilation[j] > 0 ? w->res_dilation[j] : 1;
-    const bool next_cl = j + 1 < 4 && (path[j + 1] == P_FUSED || up_h[j + 1]);      // the next stage reads channel-last (planes)
-    if (path[j] == P_FUSED && fused_h) {
-      // 16-bit split: bufA = fp16 hi/lo planes, channel-last [2][B][L][c_in] -> bufB planes [2][B][Lo][c] when the next
-      // stage is fused too, plain fp32 channel-last otherwise, or straight to the waveform
-      const bool last = j == 3;
-      const bool planes_out = !last && next_cl;
-      if ((rc = launch_voc_stage_fused_h(bufA, (long long)B * L * c_in, w->up_w[j], w->up_b[j], w->res1_w[j], w->res1_b[j], w->res2_w[j],
-                                         w->res2_b[j], last ? w->out_w : nullptr, last ? w->out_b : nullptr, fsb[j],
-                                         planes_out ? (void*)bufB : nullptr, (long long)B * Lo * c,
-                                         last ? audio : (planes_out ? nullptr : bufB), B, c, L, M2TTS_STAGE_VOC_FUSED, s))) return rc;
+    const int kind = plan.kind[j];
+    const bool last = j == 3;
+    const bool next_cl = !last && (plan.kind[j + 1] == S_FUSED_H || plan.kind[j + 1] == S_FUSED_TF32 || stage_reads_planes(plan.kind[j + 1]));
+    const long long in_plane = (long long)B * L * c_in, out_plane = (long long)B * Lo * c;
+    if (kind == S_FUSED_H) {
+      // bufA = fp16 hi/lo planes, channel-last [2][B][L][c_in] -> bufB planes [2][B][Lo][c] when the next stage reads planes,
+      // plain fp32 channel-last otherwise, or straight to the waveform
+      const bool planes_out = plan.out_planes[j];
+      if ((rc = launch_voc_stage_fused_h(run ? (const void*)bufA : nullptr, in_plane, W(w->up_w[j]), w->up_b[j], W(w->res1_w[j]), w->res1_b[j],
+                                         W(w->res2_w[j]), w->res2_b[j], last ? w->out_w : nullptr, last ? w->out_b : nullptr, bl.fs_img[j],
+                                         planes_out ? (void*)bufB : nullptr, out_plane, last ? audio : (planes_out ? nullptr : bufB), B, c, L,
+                                         M2TTS_STAGE_VOC_FUSED, status, s))) return rc;
       if (last) audio_done = true;
       else { float* t = bufA; bufA = bufB; bufB = t; }
       cl = true;
-    } else if (path[j] == P_FUSED) {
+    } else if (kind == S_FUSED_TF32) {
       // bufA channel-last [B][L][c_in] -> bufB channel-last [B][Lo][c] (or straight to the waveform)
-      const bool last = j == 3;
-      if ((rc = launch_voc_stage_fused(bufA, w->up_w[j], w->up_b[j], w->res1_w[j], w->res1_b[j], w->res2_w[j], w->res2_b[j],
-                                       last ? w->out_w : nullptr, last ? w->out_b : nullptr, fsb[j], last ? audio : bufB, B, c, L,
+      if ((rc = launch_voc_stage_fused(run ? bufA : nx, W(w->up_w[j]), w->up_b[j], W(w->res1_w[j]), w->res1_b[j], W(w->res2_w[j]), w->res2_b[j],
+                                       last ? w->out_w : nullptr, last ? w->out_b : nullptr, bl.fs_img[j], last ? audio : bufB, B, c, L,
                                        M2TTS_STAGE_VOC_FUSED, s))) return rc;
       if (last) audio_done = true;
       else { float* t = bufA; bufA = bufB; bufB = t; }
       cl = true;
-    } else if (path[j] == P_TC && fused_h && next_cl && voc_res_h_eligible(c, dil)) {
-      // C = 64: the upsampling tap-GEMM writes fp16 hi/lo planes channel-last (bufB) and the whole ResBlock is ONE
-      // 16-bit split kernel (bufB -> bufA planes): v = lrelu(conv1(u)) and the residual never travel through HBM
-      if (up_h[j]) rc = launch_voc_up_h(bufA, (long long)B * L * c_in, w->up_w[j], w->up_b[j], upb[j], bufB, (long long)B * Lo * c, B, c_in, L,
-                                        M2TTS_STAGE_VOC_UP, s);
-      else rc = launch_convT_tc(bufA, Lp, w->up_w[j], upb[j], w->up_b[j], bufB, Lo, B, c_in, c, L, r, s, 2);
+    } else if (kind == S_UPH_RESH || kind == S_TC_RESH) {
+      // C = 64: the upsampler writes fp16 hi/lo planes channel-last (bufB) and the whole ResBlock is ONE 16-bit split kernel
+      // (bufB -> bufA planes): v = lrelu(conv1(u)) and the residual never travel through HBM
+      if (kind == S_UPH_RESH) rc = launch_voc_up_h(run ? (const void*)bufA : nullptr, in_plane, W(w->up_w[j]), w->up_b[j], bl.up_img[j], bufB, out_plane, B,
+                                                   c_in, L, M2TTS_STAGE_VOC_UP, status, s);
+      else rc = launch_convT_tc(run ? bufA : nx, Lp, W(w->up_w[j]), bl.up_img[j], w->up_b[j], bufB, Lo, B, c_in, c, L, r, s, 2, status);
       if (rc) return rc;
-      if ((rc = launch_voc_res_h(bufB, (long long)B * Lo * c, w->res1_w[j], w->res1_b[j], w->res2_w[j], w->res2_b[j], r1b[j],
-                                 bufA, (long long)B * Lo * c, nullptr, B, c, Lo, M2TTS_STAGE_VOC_RES1, s))) return rc;
+      if ((rc = launch_voc_res_h(run ? (const void*)bufB : nullptr, out_plane, W(w->res1_w[j]), w->res1_b[j], W(w->res2_w[j]), w->res2_b[j], bl.r1_img[j],
+                                 bufA, out_plane, nullptr, B, c, Lo, M2TTS_STAGE_VOC_RES1, status, s))) return rc;
       Lp = Lo;
       cl = true;
-    } else if (path[j] == P_TC && fused_h && voc_conv_h_eligible(c, dil) && conv_h_enabled()) {
-      // C = 128: the upsampling tap-GEMM writes fp16 hi/lo planes channel-last (bufB); the two convolutions of the ResBlock run
-      // on those planes (no splitter, one accumulator for the three taps); conv2 writes what the next stage reads
-      const long long plane = (long long)B * Lo * c;
-      if (up_h[j]) rc = launch_voc_up_h(bufA, (long long)B * L * c_in, w->up_w[j], w->up_b[j], upb[j], bufB, plane, B, c_in, L,
-                                        M2TTS_STAGE_VOC_UP, s);
-      else rc = launch_convT_tc(bufA, Lp, w->up_w[j], upb[j], w->up_b[j], bufB, Lo, B, c_in, c, L, r, s, 2);
+    } else if (kind == S_UPH_CONVH || kind == S_TC_CONVH) {
+      // C = 128: the upsampler writes fp16 hi/lo planes channel-last (bufB); the two convolutions of the ResBlock run on those
+      // planes (no splitter, one accumulator for the three taps); conv2 writes what the next stage reads
+      if (kind == S_UPH_CONVH) rc = launch_voc_up_h(run ? (const void*)bufA : nullptr, in_plane, W(w->up_w[j]), w->up_b[j], bl.up_img[j], bufB, out_plane, B,
+                                                    c_in, L, M2TTS_STAGE_VOC_UP, status, s);
+      else rc = launch_convT_tc(run ? bufA : nx, Lp, W(w->up_w[j]), bl.up_img[j], w->up_b[j], bufB, Lo, B, c_in, c, L, r, s, 2, status);
       if (rc) return rc;
-      if ((rc = launch_voc_conv_h(bufB, plane, w->res1_w[j], w->res1_b[j], r1b[j], nullptr, 0, bufC, plane, nullptr, 0, B, c, c, Lo, 1,
-                                  M2TTS_STAGE_VOC_RES1, s))) return rc;
-      if ((rc = launch_voc_conv_h(bufC, plane, w->res2_w[j], w->res2_b[j], r2b[j], bufB, plane, next_cl ? (void*)bufA : nullptr, plane,
-                                  next_cl ? nullptr : bufA, Lo, B, c, c, Lo, 0, M2TTS_STAGE_VOC_RES2, s))) return rc;
+      const bool po = plan.out_planes[j];
+      if ((rc = launch_voc_conv_h(run ? (const void*)bufB : nullptr, out_plane, W(w->res1_w[j]), w->res1_b[j], bl.r1_img[j], nullptr, 0, bufC, out_plane,
+                                  nullptr, 0, B, c, c, Lo, 1, M2TTS_STAGE_VOC_RES1, status, s))) return rc;
+      if ((rc = launch_voc_conv_h(run ? (const void*)bufC : nullptr, out_plane, W(w->res2_w[j]), w->res2_b[j], bl.r2_img[j], bufB, out_plane,
+                                  po ? (void*)bufA : nullptr, out_plane, po ? nullptr : bufA, Lo, B, c, c, Lo, 0, M2TTS_STAGE_VOC_RES2, status, s))) return rc;
       Lp = Lo;
-      cl = next_cl;
-    } else if (path[j] == P_TC) {
+      cl = po;
+    } else if (kind == S_TC) {
       // bufA (pitch Lp) -> up -> bufB -> conv1 -> bufC -> conv2 (+ residual bufB) -> bufA; Lo = r*L is a multiple of 4
-      if ((rc = launch_convT_tc(bufA, Lp, w->up_w[j], upb[j], w->up_b[j], bufB, Lo, B, c_in, c, L, r, s))) return rc;
-      if ((rc = launch_conv3_tc(bufB, Lo, w->res1_w[j], r1b[j], w->res1_b[j], nullptr, 0, bufC, Lo, B, c, c, Lo, dil, 1,
+      if ((rc = launch_convT_tc(run ? bufA : nx, Lp, W(w->up_w[j]), bl.up_img[j], w->up_b[j], bufB, Lo, B, c_in, c, L, r, s))) return rc;
+      if ((rc = launch_conv3_tc(run ? bufB : nx, Lo, W(w->res1_w[j]), bl.r1_img[j], w->res1_b[j], nullptr, 0, bufC, Lo, B, c, c, Lo, dil, 1,
                                 M2TTS_STAGE_VOC_RES1, s))) return rc;
-      if ((rc = launch_conv3_tc(bufC, Lo, w->res2_w[j], r2b[j], w->res2_b[j], bufB, Lo, bufA, Lo, B, c, c, Lo, 1, 0,
-                                M2TTS_STAGE_VOC_RES2, s, next_cl ? (fused_h ? 2 : 1) : 0))) return rc;
+      const int ocl = next_cl ? (plan.kind[j + 1] == S_FUSED_H ? 2 : 1) : 0;
+      if ((rc = launch_conv3_tc(run ? bufC : nx, Lo, W(w->res2_w[j]), bl.r2_img[j], w->res2_b[j], bufB, Lo, bufA, Lo, B, c, c, Lo, 1, 0,
+                                M2TTS_STAGE_VOC_RES2, s, ocl, status))) return rc;
       Lp = Lo;
       cl = next_cl;
-    } else {
+    } else if (run) {
       {  // bufB = lrelu(convT(bufA)); bufA is channel-first, or channel-last after a fused stage
         ConvArgs a{bufA, (long long)c_in * L, cl ? 1 : L, cl ? c_in : 1, w->up_w[j], w->up_b[j], nullptr, bufB, c_in, c, L, 1, 1};
         if ((rc = launch_convT(a, B, r, s))) return rc;
       }
       {  // bufC = lrelu(conv1(bufB))
-        ConvArgs a{bufB, (long long)c * Lo, Lo, 1, r1p[j], w->res1_b[j], nullptr, bufC, c, c, Lo, dil, 1};
+        ConvArgs a{bufB, (long long)c * Lo, Lo, 1, bl.r1_ffma[j], w->res1_b[j], nullptr, bufC, c, c, Lo, dil, 1};
         if ((rc = launch_conv3(a, B, M2TTS_STAGE_VOC_RES1, s))) return rc;
       }
       {  // bufA = conv2(bufC) + bufB
-        ConvArgs a{bufC, (long long)c * Lo, Lo, 1, r2p[j], w->res2_b[j], bufB, bufA, c, c, Lo, 1, 0};
+        ConvArgs a{bufC, (long long)c * Lo, Lo, 1, bl.r2_ffma[j], w->res2_b[j], bufB, bufA, c, c, Lo, 1, 0};
         if ((rc = launch_conv3(a, B, M2TTS_STAGE_VOC_RES2, s))) return rc;
       }
       Lp = Lo;
@@ -728,11 +771,71 @@ extern "C" int m2tts_vocoder_forward(const m2tts_vocoder_weights* w, const float
     L = Lo; c_in = c;
   }
   // output conv + tanh: bufA [B,C/16,64T] -> audio [B,1,64T] (fused into the last stage when that stage is FUSED)
-  if (!audio_done) {
+  if (!audio_done && run) {
     const int threads = 256;
     dim3 grid(ceil_div(ceil_div(L, 4), threads), B);
     M2_LAUNCH(M2TTS_STAGE_VOC_OUT, conv3_co1_tanh_kernel, grid, threads, (size_t)c_in * 3 * sizeof(float), s, bufA,
               w->out_w, w->out_b, audio, c_in, L);
   }
   return M2TTS_OK;
+}
+
+}  // namespace
+
+extern "C" size_t m2tts_vocoder_pack_bytes(int M, int C, int precision) {
+  (void)precision;      // one layout covers every precision (the images of the kernels a precision does not use stay unwritten)
+  if (M <= 0 || C < 16 || C % 16 != 0) return 0;
+  return blobs_bytes(M, C);
+}
+
+extern "C" size_t m2tts_vocoder_workspace_bytes(int B, int T, int M, int C) {
+  if (B <= 0 || T <= 0 || M <= 0 || C < 16) return 0;
+  // widest activation: 4*C*T floats per utterance (+ row-pitch padding of the first tensor); three ping-pong buffers,
+  // plus room for the weight images when the caller passes no packed buffer
+  const size_t act = align_up((size_t)B * C * ((size_t)T + 4) * 4 * sizeof(float), 256);
+  return 3 * act + blobs_bytes(M, C);
+}
+
+extern "C" int m2tts_vocoder_pack(const m2tts_vocoder_weights* w, int M, int C, int precision, void* packed, size_t packed_bytes,
+                                  int32_t* status, m2tts_stream_t stream) {
+  int rc = check_weights(w, "vocoder_pack");
+  if (rc) return rc;
+  M2_REQUIRE(packed != nullptr, M2TTS_E_NULLPTR, "vocoder_pack: null buffer");
+  M2_REQUIRE(M > 0 && C >= 16 && C % 16 == 0, M2TTS_E_UNSUPPORTED, "vocoder_pack: M=%d C=%d", M, C);
+  Carver cv(packed, packed_bytes);
+  VocBlobs bl;
+  M2_REQUIRE(carve_blobs(cv, M, C, &bl), M2TTS_E_WORKSPACE, "vocoder_pack: buffer too small (%zu B, need %zu) or not 256-B aligned",
+             packed_bytes, blobs_bytes(M, C));
+  const VocPlan plan = make_plan(M, C, resolve_precision(precision), w->res_dilation);
+  return vocoder_chain(w, plan, bl, true, false, nullptr, 0, 0, 0, nullptr, 1, 1, M, C, nullptr, nullptr, nullptr, status, (cudaStream_t)stream);
+}
+
+extern "C" int m2tts_vocoder_forward(const m2tts_vocoder_weights* w, const void* packed, const float* mel, int64_t stride_b,
+                                     int64_t stride_m, int64_t stride_t, float* audio, int B, int T, int M,
+                                     int C, int precision, int32_t* status, void* workspace, size_t workspace_bytes,
+                                     m2tts_stream_t stream) {
+  M2_REQUIRE(w && mel && audio && workspace, M2TTS_E_NULLPTR, "vocoder_forward: null pointer");
+  M2_REQUIRE(B > 0 && T > 0 && M > 0, M2TTS_E_BADSHAPE, "vocoder_forward: B=%d T=%d M=%d", B, T, M);
+  M2_REQUIRE(B <= 65535, M2TTS_E_UNSUPPORTED, "vocoder_forward: at most 65535 utterances per call (B=%d)", B);
+  M2_REQUIRE(C >= 16 && C % 16 == 0, M2TTS_E_UNSUPPORTED,
+             "vocoder_forward: hidden_channels=%d must be a positive multiple of 16", C);
+  int rc = check_weights(w, "vocoder_forward");
+  if (rc) return rc;
+  Carver cv(workspace, workspace_bytes);
+  const size_t act = (size_t)B * C * ((size_t)T + 4) * 4;   // floats
+  float* bufA = cv.take<float>(act);
+  float* bufB = cv.take<float>(act);
+  float* bufC = cv.take<float>(act);
+  VocBlobs bl;
+  if (packed != nullptr) {
+    M2_REQUIRE((((uintptr_t)packed) & 255) == 0, M2TTS_E_WORKSPACE, "vocoder_forward: packed weights must be 256-B aligned");
+    Carver pc(const_cast<void*>(packed), blobs_bytes(M, C));
+    carve_blobs(pc, M, C, &bl);
+  } else {
+    carve_blobs(cv, M, C, &bl);
+  }
+  M2_REQUIRE(cv.ok(), M2TTS_E_WORKSPACE, "vocoder_forward: workspace too small (%zu B) or not 256-B aligned", workspace_bytes);
+  const VocPlan plan = make_plan(M, C, resolve_precision(precision), w->res_dilation);
+  return vocoder_chain(w, plan, bl, packed == nullptr, true, mel, stride_b, stride_m, stride_t, audio, B, T, M, C, bufA, bufB, bufC, status,
+                       (cudaStream_t)stream);
 }

@@ -90,12 +90,18 @@ class TransformerEncoderLayer(nn.Module):
 
     def forward(self, x: torch.Tensor, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
         if not self.training:
+            from . import _native as nat
             from .tts_model import _native_layer_stack  # local import: avoids a cycle
             lengths = None
             if mask is not None:
                 # the kernel masks keys >= length; a prefix mask is the only kind the model builds
                 lengths = mask.to(torch.int64).sum(dim=1)
-            return _native_layer_stack([self], x, lengths)
+            nat.require_cuda(x, "x")
+            out = torch.empty_like(x, memory_format=torch.contiguous_format)
+            with nat.on_device(x.device):
+                nat.guarded(x.device, lambda prec: _native_layer_stack([self], x, lengths, out=out, prec=prec),
+                            "transformer_layer", owner=self)
+            return out
         if self.use_checkpointing:
             return checkpoint(self._forward, x, mask, use_reentrant=False)
         return self._forward(x, mask)
@@ -158,20 +164,6 @@ def create_padding_mask(lengths: torch.Tensor, max_length: int) -> torch.Tensor:
     """mask[b, s] = s < lengths[b] (reference components.py:226-241)."""
     steps = torch.arange(max_length, device=lengths.device)
     return steps.unsqueeze(0).expand(lengths.size(0), max_length) < lengths.unsqueeze(1)
-
-
-def apply_spectral_norm(module: nn.Module) -> nn.Module:
-    if isinstance(module, (nn.Conv1d, nn.Conv2d, nn.Linear)):
-        return nn.utils.spectral_norm(module)
-    return module
-
-
-class GradientClipping:
-    def __init__(self, clip_value: float = 5.0):
-        self.clip_value = clip_value
-
-    def __call__(self, model: nn.Module) -> float:
-        return torch.nn.utils.clip_grad_norm_(model.parameters(), self.clip_value)
 
 
 def count_parameters(model: nn.Module) -> Tuple[int, int]:

@@ -10,6 +10,10 @@ Execution model
     into ``libm2tts_b200.so`` (hand-written sm_100a CUDA, ``include/m2tts_b200.h``) on the
     caller's current CUDA stream. Outputs carry no autograd graph. There is NO CPU / MPS /
     PyTorch fallback: CPU tensors or a missing library raise ``NativeLibraryError``.
+    Each stage module validates its result against the device status word (``_native.guarded``):
+    operands outside the fp16 range of the default 16-bit split make the stage run again with the
+    TF32 split, an out-of-range phoneme id raises ``IndexError`` like ``nn.Embedding``. Weight
+    images are packed once per module and cached until a parameter changes.
   * ``module.training == True``: the reference's formulation in plain differentiable torch ops
     on the same parameters (dropout, activation checkpointing, no vocoder in ``forward``).
 """
@@ -46,10 +50,25 @@ def _layer_struct(layer: TransformerEncoderLayer) -> nat.LayerWeights:
         w(f.linear2.weight, "ffn.linear2.weight"), w(f.linear2.bias, "ffn.linear2.bias"))
 
 
+def _layer_packed(layer: TransformerEncoderLayer, st: nat.LayerWeights, H: int, F_dim: int, prec: int,
+                  dev: torch.device) -> torch.Tensor:
+    """Weight images of one layer (m2tts_transformer_pack), cached on the layer until a weight changes."""
+    a, f = layer.self_attn, layer.ffn
+    key = nat.params_key((a.qkv.weight, a.out_proj.weight, f.linear1.weight, f.linear2.weight)) + (H, F_dim, prec)
+    lib = nat.lib()
+
+    def pack(buf: torch.Tensor) -> None:
+        nat.check(lib.m2tts_transformer_pack(C.byref(st), H, F_dim, prec, buf.data_ptr(), buf.numel(),
+                                             nat.status_ptr(dev), nat.stream_handle(dev)), "transformer_pack")
+
+    return nat.packed_weights(layer, f"layer{prec}", key, lib.m2tts_transformer_pack_bytes(H, F_dim, prec), pack, dev)
+
+
 def _native_layer_stack(layers: Sequence[TransformerEncoderLayer], x: torch.Tensor,
-                        lengths: Optional[torch.Tensor], out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Run pre-LN transformer layers through ``m2tts_transformer_layer``. ``x`` is not modified
-    unless ``out is x``; the result is written to ``out`` (allocated when None)."""
+                        lengths: Optional[torch.Tensor], out: Optional[torch.Tensor] = None,
+                        prec: int = nat.PREC_DEFAULT) -> torch.Tensor:
+    """Run pre-LN transformer layers through ``m2tts_transformer_layer`` (status word: the caller's ``guarded``).
+    ``x`` is not modified unless ``out is x``; the result is written to ``out`` (allocated when None)."""
     nat.require_cuda(x, "x")
     x = x.contiguous()
     B, L, H = x.shape
@@ -65,8 +84,9 @@ def _native_layer_stack(layers: Sequence[TransformerEncoderLayer], x: torch.Tens
         nbytes = lib.m2tts_transformer_workspace_bytes(B, L, H, F_dim)
         ws = nat.workspace(dev, nbytes)
         st = _layer_struct(layer)
-        rc = lib.m2tts_transformer_layer(C.byref(st), src.data_ptr(), out.data_ptr(), nat.ptr(lengths),
-                                         B, L, H, layer.self_attn.num_heads, F_dim, LN_EPS,
+        packed = _layer_packed(layer, st, H, F_dim, prec, dev)
+        rc = lib.m2tts_transformer_layer(C.byref(st), packed.data_ptr(), src.data_ptr(), out.data_ptr(), nat.ptr(lengths),
+                                         B, L, H, layer.self_attn.num_heads, F_dim, LN_EPS, prec, nat.status_ptr(dev),
                                          ws.data_ptr(), ws.numel(), nat.stream_handle(dev))
         nat.check(rc, "transformer_layer")
         src = out
@@ -125,18 +145,23 @@ class TextEncoder(nn.Module):
             lens = nat.require_cuda(lengths.to(device=dev, dtype=torch.int64), "lengths", torch.int64).contiguous()
             mask = torch.empty((B, S), dtype=torch.bool, device=dev)
         lib = nat.lib()
-        x = torch.empty((B, S, H), dtype=torch.float32, device=dev)
-        rc = lib.m2tts_embed_posenc(ids.data_ptr(), nat.weight(self.embedding.weight, "embedding.weight"),
-                                    nat.weight(pe, "pos_encoding.pe"), nat.ptr(lens), x.data_ptr(),
-                                    nat.ptr(mask), B, S, H, self.embedding.num_embeddings,
-                                    nat.stream_handle(dev))
-        nat.check(rc, "embed_posenc")
-        _native_layer_stack(list(self.layers), x, lens, out=x)
-        y = torch.empty_like(x)
-        rc = lib.m2tts_layernorm(x.data_ptr(), nat.weight(self.norm.weight, "norm.weight"),
-                                 nat.weight(self.norm.bias, "norm.bias"), y.data_ptr(), B * S, H, LN_EPS,
-                                 nat.stream_handle(dev))
-        nat.check(rc, "layernorm")
+        y = torch.empty((B, S, H), dtype=torch.float32, device=dev)
+
+        def run(prec: int):
+            x = torch.empty((B, S, H), dtype=torch.float32, device=dev)
+            rc = lib.m2tts_embed_posenc(ids.data_ptr(), nat.weight(self.embedding.weight, "embedding.weight"),
+                                        nat.weight(pe, "pos_encoding.pe"), nat.ptr(lens), x.data_ptr(),
+                                        nat.ptr(mask), B, S, H, self.embedding.num_embeddings, nat.status_ptr(dev),
+                                        nat.stream_handle(dev))
+            nat.check(rc, "embed_posenc")
+            _native_layer_stack(list(self.layers), x, lens, out=x, prec=prec)
+            rc = lib.m2tts_layernorm(x.data_ptr(), nat.weight(self.norm.weight, "norm.weight"),
+                                     nat.weight(self.norm.bias, "norm.bias"), y.data_ptr(), B * S, H, LN_EPS,
+                                     nat.stream_handle(dev))
+            nat.check(rc, "layernorm")
+
+        with nat.on_device(dev):
+            nat.guarded(dev, run, "text_encoder", owner=self)
         return y, mask
 
 
@@ -173,8 +198,9 @@ class DurationPredictor(nn.Module):
         st.proj_b = w(self.predictor.projection.bias, "projection.bias")
         st.bn_eps = blocks[0].norm.eps
         dur = torch.empty((B, S), dtype=torch.float32, device=enc.device)
-        rc = nat.lib().m2tts_duration_predictor(C.byref(st), enc.data_ptr(), dur.data_ptr(), B, S, H,
-                                                nat.stream_handle(enc.device))
+        with nat.on_device(enc.device):
+            rc = nat.lib().m2tts_duration_predictor(C.byref(st), enc.data_ptr(), dur.data_ptr(), B, S, H,
+                                                    nat.stream_handle(enc.device))
         nat.check(rc, "duration_predictor")
         return dur
 
@@ -223,10 +249,20 @@ class LengthRegulator(nn.Module):
         cum = torch.empty((B, S), dtype=torch.int32, device=dev)
         frames = torch.empty((B,), dtype=torch.int32, device=dev)
         meta = torch.empty((2,), dtype=torch.int32, device=dev)    # [t_max, status]
+        with nat.on_device(dev):
+            return self._regulate(lib, enc, dur, cum, frames, meta, max_length, B, S, H, dev)
+
+    def _regulate(self, lib, enc, dur, cum, frames, meta, max_length, B, S, H, dev):
         rc = lib.m2tts_length_regulate_count(dur.data_ptr(), B, S, cum.data_ptr(), frames.data_ptr(),
                                              meta.data_ptr(), meta.data_ptr() + 4, nat.stream_handle(dev))
         nat.check(rc, "length_regulate_count")
-        t_max, status = meta.tolist()           # the path's only host read
+        if max_length is not None and nat.status_deferred():
+            # no host read inside a deferred region (throughput pipelines, CUDA-graph capture): the regulator's own status
+            # bits join the device status word and surface at check_status()
+            nat.status_word(dev).bitwise_or_(meta[1:2] << 2)
+            t_max, status = int(max_length), 0
+        else:
+            t_max, status = meta.tolist()           # the path's only host read
         if status & 1:
             raise ValueError("cannot convert float NaN to integer")
         if status & 2:
@@ -272,18 +308,31 @@ class MelDecoder(nn.Module):
         x = nat.require_cuda(x, "x").contiguous()
         B, T, H = x.shape
         dev = x.device
-        h = _native_layer_stack(list(self.layers), x, None)
         M = self.mel_projection.out_features
         lib = nat.lib()
         mel = torch.empty((B, T, M), dtype=torch.float32, device=dev)
-        ws = nat.workspace(dev, lib.m2tts_ln_proj_rows_workspace_bytes(B * T, H, M), tag="ln_proj")
-        rc = lib.m2tts_layernorm_proj(h.data_ptr(), nat.weight(self.norm.weight, "norm.weight"),
-                                      nat.weight(self.norm.bias, "norm.bias"),
-                                      nat.weight(self.mel_projection.weight, "mel_projection.weight"),
-                                      nat.weight(self.mel_projection.bias, "mel_projection.bias"),
-                                      mel.data_ptr(), B * T, H, M, LN_EPS, ws.data_ptr(), ws.numel(),
-                                      nat.stream_handle(dev))
-        nat.check(rc, "layernorm_proj")
+        proj = self.mel_projection
+
+        def run(prec: int):
+            h = _native_layer_stack(list(self.layers), x, None, prec=prec)
+            key = nat.params_key((proj.weight,)) + (H, M, prec)
+
+            def pack(buf: torch.Tensor) -> None:
+                nat.check(lib.m2tts_ln_proj_pack(nat.weight(proj.weight, "mel_projection.weight"), H, M, prec, buf.data_ptr(),
+                                                 buf.numel(), nat.status_ptr(dev), nat.stream_handle(dev)), "ln_proj_pack")
+
+            packed = nat.packed_weights(self, f"ln_proj{prec}", key, lib.m2tts_ln_proj_pack_bytes(H, M, prec), pack, dev)
+            ws = nat.workspace(dev, lib.m2tts_ln_proj_rows_workspace_bytes(B * T, H, M), tag="ln_proj")
+            rc = lib.m2tts_layernorm_proj(h.data_ptr(), nat.weight(self.norm.weight, "norm.weight"),
+                                          nat.weight(self.norm.bias, "norm.bias"),
+                                          nat.weight(proj.weight, "mel_projection.weight"),
+                                          nat.weight(proj.bias, "mel_projection.bias"), packed.data_ptr(),
+                                          mel.data_ptr(), B * T, H, M, LN_EPS, prec, nat.status_ptr(dev),
+                                          ws.data_ptr(), ws.numel(), nat.stream_handle(dev))
+            nat.check(rc, "layernorm_proj")
+
+        with nat.on_device(dev):
+            nat.guarded(dev, run, "mel_decoder", owner=self)
         return mel
 
 
@@ -340,11 +389,28 @@ class SimpleVocoder(nn.Module):
         for r in UPSAMPLE_RATES:
             total *= r
         audio = torch.empty((B, 1, total * T), dtype=torch.float32, device=dev)
-        ws = nat.workspace(dev, lib.m2tts_vocoder_workspace_bytes(B, T, M, Cch), tag="vocoder")
         sb, sm, stt = mel.stride()
-        rc = lib.m2tts_vocoder_forward(C.byref(st), mel.data_ptr(), sb, sm, stt, audio.data_ptr(), B, T, M, Cch,
-                                       ws.data_ptr(), ws.numel(), nat.stream_handle(dev))
-        nat.check(rc, "vocoder_forward")
+        params = [self.input_conv.weight, self.output_conv.weight]
+        for up, res in zip(self.upsamples, self.resblocks):
+            params += [up.weight, res.conv1.weight, res.conv2.weight]
+        dils = tuple(int(res.conv1.dilation[0]) for res in self.resblocks)
+
+        def run(prec: int):
+            key = nat.params_key(params) + (M, Cch, prec) + dils
+
+            def pack(buf: torch.Tensor) -> None:
+                nat.check(lib.m2tts_vocoder_pack(C.byref(st), M, Cch, prec, buf.data_ptr(), buf.numel(),
+                                                 nat.status_ptr(dev), nat.stream_handle(dev)), "vocoder_pack")
+
+            packed = nat.packed_weights(self, f"vocoder{prec}", key, lib.m2tts_vocoder_pack_bytes(M, Cch, prec), pack, dev)
+            ws = nat.workspace(dev, lib.m2tts_vocoder_workspace_bytes(B, T, M, Cch), tag="vocoder")
+            rc = lib.m2tts_vocoder_forward(C.byref(st), packed.data_ptr(), mel.data_ptr(), sb, sm, stt, audio.data_ptr(),
+                                           B, T, M, Cch, prec, nat.status_ptr(dev), ws.data_ptr(), ws.numel(),
+                                           nat.stream_handle(dev))
+            nat.check(rc, "vocoder_forward")
+
+        with nat.on_device(dev):
+            nat.guarded(dev, run, "vocoder", owner=self)
         return audio
 
 

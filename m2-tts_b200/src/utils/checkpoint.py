@@ -2,12 +2,14 @@
 
 Reference checkpoints are `torch.save({'model_state_dict', 'config', 'step', ...})` where `config` is an OmegaConf
 DictConfig pickled by the trainer (training/train.py:359). OmegaConf is not a dependency of this build: the file is
-first read with `weights_only=True` (tensors, plain containers); if that refuses the pickled config object, a second
-pass unpickles with a stub that turns every `omegaconf.*` class into a plain attribute dict, which is all
-`model_kwargs` needs. The state_dict keys/shapes are the reference's, loaded strictly.
+first read with `weights_only=True` (tensors, plain containers); if that refuses the pickled config object (and only
+then), a second pass unpickles with an ALLOW-LIST unpickler: `omegaconf.*` classes become plain attribute dicts, tensor
+rebuild helpers and plain containers resolve normally, every other global raises `UnpicklingError` — a checkpoint cannot
+run code through this loader. The state_dict keys/shapes are the reference's, loaded strictly.
 """
 from __future__ import annotations
 
+import logging
 import pickle
 from pathlib import Path
 from typing import Any, Optional, Tuple, Union
@@ -28,15 +30,39 @@ class _ConfigStub(dict):
             self.update(state)
 
 
+# Globals the fallback unpickler will resolve besides the omegaconf stubs: what `torch.save` itself emits for tensors and
+# plain containers. Anything else in the pickle stream (os.system, builtins.eval, ...) is refused: an untrusted checkpoint
+# must not be able to run code just because it also contains an OmegaConf object.
+_ALLOWED_GLOBALS = {
+    ("collections", "OrderedDict"), ("collections", "defaultdict"),
+    ("builtins", "dict"), ("builtins", "list"), ("builtins", "tuple"), ("builtins", "set"), ("builtins", "frozenset"),
+    ("builtins", "int"), ("builtins", "float"), ("builtins", "bool"), ("builtins", "str"), ("builtins", "bytes"),
+    ("builtins", "complex"), ("builtins", "slice"), ("builtins", "object"), ("builtins", "getattr"),
+    ("typing", "Any"), ("enum", "Enum"), ("pathlib", "PosixPath"), ("pathlib", "Path"), ("pathlib", "PurePosixPath"),
+    ("torch._utils", "_rebuild_tensor_v2"), ("torch._utils", "_rebuild_tensor"), ("torch._utils", "_rebuild_parameter"),
+    ("torch._utils", "_rebuild_parameter_with_state"), ("torch", "Size"), ("torch", "device"), ("torch", "dtype"),
+    ("torch._tensor", "_rebuild_from_type_v2"), ("torch.serialization", "_get_layout"),
+    ("numpy.core.multiarray", "scalar"), ("numpy._core.multiarray", "scalar"), ("numpy", "dtype"),
+    ("numpy.core.multiarray", "_reconstruct"), ("numpy._core.multiarray", "_reconstruct"), ("numpy", "ndarray"),
+}
+_ALLOWED_TORCH_STORAGES = {"FloatStorage", "DoubleStorage", "HalfStorage", "BFloat16Storage", "LongStorage", "IntStorage",
+                           "ShortStorage", "CharStorage", "ByteStorage", "BoolStorage", "UntypedStorage"}
+
+
 class _Unpickler(pickle.Unpickler):
     def find_class(self, module: str, name: str):
         if module.split(".")[0] == "omegaconf":
             return _ConfigStub
-        return super().find_class(module, name)
+        if (module, name) in _ALLOWED_GLOBALS or (module == "torch" and (name in _ALLOWED_TORCH_STORAGES or name.endswith("Tensor"))) \
+                or (module == "torch" and name in ("float32", "float64", "float16", "bfloat16", "int64", "int32", "int16", "int8",
+                                                    "uint8", "bool")):
+            return super().find_class(module, name)
+        raise pickle.UnpicklingError(f"checkpoint refers to {module}.{name}, which the m2tts_b200 loader does not allow "
+                                     "(only tensors, plain containers and OmegaConf config objects are read)")
 
 
 class _PickleShim:
-    """`pickle_module` for torch.load: everything stock except omegaconf classes."""
+    """`pickle_module` for torch.load: an allow-list unpickler (tensors, containers, omegaconf stubs)."""
     __name__ = "pickle"
     Unpickler = _Unpickler
     load = staticmethod(lambda f, **kw: _Unpickler(f, **kw).load())
@@ -68,7 +94,13 @@ def read_checkpoint(path: Union[str, Path], map_location="cpu") -> dict:
         raise FileNotFoundError(f"Checkpoint not found: {path}")          # scripts/synthesize.py:26-27
     try:
         return torch.load(path, map_location=map_location, weights_only=True)
-    except Exception:
+    except pickle.UnpicklingError as err:
+        # weights_only refused a global: for reference checkpoints that is the pickled OmegaConf config. Second pass with the
+        # allow-list unpickler (a corrupt or truncated file raises other exceptions and is NOT retried).
+        if "omegaconf" not in str(err).lower():
+            raise
+        logging.getLogger(__name__).info("checkpoint %s holds a pickled OmegaConf config: reading it with the allow-list "
+                                         "unpickler (omegaconf classes become plain dicts)", path)
         ckpt = torch.load(path, map_location=map_location, weights_only=False, pickle_module=_PickleShim)
         if "config" in ckpt:
             ckpt["config"] = _plain(ckpt["config"])

@@ -31,6 +31,8 @@ class HostPipeline:
 
     @staticmethod
     def bounds(n: int, chunks: int, edge: float = 1.0) -> List[Tuple[int, int]]:
+        if n <= 0:
+            return []
         chunks = min(chunks, n)
         if chunks < 3 or edge >= 1.0:
             base, extra = divmod(n, chunks)

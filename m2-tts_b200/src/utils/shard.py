@@ -50,7 +50,7 @@ def gather_batch(local: torch.Tensor, n_total: int, group=None) -> torch.Tensor:
         return local
     world = dist.get_world_size(group)
     sizes = [shard_bounds(n_total, r, world)[1] - shard_bounds(n_total, r, world)[0] for r in range(world)]
-    cap = max(sizes)
+    cap = max(max(sizes), 1)
     pad = local
     if local.shape[0] < cap:
         pad = torch.cat([local, local.new_zeros((cap - local.shape[0],) + tuple(local.shape[1:]))], 0)
@@ -72,12 +72,22 @@ def synthesize_sharded(model, phoneme_ids: torch.Tensor, phoneme_lengths: Option
     ids, lens, dur = shard_batch([phoneme_ids, phoneme_lengths, target_durations], rank, world)
     if max_target_length is None:
         if dur is None:
+            # every rank takes this branch (the arguments are replicated), so nobody is left waiting in a collective
             raise ValueError("sharded synthesis with predicted durations needs max_target_length "
                              "(or run the duration predictor first and pass its output as target_durations)")
-        max_target_length = shared_max_target_length(frames_from_durations(dur), group)
-    out = model(ids, lens, target_durations=dur, max_target_length=max_target_length)
-    res = {"mel_output": out["mel_output"], "audio_output": out["audio_output"],
-           "max_target_length": max_target_length}
+        local = frames_from_durations(dur) if dur.shape[0] > 0 else torch.ones(1, dtype=torch.int64, device=dur.device)
+        max_target_length = shared_max_target_length(local, group)
+    if ids.shape[0] > 0:
+        out = model(ids, lens, target_durations=dur, max_target_length=max_target_length)
+        mel, audio = out["mel_output"], out["audio_output"]
+    else:
+        # fewer utterances than ranks: this rank owns an empty block. It must still enter the collectives below with
+        # zero-row tensors of the agreed shapes, or the other ranks wait in all_gather forever.
+        dev = next(model.parameters()).device
+        mel_ch = model.decoder.mel_projection.out_features
+        mel = torch.zeros((0, max_target_length, mel_ch), dtype=torch.float32, device=dev)
+        audio = None if model.training else torch.zeros((0, 1, 64 * max_target_length), dtype=torch.float32, device=dev)
+    res = {"mel_output": mel, "audio_output": audio, "max_target_length": max_target_length}
     if gather:
         for k in ("mel_output", "audio_output"):
             if res[k] is not None:

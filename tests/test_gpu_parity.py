@@ -20,6 +20,34 @@ FP32_TOL = 1e-4
 DEV = "cuda:0"
 
 
+class _Status:
+    """Device status word for the stand-alone C-ABI entry points (include/m2tts_b200.h, "Status word"); every test that
+    passes it also checks that it stayed clear."""
+
+    def __init__(self):
+        self._t = None
+
+    def data_ptr(self):
+        if self._t is None:
+            self._t = torch.zeros(1, dtype=torch.int32, device=DEV)
+        return self._t.data_ptr()
+
+    def take(self):
+        v = int(self._t.item()) if self._t is not None else 0
+        if self._t is not None:
+            self._t.zero_()
+        return v
+
+
+STATUS = _Status()
+
+
+@pytest.fixture(autouse=True)
+def _status_word_stays_clear():
+    yield
+    assert STATUS.take() == 0, "a stand-alone kernel raised a status bit"
+
+
 def cuda_model(stage, perturb=None, **override):
     return H.product_model(stage, perturb=perturb, **override).to(DEV).eval()
 
@@ -281,7 +309,7 @@ def test_error_paths():
     with pytest.raises(nat.NativeLibraryError):
         m(torch.zeros(1, 4, dtype=torch.long))   # no CPU fallback in eval mode
     lib = nat.lib()
-    assert lib.m2tts_vocoder_forward(None, None, 0, 0, 0, None, 1, 1, 1, 16, None, 0, None) == -5
+    assert lib.m2tts_vocoder_forward(None, None, None, 0, 0, 0, None, 1, 1, 1, 16, -1, None, None, 0, None) == -5
     assert b"null" in lib.m2tts_last_error_string()
     with pytest.raises(ValueError):   # head_dim 12 is not supported by the attention kernel
         bad = H.product_model("tiny", hidden_dim=24, num_heads=2).to(DEV).eval()
@@ -300,12 +328,10 @@ def test_batch_sharding_is_exact():
 
 
 # --------------------------------------------------------------------------- tensor-core attention
-@pytest.mark.parametrize("mode", [0, 1, 2, 3])  # 0 = 16-bit split tcgen05 kernel, 1 = fp32 FFMA, 2 = TF32 single-warpgroup, 3 = TF32 warp-specialised
-def test_attention_kernels_both_meet_fp32_tolerance(mode):
+@pytest.mark.parametrize("prec", ["split16", "ffma", "tf32"])  # 16-bit split tcgen05 kernels (default), fp32 FFMA, TF32 split
+def test_transformer_precisions_all_meet_fp32_tolerance(prec):
     from models import _native as nat
-    lib = nat.lib()
-    try:
-        nat.check(lib.m2tts_set_attention_mode(mode), "set_attention_mode")
+    with nat.precision(prec):
         for stage, heads in (("stage2", 2), ("stage1", 2)):
             m = cuda_model(stage, perturb=4)
             sd = cpu_sd(m)
@@ -317,8 +343,11 @@ def test_attention_kernels_both_meet_fp32_tolerance(mode):
             lengths = torch.tensor([200, 77, 0, 129])
             enc, _ = m.text_encoder(ids.to(DEV), lengths.to(DEV))
             assert H.max_abs(enc.cpu(), oracle.text_encoder(sd, ids, lengths, heads)[0]) <= FP32_TOL, (stage, "encoder")
-    finally:
-        lib.m2tts_set_attention_mode(0)
+        # head_dim 64 (TF32: single-warpgroup kernel) and 16
+        for heads, hidden in ((2, 128), (4, 64)):
+            m = cuda_model("stage1", perturb=2, hidden_dim=hidden, num_heads=heads, mel_channels=20, text_encoder_layers=1, decoder_layers=1)
+            x = torch.randn(2, 203, hidden, generator=torch.Generator().manual_seed(1))
+            assert H.max_abs(m.decoder(x.to(DEV)).cpu(), oracle.mel_decoder(cpu_sd(m), x, heads)) <= FP32_TOL, (heads, hidden)
 
 
 # --------------------------------------------------------------------------- tensor-core vocoder convolutions
@@ -394,8 +423,9 @@ def test_fused_vocoder_stage(C, L, B, final, prec):
     else:
         ws = torch.empty(lib.m2tts_vocoder_stage_fused_workspace_bytes(C), dtype=torch.uint8, device=DEV)
         fn = lib.m2tts_vocoder_stage_fused
+    st = (STATUS.data_ptr(),) if prec == "f16" else ()
     rc = fn(*(t.data_ptr() for t in d[:7]), d[7].data_ptr() if final else None,
-            d[8].data_ptr() if final else None, y.data_ptr(), B, C, L, ws.data_ptr(), ws.numel(), None)
+            d[8].data_ptr() if final else None, y.data_ptr(), B, C, L, *st, ws.data_ptr(), ws.numel(), None)
     nat.check(rc, "vocoder_stage_fused")
     torch.cuda.synchronize()
     assert not torch.isnan(y).any(), "unwritten output rows"
@@ -418,7 +448,8 @@ def test_fused_resblock_c64(L, B):
     d = [t.to(DEV) for t in (x.transpose(1, 2).contiguous(), w1, b1, w2, b2)]
     y = torch.full(want.shape, float("nan"), device=DEV)
     ws = torch.empty(lib.m2tts_resblock_fused_h_workspace_bytes(B, C, L), dtype=torch.uint8, device=DEV)
-    nat.check(lib.m2tts_resblock_fused_h(*(t.data_ptr() for t in d), y.data_ptr(), B, C, L, ws.data_ptr(), ws.numel(), None), "resblock_fused_h")
+    nat.check(lib.m2tts_resblock_fused_h(*(t.data_ptr() for t in d), y.data_ptr(), B, C, L, STATUS.data_ptr(), ws.data_ptr(), ws.numel(), None),
+              "resblock_fused_h")
     torch.cuda.synchronize()
     assert not torch.isnan(y).any(), "unwritten output rows"
     assert H.max_abs(y.cpu(), want) <= FP32_TOL, (L, B)
@@ -450,7 +481,7 @@ def test_conv1d_k3_h_c128_matches_torch(L, B, act, res, out_cl):
     y = torch.full(want.shape, float("nan"), device=DEV)
     ws = torch.empty(lib.m2tts_conv1d_k3_h_workspace_bytes(B, C, L), dtype=torch.uint8, device=DEV)
     nat.check(lib.m2tts_conv1d_k3_h(xd.data_ptr(), wd.data_ptr(), bd.data_ptr(), rd.data_ptr() if res else None, y.data_ptr(), B, C, L,
-                                    act, out_cl, ws.data_ptr(), ws.numel(), None), "conv1d_k3_h")
+                                    act, out_cl, STATUS.data_ptr(), ws.data_ptr(), ws.numel(), None), "conv1d_k3_h")
     torch.cuda.synchronize()
     assert not torch.isnan(y).any(), "unwritten output rows"
     assert H.max_abs(y.cpu(), want) <= FP32_TOL, (L, B, act, res, out_cl)
@@ -474,24 +505,20 @@ def test_conv_transpose_x4_h_matches_torch(CI, L, B):
     xd, wd, bd = (t.to(DEV) for t in (x.transpose(1, 2).contiguous(), w, b))
     y = torch.full(want.shape, float("nan"), device=DEV)
     ws = torch.empty(lib.m2tts_conv_transpose_x4_h_workspace_bytes(B, CI, L), dtype=torch.uint8, device=DEV)
-    nat.check(lib.m2tts_conv_transpose_x4_h(xd.data_ptr(), wd.data_ptr(), bd.data_ptr(), y.data_ptr(), B, CI, L, ws.data_ptr(), ws.numel(), None),
-              "conv_transpose_x4_h")
+    nat.check(lib.m2tts_conv_transpose_x4_h(xd.data_ptr(), wd.data_ptr(), bd.data_ptr(), y.data_ptr(), B, CI, L, STATUS.data_ptr(), ws.data_ptr(),
+                                            ws.numel(), None), "conv_transpose_x4_h")
     torch.cuda.synchronize()
     assert not torch.isnan(y).any(), "unwritten output rows"
     assert H.max_abs(y.cpu(), want) <= FP32_TOL, (CI, L, B)
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2])  # 0 = tensor cores (16-bit split fused stages), 1 = FFMA everywhere, 2 = tensor cores, TF32 split
-def test_vocoder_modes_both_meet_fp32_tolerance(mode):
+@pytest.mark.parametrize("prec", ["split16", "ffma", "tf32"])  # channel-last 16-bit split chain (default), FFMA everywhere, TF32 split chain
+def test_vocoder_precisions_all_meet_fp32_tolerance(prec):
     from models import _native as nat
-    lib = nat.lib()
-    try:
-        nat.check(lib.m2tts_set_vocoder_mode(mode), "set_vocoder_mode")
+    with nat.precision(prec):
         for stage, B, T in (("stage2", 2, 203), ("stage1", 3, 130)):
             m = cuda_model(stage, perturb=6)
             M = H.STAGE_KWARGS[stage]["mel_channels"]
             mel = torch.randn(B, M, T, generator=torch.Generator().manual_seed(T))
             got = m.vocoder(mel.to(DEV))
             assert H.max_abs(got.cpu(), oracle.vocoder(cpu_sd(m), mel)) <= FP32_TOL, stage
-    finally:
-        lib.m2tts_set_vocoder_mode(0)

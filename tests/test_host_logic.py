@@ -21,8 +21,15 @@ def test_header_symbols_are_exported_and_bound():
     lib = C.CDLL(str(nat.library_path()))
     for sym in declared:
         assert hasattr(lib, sym), f"{sym} declared in the header but not exported"
-    assert declared <= set(nat.EXPORTED_SYMBOLS), declared - set(nat.EXPORTED_SYMBOLS)
-    assert nat.lib().m2tts_version() >= 100
+    assert declared == set(nat.EXPORTED_SYMBOLS), declared ^ set(nat.EXPORTED_SYMBOLS)
+    assert nat.lib().m2tts_version() >= 200
+    # the product library carries no bring-up hooks: those live in libm2tts_b200_tools.so (include/m2tts_b200_tools.h)
+    tools_hdr = (H.REPO / "include" / "m2tts_b200_tools.h").read_text()
+    tool_syms = set(re.findall(r"\b(m2tts_[a-z0-9_]+)\s*\(", tools_hdr))
+    assert tool_syms == set(nat.TOOL_SYMBOLS)
+    if nat.library_path().name == "libm2tts_b200.so":
+        for sym in tool_syms:
+            assert not hasattr(lib, sym), f"{sym} is a bring-up hook and must not be exported by the product library"
 
 
 def test_workspace_queries_without_gpu():
@@ -31,8 +38,11 @@ def test_workspace_queries_without_gpu():
     assert lib.m2tts_transformer_workspace_bytes(64, 3446, 96, 192) > 64 * 3446 * 96 * 4 * 9
     assert lib.m2tts_vocoder_workspace_bytes(64, 3446, 80, 256) > 3 * 64 * 256 * 3446 * 4 * 4
     assert lib.m2tts_vocoder_workspace_bytes(1, 1, 80, 8) == 0     # hidden_channels must be >= 16
-    assert lib.m2tts_vocoder_forward(None, None, 0, 0, 0, None, 1, 1, 1, 16, None, 0, None) == -5
+    assert lib.m2tts_vocoder_forward(None, None, None, 0, 0, 0, None, 1, 1, 1, 16, -1, None, None, 0, None) == -5
     assert b"null" in lib.m2tts_last_error_string()
+    assert lib.m2tts_vocoder_pack_bytes(80, 256, -1) > 2 * 530000 * 4      # every weight at least as hi + lo
+    assert lib.m2tts_transformer_pack_bytes(96, 192, -1) >= 2 * 4 * (3 * 96 * 96 + 96 * 96 + 2 * 96 * 192)
+    assert lib.m2tts_ln_proj_pack_bytes(96, 80, -1) >= 2 * 4 * 96 * 80
 
 
 def test_eval_mode_has_no_cpu_fallback():

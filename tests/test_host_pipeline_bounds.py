@@ -24,3 +24,8 @@ def test_edge_chunks_are_smaller():
     sizes = [hi - lo for lo, hi in HostPipeline.bounds(64, 3, 0.5)]
     assert sizes == [16, 32, 16]
     assert [hi - lo for lo, hi in HostPipeline.bounds(64, 3, 1.0)] == [22, 21, 21]
+
+
+def test_bounds_of_an_empty_batch():
+    from utils.host_pipeline import HostPipeline
+    assert HostPipeline.bounds(0, 3) == [] and HostPipeline.bounds(0, 3, 0.5) == []

@@ -88,6 +88,47 @@ def test_checkpoint_loader_survives_pickled_config_objects(tmp_path):
     assert m.hidden_dim == kw["hidden_dim"] if hasattr(m, "hidden_dim") else True
 
 
+def test_checkpoint_loader_refuses_code_execution_and_corrupt_files(tmp_path):
+    """the OmegaConf fallback must not become a generic unpickler. A checkpoint that smuggles a callable next to an
+    omegaconf object is refused (the payload never runs); a truncated file is reported as such, not retried."""
+    import pickle
+    import types
+    marker = tmp_path / "pwned"
+
+    class Evil:
+        def __reduce__(self):
+            import os
+            return (os.system, (f"touch {marker}",))
+
+    fake = types.ModuleType("omegaconf")
+
+    class DictConfig:
+        def __init__(self):
+            self.__dict__["_content"] = {}
+    DictConfig.__module__ = "omegaconf"
+    DictConfig.__qualname__ = "DictConfig"
+    fake.DictConfig = DictConfig
+    sys.modules["omegaconf"] = fake
+    try:
+        torch.save({"model_state_dict": {}, "config": DictConfig(), "extra": Evil()}, tmp_path / "evil.pt")
+    finally:
+        del sys.modules["omegaconf"]
+    with pytest.raises(pickle.UnpicklingError):
+        read_checkpoint(tmp_path / "evil.pt")
+    assert not marker.exists()
+    # no omegaconf object at all: weights_only's own refusal is passed on, nothing is retried
+    torch.save({"model_state_dict": {}, "extra": Evil()}, tmp_path / "evil2.pt")
+    with pytest.raises(pickle.UnpicklingError):
+        read_checkpoint(tmp_path / "evil2.pt")
+    assert not marker.exists()
+    good = tmp_path / "good.pt"
+    torch.save({"model_state_dict": H.product_model("tiny").state_dict()}, good)
+    (tmp_path / "cut.pt").write_bytes(good.read_bytes()[: good.stat().st_size // 2])
+    with pytest.raises(Exception) as ei:
+        read_checkpoint(tmp_path / "cut.pt")
+    assert not isinstance(ei.value, FileNotFoundError)
+
+
 def test_cli_rejects_ambiguous_input(tmp_path):
     with pytest.raises(SystemExit):
         _cli().main(["--checkpoint", str(tmp_path / "x.pt")])
