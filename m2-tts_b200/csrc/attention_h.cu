@@ -1,22 +1,39 @@
 // attention_h.cu — flash attention on tcgen05 with a 16-BIT split: every operand x is carried as two fp16 numbers,
 // x = hi + lo (hi = fp16(x), lo = fp16(x - hi): 22 significant bits, the same as the TF32 split of attention_tc.cu),
 // and a product is a_hi*b_hi + a_hi*b_lo + a_lo*b_hi with fp32 accumulation in TMEM. Against the TF32 split this
-// halves the operand bytes (K = 16 per UMMA instead of 8) and therefore the UMMA count — the tensor pipe here is
-// bound by UMMA instructions of ~45-64 cycles each, not by math (mma_bench.cu). Accuracy on the reference's value
-// ranges is that of the TF32 split (tools: the CPU emulation in DESIGN.md §4.1; parity tests <= 1e-4); fp16 needs
-// |x| < 65504, which the producer (QKV GEMM epilogue) enforces by saturating — LayerNorm'd activations times
-// Xavier-scale weights are O(1-10).
+// halves the operand bytes (K = 16 per UMMA instead of 8) and therefore the UMMA count. Accuracy on the reference's value
+// ranges is that of the TF32 split (parity tests <= 1e-4); fp16 needs |x| <= 65504: the producers (QKV GEMM epilogue, this
+// kernel's own output planes) check their values and raise M2TTS_ST_FP16_RANGE (include/m2tts_b200.h).
 //
-// Same organisation as attention_ws_kernel (attention_tc.cu): one CTA = two 128-query tiles of one (utterance, head)
-// sharing every K/V tile; warp 0 TMA loader, warp 1 UMMA issuer (warp-collective), warps 4-7 / 8-11 softmax
-// warpgroups; lazy rescaling with O accumulating in TMEM. With the tensor work halved the softmax warpgroups are
-// the bottleneck, so the SCORES ARE DOUBLE-BUFFERED in TMEM: QK(t+2) is issued right behind PV(t), a warpgroup
-// finds S(t+1) waiting when it finishes tile t, and never idles on the tensor pipe. (Double buffering needs the 64-column
-// score tile, so Q K^T keeps its three terms as separate N = 64 UMMAs; P V folds V_hi|V_lo into N = 2 hd.)
+// One CTA = two 128-query tiles of one (utterance, head) sharing every 64-key K/V tile; warp 0 TMA loader, warps 1 / 2 the
+// UMMA issuers of tile A / B (warp-collective issue), warps 4-19 four softmax warpgroups, two per query tile (thread = query
+// row = TMEM lane, warpgroup `half` owns 32 of the 64 score columns; partial row maxima are exchanged through shared memory
+// at a 64-thread named barrier); lazy rescaling with O accumulating in TMEM. The SCORES ARE DOUBLE-BUFFERED in TMEM:
+// QK(t+2) is issued right behind PV(t), so a warpgroup finds S(t+1) waiting when it finishes tile t.
+//
+// The kernel is bound by its softmax (tools/attn_dbg.py: 0.73 of 0.91 ms per C3 layer remain with every UMMA switched off;
+// a variant with 128-key tiles and one in-place score buffer per query tile halved the Q K^T UMMAs but serialised
+// Q K^T -> softmax -> P V per tile and was slower, 0.99 ms), so round 2 went into instructions per score and MUFU load:
+//   * packed fp32 pairs (FADD2) for s - m, the row sum and p - p_hi; FMNMX3 for the maximum; p_hi by masking the low 13
+//     mantissa bits (exact in fp16), so no half -> float conversion; one F2FP per packed pair: 9 instructions per PAIR of
+//     scores (2 MUFU, 3 FADD2, 2 LOP3, 2 F2FP) instead of ~15. ncu on this kernel: issue slots 66 %, ALU pipe 56 %, MUFU
+//     43 %, tensor pipe 40 %, FMA pipe 14 % (profiles/r2_ncu_attention_h.md) — it is bound by instruction issue;
+//   * P is written over S IN PLACE per 16-key group (= one k-step of P V): the 16 fp32 scores of a group become 8 columns of
+//     packed P_hi and 8 of packed P_lo in the same 16 columns, so the two warpgroups of a tile never touch each other's
+//     columns;
+//   * Q_hi lives in TMEM as the A operand of Q K^T (packed fp16 pairs, written once by the softmax threads; head_dim <= 48):
+//     six of the nine Q K^T UMMAs per key tile fetch only K from shared memory (TMEM per query tile: 2 x 64 scores, O 2 hd,
+//     Q_hi hd / 2 = 248 of 256 columns at head_dim 48);
+//   * the two query tiles take TURNS in the exponential phase (two named barriers, strict alternation): left alone, the
+//     four warps of a scheduler drift into the same phase, all 32 x 4 MUFU.EX2 of a key tile queue up on the scheduler's one
+//     MUFU (16 results per clock per SM) while it idles through everybody's load / maximum / exchange phases (tools/
+//     attn_prof.py: 1136 of 2089 cycles per key tile in the exponential phase for 256 cycles of own MUFU work). Evaluating
+//     part of the exponentials by a degree-5 polynomial in packed FFMA2 on the FMA pipe (the FlashAttention-4 trick) was
+//     measured and is slower here: the split arithmetic already fills that pipe.
 // Operands: qkvh[6][B][nh][hd][Lp] fp16 = {Q_hi,Q_lo,K_hi,K_lo,V_hi,V_lo}, positions contiguous, Lp % 8 == 0, Q
 // pre-multiplied by scale*log2(e). A TMA box = 64 positions (128 B) x hd rows: for Q and K the MN-major 128B-swizzle
 // operand (K dim = d), for V the K-major 128B-swizzle operand (rows = d, K dim = keys) — layouts verified with
-// umma_probe_f16.cu. P is written back to TMEM as packed fp16 pairs (low half = even key).
+// tools/umma_probe_f16.cu. P is written back to TMEM as packed fp16 pairs (low half = even key). Reference: components.py:75-87.
 #include "attention_tc.cuh"
 #include <cuda_fp16.h>
 
@@ -25,10 +42,17 @@ namespace m2 {
 constexpr int AH_THREADS = 128 + 512;      // loader, two issuers, idle | four softmax warpgroups (two per query tile)
 constexpr uint32_t AH_TMEM_COLS = 512;
 // TMEM per query tile (tile stride 256 columns): two score buffers of 64 columns (tile t uses buffer t & 1; P(t) is
-// packed over it: P_hi in columns 0:32, P_lo in 32:64 of the buffer) and O in 2 hd columns from 128.
-constexpr uint32_t AH_COL_S = 0, AH_COL_PLO = 32, AH_COL_O = 128;
+// packed over it, 16-key group u in columns [16 u, 16 u + 16): P_hi in the first 8, P_lo in the last 8), O in 2 hd columns
+// from 128, Q_hi in hd / 2 columns from 224.
+constexpr uint32_t AH_COL_S = 0, AH_COL_O = 128, AH_COL_Q = 224;      // Q_hi: hd / 2 columns from 224 (head_dim <= 48)
 constexpr uint32_t AH_COL_TILE = 256;
 constexpr int AH_STAGES = 4;        // K / V ring depth
+// phase timestamps (tools/attn_prof.py) exist only in the tools build: predicated-off CS2R / STG pairs still cost issue slots
+#ifdef M2TTS_TOOLS
+#define AH_PROF(cond, stmt) do { if (cond) { stmt; } } while (0)
+#else
+#define AH_PROF(cond, stmt) do { } while (0)
+#endif
 
 template <int HD>
 struct AhSmem {
@@ -42,9 +66,10 @@ struct AhSmem {
   static constexpr uint32_t total = off_exch + 4096 + 1024 /*align slack*/;
 };
 
-__host__ __device__ constexpr uint32_t ah_idesc(int M, int N, int mn_major) {   // kind::f16: fp16 x fp16 -> fp32
-  return (1u << 4) | ((uint32_t)mn_major << 15) | ((uint32_t)mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+__host__ __device__ constexpr uint32_t ah_idesc2(int M, int N, int a_mn, int b_mn) {   // kind::f16: fp16 x fp16 -> fp32; *_mn = 1: MN-major smem operand
+  return (1u << 4) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+__host__ __device__ constexpr uint32_t ah_idesc(int M, int N, int mn_major) { return ah_idesc2(M, N, mn_major, mn_major); }
 __device__ __forceinline__ void umma_f16_ss_w(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
   asm volatile("{\n\t.reg .pred p, q;\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
@@ -56,15 +81,41 @@ __device__ __forceinline__ void umma_f16_ts_w(uint32_t d_tmem, uint32_t a_tmem, 
                ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
 }
 
+// packed fp32 pairs (Blackwell FADD2 / FFMA2): one instruction for two lanes
+__device__ __forceinline__ uint64_t ah_pack(float lo, float hi) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void ah_unpack(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t ah_add2(uint64_t a, uint64_t b) { uint64_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t ah_sub2(uint64_t a, uint64_t b) { uint64_t r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ float ah_max3(float a, float b, float c) { float r; asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
+__device__ __forceinline__ uint32_t ah_cvt2(float lo, float hi) {      // {lo, hi} -> packed fp16 pair (low half = lo), round to nearest
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ void ah_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void ah_st4(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
+}
+__device__ __forceinline__ float ws_ex2v(float x) {      // ex2 that keeps its place in the instruction stream
+  float y;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 template <int HD>
 __global__ void __launch_bounds__(AH_THREADS, 1)
-attention_h_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__ ctx, const int64_t* __restrict__ lengths,
-                   int B, int L, int nh, float* __restrict__ ctx_lo, __half* __restrict__ ctx_h, long long* __restrict__ prof, int dbg_skip,
-                   int32_t* __restrict__ status) {
+attention_h_kernel(const __grid_constant__ CUtensorMap tmap, const __half* __restrict__ qkvh, int Lp, float* __restrict__ ctx,
+                   const int64_t* __restrict__ lengths, int B, int L, int nh, float* __restrict__ ctx_lo, __half* __restrict__ ctx_h,
+                   long long* __restrict__ prof, int dbg_skip, int32_t* __restrict__ status) {
   static_assert(HD % 16 == 0 && HD >= 16 && HD <= 64, "16-bit split attention: head_dim in {16,32,48,64}");
   constexpr uint32_t BOX = AhSmem<HD>::box;
   constexpr int KSTEPS_D = HD / 16;
-  constexpr uint32_t IDESC_QK1 = ah_idesc(TC_BQ, TC_BK, 1);       // Q_* x K_*
+  constexpr bool QT = (128 + 2 * HD + HD / 2) <= 256;             // Q_hi as a TMEM A operand (head_dim <= 48), else from shared memory
+  constexpr uint32_t IDESC_QK1 = ah_idesc(TC_BQ, TC_BK, 1);       // Q_* (MN-major smem) x K_*
+  constexpr uint32_t IDESC_QKT = ah_idesc2(TC_BQ, TC_BK, 0, 1);   // Q_hi (TMEM) x K_*
   constexpr uint32_t IDESC_PV2 = ah_idesc(TC_BQ, 2 * HD, 0);      // P_hi x [V_hi | V_lo]
   constexpr uint32_t IDESC_PV1 = ah_idesc(TC_BQ, HD, 0);          // P_lo x V_hi
 
@@ -78,6 +129,7 @@ attention_h_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__
   const uint32_t bar_qf = sBar, bar_sf = sBar + 16, bar_pr = sBar + 48, bar_pv = sBar + 64;
   const uint32_t bar_kf = sBar + 80, bar_ke = bar_kf + 8 * AH_STAGES, bar_vf = bar_ke + 8 * AH_STAGES, bar_ve = bar_vf + 8 * AH_STAGES;
   const uint32_t tmem_slot = bar_ve + 8 * AH_STAGES;
+  const uint32_t bar_qh = tmem_slot + 8;                       // q_hi[2]: Q_hi of tile x has been written to TMEM (8 softmax warps)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // 1-D grid, longest first: all CTAs with two query tiles, then (odd tile count) the single-tile CTAs, which take about
@@ -103,7 +155,7 @@ attention_h_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_qf + 8 * i, 1); mbar_init(bar_sf + 16 * i, 1); mbar_init(bar_sf + 16 * i + 8, 1);
-      mbar_init(bar_pr + 8 * i, 8); mbar_init(bar_pv + 8 * i, 1);
+      mbar_init(bar_pr + 8 * i, 8); mbar_init(bar_pv + 8 * i, 1); mbar_init(bar_qh + 8 * i, 8);
     }
     for (int i = 0; i < AH_STAGES; ++i) {
       mbar_init(bar_kf + 8 * i, 1); mbar_init(bar_ke + 8 * i, (uint32_t)ntq); mbar_init(bar_vf + 8 * i, 1); mbar_init(bar_ve + 8 * i, (uint32_t)ntq);
@@ -126,8 +178,8 @@ attention_h_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__
     if (lane == 0) {
       // ===== loader =====
       for (int x = 0; x < ntq; ++x) {
-        mbar_expect_tx(bar_qf + 8 * x, AhSmem<HD>::q_bytes);
-        for (int h = 0; h < 2; ++h)
+        mbar_expect_tx(bar_qf + 8 * x, QT ? AhSmem<HD>::q_bytes / 2 : AhSmem<HD>::q_bytes);
+        for (int h = QT ? 1 : 0; h < 2; ++h)      // with Q_hi in TMEM only the lo plane is a shared-memory operand
           for (int j = 0; j < 2; ++j)
             tma_load_2d(sQ + (uint32_t)x * AhSmem<HD>::q_bytes + (h * 2 + j) * BOX, &tmap, q0 + x * TC_BQ + j * 64, h * plane + row_q,
                         bar_qf + 8 * x);
@@ -148,13 +200,26 @@ attention_h_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__
   } else if ((warp == 1 || warp == 2) && warp - 1 < ntq) {
     // ===== UMMA issuer of query tile x (whole warp, one elected lane issues) =====
     const int x = warp - 1;
+#ifdef M2TTS_TOOLS
     const bool pr_on = prof != nullptr && blockIdx.x == 0;
+#endif
     auto issue_qk = [&](int x, int st, int buf) {
       if (dbg_skip & 1) return;      // bring-up timing experiment (M2TTS_ATT_DBG): results invalid
       const uint32_t q = sQ + (uint32_t)x * AhSmem<HD>::q_bytes, k = sK + (uint32_t)st * AhSmem<HD>::kv_bytes;
       const uint32_t d = tmem_base + (uint32_t)x * AH_COL_TILE + AH_COL_S + (uint32_t)buf * 64u;
       // MN-major, 128B swizzle, 16-bit: LBO = next 64 positions (next box), SBO = next 8 d-rows (1024 B);
       // one k-step = 16 d-rows = 2048 B. Terms: hi*hi, hi*lo, lo*hi.
+      if (QT) {      // Q_hi from TMEM: one k-step = 16 d-rows = 8 columns of packed pairs
+        const uint32_t qt = tmem_base + (uint32_t)x * AH_COL_TILE + AH_COL_Q;
+#pragma unroll
+        for (int ks = 0; ks < KSTEPS_D; ++ks) {
+          const uint64_t khi = umma_desc(k + ks * 2048u, BOX, 1024u, 2u), klo = umma_desc(k + BOX + ks * 2048u, BOX, 1024u, 2u);
+          umma_f16_ts_w(d, qt + ks * 8, khi, IDESC_QKT, ks ? 1u : 0u);
+          umma_f16_ts_w(d, qt + ks * 8, klo, IDESC_QKT, 1u);
+          umma_f16_ss_w(d, umma_desc(q + 2 * BOX + ks * 2048u, BOX, 1024u, 2u), khi, IDESC_QK1, 1u);
+        }
+        return;
+      }
 #pragma unroll
       for (int term = 0; term < 3; ++term) {
         const uint32_t qa = q + (term == 2 ? 2 * BOX : 0u), kb = k + (term == 1 ? BOX : 0u);
@@ -169,13 +234,14 @@ attention_h_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__
       const uint32_t v = sV + (uint32_t)st * AhSmem<HD>::kv_bytes;
       const uint32_t tb = tmem_base + (uint32_t)x * AH_COL_TILE;
       const uint32_t pb = tb + AH_COL_S + (uint32_t)buf * 64u;
-      // V^T box: rows = d (V_hi rows then V_lo rows), keys contiguous; one k-step = 16 keys = 32 B = 8 TMEM columns of P
+      // V^T box: rows = d (V_hi rows then V_lo rows), keys contiguous; one k-step = 16 keys = 32 B = 8 TMEM columns of P.
+      // The 16 keys of k-step ks sit in score columns [16 ks, 16 ks + 16): packed P_hi in the first 8, P_lo in the last 8.
 #pragma unroll
       for (int ks = 0; ks < TC_BK / 16; ++ks)
-        umma_f16_ts_w(tb + AH_COL_O, pb + ks * 8, umma_desc(v + ks * 32u, 16u, 1024u, 2u), IDESC_PV2, ks ? 1u : accumulate);
+        umma_f16_ts_w(tb + AH_COL_O, pb + ks * 16, umma_desc(v + ks * 32u, 16u, 1024u, 2u), IDESC_PV2, ks ? 1u : accumulate);
 #pragma unroll
       for (int ks = 0; ks < TC_BK / 16; ++ks)
-        umma_f16_ts_w(tb + AH_COL_O, pb + AH_COL_PLO + ks * 8, umma_desc(v + ks * 32u, 16u, 1024u, 2u), IDESC_PV1, 1u);
+        umma_f16_ts_w(tb + AH_COL_O, pb + ks * 16 + 8, umma_desc(v + ks * 32u, 16u, 1024u, 2u), IDESC_PV1, 1u);
     };
     // One issuer warp per query tile (warps 1 and 2 sit on different schedulers): an UMMA costs its issuer ~12 instructions
     // (descriptor moves into uniform registers, elect), ~50 cycles next to two busy softmax warps, and a single issuer
@@ -184,7 +250,10 @@ attention_h_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__
     // prologue: the scores of key tiles 0 and 1
     for (int t = 0; t < 2 && t < nkt; ++t) {
       mbar_wait(bar_kf + 8 * t, 0);
-      if (t == 0) mbar_wait(bar_qf + 8 * x, 0);
+      if (t == 0) {
+        mbar_wait(bar_qf + 8 * x, 0);
+        if (QT) mbar_wait(bar_qh + 8 * x, 0);
+      }
       tc_fence_after();
       issue_qk(x, t, t);
       tc_commit_w(bar_sf + 16 * x + 8 * t);
@@ -193,9 +262,9 @@ attention_h_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__
     for (int t = 0; t < nkt; ++t) {
       const int st = t % AH_STAGES, s2 = (t + 2) % AH_STAGES, buf = t & 1;
       const uint32_t par = (uint32_t)(t & 1);
-      if (pr_on && lane == 0 && t >= 8 && t < 40) prof[384 + (t - 8) * 8 + 3 * x] = clock64();
+      AH_PROF(pr_on && lane == 0 && t >= 8 && t < 40, prof[384 + (t - 8) * 8 + 3 * x] = clock64());
       mbar_wait(bar_pr + 8 * x, par);                         // P(x,t) is in TMEM (and O has been rescaled if needed)
-      if (pr_on && lane == 0 && t >= 8 && t < 40) prof[384 + (t - 8) * 8 + 3 * x + 1] = clock64();
+      AH_PROF(pr_on && lane == 0 && t >= 8 && t < 40, prof[384 + (t - 8) * 8 + 3 * x + 1] = clock64());
       mbar_wait(bar_vf + 8 * st, (uint32_t)((t / AH_STAGES) & 1));
       tc_fence_after();
       issue_pv(x, st, buf, t > 0 ? 1u : 0u);
@@ -208,58 +277,91 @@ attention_h_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__
         tc_commit_w(bar_sf + 16 * x + 8 * buf);
         tc_commit_w(bar_ke + 8 * s2);
       }
-      if (pr_on && lane == 0 && t >= 8 && t < 40) prof[384 + (t - 8) * 8 + 3 * x + 2] = clock64();
+      AH_PROF(pr_on && lane == 0 && t >= 8 && t < 40, prof[384 + (t - 8) * 8 + 3 * x + 2] = clock64());
     }
   } else if (warp >= 4 && (((warp - 4) >> 2) & 1) < ntq) {
     // ===== softmax warpgroups: query tile x has TWO of them (warps 4-7 / 12-15 for tile A, 8-11 / 16-19 for tile B); thread =
-    // query row = TMEM lane, warpgroup `half` owns 32 of the 64 score columns of every key tile. Four softmax warps per
-    // scheduler instead of two: the loop is bound by MUFU (quarter rate) and by the latency of its own dependent
-    // instructions, not by issue slots (tools/attn_prof.py: 2054 cycles per key tile even with the UMMAs switched off).
-    // The two warps that share a row exchange their partial row maxima through shared memory at a 64-thread named barrier,
-    // which also orders "both have loaded their scores" before either packs P over the score columns.
+    // query row = TMEM lane, warpgroup `half` owns score columns [32 half, 32 half + 32) of every key tile = the 16-key groups
+    // 2 half and 2 half + 1. The two warps that share a row exchange their partial row maxima through shared memory at a
+    // 64-thread named barrier.
     const int x = ((warp - 4) >> 2) & 1, half = (warp - 4) >> 3;
     const int row = (warp & 3) * 32 + lane;
     const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)x * AH_COL_TILE;
     float* exch = reinterpret_cast<float*>(smem_raw + (sbase - smem_u32(smem_raw)) + AhSmem<HD>::off_exch);
     const int pair_bar = 1 + x * 4 + (warp & 3);          // named barrier of the two warps sharing these 32 rows
-    float m_ref = -INFINITY, l_run = 0.f;
+    if (QT) {
+      // Q_hi -> TMEM as the A operand of Q K^T: column c of this lane = (Q_hi[row][2c], Q_hi[row][2c+1]); this warpgroup writes
+      // the d range [half hd/2, (half+1) hd/2). Plane 0 of qkvh is Q_hi [B][nh][hd][Lp], positions contiguous: the 32 lanes of
+      // a warp read 64 contiguous bytes per d.
+      const int qi = q0 + x * TC_BQ + row;
+      const __half* qp = qkvh + ((long long)row_q + half * (HD / 2)) * Lp + qi;
+#pragma unroll
+      for (int c4 = 0; c4 < HD / 16; ++c4) {
+        uint32_t w[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int d = (c4 * 4 + e) * 2;
+          unsigned short lo = 0, hi = 0;
+          if (qi < L) { lo = __half_as_ushort(qp[(long long)d * Lp]); hi = __half_as_ushort(qp[(long long)(d + 1) * Lp]); }
+          w[e] = (uint32_t)lo | ((uint32_t)hi << 16);
+        }
+        ah_st4(t_lane + AH_COL_Q + (uint32_t)(half * (HD / 4) + c4 * 4), w);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_qh + 8 * x) : "memory");
+    }
+    float m_ref = -INFINITY;
+    uint64_t l2 = ah_pack(0.f, 0.f);                      // running row sum as a packed pair (even keys, odd keys)
+    const bool pingpong = ntq == 2 && !(dbg_skip & 8);
+    if (pingpong && x == 1) asm volatile("bar.arrive 10, 512;" ::: "memory");      // tile A takes the first turn
+#ifdef M2TTS_TOOLS
     const bool pw = prof != nullptr && blockIdx.x == 0 && x == 0 && half == 0 && row == 0;
+#endif
+    // key padding (only ever in the last key tile): masked keys get -inf; an utterance of length 0 reproduces the reference's
+    // uniform attention over all L positions (components.py:77-81 fills with a finite -1e9)
+    auto mask16 = [&](uint32_t* sv, int k0) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float a = __uint_as_float(sv[j]);
+        if (all_masked) a = (k0 + j < L) ? 0.f : -INFINITY;
+        else if (k0 + j >= Leff) a = -INFINITY;
+        sv[j] = __float_as_uint(a);
+      }
+    };
     for (int t = 0; t < nkt; ++t) {
+#ifdef M2TTS_TOOLS
       const bool pt = pw && t >= 8 && t < 40;
       long long* pp = prof + (pt ? (t - 8) * 8 : 0);
-      const uint32_t t_s = t_lane + AH_COL_S + (uint32_t)(t & 1) * 64u;     // this tile's score buffer (P goes over it)
-      if (pt) pp[0] = clock64();
+#endif
+      const uint32_t t_s = t_lane + AH_COL_S + (uint32_t)(t & 1) * 64u + (uint32_t)half * 32u;     // this warpgroup's 32 columns of the tile's score buffer
+      AH_PROF(pt, pp[0] = clock64());
       mbar_wait(bar_sf + 16 * x + 8 * (t & 1), (uint32_t)((t >> 1) & 1));
-      if (pt) pp[1] = clock64();
+      AH_PROF(pt, pp[1] = clock64());
       __syncwarp();
       tc_fence_after();
-      uint32_t sr[32];
-      tmem_ld16(t_s + half * 32, sr);
-      tmem_ld16(t_s + half * 32 + 16, sr + 16);
+      uint32_t sa[16], sb[16];
+      tmem_ld16(t_s, sa);
+      tmem_ld16(t_s + 16, sb);
       tmem_wait_ld();
-      if (pt) pp[2] = clock64();
+      AH_PROF(pt, pp[2] = clock64());
       const int kbase = t * TC_BK + half * 32;
-      if (all_masked || kbase + 32 > Leff) {
+      if (all_masked || kbase + 32 > Leff) { mask16(sa, kbase); mask16(sb, kbase + 16); }
+      float mx = ah_max3(__uint_as_float(sa[0]), __uint_as_float(sa[1]), __uint_as_float(sa[2]));
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float v = __uint_as_float(sr[j]);
-          if (all_masked) v = (kbase + j < L) ? 0.f : -INFINITY;
-          else if (kbase + j >= Leff) v = -INFINITY;
-          sr[j] = __float_as_uint(v);
-        }
-      }
-      float mx = __uint_as_float(sr[0]);
+      for (int j = 3; j < 15; j += 2) mx = ah_max3(mx, __uint_as_float(sa[j]), __uint_as_float(sa[j + 1]));
+      mx = ah_max3(mx, __uint_as_float(sa[15]), __uint_as_float(sb[0]));
 #pragma unroll
-      for (int j = 1; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(sr[j]));
+      for (int j = 1; j < 15; j += 2) mx = ah_max3(mx, __uint_as_float(sb[j]), __uint_as_float(sb[j + 1]));
+      mx = fmaxf(mx, __uint_as_float(sb[15]));
       {  // row maximum over all 64 columns
         float* e = exch + ((t & 1) * 4 + x * 2) * 128;
         e[half * 128 + row] = mx;
         asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
         mx = fmaxf(mx, e[(half ^ 1) * 128 + row]);
       }
-      if (t == 0) {
-        m_ref = mx;
-      }
+      if (t == 0) m_ref = mx;
       // The pv_done barrier completes one phase per key tile. We wait for phase t-1 in EVERY tile (a parity wait is
       // only exact while the waiter is at most one phase behind): early when O has to be rescaled, otherwise at the
       // end of the tile, when PV(t-1) has long landed and the wait costs nothing.
@@ -273,7 +375,9 @@ attention_h_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__
         const float m_new = fmaxf(m_ref, mx);
         const float alpha = ws_ex2(m_ref - m_new);
         m_ref = m_new;
-        l_run *= alpha;
+        float la, lb;
+        ah_unpack(l2, la, lb);
+        l2 = ah_pack(la * alpha, lb * alpha);
 #pragma unroll
         for (int c = 0; c < HD; c += 16) {
           uint32_t orr[16];
@@ -284,36 +388,65 @@ attention_h_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__
           tmem_st16(t_lane + AH_COL_O + half * HD + c, orr);
         }
       }
-      if (pt) pp[3] = clock64();
-      float rs = 0.f;
-      {        // 32 keys -> 16 packed columns of P_hi and of P_lo
-        uint32_t ph[16], pl[16];
+      // exponential phase: the two query tiles alternate (barrier 9: tile A is done, tile B may go; barrier 10: the reverse)
+      if (pingpong) asm volatile("bar.sync %0, 512;" ::"r"(10 - x) : "memory");
+      AH_PROF(pt, pp[3] = clock64());
+      // p = 2^(s - m_ref), 16 keys (= one k-step of P V) at a time, written over their own 16 score columns: 8 columns of packed
+      // P_hi (the top 11 significant bits of p) and 8 of packed P_lo = fp16(p - P_hi).
+      // All 32 exponentials are issued first (MUFU.EX2 is the unit that saturates: 8 cycles per warp instruction), the split
+      // arithmetic of a pair follows once its exponentials are back.
+      const uint64_t m2 = ah_pack(m_ref, m_ref);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float p0 = ws_ex2(__uint_as_float(sr[2 * j]) - m_ref);
-          const float p1 = ws_ex2(__uint_as_float(sr[2 * j + 1]) - m_ref);
-          rs += p0 + p1;
-          const __half2 h = __floats2half2_rn(p0, p1);
-          const float2 hf = __half22float2(h);
-          const __half2 lo = __floats2half2_rn(p0 - hf.x, p1 - hf.y);
-          ph[j] = *reinterpret_cast<const uint32_t*>(&h);
-          pl[j] = *reinterpret_cast<const uint32_t*>(&lo);
-        }
-        tmem_st16(t_s + half * 16, ph);                      // P overwrites the scores in place
-        tmem_st16(t_s + AH_COL_PLO + half * 16, pl);
+      for (int j = 0; j < 8; ++j) {
+        float d0, d1;
+        ah_unpack(ah_sub2(ah_pack(__uint_as_float(sa[2 * j]), __uint_as_float(sa[2 * j + 1])), m2), d0, d1);
+        sa[2 * j] = __float_as_uint(ws_ex2v(d0)); sa[2 * j + 1] = __float_as_uint(ws_ex2v(d1));
       }
-      l_run += rs;
-      if (pt) pp[4] = clock64();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float d0, d1;
+        ah_unpack(ah_sub2(ah_pack(__uint_as_float(sb[2 * j]), __uint_as_float(sb[2 * j + 1])), m2), d0, d1);
+        sb[2 * j] = __float_as_uint(ws_ex2v(d0)); sb[2 * j + 1] = __float_as_uint(ws_ex2v(d1));
+      }
+      auto split16 = [&](const uint32_t* pv, int u) {
+        uint32_t ph[8], pl[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float p0 = __uint_as_float(pv[2 * j]), p1 = __uint_as_float(pv[2 * j + 1]);
+          const uint64_t pp2 = ah_pack(p0, p1);
+          l2 = ah_add2(l2, pp2);
+          // Veltkamp split on the FMA pipe (the ALU pipe is the busiest one here): c = p (2^13 + 1), hi = c - (c - p) keeps the
+          // top 11 significant bits of p (round to nearest) and is exact in fp16; lo = p - hi is exact in fp32
+          // hi = p with the low 13 mantissa bits masked off (exact in fp16), lo = p - hi (exact in fp32). A Veltkamp split on the FMA
+          // pipe (hi = c - (c - p), c = 8193 p) takes the two LOP3 off the busy ALU pipe but is one instruction longer, and was
+          // slower: 0.930 against 0.888 ms per layer, the loop is bound by issue slots
+          const float h0 = __uint_as_float(__float_as_uint(p0) & 0xFFFFE000u), h1 = __uint_as_float(__float_as_uint(p1) & 0xFFFFE000u);
+          float r0, r1;
+          ah_unpack(ah_sub2(pp2, ah_pack(h0, h1)), r0, r1);
+          ph[j] = ah_cvt2(h0, h1);
+          pl[j] = ah_cvt2(r0, r1);
+        }
+        ah_st8(t_s + (uint32_t)(u * 16), ph);
+        ah_st8(t_s + (uint32_t)(u * 16 + 8), pl);
+      };
+      split16(sa, 0);
+      split16(sb, 1);
+      if (pingpong && !(x == 1 && t == nkt - 1)) asm volatile("bar.arrive %0, 512;" ::"r"(9 + x) : "memory");
+      AH_PROF(pt, pp[4] = clock64());
       tmem_wait_st();
-      if (pt) pp[5] = clock64();
+      AH_PROF(pt, pp[5] = clock64());
       if (!pv_waited) mbar_wait(bar_pv + 8 * x, (uint32_t)((t - 1) & 1));
-      if (pt) pp[6] = clock64();
+      AH_PROF(pt, pp[6] = clock64());
       tc_fence_before();
       __syncwarp();
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_pr + 8 * x) : "memory");
     }
     // total row sum: the second warpgroup of the tile publishes its part and is done
+    float l_run;
     {
+      float la, lb;
+      ah_unpack(l2, la, lb);
+      l_run = la + lb;
       float* e = exch + ((nkt & 1) * 4 + x * 2) * 128;
       if (half == 1) e[128 + row] = l_run;
       asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
@@ -394,14 +527,14 @@ static EncodeTiledFnH ah_encode_fn() {
 extern long long* g_ws_prof;      // attention_tc.cu (m2tts_attention_set_prof)
 
 template <int HD>
-static int launch_ah_hd(const CUtensorMap& tmap, float* ctx, const int64_t* lengths, int B, int L, int nh, cudaStream_t s, float* ctx_lo,
-                        __half* ctx_h, int32_t* status) {
+static int launch_ah_hd(const CUtensorMap& tmap, const __half* qkvh, int Lp, float* ctx, const int64_t* lengths, int B, int L, int nh,
+                        cudaStream_t s, float* ctx_lo, __half* ctx_h, int32_t* status) {
   const size_t smem = AhSmem<HD>::total;
   static int dbg_skip = -1;
   if (dbg_skip < 0) dbg_skip = tools_env_int("M2TTS_ATT_DBG", 0);
   M2_CUDA_OK(allow_smem(attention_h_kernel<HD>, smem));
   dim3 grid((unsigned)(ceil_div(L, 2 * TC_BQ) * nh * B), 1, 1);
-  M2_LAUNCH(M2TTS_STAGE_ATTENTION, attention_h_kernel<HD>, grid, AH_THREADS, smem, s, tmap, ctx, lengths, B, L, nh, ctx_lo, ctx_h,
+  M2_LAUNCH(M2TTS_STAGE_ATTENTION, attention_h_kernel<HD>, grid, AH_THREADS, smem, s, tmap, qkvh, Lp, ctx, lengths, B, L, nh, ctx_lo, ctx_h,
             tools_env_int("M2TTS_LIN_PROF_STAGE", -1) >= 0 ? nullptr : g_ws_prof, dbg_skip, status);      // the buffer belongs to tools/lin_prof.py then
   return M2TTS_OK;
 }
@@ -426,11 +559,12 @@ int launch_attention_h(const void* qkvh, float* ctx, const int64_t* lengths, int
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   M2_REQUIRE(r == CUDA_SUCCESS, M2TTS_E_CUDA, "attention_h: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  const __half* qh = reinterpret_cast<const __half*>(qkvh);
   switch (hd) {
-    case 16: return launch_ah_hd<16>(tmap, ctx, lengths, B, L, nh, s, ctx_lo, ctx_h, status);
-    case 32: return launch_ah_hd<32>(tmap, ctx, lengths, B, L, nh, s, ctx_lo, ctx_h, status);
-    case 48: return launch_ah_hd<48>(tmap, ctx, lengths, B, L, nh, s, ctx_lo, ctx_h, status);
-    default: return launch_ah_hd<64>(tmap, ctx, lengths, B, L, nh, s, ctx_lo, ctx_h, status);
+    case 16: return launch_ah_hd<16>(tmap, qh, Lp, ctx, lengths, B, L, nh, s, ctx_lo, ctx_h, status);
+    case 32: return launch_ah_hd<32>(tmap, qh, Lp, ctx, lengths, B, L, nh, s, ctx_lo, ctx_h, status);
+    case 48: return launch_ah_hd<48>(tmap, qh, Lp, ctx, lengths, B, L, nh, s, ctx_lo, ctx_h, status);
+    default: return launch_ah_hd<64>(tmap, qh, Lp, ctx, lengths, B, L, nh, s, ctx_lo, ctx_h, status);
   }
 }
 

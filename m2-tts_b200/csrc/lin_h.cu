@@ -506,7 +506,7 @@ int launch_linear_h(const void* a_planes, const void* w_planes, const LinHParams
   a.bias = q.bias; a.relu = q.relu; a.residual = q.residual; a.ldr = q.ldr; a.y = q.y; a.ldy = q.ldy;
   a.y_planes = (__half*)q.y_planes; a.qkvh = (__half*)q.qkvh; a.plane_stride = q.plane_stride;
   a.L = q.L; a.nh = q.nh; a.hd = q.hd; a.Lp = q.Lp; a.qscale = q.qscale; a.mode = q.mode;
-  { static int ps = -2; if (ps == -2) ps = tools_env_int("M2TTS_LIN_PROF_STAGE", -1); a.prof = (ps < 0 || ps == stage) ? g_ws_prof : nullptr; }
+  { static int ps = -2; if (ps == -2) ps = tools_env_int("M2TTS_LIN_PROF_STAGE", -1); a.prof = (ps >= 0 && ps == stage) ? g_ws_prof : nullptr; }
   { static int dbg = -1; if (dbg < 0) dbg = tools_env_int("M2TTS_LIN_DBG", 0); a.dbg = dbg; }
   a.status = q.status;
   const size_t a_stage = (size_t)2 * a.kboxes * LH_BM * 64, w_bytes = (size_t)a.kboxes * 2 * a.N * 64;

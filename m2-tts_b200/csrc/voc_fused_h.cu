@@ -344,6 +344,9 @@ voc_stage_fused_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const Fused
         const int i = 128 * h + m;
         const int t = Ts + i;
         const float keep = (t >= 0 && t < a.L_out) ? 1.f : 0.f;
+        // rows 0 and UROWS - 1 of V are computed from the two U rows outside the tile (never written: whatever shared memory
+        // held) and only feed output rows the tile discards (ILO >= 2): they must not raise the range flag
+        bool bad_v = false;
 #pragma unroll
         for (int c0 = cg0; c0 < cg0 + CG; c0 += 16) {
           float v[16];
@@ -353,12 +356,13 @@ voc_stage_fused_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const Fused
 #pragma unroll
           for (int j8 = 0; j8 < 2; ++j8) {
             uint4 hi, lo;
-            fh_split8(v + 8 * j8, hi, lo, bad);
+            fh_split8(v + 8 * j8, hi, lo, bad_v);
             const uint32_t off = fh_swz64(i + 1, (c0 >> 3) + j8);
             *reinterpret_cast<uint4*>(Vb + off) = hi;
             *reinterpret_cast<uint4*>(Vb + K::UPL + off) = lo;
           }
         }
+        bad |= bad_v && i >= 1 && i <= K::UROWS - 2;
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -256,15 +256,19 @@ voc_res_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         if (a.out_h != nullptr) {
           // planes: y overwrites this thread's own residual chunks in the input slot (same swizzled addresses); the rows
           // leave as two TMA stores below (thread-per-row global stores touch 32 lines per instruction: 0.2 ms)
+          // (rows 0 and 127 are computed from the two V rows outside the tile — never written — and are not stored: they
+          // must not raise the range flag)
           uint8_t* Xw = gbase + K::O_X + (uint32_t)(it & 1) * 2 * K::XPL;
+          bool bad_y = false;
 #pragma unroll
           for (int j8 = 0; j8 < 2; ++j8) {
             uint4 hi, lo;
-            rh_split8(y + 8 * j8, hi, lo, bad);
+            rh_split8(y + 8 * j8, hi, lo, bad_y);
             const uint32_t off = rh_swz128(m + 1, (c0 >> 3) + j8);
             *reinterpret_cast<uint4*>(Xw + off) = hi;
             *reinterpret_cast<uint4*>(Xw + K::XPL + off) = lo;
           }
+          bad |= bad_y && m >= 1 && m <= K::NOUT;
         } else if (inside && m >= 1 && m < 1 + K::NOUT) {
           const size_t o = ((size_t)b * a.L + t) * C + c0;
           float4* op = reinterpret_cast<float4*>(a.out_f + o);

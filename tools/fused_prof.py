@@ -1,4 +1,5 @@
 """Bring-up helper (GPU box): phase timestamps of the fused vocoder stage (CTA 0, context 0)."""
+import _env  # noqa: F401  (selects libm2tts_b200_tools.so)
 import ctypes as C
 import sys
 from pathlib import Path
@@ -6,8 +7,7 @@ ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT / "m2-tts_b200" / "src"))
 import torch
 from models import _native as nat
-lib = nat.lib()
-lib.m2tts_vocoder_stage_fused_set_prof.argtypes = [C.c_void_p]
+lib = nat.tools_lib()
 for Cc, final in ((32, False), (16, True)):
     B, L = 64, (55136 if Cc == 32 else 110272)
     g = torch.Generator().manual_seed(1)

@@ -1,6 +1,7 @@
 """Bring-up helper (GPU box): phase timestamps of the persistent linear kernel's first epilogue warp (CTA 0), per unit (= one
 N pass of one 128-row tile). M2TTS_LIN_PROF_STAGE=<stage id> selects the layer (2 ln_qkv, 4 out_proj, 5 ffn1, 6 ffn2, 7 ln_proj;
 see include/m2tts_b200.h); the last launch of that stage in one decoder call is reported."""
+import _env  # noqa: F401  (selects libm2tts_b200_tools.so)
 import ctypes as C
 import sys
 from pathlib import Path
@@ -9,8 +10,7 @@ for p in (str(ROOT), str(ROOT / "m2-tts_b200" / "src")):
     sys.path.insert(0, p)
 import torch
 from models import _native as nat
-lib = nat.lib()
-lib.m2tts_attention_set_prof.argtypes = [C.c_void_p]
+lib = nat.tools_lib()
 # one QKV-shaped GEMM through the layernorm_proj entry (mode 0) is not mode 3; run a full layer and keep the QKV launch by
 # stopping after it: simplest is to run the decoder and read the buffer after the first layer's QKV only -> we use a 1-layer model
 from models.tts_model import M2TTSModel

@@ -1,11 +1,12 @@
 """Bring-up tool (GPU box): cycles per tcgen05.mma kind::tf32 (M=128, K=8) for the operand configurations the kernels use."""
+import _env  # noqa: F401  (selects libm2tts_b200_tools.so)
 import sys
 from pathlib import Path
 ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT / "m2-tts_b200" / "src"))
 import torch
 from models import _native as nat
-lib = nat.lib()
+lib = nat.tools_lib()
 out = torch.zeros(2, dtype=torch.int64, device="cuda")
 names = {0: "A smem K-major SW128 / B K-major noswz", 1: "A,B smem MN-major SW128-32B", 2: "A TMEM / B K-major SW128",
          3: "A smem K-major SW64 / B K-major noswz", 4: "A,B smem K-major SW128", 5: "kind::f16, A,B smem K-major SW128",

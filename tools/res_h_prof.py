@@ -1,4 +1,5 @@
 """Bring-up helper (GPU box): phase timestamps of the fused ResBlock kernel (voc_res_h.cu), CTA 0, first epilogue warp, per tile."""
+import _env  # noqa: F401  (selects libm2tts_b200_tools.so)
 import ctypes as C
 import sys
 from pathlib import Path
@@ -9,8 +10,7 @@ import torch
 from models import _native as nat
 from models.tts_model import M2TTSModel
 from models.stage_configs import STAGE_KWARGS
-lib = nat.lib()
-lib.m2tts_attention_set_prof.argtypes = [C.c_void_p]
+lib = nat.tools_lib()
 torch.manual_seed(1234)
 m = M2TTSModel(**STAGE_KWARGS["stage2"]).eval().cuda()
 mel = torch.randn(64, 3446, 80, device="cuda").transpose(1, 2)

@@ -1,5 +1,6 @@
 """Bring-up tool (GPU box): does a K-major swizzled UMMA A operand accept a descriptor start address that is
 moved by whole rows inside the swizzle pattern?  usage: python tests/rowshift_probe_run.py all | <rowbytes> <K> <shift> <bo>"""
+import _env  # noqa: F401  (selects libm2tts_b200_tools.so)
 import ctypes as C
 import subprocess
 import sys
@@ -12,7 +13,7 @@ sys.path.insert(0, str(ROOT / "m2-tts_b200" / "src"))
 def run(rowbytes, K, shift, bo, N=32, rows_total=144):
     import torch
     from models import _native as nat
-    lib = nat.lib()
+    lib = nat.tools_lib()
     fn = lib.m2tts_rowshift_probe
     fn.restype = C.c_int
     fn.argtypes = [C.c_void_p] * 3 + [C.c_int] * 6 + [C.c_void_p]

@@ -1,4 +1,5 @@
 """Bring-up helper (GPU box): per-tile wait / epilogue cycles of the tap-GEMM convolution (CTA 0, epilogue group 0)."""
+import _env  # noqa: F401  (selects libm2tts_b200_tools.so)
 import ctypes as C
 import sys
 from pathlib import Path
@@ -6,8 +7,7 @@ ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT / "m2-tts_b200" / "src"))
 import torch
 from models import _native as nat
-lib = nat.lib()
-lib.m2tts_tapgemm_set_prof.argtypes = [C.c_void_p]
+lib = nat.tools_lib()
 for (CI, CO, L, res) in ((64, 64, 55136, True), (64, 64, 55136, False), (128, 128, 13784, True)):
     B = 64
     x = torch.randn(B, CI, L, device="cuda")

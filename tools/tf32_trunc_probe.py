@@ -1,5 +1,6 @@
 """Bring-up tool (GPU box): does tcgen05.mma kind::tf32 TRUNCATE fp32 operands (ignore the low 13 mantissa bits) or round
 them? D = A @ B^T with B = identity-like ones and A holding values whose truncation and rounding differ."""
+import _env  # noqa: F401  (selects libm2tts_b200_tools.so)
 import ctypes as C
 import sys
 from pathlib import Path
@@ -7,7 +8,7 @@ ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT / "m2-tts_b200" / "src"))
 import torch
 from models import _native as nat
-lib = nat.lib()
+lib = nat.tools_lib()
 K, N, rows = 32, 32, 144
 A = torch.zeros(rows, K)
 vals = [1 + 2 ** -10 + 2 ** -11 + 2 ** -12, 1 + 2 ** -11, 1 + 2 ** -11 + 2 ** -20, -(1 + 2 ** -10 + 2 ** -11 + 2 ** -13), 3.1415926, 1e-3 * 1.2345678]

@@ -1,4 +1,5 @@
 """Bring-up tool (GPU box): kind::f16 UMMA operand layouts. usage: python tests/umma_probe_f16_run.py all | <mode> <N> <K>"""
+import _env  # noqa: F401  (selects libm2tts_b200_tools.so)
 import subprocess
 import sys
 from pathlib import Path
@@ -10,7 +11,7 @@ sys.path.insert(0, str(ROOT / "m2-tts_b200" / "src"))
 def run(mode, N, K):
     import torch
     from models import _native as nat
-    lib = nat.lib()
+    lib = nat.tools_lib()
     g = torch.Generator().manual_seed(1)
     A = (torch.randint(-8, 9, (128, K), generator=g).float() / 4).cuda()
     Bm = (torch.randint(-8, 9, (N, K), generator=g).float() / 4).cuda()

@@ -1,5 +1,6 @@
 """Run one tcgen05 operand-layout configuration of m2tts_umma_probe (GPU box bring-up tool).
 usage: python tests/umma_probe_run.py <config-name>  |  all  (spawns one process per config)"""
+import _env  # noqa: F401  (selects libm2tts_b200_tools.so)
 import ctypes as C
 import subprocess
 import sys
@@ -60,7 +61,7 @@ def arr(d):
 def run(name):
     import torch
     from models import _native as nat
-    lib = nat.lib()
+    lib = nat.tools_lib()
     lib.m2tts_umma_probe.restype = C.c_int
     lib.m2tts_umma_probe.argtypes = [C.c_void_p] * 3 + [C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p]
     g = torch.Generator().manual_seed(1)

@@ -1,12 +1,13 @@
 """Bring-up helper (GPU box): time the upsampling kernel (voc_up_h.cu) with parts switched off.
 usage: python tools/up_h_prof.py [CI] [L] [B]"""
+import _env  # noqa: F401  (selects libm2tts_b200_tools.so)
 import sys
 from pathlib import Path
 ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT / "m2-tts_b200" / "src"))
 import torch
 from models import _native as nat
-lib = nat.lib()
+lib = nat.tools_lib()
 CI = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 L = int(sys.argv[2]) if len(sys.argv) > 2 else 13784
 B = int(sys.argv[3]) if len(sys.argv) > 3 else 64
