@@ -131,7 +131,7 @@ attention_h_kernel(const __grid_constant__ CUtensorMap tmap, const __half* __res
   const uint32_t tmem_slot = bar_ve + 8 * AH_STAGES;
   const uint32_t bar_qh = tmem_slot + 8;                       // q_hi[2]: Q_hi of tile x has been written to TMEM (8 softmax warps)
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   // 1-D grid, longest first: all CTAs with two query tiles, then (odd tile count) the single-tile CTAs, which take about
   // 0.6 of the time and fill the last wave
   const int n_tiles_q = (L + TC_BQ - 1) / TC_BQ, npf = n_tiles_q >> 1, n_long = npf * nh * B;
@@ -173,6 +173,7 @@ attention_h_kernel(const __grid_constant__ CUtensorMap tmap, const __half* __res
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);      // warp-uniform for ptxas (uniform-register UMMA operands)
 
   if (warp == 0) {
     if (lane == 0) {
@@ -509,6 +510,427 @@ attention_h_kernel(const __grid_constant__ CUtensorMap tmap, const __half* __res
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// attention_h2_kernel — same tiles, operands, TMEM map and UMMA sequence as attention_h_kernel; the SOFTMAX side is reorganised:
+//   * the two softmax warpgroups of a query tile no longer share a key tile (32 columns each, row maxima exchanged through
+//     shared memory at a named barrier, the two query tiles taking turns in the exponential phase): warpgroup w owns the key
+//     tiles t = w (mod 2) and their score buffer w, a thread = one query row over all 64 keys. Nothing is exchanged inside a
+//     tile, and while one warpgroup waits for the P V / Q K^T of its buffer the other one is in the middle of its tile, so the
+//     four warps of a scheduler sit in different phases without being forced to (ncu on v1: 57 % of the executed instructions
+//     were not softmax arithmetic — spin loops, barrier traffic, register moves; stall_barrier + stall_wait 33 % of samples);
+//   * the per-row reference maximum m_ref (lazy rescaling) lives in shared memory; the DECISION for tile t (keep m_ref or raise
+//     it and rescale O) is handed from the warpgroup of tile t-1 to the warpgroup of tile t through a one-directional named
+//     barrier (bar.arrive by the producer right after its decision, bar.sync by the consumer right before its own): the chain
+//     per tile is load + maximum + decision (~300 cycles), the exponentials run outside it. Each warpgroup keeps its own
+//     partial row sum in the scale of the m_ref it last saw and rescales it when it sees a new one;
+//   * within a tile the exponentials of 16-key group g+1 are issued between the split arithmetic of group g (MUFU and ALU / FMA
+//     work interleaved in one instruction stream); groups 2, 3 come from the registers of the maximum pass, groups 0, 1 are
+//     re-read from TMEM (32 score registers live at a time);
+//   * P(t)-ready has one mbarrier per warpgroup (alternating arrivals must not mix in one phase); the last P V also commits to
+//     a single-phase barrier for the final read of O (a parity wait is only exact for a waiter at most one phase behind).
+// Reference: components.py:75-87.
+template <int HD>
+__global__ void __launch_bounds__(AH_THREADS, 1)
+attention_h2_kernel(const __grid_constant__ CUtensorMap tmap, const __half* __restrict__ qkvh, int Lp, float* __restrict__ ctx,
+                    const int64_t* __restrict__ lengths, int B, int L, int nh, float* __restrict__ ctx_lo, __half* __restrict__ ctx_h,
+                    long long* __restrict__ prof, int dbg_skip, int32_t* __restrict__ status) {
+  static_assert(HD % 16 == 0 && HD >= 16 && HD <= 64, "16-bit split attention: head_dim in {16,32,48,64}");
+  constexpr uint32_t BOX = AhSmem<HD>::box;
+  constexpr int KSTEPS_D = HD / 16;
+  constexpr bool QT = (128 + 2 * HD + HD / 2) <= 256;             // Q_hi as a TMEM A operand (head_dim <= 48), else from shared memory
+  constexpr uint32_t IDESC_QK1 = ah_idesc(TC_BQ, TC_BK, 1);
+  constexpr uint32_t IDESC_QKT = ah_idesc2(TC_BQ, TC_BK, 0, 1);
+  constexpr uint32_t IDESC_PV2 = ah_idesc(TC_BQ, 2 * HD, 0);
+  constexpr uint32_t IDESC_PV1 = ah_idesc(TC_BQ, HD, 0);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ = sbase;
+  const uint32_t sK = sbase + AhSmem<HD>::off_k;
+  const uint32_t sV = sbase + AhSmem<HD>::off_v;
+  const uint32_t sBar = sbase + AhSmem<HD>::off_bar;
+  // barriers: q_full[2] s_full[2 tiles][2 buffers] p_ready[2 tiles][2 warpgroups] pv_done[2] o_done[2] | k_full[S] k_empty[S]
+  // v_full[S] v_empty[S] | tmem slot | q_hi[2]
+  const uint32_t bar_qf = sBar, bar_sf = sBar + 16, bar_pr = sBar + 48, bar_pv = sBar + 80, bar_done = sBar + 96;
+  const uint32_t bar_kf = sBar + 112, bar_ke = bar_kf + 8 * AH_STAGES, bar_vf = bar_ke + 8 * AH_STAGES, bar_ve = bar_vf + 8 * AH_STAGES;
+  const uint32_t tmem_slot = bar_ve + 8 * AH_STAGES;
+  const uint32_t bar_qh = tmem_slot + 8;
+
+  // warp index as a shuffle broadcast: ptxas then knows it is warp-uniform, the role branches are uniform branches and the
+  // issuer's descriptor arithmetic can live in uniform registers
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+  const int n_tiles_q = (L + TC_BQ - 1) / TC_BQ, npf = n_tiles_q >> 1, n_long = npf * nh * B;
+  int qx, bh;
+  if ((int)blockIdx.x < n_long) { bh = (int)blockIdx.x / npf; qx = (int)blockIdx.x % npf; }
+  else { bh = (int)blockIdx.x - n_long; qx = npf; }
+  const int q0 = qx * (2 * TC_BQ), head = bh % nh, b = bh / nh;
+  const int ntq = q0 + TC_BQ < L ? 2 : 1;
+
+  int Leff = L;
+  bool all_masked = false;
+  if (lengths != nullptr) {
+    const long long len = lengths[b];
+    if (len <= 0) all_masked = true;
+    else if (len < L) Leff = (int)len;
+  }
+  const int nkt = (Leff + TC_BK - 1) / TC_BK;
+  const int plane = B * nh * HD;
+  const int row_q = (b * nh + head) * HD;
+
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_qf + 8 * i, 1); mbar_init(bar_sf + 16 * i, 1); mbar_init(bar_sf + 16 * i + 8, 1);
+      mbar_init(bar_pr + 16 * i, 4); mbar_init(bar_pr + 16 * i + 8, 4); mbar_init(bar_pv + 8 * i, 1); mbar_init(bar_done + 8 * i, 1);
+      mbar_init(bar_qh + 8 * i, 8);
+    }
+    for (int i = 0; i < AH_STAGES; ++i) {
+      mbar_init(bar_kf + 8 * i, 1); mbar_init(bar_ke + 8 * i, (uint32_t)ntq); mbar_init(bar_vf + 8 * i, 1); mbar_init(bar_ve + 8 * i, (uint32_t)ntq);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+  }
+  if (warp == 0) {
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(AH_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== loader =====
+      for (int x = 0; x < ntq; ++x) {
+        mbar_expect_tx(bar_qf + 8 * x, QT ? AhSmem<HD>::q_bytes / 2 : AhSmem<HD>::q_bytes);
+        for (int h = QT ? 1 : 0; h < 2; ++h)
+          for (int j = 0; j < 2; ++j)
+            tma_load_2d(sQ + (uint32_t)x * AhSmem<HD>::q_bytes + (h * 2 + j) * BOX, &tmap, q0 + x * TC_BQ + j * 64, h * plane + row_q,
+                        bar_qf + 8 * x);
+      }
+      for (int t = 0; t < nkt; ++t) {
+        const int st = t % AH_STAGES;
+        const uint32_t par_prev = (uint32_t)(((t / AH_STAGES) - 1) & 1);
+        if (t >= AH_STAGES) mbar_wait(bar_ke + 8 * st, par_prev);
+        mbar_expect_tx(bar_kf + 8 * st, AhSmem<HD>::kv_bytes);
+        for (int h = 0; h < 2; ++h)
+          tma_load_2d(sK + (uint32_t)st * AhSmem<HD>::kv_bytes + h * BOX, &tmap, t * TC_BK, (2 + h) * plane + row_q, bar_kf + 8 * st);
+        if (t >= AH_STAGES) mbar_wait(bar_ve + 8 * st, par_prev);
+        mbar_expect_tx(bar_vf + 8 * st, AhSmem<HD>::kv_bytes);
+        for (int h = 0; h < 2; ++h)
+          tma_load_2d(sV + (uint32_t)st * AhSmem<HD>::kv_bytes + h * BOX, &tmap, t * TC_BK, (4 + h) * plane + row_q, bar_vf + 8 * st);
+      }
+    }
+  } else if ((warp == 1 || warp == 2) && warp - 1 < ntq) {
+    // ===== UMMA issuer of query tile x (whole warp, one elected lane issues) =====
+    const int x = warp - 1;
+    auto issue_qk = [&](int st, int buf) {
+      if (dbg_skip & 1) return;      // bring-up timing experiment (M2TTS_ATT_DBG): results invalid
+      const uint32_t q = sQ + (uint32_t)x * AhSmem<HD>::q_bytes, k = sK + (uint32_t)st * AhSmem<HD>::kv_bytes;
+      const uint32_t d = tmem_base + (uint32_t)x * AH_COL_TILE + AH_COL_S + (uint32_t)buf * 64u;
+      if (QT) {
+        const uint32_t qt = tmem_base + (uint32_t)x * AH_COL_TILE + AH_COL_Q;
+#pragma unroll
+        for (int ks = 0; ks < KSTEPS_D; ++ks) {
+          const uint64_t khi = umma_desc(k + ks * 2048u, BOX, 1024u, 2u), klo = umma_desc(k + BOX + ks * 2048u, BOX, 1024u, 2u);
+          umma_f16_ts_w(d, qt + ks * 8, khi, IDESC_QKT, ks ? 1u : 0u);
+          umma_f16_ts_w(d, qt + ks * 8, klo, IDESC_QKT, 1u);
+          umma_f16_ss_w(d, umma_desc(q + 2 * BOX + ks * 2048u, BOX, 1024u, 2u), khi, IDESC_QK1, 1u);
+        }
+        return;
+      }
+#pragma unroll
+      for (int term = 0; term < 3; ++term) {
+        const uint32_t qa = q + (term == 2 ? 2 * BOX : 0u), kb = k + (term == 1 ? BOX : 0u);
+#pragma unroll
+        for (int ks = 0; ks < KSTEPS_D; ++ks)
+          umma_f16_ss_w(d, umma_desc(qa + ks * 2048u, BOX, 1024u, 2u), umma_desc(kb + ks * 2048u, BOX, 1024u, 2u), IDESC_QK1,
+                        (term | ks) ? 1u : 0u);
+      }
+    };
+    auto issue_pv = [&](int st, int buf, uint32_t accumulate) {
+      if (dbg_skip & 2) return;
+      const uint32_t v = sV + (uint32_t)st * AhSmem<HD>::kv_bytes;
+      const uint32_t tb = tmem_base + (uint32_t)x * AH_COL_TILE;
+      const uint32_t pb = tb + AH_COL_S + (uint32_t)buf * 64u;
+#pragma unroll
+      for (int ks = 0; ks < TC_BK / 16; ++ks)
+        umma_f16_ts_w(tb + AH_COL_O, pb + ks * 16, umma_desc(v + ks * 32u, 16u, 1024u, 2u), IDESC_PV2, ks ? 1u : accumulate);
+#pragma unroll
+      for (int ks = 0; ks < TC_BK / 16; ++ks)
+        umma_f16_ts_w(tb + AH_COL_O, pb + ks * 16 + 8, umma_desc(v + ks * 32u, 16u, 1024u, 2u), IDESC_PV1, 1u);
+    };
+    for (int t = 0; t < 2 && t < nkt; ++t) {      // prologue: the scores of key tiles 0 and 1
+      mbar_wait(bar_kf + 8 * t, 0);
+      if (t == 0) {
+        mbar_wait(bar_qf + 8 * x, 0);
+        if (QT) mbar_wait(bar_qh + 8 * x, 0);
+      }
+      tc_fence_after();
+      issue_qk(t, t);
+      tc_commit_w(bar_sf + 16 * x + 8 * t);
+      tc_commit_w(bar_ke + 8 * t);
+    }
+    for (int t = 0; t < nkt; ++t) {
+      const int st = t % AH_STAGES, s2 = (t + 2) % AH_STAGES, buf = t & 1;
+      mbar_wait(bar_pr + 16 * x + 8 * buf, (uint32_t)((t >> 1) & 1));      // P(x,t) is in TMEM (and O has been rescaled if needed)
+      mbar_wait(bar_vf + 8 * st, (uint32_t)((t / AH_STAGES) & 1));
+      tc_fence_after();
+      issue_pv(st, buf, t > 0 ? 1u : 0u);
+      tc_commit_w(bar_pv + 8 * x);
+      if (t == nkt - 1) tc_commit_w(bar_done + 8 * x);
+      tc_commit_w(bar_ve + 8 * st);
+      if (t + 2 < nkt) {                                      // score buffer `buf` is free again once PV(x,t) has read P
+        mbar_wait(bar_kf + 8 * s2, (uint32_t)(((t + 2) / AH_STAGES) & 1));
+        tc_fence_after();
+        issue_qk(s2, buf);
+        tc_commit_w(bar_sf + 16 * x + 8 * buf);
+        tc_commit_w(bar_ke + 8 * s2);
+      }
+    }
+  } else if (warp >= 4 && (((warp - 4) >> 2) & 1) < ntq) {
+    // ===== softmax warpgroups: query tile x has two (warps 4-7 / 12-15 for tile A, 8-11 / 16-19 for tile B); warpgroup wg owns the
+    // key tiles t = wg (mod 2) and score buffer wg; thread = query row = TMEM lane, all 64 keys of the tile =====
+    const int x = ((warp - 4) >> 2) & 1, wg = (warp - 4) >> 3;
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)x * AH_COL_TILE;
+    float* exch = reinterpret_cast<float*>(smem_raw + (sbase - smem_u32(smem_raw)) + AhSmem<HD>::off_exch);
+    float* mref_s = exch + x * 128;               // per-row reference maximum of the running softmax
+    float* lsum_s = exch + 256 + x * 128;         // row sums of warpgroup 1 at the end
+    const int hb = 1 + x * 2;                     // named barriers hb / hb + 1: hand-off of the m_ref decision of even / odd key tiles
+    if (QT) {
+      // Q_hi -> TMEM as the A operand of Q K^T (see attention_h_kernel); this warpgroup writes the d range [wg hd/2, (wg+1) hd/2)
+      const int qi = q0 + x * TC_BQ + row;
+      const __half* qp = qkvh + ((long long)row_q + wg * (HD / 2)) * Lp + qi;
+#pragma unroll
+      for (int c4 = 0; c4 < HD / 16; ++c4) {
+        uint32_t w[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int d = (c4 * 4 + e) * 2;
+          unsigned short lo = 0, hi = 0;
+          if (qi < L) { lo = __half_as_ushort(qp[(long long)d * Lp]); hi = __half_as_ushort(qp[(long long)(d + 1) * Lp]); }
+          w[e] = (uint32_t)lo | ((uint32_t)hi << 16);
+        }
+        ah_st4(t_lane + AH_COL_Q + (uint32_t)(wg * (HD / 4) + c4 * 4), w);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_qh + 8 * x) : "memory");
+    }
+    float m_c = -INFINITY;                                // the m_ref this warpgroup's row sum is scaled to
+    uint64_t l2 = ah_pack(0.f, 0.f);                      // running row sum as a packed pair (even keys, odd keys)
+#ifdef M2TTS_TOOLS
+    const bool pw = prof != nullptr && blockIdx.x == 0 && x == 0 && wg == 0 && row == 0;
+#endif
+    auto mask16 = [&](uint32_t* sv, int k0) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float a = __uint_as_float(sv[j]);
+        if (all_masked) a = (k0 + j < L) ? 0.f : -INFINITY;
+        else if (k0 + j >= Leff) a = -INFINITY;
+        sv[j] = __float_as_uint(a);
+      }
+    };
+    auto max32 = [&](const uint32_t* u, const uint32_t* v) {
+      float mx = ah_max3(__uint_as_float(u[0]), __uint_as_float(u[1]), __uint_as_float(u[2]));
+#pragma unroll
+      for (int j = 3; j < 15; j += 2) mx = ah_max3(mx, __uint_as_float(u[j]), __uint_as_float(u[j + 1]));
+      mx = ah_max3(mx, __uint_as_float(u[15]), __uint_as_float(v[0]));
+#pragma unroll
+      for (int j = 1; j < 15; j += 2) mx = ah_max3(mx, __uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+      return fmaxf(mx, __uint_as_float(v[15]));
+    };
+    auto rescale_l = [&](float m_new) {                   // the row sum follows m_ref (2^-inf = 0 on the first tile: l2 is 0 then)
+      const float a = ws_ex2(m_c - m_new);
+      float la, lb;
+      ah_unpack(l2, la, lb);
+      l2 = ah_pack(la * a, lb * a);
+      m_c = m_new;
+    };
+    for (int t = wg; t < nkt; t += 2) {
+#ifdef M2TTS_TOOLS
+      const bool pt = pw && t >= 8 && t < 72;
+      long long* pp = prof + (pt ? ((t - 8) >> 1) * 8 : 0);
+#endif
+      const uint32_t t_s = t_lane + AH_COL_S + (uint32_t)wg * 64u;      // score buffer of this warpgroup
+      AH_PROF(pt, pp[0] = clock64());
+      mbar_wait(bar_sf + 16 * x + 8 * wg, (uint32_t)((t >> 1) & 1));
+      AH_PROF(pt, pp[1] = clock64());
+      __syncwarp();
+      tc_fence_after();
+      const int kbase = t * TC_BK;
+      const bool need_mask = all_masked || kbase + TC_BK > Leff;      // key padding: only ever in the last key tile
+      // pass 1: row maximum over the 64 keys; the second half of the scores stays in registers
+      uint32_t sa[16], sb[16];
+      tmem_ld16(t_s, sa);
+      tmem_ld16(t_s + 16, sb);
+      tmem_wait_ld();
+      if (need_mask) { mask16(sa, kbase); mask16(sb, kbase + 16); }
+      float mx = max32(sa, sb);
+      tmem_ld16(t_s + 32, sa);
+      tmem_ld16(t_s + 48, sb);
+      tmem_wait_ld();
+      if (need_mask) { mask16(sa, kbase + 32); mask16(sb, kbase + 48); }
+      mx = fmaxf(mx, max32(sa, sb));
+      AH_PROF(pt, pp[2] = clock64());
+      // the decision of tile t-1 (other warpgroup) precedes ours
+      if (t > 0) asm volatile("bar.sync %0, 256;" ::"r"(hb + ((t - 1) & 1)) : "memory");
+      float m_s;
+      if (t == 0) {
+        m_s = mx;
+        mref_s[row] = mx;
+      } else {
+        m_s = mref_s[row];
+        if (__any_sync(0xffffffffu, mx > m_s + 8.0f)) {
+          // lazy rescale: P V(t-1) has landed after this wait (its completion count is t-1 or t here, so the parity test is
+          // exact), P V(t) waits for our P and P V(t+1) for the other warpgroup, which waits for our hand-off: O is quiescent
+          mbar_wait(bar_pv + 8 * x, (uint32_t)((t - 1) & 1));
+          tc_fence_after();
+          const float m_new = fmaxf(m_s, mx);
+          const float alpha = ws_ex2(m_s - m_new);
+#pragma unroll
+          for (int c = 0; c < 2 * HD; c += 16) {
+            uint32_t orr[16];
+            tmem_ld16(t_lane + AH_COL_O + c, orr);
+            tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) orr[j] = __float_as_uint(__uint_as_float(orr[j]) * alpha);
+            tmem_st16(t_lane + AH_COL_O + c, orr);
+          }
+          mref_s[row] = m_new;
+          m_s = m_new;
+        }
+      }
+      asm volatile("bar.arrive %0, 256;" ::"r"(hb + (t & 1)) : "memory");      // hand the decision on to tile t+1
+      if (m_s != m_c) rescale_l(m_s);
+      AH_PROF(pt, pp[3] = clock64());
+      // pass 2: p = 2^(s - m_ref) per 16-key group (= one k-step of P V), written over the group's own score columns as 8 columns
+      // of packed P_hi (p with the low 13 mantissa bits masked off: exact in fp16) and 8 of packed P_lo = fp16(p - P_hi).
+      const uint64_t m2 = ah_pack(m_s, m_s);
+      auto exp_pair = [&](uint32_t* s, int j) {
+        float d0, d1;
+        ah_unpack(ah_sub2(ah_pack(__uint_as_float(s[2 * j]), __uint_as_float(s[2 * j + 1])), m2), d0, d1);
+        s[2 * j] = __float_as_uint(ws_ex2v(d0)); s[2 * j + 1] = __float_as_uint(ws_ex2v(d1));
+      };
+      auto split_pair = [&](const uint32_t* pv, int j, uint32_t* ph, uint32_t* pl) {
+        const float p0 = __uint_as_float(pv[2 * j]), p1 = __uint_as_float(pv[2 * j + 1]);
+        const uint64_t pp2 = ah_pack(p0, p1);
+        l2 = ah_add2(l2, pp2);
+        const float h0 = __uint_as_float(__float_as_uint(p0) & 0xFFFFE000u), h1 = __uint_as_float(__float_as_uint(p1) & 0xFFFFE000u);
+        float r0, r1;
+        ah_unpack(ah_sub2(pp2, ah_pack(h0, h1)), r0, r1);
+        ph[j] = ah_cvt2(h0, h1);
+        pl[j] = ah_cvt2(r0, r1);
+      };
+      // exponentials of group `nx` interleaved with the split arithmetic of group `cur` (already exponentiated), which is then
+      // stored at column offset col
+      auto exp_and_split = [&](uint32_t* nx, const uint32_t* cur, uint32_t col) {
+        uint32_t ph[8], pl[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (nx != nullptr) exp_pair(nx, j);
+          if (cur != nullptr) split_pair(cur, j, ph, pl);
+        }
+        if (cur != nullptr) {
+          ah_st8(t_s + col, ph);
+          ah_st8(t_s + col + 8, pl);
+        }
+      };
+      exp_and_split(sa, nullptr, 0);            // group 2
+      exp_and_split(sb, sa, 32);                // group 3 | group 2
+      uint32_t sc[16], sd[16];
+      tmem_ld16(t_s, sc);
+      tmem_ld16(t_s + 16, sd);
+      tmem_wait_ld();
+      if (need_mask) { mask16(sc, kbase); mask16(sd, kbase + 16); }
+      exp_and_split(sc, sb, 48);                // group 0 | group 3
+      exp_and_split(sd, sc, 0);                 // group 1 | group 0
+      exp_and_split(nullptr, sd, 16);           //         | group 1
+      AH_PROF(pt, pp[4] = clock64());
+      tmem_wait_st();
+      AH_PROF(pt, pp[5] = clock64());
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_pr + 16 * x + 8 * wg) : "memory");
+    }
+    // the warpgroup that did not own the last key tile takes over its decision (the final m_ref)
+    if (((nkt - 1) & 1) != wg) {
+      asm volatile("bar.sync %0, 256;" ::"r"(hb + ((nkt - 1) & 1)) : "memory");
+      const float m_s = mref_s[row];
+      if (m_s != m_c) rescale_l(m_s);
+    }
+    float l_run;
+    {
+      float la, lb;
+      ah_unpack(l2, la, lb);
+      l_run = la + lb;
+      if (wg == 1) lsum_s[row] = l_run;
+      asm volatile("bar.sync %0, 256;" ::"r"(5 + x) : "memory");
+      if (wg == 0) l_run += lsum_s[row];
+    }
+    if (wg == 0) {
+      mbar_wait(bar_done + 8 * x, 0);     // the last PV has landed: O is complete
+      __syncwarp();
+      tc_fence_after();
+      float o[HD];
+#pragma unroll
+      for (int c = 0; c < HD; c += 16) {
+        uint32_t orr[16], or2[16];
+        tmem_ld16(t_lane + AH_COL_O + c, orr);
+        tmem_ld16(t_lane + AH_COL_O + HD + c, or2);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) o[c + j] = __uint_as_float(orr[j]) + __uint_as_float(or2[j]);
+      }
+      const int qi = q0 + x * TC_BQ + row;
+      if (qi < L) {
+        const float inv = 1.0f / l_run;
+        float* dst = ctx + ((long long)b * L + qi) * (nh * HD) + head * HD;
+        if (ctx_h != nullptr) {   // fp16 hi/lo planes [2][B*L][nh*HD] for the 16-bit split out_proj (lin_h.cu)
+          __half* dh = ctx_h + ((long long)b * L + qi) * (nh * HD) + head * HD;
+          __half* dl = dh + (long long)B * L * (nh * HD);
+          bool bad = false;
+#pragma unroll
+          for (int c = 0; c < HD; c += 8) {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) h_split2(o[c + 2 * e] * inv, o[c + 2 * e + 1] * inv, hi[e], lo[e], bad);
+            *reinterpret_cast<uint4*>(dh + c) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(dl + c) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          }
+          h_flag(bad, status);
+        } else if (ctx_lo == nullptr) {
+#pragma unroll
+          for (int c = 0; c < HD; c += 4)
+            *reinterpret_cast<float4*>(dst + c) = make_float4(o[c] * inv, o[c + 1] * inv, o[c + 2] * inv, o[c + 3] * inv);
+        } else {   // TF32 hi/lo planes for the tensor-core out_proj
+          float* dlo = ctx_lo + ((long long)b * L + qi) * (nh * HD) + head * HD;
+#pragma unroll
+          for (int c = 0; c < HD; c += 4) {
+            float h[4], l[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { const float v = o[c + e] * inv; h[e] = __uint_as_float(tf32_hi(v)); l[e] = __uint_as_float(tf32_hi(v - h[e])); }
+            *reinterpret_cast<float4*>(dst + c) = make_float4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<float4*>(dlo + c) = make_float4(l[0], l[1], l[2], l[3]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(AH_TMEM_COLS) : "memory");
+  }
+}
+
 typedef CUresult (*EncodeTiledFnH)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -532,10 +954,19 @@ static int launch_ah_hd(const CUtensorMap& tmap, const __half* qkvh, int Lp, flo
   const size_t smem = AhSmem<HD>::total;
   static int dbg_skip = -1;
   if (dbg_skip < 0) dbg_skip = tools_env_int("M2TTS_ATT_DBG", 0);
-  M2_CUDA_OK(allow_smem(attention_h_kernel<HD>, smem));
+  static int ver = -1;
+  if (ver < 0) ver = tools_env_int("M2TTS_ATT_V", 2);      // tools build: 1 = attention_h_kernel (A/B measurements)
   dim3 grid((unsigned)(ceil_div(L, 2 * TC_BQ) * nh * B), 1, 1);
-  M2_LAUNCH(M2TTS_STAGE_ATTENTION, attention_h_kernel<HD>, grid, AH_THREADS, smem, s, tmap, qkvh, Lp, ctx, lengths, B, L, nh, ctx_lo, ctx_h,
-            tools_env_int("M2TTS_LIN_PROF_STAGE", -1) >= 0 ? nullptr : g_ws_prof, dbg_skip, status);      // the buffer belongs to tools/lin_prof.py then
+  long long* prof = tools_env_int("M2TTS_LIN_PROF_STAGE", -1) >= 0 ? nullptr : g_ws_prof;      // the buffer belongs to tools/lin_prof.py then
+  if (ver == 1) {
+    M2_CUDA_OK(allow_smem(attention_h_kernel<HD>, smem));
+    M2_LAUNCH(M2TTS_STAGE_ATTENTION, attention_h_kernel<HD>, grid, AH_THREADS, smem, s, tmap, qkvh, Lp, ctx, lengths, B, L, nh, ctx_lo, ctx_h,
+              prof, dbg_skip, status);
+  } else {
+    M2_CUDA_OK(allow_smem(attention_h2_kernel<HD>, smem));
+    M2_LAUNCH(M2TTS_STAGE_ATTENTION, attention_h2_kernel<HD>, grid, AH_THREADS, smem, s, tmap, qkvh, Lp, ctx, lengths, B, L, nh, ctx_lo, ctx_h,
+              prof, dbg_skip, status);
+  }
   return M2TTS_OK;
 }
 

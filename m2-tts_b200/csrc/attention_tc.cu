@@ -57,7 +57,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_co
   const uint32_t bar_q = sBar, bar_k = sBar + 8, bar_v = sBar + 16, bar_s = sBar + 24, bar_o = sBar + 32;
   const uint32_t tmem_slot = sBar + 40;
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int q0 = blockIdx.x * TC_BQ, head = blockIdx.y, b = blockIdx.z;
 
   int Leff = L;
@@ -89,6 +89,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_co
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);      // warp-uniform for ptxas (uniform-register UMMA operands)
   const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);  // this warp's 32 TMEM lanes
 
   auto load_kv = [&](uint32_t sdst, uint32_t bar, int which_hi, int k0) {
@@ -319,7 +320,7 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_co
   const uint32_t bar_sf = sBar + 80, bar_pr = sBar + 96, bar_or = sBar + 112, bar_of = sBar + 128;
   const uint32_t tmem_slot = sBar + 144;
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   const int q0 = blockIdx.x * (2 * TC_BQ), head = blockIdx.y, b = blockIdx.z;
 
   int Leff = L;
@@ -353,6 +354,7 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap tmap_qk, const __grid_co
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);      // warp-uniform for ptxas (uniform-register UMMA operands)
 
   if (warp == 0) {
     if (lane == 0) {

@@ -121,7 +121,7 @@ tapgemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const TapG
   const uint32_t tmem_slot = bar_acce + 8 * NB;
   const uint32_t w_plane_bytes = (uint32_t)a.rows_total * 64u;
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   // tile schedule: this CTA owns output-channel tile `ntile` and every cpg-th (utterance, position) tile
   const int ntile = blockIdx.x % a.n_tiles;
   const int first = blockIdx.x / a.n_tiles;
@@ -147,6 +147,7 @@ tapgemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const TapG
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);      // warp-uniform for ptxas (uniform-register UMMA operands)
   const float* wsrc = a.wblob + (size_t)ntile * a.n_chunks * (size_t)(2 * a.rows_total * 16);
 
   if (warp == 0) {

@@ -77,7 +77,7 @@ lin_h_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
   const uint32_t bar_af = sBar, bar_ae = sBar + 32, bar_cf = sBar + 64, bar_ce = sBar + 80, bar_w = sBar + 96, bar_rs = sBar + 104, tmem_slot = sBar + 112;
   float* bias_s = reinterpret_cast<float*>(gbase + (sBias - sbase));
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   const int m_tiles = a.tpu > 0 ? (a.R / a.L) * a.tpu : (a.R + LH_BM - 1) / LH_BM;
   const int S = a.a_stages;
 
@@ -102,6 +102,7 @@ lin_h_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);      // warp-uniform for ptxas (uniform-register UMMA operands)
 
   if (warp == 0) {
     if (lane == 0) {

@@ -55,7 +55,7 @@ lingemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const uint32_t sBar = sW + 2u * a.kboxes * w_box;
   const uint32_t bar_full = sBar, bar_acc = sBar + 8, bar_empty = sBar + 16, tmem_slot = sBar + 24;
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int l0 = blockIdx.x * LG_BM, ntile = blockIdx.y, b = blockIdx.z;
   const int row0 = b * a.L + l0;
   const int n0 = ntile * a.n_tile;
@@ -78,6 +78,7 @@ lingemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);      // warp-uniform for ptxas (uniform-register UMMA operands)
 
   if (warp == 0) {
     // K is consumed in passes of up to LG_KB boxes (96 columns) through the same buffers. The whole warp runs the

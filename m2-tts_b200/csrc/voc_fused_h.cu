@@ -132,7 +132,7 @@ voc_stage_fused_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const Fused
   const uint32_t tmem_slot = bar_w + 8;
   float* consts = reinterpret_cast<float*>(gbase + K::OFF_CONST);   // [0,C) b_up | [C,2C) b1 | [2C,3C) b2 | [3C,6C) out_w | [6C] out_b
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   const int n_iter = (a.total_tiles + (int)gridDim.x * NCTX - 1) / ((int)gridDim.x * NCTX);
   auto tile_of = [&](int it, int ctx) { return (it * (int)gridDim.x + (int)blockIdx.x) * NCTX + ctx; };
 
@@ -168,6 +168,7 @@ voc_stage_fused_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const Fused
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);      // warp-uniform for ptxas (uniform-register UMMA operands)
 
   if (warp == 0) {
     if (lane == 0) {

@@ -99,7 +99,7 @@ voc_res_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   const uint32_t tmem_slot = bars + 64;
   float* consts = reinterpret_cast<float*>(gbase + K::OFF_CONST);   // [0,C) b1 | [C,2C) b2
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   const int n_iter = (a.total_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
   auto tile_of = [&](int it) { return it * (int)gridDim.x + (int)blockIdx.x; };
 
@@ -120,6 +120,7 @@ voc_res_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);      // warp-uniform for ptxas (uniform-register UMMA operands)
 
   if (warp == 0) {
     if (lane == 0) {

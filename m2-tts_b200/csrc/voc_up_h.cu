@@ -77,7 +77,7 @@ voc_up_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   const uint32_t bar_f = bars, bar_e = bars + 48, bar_cf = bars + 96, bar_ce = bars + 112, bar_w = bars + 128, tmem_slot = bars + 136;
   float* bias_s = reinterpret_cast<float*>(gbase + K::OFF_CONST);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   const int ntile = blockIdx.x % a.n_tiles, first = blockIdx.x / a.n_tiles, cpg = gridDim.x / a.n_tiles;
   const int ph = ntile / a.co_tiles, co0 = (ntile % a.co_tiles) * COT;
 
@@ -100,6 +100,7 @@ voc_up_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);      // warp-uniform for ptxas (uniform-register UMMA operands)
 
   if (warp == 0) {
     if (lane == 0) {

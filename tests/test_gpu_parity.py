@@ -213,11 +213,16 @@ def test_decoder_long_sequence_stage2():
     assert H.max_abs(got.cpu(), want) <= FP32_TOL
 
 
-def test_duration_predictor_nonzero_bias_padding():
-    m = cuda_model("stage2", perturb=8)
-    enc = torch.randn(3, 77, 96, generator=torch.Generator().manual_seed(4))
+@pytest.mark.parametrize("stage,B,S", [("stage2", 3, 77), ("stage2", 8, 256), ("stage1", 5, 64), ("stage1", 2, 1), ("tiny", 2, 33)])
+def test_duration_predictor_nonzero_bias_padding(stage, B, S):
+    """Non-zero biases / BN statistics catch the per-layer zero padding; S = 1, S % 32 != 0 and S = 8 x 32 cover the tile edges,
+    stage2 (H = 96) the chunked weight staging (two output-channel chunks), stage1 the whole-layer one."""
+    m = cuda_model(stage, perturb=8)
+    Hd = H.STAGE_KWARGS[stage]["hidden_dim"]
+    enc = torch.randn(B, S, Hd, generator=torch.Generator().manual_seed(4))
     got = m.duration_predictor(enc.to(DEV))
     want = oracle.duration_predictor(cpu_sd(m), enc)
+    assert got.shape == (B, S)
     assert H.max_abs(got.cpu(), want) <= FP32_TOL
 
 
