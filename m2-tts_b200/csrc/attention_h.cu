@@ -6,30 +6,22 @@
 // kernel's own output planes) check their values and raise M2TTS_ST_FP16_RANGE (include/m2tts_b200.h).
 //
 // One CTA = two 128-query tiles of one (utterance, head) sharing every 64-key K/V tile; warp 0 TMA loader, warps 1 / 2 the
-// UMMA issuers of tile A / B (warp-collective issue), warps 4-19 four softmax warpgroups, two per query tile (thread = query
-// row = TMEM lane, warpgroup `half` owns 32 of the 64 score columns; partial row maxima are exchanged through shared memory
-// at a 64-thread named barrier); lazy rescaling with O accumulating in TMEM. The SCORES ARE DOUBLE-BUFFERED in TMEM:
-// QK(t+2) is issued right behind PV(t), so a warpgroup finds S(t+1) waiting when it finishes tile t.
-//
-// The kernel is bound by its softmax (tools/attn_dbg.py: 0.73 of 0.91 ms per C3 layer remain with every UMMA switched off;
-// a variant with 128-key tiles and one in-place score buffer per query tile halved the Q K^T UMMAs but serialised
-// Q K^T -> softmax -> P V per tile and was slower, 0.99 ms), so round 2 went into instructions per score and MUFU load:
-//   * packed fp32 pairs (FADD2) for s - m, the row sum and p - p_hi; FMNMX3 for the maximum; p_hi by masking the low 13
-//     mantissa bits (exact in fp16), so no half -> float conversion; one F2FP per packed pair: 9 instructions per PAIR of
-//     scores (2 MUFU, 3 FADD2, 2 LOP3, 2 F2FP) instead of ~15. ncu on this kernel: issue slots 66 %, ALU pipe 56 %, MUFU
-//     43 %, tensor pipe 40 %, FMA pipe 14 % (profiles/r2_ncu_attention_h.md) — it is bound by instruction issue;
-//   * P is written over S IN PLACE per 16-key group (= one k-step of P V): the 16 fp32 scores of a group become 8 columns of
-//     packed P_hi and 8 of packed P_lo in the same 16 columns, so the two warpgroups of a tile never touch each other's
-//     columns;
-//   * Q_hi lives in TMEM as the A operand of Q K^T (packed fp16 pairs, written once by the softmax threads; head_dim <= 48):
-//     six of the nine Q K^T UMMAs per key tile fetch only K from shared memory (TMEM per query tile: 2 x 64 scores, O 2 hd,
-//     Q_hi hd / 2 = 248 of 256 columns at head_dim 48);
-//   * the two query tiles take TURNS in the exponential phase (two named barriers, strict alternation): left alone, the
-//     four warps of a scheduler drift into the same phase, all 32 x 4 MUFU.EX2 of a key tile queue up on the scheduler's one
-//     MUFU (16 results per clock per SM) while it idles through everybody's load / maximum / exchange phases (tools/
-//     attn_prof.py: 1136 of 2089 cycles per key tile in the exponential phase for 256 cycles of own MUFU work). Evaluating
-//     part of the exponentials by a degree-5 polynomial in packed FFMA2 on the FMA pipe (the FlashAttention-4 trick) was
-//     measured and is slower here: the split arithmetic already fills that pipe.
+// UMMA issuers of tile A / B (warp-collective issue out of uniform registers: the warp index is a shuffle broadcast, so the
+// role branches are uniform branches for ptxas), warps 4-19 four softmax warpgroups, two per query tile; lazy rescaling
+// with O accumulating in TMEM. The SCORES ARE DOUBLE-BUFFERED in TMEM: QK(t+2) is issued right behind PV(t).
+//   * softmax warpgroup w of a query tile owns the key tiles t = w (mod 2) and score buffer w; a thread = one query row over
+//     all 64 keys of the tile (the first version split a tile's columns between the two warpgroups, exchanged row maxima
+//     through shared memory at a named barrier and made the two query tiles take turns in the exponential phase: 57 % of its
+//     executed instructions were spin loops, barrier traffic and moves — profiles/README.md);
+//   * the per-row reference maximum m_ref lives in shared memory and its per-tile decision is handed from warpgroup to
+//     warpgroup through a one-directional named barrier (details at the kernel);
+//   * 9 instructions per PAIR of scores: packed fp32 pairs (FADD2) for s - m, the row sum and p - p_hi; p_hi by masking the
+//     low 13 mantissa bits (exact in fp16); one F2FP per packed pair; FMNMX3 for the maximum;
+//   * P is written over S IN PLACE per 16-key group (= one k-step of P V): 8 columns of packed P_hi, 8 of packed P_lo;
+//   * Q_hi lives in TMEM as the A operand of Q K^T (head_dim <= 48): six of the nine Q K^T UMMAs per key tile fetch only K
+//     from shared memory (TMEM per query tile: 2 x 64 scores, O 2 hd, Q_hi hd / 2 = 248 of 256 columns at head_dim 48).
+// Measured and rejected: 128-key tiles with one in-place score buffer (serialises Q K^T -> softmax -> P V, 0.99 ms against
+// 0.91), a Veltkamp split on the FMA pipe, part of the exponentials as a degree-5 FFMA2 polynomial (issue-bound then).
 // Operands: qkvh[6][B][nh][hd][Lp] fp16 = {Q_hi,Q_lo,K_hi,K_lo,V_hi,V_lo}, positions contiguous, Lp % 8 == 0, Q
 // pre-multiplied by scale*log2(e). A TMA box = 64 positions (128 B) x hd rows: for Q and K the MN-major 128B-swizzle
 // operand (K dim = d), for V the K-major 128B-swizzle operand (rows = d, K dim = keys) — layouts verified with
@@ -105,420 +97,11 @@ __device__ __forceinline__ float ws_ex2v(float x) {      // ex2 that keeps its p
   return y;
 }
 
-template <int HD>
-__global__ void __launch_bounds__(AH_THREADS, 1)
-attention_h_kernel(const __grid_constant__ CUtensorMap tmap, const __half* __restrict__ qkvh, int Lp, float* __restrict__ ctx,
-                   const int64_t* __restrict__ lengths, int B, int L, int nh, float* __restrict__ ctx_lo, __half* __restrict__ ctx_h,
-                   long long* __restrict__ prof, int dbg_skip, int32_t* __restrict__ status) {
-  static_assert(HD % 16 == 0 && HD >= 16 && HD <= 64, "16-bit split attention: head_dim in {16,32,48,64}");
-  constexpr uint32_t BOX = AhSmem<HD>::box;
-  constexpr int KSTEPS_D = HD / 16;
-  constexpr bool QT = (128 + 2 * HD + HD / 2) <= 256;             // Q_hi as a TMEM A operand (head_dim <= 48), else from shared memory
-  constexpr uint32_t IDESC_QK1 = ah_idesc(TC_BQ, TC_BK, 1);       // Q_* (MN-major smem) x K_*
-  constexpr uint32_t IDESC_QKT = ah_idesc2(TC_BQ, TC_BK, 0, 1);   // Q_hi (TMEM) x K_*
-  constexpr uint32_t IDESC_PV2 = ah_idesc(TC_BQ, 2 * HD, 0);      // P_hi x [V_hi | V_lo]
-  constexpr uint32_t IDESC_PV1 = ah_idesc(TC_BQ, HD, 0);          // P_lo x V_hi
-
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sQ = sbase;                                   // [tile][hi|lo][2 boxes][HD rows][128 B]
-  const uint32_t sK = sbase + AhSmem<HD>::off_k;               // [stage][hi|lo][HD rows][128 B]
-  const uint32_t sV = sbase + AhSmem<HD>::off_v;
-  const uint32_t sBar = sbase + AhSmem<HD>::off_bar;
-  // barriers: q_full[2] s_full[2 tiles][2 buffers] p_ready[2] pv_done[2] | k_full[S] k_empty[S] v_full[S] v_empty[S]
-  const uint32_t bar_qf = sBar, bar_sf = sBar + 16, bar_pr = sBar + 48, bar_pv = sBar + 64;
-  const uint32_t bar_kf = sBar + 80, bar_ke = bar_kf + 8 * AH_STAGES, bar_vf = bar_ke + 8 * AH_STAGES, bar_ve = bar_vf + 8 * AH_STAGES;
-  const uint32_t tmem_slot = bar_ve + 8 * AH_STAGES;
-  const uint32_t bar_qh = tmem_slot + 8;                       // q_hi[2]: Q_hi of tile x has been written to TMEM (8 softmax warps)
-
-  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
-  // 1-D grid, longest first: all CTAs with two query tiles, then (odd tile count) the single-tile CTAs, which take about
-  // 0.6 of the time and fill the last wave
-  const int n_tiles_q = (L + TC_BQ - 1) / TC_BQ, npf = n_tiles_q >> 1, n_long = npf * nh * B;
-  int qx, bh;
-  if ((int)blockIdx.x < n_long) { bh = (int)blockIdx.x / npf; qx = (int)blockIdx.x % npf; }
-  else { bh = (int)blockIdx.x - n_long; qx = npf; }
-  const int q0 = qx * (2 * TC_BQ), head = bh % nh, b = bh / nh;
-  const int ntq = q0 + TC_BQ < L ? 2 : 1;
-
-  int Leff = L;
-  bool all_masked = false;
-  if (lengths != nullptr) {
-    const long long len = lengths[b];
-    if (len <= 0) all_masked = true;
-    else if (len < L) Leff = (int)len;
-  }
-  const int nkt = (Leff + TC_BK - 1) / TC_BK;
-  const int plane = B * nh * HD;
-  const int row_q = (b * nh + head) * HD;
-
-  if (tid == 0) {
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(bar_qf + 8 * i, 1); mbar_init(bar_sf + 16 * i, 1); mbar_init(bar_sf + 16 * i + 8, 1);
-      mbar_init(bar_pr + 8 * i, 8); mbar_init(bar_pv + 8 * i, 1); mbar_init(bar_qh + 8 * i, 8);
-    }
-    for (int i = 0; i < AH_STAGES; ++i) {
-      mbar_init(bar_kf + 8 * i, 1); mbar_init(bar_ke + 8 * i, (uint32_t)ntq); mbar_init(bar_vf + 8 * i, 1); mbar_init(bar_ve + 8 * i, (uint32_t)ntq);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
-  }
-  if (warp == 0) {
-    __syncwarp();
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(AH_TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  uint32_t tmem_base;
-  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-  tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);      // warp-uniform for ptxas (uniform-register UMMA operands)
-
-  if (warp == 0) {
-    if (lane == 0) {
-      // ===== loader =====
-      for (int x = 0; x < ntq; ++x) {
-        mbar_expect_tx(bar_qf + 8 * x, QT ? AhSmem<HD>::q_bytes / 2 : AhSmem<HD>::q_bytes);
-        for (int h = QT ? 1 : 0; h < 2; ++h)      // with Q_hi in TMEM only the lo plane is a shared-memory operand
-          for (int j = 0; j < 2; ++j)
-            tma_load_2d(sQ + (uint32_t)x * AhSmem<HD>::q_bytes + (h * 2 + j) * BOX, &tmap, q0 + x * TC_BQ + j * 64, h * plane + row_q,
-                        bar_qf + 8 * x);
-      }
-      for (int t = 0; t < nkt; ++t) {
-        const int st = t % AH_STAGES;
-        const uint32_t par_prev = (uint32_t)(((t / AH_STAGES) - 1) & 1);
-        if (t >= AH_STAGES) mbar_wait(bar_ke + 8 * st, par_prev);
-        mbar_expect_tx(bar_kf + 8 * st, AhSmem<HD>::kv_bytes);
-        for (int h = 0; h < 2; ++h)
-          tma_load_2d(sK + (uint32_t)st * AhSmem<HD>::kv_bytes + h * BOX, &tmap, t * TC_BK, (2 + h) * plane + row_q, bar_kf + 8 * st);
-        if (t >= AH_STAGES) mbar_wait(bar_ve + 8 * st, par_prev);
-        mbar_expect_tx(bar_vf + 8 * st, AhSmem<HD>::kv_bytes);
-        for (int h = 0; h < 2; ++h)
-          tma_load_2d(sV + (uint32_t)st * AhSmem<HD>::kv_bytes + h * BOX, &tmap, t * TC_BK, (4 + h) * plane + row_q, bar_vf + 8 * st);
-      }
-    }
-  } else if ((warp == 1 || warp == 2) && warp - 1 < ntq) {
-    // ===== UMMA issuer of query tile x (whole warp, one elected lane issues) =====
-    const int x = warp - 1;
-#ifdef M2TTS_TOOLS
-    const bool pr_on = prof != nullptr && blockIdx.x == 0;
-#endif
-    auto issue_qk = [&](int x, int st, int buf) {
-      if (dbg_skip & 1) return;      // bring-up timing experiment (M2TTS_ATT_DBG): results invalid
-      const uint32_t q = sQ + (uint32_t)x * AhSmem<HD>::q_bytes, k = sK + (uint32_t)st * AhSmem<HD>::kv_bytes;
-      const uint32_t d = tmem_base + (uint32_t)x * AH_COL_TILE + AH_COL_S + (uint32_t)buf * 64u;
-      // MN-major, 128B swizzle, 16-bit: LBO = next 64 positions (next box), SBO = next 8 d-rows (1024 B);
-      // one k-step = 16 d-rows = 2048 B. Terms: hi*hi, hi*lo, lo*hi.
-      if (QT) {      // Q_hi from TMEM: one k-step = 16 d-rows = 8 columns of packed pairs
-        const uint32_t qt = tmem_base + (uint32_t)x * AH_COL_TILE + AH_COL_Q;
-#pragma unroll
-        for (int ks = 0; ks < KSTEPS_D; ++ks) {
-          const uint64_t khi = umma_desc(k + ks * 2048u, BOX, 1024u, 2u), klo = umma_desc(k + BOX + ks * 2048u, BOX, 1024u, 2u);
-          umma_f16_ts_w(d, qt + ks * 8, khi, IDESC_QKT, ks ? 1u : 0u);
-          umma_f16_ts_w(d, qt + ks * 8, klo, IDESC_QKT, 1u);
-          umma_f16_ss_w(d, umma_desc(q + 2 * BOX + ks * 2048u, BOX, 1024u, 2u), khi, IDESC_QK1, 1u);
-        }
-        return;
-      }
-#pragma unroll
-      for (int term = 0; term < 3; ++term) {
-        const uint32_t qa = q + (term == 2 ? 2 * BOX : 0u), kb = k + (term == 1 ? BOX : 0u);
-#pragma unroll
-        for (int ks = 0; ks < KSTEPS_D; ++ks)
-          umma_f16_ss_w(d, umma_desc(qa + ks * 2048u, BOX, 1024u, 2u), umma_desc(kb + ks * 2048u, BOX, 1024u, 2u), IDESC_QK1,
-                        (term | ks) ? 1u : 0u);
-      }
-    };
-    auto issue_pv = [&](int x, int st, int buf, uint32_t accumulate) {
-      if (dbg_skip & 2) return;
-      const uint32_t v = sV + (uint32_t)st * AhSmem<HD>::kv_bytes;
-      const uint32_t tb = tmem_base + (uint32_t)x * AH_COL_TILE;
-      const uint32_t pb = tb + AH_COL_S + (uint32_t)buf * 64u;
-      // V^T box: rows = d (V_hi rows then V_lo rows), keys contiguous; one k-step = 16 keys = 32 B = 8 TMEM columns of P.
-      // The 16 keys of k-step ks sit in score columns [16 ks, 16 ks + 16): packed P_hi in the first 8, P_lo in the last 8.
-#pragma unroll
-      for (int ks = 0; ks < TC_BK / 16; ++ks)
-        umma_f16_ts_w(tb + AH_COL_O, pb + ks * 16, umma_desc(v + ks * 32u, 16u, 1024u, 2u), IDESC_PV2, ks ? 1u : accumulate);
-#pragma unroll
-      for (int ks = 0; ks < TC_BK / 16; ++ks)
-        umma_f16_ts_w(tb + AH_COL_O, pb + ks * 16 + 8, umma_desc(v + ks * 32u, 16u, 1024u, 2u), IDESC_PV1, 1u);
-    };
-    // One issuer warp per query tile (warps 1 and 2 sit on different schedulers): an UMMA costs its issuer ~12 instructions
-    // (descriptor moves into uniform registers, elect), ~50 cycles next to two busy softmax warps, and a single issuer
-    // for both tiles was the critical path (tools/attn_prof.py: 1870 of 2355 cycles per key tile spent issuing).
-    // A K/V stage is free when BOTH issuers' UMMAs on it have completed (k_empty / v_empty count = tiles).
-    // prologue: the scores of key tiles 0 and 1
-    for (int t = 0; t < 2 && t < nkt; ++t) {
-      mbar_wait(bar_kf + 8 * t, 0);
-      if (t == 0) {
-        mbar_wait(bar_qf + 8 * x, 0);
-        if (QT) mbar_wait(bar_qh + 8 * x, 0);
-      }
-      tc_fence_after();
-      issue_qk(x, t, t);
-      tc_commit_w(bar_sf + 16 * x + 8 * t);
-      tc_commit_w(bar_ke + 8 * t);
-    }
-    for (int t = 0; t < nkt; ++t) {
-      const int st = t % AH_STAGES, s2 = (t + 2) % AH_STAGES, buf = t & 1;
-      const uint32_t par = (uint32_t)(t & 1);
-      AH_PROF(pr_on && lane == 0 && t >= 8 && t < 40, prof[384 + (t - 8) * 8 + 3 * x] = clock64());
-      mbar_wait(bar_pr + 8 * x, par);                         // P(x,t) is in TMEM (and O has been rescaled if needed)
-      AH_PROF(pr_on && lane == 0 && t >= 8 && t < 40, prof[384 + (t - 8) * 8 + 3 * x + 1] = clock64());
-      mbar_wait(bar_vf + 8 * st, (uint32_t)((t / AH_STAGES) & 1));
-      tc_fence_after();
-      issue_pv(x, st, buf, t > 0 ? 1u : 0u);
-      tc_commit_w(bar_pv + 8 * x);
-      tc_commit_w(bar_ve + 8 * st);
-      if (t + 2 < nkt) {                                      // score buffer `buf` is free again once PV(x,t) has read P
-        mbar_wait(bar_kf + 8 * s2, (uint32_t)(((t + 2) / AH_STAGES) & 1));
-        tc_fence_after();
-        issue_qk(x, s2, buf);
-        tc_commit_w(bar_sf + 16 * x + 8 * buf);
-        tc_commit_w(bar_ke + 8 * s2);
-      }
-      AH_PROF(pr_on && lane == 0 && t >= 8 && t < 40, prof[384 + (t - 8) * 8 + 3 * x + 2] = clock64());
-    }
-  } else if (warp >= 4 && (((warp - 4) >> 2) & 1) < ntq) {
-    // ===== softmax warpgroups: query tile x has TWO of them (warps 4-7 / 12-15 for tile A, 8-11 / 16-19 for tile B); thread =
-    // query row = TMEM lane, warpgroup `half` owns score columns [32 half, 32 half + 32) of every key tile = the 16-key groups
-    // 2 half and 2 half + 1. The two warps that share a row exchange their partial row maxima through shared memory at a
-    // 64-thread named barrier.
-    const int x = ((warp - 4) >> 2) & 1, half = (warp - 4) >> 3;
-    const int row = (warp & 3) * 32 + lane;
-    const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)x * AH_COL_TILE;
-    float* exch = reinterpret_cast<float*>(smem_raw + (sbase - smem_u32(smem_raw)) + AhSmem<HD>::off_exch);
-    const int pair_bar = 1 + x * 4 + (warp & 3);          // named barrier of the two warps sharing these 32 rows
-    if (QT) {
-      // Q_hi -> TMEM as the A operand of Q K^T: column c of this lane = (Q_hi[row][2c], Q_hi[row][2c+1]); this warpgroup writes
-      // the d range [half hd/2, (half+1) hd/2). Plane 0 of qkvh is Q_hi [B][nh][hd][Lp], positions contiguous: the 32 lanes of
-      // a warp read 64 contiguous bytes per d.
-      const int qi = q0 + x * TC_BQ + row;
-      const __half* qp = qkvh + ((long long)row_q + half * (HD / 2)) * Lp + qi;
-#pragma unroll
-      for (int c4 = 0; c4 < HD / 16; ++c4) {
-        uint32_t w[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int d = (c4 * 4 + e) * 2;
-          unsigned short lo = 0, hi = 0;
-          if (qi < L) { lo = __half_as_ushort(qp[(long long)d * Lp]); hi = __half_as_ushort(qp[(long long)(d + 1) * Lp]); }
-          w[e] = (uint32_t)lo | ((uint32_t)hi << 16);
-        }
-        ah_st4(t_lane + AH_COL_Q + (uint32_t)(half * (HD / 4) + c4 * 4), w);
-      }
-      tmem_wait_st();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_qh + 8 * x) : "memory");
-    }
-    float m_ref = -INFINITY;
-    uint64_t l2 = ah_pack(0.f, 0.f);                      // running row sum as a packed pair (even keys, odd keys)
-    const bool pingpong = ntq == 2 && !(dbg_skip & 8);
-    if (pingpong && x == 1) asm volatile("bar.arrive 10, 512;" ::: "memory");      // tile A takes the first turn
-#ifdef M2TTS_TOOLS
-    const bool pw = prof != nullptr && blockIdx.x == 0 && x == 0 && half == 0 && row == 0;
-#endif
-    // key padding (only ever in the last key tile): masked keys get -inf; an utterance of length 0 reproduces the reference's
-    // uniform attention over all L positions (components.py:77-81 fills with a finite -1e9)
-    auto mask16 = [&](uint32_t* sv, int k0) {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        float a = __uint_as_float(sv[j]);
-        if (all_masked) a = (k0 + j < L) ? 0.f : -INFINITY;
-        else if (k0 + j >= Leff) a = -INFINITY;
-        sv[j] = __float_as_uint(a);
-      }
-    };
-    for (int t = 0; t < nkt; ++t) {
-#ifdef M2TTS_TOOLS
-      const bool pt = pw && t >= 8 && t < 40;
-      long long* pp = prof + (pt ? (t - 8) * 8 : 0);
-#endif
-      const uint32_t t_s = t_lane + AH_COL_S + (uint32_t)(t & 1) * 64u + (uint32_t)half * 32u;     // this warpgroup's 32 columns of the tile's score buffer
-      AH_PROF(pt, pp[0] = clock64());
-      mbar_wait(bar_sf + 16 * x + 8 * (t & 1), (uint32_t)((t >> 1) & 1));
-      AH_PROF(pt, pp[1] = clock64());
-      __syncwarp();
-      tc_fence_after();
-      uint32_t sa[16], sb[16];
-      tmem_ld16(t_s, sa);
-      tmem_ld16(t_s + 16, sb);
-      tmem_wait_ld();
-      AH_PROF(pt, pp[2] = clock64());
-      const int kbase = t * TC_BK + half * 32;
-      if (all_masked || kbase + 32 > Leff) { mask16(sa, kbase); mask16(sb, kbase + 16); }
-      float mx = ah_max3(__uint_as_float(sa[0]), __uint_as_float(sa[1]), __uint_as_float(sa[2]));
-#pragma unroll
-      for (int j = 3; j < 15; j += 2) mx = ah_max3(mx, __uint_as_float(sa[j]), __uint_as_float(sa[j + 1]));
-      mx = ah_max3(mx, __uint_as_float(sa[15]), __uint_as_float(sb[0]));
-#pragma unroll
-      for (int j = 1; j < 15; j += 2) mx = ah_max3(mx, __uint_as_float(sb[j]), __uint_as_float(sb[j + 1]));
-      mx = fmaxf(mx, __uint_as_float(sb[15]));
-      {  // row maximum over all 64 columns
-        float* e = exch + ((t & 1) * 4 + x * 2) * 128;
-        e[half * 128 + row] = mx;
-        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
-        mx = fmaxf(mx, e[(half ^ 1) * 128 + row]);
-      }
-      if (t == 0) m_ref = mx;
-      // The pv_done barrier completes one phase per key tile. We wait for phase t-1 in EVERY tile (a parity wait is
-      // only exact while the waiter is at most one phase behind): early when O has to be rescaled, otherwise at the
-      // end of the tile, when PV(t-1) has long landed and the wait costs nothing.
-      bool pv_waited = t == 0;
-      if (t > 0 && __any_sync(0xffffffffu, mx > m_ref + 8.0f)) {
-        // lazy rescale (both warps of the pair take the same decision: they see the same maxima): PV(t-1) has landed and
-        // PV(t) waits for our arrival below, so O is quiescent; this half rescales its hd of the 2 hd accumulator columns
-        mbar_wait(bar_pv + 8 * x, (uint32_t)((t - 1) & 1));
-        pv_waited = true;
-        tc_fence_after();
-        const float m_new = fmaxf(m_ref, mx);
-        const float alpha = ws_ex2(m_ref - m_new);
-        m_ref = m_new;
-        float la, lb;
-        ah_unpack(l2, la, lb);
-        l2 = ah_pack(la * alpha, lb * alpha);
-#pragma unroll
-        for (int c = 0; c < HD; c += 16) {
-          uint32_t orr[16];
-          tmem_ld16(t_lane + AH_COL_O + half * HD + c, orr);
-          tmem_wait_ld();
-#pragma unroll
-          for (int j = 0; j < 16; ++j) orr[j] = __float_as_uint(__uint_as_float(orr[j]) * alpha);
-          tmem_st16(t_lane + AH_COL_O + half * HD + c, orr);
-        }
-      }
-      // exponential phase: the two query tiles alternate (barrier 9: tile A is done, tile B may go; barrier 10: the reverse)
-      if (pingpong) asm volatile("bar.sync %0, 512;" ::"r"(10 - x) : "memory");
-      AH_PROF(pt, pp[3] = clock64());
-      // p = 2^(s - m_ref), 16 keys (= one k-step of P V) at a time, written over their own 16 score columns: 8 columns of packed
-      // P_hi (the top 11 significant bits of p) and 8 of packed P_lo = fp16(p - P_hi).
-      // All 32 exponentials are issued first (MUFU.EX2 is the unit that saturates: 8 cycles per warp instruction), the split
-      // arithmetic of a pair follows once its exponentials are back.
-      const uint64_t m2 = ah_pack(m_ref, m_ref);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float d0, d1;
-        ah_unpack(ah_sub2(ah_pack(__uint_as_float(sa[2 * j]), __uint_as_float(sa[2 * j + 1])), m2), d0, d1);
-        sa[2 * j] = __float_as_uint(ws_ex2v(d0)); sa[2 * j + 1] = __float_as_uint(ws_ex2v(d1));
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float d0, d1;
-        ah_unpack(ah_sub2(ah_pack(__uint_as_float(sb[2 * j]), __uint_as_float(sb[2 * j + 1])), m2), d0, d1);
-        sb[2 * j] = __float_as_uint(ws_ex2v(d0)); sb[2 * j + 1] = __float_as_uint(ws_ex2v(d1));
-      }
-      auto split16 = [&](const uint32_t* pv, int u) {
-        uint32_t ph[8], pl[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float p0 = __uint_as_float(pv[2 * j]), p1 = __uint_as_float(pv[2 * j + 1]);
-          const uint64_t pp2 = ah_pack(p0, p1);
-          l2 = ah_add2(l2, pp2);
-          // Veltkamp split on the FMA pipe (the ALU pipe is the busiest one here): c = p (2^13 + 1), hi = c - (c - p) keeps the
-          // top 11 significant bits of p (round to nearest) and is exact in fp16; lo = p - hi is exact in fp32
-          // hi = p with the low 13 mantissa bits masked off (exact in fp16), lo = p - hi (exact in fp32). A Veltkamp split on the FMA
-          // pipe (hi = c - (c - p), c = 8193 p) takes the two LOP3 off the busy ALU pipe but is one instruction longer, and was
-          // slower: 0.930 against 0.888 ms per layer, the loop is bound by issue slots
-          const float h0 = __uint_as_float(__float_as_uint(p0) & 0xFFFFE000u), h1 = __uint_as_float(__float_as_uint(p1) & 0xFFFFE000u);
-          float r0, r1;
-          ah_unpack(ah_sub2(pp2, ah_pack(h0, h1)), r0, r1);
-          ph[j] = ah_cvt2(h0, h1);
-          pl[j] = ah_cvt2(r0, r1);
-        }
-        ah_st8(t_s + (uint32_t)(u * 16), ph);
-        ah_st8(t_s + (uint32_t)(u * 16 + 8), pl);
-      };
-      split16(sa, 0);
-      split16(sb, 1);
-      if (pingpong && !(x == 1 && t == nkt - 1)) asm volatile("bar.arrive %0, 512;" ::"r"(9 + x) : "memory");
-      AH_PROF(pt, pp[4] = clock64());
-      tmem_wait_st();
-      AH_PROF(pt, pp[5] = clock64());
-      if (!pv_waited) mbar_wait(bar_pv + 8 * x, (uint32_t)((t - 1) & 1));
-      AH_PROF(pt, pp[6] = clock64());
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_pr + 8 * x) : "memory");
-    }
-    // total row sum: the second warpgroup of the tile publishes its part and is done
-    float l_run;
-    {
-      float la, lb;
-      ah_unpack(l2, la, lb);
-      l_run = la + lb;
-      float* e = exch + ((nkt & 1) * 4 + x * 2) * 128;
-      if (half == 1) e[128 + row] = l_run;
-      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
-      if (half == 0) l_run += e[128 + row];
-    }
-    if (half == 0) {
-    mbar_wait(bar_pv + 8 * x, (uint32_t)((nkt - 1) & 1));     // the last PV has landed: O is complete
-    __syncwarp();
-    tc_fence_after();
-    float o[HD];
-#pragma unroll
-    for (int c = 0; c < HD; c += 16) {
-      uint32_t orr[16], or2[16];
-      tmem_ld16(t_lane + AH_COL_O + c, orr);
-      tmem_ld16(t_lane + AH_COL_O + HD + c, or2);
-      tmem_wait_ld();
-#pragma unroll
-      for (int j = 0; j < 16; ++j) o[c + j] = __uint_as_float(orr[j]) + __uint_as_float(or2[j]);
-    }
-    const int qi = q0 + x * TC_BQ + row;
-    if (qi < L) {
-      const float inv = 1.0f / l_run;
-      float* dst = ctx + ((long long)b * L + qi) * (nh * HD) + head * HD;
-      if (ctx_h != nullptr) {   // fp16 hi/lo planes [2][B*L][nh*HD] for the 16-bit split out_proj (lin_h.cu)
-        __half* dh = ctx_h + ((long long)b * L + qi) * (nh * HD) + head * HD;
-        __half* dl = dh + (long long)B * L * (nh * HD);
-        bool bad = false;
-#pragma unroll
-        for (int c = 0; c < HD; c += 8) {
-          uint32_t hi[4], lo[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) h_split2(o[c + 2 * e] * inv, o[c + 2 * e + 1] * inv, hi[e], lo[e], bad);
-          *reinterpret_cast<uint4*>(dh + c) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<uint4*>(dl + c) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-        }
-        h_flag(bad, status);
-      } else if (ctx_lo == nullptr) {
-#pragma unroll
-        for (int c = 0; c < HD; c += 4)
-          *reinterpret_cast<float4*>(dst + c) = make_float4(o[c] * inv, o[c + 1] * inv, o[c + 2] * inv, o[c + 3] * inv);
-      } else {   // TF32 hi/lo planes for the tensor-core out_proj
-        float* dlo = ctx_lo + ((long long)b * L + qi) * (nh * HD) + head * HD;
-#pragma unroll
-        for (int c = 0; c < HD; c += 4) {
-          float h[4], l[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) { const float v = o[c + e] * inv; h[e] = __uint_as_float(tf32_hi(v)); l[e] = __uint_as_float(tf32_hi(v - h[e])); }
-          *reinterpret_cast<float4*>(dst + c) = make_float4(h[0], h[1], h[2], h[3]);
-          *reinterpret_cast<float4*>(dlo + c) = make_float4(l[0], l[1], l[2], l[3]);
-        }
-      }
-    }
-    }      // half == 0
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) {
-    __syncwarp();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(AH_TMEM_COLS) : "memory");
-  }
-}
-
-
 // ---------------------------------------------------------------------------------------------------------------------------
-// attention_h2_kernel — same tiles, operands, TMEM map and UMMA sequence as attention_h_kernel; the SOFTMAX side is reorganised:
-//   * the two softmax warpgroups of a query tile no longer share a key tile (32 columns each, row maxima exchanged through
-//     shared memory at a named barrier, the two query tiles taking turns in the exponential phase): warpgroup w owns the key
-//     tiles t = w (mod 2) and their score buffer w, a thread = one query row over all 64 keys. Nothing is exchanged inside a
-//     tile, and while one warpgroup waits for the P V / Q K^T of its buffer the other one is in the middle of its tile, so the
-//     four warps of a scheduler sit in different phases without being forced to (ncu on v1: 57 % of the executed instructions
-//     were not softmax arithmetic — spin loops, barrier traffic, register moves; stall_barrier + stall_wait 33 % of samples);
+// attention_h_kernel. Softmax organisation:
+//   * warpgroup w of a query tile owns the key tiles t = w (mod 2) and their score buffer w, a thread = one query row over all
+//     64 keys. Nothing is exchanged inside a tile, and while one warpgroup waits for the P V / Q K^T of its buffer the other
+//     one is in the middle of its tile, so the four warps of a scheduler sit in different phases without being forced to;
 //   * the per-row reference maximum m_ref (lazy rescaling) lives in shared memory; the DECISION for tile t (keep m_ref or raise
 //     it and rescale O) is handed from the warpgroup of tile t-1 to the warpgroup of tile t through a one-directional named
 //     barrier (bar.arrive by the producer right after its decision, bar.sync by the consumer right before its own): the chain
@@ -532,7 +115,7 @@ attention_h_kernel(const __grid_constant__ CUtensorMap tmap, const __half* __res
 // Reference: components.py:75-87.
 template <int HD>
 __global__ void __launch_bounds__(AH_THREADS, 1)
-attention_h2_kernel(const __grid_constant__ CUtensorMap tmap, const __half* __restrict__ qkvh, int Lp, float* __restrict__ ctx,
+attention_h_kernel(const __grid_constant__ CUtensorMap tmap, const __half* __restrict__ qkvh, int Lp, float* __restrict__ ctx,
                     const int64_t* __restrict__ lengths, int B, int L, int nh, float* __restrict__ ctx_lo, __half* __restrict__ ctx_h,
                     long long* __restrict__ prof, int dbg_skip, int32_t* __restrict__ status) {
   static_assert(HD % 16 == 0 && HD >= 16 && HD <= 64, "16-bit split attention: head_dim in {16,32,48,64}");
@@ -954,19 +537,10 @@ static int launch_ah_hd(const CUtensorMap& tmap, const __half* qkvh, int Lp, flo
   const size_t smem = AhSmem<HD>::total;
   static int dbg_skip = -1;
   if (dbg_skip < 0) dbg_skip = tools_env_int("M2TTS_ATT_DBG", 0);
-  static int ver = -1;
-  if (ver < 0) ver = tools_env_int("M2TTS_ATT_V", 2);      // tools build: 1 = attention_h_kernel (A/B measurements)
   dim3 grid((unsigned)(ceil_div(L, 2 * TC_BQ) * nh * B), 1, 1);
-  long long* prof = tools_env_int("M2TTS_LIN_PROF_STAGE", -1) >= 0 ? nullptr : g_ws_prof;      // the buffer belongs to tools/lin_prof.py then
-  if (ver == 1) {
-    M2_CUDA_OK(allow_smem(attention_h_kernel<HD>, smem));
-    M2_LAUNCH(M2TTS_STAGE_ATTENTION, attention_h_kernel<HD>, grid, AH_THREADS, smem, s, tmap, qkvh, Lp, ctx, lengths, B, L, nh, ctx_lo, ctx_h,
-              prof, dbg_skip, status);
-  } else {
-    M2_CUDA_OK(allow_smem(attention_h2_kernel<HD>, smem));
-    M2_LAUNCH(M2TTS_STAGE_ATTENTION, attention_h2_kernel<HD>, grid, AH_THREADS, smem, s, tmap, qkvh, Lp, ctx, lengths, B, L, nh, ctx_lo, ctx_h,
-              prof, dbg_skip, status);
-  }
+  M2_CUDA_OK(allow_smem(attention_h_kernel<HD>, smem));
+  M2_LAUNCH(M2TTS_STAGE_ATTENTION, attention_h_kernel<HD>, grid, AH_THREADS, smem, s, tmap, qkvh, Lp, ctx, lengths, B, L, nh, ctx_lo, ctx_h,
+            tools_env_int("M2TTS_LIN_PROF_STAGE", -1) >= 0 ? nullptr : g_ws_prof, dbg_skip, status);      // the buffer belongs to tools/lin_prof.py then
   return M2TTS_OK;
 }
 

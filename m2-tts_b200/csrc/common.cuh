@@ -109,6 +109,51 @@ __device__ __forceinline__ void h_split2(float a0, float a1, uint32_t& hi, uint3
   hi = *reinterpret_cast<const uint32_t*>(&h);
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
+// ---- packed fp32 pairs (Blackwell FADD2 / FMUL2 / FFMA2: one instruction for two values) -------------------------------------
+// The epilogues of the 16-bit split kernels turn every accumulator element into an fp16 hi/lo pair; per step that is 2.4 G
+// elements in the vocoder alone, and at ~10 instructions per element the kernels were bound by the issue slots of their
+// epilogue warps (tools/fused_h_prof.py). These helpers bring an element to ~5 instructions.
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ uint64_t f2_pack_u(uint32_t lo, uint32_t hi) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi)); return r; }
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) { uint64_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t f2_sub(uint64_t a, uint64_t b) { uint64_t r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) { uint64_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) { uint64_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+// running maximum of |x| that keeps a NaN once it has seen one: the fp16-range check of a whole epilogue is one comparison
+// `!(amax <= 65504)` at the end instead of one FSETP per element
+__device__ __forceinline__ float amax_nan3(float m, float a, float b) {
+  float r;
+  asm("{\n\t.reg .f32 x, y;\n\tabs.f32 x, %2;\n\tabs.f32 y, %3;\n\tmax.NaN.f32 %0, %1, x, y;\n\t}" : "=f"(r) : "f"(m), "f"(a), "f"(b));
+  return r;
+}
+// LeakyReLU(0.1) of a pair: max(x, 0.1 x) (slope < 1)
+__device__ __forceinline__ uint64_t f2_lrelu01(uint64_t x) {
+  float a, b, c, d;
+  f2_unpack(x, a, b);
+  f2_unpack(f2_mul(x, f2_pack(0.1f, 0.1f)), c, d);
+  return f2_pack(fmaxf(a, c), fmaxf(b, d));
+}
+// pair -> packed fp16 hi and packed fp16 lo with x = hi + lo (hi = fp16(x), lo = fp16(x - hi): 22 significant bits), 6
+// instructions per pair (F2FP, 2 x HADD2.F32, FADD2, F2FP, FMNMX3) against 9 of h_split2 with its per-value range checks.
+// (A Veltkamp split in packed arithmetic — c = 8193 x, hi = c - (c - x) — does not survive ptxas: it contracts mul.rn.f32x2 +
+// sub.rn.f32x2 into FFMA2, which computes c - x exactly and returns hi = x; tools/ubench/split_test.cu.)
+__device__ __forceinline__ void h_split_pair(uint64_t x, uint32_t& hi, uint32_t& lo, float& amax) {
+  float x0, x1, r0, r1;
+  f2_unpack(x, x0, x1);
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+  const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  f2_unpack(f2_sub(x, f2_pack(hf.x, hf.y)), r0, r1);
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r1), "f"(r0));
+  amax = amax_nan3(amax, x0, x1);
+}
+__device__ __forceinline__ bool h_amax_bad(float amax) { return !(amax <= 65504.f); }
+// packed fp16 hi + packed fp16 lo -> fp32 pair
+__device__ __forceinline__ uint64_t h_join_pair(uint32_t hi, uint32_t lo) {
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&lo));
+  return f2_add(f2_pack(a.x, a.y), f2_pack(b.x, b.y));
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -18,7 +18,10 @@
 namespace m2 {
 
 constexpr int LH_BM = 128;
-constexpr int LH_G = 3;                    // epilogue warpgroups: the 16-column chunks of a pass are dealt round-robin (one warp per
+#ifndef LH_NG
+#define LH_NG 3
+#endif
+constexpr int LH_G = LH_NG;                  // epilogue warpgroups: the 16-column chunks of a pass are dealt round-robin (one warp per
                                            // scheduler cannot hide the latency of its own dependent instructions)
 constexpr int LH_THREADS = 64 + 128 * LH_G;      // producer, issuer, epilogue warps
 

@@ -29,12 +29,25 @@ struct FusedHArgs {
   int dbg_nostore;                       // bring-up timing experiment (M2TTS_DBG_NOSTORE=1): skip the plane stores, results invalid
   long long out_plane;                   // elements between the hi and the lo plane of out_h
   int32_t* status;                       // M2TTS_ST_FP16_RANGE when U, V or the output planes leave the fp16 range
+  int tma_out;                           // C = 32 planes output: the tile leaves through V's shared-memory rows and two TMA stores
+  long long* prof;                       // tools build: phase timestamps of CTA 0, context 0, first epilogue warp (m2tts_attention_set_prof buffer)
 };
+#ifdef M2TTS_TOOLS
+#define FH_PROF(k) do { if (pt) a.prof[it * 8 + (k)] = clock64(); } while (0)
+#define FH_PROF2(k) do { if (pt) a.prof[512 + it * 8 + (k)] = clock64(); } while (0)      // EPI1 in detail
+#else
+#define FH_PROF(k) do { } while (0)
+#define FH_PROF2(k) do { } while (0)
+#endif
 
 template <int C, int NCTX, bool FINAL>
 struct FhCfg {
   static constexpr int NQ = 128;
-  static constexpr int G = (NCTX == 1) ? 2 : 1;      // epilogue warpgroups per context
+  // epilogue warpgroups per context: GP = 2 take the two phases of the transposed conv (EPI1) / the two 128-row halves of U
+  // (EPI2, EPI3), GC = C / 16 the 16-channel chunks. With one warpgroup per context (C = 16) or two (C = 32) the kernels
+  // ran 2 epilogue warps per scheduler and were bound by the latency of their own dependent chains (ncu: issue slots
+  // 38-47 % busy, tensor pipe 16-27 %)
+  static constexpr int GP = 2, GC = C / 16, G = GP * GC;
   static constexpr int XSLOTS = (NCTX == 1) ? 2 : 1; // input tile slots per context
   static constexpr int CI = 2 * C;
   static constexpr int XRB = CI * 2;                 // bytes of an input row (128 -> 128B swizzle, 64 -> 64B swizzle)
@@ -60,7 +73,7 @@ struct FhCfg {
   static constexpr uint32_t OFF_W = NCTX * CTX;
   static constexpr uint32_t OFF_CONST = OFF_W + WBYTES;
   static constexpr uint32_t OFF_EXCH = OFF_CONST + 1024;
-  static constexpr uint32_t OFF_BAR = OFF_EXCH + (FINAL ? NCTX * G * 3 * UROWS * 4 : 0);   // FINAL: partial tap sums [ctx][group][tap][row]
+  static constexpr uint32_t OFF_BAR = OFF_EXCH + (FINAL ? NCTX * GC * 3 * UROWS * 4 : 0);   // FINAL: partial tap sums [ctx][channel group][tap][row]
   static constexpr uint32_t TOTAL = OFF_BAR + 8 * (NCTX * NBAR + 1) + 16 + 1024;
   static constexpr int THREADS = 64 + 128 * NCTX * G;
   static_assert(C == 16 || C == 32, "fused stage: C in {16,32}");
@@ -116,11 +129,34 @@ __device__ __forceinline__ void fh_join8(const uint4& hi, const uint4& lo, float
   }
 }
 
+// accumulator chunk of 16 columns (main + correction halves) -> 8 packed fp32 pairs, + bias pairs from shared memory
+__device__ __forceinline__ void fh_ld_sum16_pairs(uint32_t t_main, uint32_t t_corr, const float* bias16, uint64_t* v) {
+  uint32_t a[16], b[16];
+  ct_ld16(t_main, a);
+  ct_ld16(t_corr, b);
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  const uint64_t* bp = reinterpret_cast<const uint64_t*>(bias16);      // 8-byte aligned: bias16 = consts + multiple of 16 floats
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = f2_add(f2_add(f2_pack_u(a[2 * j], a[2 * j + 1]), f2_pack_u(b[2 * j], b[2 * j + 1])), bp[j]);
+}
+// 8 pairs -> two 16-byte chunks of fp16 hi and two of fp16 lo, stored at 64-byte row `row`, chunks ch0, ch0 + 1 of planes P, P + UPL
+__device__ __forceinline__ void fh_split_store16(const uint64_t* v, uint8_t* plane_hi, uint32_t plane_stride, int row, int ch0, float& amax) {
+  uint32_t hi[8], lo[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) h_split_pair(v[j], hi[j], lo[j], amax);
+#pragma unroll
+  for (int j8 = 0; j8 < 2; ++j8) {
+    const uint32_t off = fh_swz64(row, ch0 + j8);
+    *reinterpret_cast<uint4*>(plane_hi + off) = make_uint4(hi[4 * j8], hi[4 * j8 + 1], hi[4 * j8 + 2], hi[4 * j8 + 3]);
+    *reinterpret_cast<uint4*>(plane_hi + plane_stride + off) = make_uint4(lo[4 * j8], lo[4 * j8 + 1], lo[4 * j8 + 2], lo[4 * j8 + 3]);
+  }
+}
+
 template <int C, int NCTX, bool FINAL>
 __global__ void __launch_bounds__(FhCfg<C, NCTX, FINAL>::THREADS, 1)
-voc_stage_fused_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedHArgs a, int* dbg) {
+voc_stage_fused_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_y, const FusedHArgs a, int* dbg) {
   using K = FhCfg<C, NCTX, FINAL>;
-  constexpr int CI = K::CI, XRB = K::XRB, URB = K::URB, HALVES = K::HALVES, XR = K::XR, G = K::G, XS = K::XSLOTS, NQ = K::NQ;
+  constexpr int CI = K::CI, XRB = K::XRB, URB = K::URB, HALVES = K::HALVES, XR = K::XR, G = K::G, GC = K::GC, XS = K::XSLOTS, NQ = K::NQ;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (ct_smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (sbase - ct_smem_u32(smem_raw));
@@ -285,16 +321,16 @@ voc_stage_fused_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const Fused
     // ===== epilogue warpgroup g of context c: thread m owns TMEM lane m =====
     const int eg = (warp - 2) >> 2;
     const int c = eg / G, g = eg % G;
+    const int gp = g / GC, gc = g % GC;             // phase / row half, 16-channel chunk
     const int qtr = warp & 3;
     const int m = qtr * 32 + lane;
     const uint32_t t_lane = tmem_base + ((uint32_t)(qtr * 32) << 16) + (uint32_t)(c * K::TCOLS_CTX);
     uint8_t* Ub = gbase + (uint32_t)c * K::CTX + K::O_U;
     uint8_t* Vb = gbase + (uint32_t)c * K::CTX + K::O_V;
-    float* exch = reinterpret_cast<float*>(gbase + K::OFF_EXCH) + c * G * 3 * K::UROWS;
+    float* exch = reinterpret_cast<float*>(gbase + K::OFF_EXCH) + c * GC * 3 * K::UROWS;
     const float* b_up = consts, *b1 = consts + C, *b2 = consts + 2 * C, *ow = consts + 3 * C;
-    constexpr int CG = C / G;                        // channels per warpgroup in EPI2 / EPI3
-    const int cg0 = g * CG;
-    bool bad = false;
+    const int c0 = 16 * gc;                          // this warpgroup's channels
+    float amax = 0.f;                                // max |value| written as fp16 planes (NaN sticks): the fp16-range check
     for (int it = 0; it < n_iter; ++it) {
       const int gt = tile_of(it, c);
       if (gt >= a.total_tiles) break;
@@ -302,44 +338,52 @@ voc_stage_fused_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const Fused
       const int b = gt / a.tiles_per_utt, k = gt % a.tiles_per_utt;
       const int Qs = k * (K::NOUT / 2) - K::ILO / 2;
       const int Ts = 2 * Qs;                               // output position of U row 0
+#ifdef M2TTS_TOOLS
+      const bool pt = a.prof != nullptr && blockIdx.x == 0 && eg == 0 && qtr == 0 && lane == 0 && it < 60;
+#endif
+      FH_PROF(0);
 
       // ---- EPI1: transposed-conv accumulator -> U = lrelu(. + bias), zero outside the utterance, fp16 hi/lo rows ----
       ct_wait(bar(c, ACC_UP), par, dbg, 8, it);
+      FH_PROF(1);
       __syncwarp();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       {
         const int q = Qs + m;
         const float keep = (q >= 0 && q < a.L_in) ? 1.f : 0.f;
+        const int p = gp;                                  // each warpgroup takes one phase and 16 channels
+        const int row = 2 * m + p + 1;
+        uint64_t v[8];
+        FH_PROF2(0);
+        fh_ld_sum16_pairs(t_lane + (uint32_t)(K::T_UP + p * 2 * C + c0), t_lane + (uint32_t)(K::T_UP + p * 2 * C + C + c0), b_up + c0, v);
+        FH_PROF2(1);
 #pragma unroll
-        for (int pp = 0; pp < 2 / G; ++pp) {
-          const int p = G == 2 ? g : pp;                   // with two warpgroups each takes one phase
-          const int row = 2 * m + p + 1;
+        for (int j = 0; j < 8; ++j) v[j] = f2_lrelu01(v[j]);
+        if (!__all_sync(0xffffffffu, keep != 0.f)) {       // only the tiles at the ends of an utterance have rows to zero
+          const uint64_t k2 = f2_pack(keep, keep);
 #pragma unroll
-          for (int c0 = 0; c0 < C; c0 += 16) {
-            float v[16];
-            fh_ld_sum16(t_lane + (uint32_t)(K::T_UP + p * 2 * C + c0), t_lane + (uint32_t)(K::T_UP + p * 2 * C + C + c0), v);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = fh_lrelu(v[j] + b_up[c0 + j]) * keep;
-#pragma unroll
-            for (int j8 = 0; j8 < 2; ++j8) {
-              uint4 hi, lo;
-              fh_split8(v + 8 * j8, hi, lo, bad);
-              const uint32_t off = fh_swz64(row, (c0 >> 3) + j8);
-              *reinterpret_cast<uint4*>(Ub + off) = hi;
-              *reinterpret_cast<uint4*>(Ub + K::UPL + off) = lo;
-            }
-          }
+          for (int j = 0; j < 8; ++j) v[j] = f2_mul(v[j], k2);
         }
+        fh_split_store16(v, Ub, K::UPL, row, c0 >> 3, amax);
+        FH_PROF2(2);
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      FH_PROF2(3);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      FH_PROF2(4);
       __syncwarp();
       if (lane == 0) ct_arrive(bar(c, U_READY));
+      FH_PROF(2);
 
       // ---- EPI2: conv1 accumulator -> V = lrelu(. + bias), zero outside the utterance, fp16 hi/lo rows ----
-#pragma unroll
-      for (int h = 0; h < HALVES; ++h) {
+      if (!FINAL && a.tma_out && it > 0) {      // the previous tile's output left through V: its TMA stores must have read it
+        if (eg == 0 && qtr == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        fh_group_sync(c, 128 * G);
+      }
+      {
+        const int h = gp;                                    // each warpgroup takes one 128-row half and 16 channels
         ct_wait(bar(c, ACC_C1 + h), par, dbg, 9, it);
+        FH_PROF(3);
         __syncwarp();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int i = 128 * h + m;
@@ -347,107 +391,128 @@ voc_stage_fused_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const Fused
         const float keep = (t >= 0 && t < a.L_out) ? 1.f : 0.f;
         // rows 0 and UROWS - 1 of V are computed from the two U rows outside the tile (never written: whatever shared memory
         // held) and only feed output rows the tile discards (ILO >= 2): they must not raise the range flag
-        bool bad_v = false;
+        float amax_v = 0.f;
+        uint64_t v[8];
+        fh_ld_sum16_pairs(t_lane + (uint32_t)(K::T_C1 + h * 2 * C + c0), t_lane + (uint32_t)(K::T_C1 + h * 2 * C + C + c0), b1 + c0, v);
 #pragma unroll
-        for (int c0 = cg0; c0 < cg0 + CG; c0 += 16) {
-          float v[16];
-          fh_ld_sum16(t_lane + (uint32_t)(K::T_C1 + h * 2 * C + c0), t_lane + (uint32_t)(K::T_C1 + h * 2 * C + C + c0), v);
+        for (int j = 0; j < 8; ++j) v[j] = f2_lrelu01(v[j]);
+        if (!__all_sync(0xffffffffu, keep != 0.f)) {
+          const uint64_t k2 = f2_pack(keep, keep);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = fh_lrelu(v[j] + b1[c0 + j]) * keep;
-#pragma unroll
-          for (int j8 = 0; j8 < 2; ++j8) {
-            uint4 hi, lo;
-            fh_split8(v + 8 * j8, hi, lo, bad_v);
-            const uint32_t off = fh_swz64(i + 1, (c0 >> 3) + j8);
-            *reinterpret_cast<uint4*>(Vb + off) = hi;
-            *reinterpret_cast<uint4*>(Vb + K::UPL + off) = lo;
-          }
+          for (int j = 0; j < 8; ++j) v[j] = f2_mul(v[j], k2);
         }
-        bad |= bad_v && i >= 1 && i <= K::UROWS - 2;
+        fh_split_store16(v, Vb, K::UPL, i + 1, c0 >> 3, amax_v);
+        if (i >= 1 && i <= K::UROWS - 2) amax = amax_nan3(amax, amax_v, 0.f);
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) ct_arrive(bar(c, V_READY));
+      FH_PROF(4);
 
       // ---- EPI3: conv2 accumulator + bias + U -> stage output (or the 1-channel output conv + tanh) ----
-#pragma unroll
-      for (int h = 0; h < HALVES; ++h) {
+      {
+        const int h = gp;
         ct_wait(bar(c, ACC_C2 + h), par, dbg, 10, it);
+        if (!FINAL && a.tma_out) ct_wait(bar(c, ACC_C2 + (h ^ 1)), par, dbg, 10, it);      // V is overwritten below: both halves of conv2 must have read it
+        FH_PROF(5);
         __syncwarp();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int i = 128 * h + m;
         const int t = Ts + i;
         const bool inside = (t >= 0 && t < a.L_out);
-        float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+        uint64_t y[8];
+        fh_ld_sum16_pairs(t_lane + (uint32_t)(K::T_C2 + h * 2 * C + c0), t_lane + (uint32_t)(K::T_C2 + h * 2 * C + C + c0), b2 + c0, y);
 #pragma unroll
-        for (int c0 = cg0; c0 < cg0 + CG; c0 += 16) {
-          float y[16];
-          fh_ld_sum16(t_lane + (uint32_t)(K::T_C2 + h * 2 * C + c0), t_lane + (uint32_t)(K::T_C2 + h * 2 * C + C + c0), y);
+        for (int j8 = 0; j8 < 2; ++j8) {      // + the residual U (hi + lo, exact)
+          const uint32_t off = fh_swz64(i + 1, (c0 >> 3) + j8);
+          const uint4 uh = *reinterpret_cast<const uint4*>(Ub + off), ul = *reinterpret_cast<const uint4*>(Ub + K::UPL + off);
+          y[4 * j8] = f2_add(y[4 * j8], h_join_pair(uh.x, ul.x));
+          y[4 * j8 + 1] = f2_add(y[4 * j8 + 1], h_join_pair(uh.y, ul.y));
+          y[4 * j8 + 2] = f2_add(y[4 * j8 + 2], h_join_pair(uh.z, ul.z));
+          y[4 * j8 + 3] = f2_add(y[4 * j8 + 3], h_join_pair(uh.w, ul.w));
+        }
+        if (!FINAL && a.tma_out) {
+          // planes through TMA: y goes to row i + 2 of V (dead once conv2 has run; index i + 2 puts the first stored row, i = ILO,
+          // on a 128-byte boundary) in V's own swizzled layout and the rows [ILO, IHI) leave as one box per plane below —
+          // thread-per-row global stores touched 32 lines per instruction (EPI3 + its barrier: half of the tile period)
+          float amax_y = 0.f;
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) h_split_pair(y[j], hi[j], lo[j], amax_y);
 #pragma unroll
           for (int j8 = 0; j8 < 2; ++j8) {
-            const uint32_t off = fh_swz64(i + 1, (c0 >> 3) + j8);
-            float u8[8];
-            fh_join8(*reinterpret_cast<const uint4*>(Ub + off), *reinterpret_cast<const uint4*>(Ub + K::UPL + off), u8);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) y[8 * j8 + e] += b2[c0 + 8 * j8 + e] + u8[e];
+            const uint32_t off = fh_swz64(i + 2, (c0 >> 3) + j8);
+            *reinterpret_cast<uint4*>(Vb + off) = make_uint4(hi[4 * j8], hi[4 * j8 + 1], hi[4 * j8 + 2], hi[4 * j8 + 3]);
+            *reinterpret_cast<uint4*>(Vb + K::UPL + off) = make_uint4(lo[4 * j8], lo[4 * j8 + 1], lo[4 * j8 + 2], lo[4 * j8 + 3]);
           }
-          if (!FINAL) {
-            if (inside && i >= K::ILO && i < K::IHI) {
-              const size_t o = ((size_t)b * a.L_out + t) * C + c0;
-              if (a.out_h != nullptr) {        // fp16 hi/lo planes for the next fused stage
+          if (inside && i >= K::ILO && i < K::IHI) amax = amax_nan3(amax, amax_y, 0.f);
+        } else if (!FINAL) {
+          if (inside && i >= K::ILO && i < K::IHI) {
+            const size_t o = ((size_t)b * a.L_out + t) * C + c0;
+            if (a.out_h != nullptr) {        // fp16 hi/lo planes for the next fused stage
+              uint32_t hi[8], lo[8];
 #pragma unroll
-                for (int j8 = 0; j8 < 2; ++j8) {
-                  uint4 hi, lo;
-                  fh_split8(y + 8 * j8, hi, lo, bad);
-                  if (!a.dbg_nostore) *reinterpret_cast<uint4*>(a.out_h + o + 8 * j8) = hi;
-                  if (!a.dbg_nostore) *reinterpret_cast<uint4*>(a.out_h + a.out_plane + o + 8 * j8) = lo;
-                }
-              } else {                         // plain fp32 channel-last
-                float4* op = reinterpret_cast<float4*>(a.out_f + o);
+              for (int j = 0; j < 8; ++j) h_split_pair(y[j], hi[j], lo[j], amax);
 #pragma unroll
-                for (int j4 = 0; j4 < 4; ++j4) op[j4] = make_float4(y[4 * j4], y[4 * j4 + 1], y[4 * j4 + 2], y[4 * j4 + 3]);
+              for (int j8 = 0; j8 < 2; ++j8) {
+                if (!a.dbg_nostore) *reinterpret_cast<uint4*>(a.out_h + o + 8 * j8) = make_uint4(hi[4 * j8], hi[4 * j8 + 1], hi[4 * j8 + 2], hi[4 * j8 + 3]);
+                if (!a.dbg_nostore) *reinterpret_cast<uint4*>(a.out_h + a.out_plane + o + 8 * j8) = make_uint4(lo[4 * j8], lo[4 * j8 + 1], lo[4 * j8 + 2], lo[4 * j8 + 3]);
               }
-            }
-          } else {
+            } else {                         // plain fp32 channel-last
+              uint64_t* op = reinterpret_cast<uint64_t*>(a.out_f + o);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              d0 = fmaf(ow[c0 + j], y[j], d0);
-              d1 = fmaf(ow[C + c0 + j], y[j], d1);
-              d2 = fmaf(ow[2 * C + c0 + j], y[j], d2);
+              for (int j = 0; j < 8; ++j) op[j] = y[j];
             }
           }
-        }
-        if (FINAL) {      // the output conv zero-pads y outside the utterance; every warpgroup contributes its channels
-          float* e = exch + g * 3 * K::UROWS;
-          e[i] = inside ? d0 : 0.f;
-          e[K::UROWS + i] = inside ? d1 : 0.f;
-          e[2 * K::UROWS + i] = inside ? d2 : 0.f;
+        } else {      // the output conv zero-pads y outside the utterance; every channel group contributes its channels
+          uint64_t d0 = f2_pack(0.f, 0.f), d1 = d0, d2 = d0;
+          const uint64_t* ow2 = reinterpret_cast<const uint64_t*>(ow + c0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            d0 = f2_fma(ow2[j], y[j], d0);
+            d1 = f2_fma(ow2[C / 2 + j], y[j], d1);
+            d2 = f2_fma(ow2[C + j], y[j], d2);
+          }
+          float e0, e1, e2, e3, e4, e5;
+          f2_unpack(d0, e0, e1); f2_unpack(d1, e2, e3); f2_unpack(d2, e4, e5);
+          float* e = exch + gc * 3 * K::UROWS;
+          e[i] = inside ? e0 + e1 : 0.f;
+          e[K::UROWS + i] = inside ? e2 + e3 : 0.f;
+          e[2 * K::UROWS + i] = inside ? e4 + e5 : 0.f;
         }
       }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      FH_PROF(6);
+      if (!FINAL && a.tma_out) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       fh_group_sync(c, 128 * G);              // U reads done (the next EPI1 may overwrite it); exch complete
+      if (!FINAL && a.tma_out && eg == 0 && qtr == 0 && lane == 0 && !a.dbg_nostore) {
+        // output rows i in [ILO, IHI) = positions k NOUT ..., V rows ILO + 2 ...; TMA clips positions >= L_out
+        const uint32_t s0 = sbase + (uint32_t)c * K::CTX + K::O_V + (uint32_t)(K::ILO + 2) * URB;
+        asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4}], [%5];"
+                     ::"l"(&tmap_y), "r"(0), "r"(k * K::NOUT), "r"(b), "r"(0), "r"(s0) : "memory");
+        asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4}], [%5];"
+                     ::"l"(&tmap_y), "r"(0), "r"(k * K::NOUT), "r"(b), "r"(1), "r"(s0 + K::UPL) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
       if (FINAL) {
-        if (g == 0) {
+        if (gc == 0) {
+          const int i = 128 * gp + m;
+          const int t = Ts + i;
+          if (i >= K::ILO && i < K::IHI && t < a.L_out) {
+            float s = consts[6 * C];
 #pragma unroll
-          for (int h = 0; h < HALVES; ++h) {
-            const int i = 128 * h + m;
-            const int t = Ts + i;
-            if (i >= K::ILO && i < K::IHI && t < a.L_out) {
-              float s = consts[6 * C];
-#pragma unroll
-              for (int gg = 0; gg < G; ++gg) {
-                const float* e = exch + gg * 3 * K::UROWS;
-                s += e[i - 1] + e[K::UROWS + i] + e[2 * K::UROWS + i + 1];
-              }
-              a.out_f[(size_t)b * a.L_out + t] = tanhf(s);
+            for (int gg = 0; gg < GC; ++gg) {
+              const float* e = exch + gg * 3 * K::UROWS;
+              s += e[i - 1] + e[K::UROWS + i] + e[2 * K::UROWS + i + 1];
             }
+            a.out_f[(size_t)b * a.L_out + t] = tanhf(s);
           }
         }
         fh_group_sync(c, 128 * G);            // exch reads done before the next tile rewrites it
       }
     }
-    h_flag(bad, a.status);
+    if (!FINAL && a.tma_out && eg == 0 && qtr == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    h_flag(h_amax_bad(amax), a.status);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -526,6 +591,8 @@ static EncodeTiledFn6 fh_encode_fn() {
   return fn;
 }
 
+extern long long* g_ws_prof;      // attention_tc.cu (m2tts_attention_set_prof)
+
 template <int C, int NCTX, bool FINAL>
 static int launch_fh(const __half* xh, long long x_plane, FusedHArgs a, int stage, cudaStream_t s) {
   using K = FhCfg<C, NCTX, FINAL>;
@@ -540,12 +607,23 @@ static int launch_fh(const __half* xh, long long x_plane, FusedHArgs a, int stag
                          CU_TENSOR_MAP_INTERLEAVE_NONE, K::XRB == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   M2_REQUIRE(r == CUDA_SUCCESS, M2TTS_E_CUDA, "voc_fused_h: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  CUtensorMap tmap_y = tmap;      // placeholder unless the output planes leave through TMA
+  a.tma_out = 0;
+  if (!FINAL && C == 32 && a.out_h != nullptr && (((uintptr_t)a.out_h) & 15) == 0) {
+    const cuuint64_t ydims[4] = {(cuuint64_t)C, (cuuint64_t)a.L_out, (cuuint64_t)a.B, 2};
+    const cuuint64_t ystrides[3] = {(cuuint64_t)C * 2, (cuuint64_t)a.L_out * C * 2, (cuuint64_t)a.out_plane * 2};
+    const cuuint32_t ybox[4] = {(cuuint32_t)C, (cuuint32_t)K::NOUT, 1u, 1u};
+    const CUresult ry = enc(&tmap_y, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, a.out_h, ydims, ystrides, ybox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    M2_REQUIRE(ry == CUDA_SUCCESS, M2TTS_E_CUDA, "voc_fused_h: cuTensorMapEncodeTiled (output planes) failed (%d)", (int)ry);
+    a.tma_out = 1;
+  }
   a.tiles_per_utt = ceil_div(a.L_out, K::NOUT);
   a.total_tiles = a.B * a.tiles_per_utt;
   int grid = ceil_div(a.total_tiles, NCTX);
   if (grid > kNumSMs) grid = kNumSMs;
   M2_CUDA_OK(allow_smem(voc_stage_fused_h_kernel<C, NCTX, FINAL>, K::TOTAL));
-  M2_LAUNCH(stage, (voc_stage_fused_h_kernel<C, NCTX, FINAL>), grid, K::THREADS, K::TOTAL, s, tmap, a, debug_words_device());
+  M2_LAUNCH(stage, (voc_stage_fused_h_kernel<C, NCTX, FINAL>), grid, K::THREADS, K::TOTAL, s, tmap, tmap_y, a, debug_words_device());
   return M2TTS_OK;
 }
 
@@ -572,6 +650,9 @@ int launch_voc_stage_fused_h(const void* xh, long long x_plane, const float* up_
   a.out_w = out_w; a.out_b = out_b; a.out_h = (__half*)out_h; a.out_f = out_f; a.out_plane = out_plane;
   { static int ns = -1; if (ns < 0) ns = tools_env_int("M2TTS_DBG_NOSTORE", 0) == 1 ? 1 : 0; a.dbg_nostore = ns; }
   a.status = status;
+#ifdef M2TTS_TOOLS
+  a.prof = g_ws_prof;
+#endif
   const bool fin = out_w != nullptr;
   if (fin) M2_REQUIRE(out_f != nullptr, M2TTS_E_NULLPTR, "voc_fused_h: the last stage writes fp32 audio");
   const __half* x = (const __half*)xh;

@@ -40,7 +40,10 @@ struct RhCfg {
   static constexpr uint32_t OFF_CONST = OFF_W + WBYTES;
   static constexpr uint32_t OFF_BAR = OFF_CONST + 1024;
   static constexpr uint32_t TOTAL = OFF_BAR + 128 + 1024;
-  static constexpr int NG = 2;                       // epilogue warpgroups, C / NG channels each (4 were measured: no faster)
+#ifndef RH_NG
+#define RH_NG 2
+#endif
+  static constexpr int NG = RH_NG;                   // epilogue warpgroups, C / NG channels each
   static constexpr int THREADS = 64 + 128 * NG;
   static constexpr int T_C1 = 0, T_C2 = 2 * C;
   static_assert(C == 64, "fused ResBlock: C = 64");

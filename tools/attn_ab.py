@@ -1,4 +1,4 @@
-"""Bring-up helper (GPU box): one attention flavour of the tools library (M2TTS_ATT_V=1|2, read once per process): parity of
+"""Bring-up helper (GPU box): one attention flavour of the tools library (the tools library): parity of
 the decoder against the TF32 split around the key-tile boundaries, then the attention stage time at the C3 size.
 usage: M2TTS_ATT_V=2 python tools/attn_ab.py [B]"""
 import _env  # noqa: F401  (selects libm2tts_b200_tools.so)

@@ -1,5 +1,5 @@
-"""Bring-up helper (GPU box): phase timestamps of the warp-specialised attention (attention_h.cu), CTA 0: the first softmax
-warpgroup of query tile A, key tiles 8..39 (of 54 at the C3 length)."""
+"""Bring-up helper (GPU box): phase timestamps of the warp-specialised attention (attention_h.cu), CTA 0: softmax warpgroup 0 of
+query tile A (the even key tiles from 8 on)."""
 import _env  # noqa: F401  (selects libm2tts_b200_tools.so)
 import sys
 from pathlib import Path
@@ -21,8 +21,12 @@ lib.m2tts_attention_set_prof(prof.data_ptr())
 m.decoder(x)
 torch.cuda.synchronize()
 lib.m2tts_attention_set_prof(None)
-w = prof.cpu()[:256].view(32, 8)      # [0] before wait S, [1] S ready, [2] scores loaded, [3] max + exchange (+ rescale), [4] exps + P stores issued, [5] stores done, [6] PV(t-1) seen
-names = ["wait S", "S ld", "max + exchange", "exp + pack + P st issue", "P st wait", "wait PV(t-1)"]
-segs = [(w[:, k + 1] - w[:, k]).float().mean().item() for k in range(6)]
-print("softmax warpgroup A0, per 64-key tile (cycles): " + ", ".join(f"{n}={v:.0f}" for n, v in zip(names, segs)) +
-      f", total={(w[31, 0] - w[0, 0]).item() / 31:.0f}")
+# softmax warpgroup 0 of query tile A owns the even key tiles; rows = tiles 8, 10, ... (54 key tiles at L = 3446 -> 23 rows)
+# [0] before wait S, [1] S ready, [2] scores loaded + row maximum, [3] hand-off + m_ref decision, [4] exps + split + P stores issued, [5] stores done
+n = 23
+w = prof.cpu()[:8 * n].view(n, 8)
+names = ["wait S", "S ld + max", "hand-off + decision", "exp + split + P st issue", "P st wait"]
+segs = [(w[:, k + 1] - w[:, k]).float().mean().item() for k in range(5)]
+per = (w[n - 1, 0] - w[0, 0]).item() / (n - 1)
+print("softmax warpgroup A0, per own key tile = 2 key tiles of the CTA (cycles): " + ", ".join(f"{n_}={v:.0f}" for n_, v in zip(names, segs)) +
+      f", period={per:.0f} (= {per / 2:.0f} per key tile)")
