@@ -237,6 +237,11 @@ size_t m2tts_vocoder_workspace_bytes(int B, int T, int M, int C);
 size_t m2tts_vocoder_pack_bytes(int M, int C, int precision);
 int m2tts_vocoder_pack(const m2tts_vocoder_weights* w, int M, int C, int precision, void* packed,
                        size_t packed_bytes, int32_t* status, m2tts_stream_t stream);
+/* Which kernels m2tts_vocoder_forward runs for (M, C, precision, res_dilation[4] or NULL = all 1): kinds[0] = input conv
+ * (0 fp32 FFMA, 1 TF32 tap-GEMM, 2 channel-last 16-bit split), kinds[1..4] = stages 0..3 (0 FFMA; 1 TF32 tap-GEMMs; 2 fused
+ * TF32; 3 fused 16-bit split; 4 / 5 voc_up_h + fused ResBlock / two conv kernels; 6 / 7 the same behind a TF32 upsampler).
+ * A pure function of its arguments — the same choice m2tts_vocoder_pack makes. */
+int m2tts_vocoder_plan(int M, int C, int precision, const int* res_dilation, int* kinds);
 /* mel element (b,m,t) is read at mel[b*stride_b + m*stride_m + t*stride_t]
  * (so both a contiguous [B,M,T] tensor and the transposed view of the decoder's
  * [B,T,M] output, tts_model.py:390, are accepted without a copy).

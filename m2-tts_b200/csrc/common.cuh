@@ -286,6 +286,7 @@ int launch_voc_stage_fused_h(const void* xh, long long x_plane, const float* up_
 int launch_split_planes_h(const float* x, void* planes, long long n, int32_t* status, cudaStream_t s);
 // fused narrow stage on channel-last activations (voc_fused.cu): upsample x2 + ResBlock (+ output conv + tanh)
 bool voc_fused_eligible(int C, int r, int dil);
+bool voc_fused_h_eligible(int C, int r, int dil, bool final_stage);      // voc_fused_h.cu: C = 8 only as the last stage (zero-padded to 16)
 size_t voc_fused_wblob_floats(int C);
 int launch_voc_stage_fused(const float* x, const float* up_w, const float* up_b, const float* w1, const float* b1,
                            const float* w2, const float* b2, const float* out_w, const float* out_b, float* wblob,

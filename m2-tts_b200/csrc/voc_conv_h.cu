@@ -22,6 +22,7 @@ struct ConvHArgs {
   int B, L, Lp_out;
   int CO;                                // output channels = row length of the output (and residual) planes
   int ks1;                               // 16-channel k-steps of the second k-block (4, or fewer when CI < 128: the input conv)
+  int nkb;                               // 64-channel k-blocks that carry data (1 when CI == 64: the second one is neither loaded nor multiplied)
   int tiles_per_utt, total_tiles, n_tiles;
   const __half* wblob;                   // [n_tile][tap][hi rows ; lo rows][C] swizzled image
   const float* bias;
@@ -106,7 +107,7 @@ voc_conv_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const ConvHArgs a,
       for (int g = first; g < a.total_tiles; g += cpg) {
         const int b = g / a.tiles_per_utt, k = g % a.tiles_per_utt;
         const int Ts = k * CH_NOUT;                    // output row 0 of the tile; X row j <-> t = Ts - 1 + j
-        for (int kb = 0; kb < CH_KB; ++kb, ++u) {
+        for (int kb = 0; kb < a.nkb; ++kb, ++u) {
           const int st = u % CH_NST, use = u / CH_NST;
           if (use > 0) ct_wait(bar_xe + 8 * st, (uint32_t)((use - 1) & 1), dbg, 1, u);
           ct_expect_tx(bar_xf + 8 * st, CH_STAGE);
@@ -126,7 +127,7 @@ voc_conv_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const ConvHArgs a,
       const int slot = it & 1, ause = it >> 1;
       if (ause > 0) ct_wait(bar_ce + 8 * slot, (uint32_t)((ause - 1) & 1), dbg, 4, it);     // accumulator buffer `slot` drained
       const uint32_t d = tmem_base + (uint32_t)slot * (2 * CH_NT);
-      for (int kb = 0; kb < CH_KB; ++kb, ++u) {
+      for (int kb = 0; kb < a.nkb; ++kb, ++u) {
         const int st = u % CH_NST, use = u / CH_NST;
         ct_wait(bar_xf + 8 * st, (uint32_t)(use & 1), dbg, 3, u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -265,10 +266,10 @@ static EncodeTiledFn8 ch_encode_fn() {
 }
 
 bool voc_conv_h_eligible(int C, int dil) { return C == CH_C && dil == 1; }
-bool voc_conv_h_io_eligible(int CI, int CO) { return CI > 64 && CI <= CH_C && CI % 16 == 0 && CO >= CH_NT && CO % CH_NT == 0; }
+bool voc_conv_h_io_eligible(int CI, int CO) { return CI >= 64 && CI <= CH_C && CI % 16 == 0 && CO >= CH_NT && CO % CH_NT == 0; }
 size_t voc_conv_h_wblob_bytes(int C) { return C % CH_NT == 0 ? (size_t)(C / CH_NT) * CH_WBYTES : 0; }      // C = output channels
 
-// xh: fp16 hi/lo planes channel-last [2][B][L][CI] (x_plane apart), 64 < CI <= 128 (channels CI..127 are zero-filled by TMA and
+// xh: fp16 hi/lo planes channel-last [2][B][L][CI] (x_plane apart), 64 <= CI <= 128 (channels CI..127 are zero-filled by TMA and
 // have zero weights); CO output channels (multiple of 64); residual planes [2][B][L][CO] optional; output planes or fp32 channel-first.
 int launch_voc_conv_h(const void* xh, long long x_plane, const float* w, const float* bias, void* wblob, const void* res_h,
                       long long res_plane, void* out_h, long long out_plane, float* out_cf, int Lp_out, int B, int CI, int CO, int L, int act,
@@ -298,7 +299,7 @@ int launch_voc_conv_h(const void* xh, long long x_plane, const float* w, const f
   ConvHArgs a{};
   a.B = B; a.L = L; a.Lp_out = Lp_out; a.wblob = (const __half*)wblob; a.bias = bias; a.act = act;
   a.res_h = (const __half*)res_h; a.res_plane = res_plane; a.out_h = (__half*)out_h; a.out_plane = out_plane; a.out_cf = out_cf;
-  a.CO = CO; a.ks1 = (CI - 64 + 15) / 16; a.status = status;
+  a.CO = CO; a.ks1 = (CI - 64 + 15) / 16; a.nkb = CI > 64 ? 2 : 1; a.status = status;
   a.n_tiles = CO / CH_NT;
   a.tiles_per_utt = ceil_div(L, CH_NOUT);
   a.total_tiles = B * a.tiles_per_utt;

@@ -29,6 +29,7 @@ struct FusedHArgs {
   int dbg_nostore;                       // bring-up timing experiment (M2TTS_DBG_NOSTORE=1): skip the plane stores, results invalid
   long long out_plane;                   // elements between the hi and the lo plane of out_h
   int32_t* status;                       // M2TTS_ST_FP16_RANGE when U, V or the output planes leave the fp16 range
+  int c_real;                            // channels that exist (8 in a 16-channel kernel: the stage-1 model's last stage; the rest are zero weights / biases)
   int tma_out;                           // C = 32 planes output: the tile leaves through V's shared-memory rows and two TMA stores
   long long* prof;                       // tools build: phase timestamps of CTA 0, context 0, first epilogue warp (m2tts_attention_set_prof buffer)
 };
@@ -186,10 +187,11 @@ voc_stage_fused_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
   }
   for (int i = tid; i < 6 * C + 1; i += K::THREADS) {
     float v = 0.f;
-    if (i < C) v = a.bias_up[i];
-    else if (i < 2 * C) v = a.bias1[i - C];
-    else if (i < 3 * C) v = a.bias2[i - 2 * C];
-    else if (FINAL && i < 6 * C) { const int e = i - 3 * C; v = a.out_w[(e % C) * 3 + e / C]; }   // [tap][ci]
+    const int cr = a.c_real;      // channels >= cr are padding: zero biases and output-conv weights
+    if (i < C) v = i < cr ? a.bias_up[i] : 0.f;
+    else if (i < 2 * C) v = i - C < cr ? a.bias1[i - C] : 0.f;
+    else if (i < 3 * C) v = i - 2 * C < cr ? a.bias2[i - 2 * C] : 0.f;
+    else if (FINAL && i < 6 * C) { const int e = i - 3 * C; v = e % C < cr ? a.out_w[(e % C) * 3 + e / C] : 0.f; }   // [tap][ci]
     else if (FINAL) v = a.out_b[0];
     consts[i] = v;
   }
@@ -523,7 +525,7 @@ voc_stage_fused_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
 }
 
 // ---- weight image: K-major rows with the swizzle of the operand they multiply; parts stack [hi rows ; lo rows] ----
-struct FhPackArgs { const float* up_w; const float* w1; const float* w2; __half* blob; int C; int32_t* status; };
+struct FhPackArgs { const float* up_w; const float* w1; const float* w2; __half* blob; int C; int32_t* status; int c_real; };
 __global__ void fh_wpack_kernel(FhPackArgs p) {
   const int C = p.C, CI = 2 * C, XRB = CI * 2;
   const int n_up0 = 4 * C * CI, n_upm = 2 * C * CI, n_conv = 2 * C * C;
@@ -537,20 +539,20 @@ __global__ void fh_wpack_kernel(FhPackArgs p) {
     if (e < n_up0) {                       // rows [p0 hi | p0 lo | p1 hi | p1 lo], each C rows
       base = 0; rowb = XRB; n = e / CI; k = e % CI;
       const int ph = n / (2 * C), co = n % C; lo = (n / C) & 1;
-      v = p.up_w[((size_t)k * C + co) * 4 + ph + 1];
+      v = (k < 2 * p.c_real && co < p.c_real) ? p.up_w[((size_t)k * p.c_real + co) * 4 + ph + 1] : 0.f;
     } else if (e < n_up0 + 2 * n_upm) {    // row q-1 (kernel tap 3) then row q+1 (kernel tap 0): [hi | lo]
       e -= n_up0;
       const int which = e / n_upm; e -= which * n_upm;
       base = which == 0 ? b_upm : b_upp; rowb = XRB; n = e / CI; k = e % CI;
       const int co = n % C; lo = n / C;
-      v = p.up_w[((size_t)k * C + co) * 4 + (which == 0 ? 3 : 0)];
+      v = (k < 2 * p.c_real && co < p.c_real) ? p.up_w[((size_t)k * p.c_real + co) * 4 + (which == 0 ? 3 : 0)] : 0.f;
     } else {                               // conv1 taps 0..2, conv2 taps 0..2: [hi | lo], 64-byte rows
       e -= n_up0 + 2 * n_upm;
       const int part = e / n_conv; e -= part * n_conv;
       base = b_c + (uint32_t)part * (2 * C * 64); rowb = 64; n = e / C; k = e % C;
       const int co = n % C; lo = n / C;
       const float* w = part < 3 ? p.w1 : p.w2;
-      v = w[((size_t)co * C + k) * 3 + (part % 3)];
+      v = (k < p.c_real && co < p.c_real) ? w[((size_t)co * p.c_real + k) * 3 + (part % 3)] : 0.f;
     }
     h_chk(v, bad);
     const __half h = __float2half_rn(v);
@@ -599,8 +601,9 @@ static int launch_fh(const __half* xh, long long x_plane, FusedHArgs a, int stag
   EncodeTiledFn6 enc = fh_encode_fn();
   M2_REQUIRE(enc != nullptr, M2TTS_E_CUDA, "voc_fused_h: cuTensorMapEncodeTiled unavailable");
   CUtensorMap tmap;
-  const cuuint64_t dims[4] = {(cuuint64_t)K::CI, (cuuint64_t)a.L_in, (cuuint64_t)a.B, 2};
-  const cuuint64_t strides[3] = {(cuuint64_t)K::CI * 2, (cuuint64_t)a.L_in * K::CI * 2, (cuuint64_t)x_plane * 2};
+  const int ci_real = 2 * a.c_real;      // the box covers CI channels; those beyond ci_real are zero-filled by TMA
+  const cuuint64_t dims[4] = {(cuuint64_t)ci_real, (cuuint64_t)a.L_in, (cuuint64_t)a.B, 2};
+  const cuuint64_t strides[3] = {(cuuint64_t)ci_real * 2, (cuuint64_t)a.L_in * ci_real * 2, (cuuint64_t)x_plane * 2};
   const cuuint32_t box[4] = {(cuuint32_t)K::CI, (cuuint32_t)K::XR, 1u, 1u};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(xh), dims, strides, box, estr,
@@ -627,17 +630,21 @@ static int launch_fh(const __half* xh, long long x_plane, FusedHArgs a, int stag
   return M2TTS_OK;
 }
 
-size_t voc_fused_h_wblob_bytes(int C) { return C == 32 ? FhCfg<32, 1, false>::WBYTES : (C == 16 ? FhCfg<16, 2, false>::WBYTES : 0); }
+size_t voc_fused_h_wblob_bytes(int C) { return C == 32 ? FhCfg<32, 1, false>::WBYTES : (C == 16 || C == 8 ? FhCfg<16, 2, false>::WBYTES : 0); }
+// C = 8 runs in the 16-channel kernel with zero-padded weights, only as the LAST stage (the output is the waveform, not planes)
+bool voc_fused_h_eligible(int C, int r, int dil, bool final_stage) { return r == 2 && dil == 1 && (C == 16 || C == 32 || (C == 8 && final_stage)); }
 
 // xh: fp16 hi/lo planes, channel-last [2][B][L_in][2C] (x_plane elements apart). Output: out_h (fp16 hi/lo planes
 // [2][B][2L][C], out_plane apart) or out_f (fp32 channel-last [B][2L][C]); with out_w != null: audio fp32 [B][2L] in out_f.
 int launch_voc_stage_fused_h(const void* xh, long long x_plane, const float* up_w, const float* up_b, const float* w1, const float* b1,
                              const float* w2, const float* b2, const float* out_w, const float* out_b, void* wblob,
                              void* out_h, long long out_plane, float* out_f, int B, int C, int L_in, int stage, int32_t* status, cudaStream_t s) {
-  M2_REQUIRE(C == 16 || C == 32, M2TTS_E_UNSUPPORTED, "voc_fused_h: C=%d (16 or 32)", C);
+  M2_REQUIRE(C == 16 || C == 32 || C == 8, M2TTS_E_UNSUPPORTED, "voc_fused_h: C=%d (8, 16 or 32)", C);
+  const int c_real = C;
+  if (C == 8) C = 16;      // zero-padded to the 16-channel kernel
   if (up_w != nullptr) {      // (re)write the weight image; up_w == nullptr: wblob already holds it
     M2_REQUIRE(w1 != nullptr && w2 != nullptr && (((uintptr_t)wblob) & 15) == 0, M2TTS_E_BADSHAPE, "voc_fused_h: pack arguments");
-    FhPackArgs p{up_w, w1, w2, (__half*)wblob, C, status};
+    FhPackArgs p{up_w, w1, w2, (__half*)wblob, C, status, c_real};
     M2_LAUNCH(M2TTS_STAGE_PACK, fh_wpack_kernel, ceil_div(28 * C * C, 256), 256, 0, s, p);
   }
   if (xh == nullptr) return M2TTS_OK;      // pack only
@@ -647,7 +654,7 @@ int launch_voc_stage_fused_h(const void* xh, long long x_plane, const float* up_
   M2_REQUIRE(out_h != nullptr || out_f != nullptr, M2TTS_E_NULLPTR, "voc_fused_h: no output");
   FusedHArgs a{};
   a.B = B; a.L_in = L_in; a.L_out = 2 * L_in; a.wblob = (const __half*)wblob; a.bias_up = up_b; a.bias1 = b1; a.bias2 = b2;
-  a.out_w = out_w; a.out_b = out_b; a.out_h = (__half*)out_h; a.out_f = out_f; a.out_plane = out_plane;
+  a.out_w = out_w; a.out_b = out_b; a.out_h = (__half*)out_h; a.out_f = out_f; a.out_plane = out_plane; a.c_real = c_real;
   { static int ns = -1; if (ns < 0) ns = tools_env_int("M2TTS_DBG_NOSTORE", 0) == 1 ? 1 : 0; a.dbg_nostore = ns; }
   a.status = status;
 #ifdef M2TTS_TOOLS
@@ -655,6 +662,7 @@ int launch_voc_stage_fused_h(const void* xh, long long x_plane, const float* up_
 #endif
   const bool fin = out_w != nullptr;
   if (fin) M2_REQUIRE(out_f != nullptr, M2TTS_E_NULLPTR, "voc_fused_h: the last stage writes fp32 audio");
+  M2_REQUIRE(c_real == C || fin, M2TTS_E_UNSUPPORTED, "voc_fused_h: C=%d only as the last stage", c_real);
   const __half* x = (const __half*)xh;
   if (C == 16) return fin ? launch_fh<16, 2, true>(x, x_plane, a, stage, s) : launch_fh<16, 2, false>(x, x_plane, a, stage, s);
   return fin ? launch_fh<32, 1, true>(x, x_plane, a, stage, s) : launch_fh<32, 1, false>(x, x_plane, a, stage, s);

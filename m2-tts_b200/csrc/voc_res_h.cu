@@ -46,7 +46,7 @@ struct RhCfg {
   static constexpr int NG = RH_NG;                   // epilogue warpgroups, C / NG channels each
   static constexpr int THREADS = 64 + 128 * NG;
   static constexpr int T_C1 = 0, T_C2 = 2 * C;
-  static_assert(C == 64, "fused ResBlock: C = 64");
+  static_assert(C == 64 || C == 32, "fused ResBlock: C in {32, 64}");
   static_assert(TOTAL <= 227 * 1024, "fused ResBlock: shared memory");
 };
 
@@ -54,10 +54,14 @@ __device__ __forceinline__ void rh_tma_4d(uint32_t dst, const CUtensorMap* map, 
   asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
                ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar) : "memory");
 }
-__device__ __forceinline__ uint64_t rh_desc(uint32_t addr) {      // K-major, 128-byte swizzle, SBO = 1024 B
-  return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+template <int RB>
+__device__ __forceinline__ uint64_t rh_desc(uint32_t addr) {      // K-major rows of RB bytes with the RB-byte swizzle, SBO = 8 rows
+  return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((uint64_t)((8u * RB) >> 4) << 32) | (1ull << 46) | ((uint64_t)(RB == 128 ? 2 : 4) << 61);
 }
-__device__ __forceinline__ uint32_t rh_swz128(int row, int chunk) { return (uint32_t)row * 128u + ((uint32_t)(chunk ^ (row & 7)) << 4); }
+template <int RB>
+__device__ __forceinline__ uint32_t rh_swz(int row, int chunk) {   // byte offset of 16-byte chunk `chunk` of row `row`
+  return RB == 128 ? (uint32_t)row * 128u + ((uint32_t)(chunk ^ (row & 7)) << 4) : (uint32_t)row * 64u + ((uint32_t)(chunk ^ ((row >> 1) & 3)) << 4);
+}
 __device__ __forceinline__ void rh_mma_w(uint32_t d, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t acc) {
   asm volatile("{\n\t.reg .pred p, q;\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
@@ -155,9 +159,9 @@ voc_res_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 #pragma unroll
         for (int ks = 0; ks < C / 16; ++ks) {
           const uint32_t a_hi = sA + (uint32_t)tap * RB + (uint32_t)ks * 32u;
-          const uint64_t bd = rh_desc(sW + (uint32_t)(conv * 3 + tap) * K::WPART + (uint32_t)ks * 32u);
-          rh_mma_w(d, rh_desc(a_hi), bd, id_2c, (tap | ks) ? 1u : 0u);
-          rh_mma_w(d, rh_desc(a_hi + plane_bytes), bd, id_c, 1u);
+          const uint64_t bd = rh_desc<RB>(sW + (uint32_t)(conv * 3 + tap) * K::WPART + (uint32_t)ks * 32u);
+          rh_mma_w(d, rh_desc<RB>(a_hi), bd, id_2c, (tap | ks) ? 1u : 0u);
+          rh_mma_w(d, rh_desc<RB>(a_hi + plane_bytes), bd, id_c, 1u);
         }
     };
     if (tile_of(0) < a.total_tiles) {
@@ -220,7 +224,7 @@ voc_res_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           for (int j8 = 0; j8 < 2; ++j8) {
             uint4 hi, lo;
             rh_split8(v + 8 * j8, hi, lo, bad);
-            const uint32_t off = rh_swz128(m + 1, (c0 >> 3) + j8);
+            const uint32_t off = rh_swz<RB>(m + 1, (c0 >> 3) + j8);
             *reinterpret_cast<uint4*>(Vb + off) = hi;
             *reinterpret_cast<uint4*>(Vb + K::VPL + off) = lo;
           }
@@ -251,7 +255,7 @@ voc_res_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         rh_ld_sum16(t_lane + (uint32_t)(K::T_C2 + c0), t_lane + (uint32_t)(K::T_C2 + C + c0), y);
 #pragma unroll
         for (int j8 = 0; j8 < 2; ++j8) {
-          const uint32_t off = rh_swz128(m + 1, (c0 >> 3) + j8);
+          const uint32_t off = rh_swz<RB>(m + 1, (c0 >> 3) + j8);
           float u8[8];
           rh_join8(*reinterpret_cast<const uint4*>(Xb + off), *reinterpret_cast<const uint4*>(Xb + K::XPL + off), u8);
 #pragma unroll
@@ -268,7 +272,7 @@ voc_res_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           for (int j8 = 0; j8 < 2; ++j8) {
             uint4 hi, lo;
             rh_split8(y + 8 * j8, hi, lo, bad_y);
-            const uint32_t off = rh_swz128(m + 1, (c0 >> 3) + j8);
+            const uint32_t off = rh_swz<RB>(m + 1, (c0 >> 3) + j8);
             *reinterpret_cast<uint4*>(Xw + off) = hi;
             *reinterpret_cast<uint4*>(Xw + K::XPL + off) = lo;
           }
@@ -325,7 +329,7 @@ __global__ void rh_wpack_kernel(RhPackArgs p) {
     const float v = w[((size_t)co * C + k) * 3 + (part % 3)];
     h_chk(v, bad);
     const __half h = __float2half_rn(v);
-    const uint32_t off = (uint32_t)part * (2 * C * RB) + (uint32_t)n * RB + ((((uint32_t)k >> 3) ^ (uint32_t)(n & 7)) << 4) + (uint32_t)(k & 7) * 2u;
+    const uint32_t off = (uint32_t)part * (2 * C * RB) + (uint32_t)n * RB + ((((uint32_t)k >> 3) ^ (RB == 128 ? (uint32_t)(n & 7) : (uint32_t)((n >> 1) & 3))) << 4) + (uint32_t)(k & 7) * 2u;
     p.blob[off >> 1] = lo ? __float2half_rn(v - __half2float(h)) : h;
   }
   h_flag(bad, p.status);
@@ -347,13 +351,13 @@ static EncodeTiledFn7 rh_encode_fn() {
 }
 
 extern long long* g_ws_prof;      // attention_tc.cu (m2tts_attention_set_prof)
-bool voc_res_h_eligible(int C, int dil) { return C == 64 && dil == 1; }
-size_t voc_res_h_wblob_bytes(int C) { return C == 64 ? RhCfg<64>::WBYTES : 0; }
+bool voc_res_h_eligible(int C, int dil) { return (C == 64 || C == 32) && dil == 1; }
+size_t voc_res_h_wblob_bytes(int C) { return C == 64 ? RhCfg<64>::WBYTES : (C == 32 ? RhCfg<32>::WBYTES : 0); }
 
 // uh: fp16 hi/lo planes channel-last [2][B][L][C] (u_plane elements apart); output planes (out_h/out_plane) or fp32 CL (out_f)
-int launch_voc_res_h(const void* uh, long long u_plane, const float* w1, const float* b1, const float* w2, const float* b2, void* wblob,
-                     void* out_h, long long out_plane, float* out_f, int B, int C, int L, int stage, int32_t* status, cudaStream_t s) {
-  M2_REQUIRE(C == 64, M2TTS_E_UNSUPPORTED, "voc_res_h: C=%d (64)", C);
+template <int C>
+static int launch_voc_res_h_t(const void* uh, long long u_plane, const float* w1, const float* b1, const float* w2, const float* b2, void* wblob,
+                     void* out_h, long long out_plane, float* out_f, int B, int L, int stage, int32_t* status, cudaStream_t s) {
   if (w1 != nullptr) {      // (re)write the weight image; w1 == nullptr: wblob already holds it
     M2_REQUIRE(w2 != nullptr && (((uintptr_t)wblob) & 15) == 0, M2TTS_E_BADSHAPE, "voc_res_h: pack arguments");
     RhPackArgs p{w1, w2, (__half*)wblob, C, status};
@@ -363,7 +367,7 @@ int launch_voc_res_h(const void* uh, long long u_plane, const float* w1, const f
   M2_REQUIRE((((uintptr_t)uh) & 15) == 0 && (((uintptr_t)wblob) & 15) == 0 && (u_plane & 7) == 0 && (out_plane & 7) == 0, M2TTS_E_BADSHAPE,
              "voc_res_h: misaligned pointers");
   M2_REQUIRE(B > 0 && L > 0 && (out_h != nullptr || out_f != nullptr), M2TTS_E_BADSHAPE, "voc_res_h: B=%d L=%d", B, L);
-  using K = RhCfg<64>;
+  using K = RhCfg<C>;
   EncodeTiledFn7 enc = rh_encode_fn();
   M2_REQUIRE(enc != nullptr, M2TTS_E_CUDA, "voc_res_h: cuTensorMapEncodeTiled unavailable");
   CUtensorMap tmap;
@@ -372,7 +376,7 @@ int launch_voc_res_h(const void* uh, long long u_plane, const float* w1, const f
   const cuuint32_t box[4] = {(cuuint32_t)C, (cuuint32_t)K::XR, 1u, 1u};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(uh), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, (C == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   M2_REQUIRE(r == CUDA_SUCCESS, M2TTS_E_CUDA, "voc_res_h: cuTensorMapEncodeTiled failed (%d)", (int)r);
   ResHArgs a{};
@@ -384,7 +388,7 @@ int launch_voc_res_h(const void* uh, long long u_plane, const float* w1, const f
   a.tiles_per_utt = ceil_div(L, K::NOUT);
   a.total_tiles = B * a.tiles_per_utt;
   const int grid = a.total_tiles < kNumSMs ? a.total_tiles : kNumSMs;
-  M2_CUDA_OK(allow_smem(voc_res_h_kernel<64>, K::TOTAL));
+  M2_CUDA_OK(allow_smem(voc_res_h_kernel<C>, K::TOTAL));
   CUtensorMap tmap_y = tmap;      // placeholder when the output is fp32
   if (out_h != nullptr) {
     const cuuint64_t ydims[4] = {(cuuint64_t)C, (cuuint64_t)L, (cuuint64_t)B, 2};
@@ -392,11 +396,18 @@ int launch_voc_res_h(const void* uh, long long u_plane, const float* w1, const f
     const cuuint32_t ybox[4] = {(cuuint32_t)C, (cuuint32_t)K::NOUT, 1u, 1u};
     const cuuint32_t yes[4] = {1, 1, 1, 1};
     const CUresult ry = enc(&tmap_y, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, out_h, ydims, ystr, ybox, yes, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                            (C == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B), CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     M2_REQUIRE(ry == CUDA_SUCCESS, M2TTS_E_CUDA, "voc_res_h: cuTensorMapEncodeTiled (output) failed (%d)", (int)ry);
   }
-  M2_LAUNCH(stage, voc_res_h_kernel<64>, grid, K::THREADS, K::TOTAL, s, tmap, tmap_y, a, debug_words_device());
+  M2_LAUNCH(stage, voc_res_h_kernel<C>, grid, K::THREADS, K::TOTAL, s, tmap, tmap_y, a, debug_words_device());
   return M2TTS_OK;
+}
+
+int launch_voc_res_h(const void* uh, long long u_plane, const float* w1, const float* b1, const float* w2, const float* b2, void* wblob,
+                     void* out_h, long long out_plane, float* out_f, int B, int C, int L, int stage, int32_t* status, cudaStream_t s) {
+  M2_REQUIRE(C == 64 || C == 32, M2TTS_E_UNSUPPORTED, "voc_res_h: C=%d (32 or 64)", C);
+  if (C == 64) return launch_voc_res_h_t<64>(uh, u_plane, w1, b1, w2, b2, wblob, out_h, out_plane, out_f, B, L, stage, status, s);
+  return launch_voc_res_h_t<32>(uh, u_plane, w1, b1, w2, b2, wblob, out_h, out_plane, out_f, B, L, stage, status, s);
 }
 
 }  // namespace m2
@@ -404,7 +415,7 @@ int launch_voc_res_h(const void* uh, long long u_plane, const float* w1, const f
 using namespace m2;
 
 extern "C" size_t m2tts_resblock_fused_h_workspace_bytes(int B, int C, int L) {
-  if (C != 64 || B <= 0 || L <= 0) return 0;
+  if ((C != 64 && C != 32) || B <= 0 || L <= 0) return 0;
   return align_up(voc_res_h_wblob_bytes(C), 256) + align_up((size_t)B * L * C * 4, 256) + 512;    // weight image + input planes
 }
 
@@ -412,7 +423,7 @@ extern "C" size_t m2tts_resblock_fused_h_workspace_bytes(int B, int C, int L) {
 extern "C" int m2tts_resblock_fused_h(const float* x, const float* w1, const float* b1, const float* w2, const float* b2, float* y,
                                       int B, int C, int L, int32_t* status, void* workspace, size_t workspace_bytes, m2tts_stream_t stream) {
   M2_REQUIRE(x && w1 && b1 && w2 && b2 && y && workspace, M2TTS_E_NULLPTR, "resblock_fused_h: null pointer");
-  M2_REQUIRE(C == 64, M2TTS_E_UNSUPPORTED, "resblock_fused_h: C=%d (64)", C);
+  M2_REQUIRE(C == 64 || C == 32, M2TTS_E_UNSUPPORTED, "resblock_fused_h: C=%d (32 or 64)", C);
   Carver cv(workspace, workspace_bytes);
   __half* wblob = cv.take<__half>(voc_res_h_wblob_bytes(C) / 2);
   const long long n = (long long)B * L * C;

@@ -300,7 +300,8 @@ static EncodeTiledFn9 uh_encode_fn() {
 }
 
 static int g_uh_dbg = 0;
-bool voc_up_h_eligible(int CI, int CO, int r) { return r == 4 && CO * 2 == CI && (CI == 256 || CI == 128); }
+bool voc_up_h_eligible(int CI, int CO, int r) { return r == 4 && CO * 2 == CI && (CI == 256 || CI == 128 || CI == 64); }
+static int uh_cot(int CI) { return CI == 64 ? 32 : 64; }      // output channels per CTA
 size_t voc_up_h_wblob_bytes(int CI) { return (size_t)8 * CI * (CI / 2) * 2 * 2; }      // every weight once, hi + lo
 
 template <int CI, int COT>
@@ -318,8 +319,8 @@ static int launch_up_h_t(const CUtensorMap& tmap, const CUtensorMap& tmap_y, UpH
 // xh: fp16 hi/lo planes channel-last [2][B][L][CI] (x_plane elements apart) -> out_h planes [2][B][4L][CI/2] = lrelu(convT(x) + bias)
 int launch_voc_up_h(const void* xh, long long x_plane, const float* w, const float* bias, void* wblob, void* out_h, long long out_plane,
                     int B, int CI, int L, int stage, int32_t* status, cudaStream_t s) {
-  M2_REQUIRE(voc_up_h_eligible(CI, CI / 2, 4), M2TTS_E_UNSUPPORTED, "voc_up_h: CI=%d (256 or 128)", CI);
-  const int COT = 64;
+  M2_REQUIRE(voc_up_h_eligible(CI, CI / 2, 4), M2TTS_E_UNSUPPORTED, "voc_up_h: CI=%d (256, 128 or 64)", CI);
+  const int COT = uh_cot(CI);
   if (w != nullptr) {      // (re)write the weight image; w == nullptr: wblob already holds it
     M2_REQUIRE((((uintptr_t)wblob) & 15) == 0, M2TTS_E_BADSHAPE, "voc_up_h: misaligned weight image");
     UhPackArgs p{w, (__half*)wblob, CI, COT, status};
@@ -358,6 +359,7 @@ int launch_voc_up_h(const void* xh, long long x_plane, const float* w, const flo
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     M2_REQUIRE(ry == CUDA_SUCCESS, M2TTS_E_CUDA, "voc_up_h: cuTensorMapEncodeTiled (output) failed (%d)", (int)ry);
   }
+  if (CI == 64) return launch_up_h_t<64, 32>(tmap, tmap_y, a, stage, s);
   return CI == 256 ? launch_up_h_t<256, 64>(tmap, tmap_y, a, stage, s) : launch_up_h_t<128, 64>(tmap, tmap_y, a, stage, s);
 }
 
@@ -389,7 +391,7 @@ extern "C" size_t m2tts_conv_transpose_x4_h_workspace_bytes(int B, int CI, int L
 extern "C" int m2tts_conv_transpose_x4_h(const float* x, const float* w, const float* b, float* y, int B, int CI, int L,
                                          int32_t* status, void* workspace, size_t workspace_bytes, m2tts_stream_t stream) {
   M2_REQUIRE(x && w && b && y && workspace, M2TTS_E_NULLPTR, "conv_transpose_x4_h: null pointer");
-  M2_REQUIRE(voc_up_h_eligible(CI, CI / 2, 4), M2TTS_E_UNSUPPORTED, "conv_transpose_x4_h: CI=%d (128 or 256)", CI);
+  M2_REQUIRE(voc_up_h_eligible(CI, CI / 2, 4), M2TTS_E_UNSUPPORTED, "conv_transpose_x4_h: CI=%d (64, 128 or 256)", CI);
   Carver cv(workspace, workspace_bytes);
   __half* wblob = cv.take<__half>(voc_up_h_wblob_bytes(CI) / 2);
   const long long n_in = (long long)B * L * CI, n_out = (long long)B * 4 * L * (CI / 2);

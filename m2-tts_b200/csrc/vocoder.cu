@@ -531,6 +531,14 @@ namespace {
 
 static const int kRates[4] = {4, 4, 2, 2};      // tts_model.py:244
 
+// image of the input conv: the tap-GEMM layout or 96 KB per 64 output channels of the channel-last kernel, whichever is larger
+size_t in_img_floats(int M, int C) {
+  const size_t tc = conv3_tc_wblob_floats(M, C), hh = voc_conv_h_io_eligible(M, C) ? (size_t)C / 64 * 98304 / sizeof(float) : 0;
+  return tc > hh ? tc : hh;
+}
+// image of a fused narrow stage (C = 8 runs zero-padded in the 16-channel kernel)
+size_t fs_img_floats(int c) { return voc_fused_wblob_floats(c == 32 ? 32 : ((c == 16 || c == 8) ? 16 : 0)); }
+
 // Per-stage kernel choice, a function of (M, C, precision, dilations) only, so that m2tts_vocoder_pack and
 // m2tts_vocoder_forward agree on which weight images exist.
 //   IN_H / S_UPH_* / S_FUSED_H : channel-last 16-bit split kernels (fp16 hi/lo planes between stages)
@@ -555,6 +563,29 @@ VocPlan make_plan(int M, int C, int prec, const int* res_dilation) {
   for (int j = 0; j < 4; ++j) { p.kind[j] = S_FFMA; p.out_planes[j] = false; }
   if (prec == M2TTS_PREC_FFMA) return p;
   const bool h = prec == M2TTS_PREC_SPLIT16;
+  // The all-16-bit-split chain: every stage has a channel-last kernel that reads and writes fp16 hi/lo planes — transposed conv
+  // (voc_up_h: 256 / 128 / 64 input channels, stride 4) + ResBlock (voc_conv_h x 2 for C = 128, voc_res_h for C = 64 / 32), or a
+  // fused narrow stage (voc_stage_fused_h: C = 32 / 16, stride 2; C = 8 zero-padded to 16 as the last stage). Covers the
+  // stage2_quality vocoder (C = 256) and the stage1_poc one (C = 128); anything else falls through to the mixed plan below.
+  if (h && C % 64 == 0 && voc_conv_h_io_eligible(M, C) && (size_t)C / 64 * 98304 <= in_img_floats(M, C) * sizeof(float)) {
+    bool all = true;
+    int kinds[4];
+    int ci2 = C;
+    for (int j = 0; j < 4 && all; ++j, ci2 /= 2) {
+      const int c = ci2 / 2;
+      const int dil = res_dilation[j] > 0 ? res_dilation[j] : 1;
+      if (voc_up_h_eligible(ci2, c, kRates[j]) && voc_res_h_eligible(c, dil)) kinds[j] = S_UPH_RESH;
+      else if (voc_up_h_eligible(ci2, c, kRates[j]) && voc_conv_h_eligible(c, dil)) kinds[j] = S_UPH_CONVH;
+      else if (voc_fused_h_eligible(c, kRates[j], dil, j == 3)) kinds[j] = S_FUSED_H;
+      else all = false;
+    }
+    if (all) {
+      p.in_kind = IN_H;
+      p.in_planes = true;
+      for (int j = 0; j < 4; ++j) { p.kind[j] = kinds[j]; p.out_planes[j] = j < 3; }
+      return p;
+    }
+  }
   // pass 1: the TF32-era skeleton — wide stages as a prefix of tap-GEMM stages, narrow stages fused
   int base[4];      // 0 ffma, 1 tc, 2 fused
   int ci = C;
@@ -605,23 +636,23 @@ struct VocBlobs {
 
 bool carve_blobs(Carver& cv, int M, int C, VocBlobs* o) {
   o->in_ffma = cv.take<float>((size_t)C * M * 3);
-  o->in_img = cv.take<float>(conv3_tc_wblob_floats(M, C));
+  o->in_img = cv.take<float>(in_img_floats(M, C));
   for (int j = 0, c = C / 2; j < 4; ++j, c /= 2) {
     o->r1_ffma[j] = cv.take<float>((size_t)c * c * 3);
     o->r2_ffma[j] = cv.take<float>((size_t)c * c * 3);
     o->r1_img[j] = cv.take<float>(conv3_tc_wblob_floats(c, c));
     o->r2_img[j] = cv.take<float>(conv3_tc_wblob_floats(c, c));
     o->up_img[j] = cv.take<float>(convT_tc_wblob_floats(2 * c, c, kRates[j]));
-    o->fs_img[j] = cv.take<float>(voc_fused_wblob_floats(c == 16 || c == 32 ? c : 0));
+    o->fs_img[j] = cv.take<float>(fs_img_floats(c));
   }
   return cv.ok();
 }
 
 size_t blobs_bytes(int M, int C) {
-  size_t wts = (size_t)C * M * 3 + conv3_tc_wblob_floats(M, C);
+  size_t wts = (size_t)C * M * 3 + in_img_floats(M, C);
   for (int j = 0, c = C / 2; j < 4; ++j, c /= 2)
     wts += 2 * (size_t)c * c * 3 + 2 * conv3_tc_wblob_floats(c, c) + convT_tc_wblob_floats(2 * c, c, kRates[j]) +
-           voc_fused_wblob_floats(c == 16 || c == 32 ? c : 0);
+           fs_img_floats(c);
   return align_up(wts * sizeof(float), 256) + 40 * 256;
 }
 
@@ -786,6 +817,16 @@ extern "C" size_t m2tts_vocoder_pack_bytes(int M, int C, int precision) {
   (void)precision;      // one layout covers every precision (the images of the kernels a precision does not use stay unwritten)
   if (M <= 0 || C < 16 || C % 16 != 0) return 0;
   return blobs_bytes(M, C);
+}
+
+extern "C" int m2tts_vocoder_plan(int M, int C, int precision, const int* res_dilation, int* kinds) {
+  M2_REQUIRE(kinds != nullptr, M2TTS_E_NULLPTR, "vocoder_plan: null pointer");
+  M2_REQUIRE(M > 0 && C >= 16 && C % 16 == 0, M2TTS_E_UNSUPPORTED, "vocoder_plan: M=%d C=%d", M, C);
+  const int one[4] = {1, 1, 1, 1};
+  const VocPlan plan = make_plan(M, C, resolve_precision(precision), res_dilation != nullptr ? res_dilation : one);
+  kinds[0] = plan.in_kind;
+  for (int j = 0; j < 4; ++j) kinds[1 + j] = plan.kind[j];
+  return M2TTS_OK;
 }
 
 extern "C" size_t m2tts_vocoder_workspace_bytes(int B, int T, int M, int C) {

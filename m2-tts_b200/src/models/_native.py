@@ -113,6 +113,7 @@ _SIGNATURES = {
     "m2tts_conv_transpose1d_lrelu_tc": (_I, [_P] * 4 + [_I] * 5 + [_P, _SZ, _P]),
     "m2tts_vocoder_stage_fused_workspace_bytes": (_SZ, [_I]),
     "m2tts_vocoder_stage_fused": (_I, [_P] * 10 + [_I] * 3 + [_P, _SZ, _P]),
+    "m2tts_vocoder_plan": (_I, [_I, _I, _I, _P, _P]),
     "m2tts_vocoder_stage_fused_h_workspace_bytes": (_SZ, [_I] * 3),
     "m2tts_vocoder_stage_fused_h": (_I, [_P] * 10 + [_I] * 3 + [_P, _P, _SZ, _P]),
     "m2tts_conv1d_k3_h_workspace_bytes": (_SZ, [_I] * 3),

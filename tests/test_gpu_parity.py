@@ -437,13 +437,14 @@ def test_fused_vocoder_stage(C, L, B, final, prec):
     assert H.max_abs(y.cpu(), want) <= FP32_TOL, (C, L, B, final)
 
 
-@pytest.mark.parametrize("L,B", [(300, 2), (126, 1), (127, 3), (1, 1), (2000, 2)])
-def test_fused_resblock_c64(L, B):
-    """A whole ResBlock (C = 64) as one channel-last 16-bit-split tcgen05 kernel."""
+@pytest.mark.parametrize("C,L,B", [(64, 300, 2), (64, 126, 1), (64, 127, 3), (64, 1, 1), (64, 2000, 2),
+                                   (32, 300, 2), (32, 126, 1), (32, 127, 3), (32, 1, 1), (32, 5000, 2)])
+def test_fused_resblock_c64(C, L, B):
+    """A whole ResBlock (C = 64: 128-byte operand rows; C = 32: 64-byte rows, the stage-1 model's second stage) as one
+    channel-last 16-bit-split tcgen05 kernel."""
     from models import _native as nat
     import torch.nn.functional as F
     lib = nat.lib()
-    C = 64
     g = torch.Generator().manual_seed(7 * L + B)
     x = torch.randn(B, C, L, generator=g)
     w1 = torch.randn(C, C, 3, generator=g) * (1.0 / (3 * C) ** 0.5)
@@ -457,7 +458,7 @@ def test_fused_resblock_c64(L, B):
               "resblock_fused_h")
     torch.cuda.synchronize()
     assert not torch.isnan(y).any(), "unwritten output rows"
-    assert H.max_abs(y.cpu(), want) <= FP32_TOL, (L, B)
+    assert H.max_abs(y.cpu(), want) <= FP32_TOL, (C, L, B)
 
 
 @pytest.mark.parametrize("L,B,act,res,out_cl", [(1, 1, 0, False, 0), (127, 2, 1, False, 1), (128, 2, 0, True, 0), (129, 3, 1, True, 1),
@@ -493,7 +494,7 @@ def test_conv1d_k3_h_c128_matches_torch(L, B, act, res, out_cl):
 
 
 @pytest.mark.parametrize("CI,L,B", [(256, 1, 1), (256, 127, 2), (256, 128, 1), (256, 129, 3), (256, 3446, 2), (128, 1, 2), (128, 128, 2),
-                                    (128, 1000, 3), (128, 13784, 2)])
+                                    (128, 1000, 3), (128, 13784, 2), (64, 1, 1), (64, 127, 2), (64, 129, 3), (64, 2000, 2)])
 def test_conv_transpose_x4_h_matches_torch(CI, L, B):
     """One upsampling layer + leaky_relu of the wide vocoder stages (voc_up_h.cu, polyphase ConvTranspose1d on channel-last
     16-bit split operands) against torch's conv_transpose1d (components.py:225-241): both shapes, lengths around the
@@ -527,3 +528,26 @@ def test_vocoder_precisions_all_meet_fp32_tolerance(prec):
             mel = torch.randn(B, M, T, generator=torch.Generator().manual_seed(T))
             got = m.vocoder(mel.to(DEV))
             assert H.max_abs(got.cpu(), oracle.vocoder(cpu_sd(m), mel)) <= FP32_TOL, stage
+
+
+def test_stage1_and_stage2_vocoders_run_the_16_bit_split_chain():
+    """Both shipped configurations (stage1_poc: C = 128, stage2_quality: C = 256) run every vocoder stage on the channel-last
+    16-bit split tcgen05 kernels — no FFMA or TF32 tap-GEMM stage (the stage-1 smoke ran conv3 / convT / tapgemm)."""
+    import ctypes as C
+    from models import _native as nat
+    for stage in ("stage1", "stage2"):
+        kw = H.STAGE_KWARGS[stage]
+        kinds = (C.c_int * 5)()
+        nat.check(nat.lib().m2tts_vocoder_plan(kw["mel_channels"], kw["vocoder_channels"], -1, None, kinds), "vocoder_plan")
+        assert kinds[0] == 2, (stage, list(kinds))
+        assert all(k in (3, 4, 5) for k in list(kinds)[1:]), (stage, list(kinds))
+        m = cuda_model(stage)
+        before = nat.launch_count()
+        m.vocoder(torch.randn(2, kw["mel_channels"], 50, device=DEV))
+        torch.cuda.synchronize()
+        nat.stage_timing_enable(True)
+        m.vocoder(torch.randn(2, kw["mel_channels"], 50, device=DEV))
+        torch.cuda.synchronize()
+        nat.stage_timing_enable(False)
+        st = nat.stage_timing_read()
+        assert "voc_out" not in st, st      # the output conv is fused into the last stage
