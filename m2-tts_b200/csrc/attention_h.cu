@@ -119,6 +119,7 @@ attention_h_kernel(const __grid_constant__ CUtensorMap tmap, const __half* __res
                     const int64_t* __restrict__ lengths, int B, int L, int nh, float* __restrict__ ctx_lo, __half* __restrict__ ctx_h,
                     long long* __restrict__ prof, int dbg_skip, int32_t* __restrict__ status) {
   static_assert(HD % 16 == 0 && HD >= 16 && HD <= 64, "16-bit split attention: head_dim in {16,32,48,64}");
+  pdl_launch_dependents();      // M2_LAUNCH_PDL: every global access below follows a pdl_wait()
   constexpr uint32_t BOX = AhSmem<HD>::box;
   constexpr int KSTEPS_D = HD / 16;
   constexpr bool QT = (128 + 2 * HD + HD / 2) <= 256;             // Q_hi as a TMEM A operand (head_dim <= 48), else from shared memory
@@ -188,6 +189,7 @@ attention_h_kernel(const __grid_constant__ CUtensorMap tmap, const __half* __res
   if (warp == 0) {
     if (lane == 0) {
       // ===== loader =====
+      pdl_wait();
       for (int x = 0; x < ntq; ++x) {
         mbar_expect_tx(bar_qf + 8 * x, QT ? AhSmem<HD>::q_bytes / 2 : AhSmem<HD>::q_bytes);
         for (int h = QT ? 1 : 0; h < 2; ++h)
@@ -285,6 +287,7 @@ attention_h_kernel(const __grid_constant__ CUtensorMap tmap, const __half* __res
     float* mref_s = exch + x * 128;               // per-row reference maximum of the running softmax
     float* lsum_s = exch + 256 + x * 128;         // row sums of warpgroup 1 at the end
     const int hb = 1 + x * 2;                     // named barriers hb / hb + 1: hand-off of the m_ref decision of even / odd key tiles
+    pdl_wait();                                   // Q is read from global memory below; ctx is written at the end
     if (QT) {
       // Q_hi -> TMEM as the A operand of Q K^T (see attention_h_kernel); this warpgroup writes the d range [wg hd/2, (wg+1) hd/2)
       const int qi = q0 + x * TC_BQ + row;
@@ -539,7 +542,7 @@ static int launch_ah_hd(const CUtensorMap& tmap, const __half* qkvh, int Lp, flo
   if (dbg_skip < 0) dbg_skip = tools_env_int("M2TTS_ATT_DBG", 0);
   dim3 grid((unsigned)(ceil_div(L, 2 * TC_BQ) * nh * B), 1, 1);
   M2_CUDA_OK(allow_smem(attention_h_kernel<HD>, smem));
-  M2_LAUNCH(M2TTS_STAGE_ATTENTION, attention_h_kernel<HD>, grid, AH_THREADS, smem, s, tmap, qkvh, Lp, ctx, lengths, B, L, nh, ctx_lo, ctx_h,
+  M2_LAUNCH_PDL(M2TTS_STAGE_ATTENTION, attention_h_kernel<HD>, grid, AH_THREADS, smem, s, tmap, qkvh, Lp, ctx, lengths, B, L, nh, ctx_lo, ctx_h,
             tools_env_int("M2TTS_LIN_PROF_STAGE", -1) >= 0 ? nullptr : g_ws_prof, dbg_skip, status);      // the buffer belongs to tools/lin_prof.py then
   return M2TTS_OK;
 }

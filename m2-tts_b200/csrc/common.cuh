@@ -52,6 +52,29 @@ struct StageScope {
     if (_le != cudaSuccess) return m2::cuda_fail(_le, #kernel, __FILE__, __LINE__); \
   } while (0)
 
+// The same with programmatic dependent launch (PDL): the kernel may be scheduled while its predecessor in the stream is still
+// draining — its CTAs take the SMs the predecessor's CTAs leave — and runs its prologue (barrier init, TMEM allocation,
+// tensor-map prefetch, weight loads) there. ONLY for kernels that call pdl_wait() in every CTA before their first access to
+// anything another kernel of the stream reads or writes, and pdl_launch_dependents() early.
+#define M2_LAUNCH_PDL(stage, kernel, grid, block, smem, strm_, ...)            \
+  do {                                                                        \
+    {                                                                         \
+      m2::StageScope _scope((stage), (strm_));                                \
+      cudaLaunchConfig_t _cfg = {};                                           \
+      _cfg.gridDim = dim3(grid); _cfg.blockDim = dim3(block);                 \
+      _cfg.dynamicSmemBytes = (smem); _cfg.stream = (strm_);                 \
+      cudaLaunchAttribute _at[1];                                             \
+      _at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;         \
+      _at[0].val.programmaticStreamSerializationAllowed = m2::pdl_enabled();  \
+      _cfg.attrs = _at; _cfg.numAttrs = 1;                                    \
+      cudaError_t _pe = cudaLaunchKernelEx(&_cfg, kernel, __VA_ARGS__);       \
+      if (_pe != cudaSuccess) { (void)cudaGetLastError(); return m2::cuda_fail(_pe, #kernel, __FILE__, __LINE__); } \
+    }                                                                         \
+    cudaError_t _le = cudaGetLastError();                                     \
+    if (_le != cudaSuccess) return m2::cuda_fail(_le, #kernel, __FILE__, __LINE__); \
+  } while (0)
+int pdl_enabled();      // runtime.cu: 1 unless M2TTS_PDL=0 (tools build: A/B measurements)
+
 // opt a kernel into > 48 KB of dynamic shared memory (once per instantiation)
 template <typename K>
 inline cudaError_t allow_smem(K kernel, size_t bytes) {
@@ -92,6 +115,9 @@ inline int tools_env_int(const char*, int dflt) { return dflt; }
 
 // ---- device helpers ---------------------------------------------------------
 #ifdef __CUDACC__
+// programmatic dependent launch (see M2_LAUNCH_PDL)
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 // fp16-range guard of the 16-bit split. A producer converts without clamping (overflow -> inf, NaN -> NaN) and records
 // the violation: one FSETP per value instead of the two FMNMX of a clamp. The flagged call's output is invalid and the
 // caller re-runs it with M2TTS_PREC_TF32 (include/m2tts_b200.h, "Status word").

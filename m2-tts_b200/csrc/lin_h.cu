@@ -64,6 +64,7 @@ __device__ __forceinline__ void lh_tma_load_3d(uint32_t dst, const CUtensorMap* 
 __global__ void __launch_bounds__(LH_THREADS, 1)
 lin_h_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_y,
              const __grid_constant__ CUtensorMap tmap_r, const LinHArgs a) {
+  pdl_launch_dependents();      // the next kernel of the stream may take the SMs this grid's CTAs leave (M2_LAUNCH_PDL)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (sbase - smem_u32(smem_raw));
@@ -115,6 +116,7 @@ lin_h_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         for (int p = 0; p < a.n_passes; ++p)
           for (int pl = 0; pl < 2; ++pl)
             tma_load_2d(sW + (uint32_t)((kb * a.n_passes + p) * 2 + pl) * w_box, &tmap_w, kb * 32, pl * a.N + p * a.np, bar_w);
+      pdl_wait();      // the weights are nobody's output; the A tiles are the previous kernel's
       int it = 0;
       for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x, ++it) {
         const int st = it % S;
@@ -159,6 +161,7 @@ lin_h_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     }
   } else {
     // ===== epilogue warpgroup eg: thread = row of the tile, chunks eg, eg + G, ... of every pass =====
+    pdl_wait();      // before the first residual read / output write
     const int eg = (warp - 2) >> 2;
     const int qtr = warp & 3;
     const int row = qtr * 32 + lane;
@@ -383,6 +386,8 @@ lin_h_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
 __global__ void __launch_bounds__(256) ln_split_h_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                          const float* __restrict__ bvec, __half* __restrict__ planes,
                                                          long long R, int K, float eps, int32_t* __restrict__ status) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31, sub = lane & 7;
   const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
   const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -480,7 +485,7 @@ int launch_ln_split_h(const float* x, const float* w, const float* b, void* plan
   M2_REQUIRE(K % 32 == 0 && K <= 256 && (((uintptr_t)x) & 15) == 0, M2TTS_E_UNSUPPORTED, "ln_split_h: K=%d", K);
   long long blocks = (R + 31) / 32;            // 8 warps x 4 rows per block pass
   if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-  M2_LAUNCH(M2TTS_STAGE_LAYERNORM, ln_split_h_kernel, (unsigned)blocks, 256, 0, s, x, w, b, (__half*)planes, R, K, eps, status);
+  M2_LAUNCH_PDL(M2TTS_STAGE_LAYERNORM, ln_split_h_kernel, (unsigned)blocks, 256, 0, s, x, w, b, (__half*)planes, R, K, eps, status);
   return M2TTS_OK;
 }
 
@@ -601,7 +606,7 @@ int launch_linear_h(const void* a_planes, const void* w_planes, const LinHParams
   M2_CUDA_OK(allow_smem(lin_h_kernel, smem));
   const int m_tiles = a.tpu > 0 ? (a.R / q.L) * a.tpu : ceil_div(a.R, LH_BM);
   const int grid = m_tiles < kNumSMs ? m_tiles : kNumSMs;
-  M2_LAUNCH(stage, lin_h_kernel, grid, LH_THREADS, smem, s, ta, tw, ty, tr, a);
+  M2_LAUNCH_PDL(stage, lin_h_kernel, grid, LH_THREADS, smem, s, ta, tw, ty, tr, a);
   return M2TTS_OK;
 }
 

@@ -123,6 +123,14 @@ extern "C" int m2tts_version(void) { return 200; }
 
 extern "C" const char* m2tts_last_error_string(void) { return g_err; }
 
+namespace m2 {
+int pdl_enabled() {
+  static int v = -1;
+  if (v < 0) v = tools_env_int("M2TTS_PDL", 1) != 0 ? 1 : 0;
+  return v;
+}
+}  // namespace m2
+
 extern "C" uint64_t m2tts_launch_count(void) { return g_launches.load(); }
 
 extern "C" int m2tts_stage_timing_enable(int on) {

@@ -66,6 +66,7 @@ __device__ __forceinline__ void ch_mma_w(uint32_t d, uint64_t ad, uint64_t bd, u
 
 __global__ void __launch_bounds__(CH_THREADS, 1)
 voc_conv_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const ConvHArgs a, int* dbg) {
+  pdl_launch_dependents();      // M2_LAUNCH_PDL: every access to another kernel's data follows a pdl_wait()
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (ct_smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (sbase - ct_smem_u32(smem_raw));
@@ -103,6 +104,7 @@ voc_conv_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const ConvHArgs a,
       ct_expect_tx(bar_w, CH_WBYTES);
       for (uint32_t off = 0; off < CH_WBYTES; off += 8192u)
         ct_bulk(sbase + CH_OFF_W + off, reinterpret_cast<const uint8_t*>(a.wblob) + (size_t)ntile * CH_WBYTES + off, 8192u, bar_w);
+      pdl_wait();
       int u = 0;
       for (int g = first; g < a.total_tiles; g += cpg) {
         const int b = g / a.tiles_per_utt, k = g % a.tiles_per_utt;
@@ -149,6 +151,7 @@ voc_conv_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const ConvHArgs a,
     }
   } else {
     // ===== epilogue warpgroup eg: thread m = output row of the tile, channels [16 eg, 16 eg + 16) =====
+    pdl_wait();
     // (several warpgroups: one warp per scheduler cannot hide the latency of its own dependent instructions)
     const int eg = (warp - 2) >> 2;
     const int qtr = warp & 3;
@@ -307,7 +310,7 @@ int launch_voc_conv_h(const void* xh, long long x_plane, const float* w, const f
   if (cpg > a.total_tiles) cpg = a.total_tiles;
   const int grid = cpg * a.n_tiles;
   M2_CUDA_OK(allow_smem(voc_conv_h_kernel, CH_TOTAL));
-  M2_LAUNCH(stage, voc_conv_h_kernel, grid, CH_THREADS, CH_TOTAL, s, tmap, a, debug_words_device());
+  M2_LAUNCH_PDL(stage, voc_conv_h_kernel, grid, CH_THREADS, CH_TOTAL, s, tmap, a, debug_words_device());
   return M2TTS_OK;
 }
 

@@ -156,6 +156,7 @@ __device__ __forceinline__ void fh_split_store16(const uint64_t* v, uint8_t* pla
 template <int C, int NCTX, bool FINAL>
 __global__ void __launch_bounds__(FhCfg<C, NCTX, FINAL>::THREADS, 1)
 voc_stage_fused_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_y, const FusedHArgs a, int* dbg) {
+  pdl_launch_dependents();      // M2_LAUNCH_PDL: every access to another kernel's data follows a pdl_wait()
   using K = FhCfg<C, NCTX, FINAL>;
   constexpr int CI = K::CI, XRB = K::XRB, URB = K::URB, HALVES = K::HALVES, XR = K::XR, G = K::G, GC = K::GC, XS = K::XSLOTS, NQ = K::NQ;
   extern __shared__ uint8_t smem_raw[];
@@ -216,6 +217,7 @@ voc_stage_fused_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
         const uint32_t n = K::WBYTES - off < 8192u ? K::WBYTES - off : 8192u;
         ct_bulk(sbase + K::OFF_W + off, reinterpret_cast<const uint8_t*>(a.wblob) + off, n, bar_w);
       }
+      pdl_wait();
       for (int it = 0; it < n_iter; ++it)
         for (int c = 0; c < NCTX; ++c) {
           const int g = tile_of(it, c);
@@ -321,6 +323,7 @@ voc_stage_fused_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
     }
   } else {
     // ===== epilogue warpgroup g of context c: thread m owns TMEM lane m =====
+    pdl_wait();
     const int eg = (warp - 2) >> 2;
     const int c = eg / G, g = eg % G;
     const int gp = g / GC, gc = g % GC;             // phase / row half, 16-channel chunk
@@ -565,6 +568,8 @@ __global__ void fh_wpack_kernel(FhPackArgs p) {
 
 // fp32 channel-last rows -> fp16 hi/lo planes (stand-alone entry / producers that are not ours) and back
 __global__ void fh_split_planes_kernel(const float* __restrict__ x, __half* __restrict__ planes, long long n, int32_t* __restrict__ status) {
+  pdl_launch_dependents();
+  pdl_wait();
   bool bad = false;
   for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8; i < n; i += (long long)gridDim.x * blockDim.x * 8) {
     float v[8];
@@ -626,7 +631,7 @@ static int launch_fh(const __half* xh, long long x_plane, FusedHArgs a, int stag
   int grid = ceil_div(a.total_tiles, NCTX);
   if (grid > kNumSMs) grid = kNumSMs;
   M2_CUDA_OK(allow_smem(voc_stage_fused_h_kernel<C, NCTX, FINAL>, K::TOTAL));
-  M2_LAUNCH(stage, (voc_stage_fused_h_kernel<C, NCTX, FINAL>), grid, K::THREADS, K::TOTAL, s, tmap, tmap_y, a, debug_words_device());
+  M2_LAUNCH_PDL(stage, (voc_stage_fused_h_kernel<C, NCTX, FINAL>), grid, K::THREADS, K::TOTAL, s, tmap, tmap_y, a, debug_words_device());
   return M2TTS_OK;
 }
 
@@ -672,7 +677,7 @@ int launch_split_planes_h(const float* x, void* planes, long long n, int32_t* st
   M2_REQUIRE((n & 7) == 0 && (((uintptr_t)x) & 15) == 0 && (((uintptr_t)planes) & 15) == 0, M2TTS_E_BADSHAPE, "split_planes: n=%lld", n);
   long long blocks = (n / 8 + 255) / 256;
   if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
-  M2_LAUNCH(M2TTS_STAGE_PACK, fh_split_planes_kernel, (unsigned)blocks, 256, 0, s, x, (__half*)planes, n, status);
+  M2_LAUNCH_PDL(M2TTS_STAGE_PACK, fh_split_planes_kernel, (unsigned)blocks, 256, 0, s, x, (__half*)planes, n, status);
   return M2TTS_OK;
 }
 

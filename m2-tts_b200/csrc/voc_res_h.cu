@@ -95,6 +95,7 @@ __device__ __forceinline__ void rh_ld_sum16(uint32_t t_main, uint32_t t_corr, fl
 template <int C>
 __global__ void __launch_bounds__(RhCfg<C>::THREADS, 1)
 voc_res_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_y, const ResHArgs a, int* dbg) {
+  pdl_launch_dependents();      // M2_LAUNCH_PDL: every access to another kernel's data follows a pdl_wait()
   using K = RhCfg<C>;
   constexpr int RB = K::RB;
   extern __shared__ uint8_t smem_raw[];
@@ -134,6 +135,7 @@ voc_res_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       ct_expect_tx(bar_w, K::WBYTES);
       for (uint32_t off = 0; off < K::WBYTES; off += 8192u)
         ct_bulk(sbase + K::OFF_W + off, reinterpret_cast<const uint8_t*>(a.wblob) + off, 8192u, bar_w);
+      pdl_wait();
       for (int it = 0; it < n_iter; ++it) {
         const int g = tile_of(it);
         if (g >= a.total_tiles) break;
@@ -186,6 +188,7 @@ voc_res_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     }
   } else {
     // ===== epilogue warpgroup g: thread m owns TMEM lane m and channels [CG g, CG g + CG) =====
+    pdl_wait();
     const int g = (warp - 2) >> 2;
     const int qtr = warp & 3;
     const int m = qtr * 32 + lane;
@@ -399,7 +402,7 @@ static int launch_voc_res_h_t(const void* uh, long long u_plane, const float* w1
                             (C == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B), CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     M2_REQUIRE(ry == CUDA_SUCCESS, M2TTS_E_CUDA, "voc_res_h: cuTensorMapEncodeTiled (output) failed (%d)", (int)ry);
   }
-  M2_LAUNCH(stage, voc_res_h_kernel<C>, grid, K::THREADS, K::TOTAL, s, tmap, tmap_y, a, debug_words_device());
+  M2_LAUNCH_PDL(stage, voc_res_h_kernel<C>, grid, K::THREADS, K::TOTAL, s, tmap, tmap_y, a, debug_words_device());
   return M2TTS_OK;
 }
 

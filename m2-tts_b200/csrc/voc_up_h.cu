@@ -68,6 +68,7 @@ __device__ __forceinline__ void uh_mma_w(uint32_t d, uint64_t ad, uint64_t bd, u
 template <int CI, int COT>
 __global__ void __launch_bounds__(UhCfg<CI, COT>::THREADS, 1)
 voc_up_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_y, const UpHArgs a, int* dbg) {
+  pdl_launch_dependents();      // M2_LAUNCH_PDL: every access to another kernel's data follows a pdl_wait()
   using K = UhCfg<CI, COT>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (ct_smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -107,6 +108,7 @@ voc_up_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       ct_expect_tx(bar_w, K::WBYTES);
       for (uint32_t off = 0; off < K::WBYTES; off += 8192u)
         ct_bulk(sbase + K::OFF_W + off, reinterpret_cast<const uint8_t*>(a.wblob) + (size_t)ntile * K::WBYTES + off, 8192u, bar_w);
+      pdl_wait();
       int u = 0;
       for (int g = first; g < a.total_tiles; g += cpg) {
         const int b = g / a.tiles_per_utt, q0 = (g % a.tiles_per_utt) * K::NQ;      // X row j <-> input row q0 - 1 + j
@@ -176,6 +178,7 @@ voc_up_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   } else {
     // ===== epilogue warpgroup eg: thread m = input row of the tile -> output row 4 (q0 + m) + phase, channels [16 eg, 16 eg + 16) =====
     // (several warpgroups: one warp per scheduler cannot hide the latency of its own dependent instructions)
+    pdl_wait();
     const int eg = (warp - 2) >> 2;
     const int qtr = warp & 3;
     const int m = qtr * 32 + lane;
@@ -312,7 +315,7 @@ static int launch_up_h_t(const CUtensorMap& tmap, const CUtensorMap& tmap_y, UpH
   int cpg = kNumSMs / a.n_tiles;
   if (cpg > a.total_tiles) cpg = a.total_tiles;
   M2_CUDA_OK(allow_smem(voc_up_h_kernel<CI, COT>, K::TOTAL));
-  M2_LAUNCH(stage, (voc_up_h_kernel<CI, COT>), cpg * a.n_tiles, K::THREADS, K::TOTAL, s, tmap, tmap_y, a, debug_words_device());
+  M2_LAUNCH_PDL(stage, (voc_up_h_kernel<CI, COT>), cpg * a.n_tiles, K::THREADS, K::TOTAL, s, tmap, tmap_y, a, debug_words_device());
   return M2TTS_OK;
 }
 
