@@ -104,6 +104,17 @@ __device__ __forceinline__ void ct_ld16(uint32_t taddr, uint32_t* r) {
         "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
 }
+// accumulator chunk of 16 columns (main + correction halves of a split-folded-into-N GEMM) -> 8 packed fp32 pairs, + the bias
+// pairs at bias16 (shared memory, 8-byte aligned)
+__device__ __forceinline__ void ct_ld_sum16_pairs(uint32_t t_main, uint32_t t_corr, const float* bias16, uint64_t* v) {
+  uint32_t a[16], b[16];
+  ct_ld16(t_main, a);
+  ct_ld16(t_corr, b);
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  const uint64_t* bp = reinterpret_cast<const uint64_t*>(bias16);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = f2_add(f2_add(f2_pack_u(a[2 * j], a[2 * j + 1]), f2_pack_u(b[2 * j], b[2 * j + 1])), bp[j]);
+}
 __device__ __forceinline__ float ct_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
 
 int launch_tapgemm_persistent(const CUtensorMap& tmap, TapGemmArgs& a, int stage, cudaStream_t s);

@@ -158,7 +158,7 @@ voc_conv_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const ConvHArgs a,
     const int m = qtr * 32 + lane;
     const uint32_t t_lane = tmem_base + ((uint32_t)(qtr * 32) << 16);
     const float* bs = bias_s + eg * 16;
-    bool bad = false;
+    float amax = 0.f;      // max |value| written as fp16 planes (NaN sticks): the fp16-range check
     int it = 0;
     for (int g = first; g < a.total_tiles; g += cpg, ++it) {
       const int slot = it & 1, use = it >> 1;
@@ -187,41 +187,44 @@ voc_conv_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const ConvHArgs a,
       __syncwarp();
       if (lane == 0) ct_arrive(bar_ce + 8 * slot);
       if (!valid) continue;
-      float y[16];
+      // packed fp32 pairs (common.cuh): main + correction halves + bias, LeakyReLU, residual, hi/lo split
+      uint64_t y[8];
+      const uint64_t* bp = reinterpret_cast<const uint64_t*>(bs);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        float x = __uint_as_float(vm[j]) + __uint_as_float(vc[j]) + bs[j];
-        if (a.act == 1) x = x > 0.f ? x : 0.1f * x;
-        y[j] = x;
+      for (int j = 0; j < 8; ++j) {
+        y[j] = f2_add(f2_add(f2_pack_u(vm[2 * j], vm[2 * j + 1]), f2_pack_u(vc[2 * j], vc[2 * j + 1])), bp[j]);
+        if (a.act == 1) y[j] = f2_lrelu01(y[j]);
       }
       if (a.res_h != nullptr) {
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-          const uint32_t h[4] = {rh[j].x, rh[j].y, rh[j].z, rh[j].w}, l[4] = {rl[j].x, rl[j].y, rl[j].z, rl[j].w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float2 fa = __half22float2(*reinterpret_cast<const __half2*>(&h[e]));
-            const float2 fb = __half22float2(*reinterpret_cast<const __half2*>(&l[e]));
-            y[8 * j + 2 * e] += fa.x + fb.x; y[8 * j + 2 * e + 1] += fa.y + fb.y;
-          }
+          y[4 * j] = f2_add(y[4 * j], h_join_pair(rh[j].x, rl[j].x));
+          y[4 * j + 1] = f2_add(y[4 * j + 1], h_join_pair(rh[j].y, rl[j].y));
+          y[4 * j + 2] = f2_add(y[4 * j + 2], h_join_pair(rh[j].z, rl[j].z));
+          y[4 * j + 3] = f2_add(y[4 * j + 3], h_join_pair(rh[j].w, rl[j].w));
         }
       }
       if (a.out_h != nullptr) {
+        uint32_t hw[8], lw[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) h_split_pair(y[j], hw[j], lw[j], amax);
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-          uint32_t hw[4], lw[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) h_split2(y[8 * j + 2 * e], y[8 * j + 2 * e + 1], hw[e], lw[e], bad);
-          *(reinterpret_cast<uint4*>(a.out_h + o) + j) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-          *(reinterpret_cast<uint4*>(a.out_h + a.out_plane + o) + j) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+          *(reinterpret_cast<uint4*>(a.out_h + o) + j) = make_uint4(hw[4 * j], hw[4 * j + 1], hw[4 * j + 2], hw[4 * j + 3]);
+          *(reinterpret_cast<uint4*>(a.out_h + a.out_plane + o) + j) = make_uint4(lw[4 * j], lw[4 * j + 1], lw[4 * j + 2], lw[4 * j + 3]);
         }
       } else {
         float* op = a.out_cf + ((size_t)b * a.CO + co0 + eg * 16) * a.Lp_out + t;     // channel-first: coalesced across the warp's rows
 #pragma unroll
-        for (int j = 0; j < 16; ++j) op[(size_t)j * a.Lp_out] = y[j];
+        for (int j = 0; j < 8; ++j) {
+          float y0, y1;
+          f2_unpack(y[j], y0, y1);
+          op[(size_t)(2 * j) * a.Lp_out] = y0;
+          op[(size_t)(2 * j + 1) * a.Lp_out] = y1;
+        }
       }
     }
-    h_flag(bad, a.status);
+    h_flag(h_amax_bad(amax), a.status);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();

@@ -197,7 +197,7 @@ voc_res_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     const float* b1 = consts, *b2 = consts + C;
     constexpr int CG = C / K::NG;
     const int cg0 = g * CG;
-    bool bad = false;
+    float amax = 0.f;      // max |value| written as fp16 planes (NaN sticks): the fp16-range check
     for (int it = 0; it < n_iter; ++it) {
       const int gt = tile_of(it);
       if (gt >= a.total_tiles) break;
@@ -217,19 +217,26 @@ voc_res_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       {
         const float keep = inside ? 1.f : 0.f;
+        const bool all_keep = __all_sync(0xffffffffu, inside);
 #pragma unroll
         for (int c0 = cg0; c0 < cg0 + CG; c0 += 16) {
-          float v[16];
-          rh_ld_sum16(t_lane + (uint32_t)(K::T_C1 + c0), t_lane + (uint32_t)(K::T_C1 + C + c0), v);
+          uint64_t v[8];
+          ct_ld_sum16_pairs(t_lane + (uint32_t)(K::T_C1 + c0), t_lane + (uint32_t)(K::T_C1 + C + c0), b1 + c0, v);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) { const float x = v[j] + b1[c0 + j]; v[j] = (x > 0.f ? x : 0.1f * x) * keep; }
+          for (int j = 0; j < 8; ++j) v[j] = f2_lrelu01(v[j]);
+          if (!all_keep) {                      // only the tiles at the ends of an utterance have rows to zero
+            const uint64_t k2 = f2_pack(keep, keep);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = f2_mul(v[j], k2);
+          }
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) h_split_pair(v[j], hi[j], lo[j], amax);
 #pragma unroll
           for (int j8 = 0; j8 < 2; ++j8) {
-            uint4 hi, lo;
-            rh_split8(v + 8 * j8, hi, lo, bad);
             const uint32_t off = rh_swz<RB>(m + 1, (c0 >> 3) + j8);
-            *reinterpret_cast<uint4*>(Vb + off) = hi;
-            *reinterpret_cast<uint4*>(Vb + K::VPL + off) = lo;
+            *reinterpret_cast<uint4*>(Vb + off) = make_uint4(hi[4 * j8], hi[4 * j8 + 1], hi[4 * j8 + 2], hi[4 * j8 + 3]);
+            *reinterpret_cast<uint4*>(Vb + K::VPL + off) = make_uint4(lo[4 * j8], lo[4 * j8 + 1], lo[4 * j8 + 2], lo[4 * j8 + 3]);
           }
         }
       }
@@ -254,15 +261,16 @@ voc_res_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
       for (int c0 = cg0; c0 < cg0 + CG; c0 += 16) {
-        float y[16];
-        rh_ld_sum16(t_lane + (uint32_t)(K::T_C2 + c0), t_lane + (uint32_t)(K::T_C2 + C + c0), y);
+        uint64_t y[8];
+        ct_ld_sum16_pairs(t_lane + (uint32_t)(K::T_C2 + c0), t_lane + (uint32_t)(K::T_C2 + C + c0), b2 + c0, y);
 #pragma unroll
-        for (int j8 = 0; j8 < 2; ++j8) {
+        for (int j8 = 0; j8 < 2; ++j8) {      // + the residual u (hi + lo, exact)
           const uint32_t off = rh_swz<RB>(m + 1, (c0 >> 3) + j8);
-          float u8[8];
-          rh_join8(*reinterpret_cast<const uint4*>(Xb + off), *reinterpret_cast<const uint4*>(Xb + K::XPL + off), u8);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) y[8 * j8 + e] += b2[c0 + 8 * j8 + e] + u8[e];
+          const uint4 uh = *reinterpret_cast<const uint4*>(Xb + off), ul = *reinterpret_cast<const uint4*>(Xb + K::XPL + off);
+          y[4 * j8] = f2_add(y[4 * j8], h_join_pair(uh.x, ul.x));
+          y[4 * j8 + 1] = f2_add(y[4 * j8 + 1], h_join_pair(uh.y, ul.y));
+          y[4 * j8 + 2] = f2_add(y[4 * j8 + 2], h_join_pair(uh.z, ul.z));
+          y[4 * j8 + 3] = f2_add(y[4 * j8 + 3], h_join_pair(uh.w, ul.w));
         }
         if (a.out_h != nullptr) {
           // planes: y overwrites this thread's own residual chunks in the input slot (same swizzled addresses); the rows
@@ -270,21 +278,22 @@ voc_res_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           // (rows 0 and 127 are computed from the two V rows outside the tile — never written — and are not stored: they
           // must not raise the range flag)
           uint8_t* Xw = gbase + K::O_X + (uint32_t)(it & 1) * 2 * K::XPL;
-          bool bad_y = false;
+          float amax_y = 0.f;
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) h_split_pair(y[j], hi[j], lo[j], amax_y);
 #pragma unroll
           for (int j8 = 0; j8 < 2; ++j8) {
-            uint4 hi, lo;
-            rh_split8(y + 8 * j8, hi, lo, bad_y);
             const uint32_t off = rh_swz<RB>(m + 1, (c0 >> 3) + j8);
-            *reinterpret_cast<uint4*>(Xw + off) = hi;
-            *reinterpret_cast<uint4*>(Xw + K::XPL + off) = lo;
+            *reinterpret_cast<uint4*>(Xw + off) = make_uint4(hi[4 * j8], hi[4 * j8 + 1], hi[4 * j8 + 2], hi[4 * j8 + 3]);
+            *reinterpret_cast<uint4*>(Xw + K::XPL + off) = make_uint4(lo[4 * j8], lo[4 * j8 + 1], lo[4 * j8 + 2], lo[4 * j8 + 3]);
           }
-          bad |= bad_y && m >= 1 && m <= K::NOUT;
+          if (m >= 1 && m <= K::NOUT) amax = amax_nan3(amax, amax_y, 0.f);
         } else if (inside && m >= 1 && m < 1 + K::NOUT) {
           const size_t o = ((size_t)b * a.L + t) * C + c0;
-          float4* op = reinterpret_cast<float4*>(a.out_f + o);
+          uint64_t* op = reinterpret_cast<uint64_t*>(a.out_f + o);
 #pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) op[j4] = make_float4(y[4 * j4], y[4 * j4 + 1], y[4 * j4 + 2], y[4 * j4 + 3]);
+          for (int j = 0; j < 8; ++j) op[j] = y[j];
         }
       }
       if (pt) a.prof[it * 8 + 4] = clock64();
@@ -308,7 +317,7 @@ voc_res_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       if (lane == 0) ct_arrive(bar_xe + 8 * (it & 1));      // this input slot (the residual) has been read
     }
     if (a.out_h != nullptr && warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-    h_flag(bad, a.status);
+    h_flag(h_amax_bad(amax), a.status);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();

@@ -190,7 +190,7 @@ voc_up_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     constexpr uint32_t ORB = COT * 2;
     const uint32_t sw = ORB == 128 ? (uint32_t)(m & 7) : (uint32_t)((m >> 1) & 3);
     const bool leader = warp == 2 && lane == 0;
-    bool bad = false;
+    float amax = 0.f;      // max |value| written as fp16 planes (NaN sticks): the fp16-range check
     int it = 0;
     for (int g = first; g < a.total_tiles; g += cpg, ++it) {
       const int ab = it & 1, ause = it >> 1;
@@ -207,20 +207,16 @@ voc_up_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       __syncwarp();
       if (lane == 0) ct_arrive(bar_ce + 8 * ab);
       uint4 hv[2], lv[2];
+      {      // packed fp32 pairs (common.cuh): main + correction halves + bias, LeakyReLU, hi/lo split
+        const uint64_t* bp = reinterpret_cast<const uint64_t*>(bs);
+        uint32_t hw[8], lw[8];
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        uint32_t hw[4], lw[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int c = 8 * j + 2 * e;
-          float y0 = __uint_as_float(vm[c]) + __uint_as_float(vc[c]) + bs[c];
-          float y1 = __uint_as_float(vm[c + 1]) + __uint_as_float(vc[c + 1]) + bs[c + 1];
-          y0 = y0 > 0.f ? y0 : 0.1f * y0;
-          y1 = y1 > 0.f ? y1 : 0.1f * y1;
-          h_split2(y0, y1, hw[e], lw[e], bad);
+        for (int j = 0; j < 8; ++j) {
+          const uint64_t y = f2_lrelu01(f2_add(f2_add(f2_pack_u(vm[2 * j], vm[2 * j + 1]), f2_pack_u(vc[2 * j], vc[2 * j + 1])), bp[j]));
+          h_split_pair(y, hw[j], lw[j], amax);
         }
-        hv[j] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-        lv[j] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        hv[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]); hv[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+        lv[0] = make_uint4(lw[0], lw[1], lw[2], lw[3]); lv[1] = make_uint4(lw[4], lw[5], lw[6], lw[7]);
       }
       const uint32_t off0 = (uint32_t)m * ORB + ((((uint32_t)(eg * 2)) ^ sw) << 4), off1 = (uint32_t)m * ORB + ((((uint32_t)(eg * 2 + 1)) ^ sw) << 4);
       const uint32_t s0 = sbase + K::OFF_STG;
@@ -251,7 +247,7 @@ voc_up_h_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       }
     }
     if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-    h_flag(bad, a.status);
+    h_flag(h_amax_bad(amax), a.status);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
