@@ -259,8 +259,12 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     from models.tts_model import M2TTSModel
     from utils.host_pipeline import HostPipeline
 
+    from utils.device import bind_host_to_gpu
+
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    all_cores = os.sched_getaffinity(0)
+    host_binding = bind_host_to_gpu(dev, local_rank, world)      # before the pinned buffers are allocated (first touch)
     dist = setup_dist(world, dev)
 
     torch.manual_seed(1234)
@@ -474,6 +478,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4,
                         "d2h_bytes_per_step": audio_host.numel() * 4, "ms_per_step": e2e_ms / args.steps,
                         "exposed_copy_ms": e2e_ms / args.steps - total_ms / args.steps,
+                        "host_binding": host_binding,
                         "api": f"utils.host_pipeline.HostPipeline(n_chunks={args.e2e_chunks}, edge={args.e2e_edge}).run(decoder+vocoder, pinned host in, pinned host out)"},
                 "e2e_from_ids": {"value": ids_value, "unit": UNIT, "ms_per_step": ids_ms / args.steps,
                                  "h2d_bytes_per_step": ids_host.numel() * 8 + len_host.numel() * 8 + dur_host.numel() * 4,
@@ -489,6 +494,8 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             if not gather_ok:
                 rc = 4
         if world == 1 and not args.skip_cpu_baseline:
+            os.sched_setaffinity(0, all_cores)      # the CPU leg gets every host core back
+            torch.set_num_threads(len(all_cores))
             cpu = CpuPath()
             n_s = 16
             cpu.decoder_vocoder(torch.randn(2, FRAMES, HIDDEN))           # page in

@@ -30,3 +30,45 @@ def get_device_info() -> dict:
 def clear_cache() -> None:
     if torch.cuda.is_available():
         torch.cuda.empty_cache()
+
+
+def _parse_cpulist(text: str) -> list:
+    cpus = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.extend(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_host_to_gpu(device: torch.device, local_rank: int = 0, local_world: int = 1) -> dict:
+    """Pin the calling process to the host cores next to `device` (the NUMA node of its PCIe root, from sysfs) and, when several
+    ranks share that node, to this rank's slice of them. Call it BEFORE allocating pinned host buffers: `cudaHostAlloc` pages
+    are first touched by the allocating thread, so they land in the local node's memory. With eight ranks copying
+    85 MB in and 56 MB out per step, un-pinned ranks share cores and memory channels and the host -> host number loses 8 % at
+    eight GPUs (round 1: 0.92 of linear) while the device-resident one stays flat. Returns what it did (for the bench line)."""
+    info = {"bound": False}
+    try:
+        prop = torch.cuda.get_device_properties(device)
+        bdf = f"{prop.pci_domain_id:04x}:{prop.pci_bus_id:02x}:{prop.pci_device_id:02x}.0"
+        base = f"/sys/bus/pci/devices/{bdf}"
+        with open(f"{base}/local_cpulist") as f:
+            cpus = _parse_cpulist(f.read())
+        node = -1
+        try:
+            with open(f"{base}/numa_node") as f:
+                node = int(f.read().strip())
+        except OSError:
+            pass
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return info
+        if local_world > 1 and len(allowed) >= 2 * local_world:      # this rank's contiguous slice
+            per = len(allowed) // local_world
+            allowed = allowed[local_rank * per:(local_rank + 1) * per]
+        os.sched_setaffinity(0, allowed)
+        info.update(bound=True, pci=bdf, numa_node=node, cores=len(allowed), first_core=allowed[0])
+    except (OSError, AttributeError, ValueError, RuntimeError, AssertionError):      # no sysfs entry, no driver: leave the process alone
+        pass
+    return info

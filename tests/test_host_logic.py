@@ -7,6 +7,8 @@ import wave
 
 import numpy as np
 import pytest
+import os
+
 import torch
 
 import helpers as H
@@ -137,3 +139,13 @@ def test_shard_bounds_cover_and_partition():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [hi - lo for lo, hi in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_cpulist_parsing_and_binding_without_a_gpu():
+    from utils.device import _parse_cpulist, bind_host_to_gpu
+    assert _parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert _parse_cpulist("") == []
+    if not torch.cuda.is_available():
+        before = os.sched_getaffinity(0)
+        assert bind_host_to_gpu(torch.device("cuda", 0)) == {"bound": False}      # no device: nothing is touched
+        assert os.sched_getaffinity(0) == before
