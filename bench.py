@@ -264,7 +264,8 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     all_cores = os.sched_getaffinity(0)
-    host_binding = bind_host_to_gpu(dev, local_rank, world)      # before the pinned buffers are allocated (first touch)
+    host_binding = ({"bound": False, "why": "--no-bind"} if args.no_bind else
+                    bind_host_to_gpu(dev, local_rank, world))      # before the pinned buffers are allocated (first touch)
     dist = setup_dist(world, dev)
 
     torch.manual_seed(1234)
@@ -663,6 +664,7 @@ def run_secondary(args, local_rank: int):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--no-bind", action="store_true", help="do not pin the rank to the cores next to its GPU (A/B of the host -> host number)")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
