@@ -350,23 +350,10 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         dur[b, torch.randperm(S, generator=g)[:FRAMES - 13 * S]] = 14.0
     dur_host = (dur + 0.5).pin_memory()
 
-    def synth_from_ids(ids, lens, durs):
-        return model(ids, lens, target_durations=durs, max_target_length=FRAMES)["audio_output"]
+    from utils.host_pipeline import synthesize_to_host
 
     def ids_step():
-        n = args.e2e_chunks
-        outs = []
-        for lo, hi in HostPipeline.bounds(BATCH, n):
-            i_d = ids_host[lo:hi].to(dev, non_blocking=True)
-            l_d = len_host[lo:hi].to(dev, non_blocking=True)
-            d_d = dur_host[lo:hi].to(dev, non_blocking=True)
-            y = synth_from_ids(i_d, l_d, d_d)
-            done = torch.cuda.Event(); done.record()
-            with torch.cuda.stream(pipe.d2h):
-                pipe.d2h.wait_event(done)
-                audio_host[lo:hi].copy_(y, non_blocking=True)
-            y.record_stream(pipe.d2h)
-            outs.append(y)
+        synthesize_to_host(model, ids_host, len_host, dur_host, FRAMES, audio_host, pipe)
         pipe.d2h.synchronize()
 
     with nat.deferred_status():
@@ -484,7 +471,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                 "e2e_from_ids": {"value": ids_value, "unit": UNIT, "ms_per_step": ids_ms / args.steps,
                                  "h2d_bytes_per_step": ids_host.numel() * 8 + len_host.numel() * 8 + dur_host.numel() * 4,
                                  "d2h_bytes_per_step": audio_host.numel() * 4,
-                                 "api": f"M2TTSModel.forward(ids[{BATCH},{S}], lengths, target_durations, max_target_length={FRAMES}) in {args.e2e_chunks} utterance chunks, pinned host ids in, pinned host waveform out"},
+                                 "api": f"utils.host_pipeline.synthesize_to_host(model, ids[{BATCH},{S}], lengths, target_durations, max_target_length={FRAMES}): acoustic front once, decoder + vocoder in {args.e2e_chunks} utterance chunks, pinned host ids in, pinned host waveform out"},
                 "parity": parity,
                 "roofline": roof, "stage_roofline": stage_roofline, "stage_tflops": all_stage_tflops,
                 "stage_ms_per_step": {k: round(v[0] / prof_steps, 4) for k, v in sorted(stage_ms.items(), key=lambda kv: -kv[1][0])},

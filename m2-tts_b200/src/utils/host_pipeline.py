@@ -87,3 +87,32 @@ class HostPipeline:
 
     def synchronize(self) -> None:
         self.d2h.synchronize()
+
+
+def synthesize_to_host(model, ids_host: torch.Tensor, lengths_host: Optional[torch.Tensor], durations_host: Optional[torch.Tensor],
+                       max_target_length: int, out_host: torch.Tensor, pipe: HostPipeline) -> None:
+    """The whole model from HOST phoneme ids to a HOST waveform: `out_host[b] = model(ids[b], ...)["audio_output"]`.
+
+    The acoustic front (text encoder, duration predictor, length regulator: < 5 % of the work, launch-bound) runs ONCE over the
+    whole batch; decoder + vocoder then run in `pipe.n_chunks` utterance chunks so each chunk's waveform copy overlaps the next
+    chunk's compute (the inputs are a few hundred KB: nothing to hide on the way in). Same results as one `model.forward`
+    (utterances are independent in eval mode given a shared `max_target_length`). Returns after enqueueing —
+    call `pipe.synchronize()` before reading `out_host`. Reference call site: scripts/synthesize.py:66-83."""
+    if model.training:
+        raise RuntimeError("synthesize_to_host runs the eval-mode path: call model.eval() first")
+    dev = pipe.device
+    compute = torch.cuda.current_stream(dev)
+    ids = ids_host.to(dev, non_blocking=True)
+    lens = None if lengths_host is None else lengths_host.to(dev, non_blocking=True)
+    durs = None if durations_host is None else durations_host.to(dev, non_blocking=True)
+    enc, _ = model.text_encoder(ids, lens)
+    pred = model.duration_predictor(enc)
+    reg = model.length_regulator(enc, durs if durs is not None else pred, max_target_length)
+    for lo, hi in HostPipeline.bounds(reg.shape[0], pipe.n_chunks, pipe.edge):
+        y = model.vocoder(model.decoder(reg[lo:hi]).transpose(1, 2))
+        done = torch.cuda.Event()
+        done.record(compute)
+        with torch.cuda.stream(pipe.d2h):
+            pipe.d2h.wait_event(done)
+            out_host[lo:hi].copy_(y, non_blocking=True)
+        y.record_stream(pipe.d2h)

@@ -300,3 +300,20 @@ def test_sharded_synthesis_over_nccl_equals_full_batch():
     ret = mgr.dict()
     mp.spawn(_nccl_worker, args=(world, port, ret), nprocs=world, join=True)
     assert dict(ret) == {0: True, 1: True}
+
+
+@pytest.mark.parametrize("n_chunks", [1, 3])
+def test_synthesize_to_host_equals_forward(n_chunks):
+    """utils.host_pipeline.synthesize_to_host (what bench.py reports as `e2e_from_ids`: acoustic front once, decoder + vocoder in
+    utterance chunks, waveform copies on a side stream) returns bit-for-bit what one M2TTSModel.forward returns
+    (reference call site scripts/synthesize.py:66-83; tts_model.py:350-400)."""
+    from utils.host_pipeline import HostPipeline, synthesize_to_host
+    m = cuda_model("stage2", perturb=5)
+    ids, lengths, dur = H.small_inputs(7, 24, 256, seed=3)
+    T = int(dur.trunc().sum(dim=1).max())
+    want = m(ids.to(DEV), lengths.to(DEV), target_durations=dur.to(DEV), max_target_length=T)["audio_output"].cpu()
+    out = torch.full((7, 1, 64 * T), float("nan")).pin_memory()
+    pipe = HostPipeline(torch.device(DEV), n_chunks=n_chunks)
+    synthesize_to_host(m, ids.pin_memory(), lengths.pin_memory(), dur.pin_memory(), T, out, pipe)
+    pipe.synchronize()
+    assert torch.equal(out, want)
