@@ -249,6 +249,9 @@ struct LinHParams {
   void* qkvh; long long plane_stride; int L, nh, hd, Lp; float qscale;   // mode 3: attention operand planes
   int mode;
   int32_t* status;                 // M2TTS_ST_FP16_RANGE when an fp16-plane output leaves the fp16 range (may be null)
+  // A = split(LayerNorm(ln_x)) computed by the kernel's own producer warps from fp32 rows [R][K] (a_planes is ignored then):
+  // no ln_split_h launch, no round trip of the normalised planes through HBM
+  const float* ln_x; const float* ln_w; const float* ln_b; float ln_eps;
 };
 bool linear_h_eligible(int K, int N);
 int launch_ln_split_h(const float* x, const float* w, const float* b, void* planes, long long R, int K, float eps, int32_t* status, cudaStream_t s);

@@ -23,7 +23,9 @@ constexpr int LH_BM = 128;
 #endif
 constexpr int LH_G = LH_NG;                  // epilogue warpgroups: the 16-column chunks of a pass are dealt round-robin (one warp per
                                            // scheduler cannot hide the latency of its own dependent instructions)
-constexpr int LH_THREADS = 64 + 128 * LH_G;      // producer, issuer, epilogue warps
+constexpr int LH_LNU = 4;                        // row groups a LayerNorm producer warp has in flight (K <= 96 on this path)
+constexpr int LH_LNW = 8;                        // LayerNorm producer warps (A = split(LN(x)) written straight into the A ring)
+constexpr int LH_THREADS = 64 + 128 * LH_G + 32 * LH_LNW;      // TMA producer, issuer, epilogue warps, LayerNorm producers
 
 struct LinHArgs {
   int R, K, N;                     // rows, inner dim, outputs
@@ -43,6 +45,7 @@ struct LinHArgs {
   long long* prof;                 // bring-up: phase timestamps of CTA 0's first epilogue warp (m2tts_attention_set_prof buffer)
   int dbg;                         // bring-up timing experiments (M2TTS_LIN_DBG): 1 no stores, 2 no UMMAs, 4 no A-tile loads; results invalid
   int32_t* status;                 // fp16-plane outputs (modes 1, 3): M2TTS_ST_FP16_RANGE
+  const float* ln_x; const float* ln_w; const float* ln_b; float ln_eps;      // A = split(LayerNorm(ln_x)) by the producer warps (null: A tiles by TMA)
 };
 
 // Operand rows are 32 halves = 64 bytes (64-B swizzle): K = 96 is then exactly three boxes (with 128-byte rows a
@@ -86,7 +89,7 @@ lin_h_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
   const int S = a.a_stages;
 
   if (tid == 0) {
-    for (int i = 0; i < 4; ++i) { mbar_init(bar_af + 8 * i, 1); mbar_init(bar_ae + 8 * i, 1); }
+    for (int i = 0; i < 4; ++i) { mbar_init(bar_af + 8 * i, a.ln_x != nullptr ? (uint32_t)LH_LNW : 1u); mbar_init(bar_ae + 8 * i, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(bar_cf + 8 * i, 1); mbar_init(bar_ce + 8 * i, 4 * LH_G); }
     mbar_init(bar_w, 1); mbar_init(bar_rs, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -118,7 +121,7 @@ lin_h_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
             tma_load_2d(sW + (uint32_t)((kb * a.n_passes + p) * 2 + pl) * w_box, &tmap_w, kb * 32, pl * a.N + p * a.np, bar_w);
       pdl_wait();      // the weights are nobody's output; the A tiles are the previous kernel's
       int it = 0;
-      for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x, ++it) {
+      for (int mt = blockIdx.x; mt < m_tiles && a.ln_x == nullptr; mt += gridDim.x, ++it) {
         const int st = it % S;
         if (it >= S) mbar_wait(bar_ae + 8 * st, (uint32_t)(((it / S) - 1) & 1));
         if (a.dbg & 4) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_af + 8 * st) : "memory"); continue; }
@@ -158,6 +161,82 @@ lin_h_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         tc_commit_w(bar_cf + 8 * buf);
       }
       tc_commit_w(bar_ae + 8 * st);        // the A tile is free once every pass has read it
+    }
+  } else if (warp >= 2 + 4 * LH_G) {
+    // ===== LayerNorm producers (a.ln_x): A tile = split(LN(x rows)) written into the ring stage in the TMA box layout (per plane
+    // and 32-column k-box: 128 rows x 64 B, 64-byte swizzle). 8 lanes per row (a float4 per 32 columns each), 4 rows per warp
+    // pass, 32 rows per warp and tile. Replaces the ln_split_h launch and the HBM round trip of the normalised planes. =====
+    if (a.ln_x != nullptr) {
+      pdl_wait();
+      const int pw = warp - (2 + 4 * LH_G), sub = lane & 7;
+      const int n4 = a.K >> 5;                     // float4 per lane (K % 32 == 0, K <= 96)
+      float amax = 0.f;
+      static_assert(LH_LNW * 4 * LH_LNU == LH_BM, "LayerNorm producers: 16 rows per warp");
+      // A warp owns 16 rows of every tile: four row groups of 4 rows, 8 lanes per row. The rows of the NEXT tile are loaded into
+      // registers right after this tile's rows have been handed over, so their latency runs under the tile's UMMAs and epilogue
+      // (the ring has a single stage next to the QKV / FFN weights: without the prefetch every tile waited for its own loads).
+      float4 v[LH_LNU][3];
+      bool valid[LH_LNU];
+      auto load_tile = [&](int mt) {
+#pragma unroll
+        for (int u = 0; u < LH_LNU; ++u) {
+          const int r = pw * (4 * LH_LNU) + u * 4 + (lane >> 3);      // row of the tile
+          long long grow;
+          if (a.tpu > 0) { const int b = mt / a.tpu, l = (mt % a.tpu) * LH_BM + r; valid[u] = l < a.L; grow = (long long)b * a.L + l; }
+          else { grow = (long long)mt * LH_BM + r; valid[u] = grow < a.R; }
+          const float* xr = a.ln_x + (valid[u] ? grow : 0) * a.K;
+#pragma unroll
+          for (int i = 0; i < 3; ++i) v[u][i] = i < n4 ? __ldg(reinterpret_cast<const float4*>(xr + 32 * i + 4 * sub)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      };
+      int it = 0, mt = blockIdx.x;
+      if (mt < m_tiles) load_tile(mt);
+      for (; mt < m_tiles; ++it) {
+        const int st = it % S;
+        if (it >= S) mbar_wait(bar_ae + 8 * st, (uint32_t)(((it / S) - 1) & 1));
+        const uint32_t stage_off = (sA - sbase) + (uint32_t)st * a_stage;
+#pragma unroll
+        for (int u = 0; u < LH_LNU; ++u) {
+          const int r = pw * (4 * LH_LNU) + u * 4 + (lane >> 3);
+          float s = 0.f;
+#pragma unroll
+          for (int i = 0; i < 3; ++i) s += (v[u][i].x + v[u][i].y) + (v[u][i].z + v[u][i].w);
+          s += __shfl_xor_sync(0xffffffffu, s, 1); s += __shfl_xor_sync(0xffffffffu, s, 2); s += __shfl_xor_sync(0xffffffffu, s, 4);
+          const float mean = s / (float)a.K;
+          float q = 0.f;
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+            if (i < n4) {
+              const float d0 = v[u][i].x - mean, d1 = v[u][i].y - mean, d2 = v[u][i].z - mean, d3 = v[u][i].w - mean;
+              q += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+            }
+          q += __shfl_xor_sync(0xffffffffu, q, 1); q += __shfl_xor_sync(0xffffffffu, q, 2); q += __shfl_xor_sync(0xffffffffu, q, 4);
+          const float rstd = 1.0f / sqrtf(q / (float)a.K + a.ln_eps);
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+            if (i < n4) {
+              const int k = 32 * i + 4 * sub;
+              const float4 ww = __ldg(reinterpret_cast<const float4*>(a.ln_w + k)), bb = __ldg(reinterpret_cast<const float4*>(a.ln_b + k));
+              uint2 hv = make_uint2(0u, 0u), lv = make_uint2(0u, 0u);
+              if (valid[u]) {
+                const float y0 = (v[u][i].x - mean) * rstd * ww.x + bb.x, y1 = (v[u][i].y - mean) * rstd * ww.y + bb.y;
+                const float y2 = (v[u][i].z - mean) * rstd * ww.z + bb.z, y3 = (v[u][i].w - mean) * rstd * ww.w + bb.w;
+                h_split_pair(f2_pack(y0, y1), hv.x, lv.x, amax);
+                h_split_pair(f2_pack(y2, y3), hv.y, lv.y, amax);
+              }
+              // k-box i, row r, 16-byte chunk (4 sub) >> 3 = sub >> 1 swizzled by (r >> 1) & 3, 8 bytes at (sub & 1) * 8
+              const uint32_t off = (uint32_t)r * 64u + ((((uint32_t)sub >> 1) ^ ((uint32_t)(r >> 1) & 3u)) << 4) + ((uint32_t)sub & 1u) * 8u;
+              *reinterpret_cast<uint2*>(gbase + stage_off + (uint32_t)i * a_box + off) = hv;
+              *reinterpret_cast<uint2*>(gbase + stage_off + (uint32_t)(a.kboxes + i) * a_box + off) = lv;
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the UMMAs read these rows through the async proxy
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_af + 8 * st) : "memory");
+        mt += (int)gridDim.x;
+        if (mt < m_tiles) load_tile(mt);
+      }
+      h_flag(h_amax_bad(amax), a.status);
     }
   } else {
     // ===== epilogue warpgroup eg: thread = row of the tile, chunks eg, eg + G, ... of every pass =====
@@ -505,6 +584,7 @@ extern long long* g_ws_prof;      // attention_tc.cu (m2tts_attention_set_prof)
 // a_planes: fp16 [2][R][K]; w_planes: fp16 [2][N][K]
 int launch_linear_h(const void* a_planes, const void* w_planes, const LinHParams& q, int stage, cudaStream_t s) {
   M2_REQUIRE(linear_h_eligible(q.K, q.N), M2TTS_E_UNSUPPORTED, "linear_h: K=%d N=%d not eligible", q.K, q.N);
+  if (q.ln_x != nullptr) a_planes = w_planes;      // unused: the tensor map below is never dereferenced
   M2_REQUIRE((((uintptr_t)a_planes) & 15) == 0 && (((uintptr_t)w_planes) & 15) == 0 && (q.K & 7) == 0, M2TTS_E_BADSHAPE,
              "linear_h: misaligned operands");
   EncodeTiledFn5 enc = lh_encode_fn();
@@ -518,6 +598,9 @@ int launch_linear_h(const void* a_planes, const void* w_planes, const LinHParams
   { static int ps = -2; if (ps == -2) ps = tools_env_int("M2TTS_LIN_PROF_STAGE", -1); a.prof = (ps >= 0 && ps == stage) ? g_ws_prof : nullptr; }
   { static int dbg = -1; if (dbg < 0) dbg = tools_env_int("M2TTS_LIN_DBG", 0); a.dbg = dbg; }
   a.status = q.status;
+  a.ln_x = q.ln_x; a.ln_w = q.ln_w; a.ln_b = q.ln_b; a.ln_eps = q.ln_eps;
+  M2_REQUIRE(q.ln_x == nullptr || (q.ln_w != nullptr && q.ln_b != nullptr && (((uintptr_t)q.ln_x) & 15) == 0 && q.K <= 96), M2TTS_E_BADSHAPE,
+             "linear_h: LayerNorm producer needs weight, bias, 16-byte aligned rows and K <= 96");
   const size_t a_stage = (size_t)2 * a.kboxes * LH_BM * 64, w_bytes = (size_t)a.kboxes * 2 * a.N * 64;
   const bool stage3 = q.mode == 3 && a.np == q.nh * q.hd && q.L > 0 && q.R % q.L == 0 && q.plane_stride == (long long)(q.R / q.L) * q.nh * q.hd * q.Lp &&
                       (q.Lp & 7) == 0 && (((uintptr_t)q.qkvh) & 15) == 0;

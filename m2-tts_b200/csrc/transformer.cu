@@ -143,12 +143,14 @@ extern "C" int m2tts_transformer_layer(const m2tts_layer_weights* w, const void*
   // ---- 16-bit split path (default): every GEMM of the layer on tcgen05 with fp16 hi/lo operand planes, persistent
   //      weight-resident linear kernels (lin_h.cu) and the warp-specialised attention (attention_h.cu) ----
   if (fam == FAM_H) {
-    if ((rc = launch_ln_split_h(x_in, w->norm1_w, w->norm1_b, ws.xn, R, H, ln_eps, status, s))) return rc;
     const int Lp = (L + 7) & ~7;
+    const bool ln_fused = H <= 96;      // LayerNorm + split by the GEMM's own producer warps (lin_h.cu), else a separate ln_split_h launch
+    if (!ln_fused && (rc = launch_ln_split_h(x_in, w->norm1_w, w->norm1_b, ws.xn, R, H, ln_eps, status, s))) return rc;
     {  // attention operand planes = split(LN1(x) Wqkv^T)
       LinHParams q{};
       q.R = R; q.K = H; q.N = 3 * H; q.mode = 3; q.qkvh = ws.q; q.plane_stride = (long long)B * H * Lp; q.status = status;
       q.L = L; q.nh = num_heads; q.hd = hd; q.Lp = Lp; q.qscale = (float)((1.0 / sqrt((double)hd)) * 1.4426950408889634);
+      if (ln_fused) { q.ln_x = x_in; q.ln_w = w->norm1_w; q.ln_b = w->norm1_b; q.ln_eps = ln_eps; }
       if ((rc = launch_linear_h(ws.xn, wimg[0], q, M2TTS_STAGE_LN_QKV, s))) return rc;
     }
     if ((rc = launch_attention_h(ws.q, nullptr, lengths, B, L, Lp, num_heads, hd, s, nullptr, ws.ctx, status))) return rc;
@@ -157,10 +159,11 @@ extern "C" int m2tts_transformer_layer(const m2tts_layer_weights* w, const void*
       q.R = R; q.K = H; q.N = H; q.mode = 0; q.bias = w->out_b; q.residual = x_in; q.ldr = H; q.y = ws.x1; q.ldy = H;
       if ((rc = launch_linear_h(ws.ctx, wimg[1], q, M2TTS_STAGE_OUTPROJ, s))) return rc;
     }
-    if ((rc = launch_ln_split_h(ws.x1, w->norm2_w, w->norm2_b, ws.xn, R, H, ln_eps, status, s))) return rc;
+    if (!ln_fused && (rc = launch_ln_split_h(ws.x1, w->norm2_w, w->norm2_b, ws.xn, R, H, ln_eps, status, s))) return rc;
     {  // hid = relu(LN2(x1) W1^T + b1) as planes
       LinHParams q{};
       q.R = R; q.K = H; q.N = F; q.mode = 1; q.bias = w->ffn1_b; q.relu = 1; q.y_planes = ws.hid; q.status = status;
+      if (ln_fused) { q.ln_x = ws.x1; q.ln_w = w->norm2_w; q.ln_b = w->norm2_b; q.ln_eps = ln_eps; }
       if ((rc = launch_linear_h(ws.xn, wimg[2], q, M2TTS_STAGE_FFN1, s))) return rc;
     }
     {  // y = x1 + hid W2^T + b2
@@ -308,9 +311,10 @@ extern "C" int m2tts_layernorm_proj(const float* x, const float* ln_w, const flo
     return rc;
   }
   if (fam == FAM_H) {
-    if ((rc = launch_ln_split_h(x, ln_w, ln_b, xn, rows, H, eps, status, s))) return rc;
     LinHParams q{};
-    q.R = rows; q.K = H; q.N = N; q.mode = 0; q.bias = bias; q.y = y; q.ldy = N;
+    q.R = rows; q.K = H; q.N = N; q.mode = 0; q.bias = bias; q.y = y; q.ldy = N; q.status = status;
+    if (H <= 96) { q.ln_x = x; q.ln_w = ln_w; q.ln_b = ln_b; q.ln_eps = eps; }      // LayerNorm + split by the GEMM's producer warps
+    else if ((rc = launch_ln_split_h(x, ln_w, ln_b, xn, rows, H, eps, status, s))) return rc;
     return launch_linear_h(xn, wt, q, M2TTS_STAGE_LN_PROJ, s);
   }
   if (fam == FAM_TF32) {
