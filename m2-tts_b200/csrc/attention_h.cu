@@ -140,6 +140,7 @@ attention_h_kernel(const __grid_constant__ CUtensorMap tmap, const __half* __res
   const uint32_t bar_kf = sBar + 112, bar_ke = bar_kf + 8 * AH_STAGES, bar_vf = bar_ke + 8 * AH_STAGES, bar_ve = bar_vf + 8 * AH_STAGES;
   const uint32_t tmem_slot = bar_ve + 8 * AH_STAGES;
   const uint32_t bar_qh = tmem_slot + 8;
+  const uint32_t bar_p2 = bar_qh + 16;      // p_ready of the second half of P, [2 tiles][2 warpgroups] (its own barriers: a fast warp's two arrivals must not land in one phase)
 
   // warp index as a shuffle broadcast: ptxas then knows it is warp-uniform, the role branches are uniform branches and the
   // issuer's descriptor arithmetic can live in uniform registers
@@ -166,7 +167,7 @@ attention_h_kernel(const __grid_constant__ CUtensorMap tmap, const __half* __res
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_qf + 8 * i, 1); mbar_init(bar_sf + 16 * i, 1); mbar_init(bar_sf + 16 * i + 8, 1);
       mbar_init(bar_pr + 16 * i, 4); mbar_init(bar_pr + 16 * i + 8, 4); mbar_init(bar_pv + 8 * i, 1); mbar_init(bar_done + 8 * i, 1);
-      mbar_init(bar_qh + 8 * i, 8);
+      mbar_init(bar_qh + 8 * i, 8); mbar_init(bar_p2 + 16 * i, 4); mbar_init(bar_p2 + 16 * i + 8, 4);
     }
     for (int i = 0; i < AH_STAGES; ++i) {
       mbar_init(bar_kf + 8 * i, 1); mbar_init(bar_ke + 8 * i, (uint32_t)ntq); mbar_init(bar_vf + 8 * i, 1); mbar_init(bar_ve + 8 * i, (uint32_t)ntq);
@@ -237,17 +238,18 @@ attention_h_kernel(const __grid_constant__ CUtensorMap tmap, const __half* __res
                         (term | ks) ? 1u : 0u);
       }
     };
-    auto issue_pv = [&](int st, int buf, uint32_t accumulate) {
+    auto issue_pv = [&](int st, int buf, int half, uint32_t accumulate) {
       if (dbg_skip & 2) return;
       const uint32_t v = sV + (uint32_t)st * AhSmem<HD>::kv_bytes;
       const uint32_t tb = tmem_base + (uint32_t)x * AH_COL_TILE;
       const uint32_t pb = tb + AH_COL_S + (uint32_t)buf * 64u;
+      // the softmax publishes P in two halves (16-key groups 2, 3 first, then 0, 1): `half` 0 issues the k-steps of the first
 #pragma unroll
-      for (int ks = 0; ks < TC_BK / 16; ++ks)
-        umma_f16_ts_w(tb + AH_COL_O, pb + ks * 16, umma_desc(v + ks * 32u, 16u, 1024u, 2u), IDESC_PV2, ks ? 1u : accumulate);
-#pragma unroll
-      for (int ks = 0; ks < TC_BK / 16; ++ks)
+      for (int kk = 0; kk < 2; ++kk) {
+        const int ks = (half == 0 ? 2 : 0) + kk;
+        umma_f16_ts_w(tb + AH_COL_O, pb + ks * 16, umma_desc(v + ks * 32u, 16u, 1024u, 2u), IDESC_PV2, (half | kk) ? 1u : accumulate);
         umma_f16_ts_w(tb + AH_COL_O, pb + ks * 16 + 8, umma_desc(v + ks * 32u, 16u, 1024u, 2u), IDESC_PV1, 1u);
+      }
     };
     for (int t = 0; t < 2 && t < nkt; ++t) {      // prologue: the scores of key tiles 0 and 1
       mbar_wait(bar_kf + 8 * t, 0);
@@ -262,10 +264,14 @@ attention_h_kernel(const __grid_constant__ CUtensorMap tmap, const __half* __res
     }
     for (int t = 0; t < nkt; ++t) {
       const int st = t % AH_STAGES, s2 = (t + 2) % AH_STAGES, buf = t & 1;
-      mbar_wait(bar_pr + 16 * x + 8 * buf, (uint32_t)((t >> 1) & 1));      // P(x,t) is in TMEM (and O has been rescaled if needed)
+      // P(x,t) arrives in two halves, each with its own barrier; O has been rescaled if needed
+      mbar_wait(bar_pr + 16 * x + 8 * buf, (uint32_t)((t >> 1) & 1));
       mbar_wait(bar_vf + 8 * st, (uint32_t)((t / AH_STAGES) & 1));
       tc_fence_after();
-      issue_pv(st, buf, t > 0 ? 1u : 0u);
+      issue_pv(st, buf, 0, t > 0 ? 1u : 0u);
+      mbar_wait(bar_p2 + 16 * x + 8 * buf, (uint32_t)((t >> 1) & 1));
+      tc_fence_after();
+      issue_pv(st, buf, 1, 1u);
       tc_commit_w(bar_pv + 8 * x);
       if (t == nkt - 1) tc_commit_w(bar_done + 8 * x);
       tc_commit_w(bar_ve + 8 * st);
@@ -436,6 +442,11 @@ attention_h_kernel(const __grid_constant__ CUtensorMap tmap, const __half* __res
       tmem_wait_ld();
       if (need_mask) { mask16(sc, kbase); mask16(sd, kbase + 16); }
       exp_and_split(sc, sb, 48);                // group 0 | group 3
+      // groups 2 and 3 of P are stored: the issuer may start their P V k-steps while groups 0 and 1 are still being computed
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_pr + 16 * x + 8 * wg) : "memory");
       exp_and_split(sd, sc, 0);                 // group 1 | group 0
       exp_and_split(nullptr, sd, 16);           //         | group 1
       AH_PROF(pt, pp[4] = clock64());
@@ -443,7 +454,7 @@ attention_h_kernel(const __grid_constant__ CUtensorMap tmap, const __half* __res
       AH_PROF(pt, pp[5] = clock64());
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_pr + 16 * x + 8 * wg) : "memory");
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_p2 + 16 * x + 8 * wg) : "memory");
     }
     // the warpgroup that did not own the last key tile takes over its decision (the final m_ref)
     if (((nkt - 1) & 1) != wg) {
