@@ -208,7 +208,7 @@ int m2tts_layernorm_proj(const float* x, const float* ln_w, const float* ln_b,
                          size_t workspace_bytes, m2tts_stream_t stream);
 
 /* ---- duration predictor (tts_model.py:99-117) ------------------------------ */
-/* enc [B,S,H] -> dur [B,S] = softplus(proj(ConvBlock(ConvBlock(enc^T)))) */
+/* enc [B,S,H] -> dur [B,S] = softplus(proj(ConvBlock(ConvBlock(enc^T)))); H a multiple of 4 (M2TTS_E_UNSUPPORTED otherwise) */
 int m2tts_duration_predictor(const m2tts_durpred_weights* w, const float* enc,
                              float* dur, int B, int S, int H,
                              m2tts_stream_t stream);
@@ -297,6 +297,7 @@ int m2tts_vocoder_stage_fused(const float* x, const float* up_w, const float* up
                               void* workspace, size_t workspace_bytes, m2tts_stream_t stream);
 
 /* The same stage with the 16-bit split: what m2tts_vocoder_forward uses for its narrow stages by default.
+ * C in {16, 32}, and C = 8 as the LAST stage only (out_w != NULL: runs zero-padded in the 16-channel kernel — the stage-1 model).
  * Same arguments plus the status word; workspace: m2tts_vocoder_stage_fused_h_workspace_bytes(B, C, L). */
 size_t m2tts_vocoder_stage_fused_h_workspace_bytes(int B, int C, int L);
 int m2tts_vocoder_stage_fused_h(const float* x, const float* up_w, const float* up_b, const float* res1_w,
@@ -305,7 +306,7 @@ int m2tts_vocoder_stage_fused_h(const float* x, const float* up_w, const float* 
                                 int32_t* status, void* workspace, size_t workspace_bytes, m2tts_stream_t stream);
 
 /* A whole LightweightResBlock (components.py:177-200), y = x + conv2(leaky_relu(conv1(x), 0.1)), as one tcgen05 kernel with
- * the 16-bit split; x / y fp32 CHANNEL-LAST [B][L][C], C = 64, kernel 3, dilation 1; weights in state_dict layout [C][C][3].
+ * the 16-bit split; x / y fp32 CHANNEL-LAST [B][L][C], C in {32, 64}, kernel 3, dilation 1; weights in state_dict layout [C][C][3].
  * workspace: m2tts_resblock_fused_h_workspace_bytes(B, C, L). */
 size_t m2tts_resblock_fused_h_workspace_bytes(int B, int C, int L);
 int m2tts_resblock_fused_h(const float* x, const float* w1, const float* b1, const float* w2, const float* b2, float* y,
@@ -321,7 +322,7 @@ int m2tts_conv1d_k3_h(const float* x, const float* w, const float* b, const floa
                       int act, int out_cl, int32_t* status, void* workspace, size_t workspace_bytes, m2tts_stream_t stream);
 
 /* One upsampling layer of the vocoder with its activation (tts_model.py:255-263,291):
- * y = leaky_relu(conv_transpose1d(x, w, b, stride 4, padding 2), 0.1), kernel 8, CI in {128, 256}, CO = CI / 2, 16-bit split,
+ * y = leaky_relu(conv_transpose1d(x, w, b, stride 4, padding 2), 0.1), kernel 8, CI in {64, 128, 256}, CO = CI / 2, 16-bit split,
  * channel-last operands: x fp32 [B][L][CI], w [CI][CO][8] (state_dict layout), y fp32 [B][4L][CO].
  * workspace: m2tts_conv_transpose_x4_h_workspace_bytes(B, CI, L). */
 size_t m2tts_conv_transpose_x4_h_workspace_bytes(int B, int CI, int L);
