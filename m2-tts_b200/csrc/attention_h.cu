@@ -91,6 +91,15 @@ __device__ __forceinline__ void ah_st8(uint32_t taddr, const uint32_t* r) {
 __device__ __forceinline__ void ah_st4(uint32_t taddr, const uint32_t* r) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
 }
+__device__ __forceinline__ void ah_ld8(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
+}
+__device__ __forceinline__ uint32_t ah_lds16(uint32_t saddr) {
+  unsigned short v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(saddr));
+  return v;
+}
 __device__ __forceinline__ float ws_ex2v(float x) {      // ex2 that keeps its place in the instruction stream
   float y;
   asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -120,6 +129,15 @@ attention_h_kernel(const __grid_constant__ CUtensorMap tmap, const __half* __res
                     long long* __restrict__ prof, int dbg_skip, int32_t* __restrict__ status) {
   static_assert(HD % 16 == 0 && HD >= 16 && HD <= 64, "16-bit split attention: head_dim in {16,32,48,64}");
   pdl_launch_dependents();      // M2_LAUNCH_PDL: every global access below follows a pdl_wait()
+#ifdef M2TTS_TOOLS
+  long long cta_t0 = 0, cta_c0 = 0;
+  if (prof != nullptr && threadIdx.x == 0) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(cta_t0)); cta_c0 = clock64(); }
+  const bool pc = prof != nullptr && blockIdx.x == 600 && threadIdx.x == 128;      // phase stamps of one mid-kernel CTA: prof[512 + k]
+#define AH_STAMP(k) do { if (pc) prof[512 + (k)] = clock64(); } while (0)
+  AH_STAMP(0);
+#else
+#define AH_STAMP(k) do { } while (0)
+#endif
   constexpr uint32_t BOX = AhSmem<HD>::box;
   constexpr int KSTEPS_D = HD / 16;
   constexpr bool QT = (128 + 2 * HD + HD / 2) <= 256;             // Q_hi as a TMEM A operand (head_dim <= 48), else from shared memory
@@ -186,14 +204,15 @@ attention_h_kernel(const __grid_constant__ CUtensorMap tmap, const __half* __res
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);
+  AH_STAMP(1);
 
   if (warp == 0) {
     if (lane == 0) {
       // ===== loader =====
       pdl_wait();
       for (int x = 0; x < ntq; ++x) {
-        mbar_expect_tx(bar_qf + 8 * x, QT ? AhSmem<HD>::q_bytes / 2 : AhSmem<HD>::q_bytes);
-        for (int h = QT ? 1 : 0; h < 2; ++h)
+        mbar_expect_tx(bar_qf + 8 * x, AhSmem<HD>::q_bytes);      // Q_hi too: the softmax warps copy it from shared memory into TMEM
+        for (int h = 0; h < 2; ++h)
           for (int j = 0; j < 2; ++j)
             tma_load_2d(sQ + (uint32_t)x * AhSmem<HD>::q_bytes + (h * 2 + j) * BOX, &tmap, q0 + x * TC_BQ + j * 64, h * plane + row_q,
                         bar_qf + 8 * x);
@@ -291,22 +310,27 @@ attention_h_kernel(const __grid_constant__ CUtensorMap tmap, const __half* __res
     const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)x * AH_COL_TILE;
     float* exch = reinterpret_cast<float*>(smem_raw + (sbase - smem_u32(smem_raw)) + AhSmem<HD>::off_exch);
     float* mref_s = exch + x * 128;               // per-row reference maximum of the running softmax
-    float* lsum_s = exch + 256 + x * 128;         // row sums of warpgroup 1 at the end
+    float* lsum_s = exch + 256 + x * 128;         // final row sums: warpgroup wg writes [wg * 256 + row]
     const int hb = 1 + x * 2;                     // named barriers hb / hb + 1: hand-off of the m_ref decision of even / odd key tiles
     pdl_wait();                                   // Q is read from global memory below; ctx is written at the end
     if (QT) {
-      // Q_hi -> TMEM as the A operand of Q K^T (see attention_h_kernel); this warpgroup writes the d range [wg hd/2, (wg+1) hd/2)
+      // Q_hi -> TMEM as the A operand of Q K^T (see attention_h_kernel); this warpgroup writes the d range [wg hd/2, (wg+1) hd/2).
+      // The rows come from the TMA-loaded Q_hi boxes in shared memory (MN-major, 128-byte swizzle: element (d, position p) of a
+      // 64-position box at d * 128 + ((2 p) ^ ((d & 7) << 4)); a warp reads 64 contiguous bytes per d). Read from global memory
+      // (2-byte loads 2 Lp bytes apart) this copy took 4.8 k cycles of every CTA's start (tools/attn_cta_prof.py).
       const int qi = q0 + x * TC_BQ + row;
-      const __half* qp = qkvh + ((long long)row_q + wg * (HD / 2)) * Lp + qi;
+      const uint32_t qs = sQ + (uint32_t)x * AhSmem<HD>::q_bytes + (uint32_t)(row >> 6) * BOX;
+      const uint32_t p2 = (uint32_t)(row & 63) * 2u;
+      mbar_wait(bar_qf + 8 * x, 0);
 #pragma unroll
       for (int c4 = 0; c4 < HD / 16; ++c4) {
         uint32_t w[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const int d = (c4 * 4 + e) * 2;
-          unsigned short lo = 0, hi = 0;
-          if (qi < L) { lo = __half_as_ushort(qp[(long long)d * Lp]); hi = __half_as_ushort(qp[(long long)(d + 1) * Lp]); }
-          w[e] = (uint32_t)lo | ((uint32_t)hi << 16);
+          const uint32_t d = (uint32_t)(wg * (HD / 2) + (c4 * 4 + e) * 2);
+          const uint32_t lo = ah_lds16(qs + d * 128u + (p2 ^ ((d & 7u) << 4)));
+          const uint32_t hi = ah_lds16(qs + (d + 1u) * 128u + (p2 ^ (((d + 1u) & 7u) << 4)));
+          w[e] = qi < L ? (lo | (hi << 16)) : 0u;
         }
         ah_st4(t_lane + AH_COL_Q + (uint32_t)(wg * (HD / 4) + c4 * 4), w);
       }
@@ -315,6 +339,7 @@ attention_h_kernel(const __grid_constant__ CUtensorMap tmap, const __half* __res
       __syncwarp();
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_qh + 8 * x) : "memory");
     }
+    AH_STAMP(2);
     float m_c = -INFINITY;                                // the m_ref this warpgroup's row sum is scaled to
     uint64_t l2 = ah_pack(0.f, 0.f);                      // running row sum as a packed pair (even keys, odd keys)
 #ifdef M2TTS_TOOLS
@@ -354,6 +379,7 @@ attention_h_kernel(const __grid_constant__ CUtensorMap tmap, const __half* __res
       AH_PROF(pt, pp[0] = clock64());
       mbar_wait(bar_sf + 16 * x + 8 * wg, (uint32_t)((t >> 1) & 1));
       AH_PROF(pt, pp[1] = clock64());
+      if (t == 0) AH_STAMP(3);
       __syncwarp();
       tc_fence_after();
       const int kbase = t * TC_BK;
@@ -456,76 +482,86 @@ attention_h_kernel(const __grid_constant__ CUtensorMap tmap, const __half* __res
       __syncwarp();
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_p2 + 16 * x + 8 * wg) : "memory");
     }
+    AH_STAMP(4);
     // the warpgroup that did not own the last key tile takes over its decision (the final m_ref)
     if (((nkt - 1) & 1) != wg) {
       asm volatile("bar.sync %0, 256;" ::"r"(hb + ((nkt - 1) & 1)) : "memory");
       const float m_s = mref_s[row];
       if (m_s != m_c) rescale_l(m_s);
     }
+    // final row sum: each warpgroup holds the sum of its own key tiles (both in the scale of the final m_ref)
     float l_run;
     {
       float la, lb;
       ah_unpack(l2, la, lb);
       l_run = la + lb;
-      if (wg == 1) lsum_s[row] = l_run;
+      lsum_s[wg * 256 + row] = l_run;
       asm volatile("bar.sync %0, 256;" ::"r"(5 + x) : "memory");
-      if (wg == 0) l_run += lsum_s[row];
+      l_run += lsum_s[(wg ^ 1) * 256 + row];
     }
-    if (wg == 0) {
+    {
+      // both warpgroups of the query tile normalise and store: warpgroup wg takes the columns [wg hd/2, (wg+1) hd/2) of every row
+      // (done by one warpgroup this was 4.7 k cycles at the end of every CTA, the other one idle)
       mbar_wait(bar_done + 8 * x, 0);     // the last PV has landed: O is complete
+      AH_STAMP(5);
       __syncwarp();
       tc_fence_after();
-      float o[HD];
-#pragma unroll
-      for (int c = 0; c < HD; c += 16) {
-        uint32_t orr[16], or2[16];
-        tmem_ld16(t_lane + AH_COL_O + c, orr);
-        tmem_ld16(t_lane + AH_COL_O + HD + c, or2);
-        tmem_wait_ld();
-#pragma unroll
-        for (int j = 0; j < 16; ++j) o[c + j] = __uint_as_float(orr[j]) + __uint_as_float(or2[j]);
-      }
       const int qi = q0 + x * TC_BQ + row;
-      if (qi < L) {
-        const float inv = 1.0f / l_run;
-        float* dst = ctx + ((long long)b * L + qi) * (nh * HD) + head * HD;
-        if (ctx_h != nullptr) {   // fp16 hi/lo planes [2][B*L][nh*HD] for the 16-bit split out_proj (lin_h.cu)
-          __half* dh = ctx_h + ((long long)b * L + qi) * (nh * HD) + head * HD;
-          __half* dl = dh + (long long)B * L * (nh * HD);
-          bool bad = false;
+      const float inv = 1.0f / l_run;
+      const long long orow = ((long long)b * L + qi) * (nh * HD) + head * HD;
+      bool bad = false;
 #pragma unroll
-          for (int c = 0; c < HD; c += 8) {
+      for (int c = wg * (HD / 2); c < (wg + 1) * (HD / 2); c += 8) {
+        uint32_t orr[8], or2[8];
+        ah_ld8(t_lane + AH_COL_O + c, orr);
+        ah_ld8(t_lane + AH_COL_O + HD + c, or2);
+        tmem_wait_ld();
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = (__uint_as_float(orr[j]) + __uint_as_float(or2[j])) * inv;
+        if (qi < L) {
+          if (ctx_h != nullptr) {   // fp16 hi/lo planes [2][B*L][nh*HD] for the 16-bit split out_proj (lin_h.cu)
+            __half* dh = ctx_h + orow + c;
+            __half* dl = dh + (long long)B * L * (nh * HD);
             uint32_t hi[4], lo[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) h_split2(o[c + 2 * e] * inv, o[c + 2 * e + 1] * inv, hi[e], lo[e], bad);
-            *reinterpret_cast<uint4*>(dh + c) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<uint4*>(dl + c) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-          }
-          h_flag(bad, status);
-        } else if (ctx_lo == nullptr) {
+            for (int e = 0; e < 4; ++e) h_split2(o[2 * e], o[2 * e + 1], hi[e], lo[e], bad);
+            *reinterpret_cast<uint4*>(dh) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(dl) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          } else if (ctx_lo == nullptr) {
+            *reinterpret_cast<float4*>(ctx + orow + c) = make_float4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<float4*>(ctx + orow + c + 4) = make_float4(o[4], o[5], o[6], o[7]);
+          } else {   // TF32 hi/lo planes for the tensor-core out_proj
+            float h[8], l[8];
 #pragma unroll
-          for (int c = 0; c < HD; c += 4)
-            *reinterpret_cast<float4*>(dst + c) = make_float4(o[c] * inv, o[c + 1] * inv, o[c + 2] * inv, o[c + 3] * inv);
-        } else {   // TF32 hi/lo planes for the tensor-core out_proj
-          float* dlo = ctx_lo + ((long long)b * L + qi) * (nh * HD) + head * HD;
-#pragma unroll
-          for (int c = 0; c < HD; c += 4) {
-            float h[4], l[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) { const float v = o[c + e] * inv; h[e] = __uint_as_float(tf32_hi(v)); l[e] = __uint_as_float(tf32_hi(v - h[e])); }
-            *reinterpret_cast<float4*>(dst + c) = make_float4(h[0], h[1], h[2], h[3]);
-            *reinterpret_cast<float4*>(dlo + c) = make_float4(l[0], l[1], l[2], l[3]);
+            for (int e = 0; e < 8; ++e) { h[e] = __uint_as_float(tf32_hi(o[e])); l[e] = __uint_as_float(tf32_hi(o[e] - h[e])); }
+            *reinterpret_cast<float4*>(ctx + orow + c) = make_float4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<float4*>(ctx + orow + c + 4) = make_float4(h[4], h[5], h[6], h[7]);
+            *reinterpret_cast<float4*>(ctx_lo + orow + c) = make_float4(l[0], l[1], l[2], l[3]);
+            *reinterpret_cast<float4*>(ctx_lo + orow + c + 4) = make_float4(l[4], l[5], l[6], l[7]);
           }
         }
       }
+      if (ctx_h != nullptr) h_flag(bad, status);
     }
   }
+  AH_STAMP(6);
   tc_fence_before();
   __syncthreads();
+  AH_STAMP(7);
   if (warp == 0) {
     __syncwarp();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(AH_TMEM_COLS) : "memory");
   }
+#ifdef M2TTS_TOOLS
+  if (prof != nullptr && threadIdx.x == 0) {      // CTA lifetime (tools/attn_cta_prof.py): [start ns, end ns, SM, start clock, end clock] from word 1024 on
+    long long t1; uint32_t sm;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+    long long* w = prof + 1024 + 5 * (long long)blockIdx.x;
+    w[0] = cta_t0; w[1] = t1; w[2] = sm; w[3] = cta_c0; w[4] = clock64();
+  }
+#endif
 }
 
 typedef CUresult (*EncodeTiledFnH)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

@@ -8,26 +8,42 @@ eval mode, so chunking dim 0 does not change any result.
 """
 from __future__ import annotations
 
-from typing import Callable, List, Optional, Tuple
+from typing import Callable, List, Optional, Sequence, Tuple
 
 import torch
 
 
 class HostPipeline:
-    def __init__(self, device: torch.device, n_chunks: int = 2, edge: float = 1.0):
+    def __init__(self, device: torch.device, n_chunks: int = 2, edge: float = 1.0, sizes: Optional[Sequence[int]] = None):
         """`edge` < 1 makes the first and the last chunk smaller than the inner ones (their H2D / D2H copy is the part of
-        the PCIe traffic that nothing overlaps): edge = 0.5 with three chunks splits 64 utterances 16 / 32 / 16."""
+        the PCIe traffic that nothing overlaps): edge = 0.5 with three chunks splits 64 utterances 16 / 32 / 16.
+        `sizes` gives the chunk sizes explicitly (used when they sum to the batch; any other batch falls back to
+        `n_chunks` / `edge`): the attention kernel's CTAs come in waves of 148, so a chunk of 10, 16, 21, 27 or 32 ten-second
+        utterances fills its last wave and one of 11, 22 or 28 does not."""
         if n_chunks < 1:
             raise ValueError("n_chunks must be >= 1")
         if not 0.0 < edge <= 1.0:
             raise ValueError("edge must be in (0, 1]")
+        if sizes is not None and (len(sizes) == 0 or min(sizes) < 1):
+            raise ValueError("sizes must be positive")
         self.device = torch.device(device)
         self.n_chunks = n_chunks
         self.edge = edge
+        self.sizes = None if sizes is None else [int(v) for v in sizes]
         self.h2d = torch.cuda.Stream(device=self.device)
         self.d2h = torch.cuda.Stream(device=self.device)
         self._in: List[Optional[torch.Tensor]] = []
         self._free: List[Optional[torch.cuda.Event]] = []     # chunk input buffer i may be overwritten
+
+    def chunk_bounds(self, n: int) -> List[Tuple[int, int]]:
+        """The chunks of a batch of n utterances: the explicit `sizes` when they fit it, else `bounds(n, n_chunks, edge)`."""
+        if self.sizes is not None and sum(self.sizes) == n:
+            out, lo = [], 0
+            for sz in self.sizes:
+                out.append((lo, lo + sz))
+                lo += sz
+            return out
+        return self.bounds(n, self.n_chunks, self.edge)
 
     @staticmethod
     def bounds(n: int, chunks: int, edge: float = 1.0) -> List[Tuple[int, int]]:
@@ -56,7 +72,7 @@ class HostPipeline:
         if x_host.is_cuda or out_host.is_cuda:
             raise ValueError("HostPipeline.run takes HOST tensors")
         compute = torch.cuda.current_stream(self.device)
-        bnds = self.bounds(x_host.shape[0], self.n_chunks, self.edge)
+        bnds = self.chunk_bounds(x_host.shape[0])
         while len(self._in) < len(bnds):
             self._in.append(None)
             self._free.append(None)
@@ -108,7 +124,7 @@ def synthesize_to_host(model, ids_host: torch.Tensor, lengths_host: Optional[tor
     enc, _ = model.text_encoder(ids, lens)
     pred = model.duration_predictor(enc)
     reg = model.length_regulator(enc, durs if durs is not None else pred, max_target_length)
-    for lo, hi in HostPipeline.bounds(reg.shape[0], pipe.n_chunks, pipe.edge):
+    for lo, hi in pipe.chunk_bounds(reg.shape[0]):
         y = model.vocoder(model.decoder(reg[lo:hi]).transpose(1, 2))
         done = torch.cuda.Event()
         done.record(compute)

@@ -39,4 +39,22 @@ with nat.deferred_status():
         torch.cuda.synchronize()
         ms = (time.perf_counter() - t0) / 8 * 1e3
         print(f"chunks={chunks} edge={edge}: sizes {[hi - lo for lo, hi in HostPipeline.bounds(64, chunks, edge)]} -> {ms:.3f} ms per step")
+    import statistics
+    cands = ([22, 21, 21], [16, 16, 16, 16], [5, 27, 27, 5], [10, 16, 27, 11], [5, 16, 27, 16], [5, 22, 32, 5], [5, 27, 22, 10], [5, 16, 16, 22, 5],
+             [5, 21, 28, 10], [5, 32, 27], [3, 27, 29, 5], [5, 27, 27, 3, 2], [2, 3, 27, 27, 5], [5, 54, 5], [5, 21, 16, 16, 6], [8, 24, 24, 8])
+    res = {tuple(c): [] for c in cands}
+    pipes = {tuple(c): HostPipeline(dev, sizes=c) for c in cands}
+    for rnd in range(6):
+        for c in cands:
+            pipe = pipes[tuple(c)]
+            pipe.run(step, x_host, out); pipe.synchronize()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(5):
+                pipe.run(step, x_host, out); pipe.synchronize()
+            torch.cuda.synchronize()
+            res[tuple(c)].append((time.perf_counter() - t0) / 5 * 1e3)
+    for c in cands:
+        v = res[tuple(c)]
+        print(f"sizes {c}: median {statistics.median(v):.3f} min {min(v):.3f} max {max(v):.3f}")
 nat.check_status(dev, "e2e sweep")
