@@ -257,7 +257,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     from models import _native as nat
     from models.stage_configs import STAGE_KWARGS
     from models.tts_model import M2TTSModel
-    from utils.host_pipeline import HostPipeline
+    from utils.host_pipeline import HostPipeline, wave_chunk_sizes
 
     from utils.device import bind_host_to_gpu
 
@@ -325,7 +325,12 @@ def run_b200(args, rank: int, world: int, local_rank: int):
 
     # ---- e2e: pinned host in -> pinned host out, copies inside the timed region. The caller-facing helper
     # (utils.host_pipeline.HostPipeline) chunks the utterance batch so the PCIe copies overlap compute. ----
-    pipe = HostPipeline(dev, n_chunks=args.e2e_chunks, edge=args.e2e_edge)
+    if args.e2e_chunks > 0:
+        pipe = HostPipeline(dev, n_chunks=args.e2e_chunks, edge=args.e2e_edge)
+    else:      # default: chunk sizes that fill the attention kernel's waves of CTAs (utils.host_pipeline.wave_chunk_sizes)
+        pipe = HostPipeline(dev, sizes=wave_chunk_sizes(BATCH, FRAMES, model.decoder.layers[0].self_attn.num_heads,
+                                                       torch.cuda.get_device_properties(dev).multi_processor_count)))
+    pipe_desc = (f"sizes={pipe.sizes}" if pipe.sizes is not None else f"n_chunks={args.e2e_chunks}, edge={args.e2e_edge}")
     with nat.deferred_status():
         for _ in range(2):
             pipe.run(step, x_host, audio_host)
@@ -467,11 +472,11 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                         "d2h_bytes_per_step": audio_host.numel() * 4, "ms_per_step": e2e_ms / args.steps,
                         "exposed_copy_ms": e2e_ms / args.steps - total_ms / args.steps,
                         "host_binding": host_binding,
-                        "api": f"utils.host_pipeline.HostPipeline(n_chunks={args.e2e_chunks}, edge={args.e2e_edge}).run(decoder+vocoder, pinned host in, pinned host out)"},
+                        "api": f"utils.host_pipeline.HostPipeline({pipe_desc}).run(decoder+vocoder, pinned host in, pinned host out)"},
                 "e2e_from_ids": {"value": ids_value, "unit": UNIT, "ms_per_step": ids_ms / args.steps,
                                  "h2d_bytes_per_step": ids_host.numel() * 8 + len_host.numel() * 8 + dur_host.numel() * 4,
                                  "d2h_bytes_per_step": audio_host.numel() * 4,
-                                 "api": f"utils.host_pipeline.synthesize_to_host(model, ids[{BATCH},{S}], lengths, target_durations, max_target_length={FRAMES}): acoustic front once, decoder + vocoder in {args.e2e_chunks} utterance chunks, pinned host ids in, pinned host waveform out"},
+                                 "api": f"utils.host_pipeline.synthesize_to_host(model, ids[{BATCH},{S}], lengths, target_durations, max_target_length={FRAMES}): acoustic front once, decoder + vocoder in utterance chunks ({pipe_desc}), pinned host ids in, pinned host waveform out"},
                 "parity": parity,
                 "roofline": roof, "stage_roofline": stage_roofline, "stage_tflops": all_stage_tflops,
                 "stage_ms_per_step": {k: round(v[0] / prof_steps, 4) for k, v in sorted(stage_ms.items(), key=lambda kv: -kv[1][0])},
@@ -657,7 +662,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="c3", choices=["c3", "c1", "c2", "c5"], help="c3 = headline (BASELINE configs[2]); c1/c2/c5 = secondary lines")
     ap.add_argument("--skip-cpu-baseline", action="store_true", help="profiling runs: omit the CPU leg")
-    ap.add_argument("--e2e-chunks", type=int, default=3, help="utterance chunks of the host-to-host pipeline (1 = no overlap)")
+    ap.add_argument("--e2e-chunks", type=int, default=0, help="utterance chunks of the host-to-host pipeline (1 = no overlap; 0 = wave-filling sizes, utils.host_pipeline.wave_chunk_sizes)")
     ap.add_argument("--e2e-edge", type=float, default=1.0, help="relative size of the first and last chunk (their copies are the unhidden ones)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

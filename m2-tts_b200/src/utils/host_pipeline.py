@@ -105,6 +105,51 @@ class HostPipeline:
         self.d2h.synchronize()
 
 
+def attention_makespan(k: int, frames: int, heads: int, sms: int = 148) -> float:
+    """Time of the decoder's attention launch for a chunk of k utterances, in units of one two-query-tile CTA. The kernel
+    (csrc/attention_h.cu) runs one CTA per SM, longest first: k * heads * (tiles // 2) CTAs with two 128-query tiles, then — when
+    the tile count is odd — k * heads single-tile CTAs of half the duration."""
+    tiles = (frames + 127) // 128
+    doubles, singles = k * heads * (tiles // 2), k * heads * (tiles % 2)
+    full, rem = divmod(doubles, sms)
+    if rem == 0:
+        return full + 0.5 * ((singles + sms - 1) // sms)
+    # the last wave of two-tile CTAs leaves sms - rem SMs to the single-tile ones (two of them fit next to it)
+    left = singles - 2 * (sms - rem)
+    return full + 1.0 + (0.5 * ((left + sms - 1) // sms) if left > 0 else 0.0)
+
+
+def wave_chunk_sizes(n: int, frames: int, heads: int, sms: int = 148) -> List[int]:
+    """Chunk sizes for `HostPipeline(sizes=...)`: a small first and last chunk (their H2D / D2H copy is what nothing overlaps)
+    around two inner ones, every chunk chosen so that the attention launch — a third of the step, one CTA per SM — fills its last
+    wave of CTAs. For 64 utterances of 3446 frames on 148 SMs this gives 5 / 27 / 27 / 5 (tools/e2e_sweep.py: 7.30 ms per host-to-host
+    step against 7.85 for three equal chunks, whose 22-utterance chunk needs 4.5 waves for 4.0 waves of work)."""
+    if n < 8:
+        return [n]
+    per_utt = attention_makespan(1024, frames, heads, sms) / 1024.0      # asymptotic cost of one utterance
+
+    def eff(k: int) -> float:
+        return k * per_utt / attention_makespan(k, frames, heads, sms)
+
+    edges = [k for k in range(max(1, n // 16), max(2, n // 6) + 1)]
+    best, best_score = [n], -1.0
+    for e in edges:
+        inner = n - 2 * e
+        if inner < 2:
+            continue
+        for a in range(inner // 2, inner // 2 + 4):
+            b = inner - a
+            if a < 1 or b < 1:
+                continue
+            # efficiency of the whole layout, the edge chunks' exposed copies counted as lost time of their own size
+            work = n * per_utt
+            spent = sum(attention_makespan(k, frames, heads, sms) for k in (e, a, b, e)) + 0.25 * 2 * e * per_utt
+            score = work / spent
+            if score > best_score:
+                best, best_score = [e, a, b, e], score
+    return best
+
+
 def synthesize_to_host(model, ids_host: torch.Tensor, lengths_host: Optional[torch.Tensor], durations_host: Optional[torch.Tensor],
                        max_target_length: int, out_host: torch.Tensor, pipe: HostPipeline) -> None:
     """The whole model from HOST phoneme ids to a HOST waveform: `out_host[b] = model(ids[b], ...)["audio_output"]`.

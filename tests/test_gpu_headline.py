@@ -102,6 +102,29 @@ def test_host_pipeline_equals_direct_call(n_chunks):
         assert torch.equal(out_host, want), (n_chunks, rep)
 
 
+def test_host_pipeline_with_explicit_chunk_sizes_equals_direct_call():
+    """The wave-filling layout the bench uses (small edge chunks around larger inner ones, `HostPipeline(sizes=...)`) must not
+    change a bit either; sizes that do not sum to the batch fall back to the equal split."""
+    from models import _native as nat
+    from utils.host_pipeline import HostPipeline
+    m = cuda_model("stage2")
+    x_host = torch.randn(9, 300, 96, generator=torch.Generator().manual_seed(4)).pin_memory()
+    out_host = torch.empty((9, 1, 64 * 300)).pin_memory()
+
+    def step(x):
+        return m.vocoder(m.decoder(x).transpose(1, 2))
+
+    want = step(x_host.to(DEV)).cpu()
+    for sizes in ([1, 4, 3, 1], [2, 7], [5, 27, 27, 5]):
+        pipe = HostPipeline(torch.device(DEV), n_chunks=2, sizes=sizes)
+        out_host.fill_(float("nan"))
+        with nat.deferred_status():
+            pipe.run(step, x_host, out_host)
+        pipe.synchronize()
+        nat.check_status(torch.device(DEV))
+        assert torch.equal(out_host, want), sizes
+
+
 # --------------------------------------------------------------------------- status word
 def test_activations_beyond_the_fp16_range_fall_back_to_tf32():
     """the 16-bit split carries operands as fp16 hi + lo. Weights scaled so that (a) the FFN hidden activations

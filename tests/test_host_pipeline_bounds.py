@@ -29,3 +29,29 @@ def test_edge_chunks_are_smaller():
 def test_bounds_of_an_empty_batch():
     from utils.host_pipeline import HostPipeline
     assert HostPipeline.bounds(0, 3) == [] and HostPipeline.bounds(0, 3, 0.5) == []
+
+
+def test_wave_chunk_sizes_cover_the_batch_and_fill_attention_waves():
+    """utils.host_pipeline.wave_chunk_sizes: positive sizes that sum to the batch; for the C3 shape (64 x 3446 frames, 2 heads,
+    148 SMs) every chunk's attention launch ends on a full wave of CTAs (makespan = work rounded up to whole waves)."""
+    from utils.host_pipeline import attention_makespan, wave_chunk_sizes
+    for n in (1, 7, 8, 16, 31, 64, 65, 128, 512):
+        for frames, heads in ((3446, 2), (314, 2), (2048, 4), (100, 2)):
+            sizes = wave_chunk_sizes(n, frames, heads)
+            assert sum(sizes) == n and min(sizes) >= 1, (n, frames, heads, sizes)
+    assert wave_chunk_sizes(64, 3446, 2) == [5, 27, 27, 5]
+    # 27 query tiles per (utterance, head): 13 two-tile CTAs + 1 single-tile CTA of half the duration
+    assert attention_makespan(64, 3446, 2) == 12.0      # 1664 two-tile CTAs = 11 waves + 36, the 128 single-tile CTAs fit beside them
+    assert attention_makespan(21, 3446, 2) == 4.0 and attention_makespan(22, 3446, 2) == 4.5
+    assert attention_makespan(5, 3446, 2) == 1.0 and attention_makespan(27, 3446, 2) == 5.0
+
+
+def test_explicit_sizes_are_used_only_when_they_fit_the_batch():
+    import torch
+    from utils.host_pipeline import HostPipeline
+    pipe = HostPipeline.__new__(HostPipeline)      # no CUDA streams on the CPU box: only the chunk logic is exercised
+    pipe.n_chunks, pipe.edge, pipe.sizes = 3, 1.0, [5, 27, 27, 5]
+    assert [hi - lo for lo, hi in pipe.chunk_bounds(64)] == [5, 27, 27, 5]
+    assert pipe.chunk_bounds(64)[0] == (0, 5) and pipe.chunk_bounds(64)[-1] == (59, 64)
+    assert [hi - lo for lo, hi in pipe.chunk_bounds(10)] == [4, 3, 3]
+    del torch
