@@ -17,7 +17,10 @@ m = M2TTSModel(**kw).eval().cuda()
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 T = int(sys.argv[2]) if len(sys.argv) > 2 else 3446
 x = torch.randn(B, T, 96, device="cuda")
-n_cta = ((T + 255) // 256) * 2 * B
+import os
+n_items = ((T + 255) // 256) * 2 * B
+persist = os.environ.get("M2TTS_ATT_PERSIST", "1") != "0"
+n_cta = min(n_items, 148) if persist else n_items
 prof = torch.zeros(1024 + 5 * n_cta, dtype=torch.int64, device="cuda")
 m.decoder(x)
 lib.m2tts_attention_set_prof(prof.data_ptr())
@@ -25,11 +28,15 @@ m.decoder(x)
 torch.cuda.synchronize()
 lib.m2tts_attention_set_prof(None)
 w = prof.cpu()[1024:].view(n_cta, 5)
-n_long = (((T + 127) // 128) // 2) * 2 * B
+n_long = n_cta if persist else (((T + 127) // 128) // 2) * 2 * B
 life = (w[:, 1] - w[:, 0]).float()
 t0, t1 = w[:, 0].min().item(), w[:, 1].max().item()
 print(f"B={B} T={T}: {n_cta} CTAs ({n_long} two-tile), kernel span {(t1 - t0) / 1e3:.1f} us; two-tile CTA lifetime mean {life[:n_long].mean() / 1e3:.2f} us "
       f"(min {life[:n_long].min() / 1e3:.2f}, max {life[:n_long].max() / 1e3:.2f}); single-tile mean {life[n_long:].mean() / 1e3 if n_long < n_cta else 0:.2f} us")
+if persist:
+    cyc = (w[:, 4] - w[:, 3]).float()
+    print(f"persistent CTAs: lifetime mean {cyc.mean():.0f} cycles, effective SM clock {cyc.sum().item() / life.sum().item() * 1e3:.0f} MHz")
+    sys.exit(0)
 # gap between consecutive CTAs on one SM
 gaps = []
 for sm in range(int(w[:, 2].max().item()) + 1):
@@ -47,6 +54,8 @@ print(f"steady-state period per key tile (CTA 0, clock cycles): {per / 2:.0f}; x
 cyc = (w[:, 4] - w[:, 3]).float()
 print(f"two-tile CTA lifetime in SM cycles: mean {cyc[:n_long].mean():.0f}; effective SM clock {cyc[:n_long].sum().item() / life[:n_long].sum().item() * 1e3:.0f} MHz")
 print(f"CTA 0: start -> key tile 8 arrives at softmax: {first[0, 1].item() - w[0, 3].item()} cycles; tile 52 wait -> CTA end: {w[0, 4].item() - first[22, 0].item()} cycles; lifetime {w[0, 4].item() - w[0, 3].item()}")
+if persist:
+    sys.exit(0)
 st = prof.cpu()[512:520]
 names = ["setup (barrier init, TMEM alloc, sync)", "Q_hi -> TMEM", "first scores ready", "key-tile loop", "last P V landed", "O normalise + store", "final sync"]
 print("CTA 600, softmax warpgroup A0, cycles: " + ", ".join(f"{n}={st[k + 1].item() - st[k].item()}" for k, n in enumerate(names)) + f"; total {st[7].item() - st[0].item()}; CTA lifetime {w[600, 4].item() - w[600, 3].item()}")
