@@ -79,7 +79,8 @@ lin_h_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
   const uint32_t sStg = sA + (uint32_t)a.a_stages * a_stage;            // output staging: 8 KB boxes of 128 rows x 64 B, 64-byte swizzle
   const uint32_t sW = sStg + (uint32_t)a.stg_bytes * (uint32_t)(1 + a.stg2);       // [kbox][pass][plane][np x 64 B]
   const uint32_t sBias = sW + w_bytes;                                  // N floats
-  const uint32_t sBar = (sBias + (uint32_t)a.N * 4u + 15u) & ~15u;
+  const uint32_t sLn = (sBias + (uint32_t)a.N * 4u + 15u) & ~15u;         // LayerNorm weight and bias of the producers: 2 x 96 floats
+  const uint32_t sBar = sLn + 768u;
   // barriers: a_full[4] a_empty[4] acc_full[2] acc_empty[2] w_full
   const uint32_t bar_af = sBar, bar_ae = sBar + 32, bar_cf = sBar + 64, bar_ce = sBar + 80, bar_w = sBar + 96, bar_rs = sBar + 104, tmem_slot = sBar + 112;
   float* bias_s = reinterpret_cast<float*>(gbase + (sBias - sbase));
@@ -99,6 +100,9 @@ lin_h_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_r) : "memory");
   }
   for (int i = tid; i < a.N; i += LH_THREADS) bias_s[i] = a.bias != nullptr ? a.bias[i] : 0.f;
+  float* ln_s = reinterpret_cast<float*>(gbase + (sLn - sbase));
+  if (a.ln_x != nullptr)      // the LayerNorm parameters are weights, nobody's output: no pdl_wait needed
+    for (int i = tid; i < 2 * a.K; i += LH_THREADS) ln_s[i < a.K ? i : 96 + (i - a.K)] = i < a.K ? a.ln_w[i] : a.ln_b[i - a.K];
   if (warp == 0) {
     __syncwarp();
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
@@ -189,8 +193,22 @@ lin_h_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
           for (int i = 0; i < 3; ++i) v[u][i] = i < n4 ? __ldg(reinterpret_cast<const float4*>(xr + 32 * i + 4 * sub)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       };
+      // The register prefetch keeps ONE tile's rows in flight per SM (48 KB), and they come from HBM. One bulk L2 prefetch per
+      // tile, issued a tile period ahead of the loads by one lane, turns those loads into L2 hits (QKV 0.132 -> 0.126, FFN1 0.081
+      // -> 0.076, mel projection 0.066 -> 0.058 ms per launch). What a producer warp spends per tile — ~7 k cycles for four row
+      // groups of ~250 instructions — did not move with packed arithmetic (100 instructions per group), MUFU.RSQ instead of
+      // the IEEE sequences, two or four groups interleaved, loads issued per group a tile ahead, L2-only loads or polling
+      // back-off in the other roles (all measured, tools/lin_prof.py).
+      auto prefetch_tile = [&](int mt) {
+        if (pw != 0 || lane != 0 || mt >= m_tiles) return;
+        long long grow; int rows;
+        if (a.tpu > 0) { const int b = mt / a.tpu, l0 = (mt % a.tpu) * LH_BM; grow = (long long)b * a.L + l0; rows = a.L - l0 < LH_BM ? a.L - l0 : LH_BM; }
+        else { grow = (long long)mt * LH_BM; rows = a.R - grow < LH_BM ? (int)(a.R - grow) : LH_BM; }
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.ln_x + grow * a.K), "r"((uint32_t)(rows * a.K * 4)) : "memory");
+      };
       int it = 0, mt = blockIdx.x;
       if (mt < m_tiles) load_tile(mt);
+      prefetch_tile(mt + (int)gridDim.x);
       for (; mt < m_tiles; ++it) {
         const int st = it % S;
         if (it >= S) mbar_wait(bar_ae + 8 * st, (uint32_t)(((it / S) - 1) & 1));
@@ -216,7 +234,7 @@ lin_h_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
           for (int i = 0; i < 3; ++i)
             if (i < n4) {
               const int k = 32 * i + 4 * sub;
-              const float4 ww = __ldg(reinterpret_cast<const float4*>(a.ln_w + k)), bb = __ldg(reinterpret_cast<const float4*>(a.ln_b + k));
+              const float4 ww = *reinterpret_cast<const float4*>(ln_s + k), bb = *reinterpret_cast<const float4*>(ln_s + 96 + k);
               uint2 hv = make_uint2(0u, 0u), lv = make_uint2(0u, 0u);
               if (valid[u]) {
                 const float y0 = (v[u][i].x - mean) * rstd * ww.x + bb.x, y1 = (v[u][i].y - mean) * rstd * ww.y + bb.y;
@@ -235,6 +253,7 @@ lin_h_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_af + 8 * st) : "memory");
         mt += (int)gridDim.x;
         if (mt < m_tiles) load_tile(mt);
+        prefetch_tile(mt + (int)gridDim.x);
       }
       h_flag(h_amax_bad(amax), a.status);
     }
@@ -605,7 +624,7 @@ int launch_linear_h(const void* a_planes, const void* w_planes, const LinHParams
   const bool stage3 = q.mode == 3 && a.np == q.nh * q.hd && q.L > 0 && q.R % q.L == 0 && q.plane_stride == (long long)(q.R / q.L) * q.nh * q.hd * q.Lp &&
                       (q.Lp & 7) == 0 && (((uintptr_t)q.qkvh) & 15) == 0;
   a.stg_bytes = (q.mode == 0 && (q.ldy & 3) == 0 && (((uintptr_t)q.y) & 15) == 0) || (q.mode == 1 && a.np % 32 == 0) || stage3 ? a.np * 512 : 0;
-  size_t fixed = w_bytes + (size_t)a.stg_bytes + (size_t)a.N * 4 + 16 + 256 + 1024;
+  size_t fixed = w_bytes + (size_t)a.stg_bytes + (size_t)a.N * 4 + 16 + 768 + 256 + 1024;      // + bias, LayerNorm parameters, barriers, alignment
   int st = (int)((225 * 1024 - fixed) / a_stage);
   if (st < 1 && a.stg_bytes != 0) {      // no room for the staging tile: the epilogue stores directly
     fixed -= (size_t)a.stg_bytes;
