@@ -329,7 +329,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         pipe = HostPipeline(dev, n_chunks=args.e2e_chunks, edge=args.e2e_edge)
     else:      # default: chunk sizes that fill the attention kernel's waves of CTAs (utils.host_pipeline.wave_chunk_sizes)
         pipe = HostPipeline(dev, sizes=wave_chunk_sizes(BATCH, FRAMES, model.decoder.layers[0].self_attn.num_heads,
-                                                       torch.cuda.get_device_properties(dev).multi_processor_count)))
+                                                       torch.cuda.get_device_properties(dev).multi_processor_count))
     pipe_desc = (f"sizes={pipe.sizes}" if pipe.sizes is not None else f"n_chunks={args.e2e_chunks}, edge={args.e2e_edge}")
     with nat.deferred_status():
         for _ in range(2):

@@ -149,3 +149,15 @@ def test_cpulist_parsing_and_binding_without_a_gpu():
         before = os.sched_getaffinity(0)
         assert bind_host_to_gpu(torch.device("cuda", 0))["bound"] is False      # no device (or one NUMA node): nothing is touched
         assert os.sched_getaffinity(0) == before
+
+
+def test_entry_scripts_compile():
+    """bench.py, __graft_entry__.py and the bring-up tools are only ever run on the GPU box: a syntax error there costs a round.
+    Compile every one of them here."""
+    import py_compile
+    from pathlib import Path
+    root = Path(__file__).resolve().parents[1]
+    files = [root / "bench.py", root / "__graft_entry__.py"] + sorted((root / "tools").glob("*.py")) + sorted((root / "m2-tts_b200").rglob("*.py"))
+    assert len(files) > 10
+    for f in files:
+        py_compile.compile(str(f), doraise=True)
