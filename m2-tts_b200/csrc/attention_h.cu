@@ -5,10 +5,11 @@
 // ranges is that of the TF32 split (parity tests <= 1e-4); fp16 needs |x| <= 65504: the producers (QKV GEMM epilogue, this
 // kernel's own output planes) check their values and raise M2TTS_ST_FP16_RANGE (include/m2tts_b200.h).
 //
-// One CTA = two 128-query tiles of one (utterance, head) sharing every 64-key K/V tile; warp 0 TMA loader, warps 1 / 2 the
-// UMMA issuers of tile A / B (warp-collective issue out of uniform registers: the warp index is a shuffle broadcast, so the
-// role branches are uniform branches for ptxas), warps 4-19 four softmax warpgroups, two per query tile; lazy rescaling
-// with O accumulating in TMEM. The SCORES ARE DOUBLE-BUFFERED in TMEM: QK(t+2) is issued right behind PV(t).
+// A work item = two 128-query tiles of one (utterance, head) sharing every 64-key K/V tile (the odd last tile of an utterance
+// is an item of its own); the kernel is PERSISTENT, one CTA per SM walking its list of items (attention_hp_kernel). Warp 0 TMA
+// loader, warps 1 / 2 the UMMA issuers of query-tile slot A / B (warp-collective issue out of uniform registers: the warp index
+// is a shuffle broadcast, so the role branches are uniform branches for ptxas), warps 4-19 four softmax warpgroups, two per
+// slot; lazy rescaling with O accumulating in TMEM. The SCORES ARE DOUBLE-BUFFERED in TMEM: QK(t+2) is issued right behind PV(t).
 //   * softmax warpgroup w of a query tile owns the key tiles t = w (mod 2) and score buffer w; a thread = one query row over
 //     all 64 keys of the tile (the first version split a tile's columns between the two warpgroups, exchanged row maxima
 //     through shared memory at a named barrier and made the two query tiles take turns in the exponential phase: 57 % of its
@@ -19,9 +20,11 @@
 //     low 13 mantissa bits (exact in fp16); one F2FP per packed pair; FMNMX3 for the maximum;
 //   * P is written over S IN PLACE per 16-key group (= one k-step of P V): 8 columns of packed P_hi, 8 of packed P_lo;
 //   * Q_hi lives in TMEM as the A operand of Q K^T (head_dim <= 48): six of the nine Q K^T UMMAs per key tile fetch only K
-//     from shared memory (TMEM per query tile: 2 x 64 scores, O 2 hd, Q_hi hd / 2 = 248 of 256 columns at head_dim 48).
+//     from shared memory (TMEM per query tile: 2 x 64 scores, O 2 hd, Q_hi hd / 2 = 248 of 256 columns at head_dim 48); it is
+//     copied there by the softmax warps from the TMA-loaded shared-memory boxes. head_dim 64: all three terms from shared memory.
 // Measured and rejected: 128-key tiles with one in-place score buffer (serialises Q K^T -> softmax -> P V, 0.99 ms against
-// 0.91), a Veltkamp split on the FMA pipe, part of the exponentials as a degree-5 FFMA2 polynomial (issue-bound then).
+// 0.91), a Veltkamp split on the FMA pipe, part of the exponentials as an FFMA2 polynomial (slower at every fraction), three score
+// buffers with O in hd columns (one more UMMA per P V k-step).
 // Operands: qkvh[6][B][nh][hd][Lp] fp16 = {Q_hi,Q_lo,K_hi,K_lo,V_hi,V_lo}, positions contiguous, Lp % 8 == 0, Q
 // pre-multiplied by scale*log2(e). A TMA box = 64 positions (128 B) x hd rows: for Q and K the MN-major 128B-swizzle
 // operand (K dim = d), for V the K-major 128B-swizzle operand (rows = d, K dim = keys) — layouts verified with
@@ -107,7 +110,7 @@ __device__ __forceinline__ float ws_ex2v(float x) {      // ex2 that keeps its p
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
-// attention_h_kernel. Softmax organisation:
+// Softmax organisation of the attention kernel below:
 //   * warpgroup w of a query tile owns the key tiles t = w (mod 2) and their score buffer w, a thread = one query row over all
 //     64 keys. Nothing is exchanged inside a tile, and while one warpgroup waits for the P V / Q K^T of its buffer the other
 //     one is in the middle of its tile, so the four warps of a scheduler sit in different phases without being forced to;
@@ -122,450 +125,8 @@ __device__ __forceinline__ float ws_ex2v(float x) {      // ex2 that keeps its p
 //   * P(t)-ready has one mbarrier per warpgroup (alternating arrivals must not mix in one phase); the last P V also commits to
 //     a single-phase barrier for the final read of O (a parity wait is only exact for a waiter at most one phase behind).
 // Reference: components.py:75-87.
-template <int HD>
-__global__ void __launch_bounds__(AH_THREADS, 1)
-attention_h_kernel(const __grid_constant__ CUtensorMap tmap, const __half* __restrict__ qkvh, int Lp, float* __restrict__ ctx,
-                    const int64_t* __restrict__ lengths, int B, int L, int nh, float* __restrict__ ctx_lo, __half* __restrict__ ctx_h,
-                    long long* __restrict__ prof, int dbg_skip, int32_t* __restrict__ status) {
-  static_assert(HD % 16 == 0 && HD >= 16 && HD <= 64, "16-bit split attention: head_dim in {16,32,48,64}");
-  pdl_launch_dependents();      // M2_LAUNCH_PDL: every global access below follows a pdl_wait()
-#ifdef M2TTS_TOOLS
-  long long cta_t0 = 0, cta_c0 = 0;
-  if (prof != nullptr && threadIdx.x == 0) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(cta_t0)); cta_c0 = clock64(); }
-  const bool pc = prof != nullptr && blockIdx.x == 600 && threadIdx.x == 128;      // phase stamps of one mid-kernel CTA: prof[512 + k]
-#define AH_STAMP(k) do { if (pc) prof[512 + (k)] = clock64(); } while (0)
-  AH_STAMP(0);
-#else
-#define AH_STAMP(k) do { } while (0)
-#endif
-  constexpr uint32_t BOX = AhSmem<HD>::box;
-  constexpr int KSTEPS_D = HD / 16;
-  constexpr bool QT = (128 + 2 * HD + HD / 2) <= 256;             // Q_hi as a TMEM A operand (head_dim <= 48), else from shared memory
-  constexpr uint32_t IDESC_QK1 = ah_idesc(TC_BQ, TC_BK, 1);
-  constexpr uint32_t IDESC_QKT = ah_idesc2(TC_BQ, TC_BK, 0, 1);
-  constexpr uint32_t IDESC_PV2 = ah_idesc(TC_BQ, 2 * HD, 0);
-  constexpr uint32_t IDESC_PV1 = ah_idesc(TC_BQ, HD, 0);
-
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sQ = sbase;
-  const uint32_t sK = sbase + AhSmem<HD>::off_k;
-  const uint32_t sV = sbase + AhSmem<HD>::off_v;
-  const uint32_t sBar = sbase + AhSmem<HD>::off_bar;
-  // barriers: q_full[2] s_full[2 tiles][2 buffers] p_ready[2 tiles][2 warpgroups] pv_done[2] o_done[2] | k_full[S] k_empty[S]
-  // v_full[S] v_empty[S] | tmem slot | q_hi[2]
-  const uint32_t bar_qf = sBar, bar_sf = sBar + 16, bar_pr = sBar + 48, bar_pv = sBar + 80, bar_done = sBar + 96;
-  const uint32_t bar_kf = sBar + 112, bar_ke = bar_kf + 8 * AH_STAGES, bar_vf = bar_ke + 8 * AH_STAGES, bar_ve = bar_vf + 8 * AH_STAGES;
-  const uint32_t tmem_slot = bar_ve + 8 * AH_STAGES;
-  const uint32_t bar_qh = tmem_slot + 8;
-  const uint32_t bar_p2 = bar_qh + 16;      // p_ready of the second half of P, [2 tiles][2 warpgroups] (its own barriers: a fast warp's two arrivals must not land in one phase)
-
-  // warp index as a shuffle broadcast: ptxas then knows it is warp-uniform, the role branches are uniform branches and the
-  // issuer's descriptor arithmetic can live in uniform registers
-  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
-  const int n_tiles_q = (L + TC_BQ - 1) / TC_BQ, npf = n_tiles_q >> 1, n_long = npf * nh * B;
-  int qx, bh;
-  if ((int)blockIdx.x < n_long) { bh = (int)blockIdx.x / npf; qx = (int)blockIdx.x % npf; }
-  else { bh = (int)blockIdx.x - n_long; qx = npf; }
-  const int q0 = qx * (2 * TC_BQ), head = bh % nh, b = bh / nh;
-  const int ntq = q0 + TC_BQ < L ? 2 : 1;
-
-  int Leff = L;
-  bool all_masked = false;
-  if (lengths != nullptr) {
-    const long long len = lengths[b];
-    if (len <= 0) all_masked = true;
-    else if (len < L) Leff = (int)len;
-  }
-  const int nkt = (Leff + TC_BK - 1) / TC_BK;
-  const int plane = B * nh * HD;
-  const int row_q = (b * nh + head) * HD;
-
-  if (tid == 0) {
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(bar_qf + 8 * i, 1); mbar_init(bar_sf + 16 * i, 1); mbar_init(bar_sf + 16 * i + 8, 1);
-      mbar_init(bar_pr + 16 * i, 4); mbar_init(bar_pr + 16 * i + 8, 4); mbar_init(bar_pv + 8 * i, 1); mbar_init(bar_done + 8 * i, 1);
-      mbar_init(bar_qh + 8 * i, 8); mbar_init(bar_p2 + 16 * i, 4); mbar_init(bar_p2 + 16 * i + 8, 4);
-    }
-    for (int i = 0; i < AH_STAGES; ++i) {
-      mbar_init(bar_kf + 8 * i, 1); mbar_init(bar_ke + 8 * i, (uint32_t)ntq); mbar_init(bar_vf + 8 * i, 1); mbar_init(bar_ve + 8 * i, (uint32_t)ntq);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
-  }
-  if (warp == 0) {
-    __syncwarp();
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(AH_TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  uint32_t tmem_base;
-  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-  tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);
-  AH_STAMP(1);
-
-  if (warp == 0) {
-    if (lane == 0) {
-      // ===== loader =====
-      pdl_wait();
-      for (int x = 0; x < ntq; ++x) {
-        mbar_expect_tx(bar_qf + 8 * x, AhSmem<HD>::q_bytes);      // Q_hi too: the softmax warps copy it from shared memory into TMEM
-        for (int h = 0; h < 2; ++h)
-          for (int j = 0; j < 2; ++j)
-            tma_load_2d(sQ + (uint32_t)x * AhSmem<HD>::q_bytes + (h * 2 + j) * BOX, &tmap, q0 + x * TC_BQ + j * 64, h * plane + row_q,
-                        bar_qf + 8 * x);
-      }
-      for (int t = 0; t < nkt; ++t) {
-        const int st = t % AH_STAGES;
-        const uint32_t par_prev = (uint32_t)(((t / AH_STAGES) - 1) & 1);
-        if (t >= AH_STAGES) mbar_wait(bar_ke + 8 * st, par_prev);
-        mbar_expect_tx(bar_kf + 8 * st, AhSmem<HD>::kv_bytes);
-        for (int h = 0; h < 2; ++h)
-          tma_load_2d(sK + (uint32_t)st * AhSmem<HD>::kv_bytes + h * BOX, &tmap, t * TC_BK, (2 + h) * plane + row_q, bar_kf + 8 * st);
-        if (t >= AH_STAGES) mbar_wait(bar_ve + 8 * st, par_prev);
-        mbar_expect_tx(bar_vf + 8 * st, AhSmem<HD>::kv_bytes);
-        for (int h = 0; h < 2; ++h)
-          tma_load_2d(sV + (uint32_t)st * AhSmem<HD>::kv_bytes + h * BOX, &tmap, t * TC_BK, (4 + h) * plane + row_q, bar_vf + 8 * st);
-      }
-    }
-  } else if ((warp == 1 || warp == 2) && warp - 1 < ntq) {
-    // ===== UMMA issuer of query tile x (whole warp, one elected lane issues) =====
-    const int x = warp - 1;
-    auto issue_qk = [&](int st, int buf) {
-      if (dbg_skip & 1) return;      // bring-up timing experiment (M2TTS_ATT_DBG): results invalid
-      const uint32_t q = sQ + (uint32_t)x * AhSmem<HD>::q_bytes, k = sK + (uint32_t)st * AhSmem<HD>::kv_bytes;
-      const uint32_t d = tmem_base + (uint32_t)x * AH_COL_TILE + AH_COL_S + (uint32_t)buf * 64u;
-      if (QT) {
-        const uint32_t qt = tmem_base + (uint32_t)x * AH_COL_TILE + AH_COL_Q;
-#pragma unroll
-        for (int ks = 0; ks < KSTEPS_D; ++ks) {
-          const uint64_t khi = umma_desc(k + ks * 2048u, BOX, 1024u, 2u), klo = umma_desc(k + BOX + ks * 2048u, BOX, 1024u, 2u);
-          umma_f16_ts_w(d, qt + ks * 8, khi, IDESC_QKT, ks ? 1u : 0u);
-          umma_f16_ts_w(d, qt + ks * 8, klo, IDESC_QKT, 1u);
-          umma_f16_ss_w(d, umma_desc(q + 2 * BOX + ks * 2048u, BOX, 1024u, 2u), khi, IDESC_QK1, 1u);
-        }
-        return;
-      }
-#pragma unroll
-      for (int term = 0; term < 3; ++term) {
-        const uint32_t qa = q + (term == 2 ? 2 * BOX : 0u), kb = k + (term == 1 ? BOX : 0u);
-#pragma unroll
-        for (int ks = 0; ks < KSTEPS_D; ++ks)
-          umma_f16_ss_w(d, umma_desc(qa + ks * 2048u, BOX, 1024u, 2u), umma_desc(kb + ks * 2048u, BOX, 1024u, 2u), IDESC_QK1,
-                        (term | ks) ? 1u : 0u);
-      }
-    };
-    auto issue_pv = [&](int st, int buf, int half, uint32_t accumulate) {
-      if (dbg_skip & 2) return;
-      const uint32_t v = sV + (uint32_t)st * AhSmem<HD>::kv_bytes;
-      const uint32_t tb = tmem_base + (uint32_t)x * AH_COL_TILE;
-      const uint32_t pb = tb + AH_COL_S + (uint32_t)buf * 64u;
-      // the softmax publishes P in two halves (16-key groups 2, 3 first, then 0, 1): `half` 0 issues the k-steps of the first
-#pragma unroll
-      for (int kk = 0; kk < 2; ++kk) {
-        const int ks = (half == 0 ? 2 : 0) + kk;
-        umma_f16_ts_w(tb + AH_COL_O, pb + ks * 16, umma_desc(v + ks * 32u, 16u, 1024u, 2u), IDESC_PV2, (half | kk) ? 1u : accumulate);
-        umma_f16_ts_w(tb + AH_COL_O, pb + ks * 16 + 8, umma_desc(v + ks * 32u, 16u, 1024u, 2u), IDESC_PV1, 1u);
-      }
-    };
-    for (int t = 0; t < 2 && t < nkt; ++t) {      // prologue: the scores of key tiles 0 and 1
-      mbar_wait(bar_kf + 8 * t, 0);
-      if (t == 0) {
-        mbar_wait(bar_qf + 8 * x, 0);
-        if (QT) mbar_wait(bar_qh + 8 * x, 0);
-      }
-      tc_fence_after();
-      issue_qk(t, t);
-      tc_commit_w(bar_sf + 16 * x + 8 * t);
-      tc_commit_w(bar_ke + 8 * t);
-    }
-    for (int t = 0; t < nkt; ++t) {
-      const int st = t % AH_STAGES, s2 = (t + 2) % AH_STAGES, buf = t & 1;
-      // P(x,t) arrives in two halves, each with its own barrier; O has been rescaled if needed
-      mbar_wait(bar_pr + 16 * x + 8 * buf, (uint32_t)((t >> 1) & 1));
-      mbar_wait(bar_vf + 8 * st, (uint32_t)((t / AH_STAGES) & 1));
-      tc_fence_after();
-      issue_pv(st, buf, 0, t > 0 ? 1u : 0u);
-      mbar_wait(bar_p2 + 16 * x + 8 * buf, (uint32_t)((t >> 1) & 1));
-      tc_fence_after();
-      issue_pv(st, buf, 1, 1u);
-      tc_commit_w(bar_pv + 8 * x);
-      if (t == nkt - 1) tc_commit_w(bar_done + 8 * x);
-      tc_commit_w(bar_ve + 8 * st);
-      if (t + 2 < nkt) {                                      // score buffer `buf` is free again once PV(x,t) has read P
-        mbar_wait(bar_kf + 8 * s2, (uint32_t)(((t + 2) / AH_STAGES) & 1));
-        tc_fence_after();
-        issue_qk(s2, buf);
-        tc_commit_w(bar_sf + 16 * x + 8 * buf);
-        tc_commit_w(bar_ke + 8 * s2);
-      }
-    }
-  } else if (warp >= 4 && (((warp - 4) >> 2) & 1) < ntq) {
-    // ===== softmax warpgroups: query tile x has two (warps 4-7 / 12-15 for tile A, 8-11 / 16-19 for tile B); warpgroup wg owns the
-    // key tiles t = wg (mod 2) and score buffer wg; thread = query row = TMEM lane, all 64 keys of the tile =====
-    const int x = ((warp - 4) >> 2) & 1, wg = (warp - 4) >> 3;
-    const int row = (warp & 3) * 32 + lane;
-    const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)x * AH_COL_TILE;
-    float* exch = reinterpret_cast<float*>(smem_raw + (sbase - smem_u32(smem_raw)) + AhSmem<HD>::off_exch);
-    float* mref_s = exch + x * 128;               // per-row reference maximum of the running softmax
-    float* lsum_s = exch + 256 + x * 128;         // final row sums: warpgroup wg writes [wg * 256 + row]
-    const int hb = 1 + x * 2;                     // named barriers hb / hb + 1: hand-off of the m_ref decision of even / odd key tiles
-    pdl_wait();                                   // Q is read from global memory below; ctx is written at the end
-    if (QT) {
-      // Q_hi -> TMEM as the A operand of Q K^T (see attention_h_kernel); this warpgroup writes the d range [wg hd/2, (wg+1) hd/2).
-      // The rows come from the TMA-loaded Q_hi boxes in shared memory (MN-major, 128-byte swizzle: element (d, position p) of a
-      // 64-position box at d * 128 + ((2 p) ^ ((d & 7) << 4)); a warp reads 64 contiguous bytes per d). Read from global memory
-      // (2-byte loads 2 Lp bytes apart) this copy took 4.8 k cycles of every CTA's start (tools/attn_cta_prof.py).
-      const int qi = q0 + x * TC_BQ + row;
-      const uint32_t qs = sQ + (uint32_t)x * AhSmem<HD>::q_bytes + (uint32_t)(row >> 6) * BOX;
-      const uint32_t p2 = (uint32_t)(row & 63) * 2u;
-      mbar_wait(bar_qf + 8 * x, 0);
-#pragma unroll
-      for (int c4 = 0; c4 < HD / 16; ++c4) {
-        uint32_t w[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const uint32_t d = (uint32_t)(wg * (HD / 2) + (c4 * 4 + e) * 2);
-          const uint32_t lo = ah_lds16(qs + d * 128u + (p2 ^ ((d & 7u) << 4)));
-          const uint32_t hi = ah_lds16(qs + (d + 1u) * 128u + (p2 ^ (((d + 1u) & 7u) << 4)));
-          w[e] = qi < L ? (lo | (hi << 16)) : 0u;
-        }
-        ah_st4(t_lane + AH_COL_Q + (uint32_t)(wg * (HD / 4) + c4 * 4), w);
-      }
-      tmem_wait_st();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_qh + 8 * x) : "memory");
-    }
-    AH_STAMP(2);
-    float m_c = -INFINITY;                                // the m_ref this warpgroup's row sum is scaled to
-    uint64_t l2 = ah_pack(0.f, 0.f);                      // running row sum as a packed pair (even keys, odd keys)
-#ifdef M2TTS_TOOLS
-    const bool pw = prof != nullptr && blockIdx.x == 0 && x == 0 && wg == 0 && row == 0;
-#endif
-    auto mask16 = [&](uint32_t* sv, int k0) {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        float a = __uint_as_float(sv[j]);
-        if (all_masked) a = (k0 + j < L) ? 0.f : -INFINITY;
-        else if (k0 + j >= Leff) a = -INFINITY;
-        sv[j] = __float_as_uint(a);
-      }
-    };
-    auto max32 = [&](const uint32_t* u, const uint32_t* v) {
-      float mx = ah_max3(__uint_as_float(u[0]), __uint_as_float(u[1]), __uint_as_float(u[2]));
-#pragma unroll
-      for (int j = 3; j < 15; j += 2) mx = ah_max3(mx, __uint_as_float(u[j]), __uint_as_float(u[j + 1]));
-      mx = ah_max3(mx, __uint_as_float(u[15]), __uint_as_float(v[0]));
-#pragma unroll
-      for (int j = 1; j < 15; j += 2) mx = ah_max3(mx, __uint_as_float(v[j]), __uint_as_float(v[j + 1]));
-      return fmaxf(mx, __uint_as_float(v[15]));
-    };
-    auto rescale_l = [&](float m_new) {                   // the row sum follows m_ref (2^-inf = 0 on the first tile: l2 is 0 then)
-      const float a = ws_ex2(m_c - m_new);
-      float la, lb;
-      ah_unpack(l2, la, lb);
-      l2 = ah_pack(la * a, lb * a);
-      m_c = m_new;
-    };
-    for (int t = wg; t < nkt; t += 2) {
-#ifdef M2TTS_TOOLS
-      const bool pt = pw && t >= 8 && t < 72;
-      long long* pp = prof + (pt ? ((t - 8) >> 1) * 8 : 0);
-#endif
-      const uint32_t t_s = t_lane + AH_COL_S + (uint32_t)wg * 64u;      // score buffer of this warpgroup
-      AH_PROF(pt, pp[0] = clock64());
-      mbar_wait(bar_sf + 16 * x + 8 * wg, (uint32_t)((t >> 1) & 1));
-      AH_PROF(pt, pp[1] = clock64());
-      if (t == 0) AH_STAMP(3);
-      __syncwarp();
-      tc_fence_after();
-      const int kbase = t * TC_BK;
-      const bool need_mask = all_masked || kbase + TC_BK > Leff;      // key padding: only ever in the last key tile
-      // pass 1: row maximum over the 64 keys; the second half of the scores stays in registers
-      uint32_t sa[16], sb[16];
-      tmem_ld16(t_s, sa);
-      tmem_ld16(t_s + 16, sb);
-      tmem_wait_ld();
-      if (need_mask) { mask16(sa, kbase); mask16(sb, kbase + 16); }
-      float mx = max32(sa, sb);
-      tmem_ld16(t_s + 32, sa);
-      tmem_ld16(t_s + 48, sb);
-      tmem_wait_ld();
-      if (need_mask) { mask16(sa, kbase + 32); mask16(sb, kbase + 48); }
-      mx = fmaxf(mx, max32(sa, sb));
-      AH_PROF(pt, pp[2] = clock64());
-      // the decision of tile t-1 (other warpgroup) precedes ours
-      if (t > 0) asm volatile("bar.sync %0, 256;" ::"r"(hb + ((t - 1) & 1)) : "memory");
-      float m_s;
-      if (t == 0) {
-        m_s = mx;
-        mref_s[row] = mx;
-      } else {
-        m_s = mref_s[row];
-        if (__any_sync(0xffffffffu, mx > m_s + 8.0f)) {
-          // lazy rescale: P V(t-1) has landed after this wait (its completion count is t-1 or t here, so the parity test is
-          // exact), P V(t) waits for our P and P V(t+1) for the other warpgroup, which waits for our hand-off: O is quiescent
-          mbar_wait(bar_pv + 8 * x, (uint32_t)((t - 1) & 1));
-          tc_fence_after();
-          const float m_new = fmaxf(m_s, mx);
-          const float alpha = ws_ex2(m_s - m_new);
-#pragma unroll
-          for (int c = 0; c < 2 * HD; c += 16) {
-            uint32_t orr[16];
-            tmem_ld16(t_lane + AH_COL_O + c, orr);
-            tmem_wait_ld();
-#pragma unroll
-            for (int j = 0; j < 16; ++j) orr[j] = __float_as_uint(__uint_as_float(orr[j]) * alpha);
-            tmem_st16(t_lane + AH_COL_O + c, orr);
-          }
-          mref_s[row] = m_new;
-          m_s = m_new;
-        }
-      }
-      asm volatile("bar.arrive %0, 256;" ::"r"(hb + (t & 1)) : "memory");      // hand the decision on to tile t+1
-      if (m_s != m_c) rescale_l(m_s);
-      AH_PROF(pt, pp[3] = clock64());
-      // pass 2: p = 2^(s - m_ref) per 16-key group (= one k-step of P V), written over the group's own score columns as 8 columns
-      // of packed P_hi (p with the low 13 mantissa bits masked off: exact in fp16) and 8 of packed P_lo = fp16(p - P_hi).
-      const uint64_t m2 = ah_pack(m_s, m_s);
-      auto exp_pair = [&](uint32_t* s, int j) {
-        float d0, d1;
-        ah_unpack(ah_sub2(ah_pack(__uint_as_float(s[2 * j]), __uint_as_float(s[2 * j + 1])), m2), d0, d1);
-        s[2 * j] = __float_as_uint(ws_ex2v(d0)); s[2 * j + 1] = __float_as_uint(ws_ex2v(d1));
-      };
-      auto split_pair = [&](const uint32_t* pv, int j, uint32_t* ph, uint32_t* pl) {
-        const float p0 = __uint_as_float(pv[2 * j]), p1 = __uint_as_float(pv[2 * j + 1]);
-        const uint64_t pp2 = ah_pack(p0, p1);
-        l2 = ah_add2(l2, pp2);
-        const float h0 = __uint_as_float(__float_as_uint(p0) & 0xFFFFE000u), h1 = __uint_as_float(__float_as_uint(p1) & 0xFFFFE000u);
-        float r0, r1;
-        ah_unpack(ah_sub2(pp2, ah_pack(h0, h1)), r0, r1);
-        ph[j] = ah_cvt2(h0, h1);
-        pl[j] = ah_cvt2(r0, r1);
-      };
-      // exponentials of group `nx` interleaved with the split arithmetic of group `cur` (already exponentiated), which is then
-      // stored at column offset col
-      auto exp_and_split = [&](uint32_t* nx, const uint32_t* cur, uint32_t col) {
-        uint32_t ph[8], pl[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (nx != nullptr) exp_pair(nx, j);
-          if (cur != nullptr) split_pair(cur, j, ph, pl);
-        }
-        if (cur != nullptr) {
-          ah_st8(t_s + col, ph);
-          ah_st8(t_s + col + 8, pl);
-        }
-      };
-      exp_and_split(sa, nullptr, 0);            // group 2
-      exp_and_split(sb, sa, 32);                // group 3 | group 2
-      uint32_t sc[16], sd[16];
-      tmem_ld16(t_s, sc);
-      tmem_ld16(t_s + 16, sd);
-      tmem_wait_ld();
-      if (need_mask) { mask16(sc, kbase); mask16(sd, kbase + 16); }
-      exp_and_split(sc, sb, 48);                // group 0 | group 3
-      // groups 2 and 3 of P are stored: the issuer may start their P V k-steps while groups 0 and 1 are still being computed
-      tmem_wait_st();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_pr + 16 * x + 8 * wg) : "memory");
-      exp_and_split(sd, sc, 0);                 // group 1 | group 0
-      exp_and_split(nullptr, sd, 16);           //         | group 1
-      AH_PROF(pt, pp[4] = clock64());
-      tmem_wait_st();
-      AH_PROF(pt, pp[5] = clock64());
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_p2 + 16 * x + 8 * wg) : "memory");
-    }
-    AH_STAMP(4);
-    // the warpgroup that did not own the last key tile takes over its decision (the final m_ref)
-    if (((nkt - 1) & 1) != wg) {
-      asm volatile("bar.sync %0, 256;" ::"r"(hb + ((nkt - 1) & 1)) : "memory");
-      const float m_s = mref_s[row];
-      if (m_s != m_c) rescale_l(m_s);
-    }
-    // final row sum: each warpgroup holds the sum of its own key tiles (both in the scale of the final m_ref)
-    float l_run;
-    {
-      float la, lb;
-      ah_unpack(l2, la, lb);
-      l_run = la + lb;
-      lsum_s[wg * 256 + row] = l_run;
-      asm volatile("bar.sync %0, 256;" ::"r"(5 + x) : "memory");
-      l_run += lsum_s[(wg ^ 1) * 256 + row];
-    }
-    {
-      // both warpgroups of the query tile normalise and store: warpgroup wg takes the columns [wg hd/2, (wg+1) hd/2) of every row
-      // (done by one warpgroup this was 4.7 k cycles at the end of every CTA, the other one idle)
-      mbar_wait(bar_done + 8 * x, 0);     // the last PV has landed: O is complete
-      AH_STAMP(5);
-      __syncwarp();
-      tc_fence_after();
-      const int qi = q0 + x * TC_BQ + row;
-      const float inv = 1.0f / l_run;
-      const long long orow = ((long long)b * L + qi) * (nh * HD) + head * HD;
-      bool bad = false;
-#pragma unroll
-      for (int c = wg * (HD / 2); c < (wg + 1) * (HD / 2); c += 8) {
-        uint32_t orr[8], or2[8];
-        ah_ld8(t_lane + AH_COL_O + c, orr);
-        ah_ld8(t_lane + AH_COL_O + HD + c, or2);
-        tmem_wait_ld();
-        float o[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = (__uint_as_float(orr[j]) + __uint_as_float(or2[j])) * inv;
-        if (qi < L) {
-          if (ctx_h != nullptr) {   // fp16 hi/lo planes [2][B*L][nh*HD] for the 16-bit split out_proj (lin_h.cu)
-            __half* dh = ctx_h + orow + c;
-            __half* dl = dh + (long long)B * L * (nh * HD);
-            uint32_t hi[4], lo[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) h_split2(o[2 * e], o[2 * e + 1], hi[e], lo[e], bad);
-            *reinterpret_cast<uint4*>(dh) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<uint4*>(dl) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-          } else if (ctx_lo == nullptr) {
-            *reinterpret_cast<float4*>(ctx + orow + c) = make_float4(o[0], o[1], o[2], o[3]);
-            *reinterpret_cast<float4*>(ctx + orow + c + 4) = make_float4(o[4], o[5], o[6], o[7]);
-          } else {   // TF32 hi/lo planes for the tensor-core out_proj
-            float h[8], l[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) { h[e] = __uint_as_float(tf32_hi(o[e])); l[e] = __uint_as_float(tf32_hi(o[e] - h[e])); }
-            *reinterpret_cast<float4*>(ctx + orow + c) = make_float4(h[0], h[1], h[2], h[3]);
-            *reinterpret_cast<float4*>(ctx + orow + c + 4) = make_float4(h[4], h[5], h[6], h[7]);
-            *reinterpret_cast<float4*>(ctx_lo + orow + c) = make_float4(l[0], l[1], l[2], l[3]);
-            *reinterpret_cast<float4*>(ctx_lo + orow + c + 4) = make_float4(l[4], l[5], l[6], l[7]);
-          }
-        }
-      }
-      if (ctx_h != nullptr) h_flag(bad, status);
-    }
-  }
-  AH_STAMP(6);
-  tc_fence_before();
-  __syncthreads();
-  AH_STAMP(7);
-  if (warp == 0) {
-    __syncwarp();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(AH_TMEM_COLS) : "memory");
-  }
-#ifdef M2TTS_TOOLS
-  if (prof != nullptr && threadIdx.x == 0) {      // CTA lifetime (tools/attn_cta_prof.py): [start ns, end ns, SM, start clock, end clock] from word 1024 on
-    long long t1; uint32_t sm;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-    asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
-    long long* w = prof + 1024 + 5 * (long long)blockIdx.x;
-    w[0] = cta_t0; w[1] = t1; w[2] = sm; w[3] = cta_c0; w[4] = clock64();
-  }
-#endif
-}
-
 // ---------------------------------------------------------------------------------------------------------------------------
-// attention_hp_kernel — the PERSISTENT form of attention_h_kernel (head_dim <= 48: Q_hi in TMEM). One CTA per SM walks a fixed
+// attention_hp_kernel — persistent (round 2; until then one CTA per item, attention_h_kernel in the history). One CTA per SM walks a fixed
 // list of work items (item = the two — at the end of an utterance one — 128-query tiles of one (utterance, head)); every role
 // (loader, issuers, softmax warpgroups) runs its own loop over the same list and all mbarrier phases simply continue from item
 // to item (g = key tiles this query-tile slot has seen so far decides score buffer, owner warpgroup and parity; gk = key tiles
@@ -621,8 +182,9 @@ __device__ __forceinline__ AhItem ah_item(int idx, int n_long, int npf, int nh, 
 template <int HD>
 __global__ void __launch_bounds__(AH_THREADS, 1)
 attention_hp_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__ ctx, const int64_t* __restrict__ lengths, int B, int L, int nh,
-                    float* __restrict__ ctx_lo, __half* __restrict__ ctx_h, long long* __restrict__ prof, int32_t* __restrict__ status) {
-  static_assert(HD % 16 == 0 && HD >= 16 && (128 + 2 * HD + HD / 2) <= 256, "persistent 16-bit split attention: head_dim in {16,32,48}");
+                    float* __restrict__ ctx_lo, __half* __restrict__ ctx_h, long long* __restrict__ prof, int32_t* __restrict__ status, int dbg_skip) {
+  static_assert(HD % 16 == 0 && HD >= 16 && HD <= 64, "16-bit split attention: head_dim in {16,32,48,64}");
+  constexpr bool QT = (128 + 2 * HD + HD / 2) <= 256;             // Q_hi as a TMEM A operand (head_dim <= 48), else from shared memory
   pdl_launch_dependents();      // M2_LAUNCH_PDL: every global access below follows a pdl_wait()
 #ifdef M2TTS_TOOLS
   long long cta_t0 = 0, cta_c0 = 0;
@@ -715,18 +277,32 @@ attention_hp_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict_
     // ===== UMMA issuer of query-tile slot x (whole warp, one elected lane issues) =====
     const int x = warp - 1;
     auto issue_qk = [&](int st, int buf) {
+      if (dbg_skip & 1) return;      // bring-up timing experiment (tools build, M2TTS_ATT_DBG): results invalid
       const uint32_t q = sQ + (uint32_t)x * AhSmem<HD>::q_bytes, k = sK + (uint32_t)st * AhSmem<HD>::kv_bytes;
       const uint32_t d = tmem_base + (uint32_t)x * AH_COL_TILE + AH_COL_S + (uint32_t)buf * 64u;
-      const uint32_t qt = tmem_base + (uint32_t)x * AH_COL_TILE + AH_COL_Q;
+      if (QT) {
+        const uint32_t qt = tmem_base + (uint32_t)x * AH_COL_TILE + AH_COL_Q;
 #pragma unroll
-      for (int ks = 0; ks < KSTEPS_D; ++ks) {
-        const uint64_t khi = umma_desc(k + ks * 2048u, BOX, 1024u, 2u), klo = umma_desc(k + BOX + ks * 2048u, BOX, 1024u, 2u);
-        umma_f16_ts_w(d, qt + ks * 8, khi, IDESC_QKT, ks ? 1u : 0u);
-        umma_f16_ts_w(d, qt + ks * 8, klo, IDESC_QKT, 1u);
-        umma_f16_ss_w(d, umma_desc(q + 2 * BOX + ks * 2048u, BOX, 1024u, 2u), khi, IDESC_QK1, 1u);
+        for (int ks = 0; ks < KSTEPS_D; ++ks) {
+          const uint64_t khi = umma_desc(k + ks * 2048u, BOX, 1024u, 2u), klo = umma_desc(k + BOX + ks * 2048u, BOX, 1024u, 2u);
+          umma_f16_ts_w(d, qt + ks * 8, khi, IDESC_QKT, ks ? 1u : 0u);
+          umma_f16_ts_w(d, qt + ks * 8, klo, IDESC_QKT, 1u);
+          umma_f16_ss_w(d, umma_desc(q + 2 * BOX + ks * 2048u, BOX, 1024u, 2u), khi, IDESC_QK1, 1u);
+        }
+        return;
+      }
+      // head_dim 64: O takes all the columns Q_hi would need; the three product terms from shared memory (hi*hi, hi*lo, lo*hi)
+#pragma unroll
+      for (int term = 0; term < 3; ++term) {
+        const uint32_t qa = q + (term == 2 ? 2 * BOX : 0u), kb = k + (term == 1 ? BOX : 0u);
+#pragma unroll
+        for (int ks = 0; ks < KSTEPS_D; ++ks)
+          umma_f16_ss_w(d, umma_desc(qa + ks * 2048u, BOX, 1024u, 2u), umma_desc(kb + ks * 2048u, BOX, 1024u, 2u), IDESC_QK1,
+                        (term | ks) ? 1u : 0u);
       }
     };
     auto issue_pv = [&](int st, int buf, int half, uint32_t accumulate) {
+      if (dbg_skip & 2) return;
       const uint32_t v = sV + (uint32_t)st * AhSmem<HD>::kv_bytes;
       const uint32_t tb = tmem_base + (uint32_t)x * AH_COL_TILE;
       const uint32_t pb = tb + AH_COL_S + (uint32_t)buf * 64u;
@@ -747,7 +323,7 @@ attention_hp_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict_
           mbar_wait(bar_kf + 8 * st, (uint32_t)(((gk + t) / AH_STAGES) & 1));
           if (t == 0) {
             mbar_wait(bar_qf + 8 * x, (uint32_t)(nq & 1));
-            mbar_wait(bar_qh + 8 * x, (uint32_t)(nq & 1));
+            if (QT) mbar_wait(bar_qh + 8 * x, (uint32_t)(nq & 1));
           }
           tc_fence_after();
           issue_qk(st, (g + t) & 1);
@@ -834,7 +410,7 @@ attention_hp_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict_
     AhItem w;
     bool have = next_item(w);
     int g = 0, nq = 0;
-    if (have) copy_q(w, 0);
+    if (QT && have) copy_q(w, 0);
     while (have) {
       const int Leff = w.Leff, nkt = w.nkt;
       const bool all_masked = w.all_masked;
@@ -996,7 +572,7 @@ attention_hp_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict_
       // the slot's next item: its Q_hi goes to TMEM now, so its first two Q K^T run under the epilogue below
       const AhItem cur = w;
       have = next_item(w);
-      if (have) copy_q(w, nq + 1);
+      if (QT && have) copy_q(w, nq + 1);
       {
         // both warpgroups normalise and store: warpgroup wg takes the columns [wg hd/2, (wg+1) hd/2) of every row
         mbar_wait(bar_done + 8 * x, (uint32_t)(nq & 1));     // the item's last PV has landed: O is complete
@@ -1084,26 +660,16 @@ static EncodeTiledFnH ah_encode_fn() {
 extern long long* g_ws_prof;      // attention_tc.cu (m2tts_attention_set_prof)
 
 template <int HD>
-static int launch_ah_hd(const CUtensorMap& tmap, const __half* qkvh, int Lp, float* ctx, const int64_t* lengths, int B, int L, int nh,
-                        cudaStream_t s, float* ctx_lo, __half* ctx_h, int32_t* status) {
+static int launch_ah_hd(const CUtensorMap& tmap, float* ctx, const int64_t* lengths, int B, int L, int nh, cudaStream_t s, float* ctx_lo,
+                        __half* ctx_h, int32_t* status) {
   const size_t smem = AhSmem<HD>::total;
   static int dbg_skip = -1;
   if (dbg_skip < 0) dbg_skip = tools_env_int("M2TTS_ATT_DBG", 0);
-  if constexpr ((128 + 2 * HD + HD / 2) <= 256) {
-    // head_dim <= 48: the persistent kernel, one CTA per SM over the item list (tools build: M2TTS_ATT_PERSIST=0 keeps one CTA per item)
-    if (tools_env_int("M2TTS_ATT_PERSIST", 1) != 0 && dbg_skip == 0) {
-      const int items = ceil_div(L, 2 * TC_BQ) * nh * B;
-      dim3 pgrid((unsigned)(items < kNumSMs ? items : kNumSMs), 1, 1);
-      M2_CUDA_OK(allow_smem(attention_hp_kernel<HD>, smem));
-      M2_LAUNCH_PDL(M2TTS_STAGE_ATTENTION, attention_hp_kernel<HD>, pgrid, AH_THREADS, smem, s, tmap, ctx, lengths, B, L, nh, ctx_lo, ctx_h,
-                    tools_env_int("M2TTS_LIN_PROF_STAGE", -1) >= 0 ? nullptr : g_ws_prof, status);
-      return M2TTS_OK;
-    }
-  }
-  dim3 grid((unsigned)(ceil_div(L, 2 * TC_BQ) * nh * B), 1, 1);
-  M2_CUDA_OK(allow_smem(attention_h_kernel<HD>, smem));
-  M2_LAUNCH_PDL(M2TTS_STAGE_ATTENTION, attention_h_kernel<HD>, grid, AH_THREADS, smem, s, tmap, qkvh, Lp, ctx, lengths, B, L, nh, ctx_lo, ctx_h,
-            tools_env_int("M2TTS_LIN_PROF_STAGE", -1) >= 0 ? nullptr : g_ws_prof, dbg_skip, status);      // the buffer belongs to tools/lin_prof.py then
+  const int items = ceil_div(L, 2 * TC_BQ) * nh * B;      // persistent: one CTA per SM over the item list
+  dim3 grid((unsigned)(items < kNumSMs ? items : kNumSMs), 1, 1);
+  M2_CUDA_OK(allow_smem(attention_hp_kernel<HD>, smem));
+  M2_LAUNCH_PDL(M2TTS_STAGE_ATTENTION, attention_hp_kernel<HD>, grid, AH_THREADS, smem, s, tmap, ctx, lengths, B, L, nh, ctx_lo, ctx_h,
+                tools_env_int("M2TTS_LIN_PROF_STAGE", -1) >= 0 ? nullptr : g_ws_prof, status, dbg_skip);      // the buffer belongs to tools/lin_prof.py then
   return M2TTS_OK;
 }
 
@@ -1127,12 +693,11 @@ int launch_attention_h(const void* qkvh, float* ctx, const int64_t* lengths, int
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   M2_REQUIRE(r == CUDA_SUCCESS, M2TTS_E_CUDA, "attention_h: cuTensorMapEncodeTiled failed (%d)", (int)r);
-  const __half* qh = reinterpret_cast<const __half*>(qkvh);
   switch (hd) {
-    case 16: return launch_ah_hd<16>(tmap, qh, Lp, ctx, lengths, B, L, nh, s, ctx_lo, ctx_h, status);
-    case 32: return launch_ah_hd<32>(tmap, qh, Lp, ctx, lengths, B, L, nh, s, ctx_lo, ctx_h, status);
-    case 48: return launch_ah_hd<48>(tmap, qh, Lp, ctx, lengths, B, L, nh, s, ctx_lo, ctx_h, status);
-    default: return launch_ah_hd<64>(tmap, qh, Lp, ctx, lengths, B, L, nh, s, ctx_lo, ctx_h, status);
+    case 16: return launch_ah_hd<16>(tmap, ctx, lengths, B, L, nh, s, ctx_lo, ctx_h, status);
+    case 32: return launch_ah_hd<32>(tmap, ctx, lengths, B, L, nh, s, ctx_lo, ctx_h, status);
+    case 48: return launch_ah_hd<48>(tmap, ctx, lengths, B, L, nh, s, ctx_lo, ctx_h, status);
+    default: return launch_ah_hd<64>(tmap, ctx, lengths, B, L, nh, s, ctx_lo, ctx_h, status);
   }
 }
 

@@ -1,5 +1,7 @@
-"""Bring-up helper (GPU box): lifetime of every CTA of the attention kernel (attention_h.cu, tools build) against the
-steady-state key-tile period: what the one-CTA-per-work-item organisation pays per CTA for start-up and drain."""
+"""Bring-up helper (GPU box): lifetime of every CTA of the persistent attention kernel (attention_h.cu, tools build) against
+the steady-state key-tile period. The per-item phase stamps quoted in DESIGN.md section 4.1 (barrier init, Q_hi copy, first scores,
+drain, O store of a mid-kernel CTA) were taken with this tool on the one-CTA-per-item kernel that preceded it (commits a5b6e82 / 4fa91de:
+`git log -- tools/attn_cta_prof.py`)."""
 import _env  # noqa: F401  (selects libm2tts_b200_tools.so)
 import sys
 from pathlib import Path
@@ -19,7 +21,7 @@ T = int(sys.argv[2]) if len(sys.argv) > 2 else 3446
 x = torch.randn(B, T, 96, device="cuda")
 import os
 n_items = ((T + 255) // 256) * 2 * B
-persist = os.environ.get("M2TTS_ATT_PERSIST", "1") != "0"
+persist = True
 n_cta = min(n_items, 148) if persist else n_items
 prof = torch.zeros(1024 + 5 * n_cta, dtype=torch.int64, device="cuda")
 m.decoder(x)
