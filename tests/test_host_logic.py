@@ -161,3 +161,41 @@ def test_entry_scripts_compile():
     assert len(files) > 10
     for f in files:
         py_compile.compile(str(f), doraise=True)
+
+
+def test_persistent_attention_item_schedule_covers_every_item_once():
+    """Restatement of `AhItems` (m2-tts_b200/csrc/attention_h.cu): the list of work items a persistent attention CTA walks. Every
+    item must appear in exactly one CTA's list, two-tile items first, and the single-tile items (0.5-0.66 of a two-tile one) must go
+    to the CTAs that got one two-tile item less before anyone gets a third."""
+    def items_of(n_long, n_single, G, c):
+        out, r = [], n_long % G
+        nd = G - r
+        m = 0
+        while c + m * G < n_long:
+            out.append(c + m * G); m += 1
+        lim = min(n_single, 2 * nd)
+        for m in range(2):
+            j = (c - r) + m * nd
+            if c >= r and j < lim:
+                out.append(n_long + j)
+        m = 0
+        while 2 * nd + c + m * G < n_single:
+            out.append(n_long + 2 * nd + c + m * G); m += 1
+        return out
+
+    for n_long, n_single, sms in ((1664, 128, 148), (0, 5, 148), (0, 300, 148), (10, 5, 148), (13, 1, 148), (1000, 0, 148), (147, 147, 148),
+                                  (148, 148, 148), (149, 1, 148), (296, 600, 148), (7, 3, 4), (1, 1, 148)):
+        G = min(n_long + n_single, sms)
+        seen = []
+        loads = []
+        for c in range(G):
+            it = items_of(n_long, n_single, G, c)
+            assert it == sorted(it), "two-tile items come first, every list is ascending"
+            seen += it
+            loads.append(sum(1.0 if i < n_long else 0.5 for i in it))
+        assert sorted(seen) == list(range(n_long + n_single)), (n_long, n_single, G)
+        # balance: no CTA carries more than one two-tile item above the least loaded one
+        assert max(loads) - min(loads) <= 1.0 + 1e-9, (n_long, n_single, G, max(loads), min(loads))
+    # the C3 launch: 36 CTAs with 12 two-tile items, 112 with 11 and one or two single-tile ones: makespan 12 two-tile units
+    loads = [sum(1.0 if i < 1664 else 0.5 for i in items_of(1664, 128, 148, c)) for c in range(148)]
+    assert max(loads) == 12.0 and min(loads) == 11.5
