@@ -257,7 +257,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     from models import _native as nat
     from models.stage_configs import STAGE_KWARGS
     from models.tts_model import M2TTSModel
-    from utils.host_pipeline import HostPipeline, wave_chunk_sizes
+    from utils.host_pipeline import HostPipeline
 
     from utils.device import bind_host_to_gpu
 
@@ -327,9 +327,13 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     # (utils.host_pipeline.HostPipeline) chunks the utterance batch so the PCIe copies overlap compute. ----
     if args.e2e_chunks > 0:
         pipe = HostPipeline(dev, n_chunks=args.e2e_chunks, edge=args.e2e_edge)
-    else:      # default: chunk sizes that fill the attention kernel's waves of CTAs (utils.host_pipeline.wave_chunk_sizes)
-        pipe = HostPipeline(dev, sizes=wave_chunk_sizes(BATCH, FRAMES, model.decoder.layers[0].self_attn.num_heads,
-                                                       torch.cuda.get_device_properties(dev).multi_processor_count))
+    else:
+        # default: the pipeline measures a handful of chunk layouts on this step and keeps the fastest (collective at N > 1: what the
+        # copy streams get depends on how many ranks of the host copy at once — utils.host_pipeline.HostPipeline.autotune)
+        pipe = HostPipeline(dev, n_chunks=3)
+        with nat.deferred_status():
+            pipe.autotune(step, x_host, audio_host, FRAMES, model.decoder.layers[0].self_attn.num_heads)
+        nat.check_status(dev, "e2e chunk layout autotune")
     pipe_desc = (f"sizes={pipe.sizes}" if pipe.sizes is not None else f"n_chunks={args.e2e_chunks}, edge={args.e2e_edge}")
     with nat.deferred_status():
         for _ in range(2):
@@ -472,6 +476,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                         "d2h_bytes_per_step": audio_host.numel() * 4, "ms_per_step": e2e_ms / args.steps,
                         "exposed_copy_ms": e2e_ms / args.steps - total_ms / args.steps,
                         "host_binding": host_binding,
+                        "chunk_layout": {"sizes": pipe.sizes, "autotune": pipe.tuned},
                         "api": f"utils.host_pipeline.HostPipeline({pipe_desc}).run(decoder+vocoder, pinned host in, pinned host out)"},
                 "e2e_from_ids": {"value": ids_value, "unit": UNIT, "ms_per_step": ids_ms / args.steps,
                                  "h2d_bytes_per_step": ids_host.numel() * 8 + len_host.numel() * 8 + dur_host.numel() * 4,
@@ -662,7 +667,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="c3", choices=["c3", "c1", "c2", "c5"], help="c3 = headline (BASELINE configs[2]); c1/c2/c5 = secondary lines")
     ap.add_argument("--skip-cpu-baseline", action="store_true", help="profiling runs: omit the CPU leg")
-    ap.add_argument("--e2e-chunks", type=int, default=0, help="utterance chunks of the host-to-host pipeline (1 = no overlap; 0 = wave-filling sizes, utils.host_pipeline.wave_chunk_sizes)")
+    ap.add_argument("--e2e-chunks", type=int, default=0, help="utterance chunks of the host-to-host pipeline (1 = no overlap; 0 = measured: HostPipeline.autotune)")
     ap.add_argument("--e2e-edge", type=float, default=1.0, help="relative size of the first and last chunk (their copies are the unhidden ones)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -30,6 +30,7 @@ class HostPipeline:
         self.n_chunks = n_chunks
         self.edge = edge
         self.sizes = None if sizes is None else [int(v) for v in sizes]
+        self.tuned = None      # filled by autotune(): the candidates it measured and their times
         self.h2d = torch.cuda.Stream(device=self.device)
         self.d2h = torch.cuda.Stream(device=self.device)
         self._in: List[Optional[torch.Tensor]] = []
@@ -104,6 +105,53 @@ class HostPipeline:
     def synchronize(self) -> None:
         self.d2h.synchronize()
 
+    def autotune(self, fn: Callable[[torch.Tensor], torch.Tensor], x_host: torch.Tensor, out_host: torch.Tensor, frames: int, heads: int,
+                 reps: int = 3) -> List[int]:
+        """Measure a handful of chunk layouts (`candidate_layouts`) on the real step and keep the fastest in `self.sizes`. Which
+        layout wins depends on what the copy streams get: a GPU with the PCIe link to itself likes few large chunks with small
+        edges (5 / 27 / 27 / 5 for the C3 batch), eight ranks of one host copying at once (20 GB/s each instead of 55) like more,
+        smaller ones (10 / 16 / 16 / 17 / 5). COLLECTIVE when torch.distributed is initialised: every rank runs the same
+        candidates at the same time and all keep the layout with the best slowest rank. Leaves `out_host` filled with a valid
+        result."""
+        import time
+        import torch.distributed as dist
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        n = int(x_host.shape[0])
+        sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+        in_b = float(x_host[0].numel() * x_host.element_size())
+        out_b = float(out_host[0].numel() * out_host.element_size())
+        # compute per utterance of the whole batch, measured once with the inputs resident (after one warm-up call)
+        x_dev = x_host.to(self.device)
+        fn(x_dev)
+        torch.cuda.synchronize(self.device)
+        t0 = time.perf_counter()
+        fn(x_dev)
+        torch.cuda.synchronize(self.device)
+        utt_ms = (time.perf_counter() - t0) * 1e3 / max(n, 1)
+        del x_dev
+        cands = candidate_layouts(n, frames, heads, sms, utt_ms, in_b, out_b)
+        times = []
+        for sizes in cands:
+            self.sizes = list(sizes)
+            self.run(fn, x_host, out_host)      # (re)allocates the chunk buffers of this layout
+            self.synchronize()
+            if multi:
+                dist.barrier()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                self.run(fn, x_host, out_host)
+                self.synchronize()
+            times.append((time.perf_counter() - t0) / reps)
+        t = torch.tensor(times, dtype=torch.float64, device=self.device)
+        if multi:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        best = int(torch.argmin(t).item())
+        self.sizes = list(cands[best])
+        self.tuned = {"candidates": cands, "ms": [round(float(v) * 1e3, 3) for v in t.tolist()], "utt_ms": round(utt_ms, 4)}
+        self.run(fn, x_host, out_host)
+        self.synchronize()
+        return self.sizes
+
 
 def attention_makespan(k: int, frames: int, heads: int, sms: int = 148) -> float:
     """Time of the decoder's attention launch for a chunk of k utterances, in units of one two-query-tile CTA. The kernel
@@ -120,16 +168,15 @@ def attention_makespan(k: int, frames: int, heads: int, sms: int = 148) -> float
 
 
 def wave_chunk_sizes(n: int, frames: int, heads: int, sms: int = 148) -> List[int]:
-    """Chunk sizes for `HostPipeline(sizes=...)`: a small first and last chunk (their H2D / D2H copy is what nothing overlaps)
-    around two inner ones, every chunk chosen so that the attention launch — a third of the step, one CTA per SM — fills its last
-    wave of CTAs. For 64 utterances of 3446 frames on 148 SMs this gives 5 / 27 / 27 / 5 (tools/e2e_sweep.py: 7.30 ms per host-to-host
-    step against 7.85 for three equal chunks, whose 22-utterance chunk needs 4.5 waves for 4.0 waves of work)."""
+    """Chunk sizes for `HostPipeline(sizes=...)` on a GPU that has the PCIe link to itself: a small first and last chunk (their
+    H2D / D2H copy is what nothing overlaps) around two inner ones, every chunk chosen so that the attention launch — a third of
+    the step, one CTA per SM — fills its last wave of CTAs. For 64 utterances of 3446 frames on 148 SMs this gives 5 / 27 / 27 / 5
+    (tools/e2e_sweep.py: 7.30 ms per host-to-host step against 7.85 for three equal chunks, whose 22-utterance chunk needs 4.5
+    waves for 4.0 waves of work). With several ranks of one host copying at once the copies are slower and more, smaller chunks
+    win: `HostPipeline.autotune` measures."""
     if n < 8:
         return [n]
     per_utt = attention_makespan(1024, frames, heads, sms) / 1024.0      # asymptotic cost of one utterance
-
-    def eff(k: int) -> float:
-        return k * per_utt / attention_makespan(k, frames, heads, sms)
 
     edges = [k for k in range(max(1, n // 16), max(2, n // 6) + 1)]
     best, best_score = [n], -1.0
@@ -148,6 +195,66 @@ def wave_chunk_sizes(n: int, frames: int, heads: int, sms: int = 148) -> List[in
             if score > best_score:
                 best, best_score = [e, a, b, e], score
     return best
+
+
+def predict_ms(sizes: Sequence[int], frames: int, heads: int, sms: int, copy_gbps: float, utt_ms: float, in_bytes: float, out_bytes: float,
+               ramp_ms: float = 0.15, att_share: float = 0.32) -> float:
+    """Model of one `HostPipeline.run`: three queues (H2D copies, compute, D2H copies), chunk i computes when its input has
+    arrived and chunk i-1 is done, and is copied back when it is done and chunk i-1 has been copied. Compute of a chunk =
+    `ramp_ms` + its attention launch in whole waves of CTAs (`attention_makespan`) + the rest in proportion to its size;
+    `utt_ms` = compute per utterance of a large batch, `in_bytes` / `out_bytes` per utterance, `copy_gbps` what one copy stream
+    gets. Against tools/e2e_sweep.py (one GPU, 55-60 GB/s) and tools/e2e_sweep_dist.py (eight ranks at once: 20-22 GB/s each) the
+    model ranks 14 / 18 measured layouts with correlation 0.96 / 0.98 and an RMS error of 0.15 / 0.23 ms."""
+    n = sum(sizes)
+    big = max(n, 8 * sms)
+    t_unit = att_share * utt_ms * big / attention_makespan(big, frames, heads, sms)
+    t_other = (1.0 - att_share) * utt_ms
+    th, td = in_bytes / (copy_gbps * 1e6), out_bytes / (copy_gbps * 1e6)
+    h = c = d = 0.0
+    for k in sizes:
+        h += k * th + 0.02
+        c = max(c, h) + ramp_ms + attention_makespan(k, frames, heads, sms) * t_unit + k * t_other
+        d = max(d, c) + k * td
+    return d
+
+
+def candidate_layouts(n: int, frames: int, heads: int, sms: int, utt_ms: float, in_bytes: float, out_bytes: float) -> List[List[int]]:
+    """A handful of chunk layouts worth measuring: for each assumed copy bandwidth (a link of its own ... eight ranks behind one
+    host) the two layouts `predict_ms` likes best among 3-6 chunks built from sizes that fill the attention kernel's waves."""
+    if n < 8:
+        return [[n]]
+    per_utt = attention_makespan(1024, frames, heads, sms) / 1024.0
+    good = [k for k in range(1, n) if k * per_utt / attention_makespan(k, frames, heads, sms) >= 0.9] or list(range(1, n))
+
+    def nearest(v: float, hi: int) -> int:
+        c = [k for k in good if k <= hi] or [max(1, hi)]
+        return min(c, key=lambda k: abs(k - v))
+
+    layouts = {tuple(wave_chunk_sizes(n, frames, heads, sms)), tuple(hi - lo for lo, hi in HostPipeline.bounds(n, 3)),
+               tuple(hi - lo for lo, hi in HostPipeline.bounds(n, 4))}
+    firsts = sorted({nearest(n / 12.0, n // 3), nearest(n / 6.0, n // 3), nearest(n / 4.0, n // 3)})
+    lasts = sorted({nearest(n / 12.0, n // 4), nearest(n / 6.0, n // 4)})
+    for chunks in (3, 4, 5, 6):
+        for f in firsts:
+            for l in lasts:
+                inner, m = n - f - l, chunks - 2
+                if inner < m:
+                    continue
+                mid, left = [], inner
+                for j in range(m):
+                    k = left if j == m - 1 else nearest(left / (m - j), left - (m - j - 1))
+                    mid.append(k)
+                    left -= k
+                if min(mid) >= 1:
+                    layouts.add(tuple([f] + sorted(mid) + [l]))
+                    layouts.add(tuple([f] + sorted(mid, reverse=True) + [l]))
+    out: List[List[int]] = []
+    for bw in (56.0, 36.0, 24.0, 16.0):
+        ranked = sorted(layouts, key=lambda t: predict_ms(t, frames, heads, sms, bw, utt_ms, in_bytes, out_bytes))
+        for t in ranked[:2]:
+            if list(t) not in out:
+                out.append(list(t))
+    return out
 
 
 def synthesize_to_host(model, ids_host: torch.Tensor, lengths_host: Optional[torch.Tensor], durations_host: Optional[torch.Tensor],

@@ -77,6 +77,35 @@ def test_c3_through_the_real_length_regulator_s256():
         assert H.max_abs(out[k].cpu(), ref[k]) <= FP32_TOL, k
 
 
+def test_host_pipeline_autotune_keeps_a_valid_layout_and_the_result():
+    """HostPipeline.autotune measures its candidate layouts on the real step and keeps the fastest: whatever it picks must be a
+    composition of the batch, and the result left in the output buffer (and of a later run) must equal the direct call."""
+    from models import _native as nat
+    from utils.host_pipeline import HostPipeline
+    m = cuda_model("stage2")
+    x_host = torch.randn(12, 260, 96, generator=torch.Generator().manual_seed(5)).pin_memory()
+    out_host = torch.empty((12, 1, 64 * 260)).pin_memory()
+
+    def step(x):
+        return m.vocoder(m.decoder(x).transpose(1, 2))
+
+    want = step(x_host.to(DEV)).cpu()
+    pipe = HostPipeline(torch.device(DEV), n_chunks=2)
+    out_host.fill_(float("nan"))
+    with nat.deferred_status():
+        sizes = pipe.autotune(step, x_host, out_host, frames=260, heads=2, reps=1)
+    nat.check_status(torch.device(DEV))
+    assert sum(sizes) == 12 and min(sizes) >= 1 and pipe.sizes == sizes
+    assert pipe.tuned is not None and len(pipe.tuned["ms"]) == len(pipe.tuned["candidates"]) and sizes in pipe.tuned["candidates"]
+    assert torch.equal(out_host, want)
+    out_host.fill_(float("nan"))
+    with nat.deferred_status():
+        pipe.run(step, x_host, out_host)
+    pipe.synchronize()
+    nat.check_status(torch.device(DEV))
+    assert torch.equal(out_host, want)
+
+
 # --------------------------------------------------------------------------- host-to-host pipeline (the e2e number)
 @pytest.mark.parametrize("n_chunks", [1, 3, 5])
 def test_host_pipeline_equals_direct_call(n_chunks):

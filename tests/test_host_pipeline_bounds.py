@@ -55,3 +55,22 @@ def test_explicit_sizes_are_used_only_when_they_fit_the_batch():
     assert pipe.chunk_bounds(64)[0] == (0, 5) and pipe.chunk_bounds(64)[-1] == (59, 64)
     assert [hi - lo for lo, hi in pipe.chunk_bounds(10)] == [4, 3, 3]
     del torch
+
+
+def test_candidate_layouts_and_the_pipeline_model():
+    """`candidate_layouts`: every candidate is a positive composition of the batch; `predict_ms` reproduces the two measured
+    regimes (tools/e2e_sweep.py on one GPU, tools/e2e_sweep_dist.py with eight ranks of one host copying at once)."""
+    from utils.host_pipeline import candidate_layouts, predict_ms
+    for n, frames, heads in ((64, 3446, 2), (16, 314, 2), (9, 300, 2), (512, 3446, 2), (3, 100, 2), (65, 2048, 4)):
+        cands = candidate_layouts(n, frames, heads, 148, 0.1, 1.3e6, 0.88e6)
+        assert 1 <= len(cands) <= 8
+        for c in cands:
+            assert sum(c) == n and min(c) >= 1, (n, c)
+    kw = dict(frames=3446, heads=2, sms=148, utt_ms=0.102, in_bytes=1.3233e6, out_bytes=0.8822e6)
+    alone = {t: predict_ms(t, copy_gbps=56.0, **kw) for t in ((5, 27, 27, 5), (22, 21, 21), (10, 16, 16, 17, 5), (5, 54, 5), (64,))}
+    assert alone[(5, 27, 27, 5)] == min(alone.values())                       # measured: 7.30 against 7.85 / 7.67 / 8.04 / 8.93 ms
+    assert alone[(64,)] == max(alone.values())
+    shared = {t: predict_ms(t, copy_gbps=21.0, **kw) for t in ((5, 27, 27, 5), (22, 21, 21), (10, 16, 16, 17, 5), (10, 54))}
+    assert shared[(10, 16, 16, 17, 5)] == min(shared.values())                # measured at 8 GPUs: 8.51 against 9.39 / 9.20 / 11.94 ms
+    assert shared[(10, 54)] == max(shared.values())
+    assert [5, 27, 27, 5] in candidate_layouts(64, 3446, 2, 148, 0.102, 1.3233e6, 0.8822e6)
