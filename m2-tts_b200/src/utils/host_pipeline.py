@@ -106,7 +106,7 @@ class HostPipeline:
         self.d2h.synchronize()
 
     def autotune(self, fn: Callable[[torch.Tensor], torch.Tensor], x_host: torch.Tensor, out_host: torch.Tensor, frames: int, heads: int,
-                 reps: int = 3) -> List[int]:
+                 reps: int = 4) -> List[int]:
         """Measure a handful of chunk layouts (`candidate_layouts`) on the real step and keep the fastest in `self.sizes`. Which
         layout wins depends on what the copy streams get: a GPU with the PCIe link to itself likes few large chunks with small
         edges (5 / 27 / 27 / 5 for the C3 batch), eight ranks of one host copying at once (20 GB/s each instead of 55) like more,
@@ -137,6 +137,11 @@ class HostPipeline:
             self.synchronize()
             if multi:
                 dist.barrier()
+            # ranks in lock-step all copy at the same instant, which a free-running service does not: two untimed runs let them
+            # drift apart before the timed ones (measured at 8 GPUs: 5 / 27 / 27 / 5 takes 9.9 ms in lock-step, 8.2 free-running)
+            for _ in range(2 if multi else 0):
+                self.run(fn, x_host, out_host)
+                self.synchronize()
             t0 = time.perf_counter()
             for _ in range(reps):
                 self.run(fn, x_host, out_host)
