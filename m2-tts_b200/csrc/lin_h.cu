@@ -273,6 +273,7 @@ lin_h_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     const uint32_t swz = (uint32_t)((row >> 1) & 3);
     const bool leader = warp == 2 && lane == 0;
     bool bad = false;               // an fp16-plane output left the fp16 range
+    float amax = 0.f;               // running maximum of |x| of the packed-pair splits (NaN-propagating): one range check at the end
     int unit = 0;
     for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x) {
       const long long r = (long long)mt * LH_BM + row;
@@ -353,11 +354,12 @@ lin_h_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
               const float4 bv = bp[j4];
               const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
+              for (int e = 0; e < 4; e += 2) {      // packed pairs (FADD2): accumulator halves + bias
                 const int j = 4 * j4 + e;
-                float t = __uint_as_float(v[j]) + __uint_as_float(w[j]) + bb[e];
-                if (a.relu) t = fmaxf(t, 0.f);
-                x[j] = t;
+                float t0, t1;
+                f2_unpack(f2_add(f2_add(f2_pack_u(v[j], v[j + 1]), f2_pack_u(w[j], w[j + 1])), f2_pack(bb[e], bb[e + 1])), t0, t1);
+                if (a.relu) { t0 = fmaxf(t0, 0.f); t1 = fmaxf(t1, 0.f); }
+                x[j] = t0; x[j + 1] = t1;
               }
             }
           }
@@ -375,7 +377,7 @@ lin_h_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
           } else if (a.mode == 1) {
             uint32_t hi[8], lo[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) h_split2(x[2 * j], x[2 * j + 1], hi[j], lo[j], bad);
+            for (int j = 0; j < 8; ++j) h_split_pair(f2_pack(x[2 * j], x[2 * j + 1]), hi[j], lo[j], amax);
             if (tma_out) {
               uint8_t* bh = stg + (uint32_t)(c0 >> 5) * 8192u + (uint32_t)row * 64u;
               uint8_t* bl = bh + (uint32_t)(a.np >> 5) * 8192u;
@@ -405,13 +407,12 @@ lin_h_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
               __half* sp = reinterpret_cast<__half*>(stg) + (uint32_t)c0 * 128u + (uint32_t)row;
               // packed conversions (F2FP / HADD2.F32 run at full rate; the scalar cvt goes through the quarter-rate XU pipe and
               // made this epilogue XU-bound)
+              const uint64_t sc2 = f2_pack(sc, sc);
 #pragma unroll
               for (int j = 0; j < 16; j += 2) {
-                const float t0 = x[j] * sc, t1 = x[j + 1] * sc;
-                h_chk(t0, bad); h_chk(t1, bad);
-                const __half2 h = __floats2half2_rn(t0, t1);
-                const float2 hf = __half22float2(h);
-                const __half2 lo = __floats2half2_rn(t0 - hf.x, t1 - hf.y);
+                uint32_t hw, lw;
+                h_split_pair(f2_mul(f2_pack(x[j], x[j + 1]), sc2), hw, lw, amax);
+                const __half2 h = *reinterpret_cast<const __half2*>(&hw), lo = *reinterpret_cast<const __half2*>(&lw);
                 sp[j * 128] = __low2half(h);
                 sp[(j + 1) * 128] = __high2half(h);
                 sp[j * 128 + a.np * 128] = __low2half(lo);
@@ -469,7 +470,7 @@ lin_h_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
       }
     }
     if (tma_out && leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-    h_flag(bad, a.status);
+    h_flag(bad || h_amax_bad(amax), a.status);
   }
   tc_fence_before();
   __syncthreads();
