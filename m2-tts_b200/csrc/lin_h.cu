@@ -40,6 +40,8 @@ struct LinHArgs {
   int mode;
   int stg2;                        // 1: two staging tiles (units alternate), when shared memory allows
   int res_tma;                     // mode 0 with staging: the residual tile is TMA-loaded into the staging tile and updated in place
+  int tpose;                       // mode 3 with staging: TRANSPOSED product (weights = A, positions = N): a thread is an output channel and holds 16
+                                   // consecutive positions per chunk, so the attention operand planes leave as 16-byte row pieces (see the epilogue)
   int tpu;                         // mode 3 with staging: 128-row tiles per utterance (tiles do not straddle utterances); else 0
   int stg_bytes;                   // > 0: the epilogue stages the output tile in shared memory and writes it with TMA stores (modes 0, 1)
   long long* prof;                 // bring-up: phase timestamps of CTA 0's first epilogue warp (m2tts_attention_set_prof buffer)
@@ -144,6 +146,7 @@ lin_h_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     mbar_wait(bar_w, 0);
     const uint32_t idesc2 = (1u << 4) | ((uint32_t)((2 * a.np) >> 3) << 17) | ((uint32_t)(LH_BM >> 4) << 24);   // fp16 x fp16 -> fp32, K-major
     const uint32_t idesc1 = (1u << 4) | ((uint32_t)(a.np >> 3) << 17) | ((uint32_t)(LH_BM >> 4) << 24);
+    const uint32_t idescT = (1u << 4) | ((uint32_t)(LH_BM >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);      // transposed: M = 128 channels, N = 128 positions
     const int ksteps = a.K / 16;
     int it = 0, unit = 0;
     for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x, ++it) {
@@ -158,7 +161,17 @@ lin_h_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         const uint32_t d = tmem_base + (uint32_t)buf * 256u;
         for (int ks = 0; ks < ksteps && !(a.dbg & 2); ++ks) {
           const uint32_t koff = (uint32_t)(ks >> 1) * a_box + (uint32_t)(ks & 1) * 32u;
-          const uint64_t bd = lh_desc(sW + (uint32_t)(((ks >> 1) * a.n_passes + p) * 2) * w_box + (uint32_t)(ks & 1) * 32u);
+          const uint32_t wb = sW + (uint32_t)(((ks >> 1) * a.n_passes + p) * 2) * w_box + (uint32_t)(ks & 1) * 32u;
+          if (a.tpose) {
+            // D[channel, position]: the pass's weight rows are the A operand (M = 128: the 96 rows of the pass and 32 rows of whatever
+            // follows them in shared memory — lanes nobody reads), the activation tile is the B operand (N = 128 positions); the three
+            // product terms accumulate into the same 128 columns
+            lh_mma_w(d, lh_desc(wb), lh_desc(aHi + koff), idescT, ks ? 1u : 0u);      // W_hi x X_hi
+            lh_mma_w(d, lh_desc(wb), lh_desc(aLo + koff), idescT, 1u);                // W_hi x X_lo
+            lh_mma_w(d, lh_desc(wb + w_box), lh_desc(aHi + koff), idescT, 1u);        // W_lo x X_hi
+            continue;
+          }
+          const uint64_t bd = lh_desc(wb);
           lh_mma_w(d, lh_desc(aHi + koff), bd, idesc2, ks ? 1u : 0u);     // A_hi x [W_hi ; W_lo]
           lh_mma_w(d, lh_desc(aLo + koff), bd, idesc1, 1u);               // A_lo x W_hi
         }
@@ -321,7 +334,39 @@ lin_h_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         if (pt) a.prof[unit * 8 + 2] = clock64();
         const uint32_t tb = t_lane + (uint32_t)buf * 256u;
         bool released = false;
-        for (int c0 = eg * 16; c0 < a.np; c0 += 16 * LH_G) {
+        if (a.tpose) {
+          // thread = output channel `row` of pass p (q, k or v), TMEM columns = the tile's 128 positions; a chunk = 16 positions =
+          // 32 bytes of a plane row. Staging: per (plane, head, 64-position half) a box of hd rows x 128 B in the 128-byte swizzle of
+          // the TMA store (the attention kernel's own load box): the 8 lanes of a quarter-warp hit 8 different 16-byte columns. With
+          // positions in the lanes this epilogue issued 64 two-byte stores per chunk and thread; now four 16-byte ones.
+          const bool act = row < a.np;                   // lanes 96..127 of the accumulator belong to nobody (warp-uniform)
+          const int head = act ? row / a.hd : 0, dd = act ? row - head * a.hd : 0;
+          const float sc = (p == 0) ? a.qscale : 1.0f;
+          const uint64_t sc2 = f2_pack(sc, sc);
+          const uint32_t boxb = (uint32_t)a.hd * 128u;
+          for (int k = eg; k < LH_BM / 16; k += LH_G) {
+            uint32_t v[16];
+            if (act) { tmem_ld16(tb + 16 * k, v); tmem_wait_ld(); }
+            if (k + LH_G >= LH_BM / 16) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_ce + 8 * buf) : "memory");
+              released = true;
+            }
+            if (!act || (a.dbg & 1)) continue;
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) h_split_pair(f2_mul(f2_pack_u(v[2 * j], v[2 * j + 1]), sc2), hi[j], lo[j], amax);
+            uint8_t* bh = stg + (uint32_t)(head * 2 + (k >> 2)) * boxb + (uint32_t)dd * 128u;
+            uint8_t* bl = bh + (uint32_t)(a.nh * 2) * boxb;
+            const uint32_t c16 = (uint32_t)(k & 3) * 2u, sw = (uint32_t)dd & 7u;
+            *reinterpret_cast<uint4*>(bh + ((c16 ^ sw) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(bh + (((c16 + 1u) ^ sw) << 4)) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+            *reinterpret_cast<uint4*>(bl + ((c16 ^ sw) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            *reinterpret_cast<uint4*>(bl + (((c16 + 1u) ^ sw) << 4)) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+          }
+        }
+        for (int c0 = eg * 16; c0 < a.np && !a.tpose; c0 += 16 * LH_G) {
           uint32_t v[16], w[16];
           float4 rs[4];
           if (a.res_tma) {
@@ -445,7 +490,16 @@ lin_h_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
           asm volatile("bar.sync 2, %0;" ::"n"(128 * LH_G) : "memory");
           if (leader && !(a.dbg & 1)) {
             const int r0 = mt * LH_BM;
-            if (a.mode == 3) {      // pass p = q, k or v: one box of 128 positions x hd rows per (plane, head)
+            if (a.mode == 3 && a.tpose) {      // pass p = q, k or v: one box of 64 positions x hd rows per (plane, head, half)
+              const int nbat = a.R / a.L, l0 = (mt % a.tpu) * LH_BM;
+              for (int pl = 0; pl < 2; ++pl)
+                for (int hh = 0; hh < a.nh; ++hh)
+                  for (int hf = 0; hf < 2; ++hf)
+                    if (l0 + 64 * hf < a.L)
+                      asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                                   ::"l"(&tmap_y), "r"(l0 + 64 * hf), "r"((((2 * p + pl) * nbat + b) * a.nh + hh) * a.hd),
+                                     "r"(sStgU + (uint32_t)(((pl * a.nh + hh) * 2 + hf) * a.hd * 128)) : "memory");
+            } else if (a.mode == 3) {      // pass p = q, k or v: one box of 128 positions x hd rows per (plane, head)
               const int nbat = a.R / a.L, l0 = (mt % a.tpu) * LH_BM;
               for (int pl = 0; pl < 2; ++pl)
                 for (int hh = 0; hh < a.nh; ++hh)
@@ -640,6 +694,11 @@ int launch_linear_h(const void* a_planes, const void* w_planes, const LinHParams
   }
   a.a_stages = st > 4 ? 4 : st;
   a.tpu = (q.mode == 3 && a.stg_bytes != 0) ? ceil_div(q.L, LH_BM) : 0;
+  {
+    static int use_t = -1;
+    if (use_t < 0) use_t = tools_env_int("M2TTS_LIN_TPOSE", 1);
+    a.tpose = (a.tpu > 0 && use_t != 0 && a.np <= 128 && (q.hd & 7) == 0 && q.bias == nullptr && !q.relu) ? 1 : 0;      // the QKV projection has no bias (components.py:51)
+  }
   M2_REQUIRE(a.a_stages >= 1, M2TTS_E_UNSUPPORTED, "linear_h: operands do not fit shared memory");
   const size_t smem = fixed + (size_t)a.a_stages * a_stage;
   CUtensorMap ta, tw;
@@ -693,9 +752,10 @@ int launch_linear_h(const void* a_planes, const void* w_planes, const LinHParams
   } else if (a.stg_bytes != 0 && q.mode == 3) {      // operand planes as {positions (clipped at L), all d-rows}
     const cuuint64_t dims[2] = {(cuuint64_t)q.L, (cuuint64_t)6 * (a.R / q.L) * q.nh * q.hd};
     const cuuint64_t strides[1] = {(cuuint64_t)q.Lp * 2};
-    const cuuint32_t box[2] = {(cuuint32_t)LH_BM, (cuuint32_t)q.hd};
+    const cuuint32_t box[2] = {a.tpose ? 64u : (cuuint32_t)LH_BM, (cuuint32_t)q.hd};
     const CUresult r = enc(&ty, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, q.qkvh, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                           a.tpose ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     M2_REQUIRE(r == CUDA_SUCCESS, M2TTS_E_CUDA, "linear_h: tensor map (attention planes) failed (%d)", (int)r);
   } else if (a.stg_bytes != 0) {
     const cuuint64_t dims[3] = {(cuuint64_t)a.N, (cuuint64_t)a.R, 2};
