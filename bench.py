@@ -361,9 +361,19 @@ def run_b200(args, rank: int, world: int, local_rank: int):
 
     from utils.host_pipeline import synthesize_to_host
 
+    # the ids path copies only waveforms: its own pipeline, its own chunk layout (tuned on a resident input of the regulated shape)
+    if args.e2e_chunks > 0:
+        pipe_ids = pipe
+    else:
+        pipe_ids = HostPipeline(dev, n_chunks=3)
+        with nat.deferred_status():
+            pipe_ids.autotune(step, x_dev, audio_host, FRAMES, model.decoder.layers[0].self_attn.num_heads)
+        nat.check_status(dev, "e2e-from-ids chunk layout autotune")
+    ids_desc = (f"sizes={pipe_ids.sizes}" if pipe_ids.sizes is not None else pipe_desc)
+
     def ids_step():
-        synthesize_to_host(model, ids_host, len_host, dur_host, FRAMES, audio_host, pipe)
-        pipe.d2h.synchronize()
+        synthesize_to_host(model, ids_host, len_host, dur_host, FRAMES, audio_host, pipe_ids)
+        pipe_ids.d2h.synchronize()
 
     with nat.deferred_status():
         for _ in range(2):
@@ -481,7 +491,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                 "e2e_from_ids": {"value": ids_value, "unit": UNIT, "ms_per_step": ids_ms / args.steps,
                                  "h2d_bytes_per_step": ids_host.numel() * 8 + len_host.numel() * 8 + dur_host.numel() * 4,
                                  "d2h_bytes_per_step": audio_host.numel() * 4,
-                                 "api": f"utils.host_pipeline.synthesize_to_host(model, ids[{BATCH},{S}], lengths, target_durations, max_target_length={FRAMES}): acoustic front once, decoder + vocoder in utterance chunks ({pipe_desc}), pinned host ids in, pinned host waveform out"},
+                                 "api": f"utils.host_pipeline.synthesize_to_host(model, ids[{BATCH},{S}], lengths, target_durations, max_target_length={FRAMES}): acoustic front once, decoder + vocoder in utterance chunks ({ids_desc}), pinned host ids in, pinned host waveform out"},
                 "parity": parity,
                 "roofline": roof, "stage_roofline": stage_roofline, "stage_tflops": all_stage_tflops,
                 "stage_ms_per_step": {k: round(v[0] / prof_steps, 4) for k, v in sorted(stage_ms.items(), key=lambda kv: -kv[1][0])},

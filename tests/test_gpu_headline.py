@@ -152,6 +152,14 @@ def test_host_pipeline_with_explicit_chunk_sizes_equals_direct_call():
         pipe.synchronize()
         nat.check_status(torch.device(DEV))
         assert torch.equal(out_host, want), sizes
+    # an input that is already on the device (the ids path of synthesize_to_host): chunked views, only the results are copied
+    pipe = HostPipeline(torch.device(DEV), sizes=[2, 4, 3])
+    out_host.fill_(float("nan"))
+    with nat.deferred_status():
+        pipe.run(step, x_host.to(DEV), out_host)
+    pipe.synchronize()
+    nat.check_status(torch.device(DEV))
+    assert torch.equal(out_host, want)
 
 
 # --------------------------------------------------------------------------- status word
