@@ -113,54 +113,63 @@ class HostPipeline:
     def synchronize(self) -> None:
         self.d2h.synchronize()
 
-    def autotune(self, fn: Callable[[torch.Tensor], torch.Tensor], x_host: torch.Tensor, out_host: torch.Tensor, frames: int, heads: int,
-                 reps: int = 3) -> List[int]:
-        """Measure a handful of chunk layouts (`candidate_layouts`) on the real step and keep the fastest in `self.sizes`. Which
-        layout wins depends on what the copy streams get: a GPU with the PCIe link to itself likes few large chunks with small
-        edges (5 / 27 / 27 / 5 for the C3 batch), eight ranks of one host copying at once (20 GB/s each instead of 55) like more,
-        smaller ones (10 / 16 / 16 / 17 / 5). COLLECTIVE when torch.distributed is initialised: every rank runs the same
-        candidates at the same time and all keep the layout with the best slowest rank. Leaves `out_host` filled with a valid
-        result."""
+    AUTOTUNE_SLOTS = 8      # fixed length of the vector the ranks agree on: the number of collectives never depends on the candidates
+
+    def _sm_count(self) -> int:
+        return torch.cuda.get_device_properties(self.device).multi_processor_count
+
+    def _utterance_ms(self, fn: Callable[[torch.Tensor], torch.Tensor], x_host: torch.Tensor) -> float:
+        """Compute time per utterance of the whole batch with the input resident (after one warm-up call)."""
         import time
-        import torch.distributed as dist
-        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
-        n = int(x_host.shape[0])
-        sms = torch.cuda.get_device_properties(self.device).multi_processor_count
-        in_b = 0.0 if x_host.is_cuda else float(x_host[0].numel() * x_host.element_size())      # a resident input is not copied
-        out_b = float(out_host[0].numel() * out_host.element_size())
-        # compute per utterance of the whole batch, measured once with the inputs resident (after one warm-up call)
         x_dev = x_host.to(self.device)
         fn(x_dev)
         torch.cuda.synchronize(self.device)
         t0 = time.perf_counter()
         fn(x_dev)
         torch.cuda.synchronize(self.device)
-        utt_ms = (time.perf_counter() - t0) * 1e3 / max(n, 1)
-        del x_dev
-        cands = candidate_layouts(n, frames, heads, sms, utt_ms, in_b, out_b)
-        times = [float("inf")] * len(cands)
+        return (time.perf_counter() - t0) * 1e3 / max(int(x_host.shape[0]), 1)
+
+    def _agree_max(self, values: List[float]) -> List[float]:
+        """Element-wise maximum over the ranks (one all-reduce of a fixed-length vector); the identity without torch.distributed."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            return list(values)
+        t = torch.tensor(values, dtype=torch.float64, device=self.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t.tolist()]
+
+    def autotune(self, fn: Callable[[torch.Tensor], torch.Tensor], x_host: torch.Tensor, out_host: torch.Tensor, frames: int, heads: int,
+                 reps: int = 3) -> List[int]:
+        """Measure a handful of chunk layouts (`candidate_layouts`) on the real step and keep the fastest in `self.sizes`. Which
+        layout wins depends on what the copy streams get: a GPU with the PCIe link to itself likes few large chunks with small
+        edges (5 / 27 / 27 / 5 for the C3 batch), eight ranks of one host copying at once (20 GB/s each instead of 55) like more,
+        smaller ones (5 / 10 / 14 / 15 / 15 / 5). COLLECTIVE when torch.distributed is initialised — every rank must call it —
+        with EXACTLY TWO all-reduces whatever the candidates are: the first makes every rank build the same candidate list (the
+        list depends on the measured compute time per utterance, which differs from rank to rank: the maximum is used), the second
+        takes, per candidate, the time of the slowest rank; in between the ranks run the same candidates free-running (no barrier
+        per candidate: ranks in lock-step all copy at the same instant, which a service does not — at 8 GPUs 5 / 27 / 27 / 5 takes
+        9.9 ms in lock-step and 8.2 free-running). Leaves `out_host` filled with a valid result."""
+        import time
+        n = int(x_host.shape[0])
+        sms = self._sm_count()
+        in_b = 0.0 if x_host.is_cuda else float(x_host[0].numel() * x_host.element_size())      # a resident input is not copied
+        out_b = float(out_host[0].numel() * out_host.element_size())
+        utt_ms = self._agree_max([self._utterance_ms(fn, x_host)])[0]                            # collective 1 of 2
+        cands = candidate_layouts(n, frames, heads, sms, utt_ms, in_b, out_b)[:self.AUTOTUNE_SLOTS]
+        times = [float("inf")] * self.AUTOTUNE_SLOTS
         for ci, sizes in [(i, c) for _ in range(2) for i, c in enumerate(cands)]:      # two interleaved rounds, the better one counts
             self.sizes = list(sizes)
             self.run(fn, x_host, out_host)      # (re)allocates the chunk buffers of this layout
             self.synchronize()
-            if multi:
-                dist.barrier()
-            # ranks in lock-step all copy at the same instant, which a free-running service does not: two untimed runs let them
-            # drift apart before the timed ones (measured at 8 GPUs: 5 / 27 / 27 / 5 takes 9.9 ms in lock-step, 8.2 free-running)
-            for _ in range(2 if multi else 0):
-                self.run(fn, x_host, out_host)
-                self.synchronize()
             t0 = time.perf_counter()
             for _ in range(reps):
                 self.run(fn, x_host, out_host)
                 self.synchronize()
             times[ci] = min(times[ci], (time.perf_counter() - t0) / reps)
-        t = torch.tensor(times, dtype=torch.float64, device=self.device)
-        if multi:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        best = int(torch.argmin(t).item())
+        agreed = self._agree_max([v if v != float("inf") else 1e30 for v in times])              # collective 2 of 2
+        best = min(range(len(cands)), key=lambda i: agreed[i])
         self.sizes = list(cands[best])
-        self.tuned = {"candidates": cands, "ms": [round(float(v) * 1e3, 3) for v in t.tolist()], "utt_ms": round(utt_ms, 4)}
+        self.tuned = {"candidates": cands, "ms": [round(agreed[i] * 1e3, 3) for i in range(len(cands))], "utt_ms": round(utt_ms, 4)}
         self.run(fn, x_host, out_host)
         self.synchronize()
         return self.sizes
