@@ -328,8 +328,9 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     if args.e2e_chunks > 0:
         pipe = HostPipeline(dev, n_chunks=args.e2e_chunks, edge=args.e2e_edge)
     else:
-        # default: the pipeline measures a handful of chunk layouts on this step and keeps the fastest (collective at N > 1: what the
-        # copy streams get depends on how many ranks of the host copy at once — utils.host_pipeline.HostPipeline.autotune)
+        # default: the pipeline measures a handful of chunk layouts on this step and keeps the fastest (what the copy streams get
+        # depends on how many ranks of the host copy at once; every rank tunes on its own, at the same point of the program: no
+        # collective — utils.host_pipeline.HostPipeline.autotune)
         pipe = HostPipeline(dev, n_chunks=3)
         with nat.deferred_status():
             pipe.autotune(step, x_host, audio_host, FRAMES, model.decoder.layers[0].self_attn.num_heads)

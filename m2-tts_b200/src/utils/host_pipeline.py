@@ -129,32 +129,36 @@ class HostPipeline:
         torch.cuda.synchronize(self.device)
         return (time.perf_counter() - t0) * 1e3 / max(int(x_host.shape[0]), 1)
 
-    def _agree_max(self, values: List[float]) -> List[float]:
-        """Element-wise maximum over the ranks (one all-reduce of a fixed-length vector); the identity without torch.distributed."""
+    def _agree_max(self, values: List[float], collective: bool = True) -> List[float]:
+        """Element-wise maximum over the ranks (one all-reduce of a fixed-length vector); the identity without torch.distributed
+        or when the caller tunes every rank on its own."""
         import torch.distributed as dist
-        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        if not (collective and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
             return list(values)
         t = torch.tensor(values, dtype=torch.float64, device=self.device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return [float(v) for v in t.tolist()]
 
     def autotune(self, fn: Callable[[torch.Tensor], torch.Tensor], x_host: torch.Tensor, out_host: torch.Tensor, frames: int, heads: int,
-                 reps: int = 3) -> List[int]:
+                 reps: int = 3, collective: bool = False) -> List[int]:
         """Measure a handful of chunk layouts (`candidate_layouts`) on the real step and keep the fastest in `self.sizes`. Which
         layout wins depends on what the copy streams get: a GPU with the PCIe link to itself likes few large chunks with small
         edges (5 / 27 / 27 / 5 for the C3 batch), eight ranks of one host copying at once (20 GB/s each instead of 55) like more,
-        smaller ones (5 / 10 / 14 / 15 / 15 / 5). COLLECTIVE when torch.distributed is initialised — every rank must call it —
+        smaller ones (5 / 10 / 14 / 15 / 15 / 5). By default every rank tunes ON ITS OWN — no collective at all: the path has no
+        data-path collective either, ranks that call this at the same point of their program measure each other's copy traffic
+        anyway, and nothing can dead-lock. `collective=True` (every rank must then call it) makes all ranks keep the SAME layout
         with EXACTLY TWO all-reduces whatever the candidates are: the first makes every rank build the same candidate list (the
         list depends on the measured compute time per utterance, which differs from rank to rank: the maximum is used), the second
-        takes, per candidate, the time of the slowest rank; in between the ranks run the same candidates free-running (no barrier
-        per candidate: ranks in lock-step all copy at the same instant, which a service does not — at 8 GPUs 5 / 27 / 27 / 5 takes
-        9.9 ms in lock-step and 8.2 free-running). Leaves `out_host` filled with a valid result."""
+        takes, per candidate, the time of the slowest rank. Either way the ranks run their candidates free-running (a barrier per
+        candidate puts the ranks in lock-step, where all copy at the same instant, which a service does not — at 8 GPUs
+        5 / 27 / 27 / 5 takes 9.9 ms in lock-step and 8.2 free-running — and ranks whose candidate lists differed in length
+        dead-locked an 8-GPU run of the first version). Leaves `out_host` filled with a valid result."""
         import time
         n = int(x_host.shape[0])
         sms = self._sm_count()
         in_b = 0.0 if x_host.is_cuda else float(x_host[0].numel() * x_host.element_size())      # a resident input is not copied
         out_b = float(out_host[0].numel() * out_host.element_size())
-        utt_ms = self._agree_max([self._utterance_ms(fn, x_host)])[0]                            # collective 1 of 2
+        utt_ms = self._agree_max([self._utterance_ms(fn, x_host)], collective)[0]                # collective 1 of 2
         cands = candidate_layouts(n, frames, heads, sms, utt_ms, in_b, out_b)[:self.AUTOTUNE_SLOTS]
         times = [float("inf")] * self.AUTOTUNE_SLOTS
         for ci, sizes in [(i, c) for _ in range(2) for i, c in enumerate(cands)]:      # two interleaved rounds, the better one counts
@@ -166,7 +170,7 @@ class HostPipeline:
                 self.run(fn, x_host, out_host)
                 self.synchronize()
             times[ci] = min(times[ci], (time.perf_counter() - t0) / reps)
-        agreed = self._agree_max([v if v != float("inf") else 1e30 for v in times])              # collective 2 of 2
+        agreed = self._agree_max([v if v != float("inf") else 1e30 for v in times], collective)  # collective 2 of 2
         best = min(range(len(cands)), key=lambda i: agreed[i])
         self.sizes = list(cands[best])
         self.tuned = {"candidates": cands, "ms": [round(agreed[i] * 1e3, 3) for i in range(len(cands))], "utt_ms": round(utt_ms, 4)}

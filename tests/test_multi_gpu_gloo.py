@@ -80,14 +80,14 @@ def _autotune_worker(rank, world, port, ret):
         x = torch.zeros(64, 4, 4)
         out = torch.zeros(64, 1, 16)
         # a "resident" input is modelled by in_bytes = 0: use the is_cuda switch through a tensor subclass-free trick — call the pieces
-        sizes = pipe.autotune(lambda t: t, x, out, frames=3446, heads=2, reps=1)
+        sizes = pipe.autotune(lambda t: t, x, out, frames=3446, heads=2, reps=1, collective=True)
         ret[rank] = (differ, sizes, pipe.tuned["candidates"], len(pipe.tuned["ms"]), pipe.runs)
     finally:
         dist.destroy_process_group()
 
 
 def test_host_pipeline_autotune_protocol_world2_cannot_deadlock():
-    """HostPipeline.autotune under torch.distributed: exactly two all-reduces whatever the candidates are, every rank ends with
+    """HostPipeline.autotune(collective=True) under torch.distributed: exactly two all-reduces whatever the candidates are, every rank ends with
     the same candidate list and the same layout although the ranks 'measure' different compute times (run under gloo with the
     CUDA pieces replaced: the protocol is what is tested)."""
     world = 2
