@@ -679,7 +679,13 @@ int launch_linear_h(const void* a_planes, const void* w_planes, const LinHParams
   const bool stage3 = q.mode == 3 && a.np == q.nh * q.hd && q.L > 0 && q.R % q.L == 0 && q.plane_stride == (long long)(q.R / q.L) * q.nh * q.hd * q.Lp &&
                       (q.Lp & 7) == 0 && (((uintptr_t)q.qkvh) & 15) == 0;
   a.stg_bytes = (q.mode == 0 && (q.ldy & 3) == 0 && (((uintptr_t)q.y) & 15) == 0) || (q.mode == 1 && a.np % 32 == 0) || stage3 ? a.np * 512 : 0;
-  size_t fixed = w_bytes + (size_t)a.stg_bytes + (size_t)a.N * 4 + 16 + 768 + 256 + 1024;      // + bias, LayerNorm parameters, barriers, alignment
+  // transposed QKV product (see the issuer): its A operand is 128 weight rows starting at a pass's first row, i.e. up to 128 - np rows
+  // past the pass — for the last pass past the weight images. 8 KB of slack at the end of the allocation keep those reads (of lanes
+  // nobody uses) inside this CTA's shared-memory window.
+  static int use_t = -1;
+  if (use_t < 0) use_t = tools_env_int("M2TTS_LIN_TPOSE", 1);
+  const bool want_t = stage3 && use_t != 0 && a.np <= 128 && (q.hd & 7) == 0 && q.bias == nullptr && !q.relu;      // the QKV projection has no bias (components.py:51)
+  size_t fixed = w_bytes + (size_t)a.stg_bytes + (size_t)a.N * 4 + 16 + 768 + 256 + 1024 + (want_t ? 8192 : 0);      // + bias, LayerNorm parameters, barriers, alignment
   int st = (int)((225 * 1024 - fixed) / a_stage);
   if (st < 1 && a.stg_bytes != 0) {      // no room for the staging tile: the epilogue stores directly
     fixed -= (size_t)a.stg_bytes;
@@ -694,11 +700,7 @@ int launch_linear_h(const void* a_planes, const void* w_planes, const LinHParams
   }
   a.a_stages = st > 4 ? 4 : st;
   a.tpu = (q.mode == 3 && a.stg_bytes != 0) ? ceil_div(q.L, LH_BM) : 0;
-  {
-    static int use_t = -1;
-    if (use_t < 0) use_t = tools_env_int("M2TTS_LIN_TPOSE", 1);
-    a.tpose = (a.tpu > 0 && use_t != 0 && a.np <= 128 && (q.hd & 7) == 0 && q.bias == nullptr && !q.relu) ? 1 : 0;      // the QKV projection has no bias (components.py:51)
-  }
+  a.tpose = (a.tpu > 0 && want_t) ? 1 : 0;
   M2_REQUIRE(a.a_stages >= 1, M2TTS_E_UNSUPPORTED, "linear_h: operands do not fit shared memory");
   const size_t smem = fixed + (size_t)a.a_stages * a_stage;
   CUtensorMap ta, tw;
